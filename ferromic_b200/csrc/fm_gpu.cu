@@ -1,0 +1,1370 @@
+// fm_gpu.cu -- C-ABI implementation (include/ferromic_gpu.h): handle management, the host-side
+// guard/dispatch logic of the reference's public stats.rs functions, kernel launches and the
+// deterministic final reductions.  No CPU fallback: every compute entry point needs a device.
+#include "../../include/ferromic_gpu.h"
+#include "fm_kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string t_err;
+thread_local int t_device = 0;
+thread_local fm_timings t_tim = {};
+std::atomic<uint64_t> g_launches{0};
+
+struct FmError {
+    fm_status code;
+    std::string msg;
+};
+
+[[noreturn]] void fail(fm_status code, const std::string &msg) { throw FmError{code, msg}; }
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            char buf_[512];                                                                   \
+            snprintf(buf_, sizeof(buf_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                     __FILE__, __LINE__);                                                     \
+            cudaError_t last_ = cudaGetLastError();                                           \
+            (void)last_;                                                                      \
+            fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? FM_ERR_NO_DEVICE \
+                                                                               : FM_ERR_CUDA, \
+                 buf_);                                                                       \
+        }                                                                                     \
+    } while (0)
+
+template <class F>
+fm_status guarded(F &&f) {
+    try {
+        f();
+        return FM_OK;
+    } catch (const FmError &e) {
+        t_err = e.msg;
+        return e.code;
+    } catch (const std::bad_alloc &) {
+        t_err = "out of host memory";
+        return FM_ERR_INVALID_ARG;
+    } catch (const std::exception &e) {
+        t_err = e.what();
+        return FM_ERR_INVALID_ARG;
+    } catch (...) {
+        t_err = "unknown error";
+        return FM_ERR_INVALID_ARG;
+    }
+}
+
+void require_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        fail(FM_ERR_NO_DEVICE,
+             "no CUDA device available: ferromic_gpu has no CPU fallback on this path");
+    }
+}
+
+cudaStream_t stream() { return cudaStreamPerThread; }
+
+struct Timer {
+    cudaEvent_t a, b;
+    Timer() {
+        CK(cudaEventCreate(&a));
+        CK(cudaEventCreate(&b));
+    }
+    ~Timer() {
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+    }
+    void start() { CK(cudaEventRecord(a, stream())); }
+    void stop() { CK(cudaEventRecord(b, stream())); }
+    float ms() {
+        CK(cudaEventSynchronize(b));
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, a, b));
+        return t;
+    }
+};
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) CK(cudaMalloc((void **)&p, count * sizeof(T)));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+    void upload(const T *h, size_t count) {
+        if (count) CK(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, stream()));
+    }
+    void download(T *h, size_t count) const {
+        if (count) CK(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, stream()));
+    }
+};
+
+int sm_count(int device) {
+    static std::mutex mu;
+    static std::vector<int> cache(64, 0);
+    std::lock_guard<std::mutex> lk(mu);
+    if (device < 64 && cache[device]) return cache[device];
+    int n = 0;
+    CK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
+    if (device < 64) cache[device] = n;
+    return n;
+}
+
+inline int64_t sat_sub(int64_t a, int64_t b) {
+    if (b > 0 && a < std::numeric_limits<int64_t>::min() + b) return std::numeric_limits<int64_t>::min();
+    if (b < 0 && a > std::numeric_limits<int64_t>::max() + b) return std::numeric_limits<int64_t>::max();
+    return a - b;
+}
+
+inline int64_t region_len(int64_t rs, int64_t re) {  // QueryRegion::len (process.rs:573-584)
+    if (rs > re) return 0;
+    int64_t as = rs < 0 ? 0 : rs;
+    int64_t ae;
+    if (re < as)
+        ae = as;
+    else {
+        ae = re == std::numeric_limits<int64_t>::max() ? re : re + 1;
+        if (ae < as) ae = as;
+    }
+    return ae > as ? ae - as : 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ handles
+struct fm_matrix {
+    std::atomic<int> refs{1};
+    int device = 0;
+    const uint8_t *d_data = nullptr;
+    const uint64_t *d_missing = nullptr;
+    bool owns = true;
+    size_t V = 0, S = 0, ploidy = 0, stride = 0;
+    uint8_t max_allele = 0;
+    std::vector<int64_t> pos;
+    int64_t *d_pos = nullptr;
+    bool sorted = true;
+};
+
+struct fm_group {
+    fm_matrix *m = nullptr;
+    std::vector<uint32_t> off;
+    uint32_t n = 0;   // haplotype capacity
+    uint32_t wq = 0;  // uint4 per plane row
+    uint4 *d_allele = nullptr;
+    uint4 *d_called = nullptr;
+    double *d_harm = nullptr;  // H[0..n]
+    std::mutex mu;
+    bool have_counts = false;
+    uint32_t *d_alt = nullptr, *d_cnt = nullptr;
+    uint64_t seg = 0, unc = 0;
+    double pi_sum = 0.0;  // dense_pi_from_counts form over all sites
+};
+
+struct fm_partition {
+    fm_matrix *m = nullptr;
+    size_t G = 0;
+    std::vector<fm_group *> groups;  // one bitplane group per subpopulation
+    fm_group *rest = nullptr;        // haplotypes with no group (needed for "alleles present")
+};
+
+namespace {
+
+void set_dev(const fm_matrix *m) { CK(cudaSetDevice(m->device)); }
+
+// site index range of variants with rs <= pos <= re (positions sorted ascending)
+void site_range(const fm_matrix *m, int64_t rs, int64_t re, uint32_t &lo, uint32_t &hi) {
+    if (!m->sorted)
+        fail(FM_ERR_UNSUPPORTED, "region queries need variant positions sorted ascending");
+    lo = (uint32_t)(std::lower_bound(m->pos.begin(), m->pos.end(), rs) - m->pos.begin());
+    hi = (uint32_t)(std::upper_bound(m->pos.begin(), m->pos.end(), re) - m->pos.begin());
+    if (hi < lo) hi = lo;
+}
+
+struct Geom {
+    fm::PassGeom g;
+    size_t smem;
+};
+
+fm::PassGeom make_geom(const fm_group *const *gs, int ng, uint32_t v_lo, uint32_t v_hi) {
+    fm::PassGeom G{};
+    uint32_t row_bytes = 0, planes = 0, max_wq = 0;
+    for (int i = 0; i < ng; ++i) {
+        const uint32_t p = gs[i]->d_called ? 2u : 1u;
+        row_bytes += gs[i]->wq * 16u * p;
+        planes += p;
+        max_wq = std::max(max_wq, gs[i]->wq);
+    }
+    uint32_t lps = 1;
+    while (lps < 32 && (uint64_t)row_bytes * (32 / lps) > fm::kStageBytes) lps <<= 1;
+    G.lps = lps;
+    G.n_chunks = 1;
+    G.cq = max_wq;
+    if (lps == 32) {
+        const uint32_t cq_max = fm::kStageBytes / (16u * planes);
+        G.cq = std::min(max_wq, cq_max);
+        G.n_chunks = (max_wq + G.cq - 1) / G.cq;
+    }
+    G.v_lo = v_lo;
+    G.v_hi = v_hi;
+    G.b_lo = v_lo / 32;
+    G.n_batches = v_hi > v_lo ? (v_hi + 31) / 32 - G.b_lo : 0;
+    G.n_sites_total = (uint32_t)gs[0]->m->V;
+    return G;
+}
+
+template <int NG>
+void launch_plane_pass(const fm::PassParams<NG> &P, int device) {
+    if (P.geom.n_batches == 0) return;
+    const size_t smem = (size_t)fm::kWarpsPerCta * fm::kStages * fm::kStageBytes;
+    CK(cudaFuncSetAttribute(fm::fm_k_plane_pass<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)smem));
+    const uint32_t need = (P.geom.n_batches + fm::kWarpsPerCta - 1) / fm::kWarpsPerCta;
+    const uint32_t grid = std::min<uint32_t>((uint32_t)sm_count(device), need);
+    fm::fm_k_plane_pass<NG><<<grid, fm::kWarpsPerCta * 32, smem, stream()>>>(P);
+    CK(cudaGetLastError());
+    g_launches++;
+    t_tim.stats_launches++;
+    uint64_t bytes = 0;
+    for (int g = 0; g < NG; ++g)
+        bytes += (uint64_t)(P.geom.v_hi - P.geom.v_lo) * P.g[g].wq * 16u * (P.g[g].called ? 2u : 1u);
+    t_tim.stats_bytes = bytes;
+}
+
+// reduce per-batch partials to per-super-batch on device, finish sequentially on the host
+void finish_partials(const double *d_pd, int nd, const uint32_t *d_pu, int nu, const fm::PassGeom &G,
+                     double *out_d, uint64_t *out_u) {
+    for (int i = 0; i < nd; ++i) out_d[i] = 0.0;
+    for (int i = 0; i < nu; ++i) out_u[i] = 0;
+    if (G.n_batches == 0) return;
+    const uint32_t s_lo = G.b_lo / fm::kSuperBatches;
+    const uint32_t n_super = (G.b_lo + G.n_batches + fm::kSuperBatches - 1) / fm::kSuperBatches - s_lo;
+    DevBuf<double> sd((size_t)n_super * std::max(nd, 1));
+    DevBuf<uint64_t> su((size_t)n_super * std::max(nu, 1));
+    const uint32_t threads = n_super * (uint32_t)(nd + nu);
+    fm::fm_k_reduce_partials<<<(threads + 127) / 128, 128, 0, stream()>>>(
+        d_pd, nd, d_pu, nu, G.b_lo, G.n_batches, s_lo, n_super, sd.p, su.p);
+    CK(cudaGetLastError());
+    g_launches++;
+    std::vector<double> hd((size_t)n_super * std::max(nd, 1));
+    std::vector<uint64_t> hu((size_t)n_super * std::max(nu, 1));
+    sd.download(hd.data(), (size_t)n_super * nd);
+    su.download(hu.data(), (size_t)n_super * nu);
+    CK(cudaStreamSynchronize(stream()));
+    for (uint32_t s = 0; s < n_super; ++s) {  // fixed order: independent of grid / GPU count
+        for (int i = 0; i < nd; ++i) out_d[i] += hd[(size_t)s * nd + i];
+        for (int i = 0; i < nu; ++i) out_u[i] += hu[(size_t)s * nu + i];
+    }
+}
+
+fm::GroupPlanes planes_of(const fm_group *g) {
+    return fm::GroupPlanes{g->d_allele, g->d_called, g->wq, g->n};
+}
+
+struct DivResult {
+    double pi_sum;
+    uint64_t seg, unc;
+};
+
+// Run the diversity statistics for sites [v_lo, v_hi): fused plane pass when counts are not
+// cached (optionally caching them when the range is the whole matrix), light kernel otherwise.
+DivResult run_diversity(fm_group *g, uint32_t v_lo, uint32_t v_hi, int pi_form, double *d_pi,
+                        double *d_theta, const int64_t *d_mask, uint32_t n_mask, const int64_t *d_filt,
+                        uint32_t n_filt, bool store_counts, bool force_plane_pass = false) {
+    const fm_group *gs[1] = {g};
+    fm::PassGeom G = make_geom(gs, 1, v_lo, v_hi);
+    DivResult r{0.0, 0, 0};
+    if (G.n_batches == 0) return r;
+    DevBuf<double> part_pi(G.n_batches);
+    DevBuf<uint32_t> part_u((size_t)G.n_batches * 2);
+    fm::DivEpilogue e{};
+    e.pi_out = d_pi;
+    e.theta_out = d_theta;
+    e.pos = g->m->d_pos;
+    e.mask = d_mask;
+    e.n_mask = n_mask;
+    e.filt = d_filt;
+    e.n_filt = n_filt;
+    e.harmonic = g->d_harm;
+    e.pi_form = pi_form;
+    e.part_pi = part_pi.p;
+    e.part_u = part_u.p;
+    Timer tm;
+    tm.start();
+    if (g->have_counts && !force_plane_pass) {
+        const uint32_t blocks = std::min<uint32_t>((G.n_batches + 7) / 8, 8u * sm_count(g->m->device));
+        fm::fm_k_div_from_counts<<<blocks, 256, 0, stream()>>>(g->d_alt, g->d_cnt, e, v_lo, v_hi,
+                                                                G.b_lo, G.n_batches);
+        CK(cudaGetLastError());
+        g_launches++;
+    } else {
+        if (store_counts) {
+            e.alt_out = g->d_alt;
+            e.called_out = g->d_cnt;
+        }
+        fm::PassParams<1> P{};
+        P.g[0] = planes_of(g);
+        P.geom = G;
+        P.div = e;
+        launch_plane_pass<1>(P, g->m->device);
+    }
+    tm.stop();
+    double od[1];
+    uint64_t ou[2];
+    Timer tr;
+    tr.start();
+    finish_partials(part_pi.p, 1, part_u.p, 2, G, od, ou);
+    r.pi_sum = od[0];
+    r.seg = ou[0];
+    r.unc = ou[1];
+    tr.stop();
+    t_tim.stats_ms += tm.ms();
+    t_tim.reduce_ms += tr.ms();
+    return r;
+}
+
+void ensure_counts(fm_group *g) {
+    std::lock_guard<std::mutex> lk(g->mu);
+    if (g->have_counts) return;
+    set_dev(g->m);
+    const size_t V = g->m->V;
+    if (!g->d_alt) {
+        CK(cudaMalloc((void **)&g->d_alt, std::max<size_t>(V, 1) * sizeof(uint32_t)));
+        CK(cudaMalloc((void **)&g->d_cnt, std::max<size_t>(V, 1) * sizeof(uint32_t)));
+    }
+    DivResult r = run_diversity(g, 0, (uint32_t)V, FM_PIFORM_COUNTS, nullptr, nullptr, nullptr, 0,
+                                nullptr, 0, /*store_counts=*/true);
+    g->seg = r.seg;
+    g->unc = r.unc;
+    g->pi_sum = r.pi_sum;
+    g->have_counts = true;
+}
+
+struct HudsonTotals {
+    double num, den, dxy, pi1, pi2;
+    uint64_t skipped, unc1, unc2;
+};
+
+// Hudson sums (and optional per-site outputs) for [v_lo, v_hi) from cached counts.
+HudsonTotals run_hudson_counts(fm_group *g1, fm_group *g2, uint32_t v_lo, uint32_t v_hi, int variant,
+                               fm::HudsonEpilogue e) {
+    const fm_group *gs[2] = {g1, g2};
+    fm::PassGeom G = make_geom(gs, 2, v_lo, v_hi);
+    HudsonTotals t{0, 0, 0, 0, 0, 0, 0, 0};
+    if (G.n_batches == 0) return t;
+    DevBuf<double> pd((size_t)G.n_batches * 5);
+    DevBuf<uint32_t> pu((size_t)G.n_batches * 3);
+    e.variant = variant;
+    e.part_d = pd.p;
+    e.part_u = pu.p;
+    Timer tm;
+    tm.start();
+    const uint32_t blocks = std::min<uint32_t>((G.n_batches + 7) / 8, 8u * sm_count(g1->m->device));
+    fm::fm_k_hudson_from_counts<<<blocks, 256, 0, stream()>>>(g1->d_alt, g1->d_cnt, g2->d_alt, g2->d_cnt,
+                                                               e, v_lo, v_hi, G.b_lo, G.n_batches);
+    CK(cudaGetLastError());
+    g_launches++;
+    tm.stop();
+    double od[5];
+    uint64_t ou[3];
+    finish_partials(pd.p, 5, pu.p, 3, G, od, ou);
+    t_tim.stats_ms += tm.ms();
+    t = HudsonTotals{od[0], od[1], od[2], od[3], od[4], ou[0], ou[1], ou[2]};
+    return t;
+}
+
+// Fused two-group plane pass: both groups' counts + Hudson partials in one sweep.
+HudsonTotals run_hudson_fused(fm_group *g1, fm_group *g2, uint32_t v_lo, uint32_t v_hi, int variant,
+                              fm::HudsonEpilogue e, bool store_counts) {
+    const fm_group *gs[2] = {g1, g2};
+    fm::PassGeom G = make_geom(gs, 2, v_lo, v_hi);
+    HudsonTotals t{0, 0, 0, 0, 0, 0, 0, 0};
+    if (G.n_batches == 0) return t;
+    DevBuf<double> pd((size_t)G.n_batches * 5);
+    DevBuf<uint32_t> pu((size_t)G.n_batches * 3);
+    e.variant = variant;
+    e.part_d = pd.p;
+    e.part_u = pu.p;
+    if (store_counts) {
+        e.alt_out[0] = g1->d_alt;
+        e.called_out[0] = g1->d_cnt;
+        e.alt_out[1] = g2->d_alt;
+        e.called_out[1] = g2->d_cnt;
+    }
+    fm::PassParams<2> P{};
+    P.g[0] = planes_of(g1);
+    P.g[1] = planes_of(g2);
+    P.geom = G;
+    P.hud = e;
+    Timer tm;
+    tm.start();
+    launch_plane_pass<2>(P, g1->m->device);
+    tm.stop();
+    double od[5];
+    uint64_t ou[3];
+    finish_partials(pd.p, 5, pu.p, 3, G, od, ou);
+    t_tim.stats_ms += tm.ms();
+    t = HudsonTotals{od[0], od[1], od[2], od[3], od[4], ou[0], ou[1], ou[2]};
+    return t;
+}
+
+void merge_intervals(const int64_t *iv, size_t n, std::vector<int64_t> &out) {
+    std::vector<std::pair<int64_t, int64_t>> v;
+    v.reserve(n);
+    for (size_t i = 0; i < n; ++i)
+        if (iv[2 * i + 1] > iv[2 * i]) v.emplace_back(iv[2 * i], iv[2 * i + 1]);
+    std::sort(v.begin(), v.end());
+    out.clear();
+    for (auto &p : v) {
+        if (!out.empty() && p.first <= out[out.size() - 1]) {
+            if (p.second > out[out.size() - 1]) out[out.size() - 1] = p.second;
+        } else {
+            out.push_back(p.first);
+            out.push_back(p.second);
+        }
+    }
+}
+
+int dense_variant(const fm_matrix *m) { return m->d_missing ? FM_HV_DENSE_MISSING : FM_HV_DENSE_NOMISSING; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ library
+extern "C" {
+
+const char *fm_last_error(void) { return t_err.c_str(); }
+const char *fm_version(void) { return "ferromic_gpu 0.1.0 (sm_100a)"; }
+
+fm_status fm_device_count(int *count) {
+    return guarded([&] {
+        if (!count) fail(FM_ERR_INVALID_ARG, "count is NULL");
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            n = 0;
+        }
+        *count = n;
+    });
+}
+
+fm_status fm_set_device(int device) {
+    return guarded([&] {
+        require_device();
+        CK(cudaSetDevice(device));
+        t_device = device;
+    });
+}
+
+fm_status fm_synchronize(void) {
+    return guarded([&] {
+        require_device();
+        CK(cudaStreamSynchronize(stream()));
+    });
+}
+
+fm_status fm_timings_reset(void) {
+    t_tim = fm_timings{};
+    g_launches = 0;
+    return FM_OK;
+}
+fm_status fm_timings_get(fm_timings *out) {
+    if (!out) return FM_ERR_INVALID_ARG;
+    *out = t_tim;
+    out->kernel_launches = g_launches.load();
+    return FM_OK;
+}
+
+// ------------------------------------------------------------------------------------ matrix
+static fm_matrix *matrix_common(size_t V, size_t S, size_t ploidy, uint8_t max_allele,
+                                const int64_t *positions) {
+    if (ploidy != 0 && S != 0 && V > std::numeric_limits<size_t>::max() / S / ploidy)
+        fail(FM_ERR_INVALID_ARG, "dense genotype matrix dimensions overflow");  // stats.rs:276-279
+    if (V >= (1ull << 32) - 64) fail(FM_ERR_UNSUPPORTED, "more than 2^32 variants per matrix handle");
+    if (S * ploidy >= (1ull << 32)) fail(FM_ERR_UNSUPPORTED, "row stride exceeds 2^32 entries");
+    fm_matrix *m = new fm_matrix();
+    m->device = t_device;
+    m->V = V;
+    m->S = S;
+    m->ploidy = ploidy;
+    m->stride = S * ploidy;
+    m->max_allele = max_allele;
+    m->pos.resize(V);
+    for (size_t i = 0; i < V; ++i) m->pos[i] = positions ? positions[i] : (int64_t)i;
+    m->sorted = std::is_sorted(m->pos.begin(), m->pos.end());
+    return m;
+}
+
+fm_status fm_matrix_create(const uint8_t *data, const uint64_t *missing, size_t V, size_t S,
+                           size_t ploidy, uint8_t max_allele, const int64_t *positions,
+                           fm_matrix **out) {
+    return guarded([&] {
+        if (!out) fail(FM_ERR_INVALID_ARG, "out is NULL");
+        *out = nullptr;
+        require_device();
+        CK(cudaSetDevice(t_device));
+        fm_matrix *m = matrix_common(V, S, ploidy, max_allele, positions);
+        try {
+            const size_t total = V * m->stride;
+            if (total && !data) fail(FM_ERR_INVALID_ARG, "data is NULL");
+            Timer tm;
+            tm.start();
+            uint8_t *dd = nullptr;
+            CK(cudaMalloc((void **)&dd, std::max<size_t>(total, 16)));
+            m->d_data = dd;
+            if (total) CK(cudaMemcpyAsync(dd, data, total, cudaMemcpyHostToDevice, stream()));
+            if (missing) {
+                const size_t words = (total + 63) / 64;
+                uint64_t *dm = nullptr;
+                CK(cudaMalloc((void **)&dm, std::max<size_t>(words, 2) * 8));
+                m->d_missing = dm;
+                if (words) CK(cudaMemcpyAsync(dm, missing, words * 8, cudaMemcpyHostToDevice, stream()));
+            }
+            CK(cudaMalloc((void **)&m->d_pos, std::max<size_t>(V, 1) * 8));
+            if (V) CK(cudaMemcpyAsync(m->d_pos, m->pos.data(), V * 8, cudaMemcpyHostToDevice, stream()));
+            tm.stop();
+            t_tim.h2d_ms += tm.ms();
+        } catch (...) {
+            fm_matrix_release(m);
+            throw;
+        }
+        *out = m;
+    });
+}
+
+fm_status fm_matrix_create_device(const uint8_t *d_data, const uint64_t *d_missing, size_t V, size_t S,
+                                  size_t ploidy, uint8_t max_allele, const int64_t *positions,
+                                  fm_matrix **out) {
+    return guarded([&] {
+        if (!out) fail(FM_ERR_INVALID_ARG, "out is NULL");
+        *out = nullptr;
+        require_device();
+        CK(cudaSetDevice(t_device));
+        fm_matrix *m = matrix_common(V, S, ploidy, max_allele, positions);
+        m->owns = false;
+        m->d_data = d_data;
+        m->d_missing = d_missing;
+        try {
+            CK(cudaMalloc((void **)&m->d_pos, std::max<size_t>(V, 1) * 8));
+            if (V) CK(cudaMemcpyAsync(m->d_pos, m->pos.data(), V * 8, cudaMemcpyHostToDevice, stream()));
+            CK(cudaStreamSynchronize(stream()));
+        } catch (...) {
+            fm_matrix_release(m);
+            throw;
+        }
+        *out = m;
+    });
+}
+
+fm_status fm_matrix_retain(fm_matrix *m) {
+    if (!m) return FM_ERR_INVALID_ARG;
+    m->refs++;
+    return FM_OK;
+}
+
+fm_status fm_matrix_release(fm_matrix *m) {
+    if (!m) return FM_OK;
+    if (--m->refs == 0) {
+        cudaSetDevice(m->device);
+        if (m->owns) {
+            cudaFree((void *)m->d_data);
+            cudaFree((void *)m->d_missing);
+        }
+        cudaFree(m->d_pos);
+        delete m;
+    }
+    return FM_OK;
+}
+
+fm_status fm_matrix_info(const fm_matrix *m, size_t *V, size_t *S, size_t *ploidy, uint8_t *max_allele,
+                         int *has_missing) {
+    if (!m) return FM_ERR_INVALID_ARG;
+    if (V) *V = m->V;
+    if (S) *S = m->S;
+    if (ploidy) *ploidy = m->ploidy;
+    if (max_allele) *max_allele = m->max_allele;
+    if (has_missing) *has_missing = m->d_missing != nullptr;
+    return FM_OK;
+}
+
+// ------------------------------------------------------------------------------------ group
+fm_status fm_group_create(fm_matrix *m, const uint64_t *sample_idx, const uint8_t *side, size_t n,
+                          fm_group **out) {
+    return guarded([&] {
+        if (!out || !m) fail(FM_ERR_INVALID_ARG, "NULL argument");
+        *out = nullptr;
+        if (n && (!sample_idx || !side)) fail(FM_ERR_INVALID_ARG, "haplotype arrays are NULL");
+        if (m->max_allele > 1)
+            fail(FM_ERR_UNSUPPORTED,
+                 "multi-allelic matrices (max_allele > 1) are not on the GPU path yet");
+        set_dev(m);
+        fm_group *g = new fm_group();
+        g->m = m;
+        fm_matrix_retain(m);
+        try {
+            // DenseMembership::build (stats.rs:1251-1284)
+            std::vector<uint8_t> left(m->S, 0), right(m->S, 0);
+            g->off.reserve(n);
+            for (size_t i = 0; i < n; ++i) {
+                const uint64_t s = sample_idx[i];
+                if (s >= m->S) continue;
+                if (side[i] == 0) {
+                    if (!left[s]) {
+                        left[s] = 1;
+                        g->off.push_back((uint32_t)(s * m->ploidy));
+                    }
+                } else {
+                    if (m->ploidy <= 1) continue;
+                    if (!right[s]) {
+                        right[s] = 1;
+                        g->off.push_back((uint32_t)(s * m->ploidy + 1));
+                    }
+                }
+            }
+            std::sort(g->off.begin(), g->off.end());
+            g->n = (uint32_t)g->off.size();
+            g->wq = std::max<uint32_t>(1, (g->n + 127) / 128);
+            const size_t plane_u4 = std::max<size_t>(m->V, 1) * g->wq;
+            CK(cudaMalloc((void **)&g->d_allele, plane_u4 * 16));
+            if (m->d_missing) CK(cudaMalloc((void **)&g->d_called, plane_u4 * 16));
+            // harmonic table, forward summation exactly like stats.rs:4234-4240
+            std::vector<double> H((size_t)g->n + 1);
+            double s = 0.0;
+            H[0] = 0.0;
+            for (uint32_t k = 1; k <= g->n; ++k) {
+                s += 1.0 / (double)k;
+                H[k] = s;
+            }
+            CK(cudaMalloc((void **)&g->d_harm, H.size() * 8));
+            CK(cudaMemcpyAsync(g->d_harm, H.data(), H.size() * 8, cudaMemcpyHostToDevice, stream()));
+            DevBuf<uint32_t> d_off(std::max<size_t>(g->n, 1));
+            d_off.upload(g->off.data(), g->n);
+            if (m->V) {
+                Timer tm;
+                tm.start();
+                const uint32_t blocks = (uint32_t)std::min<uint64_t>(
+                    (uint64_t)sm_count(m->device) * 8,
+                    std::max<uint64_t>(1, ((uint64_t)m->V * ((g->wq * 4 + 31) / 32) + 7) / 8));
+                fm::fm_k_repack<<<blocks, 256, 0, stream()>>>(
+                    m->d_data, m->d_missing, m->stride, d_off.p, g->n, g->wq, 0, (uint32_t)m->V,
+                    reinterpret_cast<uint32_t *>(g->d_allele), reinterpret_cast<uint32_t *>(g->d_called));
+                CK(cudaGetLastError());
+                g_launches++;
+                tm.stop();
+                t_tim.repack_ms += tm.ms();
+            }
+            CK(cudaStreamSynchronize(stream()));
+        } catch (...) {
+            fm_group_release(g);
+            throw;
+        }
+        *out = g;
+    });
+}
+
+fm_status fm_group_release(fm_group *g) {
+    if (!g) return FM_OK;
+    if (g->m) cudaSetDevice(g->m->device);
+    cudaFree(g->d_allele);
+    cudaFree(g->d_called);
+    cudaFree(g->d_harm);
+    cudaFree(g->d_alt);
+    cudaFree(g->d_cnt);
+    fm_matrix_release(g->m);
+    delete g;
+    return FM_OK;
+}
+
+fm_status fm_group_capacity(const fm_group *g, size_t *cap) {
+    if (!g || !cap) return FM_ERR_INVALID_ARG;
+    *cap = g->n;
+    return FM_OK;
+}
+
+fm_status fm_group_summary(fm_group *g, uint32_t *alt_out, uint32_t *called_out, uint64_t *seg,
+                           double *pi_sum, uint64_t *unc) {
+    return guarded([&] {
+        if (!g) fail(FM_ERR_INVALID_ARG, "group is NULL");
+        require_device();
+        ensure_counts(g);
+        set_dev(g->m);
+        Timer tm;
+        tm.start();
+        if (alt_out && g->m->V)
+            CK(cudaMemcpyAsync(alt_out, g->d_alt, g->m->V * 4, cudaMemcpyDeviceToHost, stream()));
+        if (called_out && g->m->V)
+            CK(cudaMemcpyAsync(called_out, g->d_cnt, g->m->V * 4, cudaMemcpyDeviceToHost, stream()));
+        tm.stop();
+        CK(cudaStreamSynchronize(stream()));
+        t_tim.d2h_ms += tm.ms();
+        if (seg) *seg = g->seg;
+        if (pi_sum) *pi_sum = g->pi_sum;
+        if (unc) *unc = g->unc;
+    });
+}
+
+fm_status fm_group_segregating_sites(fm_group *g, uint64_t *out) {
+    return guarded([&] {
+        if (!g || !out) fail(FM_ERR_INVALID_ARG, "NULL argument");
+        require_device();
+        // stats.rs:3835-3842 / 4033-4035: membership.len() <= 1 -> 0
+        if (g->n <= 1) {
+            *out = 0;
+            return;
+        }
+        ensure_counts(g);
+        *out = g->seg;
+    });
+}
+
+fm_status fm_group_pi(fm_group *g, int64_t L, int path, size_t raw_n, double *out) {
+    return guarded([&] {
+        if (!g || !out) fail(FM_ERR_INVALID_ARG, "NULL argument");
+        require_device();
+        const double NaN = std::numeric_limits<double>::quiet_NaN();
+        const double Inf = std::numeric_limits<double>::infinity();
+        if (path == FM_PI_SPARSE) {
+            if (raw_n <= 1) { *out = NaN; return; }          // stats.rs:4322-4331
+        } else if (g->n <= 1) { *out = NaN; return; }        // :1485 / :4539
+        if (L < 0) { *out = 0.0; return; }
+        if (L == 0) { *out = Inf; return; }
+        if (path == FM_PI_SPARSE && g->n <= 1) { *out = NaN; return; }  // :4365
+        ensure_counts(g);
+        set_dev(g->m);
+        double pi_sum;
+        uint64_t skipped;
+        if (path == FM_PI_SUMMARY || (path == FM_PI_DENSE && g->m->d_missing)) {
+            pi_sum = g->pi_sum;  // dense_pi_from_counts form
+            skipped = g->unc;
+        } else {
+            const int form = path == FM_PI_DENSE ? FM_PIFORM_NOMISSING : FM_PIFORM_COMPONENTS;
+            DivResult r = run_diversity(g, 0, (uint32_t)g->m->V, form, nullptr, nullptr, nullptr, 0,
+                                        nullptr, 0, false);
+            pi_sum = r.pi_sum;
+            skipped = path == FM_PI_DENSE ? 0 : r.unc;  // stats.rs:4523: (sum_pi, 0usize)
+        }
+        const int64_t eff = sat_sub(L, (int64_t)skipped);
+        if (eff == 0) { *out = NaN; return; }
+        *out = pi_sum / (double)eff;
+    });
+}
+
+fm_status fm_harmonic(size_t n, double *out) {
+    if (!out) return FM_ERR_INVALID_ARG;
+    double s = 0.0;
+    for (size_t k = 1; k <= n; ++k) s += 1.0 / (double)k;
+    *out = s;
+    return FM_OK;
+}
+
+fm_status fm_watterson_theta(size_t seg, size_t n, int64_t L, double *out) {
+    if (!out) return FM_ERR_INVALID_ARG;
+    const double NaN = std::numeric_limits<double>::quiet_NaN();
+    const double Inf = std::numeric_limits<double>::infinity();
+    if (n <= 1 || L <= 0) {  // stats.rs:4246-4279
+        *out = seg == 0 ? NaN : Inf;
+        return FM_OK;
+    }
+    double h;
+    fm_harmonic(n - 1, &h);
+    *out = h > 0.0 ? (double)seg / h / (double)L : (seg == 0 ? NaN : Inf);
+    return FM_OK;
+}
+
+fm_status fm_per_site_diversity(fm_group *g, size_t raw_n, int64_t rs, int64_t re, const int64_t *mask_iv,
+                                size_t n_mask, const int64_t *filtered, size_t n_filt, int64_t *pos_out,
+                                double *pi_out, double *theta_out, size_t capacity, size_t *n_out) {
+    return guarded([&] {
+        if (!g || !n_out) fail(FM_ERR_INVALID_ARG, "NULL argument");
+        *n_out = 0;
+        require_device();
+        if (region_len(rs, re) <= 0) return;  // stats.rs:4656-4666
+        if (raw_n < 2) return;                // stats.rs:4675-4681
+        set_dev(g->m);
+        uint32_t lo, hi;
+        site_range(g->m, rs, re, lo, hi);
+        const size_t n = hi - lo;
+        if (n == 0) return;
+        if (n > capacity) fail(FM_ERR_INVALID_ARG, "output capacity too small");
+        if (!pos_out || !pi_out || !theta_out) fail(FM_ERR_INVALID_ARG, "output arrays are NULL");
+        std::vector<int64_t> merged;
+        DevBuf<int64_t> d_mask, d_filt;
+        if (mask_iv) {
+            merge_intervals(mask_iv, n_mask, merged);
+            d_mask.alloc(std::max<size_t>(merged.size(), 2));
+            d_mask.upload(merged.data(), merged.size());
+        }
+        std::vector<int64_t> fs;
+        if (filtered && n_filt) {
+            fs.assign(filtered, filtered + n_filt);
+            std::sort(fs.begin(), fs.end());
+            d_filt.alloc(fs.size());
+            d_filt.upload(fs.data(), fs.size());
+        }
+        DevBuf<double> d_pi(n), d_theta(n);
+        {
+            std::lock_guard<std::mutex> lk(g->mu);  // serialise with lazy count caching
+            run_diversity(g, lo, hi, FM_PIFORM_COMPONENTS, d_pi.p, d_theta.p, mask_iv ? d_mask.p : nullptr,
+                          (uint32_t)(merged.size() / 2), fs.empty() ? nullptr : d_filt.p,
+                          (uint32_t)fs.size(), false);
+        }
+        Timer tm;
+        tm.start();
+        d_pi.download(pi_out, n);
+        d_theta.download(theta_out, n);
+        tm.stop();
+        CK(cudaStreamSynchronize(stream()));
+        t_tim.d2h_ms += tm.ms();
+        for (size_t i = 0; i < n; ++i) pos_out[i] = g->m->pos[lo + i] + 1;  // stats.rs:4746
+        *n_out = n;
+    });
+}
+
+// ------------------------------------------------------------------------------------ Hudson
+static void check_pair(fm_group *g1, fm_group *g2, bool allow_distinct_matrices = false) {
+    if (!g1 || !g2) fail(FM_ERR_INVALID_ARG, "group is NULL");
+    if (g1->m == g2->m) return;
+    // Two contexts with their own matrices are only meaningful on the summaries path, which
+    // works on the per-group count arrays (stats.rs:1554-1623); variants_compatible
+    // (stats.rs:3399-3401) still has to hold.
+    if (!allow_distinct_matrices || g1->m->device != g2->m->device || g1->m->pos != g2->m->pos)
+        fail(FM_ERR_PARSE, "Variant slices differ in positions/length.");  // stats.rs:3451-3455
+}
+
+// regional Dxy of calculate_d_xy_hudson (stats.rs:2403-2524) given totals of the matching variant
+static void dxy_outcome(int path, fm_group *g1, fm_group *g2, int64_t L, size_t raw_n1, size_t raw_n2,
+                        const HudsonTotals &t, double *d, bool *some) {
+    *some = false;
+    *d = 0.0;
+    if (raw_n1 == 0 || raw_n2 == 0) return;                                 // :2434-2446
+    if (path == FM_HUDSON_DENSE && (g1->n == 0 || g2->n == 0)) return;      // :2532-2534
+    const int64_t eff = sat_sub(L, (int64_t)t.skipped);
+    if (eff > 0) {
+        *d = t.dxy / (double)eff;
+        *some = true;
+    }
+}
+
+fm_status fm_hudson_dxy(fm_group *g1, fm_group *g2, int64_t L1, int64_t L2, int path, size_t raw_n1,
+                        size_t raw_n2, double *d_xy, int *is_some) {
+    return guarded([&] {
+        if (!d_xy || !is_some) fail(FM_ERR_INVALID_ARG, "NULL argument");
+        *is_some = 0;
+        *d_xy = 0.0;
+        if (L1 <= 0) fail(FM_ERR_INVALID_REGION, "Sequence length must be positive for Dxy calculation");
+        if (L1 != L2) fail(FM_ERR_PARSE, "Sequence length mismatch in Dxy calculation");
+        check_pair(g1, g2, path == FM_HUDSON_SUMMARIES);
+        require_device();
+        if (raw_n1 == 0 || raw_n2 == 0) return;
+        ensure_counts(g1);
+        ensure_counts(g2);
+        set_dev(g1->m);
+        const int variant = path == FM_HUDSON_SUMMARIES ? -1
+                            : path == FM_HUDSON_DENSE   ? dense_variant(g1->m)
+                                                        : FM_HV_SPARSE;
+        HudsonTotals t = run_hudson_counts(g1, g2, 0, (uint32_t)g1->m->V, variant, fm::HudsonEpilogue{});
+        bool some;
+        dxy_outcome(path, g1, g2, L1, raw_n1, raw_n2, t, d_xy, &some);
+        *is_some = some;
+    });
+}
+
+// calculate_pi_for_population for one side of a Hudson call, given the matching totals
+static double pi_outcome(int path, fm_group *g, int64_t L, size_t raw_n, double pi_sum, uint64_t unc) {
+    const double NaN = std::numeric_limits<double>::quiet_NaN();
+    if (path == FM_HUDSON_SPARSE) {
+        if (raw_n <= 1) return NaN;
+    } else if (g->n <= 1)
+        return NaN;
+    if (L < 0) return 0.0;
+    if (L == 0) return std::numeric_limits<double>::infinity();
+    if (path == FM_HUDSON_SPARSE && g->n <= 1) return NaN;
+    const uint64_t skipped = (path == FM_HUDSON_DENSE && !g->m->d_missing) ? 0 : unc;
+    const int64_t eff = sat_sub(L, (int64_t)skipped);
+    if (eff == 0) return NaN;
+    return pi_sum / (double)eff;
+}
+
+fm_status fm_hudson_pair(fm_group *g1, fm_group *g2, int64_t L1, int64_t L2, int path, int has_region,
+                         int64_t rs, int64_t re, size_t raw_n1, size_t raw_n2, fm_hudson_outcome *out,
+                         fm_hudson_sites *sites, size_t *n_sites) {
+    return guarded([&] {
+        if (!out) fail(FM_ERR_INVALID_ARG, "out is NULL");
+        std::memset(out, 0, sizeof(*out));
+        if (n_sites) *n_sites = 0;
+        if (L1 <= 0)
+            fail(FM_ERR_INVALID_REGION, "Sequence length must be positive for Hudson FST calculation.");
+        if (L1 != L2)
+            fail(FM_ERR_PARSE,
+                 "Sequence length mismatch between population contexts for Hudson FST calculation.");
+        check_pair(g1, g2, path == FM_HUDSON_SUMMARIES && !has_region);
+        require_device();
+        fm_matrix *m = g1->m;
+        set_dev(m);
+        const uint32_t V = (uint32_t)m->V;
+        const int aux_variant = path == FM_HUDSON_SUMMARIES ? -1
+                                : path == FM_HUDSON_DENSE   ? dense_variant(m)
+                                                            : FM_HV_SPARSE;
+        HudsonTotals main_t{0, 0, 0, 0, 0, 0, 0, 0}, aux_t{0, 0, 0, 0, 0, 0, 0, 0};
+        bool aux_done = false;
+
+        // --- per-site outputs (region => sparse per-site path; else the path's own per-site form)
+        uint32_t lo = 0, hi = V;
+        int site_variant = aux_variant;
+        if (has_region) {
+            site_range(m, rs, re, lo, hi);
+            site_variant = FM_HV_SPARSE;  // stats.rs:3473-3475
+        }
+        const bool emit_sites = sites && site_variant >= 0;
+        const size_t ns = hi - lo;
+        DevBuf<double> sd;
+        DevBuf<uint32_t> su;
+        fm::HudsonEpilogue e{};
+        if (emit_sites && ns) {
+            if (ns > sites->capacity) fail(FM_ERR_INVALID_ARG, "per-site output capacity too small");
+            sd.alloc(ns * 6);
+            su.alloc(ns * 2);
+            e.fst = sd.p;
+            e.dxy = sd.p + ns;
+            e.pi1 = sd.p + 2 * ns;
+            e.pi2 = sd.p + 3 * ns;
+            e.num = sd.p + 4 * ns;
+            e.den = sd.p + 5 * ns;
+            e.n1_out = su.p;
+            e.n2_out = su.p + ns;
+        }
+        // counts: fused two-group sweep when nothing is cached yet and the main pass covers the
+        // whole matrix; otherwise per-group plane passes (cached) + light kernels on the counts.
+        bool fused = false;
+        if (g1 != g2 && g1->m == g2->m && lo == 0 && hi == V && V > 0) {
+            std::unique_lock<std::mutex> l1(g1->mu, std::defer_lock), l2(g2->mu, std::defer_lock);
+            std::lock(l1, l2);
+            if (!g1->have_counts && !g2->have_counts) {
+                for (fm_group *g : {g1, g2})
+                    if (!g->d_alt) {
+                        CK(cudaMalloc((void **)&g->d_alt, (size_t)V * 4));
+                        CK(cudaMalloc((void **)&g->d_cnt, (size_t)V * 4));
+                    }
+                main_t = run_hudson_fused(g1, g2, 0, V, site_variant, e, true);
+                for (fm_group *g : {g1, g2}) {  // per-group summary scalars from the cached counts
+                    g->have_counts = true;
+                    DivResult r = run_diversity(g, 0, V, FM_PIFORM_COUNTS, nullptr, nullptr, nullptr, 0,
+                                                nullptr, 0, false);
+                    g->seg = r.seg;
+                    g->unc = r.unc;
+                    g->pi_sum = r.pi_sum;
+                }
+                fused = true;
+            }
+        }
+        if (!fused) {
+            ensure_counts(g1);
+            ensure_counts(g2);
+            main_t = run_hudson_counts(g1, g2, lo, hi, site_variant, e);
+        }
+        if (!has_region || (lo == 0 && hi == V && site_variant == aux_variant)) {
+            aux_t = main_t;
+            aux_done = true;
+        }
+        if (!aux_done) aux_t = run_hudson_counts(g1, g2, 0, V, aux_variant, fm::HudsonEpilogue{});
+
+        // --- regional FST (stats.rs:3505-3509); DENSE/SPARSE with no variants -> (0,0)
+        const double num_sum = main_t.num, den_sum = main_t.den;
+        if (den_sum > FM_FST_EPSILON) {
+            out->fst = num_sum / den_sum;
+            out->some |= 1u;
+        }
+        // --- auxiliary pi / Dxy (stats.rs:3512-3566)
+        double pi1_raw, pi2_raw;
+        bool dsome = false;
+        double dval = 0.0;
+        if (path == FM_HUDSON_SUMMARIES && !has_region) {
+            // calculate_pi_from_summary_with_precomputed(Some(totals.piX_sum))
+            pi1_raw = pi_outcome(path, g1, L1, raw_n1, aux_t.pi1, g1->unc);
+            pi2_raw = pi_outcome(path, g2, L2, raw_n2, aux_t.pi2, g2->unc);
+            if (raw_n1 != 0 && raw_n2 != 0) {
+                const int64_t eff = sat_sub(L1, (int64_t)aux_t.skipped);
+                if (eff > 0) {
+                    dval = aux_t.dxy / (double)eff;
+                    dsome = true;
+                }
+            }
+        } else if (path == FM_HUDSON_SUMMARIES) {
+            // calculate_pi_for_population -> calculate_pi_from_summary (cached pi_sum)
+            pi1_raw = pi_outcome(path, g1, L1, raw_n1, g1->pi_sum, g1->unc);
+            pi2_raw = pi_outcome(path, g2, L2, raw_n2, g2->pi_sum, g2->unc);
+            dxy_outcome(path, g1, g2, L1, raw_n1, raw_n2, aux_t, &dval, &dsome);
+        } else {
+            pi1_raw = pi_outcome(path, g1, L1, raw_n1, aux_t.pi1, aux_t.unc1);
+            pi2_raw = pi_outcome(path, g2, L2, raw_n2, aux_t.pi2, aux_t.unc2);
+            dxy_outcome(path, g1, g2, L1, raw_n1, raw_n2, aux_t, &dval, &dsome);
+        }
+        if (std::isfinite(pi1_raw)) { out->pi_pop1 = pi1_raw; out->some |= 4u; }
+        if (std::isfinite(pi2_raw)) { out->pi_pop2 = pi2_raw; out->some |= 8u; }
+        if (dsome) { out->d_xy = dval; out->some |= 2u; }
+        if ((out->some & 12u) == 12u) {
+            out->pi_xy_avg = 0.5 * (out->pi_pop1 + out->pi_pop2);
+            out->some |= 16u;
+        }
+        // --- copy per-site outputs
+        if (emit_sites && ns) {
+            Timer tm;
+            tm.start();
+            double *dst[6] = {sites->fst, sites->d_xy, sites->pi_pop1, sites->pi_pop2,
+                              sites->num_component, sites->den_component};
+            for (int i = 0; i < 6; ++i)
+                if (dst[i]) CK(cudaMemcpyAsync(dst[i], sd.p + (size_t)i * ns, ns * 8, cudaMemcpyDeviceToHost, stream()));
+            if (sites->n1_called) CK(cudaMemcpyAsync(sites->n1_called, su.p, ns * 4, cudaMemcpyDeviceToHost, stream()));
+            if (sites->n2_called) CK(cudaMemcpyAsync(sites->n2_called, su.p + ns, ns * 4, cudaMemcpyDeviceToHost, stream()));
+            tm.stop();
+            CK(cudaStreamSynchronize(stream()));
+            t_tim.d2h_ms += tm.ms();
+            if (sites->position)
+                for (size_t i = 0; i < ns; ++i) sites->position[i] = m->pos[lo + i] + 1;
+        }
+        if (n_sites) *n_sites = (site_variant >= 0) ? ns : 0;
+    });
+}
+
+// ------------------------------------------------------------------------------------ W&C (see fm_wc.cuh)
+fm_status fm_partition_create(fm_matrix *, const uint16_t *, const uint16_t *, size_t, size_t,
+                              fm_partition **out) {
+    return guarded([&] {
+        if (out) *out = nullptr;
+        fail(FM_ERR_UNSUPPORTED, "Weir & Cockerham path not built yet");
+    });
+}
+fm_status fm_partition_release(fm_partition *) { return FM_OK; }
+fm_status fm_wc_fst(fm_partition *, int64_t, int64_t, fm_fst_estimate *, fm_fst_estimate *, uint8_t *,
+                    int64_t *, int32_t *, double *, double *, uint32_t *, double *, double *, size_t,
+                    size_t *) {
+    return guarded([&] { fail(FM_ERR_UNSUPPORTED, "Weir & Cockerham path not built yet"); });
+}
+
+// ------------------------------------------------------------------------------------ L_adj
+fm_status fm_adjusted_sequence_length(int64_t region_start, int64_t region_end, const int64_t *allow,
+                                      size_t n_allow, const int64_t *mask, size_t n_mask, int64_t *out) {
+    return guarded([&] {
+        if (!out) fail(FM_ERR_INVALID_ARG, "out is NULL");
+        // stats.rs:3644-3736.  ZeroBasedHalfOpen::from_1based_inclusive (process.rs:193-206)
+        auto hb = [](int64_t s, int64_t e, uint64_t &hs, uint64_t &he) {
+            if (s < 1) s = 1;
+            if (e < s) e = s;
+            hs = (uint64_t)(s - 1);
+            he = (uint64_t)e;
+        };
+        uint64_t rs, re;
+        hb(region_start, region_end, rs, re);
+        std::vector<std::pair<int64_t, int64_t>> allowed;
+        if (allow) {
+            for (size_t i = 0; i < n_allow; ++i) {
+                const uint64_t as = (uint64_t)allow[2 * i], ae = (uint64_t)allow[2 * i + 1];
+                const uint64_t s = std::max(rs, as), e = std::min(re, ae);
+                if (s < e) allowed.emplace_back((int64_t)s + 1, (int64_t)e);
+            }
+        } else {
+            allowed.emplace_back(region_start, region_end);
+        }
+        int64_t total = 0;
+        std::vector<std::pair<int64_t, int64_t>> parts, next;
+        for (auto &a : allowed) {  // subtract_regions (stats.rs:3739-3775): masks applied in order
+            parts.assign(1, a);
+            if (mask) {
+                for (size_t mi = 0; mi < n_mask && !parts.empty(); ++mi) {
+                    const int64_t m_start = (int64_t)((uint64_t)mask[2 * mi]) + 1;
+                    const int64_t m_end = (int64_t)((uint64_t)mask[2 * mi + 1]);
+                    next.clear();
+                    for (auto &p : parts) {
+                        const int64_t s = p.first, e = p.second;
+                        if (m_end < s || m_start > e) {
+                            next.push_back(p);
+                            continue;
+                        }
+                        if (m_start > s && m_start - 1 >= s) next.emplace_back(s, m_start - 1);
+                        if (m_end < e && m_end + 1 <= e) next.emplace_back(m_end + 1, e);
+                    }
+                    parts.swap(next);
+                }
+            }
+            for (auto &p : parts) {
+                uint64_t hs, he;
+                hb(p.first, p.second, hs, he);
+                total += he > hs ? (int64_t)(he - hs) : 0;
+            }
+        }
+        *out = total;
+    });
+}
+
+// ------------------------------------------------------------------------------------ windows (K5)
+static void window_ranges(const fm_matrix *m, const int64_t *windows, size_t n, std::vector<uint32_t> &lo,
+                          std::vector<uint32_t> &hi) {
+    lo.resize(n);
+    hi.resize(n);
+    for (size_t i = 0; i < n; ++i) site_range(m, windows[2 * i], windows[2 * i + 1], lo[i], hi[i]);
+}
+
+fm_status fm_group_window_sums(fm_group *g, const int64_t *windows, size_t n_windows, uint64_t *n_variants,
+                               uint64_t *seg, double *pi_sum, uint64_t *unc) {
+    return guarded([&] {
+        if (!g || (n_windows && !windows)) fail(FM_ERR_INVALID_ARG, "NULL argument");
+        require_device();
+        if (!n_windows) return;
+        ensure_counts(g);
+        set_dev(g->m);
+        std::vector<uint32_t> lo, hi;
+        window_ranges(g->m, windows, n_windows, lo, hi);
+        DevBuf<uint32_t> dlo(n_windows), dhi(n_windows);
+        dlo.upload(lo.data(), n_windows);
+        dhi.upload(hi.data(), n_windows);
+        DevBuf<uint64_t> dseg(n_windows), dunc(n_windows);
+        DevBuf<double> dpi(n_windows);
+        const uint32_t blocks = (uint32_t)std::min<size_t>((n_windows + 7) / 8, 8u * sm_count(g->m->device));
+        fm::fm_k_window_div<<<blocks, 256, 0, stream()>>>(g->d_alt, g->d_cnt, dlo.p, dhi.p, (uint32_t)n_windows,
+                                                           FM_PIFORM_COUNTS, dseg.p, dpi.p, dunc.p);
+        CK(cudaGetLastError());
+        g_launches++;
+        if (seg) dseg.download(seg, n_windows);
+        if (unc) dunc.download(unc, n_windows);
+        if (pi_sum) dpi.download(pi_sum, n_windows);
+        CK(cudaStreamSynchronize(stream()));
+        if (n_variants)
+            for (size_t i = 0; i < n_windows; ++i) n_variants[i] = hi[i] - lo[i];
+    });
+}
+
+fm_status fm_hudson_window_sums(fm_group *g1, fm_group *g2, const int64_t *windows, size_t n_windows,
+                                double *num_sum, double *den_sum, double *dxy_sum, uint64_t *dxy_unc,
+                                double *pi1_sum, double *pi2_sum) {
+    return guarded([&] {
+        check_pair(g1, g2);
+        if (n_windows && !windows) fail(FM_ERR_INVALID_ARG, "NULL argument");
+        require_device();
+        if (!n_windows) return;
+        ensure_counts(g1);
+        ensure_counts(g2);
+        set_dev(g1->m);
+        std::vector<uint32_t> lo, hi;
+        window_ranges(g1->m, windows, n_windows, lo, hi);
+        DevBuf<uint32_t> dlo(n_windows), dhi(n_windows);
+        dlo.upload(lo.data(), n_windows);
+        dhi.upload(hi.data(), n_windows);
+        DevBuf<double> dd(n_windows * 5);
+        DevBuf<uint64_t> ds(n_windows);
+        const uint32_t blocks = (uint32_t)std::min<size_t>((n_windows + 7) / 8, 8u * sm_count(g1->m->device));
+        fm::fm_k_window_hudson<<<blocks, 256, 0, stream()>>>(g1->d_alt, g1->d_cnt, g2->d_alt, g2->d_cnt, dlo.p,
+                                                              dhi.p, (uint32_t)n_windows, dd.p, ds.p);
+        CK(cudaGetLastError());
+        g_launches++;
+        std::vector<double> h(n_windows * 5);
+        dd.download(h.data(), n_windows * 5);
+        if (dxy_unc) ds.download(dxy_unc, n_windows);
+        CK(cudaStreamSynchronize(stream()));
+        for (size_t i = 0; i < n_windows; ++i) {
+            if (num_sum) num_sum[i] = h[i * 5 + 0];
+            if (den_sum) den_sum[i] = h[i * 5 + 1];
+            if (dxy_sum) dxy_sum[i] = h[i * 5 + 2];
+            if (pi1_sum) pi1_sum[i] = h[i * 5 + 3];
+            if (pi2_sum) pi2_sum[i] = h[i * 5 + 4];
+        }
+    });
+}
+
+// ------------------------------------------------------------------------------------ bench hooks
+namespace {
+struct EventPairs {
+    std::vector<cudaEvent_t> ev;
+    ~EventPairs() {
+        for (auto e : ev) cudaEventDestroy(e);
+    }
+    cudaEvent_t next() {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        ev.push_back(e);
+        return e;
+    }
+};
+
+void launch_reduce(const double *pd, int nd, const uint32_t *pu, int nu, const fm::PassGeom &G, double *sd,
+                   uint64_t *su) {
+    const uint32_t s_lo = G.b_lo / fm::kSuperBatches;
+    const uint32_t n_super = (G.b_lo + G.n_batches + fm::kSuperBatches - 1) / fm::kSuperBatches - s_lo;
+    const uint32_t threads = n_super * (uint32_t)(nd + nu);
+    fm::fm_k_reduce_partials<<<(threads + 127) / 128, 128, 0, stream()>>>(pd, nd, pu, nu, G.b_lo, G.n_batches,
+                                                                           s_lo, n_super, sd, su);
+    CK(cudaGetLastError());
+    g_launches++;
+}
+}  // namespace
+
+fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode, const int64_t *mask_iv,
+                             size_t n_mask, int iterations, fm_bench_result *out) {
+    return guarded([&] {
+        if (!groups || !n_groups || !out || iterations < 1) fail(FM_ERR_INVALID_ARG, "bad argument");
+        require_device();
+        std::memset(out, 0, sizeof(*out));
+        fm_matrix *m = groups[0]->m;
+        set_dev(m);
+        const uint32_t V = (uint32_t)m->V;
+        struct PerGroup {
+            fm::PassParams<1> P;
+            DevBuf<double> part_pi, pi, theta, sd;
+            DevBuf<uint32_t> part_u;
+            DevBuf<uint64_t> su;
+        };
+        std::vector<PerGroup> pg(n_groups);
+        DevBuf<int64_t> d_mask;
+        std::vector<int64_t> merged;
+        if (mode == 1 && mask_iv) {
+            merge_intervals(mask_iv, n_mask, merged);
+            d_mask.alloc(std::max<size_t>(merged.size(), 2));
+            d_mask.upload(merged.data(), merged.size());
+        }
+        uint64_t bytes = 0;
+        for (size_t i = 0; i < n_groups; ++i) {
+            fm_group *g = groups[i];
+            if (g->m != m) fail(FM_ERR_INVALID_ARG, "groups must share one matrix");
+            const fm_group *gs[1] = {g};
+            fm::PassGeom G = make_geom(gs, 1, 0, V);
+            const size_t nb = std::max<uint32_t>(G.n_batches, 1);
+            pg[i].part_pi.alloc(nb);
+            pg[i].part_u.alloc(nb * 2);
+            pg[i].sd.alloc(nb / fm::kSuperBatches + 2);
+            pg[i].su.alloc(2 * (nb / fm::kSuperBatches + 2));
+            fm::DivEpilogue e{};
+            e.pos = m->d_pos;
+            e.harmonic = g->d_harm;
+            e.pi_form = FM_PIFORM_COUNTS;
+            e.part_pi = pg[i].part_pi.p;
+            e.part_u = pg[i].part_u.p;
+            bytes += (uint64_t)V * g->wq * 16u * (g->d_called ? 2u : 1u);
+            if (mode == 1) {
+                pg[i].pi.alloc(std::max<uint32_t>(V, 1));
+                pg[i].theta.alloc(std::max<uint32_t>(V, 1));
+                e.pi_out = pg[i].pi.p;
+                e.theta_out = pg[i].theta.p;
+                e.pi_form = FM_PIFORM_COMPONENTS;
+                if (mask_iv) {
+                    e.mask = d_mask.p;
+                    e.n_mask = (uint32_t)(merged.size() / 2);
+                }
+                bytes += (uint64_t)V * 16u;
+            }
+            pg[i].P = fm::PassParams<1>{};
+            pg[i].P.g[0] = planes_of(g);
+            pg[i].P.geom = G;
+            pg[i].P.div = e;
+        }
+        EventPairs evs;
+        std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans;
+        cudaEvent_t t0 = evs.next(), t1 = evs.next();
+        CK(cudaStreamSynchronize(stream()));
+        CK(cudaEventRecord(t0, stream()));
+        for (int it = 0; it < iterations; ++it) {
+            for (size_t i = 0; i < n_groups; ++i) {
+                cudaEvent_t a = evs.next(), b = evs.next();
+                CK(cudaEventRecord(a, stream()));
+                launch_plane_pass<1>(pg[i].P, m->device);
+                CK(cudaEventRecord(b, stream()));
+                spans.emplace_back(a, b);
+                out->plane_launches++;
+                if (pg[i].P.geom.n_batches) {
+                    launch_reduce(pg[i].part_pi.p, 1, pg[i].part_u.p, 2, pg[i].P.geom, pg[i].sd.p, pg[i].su.p);
+                    out->other_launches++;
+                }
+            }
+        }
+        CK(cudaEventRecord(t1, stream()));
+        CK(cudaEventSynchronize(t1));
+        float total = 0.f, plane = 0.f;
+        CK(cudaEventElapsedTime(&total, t0, t1));
+        for (auto &sp : spans) {
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, sp.first, sp.second));
+            plane += t;
+        }
+        out->step_ms_avg = total / (float)iterations;
+        out->plane_ms_avg = spans.empty() ? 0.f : plane / (float)spans.size();
+        out->plane_bytes_per_step = bytes;
+    });
+}
+
+fm_status fm_bench_hudson(fm_group *g1, fm_group *g2, int iterations, fm_bench_result *out) {
+    return guarded([&] {
+        check_pair(g1, g2);
+        if (!out || iterations < 1) fail(FM_ERR_INVALID_ARG, "bad argument");
+        require_device();
+        std::memset(out, 0, sizeof(*out));
+        set_dev(g1->m);
+        const uint32_t V = (uint32_t)g1->m->V;
+        const fm_group *gs[2] = {g1, g2};
+        fm::PassGeom G = make_geom(gs, 2, 0, V);
+        const size_t nb = std::max<uint32_t>(G.n_batches, 1);
+        DevBuf<double> pd(nb * 5), sd(5 * (nb / fm::kSuperBatches + 2));
+        DevBuf<uint32_t> pu(nb * 3);
+        DevBuf<uint64_t> su(3 * (nb / fm::kSuperBatches + 2));
+        fm::HudsonEpilogue e{};
+        e.variant = dense_variant(g1->m);
+        e.part_d = pd.p;
+        e.part_u = pu.p;
+        fm::PassParams<2> P{};
+        P.g[0] = planes_of(g1);
+        P.g[1] = planes_of(g2);
+        P.geom = G;
+        P.hud = e;
+        EventPairs evs;
+        std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans;
+        cudaEvent_t t0 = evs.next(), t1 = evs.next();
+        CK(cudaStreamSynchronize(stream()));
+        CK(cudaEventRecord(t0, stream()));
+        for (int it = 0; it < iterations; ++it) {
+            cudaEvent_t a = evs.next(), b = evs.next();
+            CK(cudaEventRecord(a, stream()));
+            launch_plane_pass<2>(P, g1->m->device);
+            CK(cudaEventRecord(b, stream()));
+            spans.emplace_back(a, b);
+            out->plane_launches++;
+            if (G.n_batches) {
+                launch_reduce(pd.p, 5, pu.p, 3, G, sd.p, su.p);
+                out->other_launches++;
+            }
+        }
+        CK(cudaEventRecord(t1, stream()));
+        CK(cudaEventSynchronize(t1));
+        float total = 0.f, plane = 0.f;
+        CK(cudaEventElapsedTime(&total, t0, t1));
+        for (auto &sp : spans) {
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, sp.first, sp.second));
+            plane += t;
+        }
+        out->step_ms_avg = total / (float)iterations;
+        out->plane_ms_avg = plane / (float)spans.size();
+        out->plane_bytes_per_step = (uint64_t)V * 16u *
+                                    (g1->wq * (g1->d_called ? 2u : 1u) + g2->wq * (g2->d_called ? 2u : 1u));
+    });
+}
+
+}  // extern "C"

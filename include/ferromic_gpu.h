@@ -1,0 +1,224 @@
+/*
+ * ferromic_gpu.h -- C ABI of the B200 (sm_100a) implementation of ferromic's per-site
+ * population-genetics estimators (reference: SauersML/ferromic, src/stats.rs).
+ *
+ * This is the drop-in boundary: the Rust crate (src/stats.rs entry points, src/lib.rs PyO3
+ * wrappers, src/process.rs CLI call sites) binds exactly these symbols through `extern "C"`
+ * (see INTEGRATION.md for the build.rs / gpu_ffi.rs stubs).  Plain pointers and sizes only.
+ *
+ * Conventions
+ *  - every function returns an fm_status; fm_last_error() gives the thread-local message.
+ *    FM_ERR_INVALID_REGION / FM_ERR_PARSE map to VcfError::InvalidRegion / VcfError::Parse
+ *    (process.rs:631-640); nothing ever aborts or throws across the boundary.
+ *  - host buffers are owned by the caller and are not retained after the call returns.
+ *  - Option<f64> results are returned as a value plus a flag word (bit set = Some); per-site
+ *    Option<f64> arrays use NaN for None (no Some value on this path can be NaN).
+ *  - positions are 0-based on input; per-site outputs report position+1 (stats.rs:747,3004,4746).
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *    FM_ERR_NO_DEVICE.
+ *  - handles are thread-safe (immutable device buffers; lazily cached summaries are guarded).
+ */
+#ifndef FERROMIC_GPU_H
+#define FERROMIC_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int fm_status;
+#define FM_OK 0
+#define FM_ERR_INVALID_REGION 1 /* VcfError::InvalidRegion */
+#define FM_ERR_PARSE 2          /* VcfError::Parse */
+#define FM_ERR_INVALID_ARG 3
+#define FM_ERR_CUDA 4
+#define FM_ERR_UNSUPPORTED 5
+#define FM_ERR_NO_DEVICE 6
+
+typedef struct fm_matrix fm_matrix; /* device-resident DenseGenotypeMatrix (stats.rs:249-331) */
+typedef struct fm_group fm_group;   /* one population's haplotypes repacked into bitplanes      */
+typedef struct fm_partition fm_partition; /* G-group partition for Weir & Cockerham (stats.rs:1093-1150) */
+
+/* ---- library / device ---- */
+const char *fm_last_error(void);
+const char *fm_version(void);
+fm_status fm_device_count(int *count);
+fm_status fm_set_device(int device); /* device used by handles created afterwards on this thread */
+fm_status fm_synchronize(void);
+
+/* ---- matrix: replaces DenseGenotypeMatrix::new / ::from_variants (stats.rs:261-296, 339-500) ----
+ * data[v*S*ploidy + s*ploidy + side] = allele index; missing = packed bitmap, 1 bit per entry,
+ * LSB-first in u64 words (stats.rs:1298-1302), or NULL.  positions may be NULL (then 0..V-1).
+ * The u8 matrix is uploaded once and stays resident; groups are repacked from it on device. */
+fm_status fm_matrix_create(const uint8_t *data, const uint64_t *missing_or_null, size_t n_variants,
+                           size_t n_samples, size_t ploidy, uint8_t max_allele,
+                           const int64_t *positions_or_null, fm_matrix **out);
+/* Same, but data/missing already live in device memory of the current device (not copied, not
+ * freed; must outlive the handle).  positions is a host pointer. */
+fm_status fm_matrix_create_device(const uint8_t *d_data, const uint64_t *d_missing_or_null,
+                                  size_t n_variants, size_t n_samples, size_t ploidy,
+                                  uint8_t max_allele, const int64_t *positions_or_null,
+                                  fm_matrix **out);
+fm_status fm_matrix_retain(fm_matrix *m);
+fm_status fm_matrix_release(fm_matrix *m);
+fm_status fm_matrix_info(const fm_matrix *m, size_t *n_variants, size_t *n_samples, size_t *ploidy,
+                         uint8_t *max_allele, int *has_missing);
+
+/* ---- group: replaces DenseMembership::build (stats.rs:1251-1284) + the per-group gather ----
+ * haplotypes are (sample index, side 0=Left/1=Right); duplicates are counted once, out-of-range
+ * samples are dropped, Right is dropped when ploidy <= 1 -- exactly as the reference.  The
+ * group's columns are repacked on device into an allele bitplane and (when the matrix has a
+ * missing bitmap) a called bitplane. */
+fm_status fm_group_create(fm_matrix *m, const uint64_t *sample_idx, const uint8_t *side, size_t n,
+                          fm_group **out);
+fm_status fm_group_release(fm_group *g);
+fm_status fm_group_capacity(const fm_group *g, size_t *haplotype_capacity);
+
+/* build_dense_population_summary (stats.rs:1367-1470): alt/called may be NULL.  The summary is
+ * computed once per group (the reference caches it in a OnceLock, lib.rs:738,777-789).
+ * uncallable_lt2 = #{sites with called < 2} (used by stats.rs:1512-1517). */
+fm_status fm_group_summary(fm_group *g, uint32_t *alt_out_or_null, uint32_t *called_out_or_null,
+                           uint64_t *segregating_sites, double *pi_sum, uint64_t *uncallable_lt2);
+
+/* count_segregating_sites_for_population (stats.rs:3831-3851) for a dense ploidy-2 context. */
+fm_status fm_group_segregating_sites(fm_group *g, uint64_t *out);
+
+/* calculate_pi_for_population (stats.rs:4599-4614).  path: FM_PI_SUMMARY follows
+ * calculate_pi_from_summary (:1480-1542); FM_PI_DENSE follows calculate_pi_dense(_biallelic)
+ * (:4434-4597); FM_PI_SPARSE follows calculate_pi (:4317-4432, per-site form :2723-2733) and is
+ * meant for matrices built with from_variants semantics. */
+#define FM_PI_SUMMARY 0
+#define FM_PI_DENSE 1
+#define FM_PI_SPARSE 2
+fm_status fm_group_pi(fm_group *g, int64_t sequence_length, int path, size_t raw_haplotype_count,
+                      double *out);
+
+/* harmonic (stats.rs:4234-4240) / calculate_watterson_theta (stats.rs:4243-4307); host scalars. */
+fm_status fm_harmonic(size_t n, double *out);
+fm_status fm_watterson_theta(size_t seg_sites, size_t n, int64_t sequence_length, double *out);
+
+/* calculate_per_site_diversity (stats.rs:4628-4806) on the group's matrix (from_variants
+ * missingness == the reference's sparse semantics).  region is 0-based inclusive; mask intervals
+ * are 0-based half-open pairs [s,e) (mask_iv_or_null == NULL <=> None); filtered positions are
+ * 0-based.  Outputs are caller-allocated with room for `capacity` sites; *n_out receives the
+ * number of variants inside the region (in variant order).  raw_haplotype_count is
+ * haplotypes_in_group.len() before de-duplication (the <2 guard at :4675 uses it). */
+fm_status fm_per_site_diversity(fm_group *g, size_t raw_haplotype_count, int64_t region_start,
+                                int64_t region_end, const int64_t *mask_iv_or_null, size_t n_mask,
+                                const int64_t *filtered_pos, size_t n_filtered, int64_t *pos_out,
+                                double *pi_out, double *theta_out, size_t capacity, size_t *n_out);
+
+/* ---- Hudson FST / Dxy (stats.rs:2403-2611, 2969-3278, 3435-3641) ---- */
+typedef struct {
+    double fst, d_xy, pi_pop1, pi_pop2, pi_xy_avg;
+    uint32_t some; /* bit0 fst, bit1 d_xy, bit2 pi_pop1, bit3 pi_pop2, bit4 pi_xy_avg */
+} fm_hudson_outcome;
+
+/* SoA per-site outputs (any pointer may be NULL); Option<f64> => NaN for None. */
+typedef struct {
+    int64_t *position; /* 1-based */
+    double *fst, *d_xy, *pi_pop1, *pi_pop2, *num_component, *den_component;
+    uint32_t *n1_called, *n2_called;
+    size_t capacity;
+} fm_hudson_sites;
+
+/* Which reference code path the call mirrors (stats.rs:3473-3503): */
+#define FM_HUDSON_SUMMARIES 0 /* both contexts carry dense summaries (Python Population path) */
+#define FM_HUDSON_DENSE 1     /* shared dense matrix, no summaries (CLI contexts)             */
+#define FM_HUDSON_SPARSE 2    /* sparse per-site path (always taken when a region is given)   */
+
+/* calculate_hudson_fst_for_pair_core (stats.rs:3435-3599).  g1 and g2 must share one matrix.
+ * has_region != 0 selects calculate_hudson_fst_for_pair_with_sites (per-site values for variants
+ * inside [region_start, region_end], FST from the sparse per-site form); the auxiliary pi/Dxy of
+ * the outcome follow aux_path (FM_HUDSON_SUMMARIES / _DENSE / _SPARSE).  raw_n1/raw_n2 are the
+ * un-deduplicated haplotype list lengths.  sites_or_null->capacity bounds the per-site outputs. */
+fm_status fm_hudson_pair(fm_group *g1, fm_group *g2, int64_t sequence_length1,
+                         int64_t sequence_length2, int path, int has_region, int64_t region_start,
+                         int64_t region_end, size_t raw_n1, size_t raw_n2, fm_hudson_outcome *out,
+                         fm_hudson_sites *sites_or_null, size_t *n_sites);
+
+/* calculate_d_xy_hudson (stats.rs:2403-2524) */
+fm_status fm_hudson_dxy(fm_group *g1, fm_group *g2, int64_t sequence_length1,
+                        int64_t sequence_length2, int path, size_t raw_n1, size_t raw_n2,
+                        double *d_xy, int *is_some);
+
+/* ---- Weir & Cockerham (stats.rs:675-934, 1814-2374) ----
+ * left/right[n_samples] give the group index (0..G-1) of each sample's Left/Right haplotype or
+ * 0xFFFF (SubpopulationMembership, stats.rs:1093-1150); labels/pair keys stay on the host side.
+ * The matrix must carry from_variants missingness (the reference's W&C path is sparse-only). */
+typedef struct {
+    int32_t state; /* 0 Calculable, 1 ComponentsYieldIndeterminateRatio,
+                      2 NoInterPopulationVariance, 3 InsufficientDataForEstimation */
+    double value;  /* FST when state == 0 (may be +-inf), NaN otherwise */
+    double sum_a, sum_b;
+    uint64_t sites;
+} fm_fst_estimate;
+
+fm_status fm_partition_create(fm_matrix *m, const uint16_t *left, const uint16_t *right,
+                              size_t n_samples, size_t n_groups, fm_partition **out);
+fm_status fm_partition_release(fm_partition *p);
+
+/* Region W&C: overall estimate, per-pair estimates (pair order i<j, n_groups*(n_groups-1)/2
+ * entries; pair_present[i]=0 when the key never appears in the reference's maps), and optional
+ * per-site outputs for the variants inside the region (capacity entries each):
+ *   site_pos (1-based), site_state, site_a, site_b, site_pop_sizes [capacity * n_groups],
+ *   pair_a / pair_b [capacity * n_pairs] (per-site pairwise components). */
+fm_status fm_wc_fst(fm_partition *p, int64_t region_start, int64_t region_end,
+                    fm_fst_estimate *overall, fm_fst_estimate *pairs, uint8_t *pair_present,
+                    int64_t *site_pos, int32_t *site_state, double *site_a, double *site_b,
+                    uint32_t *site_pop_sizes, double *pair_a, double *pair_b, size_t capacity,
+                    size_t *n_sites);
+
+/* ---- calculate_adjusted_sequence_length (stats.rs:3644-3736); host integer arithmetic ----
+ * region is 1-based inclusive; allow/mask are 0-based half-open pairs; NULL <=> None. */
+fm_status fm_adjusted_sequence_length(int64_t region_start, int64_t region_end,
+                                      const int64_t *allow_or_null, size_t n_allow,
+                                      const int64_t *mask_or_null, size_t n_mask, int64_t *out);
+
+/* ---- windowed region summaries (K5: segmented reductions over site ranges) ----
+ * windows are 0-based inclusive [start,end] pairs over positions (must be sorted ascending in the
+ * matrix).  Per window: #variants, segregating sites, sum of per-site pi, #sites with called<2. */
+fm_status fm_group_window_sums(fm_group *g, const int64_t *windows, size_t n_windows,
+                               uint64_t *n_variants, uint64_t *seg_sites, double *pi_sum,
+                               uint64_t *uncallable_lt2);
+/* Per window Hudson component sums (from the two groups' cached summaries):
+ * sum num, sum den, sum dxy (all callable), #uncallable, sum pi1, sum pi2. */
+fm_status fm_hudson_window_sums(fm_group *g1, fm_group *g2, const int64_t *windows, size_t n_windows,
+                                double *num_sum, double *den_sum, double *dxy_sum,
+                                uint64_t *dxy_uncallable, double *pi1_sum, double *pi2_sum);
+
+/* ---- instrumentation for bench.py (device timings of the last call, milliseconds) ---- */
+typedef struct {
+    float h2d_ms, repack_ms, stats_ms, reduce_ms, d2h_ms;
+    uint64_t stats_launches;   /* launches of the plane-streaming kernels */
+    uint64_t kernel_launches;  /* all kernel launches since the counters were reset */
+    uint64_t stats_bytes;      /* algorithmic plane bytes streamed by the last stats kernel */
+} fm_timings;
+fm_status fm_timings_reset(void);
+fm_status fm_timings_get(fm_timings *out);
+
+/* Device-resident benchmark of the hot kernels (no host transfer inside the timed region).
+ * One "step" streams the planes of every listed group once with the fused diversity epilogue
+ * (mode 0: counts + summary partials; mode 1: + per-site pi/theta tracks with the mask applied)
+ * and folds the per-batch partials on device.  Timing uses CUDA events on the launching stream:
+ * step_ms_avg brackets all `iterations` steps, plane_ms_avg is the mean duration of one
+ * plane-pass launch (events around every launch). */
+typedef struct {
+    float step_ms_avg;
+    float plane_ms_avg;
+    uint64_t plane_launches;       /* plane-pass launches inside the timed region */
+    uint64_t other_launches;       /* partial-reduction launches inside the timed region */
+    uint64_t plane_bytes_per_step; /* algorithmic bytes: plane rows read + per-site outputs written */
+} fm_bench_result;
+fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
+                             const int64_t *mask_iv_or_null, size_t n_mask, int iterations,
+                             fm_bench_result *out);
+/* Same for the fused two-group Hudson pass (K3). */
+fm_status fm_bench_hudson(fm_group *g1, fm_group *g2, int iterations, fm_bench_result *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FERROMIC_GPU_H */

@@ -1,0 +1,290 @@
+"""GPU parity tests: the CUDA path (through the C-ABI library and the Python mirror) against the
+CPU oracle on the same seeded inputs.  Integer outputs are compared bit-exactly; FP64 outputs
+within REL (the north-star tolerance is 1e-9 relative; per-site values normally agree to the
+last bit because the kernels keep the reference's operation order)."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as orc
+from tests.synth import both_sides, make_cohort
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-9
+
+
+def fm():
+    import ferromic_b200 as m
+    return m
+
+
+def close(a, b, rel=REL):
+    if a is None or b is None:
+        return a is None and b is None
+    if isinstance(a, float) and math.isnan(a):
+        return isinstance(b, float) and math.isnan(b)
+    if math.isinf(a) or math.isinf(b):
+        return a == b
+    return abs(a - b) <= rel * max(abs(a), abs(b)) + 1e-300
+
+
+def assert_arrays_close(a, b, rel=REL):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape
+    assert np.array_equal(np.isnan(a), np.isnan(b)), "NaN/None pattern differs"
+    m = ~np.isnan(a)
+    assert np.all(np.abs(a[m] - b[m]) <= rel * np.maximum(np.abs(a[m]), np.abs(b[m])) + 1e-300)
+
+
+def dense_pair(g, positions):
+    """Oracle dense matrix + device matrix with from_numpy (dense) semantics."""
+    from ferromic_b200.api import _Matrix
+    vs, d = orc.from_numpy(g, positions)
+    miss = (g < 0)
+    alle = np.where(miss, 0, g).astype(np.uint8)
+    m = _Matrix(alle, miss, positions, max_allele=d.max_allele)
+    return vs, d, m
+
+
+# ------------------------------------------------------------------ K1 + K2: counts / summary
+@pytest.mark.parametrize("n_samples,missing", [(1, 0.0), (3, 0.2), (40, 0.1), (64, 0.0), (65, 0.05),
+                                               (700, 0.02), (2504, 0.0), (2504, 0.01)])
+def test_summary_matches_oracle(n_samples, missing):
+    V = 4100 if n_samples < 1000 else 700
+    g, pos, _ = make_cohort(V, n_samples, missing_rate=missing, seed=7 + n_samples)
+    vs, d, m = dense_pair(g, pos)
+    rng = np.random.default_rng(n_samples)
+    groups = [both_sides(range(n_samples)),
+              [(int(s), int(rng.integers(0, 2))) for s in rng.choice(n_samples, max(1, n_samples // 2), replace=False)],
+              both_sides(range(n_samples))[::3] + [(0, 0), (0, 0), (n_samples + 5, 1)]]  # dups + out of range
+    for haps in groups:
+        ref = orc.build_summary(d, haps)
+        got = m.group(haps).summary(want_arrays=True)
+        assert np.array_equal(got["alt"], ref.alt)
+        assert np.array_equal(got["called"], ref.called)
+        assert got["segregating_sites"] == ref.seg
+        assert got["uncallable_lt2"] == int((ref.called < 2).sum())
+        assert close(got["pi_sum"], ref.pi_sum, 1e-12)
+        assert m.group(haps).capacity == ref.capacity
+
+
+def test_wide_rows_chunked_mode():
+    # > 12 KB per plane row forces the column-chunked path (lps == 32, n_chunks > 1)
+    g, pos, _ = make_cohort(70, 52000, missing_rate=0.01, seed=3)
+    vs, d, m = dense_pair(g, pos)
+    haps = both_sides(range(52000))
+    ref = orc.build_summary(d, haps)
+    got = m.group(haps).summary(want_arrays=True)
+    assert np.array_equal(got["alt"], ref.alt) and np.array_equal(got["called"], ref.called)
+    assert got["segregating_sites"] == ref.seg and close(got["pi_sum"], ref.pi_sum, 1e-12)
+
+
+@pytest.mark.parametrize("missing", [0.0, 0.15])
+def test_pi_paths_match_oracle(missing):
+    g, pos, pops = make_cohort(3000, 30, missing_rate=missing, seed=11)
+    vs, d, m = dense_pair(g, pos)
+    L = int(pos[-1] - pos[0] + 1)
+    from ferromic_b200 import _lib
+    for haps in (both_sides(pops[0]), both_sides(range(30)), [(2, 0)], []):
+        grp = m.group(haps)
+        # summary path (lib.rs:777-789 -> stats.rs:1476-1542)
+        summ = orc.build_summary(d, haps)
+        ref = orc.pi_for_population(orc.Pop(haps, vs, 30, L, dense=d, summary=summ))
+        assert close(grp.pi(L, _lib.FM_PI_SUMMARY), ref, 1e-12)
+        # dense path (CLI contexts: process.rs:970-983 -> stats.rs:4534-4597)
+        ref = orc.pi_for_population(orc.Pop(haps, vs, 30, L, dense=d))
+        assert close(grp.pi(L, _lib.FM_PI_DENSE), ref, 1e-12)
+    for Lx, exp in ((-5, 0.0), (0, math.inf)):
+        assert m.group(both_sides(pops[0])).pi(Lx, _lib.FM_PI_SUMMARY) == exp
+
+
+def test_population_api_matches_oracle_paths():
+    F = fm()
+    for missing in (0.0, 0.1):
+        g, pos, pops = make_cohort(2500, 24, missing_rate=missing, seed=5)
+        L = int(pos[-1] - pos[0] + 1)
+        haps = both_sides(range(24))
+        vs, d = orc.from_numpy(g, pos)
+        pop = F.Population.from_numpy("all", g, pos, haps, L, sample_names=[f"s{i}" for i in range(24)])
+        summ = orc.build_summary(d, haps)
+        ref_pop = orc.Pop(haps, vs, 24, L, dense=d, summary=summ)
+        assert pop.segregating_sites() == orc.count_segregating_sites_for_population(ref_pop)
+        assert close(pop.nucleotide_diversity(), orc.pi_for_population(ref_pop), 1e-12)
+        sub = pop.with_haplotypes("p1", both_sides(pops[0]))
+        summ1 = orc.build_summary(d, both_sides(pops[0]))
+        ref1 = orc.Pop(both_sides(pops[0]), vs, 24, L, dense=d, summary=summ1)
+        assert sub.segregating_sites() == orc.count_segregating_sites_for_population(ref1)
+        assert close(sub.nucleotide_diversity(), orc.pi_for_population(ref1), 1e-12)
+        # sparse free functions
+        variants = [{"position": int(p), "genotypes": [None if (row < 0).any() else row.tolist() for row in site]}
+                    for p, site in zip(pos[:400], g[:400])]
+        ovs = orc.variants_from_python(variants)
+        assert F.segregating_sites(variants) == orc.count_segregating_sites(ovs)
+        assert close(F.nucleotide_diversity(variants, both_sides(pops[1]), 1000),
+                     orc.pi_sparse(ovs, both_sides(pops[1]), 1000), 1e-12)
+
+
+# ------------------------------------------------------------------ per-site tracks
+@pytest.mark.parametrize("missing", [0.0, 0.2])
+def test_per_site_diversity_matches_oracle(missing):
+    F = fm()
+    g, pos, pops = make_cohort(5000, 20, missing_rate=missing, seed=21)
+    g[:, :, 1][g[:, :, 0] < 0] = -1  # whole-sample missingness (sparse semantics)
+    g[:, :, 0][g[:, :, 1] < 0] = -1
+    vs, _ = orc.from_numpy(g, pos)
+    from ferromic_b200.api import _Variants
+    fvs = _Variants(vs.positions, vs.gt)
+    haps = both_sides(pops[0]) + [(3, 0)]
+    region = (int(pos[100]), int(pos[4700]))
+    mask = [(int(pos[500]), int(pos[650])), (int(pos[600]), int(pos[700]) + 1), (int(pos[3000]), int(pos[3000]) + 1)]
+    filtered = [int(pos[200]), int(pos[201]), int(pos[4000]), 123456789]
+    for kw in (dict(), dict(mask=mask), dict(mask=mask, filtered_positions=filtered), dict(mask=[])):
+        rp, rpi, rth = orc.per_site_diversity(vs, haps, region, filtered=kw.get("filtered_positions", ()),
+                                              mask=kw.get("mask"))
+        gp, gpi, gth = F.per_site_diversity_arrays(fvs, haps, region, **kw)
+        assert np.array_equal(gp, rp)
+        assert_arrays_close(gpi, rpi, 1e-12)
+        assert_arrays_close(gth, rth, 1e-12)
+    # region = None -> min..max positions; fewer than two haplotypes -> ValueError (lib.rs:1653)
+    gp, _, _ = F.per_site_diversity_arrays(fvs, haps, None)
+    assert len(gp) == 5000
+    with pytest.raises(ValueError):
+        F.per_site_diversity(fvs, [(0, 0)], region)
+    assert len(F.per_site_diversity_arrays(fvs, haps, (10**12, 10**12 + 5))[0]) == 0
+
+
+# ------------------------------------------------------------------ Hudson
+def _outcome_close(got, ref):
+    for k in ("fst", "d_xy", "pi_pop1", "pi_pop2", "pi_xy_avg"):
+        assert close(getattr(got, k), ref[k], REL), (k, getattr(got, k), ref[k])
+
+
+@pytest.mark.parametrize("missing", [0.0, 0.12])
+def test_hudson_summaries_path(missing):
+    F = fm()
+    g, pos, pops = make_cohort(6000, 32, missing_rate=missing, seed=31)
+    L = int(pos[-1] - pos[0] + 1)
+    names = [f"s{i}" for i in range(32)]
+    base = F.Population.from_numpy("all", g, pos, both_sides(range(32)), L, sample_names=names)
+    p1 = base.with_haplotypes("p1", both_sides(pops[0]))
+    p2 = base.with_haplotypes("p2", both_sides(pops[1]))
+    vs, d = orc.from_numpy(g, pos)
+    o1 = orc.Pop(both_sides(pops[0]), vs, 32, L, dense=d, summary=orc.build_summary(d, both_sides(pops[0])))
+    o2 = orc.Pop(both_sides(pops[1]), vs, 32, L, dense=d, summary=orc.build_summary(d, both_sides(pops[1])))
+    rc, ref, _ = orc.hudson_pair(o1, o2)
+    assert rc == 0
+    _outcome_close(F.hudson_fst(p1, p2), ref)
+    rc, rd = orc.dxy_hudson(o1, o2)
+    assert close(F.hudson_dxy(p1, p2).d_xy, rd)
+    # with a region: per-site sparse values + FST, auxiliary pi/Dxy from the summaries
+    region = (int(pos[50]), int(pos[5000]))
+    rc, ref, rsites = orc.hudson_pair(o1, o2, region=region)
+    got, gsites = F.hudson_fst_with_sites(p1, p2, region)
+    _outcome_close(got, ref)
+    assert len(gsites) == len(rsites)
+    for a, b in zip(gsites[::37], rsites[::37]):
+        assert a.position == b["position"] and a.n1_called == b["n1_called"] and a.n2_called == b["n2_called"]
+        for k in ("fst", "d_xy", "pi_pop1", "pi_pop2", "numerator_component", "denominator_component"):
+            assert close(getattr(a, k), b[k], 1e-12), k
+
+
+@pytest.mark.parametrize("missing", [0.0, 0.1])
+def test_hudson_dense_and_sparse_paths_c_abi(missing):
+    """CLI-style contexts (dense matrix, no summaries: process.rs:3191-3215) and sparse contexts."""
+    import ctypes as C
+    from ferromic_b200 import _lib
+    g, pos, pops = make_cohort(3000, 16, missing_rate=missing, seed=41)
+    g[:, :, 1][g[:, :, 0] < 0] = -1
+    g[:, :, 0][g[:, :, 1] < 0] = -1
+    vs, _ = orc.from_numpy(g, pos)
+    d = orc.dense_from_variants(vs, 16)  # from_variants: bitmap always present
+    from ferromic_b200.api import _Matrix
+    m = _Matrix(np.where(g < 0, 0, g).astype(np.uint8), g < 0, pos, always_bitmap=True)
+    L = int(pos[-1] - pos[0] + 1)
+    h1, h2 = both_sides(pops[0]), both_sides(pops[1])
+    g1, g2 = m.group(h1), m.group(h2)
+    for path, o1, o2 in ((_lib.FM_HUDSON_DENSE, orc.Pop(h1, vs, 16, L, dense=d), orc.Pop(h2, vs, 16, L, dense=d)),
+                         (_lib.FM_HUDSON_SPARSE, orc.Pop(h1, vs, 16, L), orc.Pop(h2, vs, 16, L))):
+        for region in (None, (int(pos[10]), int(pos[2500]))):
+            rc, ref, rsites = orc.hudson_pair(o1, o2, region=region)
+            out = _lib.HudsonOutcome()
+            V = len(pos)
+            arrs = [np.zeros(V) for _ in range(6)]
+            p_ = np.zeros(V, dtype=np.int64)
+            n1 = np.zeros(V, dtype=np.uint32)
+            n2 = np.zeros(V, dtype=np.uint32)
+            hs = _lib.HudsonSites(*[a.ctypes.data for a in [p_] + arrs + [n1, n2]], V)
+            n = C.c_size_t()
+            rs, re = region if region else (0, 0)
+            _lib.check(_lib.lib().fm_hudson_pair(g1.handle, g2.handle, L, L, path, int(region is not None), rs, re,
+                                                 len(h1), len(h2), C.byref(out), C.byref(hs), C.byref(n)))
+            for bit, k in enumerate(("fst", "d_xy", "pi_pop1", "pi_pop2", "pi_xy_avg")):
+                got = getattr(out, k) if (out.some >> bit) & 1 else None
+                assert close(got, ref[k]), (path, region, k, got, ref[k])
+            assert n.value == len(rsites)
+            k = n.value
+            assert np.array_equal(p_[:k], [s["position"] for s in rsites])
+            assert np.array_equal(n1[:k], [s["n1_called"] for s in rsites])
+            for arr, key in zip(arrs, ("fst", "d_xy", "pi_pop1", "pi_pop2", "numerator_component",
+                                       "denominator_component")):
+                refv = np.array([np.nan if s[key] is None else s[key] for s in rsites])
+                assert_arrays_close(arr[:k], refv, 1e-12)
+
+
+def test_hudson_error_behaviour():
+    F = fm()
+    g, pos, pops = make_cohort(50, 8, seed=2)
+    names = [f"s{i}" for i in range(8)]
+    a = F.Population.from_numpy("a", g, pos, both_sides(pops[0]), 100, sample_names=names)
+    b = F.Population.from_numpy("b", g, pos, both_sides(pops[1]), 200, sample_names=names)
+    with pytest.raises(ValueError, match="Parse"):
+        F.hudson_fst(a, b)  # sequence length mismatch (stats.rs:3445-3450)
+    c = F.Population.from_numpy("c", g, pos + 1, both_sides(pops[1]), 100, sample_names=names)
+    with pytest.raises(ValueError, match="Parse"):
+        F.hudson_fst(a, c)  # incompatible variant positions (stats.rs:3451-3455)
+    assert F.hudson_fst_sites(a, c, (0, 10**6)) == []  # stats.rs:3027-3034
+    with pytest.raises(ValueError):
+        F.Population("demo", [], [], 0)
+
+
+# ------------------------------------------------------------------ windows (K5)
+def test_window_sums_match_per_site_oracle():
+    import ctypes as C
+    from ferromic_b200 import _lib
+    g, pos, pops = make_cohort(20000, 12, missing_rate=0.05, seed=51)
+    vs, d, m = dense_pair(g, pos)
+    h1, h2 = both_sides(pops[0]), both_sides(pops[1])
+    g1, g2 = m.group(h1), m.group(h2)
+    edges = np.arange(int(pos[0]), int(pos[-1]) + 1, 10_000)
+    windows = np.array([(int(s), int(s) + 9_999) for s in edges], dtype=np.int64)
+    nw = len(windows)
+    nv = np.zeros(nw, dtype=np.uint64); seg = np.zeros(nw, dtype=np.uint64); unc = np.zeros(nw, dtype=np.uint64)
+    pis = np.zeros(nw)
+    _lib.check(_lib.lib().fm_group_window_sums(g1.handle, windows.ctypes.data, nw, nv.ctypes.data, seg.ctypes.data,
+                                               pis.ctypes.data, unc.ctypes.data))
+    s1, s2 = orc.build_summary(d, h1), orc.build_summary(d, h2)
+    for w, (ws, we) in enumerate(windows):
+        sel = (pos >= ws) & (pos <= we)
+        a, c = s1.alt[sel].astype(np.int64), s1.called[sel].astype(np.int64)
+        assert nv[w] == sel.sum()
+        assert seg[w] == int(((c >= 2) & (a > 0) & (a < c)).sum())
+        assert unc[w] == int((c < 2).sum())
+        ok = c >= 2
+        n = c[ok].astype(np.float64); al = a[ok].astype(np.float64); rf = n - al
+        ref = float(np.sum(n / (n - 1.0) * (1.0 - (rf * rf + al * al) / (n * n))))
+        assert close(float(pis[w]), ref, 1e-10)
+    num = np.zeros(nw); den = np.zeros(nw); dxy = np.zeros(nw); p1 = np.zeros(nw); p2 = np.zeros(nw)
+    sk = np.zeros(nw, dtype=np.uint64)
+    _lib.check(_lib.lib().fm_hudson_window_sums(g1.handle, g2.handle, windows.ctypes.data, nw, num.ctypes.data,
+                                                den.ctypes.data, dxy.ctypes.data, sk.ctypes.data, p1.ctypes.data,
+                                                p2.ctypes.data))
+    for w, (ws, we) in enumerate(windows[:6]):
+        sel = np.nonzero((pos >= ws) & (pos <= we))[0]
+        sub1 = orc.Summary(s1.alt[sel], s1.called[sel], s1.capacity, 0, 0.0)
+        sub2 = orc.Summary(s2.alt[sel], s2.called[sel], s2.capacity, 0, 0.0)
+        L = 10_000
+        rc, ref, _ = orc.hudson_pair(orc.Pop(h1, None, 12, L, summary=sub1), orc.Pop(h2, None, 12, L, summary=sub2))
+        fst = num[w] / den[w] if den[w] > 1e-12 else None
+        assert close(fst, ref["fst"], 1e-10)
