@@ -320,7 +320,10 @@ def run_ours(args):
             traffic = None
     roofline = {"bound": "hbm", "kernel": "fm_k_plane_pass<1>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0, "peak_source": peak_src,
-                "traffic": traffic, "bytes_per_launch": plane_launch_bytes, "ms_per_launch": res.plane_ms_avg}
+                "traffic": traffic, "bytes_per_launch": plane_launch_bytes, "ms_per_launch": res.plane_ms_avg,
+                "per_group": [{"haplotypes": len(h), "ms": res.group_ms_avg[i],
+                               "GBps": res.group_bytes[i] / (res.group_ms_avg[i] * 1e-3) / 1e9}
+                              for i, h in enumerate((g0, g1))]}
 
     for g in groups:
         L.fm_group_release(g)

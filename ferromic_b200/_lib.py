@@ -41,7 +41,8 @@ class Timings(C.Structure):
 
 class BenchResult(C.Structure):
     _fields_ = [("step_ms_avg", C.c_float), ("plane_ms_avg", C.c_float), ("plane_launches", C.c_uint64),
-                ("other_launches", C.c_uint64), ("plane_bytes_per_step", C.c_uint64)]
+                ("other_launches", C.c_uint64), ("plane_bytes_per_step", C.c_uint64),
+                ("group_ms_avg", C.c_float * 8), ("group_bytes", C.c_uint64 * 8)]
 
 
 EXPORTS = [

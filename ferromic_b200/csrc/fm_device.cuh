@@ -48,6 +48,11 @@ __device__ __forceinline__ void fm_mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!fm_mbar_try_wait(bar, parity)) {
     }
 }
+__device__ __forceinline__ uint4 fm_lds128(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
 __device__ __forceinline__ uint32_t fm_popc4(const uint4 &v) {
     return __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
 }

@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -175,7 +176,7 @@ struct fm_group {
     uint32_t wq = 0;  // uint4 per plane row
     uint4 *d_allele = nullptr;
     uint4 *d_called = nullptr;
-    double *d_harm = nullptr;  // H[0..n]
+    double *d_tab = nullptr;   // 3 x (n+1) doubles: 1/k, k/(k-1), 1/H_{k-1}
     std::mutex mu;
     bool have_counts = false;
     uint32_t *d_alt = nullptr, *d_cnt = nullptr;
@@ -203,10 +204,12 @@ void site_range(const fm_matrix *m, int64_t rs, int64_t re, uint32_t &lo, uint32
     if (hi < lo) hi = lo;
 }
 
-struct Geom {
-    fm::PassGeom g;
-    size_t smem;
-};
+uint32_t env_u32(const char *name, uint32_t dflt) {
+    const char *v = getenv(name);
+    if (!v || !*v) return dflt;
+    const long x = strtol(v, nullptr, 10);
+    return x > 0 ? (uint32_t)x : dflt;
+}
 
 fm::PassGeom make_geom(const fm_group *const *gs, int ng, uint32_t v_lo, uint32_t v_hi) {
     fm::PassGeom G{};
@@ -217,16 +220,39 @@ fm::PassGeom make_geom(const fm_group *const *gs, int ng, uint32_t v_lo, uint32_
         planes += p;
         max_wq = std::max(max_wq, gs[i]->wq);
     }
-    uint32_t lps = 1;
-    while (lps < 32 && (uint64_t)row_bytes * (32 / lps) > fm::kStageBytes) lps <<= 1;
-    G.lps = lps;
+    static const uint32_t step_target = env_u32("FM_STEP_BYTES", fm::kStepBytesTarget);
+    static const uint32_t warp_smem = std::min(env_u32("FM_WARP_SMEM", fm::kWarpSmemBytes), fm::kWarpSmemBytes);
+    static const uint32_t force_lg = env_u32("FM_FORCE_LG", 99);
+    G.warp_smem_bytes = warp_smem;
+    static const uint32_t dbg = env_u32("FM_DEBUG", 0);
+    G.debug = dbg;
+    // lanes per site: enough lanes to cover a row's uint4 columns (quarter-warps then read
+    // contiguous 128-byte spans), capped so that at least two pipeline stages fit.
+    uint32_t lg = 0;
+    while ((1u << lg) < std::min(max_wq, 8u)) ++lg;
+    if (force_lg <= 4) lg = force_lg;
+    while (lg < 5 && (uint64_t)row_bytes * (32u >> lg) * 2 > warp_smem) ++lg;
+    G.lps_log2 = lg;
+    G.lps = 1u << lg;
+    G.rounds = 1;
     G.n_chunks = 1;
     G.cq = max_wq;
-    if (lps == 32) {
-        const uint32_t cq_max = fm::kStageBytes / (16u * planes);
-        G.cq = std::min(max_wq, cq_max);
-        G.n_chunks = (max_wq + G.cq - 1) / G.cq;
+    uint32_t step_bytes;
+    if (lg < 5) {
+        // several rounds of (32/lps) sites per step while the step stays near the target size
+        const uint32_t round_bytes = row_bytes * (32u >> lg);
+        while (G.rounds * 2 <= G.lps && round_bytes * G.rounds * 2 <= step_target) G.rounds *= 2;
+        step_bytes = round_bytes * G.rounds;
+    } else {
+        if (row_bytes * 2 > warp_smem) {  // a single row does not fit twice: chunk its columns
+            G.cq = std::max(1u, step_target / (16u * planes));
+            G.n_chunks = (max_wq + G.cq - 1) / G.cq;
+        }
+        step_bytes = G.cq * 16u * planes;
     }
+    G.stage_bytes = (step_bytes + 127u) & ~127u;
+    G.n_stages = std::min<uint32_t>(fm::kMaxStages, warp_smem / G.stage_bytes);
+    if (G.n_stages < 2) fail(FM_ERR_INVALID_ARG, "internal: pipeline stage does not fit");
     G.v_lo = v_lo;
     G.v_hi = v_hi;
     G.b_lo = v_lo / 32;
@@ -235,15 +261,63 @@ fm::PassGeom make_geom(const fm_group *const *gs, int ng, uint32_t v_lo, uint32_
     return G;
 }
 
-template <int NG>
-void launch_plane_pass(const fm::PassParams<NG> &P, int device) {
-    if (P.geom.n_batches == 0) return;
-    const size_t smem = (size_t)fm::kWarpsPerCta * fm::kStages * fm::kStageBytes;
-    CK(cudaFuncSetAttribute(fm::fm_k_plane_pass<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+// Zeroed device counters for the dynamic batch scheduler: kSchedCounters counters in separate
+// 128-byte lines per launch, handed out from a pool that is re-zeroed on the stream when it wraps.
+struct CounterPool {
+    uint32_t *d = nullptr;
+    int device = -1;
+    uint32_t next = 0;
+    static constexpr uint32_t kLaunches = 64;
+    static constexpr uint32_t kWordsPerLaunch = fm::kSchedCounters * fm::kSchedStrideWords;
+    uint32_t *take(int dev) {
+        if (device != dev) {  // a host thread normally stays on one device
+            d = nullptr;
+            CK(cudaMalloc((void **)&d, (size_t)kLaunches * kWordsPerLaunch * sizeof(uint32_t)));
+            device = dev;
+            next = kLaunches;
+        }
+        if (next == kLaunches) {
+            CK(cudaMemsetAsync(d, 0, (size_t)kLaunches * kWordsPerLaunch * sizeof(uint32_t), stream()));
+            next = 0;
+        }
+        return d + (size_t)(next++) * kWordsPerLaunch;
+    }
+};
+thread_local CounterPool t_counters;
+
+template <int NG, int LG, bool HC>
+void launch_plane_pass_t(const fm::PassParams<NG> &P, uint32_t grid, size_t smem) {
+    CK(cudaFuncSetAttribute(fm::fm_k_plane_pass<NG, LG, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)smem));
+    fm::fm_k_plane_pass<NG, LG, HC><<<grid, fm::kWarpsPerCta * 32, smem, stream()>>>(P);
+}
+
+template <int NG, bool HC>
+void launch_plane_pass_lg(const fm::PassParams<NG> &P, uint32_t grid, size_t smem) {
+    switch (P.geom.lps_log2) {
+        case 0: launch_plane_pass_t<NG, 0, HC>(P, grid, smem); break;
+        case 1: launch_plane_pass_t<NG, 1, HC>(P, grid, smem); break;
+        case 2: launch_plane_pass_t<NG, 2, HC>(P, grid, smem); break;
+        case 3: launch_plane_pass_t<NG, 3, HC>(P, grid, smem); break;
+        case 4: launch_plane_pass_t<NG, 4, HC>(P, grid, smem); break;
+        default: launch_plane_pass_t<NG, 5, HC>(P, grid, smem); break;
+    }
+}
+
+template <int NG>
+void launch_plane_pass(fm::PassParams<NG> P, int device) {
+    if (P.geom.n_batches == 0) return;
+    P.geom.batch_counter = t_counters.take(device);
+    const size_t smem = (size_t)fm::kWarpsPerCta * P.geom.warp_smem_bytes;
     const uint32_t need = (P.geom.n_batches + fm::kWarpsPerCta - 1) / fm::kWarpsPerCta;
     const uint32_t grid = std::min<uint32_t>((uint32_t)sm_count(device), need);
-    fm::fm_k_plane_pass<NG><<<grid, fm::kWarpsPerCta * 32, smem, stream()>>>(P);
+    bool hc = P.g[0].called != nullptr;
+    for (int g = 1; g < NG; ++g)
+        if ((P.g[g].called != nullptr) != hc) fail(FM_ERR_INVALID_ARG, "groups of one pass must share a matrix");
+    if (hc)
+        launch_plane_pass_lg<NG, true>(P, grid, smem);
+    else
+        launch_plane_pass_lg<NG, false>(P, grid, smem);
     CK(cudaGetLastError());
     g_launches++;
     t_tim.stats_launches++;
@@ -263,8 +337,7 @@ void finish_partials(const double *d_pd, int nd, const uint32_t *d_pu, int nu, c
     const uint32_t n_super = (G.b_lo + G.n_batches + fm::kSuperBatches - 1) / fm::kSuperBatches - s_lo;
     DevBuf<double> sd((size_t)n_super * std::max(nd, 1));
     DevBuf<uint64_t> su((size_t)n_super * std::max(nu, 1));
-    const uint32_t threads = n_super * (uint32_t)(nd + nu);
-    fm::fm_k_reduce_partials<<<(threads + 127) / 128, 128, 0, stream()>>>(
+    fm::fm_k_reduce_partials<<<(n_super + 3) / 4, 128, 0, stream()>>>(
         d_pd, nd, d_pu, nu, G.b_lo, G.n_batches, s_lo, n_super, sd.p, su.p);
     CK(cudaGetLastError());
     g_launches++;
@@ -277,6 +350,13 @@ void finish_partials(const double *d_pd, int nd, const uint32_t *d_pu, int nu, c
         for (int i = 0; i < nd; ++i) out_d[i] += hd[(size_t)s * nd + i];
         for (int i = 0; i < nu; ++i) out_u[i] += hu[(size_t)s * nu + i];
     }
+}
+
+void set_tables(fm::DivEpilogue &e, const fm_group *g) {
+    const size_t tn = (size_t)g->n + 1;
+    e.tab_inv_n = g->d_tab;
+    e.tab_scale = g->d_tab + tn;
+    e.tab_theta = g->d_tab + 2 * tn;
 }
 
 fm::GroupPlanes planes_of(const fm_group *g) {
@@ -302,17 +382,22 @@ DivResult run_diversity(fm_group *g, uint32_t v_lo, uint32_t v_hi, int pi_form, 
     fm::DivEpilogue e{};
     e.pi_out = d_pi;
     e.theta_out = d_theta;
-    e.pos = g->m->d_pos;
-    e.mask = d_mask;
-    e.n_mask = n_mask;
-    e.filt = d_filt;
-    e.n_filt = n_filt;
-    e.harmonic = g->d_harm;
+    set_tables(e, g);
+    DevBuf<uint32_t> flags;
+    Timer tm;
+    tm.start();
+    if (d_pi && (d_mask || d_filt)) {  // K5a: mask / filtered-position bits, one word per batch
+        flags.alloc(G.n_batches);
+        const uint32_t fb = std::min<uint32_t>((G.n_batches + 7) / 8, 8u * sm_count(g->m->device));
+        fm::fm_k_site_flags<<<fb, 256, 0, stream()>>>(g->m->d_pos, v_lo, v_hi, G.b_lo, G.n_batches, d_mask,
+                                                       n_mask, d_filt, n_filt, flags.p);
+        CK(cudaGetLastError());
+        g_launches++;
+        e.site_flags = flags.p;
+    }
     e.pi_form = pi_form;
     e.part_pi = part_pi.p;
     e.part_u = part_u.p;
-    Timer tm;
-    tm.start();
     if (g->have_counts && !force_plane_pass) {
         const uint32_t blocks = std::min<uint32_t>((G.n_batches + 7) / 8, 8u * sm_count(g->m->device));
         fm::fm_k_div_from_counts<<<blocks, 256, 0, stream()>>>(g->d_alt, g->d_cnt, e, v_lo, v_hi,
@@ -649,16 +734,20 @@ fm_status fm_group_create(fm_matrix *m, const uint64_t *sample_idx, const uint8_
             const size_t plane_u4 = std::max<size_t>(m->V, 1) * g->wq;
             CK(cudaMalloc((void **)&g->d_allele, plane_u4 * 16));
             if (m->d_missing) CK(cudaMalloc((void **)&g->d_called, plane_u4 * 16));
-            // harmonic table, forward summation exactly like stats.rs:4234-4240
-            std::vector<double> H((size_t)g->n + 1);
-            double s = 0.0;
-            H[0] = 0.0;
-            for (uint32_t k = 1; k <= g->n; ++k) {
-                s += 1.0 / (double)k;
-                H[k] = s;
+            // per-n tables: 1/n, n/(n-1) (stats.rs:2728-2732) and 1/H_{n-1} with the harmonic number
+            // by forward summation exactly like stats.rs:4234-4240 / 4718-4719
+            const size_t tn = (size_t)g->n + 1;
+            std::vector<double> T(3 * tn, 0.0);
+            double hsum = 0.0;  // H_{k-1} while visiting k
+            for (size_t k = 1; k < tn; ++k) {
+                const double kd = (double)k;
+                T[k] = 1.0 / kd;
+                T[tn + k] = kd / (kd - 1.0);
+                T[2 * tn + k] = hsum > 0.0 ? 1.0 / hsum : 0.0;
+                hsum += 1.0 / kd;
             }
-            CK(cudaMalloc((void **)&g->d_harm, H.size() * 8));
-            CK(cudaMemcpyAsync(g->d_harm, H.data(), H.size() * 8, cudaMemcpyHostToDevice, stream()));
+            CK(cudaMalloc((void **)&g->d_tab, T.size() * 8));
+            CK(cudaMemcpyAsync(g->d_tab, T.data(), T.size() * 8, cudaMemcpyHostToDevice, stream()));
             DevBuf<uint32_t> d_off(std::max<size_t>(g->n, 1));
             d_off.upload(g->off.data(), g->n);
             if (m->V) {
@@ -689,7 +778,7 @@ fm_status fm_group_release(fm_group *g) {
     if (g->m) cudaSetDevice(g->m->device);
     cudaFree(g->d_allele);
     cudaFree(g->d_called);
-    cudaFree(g->d_harm);
+    cudaFree(g->d_tab);
     cudaFree(g->d_alt);
     cudaFree(g->d_cnt);
     fm_matrix_release(g->m);
@@ -1211,9 +1300,8 @@ void launch_reduce(const double *pd, int nd, const uint32_t *pu, int nu, const f
                    uint64_t *su) {
     const uint32_t s_lo = G.b_lo / fm::kSuperBatches;
     const uint32_t n_super = (G.b_lo + G.n_batches + fm::kSuperBatches - 1) / fm::kSuperBatches - s_lo;
-    const uint32_t threads = n_super * (uint32_t)(nd + nu);
-    fm::fm_k_reduce_partials<<<(threads + 127) / 128, 128, 0, stream()>>>(pd, nd, pu, nu, G.b_lo, G.n_batches,
-                                                                           s_lo, n_super, sd, su);
+    fm::fm_k_reduce_partials<<<(n_super + 3) / 4, 128, 0, stream()>>>(pd, nd, pu, nu, G.b_lo, G.n_batches,
+                                                                       s_lo, n_super, sd, su);
     CK(cudaGetLastError());
     g_launches++;
 }
@@ -1236,11 +1324,14 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
         };
         std::vector<PerGroup> pg(n_groups);
         DevBuf<int64_t> d_mask;
+        DevBuf<uint32_t> d_flags;
         std::vector<int64_t> merged;
+        const uint32_t nb_all = V ? (V + 31) / 32 : 0;
         if (mode == 1 && mask_iv) {
             merge_intervals(mask_iv, n_mask, merged);
             d_mask.alloc(std::max<size_t>(merged.size(), 2));
             d_mask.upload(merged.data(), merged.size());
+            d_flags.alloc(std::max<uint32_t>(nb_all, 1));
         }
         uint64_t bytes = 0;
         for (size_t i = 0; i < n_groups; ++i) {
@@ -1254,22 +1345,19 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
             pg[i].sd.alloc(nb / fm::kSuperBatches + 2);
             pg[i].su.alloc(2 * (nb / fm::kSuperBatches + 2));
             fm::DivEpilogue e{};
-            e.pos = m->d_pos;
-            e.harmonic = g->d_harm;
+            set_tables(e, g);
             e.pi_form = FM_PIFORM_COUNTS;
             e.part_pi = pg[i].part_pi.p;
             e.part_u = pg[i].part_u.p;
             bytes += (uint64_t)V * g->wq * 16u * (g->d_called ? 2u : 1u);
+            if (i < 8) out->group_bytes[i] = (uint64_t)V * g->wq * 16u * (g->d_called ? 2u : 1u) + (mode == 1 ? (uint64_t)V * 16u : 0);
             if (mode == 1) {
                 pg[i].pi.alloc(std::max<uint32_t>(V, 1));
                 pg[i].theta.alloc(std::max<uint32_t>(V, 1));
                 e.pi_out = pg[i].pi.p;
                 e.theta_out = pg[i].theta.p;
                 e.pi_form = FM_PIFORM_COMPONENTS;
-                if (mask_iv) {
-                    e.mask = d_mask.p;
-                    e.n_mask = (uint32_t)(merged.size() / 2);
-                }
+                if (mask_iv) e.site_flags = d_flags.p;
                 bytes += (uint64_t)V * 16u;
             }
             pg[i].P = fm::PassParams<1>{};
@@ -1283,6 +1371,15 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
         CK(cudaStreamSynchronize(stream()));
         CK(cudaEventRecord(t0, stream()));
         for (int it = 0; it < iterations; ++it) {
+            if (mode == 1 && mask_iv && nb_all) {  // the mask lookup is part of every step
+                const uint32_t fb = std::min<uint32_t>((nb_all + 7) / 8, 8u * sm_count(m->device));
+                fm::fm_k_site_flags<<<fb, 256, 0, stream()>>>(m->d_pos, 0, V, 0, nb_all, d_mask.p,
+                                                               (uint32_t)(merged.size() / 2), nullptr, 0,
+                                                               d_flags.p);
+                CK(cudaGetLastError());
+                g_launches++;
+                out->other_launches++;
+            }
             for (size_t i = 0; i < n_groups; ++i) {
                 cudaEvent_t a = evs.next(), b = evs.next();
                 CK(cudaEventRecord(a, stream()));
@@ -1300,10 +1397,12 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
         CK(cudaEventSynchronize(t1));
         float total = 0.f, plane = 0.f;
         CK(cudaEventElapsedTime(&total, t0, t1));
-        for (auto &sp : spans) {
+        for (size_t si = 0; si < spans.size(); ++si) {
             float t = 0.f;
-            CK(cudaEventElapsedTime(&t, sp.first, sp.second));
+            CK(cudaEventElapsedTime(&t, spans[si].first, spans[si].second));
             plane += t;
+            const size_t gi = si % n_groups;
+            if (gi < 8) out->group_ms_avg[gi] += t / (float)iterations;
         }
         out->step_ms_avg = total / (float)iterations;
         out->plane_ms_avg = spans.empty() ? 0.f : plane / (float)spans.size();

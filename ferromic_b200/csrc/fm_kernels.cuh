@@ -17,10 +17,17 @@
 
 namespace fm {
 
-constexpr int kWarpsPerCta = 8;
-constexpr int kStages = 2;
-constexpr uint32_t kStageBytes = 12 * 1024;  // per warp, per stage
-constexpr uint32_t kSuperBatches = 256;      // batches folded by fm_k_reduce_partials
+constexpr int kWarpsPerCta = 16;
+constexpr uint32_t kWarpSmemBytes = 14 * 1024;  // private staging ring of one warp (16 x 14 KB = 224 KB)
+constexpr int kMaxStages = 6;
+constexpr uint32_t kStepBytesTarget = 7 * 1024;  // preferred bytes per pipeline step (two stages per warp)
+// Dynamic scheduler: same-address atomics serialise in L2 (~3.6 ns each on B200, which capped the
+// pass at one batch per 3.6 ns), so the batch range is split over kSchedCounters counters that
+// live in separate 128-byte lines; a CTA starts on its home range and steals from the others.
+constexpr uint32_t kSchedCounters = 16;
+constexpr uint32_t kSchedStrideWords = 32;
+constexpr uint32_t kSuperBatches = 256;          // batches folded by fm_k_reduce_partials
+constexpr int kBatchRing = 8;                    // claimed-batch ring per warp (> kMaxStages)
 
 // ------------------------------------------------------------------------------ K1 repack
 // One warp builds 32-bit words with __ballot_sync: lane j handles haplotype k = 32*w + j of
@@ -79,12 +86,19 @@ struct GroupPlanes {
 };
 
 struct PassGeom {
-    uint32_t lps;       // lanes per site: 1,2,4,...,32
-    uint32_t n_chunks;  // column chunks per row (1 unless lps == 32)
-    uint32_t cq;        // chunk width in uint4 (chunked mode)
+    uint32_t lps;         // lanes per site: 1,2,4,...,32 (power of two)
+    uint32_t lps_log2;
+    uint32_t rounds;      // rounds of (32/lps) sites held by one pipeline step (power of two <= lps)
+    uint32_t n_chunks;    // column chunks per row (1 unless lps == 32)
+    uint32_t cq;          // chunk width in uint4 (chunked mode)
+    uint32_t n_stages;    // pipeline depth of the per-warp ring (2..kMaxStages)
+    uint32_t stage_bytes; // bytes reserved per stage (multiple of 128)
+    uint32_t warp_smem_bytes;  // private staging ring of one warp (n_stages * stage_bytes <= this)
     uint32_t v_lo, v_hi;
     uint32_t b_lo, n_batches;  // global batch range (batch b = sites [32b, 32b+32))
     uint32_t n_sites_total;    // V (rows available in the planes)
+    uint32_t *batch_counter;   // dynamic scheduler counters (zeroed before launch)
+    uint32_t debug;            // tuning only: bit0 skip epilogue, bit1 skip column loop
 };
 
 // Diversity epilogue (NG == 1): build_dense_population_summary (stats.rs:1367-1470) +
@@ -92,11 +106,13 @@ struct PassGeom {
 struct DivEpilogue {
     uint32_t *alt_out, *called_out;  // [V] or nullptr
     double *pi_out, *theta_out;      // [v_hi - v_lo] or nullptr   (tracks)
-    const int64_t *pos;              // [V]
-    const int64_t *mask;             // merged, sorted half-open intervals [s,e) (2*n_mask) or nullptr
-    const int64_t *filt;             // sorted filtered positions or nullptr
-    const double *harmonic;          // H[k], k = 0..cap (forward summation, stats.rs:4234-4240)
-    uint32_t n_mask, n_filt;
+    const uint32_t *site_flags;      // [n_batches] bit i of word b-b_lo: site 32b+i is masked or
+                                     // filtered (fm_k_site_flags); nullptr when nothing is dropped
+    // per-group lookup tables indexed by the called count n = 0..cap.  They hold exactly the
+    // values the reference computes per site (IEEE division is correctly rounded on host and
+    // device alike): inv_n = 1/n, scale = n/(n-1), theta = 1/H_{n-1} with H by forward summation
+    // (stats.rs:4234-4240, 4716-4722).
+    const double *tab_inv_n, *tab_scale, *tab_theta;
     int pi_form;                     // formula used for the sum-of-pi partial
     double *part_pi;                 // [n_batches]
     uint32_t *part_u;                // [n_batches][2]: segregating sites, sites with called < 2
@@ -149,39 +165,61 @@ __device__ __forceinline__ uint32_t fm_warp_sum_u(uint32_t v) {
     return v;
 }
 
+// Mask / filtered-position lookup hoisted out of the streaming kernel: one bit per site
+// (stats.rs:4731-4743: position in filtered_positions or inside any mask interval [s,e)).
+// One warp per batch; the result is a 32-bit word per batch.
+__global__ void __launch_bounds__(256)
+fm_k_site_flags(const int64_t *__restrict__ pos, uint32_t v_lo, uint32_t v_hi, uint32_t b_lo,
+                uint32_t n_batches, const int64_t *__restrict__ mask, uint32_t n_mask,
+                const int64_t *__restrict__ filt, uint32_t n_filt, uint32_t *__restrict__ flags) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t GW = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t bi = gw; bi < n_batches; bi += GW) {
+        const uint32_t v = (b_lo + bi) * 32 + lane;
+        bool drop = false;
+        if (v >= v_lo && v < v_hi) {
+            const int64_t p = pos[v];
+            if (filt) drop = fm_in_sorted(filt, n_filt, p);
+            if (!drop && mask) drop = fm_in_intervals(mask, n_mask, p);
+        }
+        const uint32_t w = __ballot_sync(0xffffffffu, drop);
+        if (lane == 0) flags[bi] = w;
+    }
+}
+
 // Per-site diversity values (shared by the fused epilogue and the light kernel).
 __device__ __forceinline__ void fm_div_site(const DivEpilogue &e, uint32_t v, uint32_t v_lo,
-                                            uint32_t n, uint32_t alt, double &pi_part,
+                                            uint32_t n, uint32_t alt, bool dropped, double &pi_part,
                                             uint32_t &seg, uint32_t &unc) {
-    seg = (n >= 2 && alt > 0 && alt < n) ? 1u : 0u;  // stats.rs:1389 / 1406
-    unc = (n < 2) ? 1u : 0u;                         // stats.rs:1512-1516
-    double val;
-    pi_part = fm_pi_form(e.pi_form, n, alt, val) ? val : 0.0;
+    const bool poly = (n >= 2 && alt > 0 && alt < n);
+    seg = poly ? 1u : 0u;       // stats.rs:1389 / 1406
+    unc = (n < 2) ? 1u : 0u;    // stats.rs:1512-1516
+    double pi_comp = 0.0;       // pi_from_components (stats.rs:2723-2733) via the tables
+    if (n >= 2 && (e.pi_out || e.pi_form == FM_PIFORM_COMPONENTS)) {
+        const double r = (double)(n - alt), a = (double)alt;
+        const double sum_counts_sq = r * r + a * a;
+        const double inv_n = __ldg(e.tab_inv_n + n);
+        const double sum_p2 = sum_counts_sq * inv_n * inv_n;
+        pi_comp = __ldg(e.tab_scale + n) * (1.0 - sum_p2);
+    }
+    if (e.pi_form == FM_PIFORM_COMPONENTS) {
+        pi_part = pi_comp;
+    } else {
+        double val;
+        pi_part = fm_pi_form(e.pi_form, n, alt, val) ? val : 0.0;
+    }
     if (e.alt_out) e.alt_out[v] = alt;
     if (e.called_out) e.called_out[v] = n;
     if (e.pi_out) {
         // calculate_per_site_diversity, stats.rs:4710-4743
         double pi_value, theta_value;
-        if (n < 2) {
+        if (n < 2 || dropped) {
             pi_value = fm_nan();
             theta_value = fm_nan();
         } else {
-            if (alt > 0 && alt < n) {  // distinct_alleles > 1
-                double denom = e.harmonic[n - 1];
-                theta_value = denom > 0.0 ? 1.0 / denom : 0.0;
-            } else {
-                theta_value = 0.0;
-            }
-            double p;
-            pi_value = fm_pi_components(n, alt, p) ? p : 0.0;
-        }
-        const int64_t pos = e.pos[v];
-        bool drop = false;
-        if (e.filt) drop = fm_in_sorted(e.filt, e.n_filt, pos);
-        if (!drop && e.mask) drop = fm_in_intervals(e.mask, e.n_mask, pos);
-        if (drop) {
-            pi_value = fm_nan();
-            theta_value = fm_nan();
+            theta_value = poly ? __ldg(e.tab_theta + n) : 0.0;  // distinct_alleles > 1
+            pi_value = pi_comp;
         }
         e.pi_out[v - v_lo] = pi_value;
         e.theta_out[v - v_lo] = theta_value;
@@ -255,231 +293,340 @@ struct PassParams {
     HudsonEpilogue hud;  // used when NG == 2
 };
 
-template <int NG>
+// Specialisations: NG groups, LG = log2(lanes per site) (LG == 5 is the column-chunked mode for
+// rows wider than a pipeline step), HC = planes carry a called bitplane.
+//
+// Non-chunked geometry: a pipeline step holds `rounds` x SPS consecutive sites (SPS = 32/LPS);
+// in every round LPS consecutive lanes read consecutive uint4 of one row, so a quarter-warp
+// always touches one contiguous 128-byte span (bank-conflict free without padding).
+template <int NG, int LG, bool HC>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 1)
 fm_k_plane_pass(const __grid_constant__ PassParams<NG> P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[kWarpsPerCta * kStages];
+    __shared__ __align__(8) uint64_t bars[kWarpsPerCta * kMaxStages];
+    __shared__ uint32_t batch_ring[kWarpsPerCta * kBatchRing];
+
+    constexpr uint32_t LPS = 1u << LG;       // lanes per site
+    constexpr uint32_t SPS = 32u >> LG;      // sites per round
+    constexpr bool CHUNKED = (LG == 5);
+    constexpr uint32_t NPL = HC ? 2u : 1u;   // planes per group
+    constexpr uint32_t FULL = 0xffffffffu;
 
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warp = threadIdx.x >> 5;
-    const uint32_t gw = blockIdx.x * kWarpsPerCta + warp;
-    const uint32_t GW = gridDim.x * kWarpsPerCta;
+    // broadcast through a shuffle so the compiler knows the warp index (and everything derived
+    // from it: staging addresses, barrier addresses) is warp-uniform
+    const uint32_t warp = __shfl_sync(FULL, threadIdx.x >> 5, 0);
     const PassGeom &G = P.geom;
+    const uint32_t n_stages = G.n_stages;
+    const uint32_t stage_bytes = G.stage_bytes;
+    const uint32_t n_sites_total = G.n_sites_total;
+    const uint32_t n_batches = G.n_batches;
+    const uint32_t n_chunks = CHUNKED ? G.n_chunks : 1u;
+    const uint32_t cq = G.cq;
+    const uint32_t rounds = CHUNKED ? 1u : G.rounds;
+    const uint32_t step_sites = CHUNKED ? 1u : SPS * rounds;
+    const uint32_t spb = CHUNKED ? 32u * n_chunks : LPS / rounds;  // steps per batch
 
-    uint8_t *my_smem = smem_raw + (size_t)warp * kStages * kStageBytes;
-    uint64_t *my_bar = bars + warp * kStages;
+    uint32_t wq16[NG];  // row bytes per plane
+#pragma unroll
+    for (int g = 0; g < NG; ++g) wq16[g] = P.g[g].wq * 16u;
+
+    const uint32_t smem_base = fm_smem_u32(smem_raw) + warp * G.warp_smem_bytes;
+    const uint32_t bar_base = fm_smem_u32(bars + warp * kMaxStages);
+    uint32_t *my_ring = batch_ring + warp * kBatchRing;
     if (lane == 0) {
-        for (int s = 0; s < kStages; ++s) fm_mbar_init(&my_bar[s], 1);
+        for (uint32_t s = 0; s < n_stages; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_base + 8u * s));
         fm_fence_mbar_init();
     }
     __syncwarp();
 
-    const bool chunked = (G.lps == 32);
-    const uint32_t lps = G.lps;
-    const uint32_t sps = 32 / lps;  // sites per step (non-chunked)
-    const uint32_t steps_per_batch = chunked ? 32 * G.n_chunks : lps;
-    // batches handled by this warp: b = b_lo + gw, + GW, ...
-    const uint32_t my_batches = (G.n_batches > gw) ? (G.n_batches - gw + GW - 1) / GW : 0;
-    const uint64_t my_steps = (uint64_t)my_batches * steps_per_batch;
-
-    // geometry of step q -> (first site, #sites, column range)
-    auto step_geom = [&](uint64_t q, uint32_t &v0, uint32_t &nsites, uint32_t &c0) {
-        const uint32_t bi = (uint32_t)(q / steps_per_batch);
-        const uint32_t k = (uint32_t)(q % steps_per_batch);
-        const uint32_t b = G.b_lo + gw + bi * GW;
-        if (chunked) {
-            v0 = b * 32 + k / G.n_chunks;
-            c0 = (k % G.n_chunks) * G.cq;
-            nsites = (v0 < G.n_sites_total) ? 1u : 0u;
-        } else {
-            v0 = b * 32 + k * sps;
-            c0 = 0;
-            nsites = (v0 < G.n_sites_total) ? min(sps, G.n_sites_total - v0) : 0u;
-        }
-    };
-    // columns of group g present in a step starting at column c0
-    auto cols_of = [&](int g, uint32_t c0) -> uint32_t {
-        if (!chunked) return P.g[g].wq;
-        return (c0 < P.g[g].wq) ? min(G.cq, P.g[g].wq - c0) : 0u;
-    };
-
-    auto issue = [&](uint64_t q) {  // lane 0 only
-        uint32_t v0, nsites, c0;
-        step_geom(q, v0, nsites, c0);
-        const uint32_t stage = (uint32_t)(q % kStages);
-        uint8_t *dst = my_smem + (size_t)stage * kStageBytes;
-        uint32_t total = 0;
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            const uint32_t bytes = nsites * cols_of(g, c0) * 16u;
-            total += bytes * (P.g[g].called ? 2u : 1u);
-        }
-        if (total == 0) {
-            // nothing to load (batch tail beyond V): complete the phase with a plain arrive
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fm_smem_u32(&my_bar[stage]))
-                         : "memory");
-            return;
-        }
-        fm_mbar_expect_tx(&my_bar[stage], total);
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            const uint32_t cols = cols_of(g, c0);
-            const uint32_t bytes = nsites * cols * 16u;
-            const uint32_t slot = (chunked ? G.cq : P.g[g].wq) * sps * 16u;  // smem bytes per plane
-            if (bytes) {
-                const size_t src = ((size_t)v0 * P.g[g].wq + c0);
-                fm_bulk_g2s(dst, P.g[g].allele + src, bytes, &my_bar[stage]);
-                if (P.g[g].called)
-                    fm_bulk_g2s(dst + slot, P.g[g].called + src, bytes, &my_bar[stage]);
+    // ---- dynamic batch scheduler: the issue side claims batches, the consume side replays the
+    // same sequence from a small per-warp ring.  Partials are keyed by the batch index, so the
+    // result does not depend on which warp processed which batch.
+    // The atomic is fired one batch ahead so its round trip never sits on the critical path.
+    uint32_t sched_j = blockIdx.x % kSchedCounters, sched_tried = 0;
+    auto range_lo = [&](uint32_t j) { return (uint32_t)(((uint64_t)n_batches * j) / kSchedCounters); };
+    uint32_t prefetched = 0;
+    if (lane == 0) prefetched = atomicAdd(G.batch_counter + sched_j * kSchedStrideWords, 1u);
+    auto claim = [&]() -> uint32_t {
+        for (;;) {
+            const uint32_t idx = __shfl_sync(FULL, prefetched, 0);
+            const uint32_t lo = range_lo(sched_j), hi = range_lo(sched_j + 1);
+            if (idx < hi - lo) {  // fire the next claim on the same range, one batch ahead
+                if (lane == 0) prefetched = atomicAdd(G.batch_counter + sched_j * kSchedStrideWords, 1u);
+                return lo + idx;
             }
-            dst += (size_t)slot * (P.g[g].called ? 2u : 1u);
+            if (++sched_tried == kSchedCounters) return 0xffffffffu;  // every range is drained
+            sched_j = (sched_j + 1 == kSchedCounters) ? 0 : sched_j + 1;
+            if (lane == 0) prefetched = atomicAdd(G.batch_counter + sched_j * kSchedStrideWords, 1u);
         }
     };
 
-    if (lane == 0) {
-        for (uint64_t q = 0; q < (uint64_t)kStages && q < my_steps; ++q) issue(q);
+    // issue the TMA bulk copies of step k of local batch `bl` into `stage` (lane 0 only)
+    auto issue = [&](uint32_t bl, uint32_t k, uint32_t stage) {
+        const uint32_t b = G.b_lo + bl;
+        const uint32_t bar = bar_base + 8u * stage;
+        uint32_t dst = smem_base + stage * stage_bytes;
+        if constexpr (CHUNKED) {
+            const uint32_t v0 = b * 32 + k / n_chunks;
+            const uint32_t c0 = (k % n_chunks) * cq;
+            uint32_t bytes[NG], total = 0;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const uint32_t w = P.g[g].wq;
+                bytes[g] = (v0 < n_sites_total && c0 < w) ? min(cq, w - c0) * 16u : 0u;
+                total += bytes[g] * NPL;
+            }
+            if (total == 0) {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+                return;
+            }
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                if (bytes[g]) {
+                    const size_t src = (size_t)v0 * P.g[g].wq + c0;
+                    asm volatile(
+                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                            "r"(dst), "l"(P.g[g].allele + src), "r"(bytes[g]), "r"(bar) : "memory");
+                    if constexpr (HC)
+                        asm volatile(
+                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                                "r"(dst + cq * 16u), "l"(P.g[g].called + src), "r"(bytes[g]), "r"(bar) : "memory");
+                }
+                dst += cq * 16u * NPL;
+            }
+        } else {
+            const uint32_t v0 = b * 32 + k * step_sites;
+            const uint32_t nsites = (v0 < n_sites_total) ? min(step_sites, n_sites_total - v0) : 0u;
+            if (nsites == 0) {  // batch tail beyond V: complete the phase with a plain arrive
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+                return;
+            }
+            uint32_t total = 0;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) total += nsites * wq16[g] * NPL;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const uint32_t bytes = nsites * wq16[g];
+                const uint32_t slot = step_sites * wq16[g];
+                const size_t off = (size_t)v0 * wq16[g];
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                        "r"(dst), "l"(reinterpret_cast<const uint8_t *>(P.g[g].allele) + off), "r"(bytes), "r"(bar)
+                    : "memory");
+                if constexpr (HC)
+                    asm volatile(
+                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                            "r"(dst + slot), "l"(reinterpret_cast<const uint8_t *>(P.g[g].called) + off), "r"(bytes),
+                        "r"(bar)
+                        : "memory");
+                dst += slot * NPL;
+            }
+        }
+    };
+
+    // issue cursor (uniform across the warp)
+    uint32_t iss_ring = 0, iss_k = spb, iss_stage = 0, iss_batch = 0;
+    auto issue_next = [&]() {
+        if (iss_k == spb) {
+            if (iss_ring != 0 && iss_batch >= n_batches) return;  // scheduler drained
+            iss_batch = claim();
+            iss_k = 0;
+            if (lane == 0) my_ring[iss_ring & (kBatchRing - 1)] = iss_batch;
+            ++iss_ring;
+            if (iss_batch >= n_batches) {
+                iss_k = spb;
+                return;
+            }
+        }
+        if (lane == 0) issue(iss_batch, iss_k, iss_stage);
+        ++iss_k;
+        iss_stage = (iss_stage + 1 == n_stages) ? 0 : iss_stage + 1;
+    };
+    for (uint32_t s = 0; s < n_stages; ++s) issue_next();
+    __syncwarp();
+
+    // per-site totals of this lane's batch site; packed alt | called << 16 when HC (rows of the
+    // non-chunked modes hold < 65536 haplotypes), plain counts in chunked mode
+    uint32_t site_a[NG], site_c[NG], acc_a[NG], acc_c[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) site_a[g] = site_c[g] = acc_a[g] = acc_c[g] = 0;
+
+    const uint32_t slot_in_round = lane >> LG;
+    const uint32_t phase = lane & (LPS - 1);
+    const uint32_t xfer_from = (lane & (SPS - 1)) << LG;          // source lane of the transpose
+    const uint32_t xfer_round = CHUNKED ? 0u : (lane >> (5 - LG));  // round whose sites land here
+
+    uint32_t plane_off[NG];  // byte offset of group g's allele plane inside a stage
+    uint32_t nit_full[NG];   // column iterations that are in range for every lane
+    uint32_t last_cols[NG];  // lanes (phases) that still have a column in the last iteration
+    {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            plane_off[g] = acc;
+            acc += (CHUNKED ? cq * 16u : step_sites * wq16[g]) * NPL;
+            const uint32_t w = P.g[g].wq;
+            const uint32_t nit = (w + LPS - 1) / LPS;
+            nit_full[g] = nit - 1;
+            last_cols[g] = w - (nit - 1) * LPS;
+        }
     }
 
-    // per-lane accumulators for the site this lane is working on (alt, called) per group,
-    // and the batch-transposed counts (lane i <-> site 32b+i)
-    uint32_t acc_a[NG], acc_c[NG], site_a[NG], site_c[NG];
-#pragma unroll
-    for (int g = 0; g < NG; ++g) acc_a[g] = acc_c[g] = site_a[g] = site_c[g] = 0;
-
-    const uint32_t slot_in_step = lane / lps;  // site slot within a step (non-chunked)
-    const uint32_t phase = lane % lps;
-
-    for (uint64_t q = 0; q < my_steps; ++q) {
-        const uint32_t stage = (uint32_t)(q % kStages);
-        const uint32_t parity = (uint32_t)((q / kStages) & 1);
-        uint32_t v0, nsites, c0;
-        step_geom(q, v0, nsites, c0);
-        const uint32_t k = (uint32_t)(q % steps_per_batch);
-        fm_mbar_wait(&my_bar[stage], parity);
-
-        const uint8_t *src = my_smem + (size_t)stage * kStageBytes;
-        if (!chunked) {
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                const uint32_t wq = P.g[g].wq;
-                const uint4 *sa = reinterpret_cast<const uint4 *>(src);
-                const uint4 *sc = sa + (size_t)wq * sps;
-                uint32_t a = 0, c = 0;
-                if (slot_in_step < nsites) {
-                    // bank-conflict-free rotation: make (row*wq + col) mod 8 distinct across the
-                    // 8 lanes of every quarter-warp (see DESIGN.md "shared-memory access")
-                    const uint32_t row = slot_in_step;
-                    uint32_t rot = ((lane & 7u) / lps * lps + 8u * wq - (row * wq) % 8u) % 8u;
-                    if (lps >= 8) rot = 0;
-                    rot %= wq;
-                    const uint4 *ra = sa + (size_t)row * wq;
-                    const uint4 *rc = sc + (size_t)row * wq;
-                    if (P.g[g].called) {
-#pragma unroll 4
-                        for (uint32_t u = phase; u < wq; u += lps) {
-                            uint32_t col = u + rot;
-                            if (col >= wq) col -= wq;
-                            a += fm_popc4(ra[col]);
-                            c += fm_popc4(rc[col]);
-                        }
-                    } else {
-#pragma unroll 4
-                        for (uint32_t u = phase; u < wq; u += lps) {
-                            uint32_t col = u + rot;
-                            if (col >= wq) col -= wq;
-                            a += fm_popc4(ra[col]);
-                        }
-                    }
-                }
-                // reduce across the lps lanes of a site
-                for (uint32_t o = lps >> 1; o > 0; o >>= 1) {
-                    a += __shfl_xor_sync(0xffffffffu, a, o);
-                    c += __shfl_xor_sync(0xffffffffu, c, o);
-                }
-                // transpose: batch lane i = k*sps + slot takes slot's totals
-                const uint32_t from = (lane % sps) * lps;
-                const uint32_t ta = __shfl_sync(0xffffffffu, a, from);
-                const uint32_t tc = __shfl_sync(0xffffffffu, c, from);
-                if (lane / sps == k) {
-                    site_a[g] = ta;
-                    site_c[g] = P.g[g].called ? tc : P.g[g].cap;
-                }
-                src += (size_t)wq * sps * 16u * (P.g[g].called ? 2u : 1u);
+    uint32_t con_ring = 0, stage = 0, parity = 0;
+    for (;;) {
+        const uint32_t bl = my_ring[con_ring & (kBatchRing - 1)];
+        ++con_ring;
+        if (bl >= n_batches) break;
+        const uint32_t b = G.b_lo + bl;
+        for (uint32_t k = 0; k < spb; ++k) {
+            {
+                const uint32_t bar = bar_base + 8u * stage;
+                uint32_t ok;
+                do {
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\t"
+                        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                        "selp.u32 %0, 1, 0, p;\n\t}"
+                        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+                } while (!ok);
             }
-        } else {
-            const uint32_t site_in_batch = k / G.n_chunks;
-            const bool last_chunk = (k % G.n_chunks) == G.n_chunks - 1;
+            const uint32_t sbase = smem_base + stage * stage_bytes;
+            if constexpr (!CHUNKED) {
+                const uint32_t v0 = b * 32 + k * step_sites;
+                auto round_body = [&](uint32_t r) {
+                    const uint32_t site_local = r * SPS + slot_in_round;
+                    const bool live = (v0 + site_local) < n_sites_total;
 #pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                const uint32_t cols = cols_of(g, c0);
-                const uint4 *sa = reinterpret_cast<const uint4 *>(src);
-                const uint4 *sc = sa + G.cq;
-                if (nsites) {
-                    if (P.g[g].called) {
-                        for (uint32_t u = lane; u < cols; u += 32) {
-                            acc_a[g] += fm_popc4(sa[u]);
-                            acc_c[g] += fm_popc4(sc[u]);
+                    for (int g = 0; g < NG; ++g) {
+                        const uint32_t w16 = wq16[g];
+                        const uint32_t ra = sbase + plane_off[g] + site_local * w16;
+                        const uint32_t pb = step_sites * w16;  // distance allele -> called plane
+                        uint32_t a = 0, c = 0;
+                        if (live && !(G.debug & 2u)) {
+                            // columns phase, phase+LPS, ...: the first nit-1 are inside the row for
+                            // every lane, only the last one needs a bound check
+                            uint32_t p = ra + phase * 16u;
+                            const uint32_t nfull = nit_full[g];
+#pragma unroll 2
+                            for (uint32_t j = 0; j < nfull; ++j) {
+                                const uint4 xa = fm_lds128(p);
+                                a += fm_popc4(xa);
+                                if constexpr (HC) {
+                                    const uint4 xc = fm_lds128(p + pb);
+                                    c += fm_popc4(xc);
+                                }
+                                p += LPS * 16u;
+                            }
+                            if (phase < last_cols[g]) {
+                                const uint4 xa = fm_lds128(p);
+                                a += fm_popc4(xa);
+                                if constexpr (HC) {
+                                    const uint4 xc = fm_lds128(p + pb);
+                                    c += fm_popc4(xc);
+                                }
+                            }
                         }
-                    } else {
-                        for (uint32_t u = lane; u < cols; u += 32) acc_a[g] += fm_popc4(sa[u]);
+                        uint32_t ac = HC ? (a | (c << 16)) : a;
+#pragma unroll
+                        for (uint32_t o = LPS >> 1; o > 0; o >>= 1) ac += __shfl_xor_sync(FULL, ac, o);
+                        const uint32_t t = __shfl_sync(FULL, ac, xfer_from);
+                        if (xfer_round == k * rounds + r) site_a[g] = t;
+                    }
+                };
+                if (rounds == 1) {
+                    round_body(0);
+                } else {
+                    for (uint32_t r = 0; r < rounds; r += 2) {  // rounds is a power of two
+                        round_body(r);
+                        round_body(r + 1);
                     }
                 }
-                if (last_chunk) {
-                    const uint32_t ta = fm_warp_sum_u(acc_a[g]);
-                    const uint32_t tc = fm_warp_sum_u(acc_c[g]);
-                    if (lane == site_in_batch) {
-                        site_a[g] = ta;
-                        site_c[g] = P.g[g].called ? tc : P.g[g].cap;
+            } else {
+                const uint32_t site_in_batch = k / n_chunks;
+                const uint32_t ck = k - site_in_batch * n_chunks;
+                const uint32_t c0 = ck * cq;
+                const bool live = (b * 32 + site_in_batch) < n_sites_total;
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    const uint32_t w = P.g[g].wq;
+                    const uint32_t cols16 = (c0 < w) ? min(cq, w - c0) * 16u : 0u;
+                    const uint32_t ra = sbase + plane_off[g];
+                    if (live) {
+#pragma unroll 2
+                        for (uint32_t u = lane * 16u; u < cols16; u += 512u) {
+                            acc_a[g] += fm_popc4(fm_lds128(ra + u));
+                            if constexpr (HC) acc_c[g] += fm_popc4(fm_lds128(ra + cq * 16u + u));
+                        }
                     }
-                    acc_a[g] = 0;
-                    acc_c[g] = 0;
+                    if (ck == n_chunks - 1) {
+                        const uint32_t ta = fm_warp_sum_u(acc_a[g]);
+                        uint32_t tc = 0;
+                        if constexpr (HC) tc = fm_warp_sum_u(acc_c[g]);
+                        if (lane == site_in_batch) {
+                            site_a[g] = ta;
+                            site_c[g] = tc;
+                        }
+                        acc_a[g] = 0;
+                        acc_c[g] = 0;
+                    }
                 }
-                src += (size_t)G.cq * 16u * (P.g[g].called ? 2u : 1u);
             }
+            __syncwarp();   // every lane is done reading this stage
+            issue_next();   // refill it with the step n_stages ahead
+            stage = (stage + 1 == n_stages) ? 0 : stage + 1;
+            parity ^= (stage == 0);
         }
-        __syncwarp();  // all lanes finished reading this stage
-        if (lane == 0 && q + kStages < my_steps) issue(q + kStages);
-
-        if (k == steps_per_batch - 1) {
-            // ---- batch epilogue: lane i <-> site 32b + i
-            const uint32_t bi = (uint32_t)(q / steps_per_batch);
-            const uint32_t b = G.b_lo + gw + bi * GW;
+        // ---- batch epilogue: lane i <-> site 32b + i, all 32 lanes active
+        {
+            uint32_t alt[NG], cnt[NG];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                if constexpr (CHUNKED) {
+                    alt[g] = site_a[g];
+                    cnt[g] = HC ? site_c[g] : P.g[g].cap;
+                } else {
+                    alt[g] = HC ? (site_a[g] & 0xffffu) : site_a[g];
+                    cnt[g] = HC ? (site_a[g] >> 16) : P.g[g].cap;
+                }
+            }
             const uint32_t v = b * 32 + lane;
             const bool valid = (v >= G.v_lo) && (v < G.v_hi);
             if constexpr (NG == 1) {
                 double pi_part = 0.0;
                 uint32_t seg = 0, unc = 0;
-                if (valid) fm_div_site(P.div, v, G.v_lo, site_c[0], site_a[0], pi_part, seg, unc);
+                const uint32_t flags = P.div.site_flags ? __ldg(P.div.site_flags + bl) : 0u;
+                if (valid && !(G.debug & 1u))
+                    fm_div_site(P.div, v, G.v_lo, cnt[0], alt[0], (flags >> lane) & 1u, pi_part, seg, unc);
                 const double s_pi = fm_warp_sum(pi_part);
-                const uint32_t s_seg = fm_warp_sum_u(seg), s_unc = fm_warp_sum_u(unc);
+                const uint32_t s_u = fm_warp_sum_u(seg | (unc << 16));
                 if (lane == 0) {
-                    const uint32_t slot = b - G.b_lo;
-                    P.div.part_pi[slot] = s_pi;
-                    P.div.part_u[2 * slot] = s_seg;
-                    P.div.part_u[2 * slot + 1] = s_unc;
+                    P.div.part_pi[bl] = s_pi;
+                    P.div.part_u[2 * bl] = s_u & 0xffffu;
+                    P.div.part_u[2 * bl + 1] = s_u >> 16;
                 }
             } else {
                 HudsonAcc acc{0.0, 0.0, 0.0, 0.0, 0.0, 0u, 0u, 0u};
                 if (valid) {
-                    fm_hudson_contrib(P.hud, v, G.v_lo, site_c[0], site_a[0], site_c[1], site_a[1], acc);
+                    fm_hudson_contrib(P.hud, v, G.v_lo, cnt[0], alt[0], cnt[1], alt[1], acc);
 #pragma unroll
                     for (int g = 0; g < NG; ++g) {
-                        if (P.hud.alt_out[g]) P.hud.alt_out[g][v] = site_a[g];
-                        if (P.hud.called_out[g]) P.hud.called_out[g][v] = site_c[g];
+                        if (P.hud.alt_out[g]) P.hud.alt_out[g][v] = alt[g];
+                        if (P.hud.called_out[g]) P.hud.called_out[g][v] = cnt[g];
                     }
                 }
                 const double r0 = fm_warp_sum(acc.num), r1 = fm_warp_sum(acc.den),
                              r2 = fm_warp_sum(acc.dxy), r3 = fm_warp_sum(acc.pi1),
                              r4 = fm_warp_sum(acc.pi2);
-                const uint32_t u0 = fm_warp_sum_u(acc.skipped), u1 = fm_warp_sum_u(acc.unc1),
-                               u2 = fm_warp_sum_u(acc.unc2);
+                const uint32_t u01 = fm_warp_sum_u(acc.skipped | (acc.unc1 << 8) | (acc.unc2 << 16));
                 if (lane == 0) {
-                    const uint32_t slot = b - G.b_lo;
-                    double *pd = P.hud.part_d + (size_t)slot * 5;
+                    double *pd = P.hud.part_d + (size_t)bl * 5;
                     pd[0] = r0; pd[1] = r1; pd[2] = r2; pd[3] = r3; pd[4] = r4;
-                    uint32_t *pu = P.hud.part_u + (size_t)slot * 3;
-                    pu[0] = u0; pu[1] = u1; pu[2] = u2;
+                    uint32_t *pu = P.hud.part_u + (size_t)bl * 3;
+                    pu[0] = u01 & 0xffu; pu[1] = (u01 >> 8) & 0xffu; pu[2] = u01 >> 16;
                 }
             }
         }
@@ -501,7 +648,8 @@ fm_k_div_from_counts(const uint32_t *__restrict__ alt, const uint32_t *__restric
         const bool valid = v >= v_lo && v < v_hi;
         double pi_part = 0.0;
         uint32_t seg = 0, unc = 0;
-        if (valid) fm_div_site(e, v, v_lo, called[v], alt[v], pi_part, seg, unc);
+        const uint32_t flags = e.site_flags ? e.site_flags[bi] : 0u;
+        if (valid) fm_div_site(e, v, v_lo, called[v], alt[v], (flags >> lane) & 1u, pi_part, seg, unc);
         const double s_pi = fm_warp_sum(pi_part);
         const uint32_t s_seg = fm_warp_sum_u(seg), s_unc = fm_warp_sum_u(unc);
         if (lane == 0) {
@@ -538,28 +686,38 @@ fm_k_hudson_from_counts(const uint32_t *__restrict__ alt1, const uint32_t *__res
     }
 }
 
-// Second-level reduction: super-batch s sums batches [s*256, s*256+256) of the GLOBAL batch
-// grid sequentially (fixed order), for `nd` double columns and `nu` u32 columns.
-__global__ void fm_k_reduce_partials(const double *__restrict__ pd, int nd,
-                                     const uint32_t *__restrict__ pu, int nu, uint32_t b_lo,
-                                     uint32_t n_batches, uint32_t s_lo, uint32_t n_super,
-                                     double *__restrict__ out_d, uint64_t *__restrict__ out_u) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t ncol = (uint32_t)(nd + nu);
-    if (t >= n_super * ncol) return;
-    const uint32_t s = t / ncol, col = t % ncol;
-    const uint64_t g0 = (uint64_t)(s_lo + s) * kSuperBatches, g1 = g0 + kSuperBatches;
-    const uint64_t lo = g0 > b_lo ? g0 : b_lo;
-    const uint64_t hi = g1 < (uint64_t)b_lo + n_batches ? g1 : (uint64_t)b_lo + n_batches;
-    if (col < (uint32_t)nd) {
+// Second-level reduction: super-batch s folds batches [s*256, s*256+256) of the GLOBAL batch
+// grid with a fixed shape -- lane l sums its 8 consecutive batches in order, then a butterfly
+// over lanes -- for `nd` double columns and `nu` u32 columns.  One warp per super-batch.
+__global__ void __launch_bounds__(128)
+fm_k_reduce_partials(const double *__restrict__ pd, int nd, const uint32_t *__restrict__ pu, int nu,
+                     uint32_t b_lo, uint32_t n_batches, uint32_t s_lo, uint32_t n_super,
+                     double *__restrict__ out_d, uint64_t *__restrict__ out_u) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= n_super) return;
+    constexpr uint32_t per_lane = kSuperBatches / 32;
+    const uint64_t g0 = (uint64_t)(s_lo + s) * kSuperBatches + (uint64_t)lane * per_lane;
+    const uint64_t b_hi = (uint64_t)b_lo + n_batches;
+    for (int col = 0; col < nd; ++col) {
         double acc = 0.0;
-        for (uint64_t b = lo; b < hi; ++b) acc += pd[(b - b_lo) * nd + col];
-        out_d[(size_t)s * nd + col] = acc;
-    } else {
-        const uint32_t c = col - nd;
-        uint64_t acc = 0;
-        for (uint64_t b = lo; b < hi; ++b) acc += pu[(b - b_lo) * nu + c];
-        out_u[(size_t)s * nu + c] = acc;
+#pragma unroll
+        for (uint32_t i = 0; i < per_lane; ++i) {
+            const uint64_t b = g0 + i;
+            if (b >= b_lo && b < b_hi) acc += pd[(b - b_lo) * nd + col];
+        }
+        acc = fm_warp_sum(acc);
+        if (lane == 0) out_d[(size_t)s * nd + col] = acc;
+    }
+    for (int col = 0; col < nu; ++col) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < per_lane; ++i) {
+            const uint64_t b = g0 + i;
+            if (b >= b_lo && b < b_hi) acc += pu[(b - b_lo) * nu + col];
+        }
+        acc = fm_warp_sum_u(acc);
+        if (lane == 0) out_u[(size_t)s * nu + col] = acc;
     }
 }
 

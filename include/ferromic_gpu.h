@@ -211,6 +211,8 @@ typedef struct {
     uint64_t plane_launches;       /* plane-pass launches inside the timed region */
     uint64_t other_launches;       /* partial-reduction launches inside the timed region */
     uint64_t plane_bytes_per_step; /* algorithmic bytes: plane rows read + per-site outputs written */
+    float group_ms_avg[8];         /* mean plane-pass duration per listed group (first 8) */
+    uint64_t group_bytes[8];       /* algorithmic bytes of one launch per listed group */
 } fm_bench_result;
 fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
                              const int64_t *mask_iv_or_null, size_t n_mask, int iterations,
