@@ -3,6 +3,7 @@
 // deterministic final reductions.  No CPU fallback: every compute entry point needs a device.
 #include "../../include/ferromic_gpu.h"
 #include "fm_kernels.cuh"
+#include "fm_wc.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -695,81 +696,88 @@ fm_status fm_matrix_info(const fm_matrix *m, size_t *V, size_t *S, size_t *ploid
 }
 
 // ------------------------------------------------------------------------------------ group
+// Repack the matrix columns listed in `off` (sorted, unique) into a group's bitplanes (K1).
+static fm_group *make_group(fm_matrix *m, std::vector<uint32_t> &&off) {
+    if (m->max_allele > 1)
+        fail(FM_ERR_UNSUPPORTED, "multi-allelic matrices (max_allele > 1) are not on the GPU path yet");
+    set_dev(m);
+    fm_group *g = new fm_group();
+    g->m = m;
+    fm_matrix_retain(m);
+    try {
+        g->off = std::move(off);
+        g->n = (uint32_t)g->off.size();
+        g->wq = std::max<uint32_t>(1, (g->n + 127) / 128);
+        const size_t plane_u4 = std::max<size_t>(m->V, 1) * g->wq;
+        CK(cudaMalloc((void **)&g->d_allele, plane_u4 * 16));
+        if (m->d_missing) CK(cudaMalloc((void **)&g->d_called, plane_u4 * 16));
+        // per-n tables: 1/n, n/(n-1) (stats.rs:2728-2732) and 1/H_{n-1} with the harmonic number
+        // by forward summation exactly like stats.rs:4234-4240 / 4718-4719
+        const size_t tn = (size_t)g->n + 1;
+        std::vector<double> T(3 * tn, 0.0);
+        double hsum = 0.0;  // H_{k-1} while visiting k
+        for (size_t k = 1; k < tn; ++k) {
+            const double kd = (double)k;
+            T[k] = 1.0 / kd;
+            T[tn + k] = kd / (kd - 1.0);
+            T[2 * tn + k] = hsum > 0.0 ? 1.0 / hsum : 0.0;
+            hsum += 1.0 / kd;
+        }
+        CK(cudaMalloc((void **)&g->d_tab, T.size() * 8));
+        CK(cudaMemcpyAsync(g->d_tab, T.data(), T.size() * 8, cudaMemcpyHostToDevice, stream()));
+        DevBuf<uint32_t> d_off(std::max<size_t>(g->n, 1));
+        d_off.upload(g->off.data(), g->n);
+        if (m->V) {
+            Timer tm;
+            tm.start();
+            const uint32_t blocks = (uint32_t)std::min<uint64_t>(
+                (uint64_t)sm_count(m->device) * 8,
+                std::max<uint64_t>(1, ((uint64_t)m->V * ((g->wq * 4 + 31) / 32) + 7) / 8));
+            fm::fm_k_repack<<<blocks, 256, 0, stream()>>>(
+                m->d_data, m->d_missing, m->stride, d_off.p, g->n, g->wq, 0, (uint32_t)m->V,
+                reinterpret_cast<uint32_t *>(g->d_allele), reinterpret_cast<uint32_t *>(g->d_called));
+            CK(cudaGetLastError());
+            g_launches++;
+            tm.stop();
+            t_tim.repack_ms += tm.ms();
+        }
+        CK(cudaStreamSynchronize(stream()));
+    } catch (...) {
+        fm_group_release(g);
+        throw;
+    }
+    return g;
+}
+
 fm_status fm_group_create(fm_matrix *m, const uint64_t *sample_idx, const uint8_t *side, size_t n,
                           fm_group **out) {
     return guarded([&] {
         if (!out || !m) fail(FM_ERR_INVALID_ARG, "NULL argument");
         *out = nullptr;
         if (n && (!sample_idx || !side)) fail(FM_ERR_INVALID_ARG, "haplotype arrays are NULL");
-        if (m->max_allele > 1)
-            fail(FM_ERR_UNSUPPORTED,
-                 "multi-allelic matrices (max_allele > 1) are not on the GPU path yet");
-        set_dev(m);
-        fm_group *g = new fm_group();
-        g->m = m;
-        fm_matrix_retain(m);
-        try {
-            // DenseMembership::build (stats.rs:1251-1284)
-            std::vector<uint8_t> left(m->S, 0), right(m->S, 0);
-            g->off.reserve(n);
-            for (size_t i = 0; i < n; ++i) {
-                const uint64_t s = sample_idx[i];
-                if (s >= m->S) continue;
-                if (side[i] == 0) {
-                    if (!left[s]) {
-                        left[s] = 1;
-                        g->off.push_back((uint32_t)(s * m->ploidy));
-                    }
-                } else {
-                    if (m->ploidy <= 1) continue;
-                    if (!right[s]) {
-                        right[s] = 1;
-                        g->off.push_back((uint32_t)(s * m->ploidy + 1));
-                    }
+        require_device();
+        // DenseMembership::build (stats.rs:1251-1284)
+        std::vector<uint8_t> left(m->S, 0), right(m->S, 0);
+        std::vector<uint32_t> off;
+        off.reserve(n);
+        for (size_t i = 0; i < n; ++i) {
+            const uint64_t s = sample_idx[i];
+            if (s >= m->S) continue;
+            if (side[i] == 0) {
+                if (!left[s]) {
+                    left[s] = 1;
+                    off.push_back((uint32_t)(s * m->ploidy));
+                }
+            } else {
+                if (m->ploidy <= 1) continue;
+                if (!right[s]) {
+                    right[s] = 1;
+                    off.push_back((uint32_t)(s * m->ploidy + 1));
                 }
             }
-            std::sort(g->off.begin(), g->off.end());
-            g->n = (uint32_t)g->off.size();
-            g->wq = std::max<uint32_t>(1, (g->n + 127) / 128);
-            const size_t plane_u4 = std::max<size_t>(m->V, 1) * g->wq;
-            CK(cudaMalloc((void **)&g->d_allele, plane_u4 * 16));
-            if (m->d_missing) CK(cudaMalloc((void **)&g->d_called, plane_u4 * 16));
-            // per-n tables: 1/n, n/(n-1) (stats.rs:2728-2732) and 1/H_{n-1} with the harmonic number
-            // by forward summation exactly like stats.rs:4234-4240 / 4718-4719
-            const size_t tn = (size_t)g->n + 1;
-            std::vector<double> T(3 * tn, 0.0);
-            double hsum = 0.0;  // H_{k-1} while visiting k
-            for (size_t k = 1; k < tn; ++k) {
-                const double kd = (double)k;
-                T[k] = 1.0 / kd;
-                T[tn + k] = kd / (kd - 1.0);
-                T[2 * tn + k] = hsum > 0.0 ? 1.0 / hsum : 0.0;
-                hsum += 1.0 / kd;
-            }
-            CK(cudaMalloc((void **)&g->d_tab, T.size() * 8));
-            CK(cudaMemcpyAsync(g->d_tab, T.data(), T.size() * 8, cudaMemcpyHostToDevice, stream()));
-            DevBuf<uint32_t> d_off(std::max<size_t>(g->n, 1));
-            d_off.upload(g->off.data(), g->n);
-            if (m->V) {
-                Timer tm;
-                tm.start();
-                const uint32_t blocks = (uint32_t)std::min<uint64_t>(
-                    (uint64_t)sm_count(m->device) * 8,
-                    std::max<uint64_t>(1, ((uint64_t)m->V * ((g->wq * 4 + 31) / 32) + 7) / 8));
-                fm::fm_k_repack<<<blocks, 256, 0, stream()>>>(
-                    m->d_data, m->d_missing, m->stride, d_off.p, g->n, g->wq, 0, (uint32_t)m->V,
-                    reinterpret_cast<uint32_t *>(g->d_allele), reinterpret_cast<uint32_t *>(g->d_called));
-                CK(cudaGetLastError());
-                g_launches++;
-                tm.stop();
-                t_tim.repack_ms += tm.ms();
-            }
-            CK(cudaStreamSynchronize(stream()));
-        } catch (...) {
-            fm_group_release(g);
-            throw;
         }
-        *out = g;
+        std::sort(off.begin(), off.end());
+        *out = make_group(m, std::move(off));
     });
 }
 
@@ -1137,19 +1145,215 @@ fm_status fm_hudson_pair(fm_group *g1, fm_group *g2, int64_t L1, int64_t L2, int
     });
 }
 
-// ------------------------------------------------------------------------------------ W&C (see fm_wc.cuh)
-fm_status fm_partition_create(fm_matrix *, const uint16_t *, const uint16_t *, size_t, size_t,
-                              fm_partition **out) {
+// ------------------------------------------------------------------------------------ W&C (fm_wc.cuh)
+fm_status fm_partition_create(fm_matrix *m, const uint16_t *left, const uint16_t *right, size_t n_samples,
+                              size_t n_groups, fm_partition **out) {
     return guarded([&] {
-        if (out) *out = nullptr;
-        fail(FM_ERR_UNSUPPORTED, "Weir & Cockerham path not built yet");
+        if (!out || !m) fail(FM_ERR_INVALID_ARG, "NULL argument");
+        *out = nullptr;
+        if (n_samples && (!left || !right)) fail(FM_ERR_INVALID_ARG, "membership arrays are NULL");
+        if (n_groups >= 0xFFFF) fail(FM_ERR_INVALID_ARG, "too many groups");
+        require_device();
+        fm_partition *p = new fm_partition();
+        p->m = m;
+        p->G = n_groups;
+        fm_matrix_retain(m);
+        try {
+            // SubpopulationMembership (stats.rs:1093-1150): Left -> genotype[0], Right -> genotype[1]
+            std::vector<std::vector<uint32_t>> cols(n_groups + 1);
+            const size_t P = m->ploidy;
+            for (size_t s = 0; s < m->S; ++s) {
+                for (size_t k = 0; k < P; ++k) {
+                    uint16_t g = 0xFFFF;
+                    if (s < n_samples) {
+                        if (k == 0) g = left[s];
+                        else if (k == 1) g = right[s];
+                    }
+                    const size_t slot = (g != 0xFFFF && g < n_groups) ? g : n_groups;
+                    cols[slot].push_back((uint32_t)(s * P + k));
+                }
+            }
+            for (size_t g = 0; g <= n_groups; ++g) p->groups.push_back(make_group(m, std::move(cols[g])));
+        } catch (...) {
+            fm_partition_release(p);
+            throw;
+        }
+        *out = p;
     });
 }
-fm_status fm_partition_release(fm_partition *) { return FM_OK; }
-fm_status fm_wc_fst(fm_partition *, int64_t, int64_t, fm_fst_estimate *, fm_fst_estimate *, uint8_t *,
-                    int64_t *, int32_t *, double *, double *, uint32_t *, double *, double *, size_t,
-                    size_t *) {
-    return guarded([&] { fail(FM_ERR_UNSUPPORTED, "Weir & Cockerham path not built yet"); });
+
+fm_status fm_partition_release(fm_partition *p) {
+    if (!p) return FM_OK;
+    for (fm_group *g : p->groups) fm_group_release(g);
+    fm_matrix_release(p->m);
+    delete p;
+    return FM_OK;
+}
+
+static fm_fst_estimate classify_estimate(double a, double b, uint64_t sites) {
+    // threshold ladder of stats.rs:2237-2270 / 2297-2328 (same as :1785-1811)
+    fm_fst_estimate e;
+    e.sum_a = a;
+    e.sum_b = b;
+    e.sites = sites;
+    e.value = std::numeric_limits<double>::quiet_NaN();
+    e.state = fm_fst_state(a, b);
+    if (e.state == 0) e.value = a / (a + b);
+    return e;
+}
+
+fm_status fm_wc_fst(fm_partition *p, int64_t rs, int64_t re, fm_fst_estimate *overall, fm_fst_estimate *pairs,
+                    uint8_t *pair_present, int64_t *site_pos, int32_t *site_state, double *site_a, double *site_b,
+                    uint32_t *site_pop_sizes, double *pair_a, double *pair_b, size_t capacity, size_t *n_sites_out) {
+    return guarded([&] {
+        if (!p || !overall) fail(FM_ERR_INVALID_ARG, "NULL argument");
+        if (n_sites_out) *n_sites_out = 0;
+        require_device();
+        fm_matrix *m = p->m;
+        set_dev(m);
+        const uint32_t G = (uint32_t)p->G;
+        const uint32_t n_pairs = G * (G > 0 ? G - 1 : 0) / 2;
+        if (n_pairs && !pairs) fail(FM_ERR_INVALID_ARG, "pairs is NULL");
+        const double NaN = std::numeric_limits<double>::quiet_NaN();
+        auto insufficient = [&](uint64_t sites) {
+            fm_fst_estimate e;
+            e.state = 3;
+            e.value = NaN;
+            e.sum_a = 0.0;
+            e.sum_b = 0.0;
+            e.sites = sites;
+            return e;
+        };
+        uint32_t lo = 0, hi = 0;
+        site_range(m, rs, re, lo, hi);
+        const size_t ns = hi - lo;
+        if (ns == 0) {  // stats.rs:2152-2159
+            *overall = insufficient(0);
+            for (uint32_t i = 0; i < n_pairs; ++i) {
+                pairs[i] = insufficient(0);
+                if (pair_present) pair_present[i] = 0;
+            }
+            return;
+        }
+        const bool want_sites = site_state || site_a || site_b || site_pop_sizes || pair_a || pair_b || site_pos;
+        if (want_sites && ns > capacity) fail(FM_ERR_INVALID_ARG, "per-site output capacity too small");
+        for (fm_group *g : p->groups) ensure_counts(g);
+        std::vector<const uint32_t *> h_alt(G + 1), h_cnt(G + 1);
+        for (uint32_t g = 0; g <= G; ++g) {
+            h_alt[g] = p->groups[g]->d_alt;
+            h_cnt[g] = p->groups[g]->d_cnt;
+        }
+        DevBuf<const uint32_t *> d_alt(G + 1), d_cnt(G + 1);
+        d_alt.upload(h_alt.data(), G + 1);
+        d_cnt.upload(h_cnt.data(), G + 1);
+        std::vector<uint16_t> pi(std::max(n_pairs, 1u)), pj(std::max(n_pairs, 1u));
+        {
+            uint32_t k = 0;
+            for (uint32_t i = 0; i < G; ++i)
+                for (uint32_t j = i + 1; j < G; ++j, ++k) {
+                    pi[k] = (uint16_t)i;
+                    pj[k] = (uint16_t)j;
+                }
+        }
+        DevBuf<uint16_t> d_pi(pi.size()), d_pj(pj.size());
+        d_pi.upload(pi.data(), pi.size());
+        d_pj.upload(pj.data(), pj.size());
+
+        fm::WcParams W{};
+        W.alt = d_alt.p;
+        W.cnt = d_cnt.p;
+        W.G = G;
+        W.n_pairs = n_pairs;
+        W.pair_i = d_pi.p;
+        W.pair_j = d_pj.p;
+        W.v_lo = lo;
+        W.v_hi = hi;
+        W.s_lo = lo / fm::kWcSitesPerSuper;
+        W.n_super = (hi + fm::kWcSitesPerSuper - 1) / fm::kWcSitesPerSuper - W.s_lo;
+        DevBuf<int32_t> d_state;
+        DevBuf<double> d_sa, d_sb, d_pa, d_pb;
+        DevBuf<uint32_t> d_sizes;
+        if (site_state) { d_state.alloc(ns); W.site_state = d_state.p; }
+        if (site_a) { d_sa.alloc(ns); W.site_a = d_sa.p; }
+        if (site_b) { d_sb.alloc(ns); W.site_b = d_sb.p; }
+        if (site_pop_sizes && G) { d_sizes.alloc(ns * G); W.site_sizes = d_sizes.p; }
+        if (pair_a && pair_b && n_pairs) {
+            d_pa.alloc(ns * n_pairs);
+            d_pb.alloc(ns * n_pairs);
+            W.pair_a = d_pa.p;
+            W.pair_b = d_pb.p;
+        }
+        DevBuf<double> d_po((size_t)W.n_super * 2), d_pp((size_t)W.n_super * std::max(n_pairs, 1u) * 2);
+        DevBuf<uint32_t> d_pc((size_t)W.n_super * 2), d_pn((size_t)W.n_super * std::max(n_pairs, 1u));
+        W.part_overall = d_po.p;
+        W.part_counts = d_pc.p;
+        W.part_pair = d_pp.p;
+        W.part_pair_n = d_pn.p;
+
+        const size_t per_warp = (((size_t)32 * (G + 1) * 8 + (size_t)n_pairs * 20 + 16) + 15) & ~(size_t)15;
+        int warps = fm::kWcWarpsPerCta;
+        while (warps > 1 && per_warp * warps > 200 * 1024) --warps;
+        if (per_warp > 200 * 1024) fail(FM_ERR_UNSUPPORTED, "too many populations for the W&C kernel's staging");
+        // the kernel indexes shared memory with kWcWarpsPerCta warps; run fewer warps by shrinking
+        // the block (extra warps simply do not exist)
+        const size_t smem = per_warp * warps;
+        CK(cudaFuncSetAttribute(fm::fm_k_wc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const uint32_t blocks = std::max<uint32_t>(1, std::min<uint32_t>((W.n_super + warps - 1) / warps,
+                                                                         4u * sm_count(m->device)));
+        Timer tm;
+        tm.start();
+        fm::fm_k_wc<<<blocks, warps * 32, smem, stream()>>>(W);
+        CK(cudaGetLastError());
+        g_launches++;
+        tm.stop();
+        std::vector<double> h_po((size_t)W.n_super * 2), h_pp((size_t)W.n_super * std::max(n_pairs, 1u) * 2);
+        std::vector<uint32_t> h_pc((size_t)W.n_super * 2), h_pn((size_t)W.n_super * std::max(n_pairs, 1u));
+        d_po.download(h_po.data(), h_po.size());
+        d_pc.download(h_pc.data(), h_pc.size());
+        if (n_pairs) {
+            d_pp.download(h_pp.data(), (size_t)W.n_super * n_pairs * 2);
+            d_pn.download(h_pn.data(), (size_t)W.n_super * n_pairs);
+        }
+        if (site_state) d_state.download(site_state, ns);
+        if (site_a) d_sa.download(site_a, ns);
+        if (site_b) d_sb.download(site_b, ns);
+        if (W.site_sizes) d_sizes.download(site_pop_sizes, ns * G);
+        if (W.pair_a) {
+            d_pa.download(pair_a, ns * n_pairs);
+            d_pb.download(pair_b, ns * n_pairs);
+        }
+        CK(cudaStreamSynchronize(stream()));
+        t_tim.stats_ms += tm.ms();
+        if (site_pos)
+            for (size_t i = 0; i < ns; ++i) site_pos[i] = m->pos[lo + i] + 1;  // stats.rs:747
+        // region aggregation (stats.rs:2145-2374): super-batch partials combined in site order
+        double sum_a = 0.0, sum_b = 0.0;
+        uint64_t n_inf = 0, n_maps = 0;
+        for (uint32_t s = 0; s < W.n_super; ++s) {
+            sum_a += h_po[2 * s];
+            sum_b += h_po[2 * s + 1];
+            n_inf += h_pc[2 * s];
+            n_maps += h_pc[2 * s + 1];
+        }
+        *overall = n_inf == 0 ? insufficient(ns) : classify_estimate(sum_a, sum_b, n_inf);
+        for (uint32_t k = 0; k < n_pairs; ++k) {
+            double pa = 0.0, pb = 0.0;
+            uint64_t pn = 0;
+            for (uint32_t s = 0; s < W.n_super; ++s) {
+                pa += h_pp[((size_t)s * n_pairs + k) * 2];
+                pb += h_pp[((size_t)s * n_pairs + k) * 2 + 1];
+                pn += h_pn[(size_t)s * n_pairs + k];
+            }
+            if (pair_present) pair_present[k] = n_maps > 0;
+            if (n_maps == 0)
+                pairs[k] = insufficient(0);
+            else if (pn > 0)
+                pairs[k] = classify_estimate(pa, pb, pn);
+            else
+                pairs[k] = insufficient(n_maps);  // stats.rs:2342-2356
+        }
+        if (n_sites_out) *n_sites_out = ns;
+    });
 }
 
 // ------------------------------------------------------------------------------------ L_adj

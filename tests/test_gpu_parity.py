@@ -288,3 +288,110 @@ def test_window_sums_match_per_site_oracle():
         rc, ref, _ = orc.hudson_pair(orc.Pop(h1, None, 12, L, summary=sub1), orc.Pop(h2, None, 12, L, summary=sub2))
         fst = num[w] / den[w] if den[w] > 1e-12 else None
         assert close(fst, ref["fst"], 1e-10)
+
+
+# ------------------------------------------------------------------ Weir & Cockerham (K4)
+def _wc_compare(F, variants_py, vs, left, right, labels, region, rel=REL):
+    G = len(labels)
+    ref = orc.wc_fst(vs, left, right, G, region)
+    got = F.wc_fst_from_membership(variants_py, labels, left, right, region)
+    keys = [f"{labels[i]}_vs_{labels[j]}" for i in range(G) for j in range(i + 1, G)]
+    # region: overall
+    assert got.overall_fst.state == ref["overall"]["state"]
+    assert got.overall_fst.sites == ref["overall"]["sites"]
+    assert close(got.overall_fst.sum_a, ref["overall"]["sum_a"], rel)
+    assert close(got.overall_fst.sum_b, ref["overall"]["sum_b"], rel)
+    assert close(got.overall_fst.value, ref["overall"]["value"], rel)
+    # region: pairs
+    for k, key in enumerate(keys):
+        if not ref["pair_present"][k]:
+            assert key not in got.pairwise_fst
+            continue
+        e, r = got.pairwise_fst[key], ref["pairs"][k]
+        assert e.state == r["state"] and e.sites == r["sites"], key
+        assert close(e.sum_a, r["sum_a"], rel) and close(e.sum_b, r["sum_b"], rel), key
+        assert close(e.value, r["value"], rel), key
+        assert got.pairwise_variance_components[key] == (e.sum_a, e.sum_b)
+    # per site
+    assert len(got.site_fst) == ref["n_sites"]
+    for i, s in enumerate(got.site_fst):
+        assert s.position == ref["position"][i]
+        assert s.overall_fst.state == orc.STATE_NAMES[ref["state"][i]]
+        assert close(s.variance_components_a, float(ref["a"][i]), 1e-12)
+        assert close(s.variance_components_b, float(ref["b"][i]), 1e-12)
+        exp_sizes = {labels[g]: int(n) for g, n in enumerate(ref["pop_sizes"][i]) if n > 0} if ref["has_maps"][i] else {}
+        assert s.population_sizes == exp_sizes
+        if ref["has_maps"][i]:
+            for k, key in enumerate(keys):
+                st = ref["pair_state"][i][k]
+                assert s.pairwise_fst[key].state == orc.STATE_NAMES[st]
+                a, b = s.pairwise_variance_components[key]
+                assert close(a, float(ref["pair_a"][i][k]), 1e-12) and close(b, float(ref["pair_b"][i][k]), 1e-12)
+        else:
+            assert s.pairwise_fst == {} and s.pairwise_variance_components == {}
+    return got, ref
+
+
+def _to_python_variants(g, pos):
+    return [{"position": int(p), "genotypes": [None if (row < 0).any() else row.tolist() for row in site]}
+            for p, site in zip(pos, g)]
+
+
+@pytest.mark.parametrize("n_pops,missing", [(2, 0.0), (2, 0.3), (5, 0.15), (26, 0.02)])
+def test_wc_fst_matches_oracle(n_pops, missing):
+    F = fm()
+    S = 60 if n_pops < 26 else 130
+    V = 900 if n_pops < 26 else 300
+    g, pos, pops = make_cohort(V, S, n_pops=n_pops, sigma=0.08, missing_rate=missing, seed=100 + n_pops)
+    g[:, :, 1][g[:, :, 0] < 0] = -1
+    g[:, :, 0][g[:, :, 1] < 0] = -1
+    g[5] = 0          # monomorphic site
+    g[6] = -1         # no data at all -> InsufficientData (stats.rs:1987-2001)
+    g[7, : S // 2] = -1  # data only in some populations
+    rng = np.random.default_rng(n_pops)
+    left = np.full(S, 0xFFFF, dtype=np.uint16)
+    right = np.full(S, 0xFFFF, dtype=np.uint16)
+    for p, members in enumerate(pops):
+        left[members] = p
+        right[members] = p
+    # a few samples without a group (their alleles still count as "present", stats.rs:1826-1833)
+    # and a few whose two haplotypes sit in different groups
+    left[rng.choice(S, 3, replace=False)] = 0xFFFF
+    swap = rng.choice(S, 4, replace=False)
+    right[swap] = (right[swap] + 1) % n_pops
+    labels = sorted(str(i) for i in range(n_pops))  # lexicographic label order (stats.rs:1105-1107)
+    vs, _ = orc.from_numpy(g, pos)
+    variants_py = _to_python_variants(g, pos)
+    region = (int(pos[3]), int(pos[-10]))
+    _wc_compare(F, variants_py, vs, left, right, labels, region)
+
+
+def test_wc_fst_public_api_and_edge_cases():
+    F = fm()
+    names = ["s0", "s1", "s2", "s3"]
+    variants = [{"position": 10, "genotypes": [[0, 0], [0, 1], [1, 1], [0, 1]]},
+                {"position": 20, "genotypes": [[0, 1], [0, 1], [0, 1], [0, 1]]},
+                {"position": 30, "genotypes": [None, None, None, None]},
+                {"position": 40, "genotypes": [[0, 0], [0, 0], [1, 1], [1, 1]]}]
+    groups = {"s0": (0, 0), "s1": (0, 0), "s2_L": (1, 1), "s3": (1, 1), "unknown": (1, 0)}
+    res = F.wc_fst(variants, names, groups, (0, 100))
+    assert res.fst_type == "haplotype_groups"
+    assert len(res.site_fst) == 4 and [s.position for s in res.site_fst] == [11, 21, 31, 41]
+    assert res.site_fst[0].variance_components() == pytest.approx((0.125, 0.5), abs=1e-12)   # SURVEY §8c KATs
+    assert res.site_fst[1].variance_components() == pytest.approx((-1 / 6, 2 / 3), abs=1e-12)
+    assert res.site_fst[2].overall_fst.state == "insufficient_data_for_estimation"
+    assert res.site_fst[3].overall_fst.value == pytest.approx(1.0, abs=1e-12)
+    assert res.overall_fst.sites == 3 and set(res.pairwise_fst) == {"0_vs_1"}
+    a = 0.125 - 1 / 6 + 1.0
+    b = 0.5 + 2 / 3 + 0.0
+    assert res.overall_fst.sum_a == pytest.approx(a, rel=1e-12) and res.overall_fst.sum_b == pytest.approx(b, rel=1e-12)
+    assert res.overall_fst.value == pytest.approx(a / (a + b), rel=1e-12)
+    assert F.wc_fst_components(res.overall_fst) == res.overall_fst.components()
+    # empty region -> InsufficientData{sites_attempted: 0} and no pair keys (stats.rs:2152-2159)
+    res = F.wc_fst(variants, names, groups, (1000, 2000))
+    assert res.overall_fst.state == "insufficient_data_for_estimation" and res.overall_fst.sites == 0
+    assert res.pairwise_fst == {} and res.site_fst == []
+    with pytest.raises(ValueError):
+        F.wc_fst(variants, [], groups, (0, 100))
+    with pytest.raises(ValueError):
+        F.wc_fst(variants, names, groups, (10, 5))
