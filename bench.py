@@ -291,10 +291,12 @@ def run_ours(args):
         wall_ms = (time.perf_counter() - wall0) * 1e3
         if world > 1:
             dist.barrier()
-        # keep sampling a little so short runs still see clocks under load
-        if len(clocks.samples) < 3:
-            _lib.check(L.fm_bench_diversity(garr, 2, 1, mask.ctypes.data, mask.size // 2,
-                                            max(args.steps, 200), C.byref(_lib.BenchResult())))
+        # the timed region is a few milliseconds: keep the same kernels running (untimed) until the
+        # sampler has seen the clocks under this load a few times
+        t_keep = time.perf_counter()
+        while len(clocks.samples) < 8 and time.perf_counter() - t_keep < 4.0:
+            _lib.check(L.fm_bench_diversity(garr, 2, 1, mask.ctypes.data, mask.size // 2, 200,
+                                            C.byref(_lib.BenchResult())))
     tmax = torch.tensor([dev_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)

@@ -46,7 +46,7 @@ class BenchResult(C.Structure):
 
 
 EXPORTS = [
-    "fm_last_error", "fm_version", "fm_device_count", "fm_set_device", "fm_synchronize",
+    "fm_last_error", "fm_version", "fm_device_count", "fm_set_device", "fm_synchronize", "fm_trim_pool",
     "fm_matrix_create", "fm_matrix_create_device", "fm_matrix_retain", "fm_matrix_release",
     "fm_matrix_info", "fm_group_create", "fm_group_release", "fm_group_capacity", "fm_group_summary",
     "fm_group_segregating_sites", "fm_group_pi", "fm_harmonic", "fm_watterson_theta",

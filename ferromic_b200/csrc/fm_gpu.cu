@@ -77,6 +77,33 @@ void require_device() {
 
 cudaStream_t stream() { return cudaStreamPerThread; }
 
+// Device memory comes from the device's stream-ordered pool with the release threshold lifted, so
+// the bitplanes / u8 matrix of a released handle are reused by the next one instead of going back
+// to the driver (cudaMalloc + cudaFree of a 5 GB matrix cost far more than the kernels).
+// fm_trim_pool() hands the cached memory back.
+void pool_setup(int device) {
+    static std::mutex mu;
+    static bool done[64] = {};
+    std::lock_guard<std::mutex> lk(mu);
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX;
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    done[device] = true;
+}
+void *dev_alloc(size_t bytes) {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    pool_setup(dev);
+    void *p = nullptr;
+    CK(cudaMallocAsync(&p, std::max<size_t>(bytes, 16), stream()));
+    return p;
+}
+void dev_free(const void *p) {
+    if (p) cudaFreeAsync(const_cast<void *>(p), stream());
+}
+
 struct Timer {
     cudaEvent_t a, b;
     Timer() {
@@ -108,10 +135,10 @@ struct DevBuf {
     void alloc(size_t count) {
         release();
         n = count;
-        if (count) CK(cudaMalloc((void **)&p, count * sizeof(T)));
+        if (count) p = static_cast<T *>(dev_alloc(count * sizeof(T)));
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) dev_free(p);
         p = nullptr;
         n = 0;
     }
@@ -273,7 +300,7 @@ struct CounterPool {
     uint32_t *take(int dev) {
         if (device != dev) {  // a host thread normally stays on one device
             d = nullptr;
-            CK(cudaMalloc((void **)&d, (size_t)kLaunches * kWordsPerLaunch * sizeof(uint32_t)));
+            d = static_cast<uint32_t *>(dev_alloc((size_t)kLaunches * kWordsPerLaunch * sizeof(uint32_t)));
             device = dev;
             next = kLaunches;
         }
@@ -437,8 +464,8 @@ void ensure_counts(fm_group *g) {
     set_dev(g->m);
     const size_t V = g->m->V;
     if (!g->d_alt) {
-        CK(cudaMalloc((void **)&g->d_alt, std::max<size_t>(V, 1) * sizeof(uint32_t)));
-        CK(cudaMalloc((void **)&g->d_cnt, std::max<size_t>(V, 1) * sizeof(uint32_t)));
+        g->d_alt = static_cast<uint32_t *>(dev_alloc(std::max<size_t>(V, 1) * sizeof(uint32_t)));
+        g->d_cnt = static_cast<uint32_t *>(dev_alloc(std::max<size_t>(V, 1) * sizeof(uint32_t)));
     }
     DivResult r = run_diversity(g, 0, (uint32_t)V, FM_PIFORM_COUNTS, nullptr, nullptr, nullptr, 0,
                                 nullptr, 0, /*store_counts=*/true);
@@ -571,6 +598,17 @@ fm_status fm_synchronize(void) {
     });
 }
 
+fm_status fm_trim_pool(void) {
+    return guarded([&] {
+        require_device();
+        CK(cudaSetDevice(t_device));
+        CK(cudaStreamSynchronize(stream()));
+        cudaMemPool_t pool;
+        CK(cudaDeviceGetDefaultMemPool(&pool, t_device));
+        CK(cudaMemPoolTrimTo(pool, 0));
+    });
+}
+
 fm_status fm_timings_reset(void) {
     t_tim = fm_timings{};
     g_launches = 0;
@@ -617,18 +655,16 @@ fm_status fm_matrix_create(const uint8_t *data, const uint64_t *missing, size_t 
             if (total && !data) fail(FM_ERR_INVALID_ARG, "data is NULL");
             Timer tm;
             tm.start();
-            uint8_t *dd = nullptr;
-            CK(cudaMalloc((void **)&dd, std::max<size_t>(total, 16)));
+            uint8_t *dd = static_cast<uint8_t *>(dev_alloc(std::max<size_t>(total, 16)));
             m->d_data = dd;
             if (total) CK(cudaMemcpyAsync(dd, data, total, cudaMemcpyHostToDevice, stream()));
             if (missing) {
                 const size_t words = (total + 63) / 64;
-                uint64_t *dm = nullptr;
-                CK(cudaMalloc((void **)&dm, std::max<size_t>(words, 2) * 8));
+                uint64_t *dm = static_cast<uint64_t *>(dev_alloc(std::max<size_t>(words, 2) * 8));
                 m->d_missing = dm;
                 if (words) CK(cudaMemcpyAsync(dm, missing, words * 8, cudaMemcpyHostToDevice, stream()));
             }
-            CK(cudaMalloc((void **)&m->d_pos, std::max<size_t>(V, 1) * 8));
+            m->d_pos = static_cast<int64_t *>(dev_alloc(std::max<size_t>(V, 1) * 8));
             if (V) CK(cudaMemcpyAsync(m->d_pos, m->pos.data(), V * 8, cudaMemcpyHostToDevice, stream()));
             tm.stop();
             t_tim.h2d_ms += tm.ms();
@@ -653,7 +689,7 @@ fm_status fm_matrix_create_device(const uint8_t *d_data, const uint64_t *d_missi
         m->d_data = d_data;
         m->d_missing = d_missing;
         try {
-            CK(cudaMalloc((void **)&m->d_pos, std::max<size_t>(V, 1) * 8));
+            m->d_pos = static_cast<int64_t *>(dev_alloc(std::max<size_t>(V, 1) * 8));
             if (V) CK(cudaMemcpyAsync(m->d_pos, m->pos.data(), V * 8, cudaMemcpyHostToDevice, stream()));
             CK(cudaStreamSynchronize(stream()));
         } catch (...) {
@@ -675,10 +711,10 @@ fm_status fm_matrix_release(fm_matrix *m) {
     if (--m->refs == 0) {
         cudaSetDevice(m->device);
         if (m->owns) {
-            cudaFree((void *)m->d_data);
-            cudaFree((void *)m->d_missing);
+            dev_free(m->d_data);
+            dev_free(m->d_missing);
         }
-        cudaFree(m->d_pos);
+        dev_free(m->d_pos);
         delete m;
     }
     return FM_OK;
@@ -709,8 +745,8 @@ static fm_group *make_group(fm_matrix *m, std::vector<uint32_t> &&off) {
         g->n = (uint32_t)g->off.size();
         g->wq = std::max<uint32_t>(1, (g->n + 127) / 128);
         const size_t plane_u4 = std::max<size_t>(m->V, 1) * g->wq;
-        CK(cudaMalloc((void **)&g->d_allele, plane_u4 * 16));
-        if (m->d_missing) CK(cudaMalloc((void **)&g->d_called, plane_u4 * 16));
+        g->d_allele = static_cast<uint4 *>(dev_alloc(plane_u4 * 16));
+        if (m->d_missing) g->d_called = static_cast<uint4 *>(dev_alloc(plane_u4 * 16));
         // per-n tables: 1/n, n/(n-1) (stats.rs:2728-2732) and 1/H_{n-1} with the harmonic number
         // by forward summation exactly like stats.rs:4234-4240 / 4718-4719
         const size_t tn = (size_t)g->n + 1;
@@ -723,7 +759,7 @@ static fm_group *make_group(fm_matrix *m, std::vector<uint32_t> &&off) {
             T[2 * tn + k] = hsum > 0.0 ? 1.0 / hsum : 0.0;
             hsum += 1.0 / kd;
         }
-        CK(cudaMalloc((void **)&g->d_tab, T.size() * 8));
+        g->d_tab = static_cast<double *>(dev_alloc(T.size() * 8));
         CK(cudaMemcpyAsync(g->d_tab, T.data(), T.size() * 8, cudaMemcpyHostToDevice, stream()));
         DevBuf<uint32_t> d_off(std::max<size_t>(g->n, 1));
         d_off.upload(g->off.data(), g->n);
@@ -784,11 +820,11 @@ fm_status fm_group_create(fm_matrix *m, const uint64_t *sample_idx, const uint8_
 fm_status fm_group_release(fm_group *g) {
     if (!g) return FM_OK;
     if (g->m) cudaSetDevice(g->m->device);
-    cudaFree(g->d_allele);
-    cudaFree(g->d_called);
-    cudaFree(g->d_tab);
-    cudaFree(g->d_alt);
-    cudaFree(g->d_cnt);
+    dev_free(g->d_allele);
+    dev_free(g->d_called);
+    dev_free(g->d_tab);
+    dev_free(g->d_alt);
+    dev_free(g->d_cnt);
     fm_matrix_release(g->m);
     delete g;
     return FM_OK;
@@ -1061,8 +1097,8 @@ fm_status fm_hudson_pair(fm_group *g1, fm_group *g2, int64_t L1, int64_t L2, int
             if (!g1->have_counts && !g2->have_counts) {
                 for (fm_group *g : {g1, g2})
                     if (!g->d_alt) {
-                        CK(cudaMalloc((void **)&g->d_alt, (size_t)V * 4));
-                        CK(cudaMalloc((void **)&g->d_cnt, (size_t)V * 4));
+                        g->d_alt = static_cast<uint32_t *>(dev_alloc((size_t)V * 4));
+                        g->d_cnt = static_cast<uint32_t *>(dev_alloc((size_t)V * 4));
                     }
                 main_t = run_hudson_fused(g1, g2, 0, V, site_variant, e, true);
                 for (fm_group *g : {g1, g2}) {  // per-group summary scalars from the cached counts

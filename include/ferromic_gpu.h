@@ -47,6 +47,9 @@ const char *fm_version(void);
 fm_status fm_device_count(int *count);
 fm_status fm_set_device(int device); /* device used by handles created afterwards on this thread */
 fm_status fm_synchronize(void);
+/* Device buffers come from the device's stream-ordered memory pool and are kept for reuse when a
+ * handle is released; this returns the cached memory of the current device to the driver. */
+fm_status fm_trim_pool(void);
 
 /* ---- matrix: replaces DenseGenotypeMatrix::new / ::from_variants (stats.rs:261-296, 339-500) ----
  * data[v*S*ploidy + s*ploidy + side] = allele index; missing = packed bitmap, 1 bit per entry,
