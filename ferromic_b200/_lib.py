@@ -33,6 +33,11 @@ class FstEstimateC(C.Structure):
                 ("sum_b", C.c_double), ("sites", C.c_uint64)]
 
 
+class HudsonSums(C.Structure):
+    _fields_ = [("num", C.c_double), ("den", C.c_double), ("dxy", C.c_double), ("pi1", C.c_double),
+                ("pi2", C.c_double), ("dxy_uncallable", C.c_uint64), ("unc1", C.c_uint64), ("unc2", C.c_uint64)]
+
+
 class Timings(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("repack_ms", C.c_float), ("stats_ms", C.c_float),
                 ("reduce_ms", C.c_float), ("d2h_ms", C.c_float), ("stats_launches", C.c_uint64),
@@ -51,8 +56,8 @@ EXPORTS = [
     "fm_matrix_info", "fm_group_create", "fm_group_release", "fm_group_capacity", "fm_group_summary",
     "fm_group_segregating_sites", "fm_group_pi", "fm_harmonic", "fm_watterson_theta",
     "fm_per_site_diversity", "fm_hudson_pair", "fm_hudson_dxy", "fm_partition_create",
-    "fm_partition_release", "fm_wc_fst", "fm_adjusted_sequence_length", "fm_group_window_sums",
-    "fm_hudson_window_sums", "fm_timings_reset", "fm_timings_get", "fm_bench_diversity",
+    "fm_partition_release", "fm_wc_fst", "fm_wc_window_sums", "fm_fst_estimate_from_sums", "fm_adjusted_sequence_length", "fm_group_window_sums",
+    "fm_hudson_window_sums", "fm_pi_from_sums", "fm_hudson_outcome_from_sums", "fm_timings_reset", "fm_timings_get", "fm_bench_diversity",
     "fm_bench_hudson",
 ]
 
@@ -101,9 +106,13 @@ def lib() -> C.CDLL:
     L.fm_partition_release.argtypes = [vp]
     L.fm_wc_fst.argtypes = [vp, i64, i64, C.POINTER(FstEstimateC), vp, vp, vp, vp, vp, vp, vp, vp, vp, sz,
                             C.POINTER(sz)]
+    L.fm_wc_window_sums.argtypes = [vp, vp, sz, vp, vp, vp, vp, vp, vp, vp]
+    L.fm_fst_estimate_from_sums.argtypes = [dbl, dbl, u64, u64, C.POINTER(FstEstimateC)]
     L.fm_adjusted_sequence_length.argtypes = [i64, i64, vp, sz, vp, sz, C.POINTER(i64)]
     L.fm_group_window_sums.argtypes = [vp, vp, sz, vp, vp, vp, vp]
     L.fm_hudson_window_sums.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, vp, vp]
+    L.fm_pi_from_sums.argtypes = [dbl, u64, i64, sz, C.POINTER(dbl)]
+    L.fm_hudson_outcome_from_sums.argtypes = [C.POINTER(HudsonSums), i64, sz, sz, C.POINTER(HudsonOutcome)]
     L.fm_timings_get.argtypes = [C.POINTER(Timings)]
     L.fm_bench_diversity.argtypes = [C.POINTER(vp), sz, C.c_int, vp, sz, C.c_int, C.POINTER(BenchResult)]
     L.fm_bench_hudson.argtypes = [vp, vp, C.c_int, C.POINTER(BenchResult)]

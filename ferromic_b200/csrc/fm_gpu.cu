@@ -1226,6 +1226,9 @@ fm_status fm_partition_release(fm_partition *p) {
     return FM_OK;
 }
 
+static void window_ranges(const fm_matrix *m, const int64_t *windows, size_t n, std::vector<uint32_t> &lo,
+                          std::vector<uint32_t> &hi);
+
 static fm_fst_estimate classify_estimate(double a, double b, uint64_t sites) {
     // threshold ladder of stats.rs:2237-2270 / 2297-2328 (same as :1785-1811)
     fm_fst_estimate e;
@@ -1236,6 +1239,168 @@ static fm_fst_estimate classify_estimate(double a, double b, uint64_t sites) {
     e.state = fm_fst_state(a, b);
     if (e.state == 0) e.value = a / (a + b);
     return e;
+}
+
+namespace {
+struct WcSiteOut {
+    int32_t *state = nullptr;
+    double *a = nullptr, *b = nullptr;
+    uint32_t *sizes = nullptr;
+    double *pair_a = nullptr, *pair_b = nullptr;
+};
+struct WcWindowTotals {  // host copies, one entry per window
+    std::vector<double> overall;     // [n_w][2]
+    std::vector<uint64_t> sites;     // [n_w]
+    std::vector<double> pair;        // [n_w][n_pairs][2]
+    std::vector<uint64_t> pair_n;    // [n_w][n_pairs]
+};
+
+// K4 over a list of windows given as site-index ranges: segments cut at multiples of
+// kWcSegSites, one warp per segment, then the per-window fold.  Per-site outputs (host
+// pointers, indexed v - out_base) are only meaningful for a single window.
+void run_wc(fm_partition *p, const std::vector<uint32_t> &wlo, const std::vector<uint32_t> &whi,
+            const WcSiteOut &so, uint32_t out_base, size_t n_out_sites, WcWindowTotals &tot) {
+    fm_matrix *m = p->m;
+    const uint32_t G = (uint32_t)p->G;
+    const uint32_t n_pairs = G * (G > 0 ? G - 1 : 0) / 2;
+    const size_t nw = wlo.size();
+    tot.overall.assign(nw * 2, 0.0);
+    tot.sites.assign(nw, 0);
+    tot.pair.assign(nw * std::max(n_pairs, 1u) * 2, 0.0);
+    tot.pair_n.assign(nw * std::max(n_pairs, 1u), 0);
+    std::vector<uint32_t> seg_lo, seg_hi, wseg(nw + 1, 0);
+    for (size_t w = 0; w < nw; ++w) {
+        wseg[w] = (uint32_t)seg_lo.size();
+        for (uint32_t v = wlo[w]; v < whi[w];) {
+            const uint32_t e = std::min<uint64_t>(whi[w], ((uint64_t)v / fm::kWcSegSites + 1) * fm::kWcSegSites);
+            seg_lo.push_back(v);
+            seg_hi.push_back(e);
+            v = e;
+        }
+    }
+    wseg[nw] = (uint32_t)seg_lo.size();
+    const uint32_t n_seg = (uint32_t)seg_lo.size();
+    if (n_seg == 0) return;
+    for (fm_group *g : p->groups) ensure_counts(g);
+    set_dev(m);
+    std::vector<const uint32_t *> h_alt(G + 1), h_cnt(G + 1);
+    for (uint32_t g = 0; g <= G; ++g) {
+        h_alt[g] = p->groups[g]->d_alt;
+        h_cnt[g] = p->groups[g]->d_cnt;
+    }
+    DevBuf<const uint32_t *> d_alt(G + 1), d_cnt(G + 1);
+    d_alt.upload(h_alt.data(), G + 1);
+    d_cnt.upload(h_cnt.data(), G + 1);
+    std::vector<uint16_t> pi(std::max(n_pairs, 1u)), pj(std::max(n_pairs, 1u));
+    {
+        uint32_t k = 0;
+        for (uint32_t i = 0; i < G; ++i)
+            for (uint32_t j = i + 1; j < G; ++j, ++k) {
+                pi[k] = (uint16_t)i;
+                pj[k] = (uint16_t)j;
+            }
+    }
+    DevBuf<uint16_t> d_pi(pi.size()), d_pj(pj.size());
+    d_pi.upload(pi.data(), pi.size());
+    d_pj.upload(pj.data(), pj.size());
+    DevBuf<uint32_t> d_slo(n_seg), d_shi(n_seg), d_wseg(nw + 1);
+    d_slo.upload(seg_lo.data(), n_seg);
+    d_shi.upload(seg_hi.data(), n_seg);
+    d_wseg.upload(wseg.data(), nw + 1);
+
+    fm::WcParams W{};
+    W.alt = d_alt.p;
+    W.cnt = d_cnt.p;
+    W.G = G;
+    W.n_pairs = n_pairs;
+    W.pair_i = d_pi.p;
+    W.pair_j = d_pj.p;
+    W.seg_lo = d_slo.p;
+    W.seg_hi = d_shi.p;
+    W.n_seg = n_seg;
+    W.out_base = out_base;
+    const size_t ns = n_out_sites;
+    DevBuf<int32_t> d_state;
+    DevBuf<double> d_sa, d_sb, d_pa, d_pb;
+    DevBuf<uint32_t> d_sizes;
+    if (so.state && ns) { d_state.alloc(ns); W.site_state = d_state.p; }
+    if (so.a && ns) { d_sa.alloc(ns); W.site_a = d_sa.p; }
+    if (so.b && ns) { d_sb.alloc(ns); W.site_b = d_sb.p; }
+    if (so.sizes && G && ns) { d_sizes.alloc(ns * G); W.site_sizes = d_sizes.p; }
+    if (so.pair_a && so.pair_b && n_pairs && ns) {
+        d_pa.alloc(ns * n_pairs);
+        d_pb.alloc(ns * n_pairs);
+        W.pair_a = d_pa.p;
+        W.pair_b = d_pb.p;
+    }
+    DevBuf<double> d_po((size_t)n_seg * 2), d_pp((size_t)n_seg * std::max(n_pairs, 1u) * 2);
+    DevBuf<uint32_t> d_pc((size_t)n_seg), d_pn((size_t)n_seg * std::max(n_pairs, 1u));
+    W.part_overall = d_po.p;
+    W.part_counts = d_pc.p;
+    W.part_pair = d_pp.p;
+    W.part_pair_n = d_pn.p;
+
+    const size_t per_warp = fm::fm_wc_warp_smem(G, n_pairs);
+    int warps = fm::kWcWarpsPerCta;
+    while (warps > 1 && per_warp * warps > 200 * 1024) --warps;
+    if (per_warp > 200 * 1024) fail(FM_ERR_UNSUPPORTED, "too many populations for the W&C kernel's staging");
+    const size_t smem = per_warp * warps;
+    CK(cudaFuncSetAttribute(fm::fm_k_wc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t blocks = std::max<uint32_t>(
+        1, std::min<uint32_t>((n_seg + warps - 1) / warps, 16u * sm_count(m->device)));
+    Timer tm;
+    tm.start();
+    fm::fm_k_wc<<<blocks, warps * 32, smem, stream()>>>(W);
+    CK(cudaGetLastError());
+    g_launches++;
+    DevBuf<double> d_oo(nw * 2), d_op(nw * std::max(n_pairs, 1u) * 2);
+    DevBuf<uint64_t> d_os(nw), d_on(nw * std::max(n_pairs, 1u));
+    {
+        const uint64_t threads = (uint64_t)nw * (n_pairs + 1);
+        const uint32_t fb = (uint32_t)std::min<uint64_t>((threads + 127) / 128, 8ull * sm_count(m->device));
+        fm::fm_k_wc_fold<<<std::max(fb, 1u), 128, 0, stream()>>>(d_po.p, d_pc.p, d_pp.p, d_pn.p, d_wseg.p,
+                                                                  (uint32_t)nw, n_pairs, d_oo.p, d_os.p, d_op.p,
+                                                                  d_on.p);
+        CK(cudaGetLastError());
+        g_launches++;
+    }
+    tm.stop();
+    d_oo.download(tot.overall.data(), nw * 2);
+    d_os.download(tot.sites.data(), nw);
+    if (n_pairs) {
+        d_op.download(tot.pair.data(), nw * n_pairs * 2);
+        d_on.download(tot.pair_n.data(), nw * n_pairs);
+    }
+    if (W.site_state) d_state.download(so.state, ns);
+    if (W.site_a) d_sa.download(so.a, ns);
+    if (W.site_b) d_sb.download(so.b, ns);
+    if (W.site_sizes) d_sizes.download(so.sizes, ns * G);
+    if (W.pair_a) {
+        d_pa.download(so.pair_a, ns * n_pairs);
+        d_pb.download(so.pair_b, ns * n_pairs);
+    }
+    CK(cudaStreamSynchronize(stream()));
+    t_tim.stats_ms += tm.ms();
+}
+
+fm_fst_estimate insufficient_estimate(uint64_t sites) {
+    fm_fst_estimate e;
+    e.state = 3;
+    e.value = std::numeric_limits<double>::quiet_NaN();
+    e.sum_a = 0.0;
+    e.sum_b = 0.0;
+    e.sites = sites;
+    return e;
+}
+}  // namespace
+
+fm_status fm_fst_estimate_from_sums(double sum_a, double sum_b, uint64_t informative_sites,
+                                    uint64_t sites_attempted, fm_fst_estimate *out) {
+    if (!out) return FM_ERR_INVALID_ARG;
+    // stats.rs:2231-2270 (overall) / 2290-2356 (pairs)
+    *out = informative_sites == 0 ? insufficient_estimate(sites_attempted)
+                                  : classify_estimate(sum_a, sum_b, informative_sites);
+    return FM_OK;
 }
 
 fm_status fm_wc_fst(fm_partition *p, int64_t rs, int64_t re, fm_fst_estimate *overall, fm_fst_estimate *pairs,
@@ -1250,145 +1415,73 @@ fm_status fm_wc_fst(fm_partition *p, int64_t rs, int64_t re, fm_fst_estimate *ov
         const uint32_t G = (uint32_t)p->G;
         const uint32_t n_pairs = G * (G > 0 ? G - 1 : 0) / 2;
         if (n_pairs && !pairs) fail(FM_ERR_INVALID_ARG, "pairs is NULL");
-        const double NaN = std::numeric_limits<double>::quiet_NaN();
-        auto insufficient = [&](uint64_t sites) {
-            fm_fst_estimate e;
-            e.state = 3;
-            e.value = NaN;
-            e.sum_a = 0.0;
-            e.sum_b = 0.0;
-            e.sites = sites;
-            return e;
-        };
         uint32_t lo = 0, hi = 0;
         site_range(m, rs, re, lo, hi);
         const size_t ns = hi - lo;
         if (ns == 0) {  // stats.rs:2152-2159
-            *overall = insufficient(0);
+            *overall = insufficient_estimate(0);
             for (uint32_t i = 0; i < n_pairs; ++i) {
-                pairs[i] = insufficient(0);
+                pairs[i] = insufficient_estimate(0);
                 if (pair_present) pair_present[i] = 0;
             }
             return;
         }
         const bool want_sites = site_state || site_a || site_b || site_pop_sizes || pair_a || pair_b || site_pos;
         if (want_sites && ns > capacity) fail(FM_ERR_INVALID_ARG, "per-site output capacity too small");
-        for (fm_group *g : p->groups) ensure_counts(g);
-        std::vector<const uint32_t *> h_alt(G + 1), h_cnt(G + 1);
-        for (uint32_t g = 0; g <= G; ++g) {
-            h_alt[g] = p->groups[g]->d_alt;
-            h_cnt[g] = p->groups[g]->d_cnt;
-        }
-        DevBuf<const uint32_t *> d_alt(G + 1), d_cnt(G + 1);
-        d_alt.upload(h_alt.data(), G + 1);
-        d_cnt.upload(h_cnt.data(), G + 1);
-        std::vector<uint16_t> pi(std::max(n_pairs, 1u)), pj(std::max(n_pairs, 1u));
-        {
-            uint32_t k = 0;
-            for (uint32_t i = 0; i < G; ++i)
-                for (uint32_t j = i + 1; j < G; ++j, ++k) {
-                    pi[k] = (uint16_t)i;
-                    pj[k] = (uint16_t)j;
-                }
-        }
-        DevBuf<uint16_t> d_pi(pi.size()), d_pj(pj.size());
-        d_pi.upload(pi.data(), pi.size());
-        d_pj.upload(pj.data(), pj.size());
-
-        fm::WcParams W{};
-        W.alt = d_alt.p;
-        W.cnt = d_cnt.p;
-        W.G = G;
-        W.n_pairs = n_pairs;
-        W.pair_i = d_pi.p;
-        W.pair_j = d_pj.p;
-        W.v_lo = lo;
-        W.v_hi = hi;
-        W.s_lo = lo / fm::kWcSitesPerSuper;
-        W.n_super = (hi + fm::kWcSitesPerSuper - 1) / fm::kWcSitesPerSuper - W.s_lo;
-        DevBuf<int32_t> d_state;
-        DevBuf<double> d_sa, d_sb, d_pa, d_pb;
-        DevBuf<uint32_t> d_sizes;
-        if (site_state) { d_state.alloc(ns); W.site_state = d_state.p; }
-        if (site_a) { d_sa.alloc(ns); W.site_a = d_sa.p; }
-        if (site_b) { d_sb.alloc(ns); W.site_b = d_sb.p; }
-        if (site_pop_sizes && G) { d_sizes.alloc(ns * G); W.site_sizes = d_sizes.p; }
-        if (pair_a && pair_b && n_pairs) {
-            d_pa.alloc(ns * n_pairs);
-            d_pb.alloc(ns * n_pairs);
-            W.pair_a = d_pa.p;
-            W.pair_b = d_pb.p;
-        }
-        DevBuf<double> d_po((size_t)W.n_super * 2), d_pp((size_t)W.n_super * std::max(n_pairs, 1u) * 2);
-        DevBuf<uint32_t> d_pc((size_t)W.n_super * 2), d_pn((size_t)W.n_super * std::max(n_pairs, 1u));
-        W.part_overall = d_po.p;
-        W.part_counts = d_pc.p;
-        W.part_pair = d_pp.p;
-        W.part_pair_n = d_pn.p;
-
-        const size_t per_warp = (((size_t)32 * (G + 1) * 8 + (size_t)n_pairs * 20 + 16) + 15) & ~(size_t)15;
-        int warps = fm::kWcWarpsPerCta;
-        while (warps > 1 && per_warp * warps > 200 * 1024) --warps;
-        if (per_warp > 200 * 1024) fail(FM_ERR_UNSUPPORTED, "too many populations for the W&C kernel's staging");
-        // the kernel indexes shared memory with kWcWarpsPerCta warps; run fewer warps by shrinking
-        // the block (extra warps simply do not exist)
-        const size_t smem = per_warp * warps;
-        CK(cudaFuncSetAttribute(fm::fm_k_wc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const uint32_t blocks = std::max<uint32_t>(1, std::min<uint32_t>((W.n_super + warps - 1) / warps,
-                                                                         4u * sm_count(m->device)));
-        Timer tm;
-        tm.start();
-        fm::fm_k_wc<<<blocks, warps * 32, smem, stream()>>>(W);
-        CK(cudaGetLastError());
-        g_launches++;
-        tm.stop();
-        std::vector<double> h_po((size_t)W.n_super * 2), h_pp((size_t)W.n_super * std::max(n_pairs, 1u) * 2);
-        std::vector<uint32_t> h_pc((size_t)W.n_super * 2), h_pn((size_t)W.n_super * std::max(n_pairs, 1u));
-        d_po.download(h_po.data(), h_po.size());
-        d_pc.download(h_pc.data(), h_pc.size());
-        if (n_pairs) {
-            d_pp.download(h_pp.data(), (size_t)W.n_super * n_pairs * 2);
-            d_pn.download(h_pn.data(), (size_t)W.n_super * n_pairs);
-        }
-        if (site_state) d_state.download(site_state, ns);
-        if (site_a) d_sa.download(site_a, ns);
-        if (site_b) d_sb.download(site_b, ns);
-        if (W.site_sizes) d_sizes.download(site_pop_sizes, ns * G);
-        if (W.pair_a) {
-            d_pa.download(pair_a, ns * n_pairs);
-            d_pb.download(pair_b, ns * n_pairs);
-        }
-        CK(cudaStreamSynchronize(stream()));
-        t_tim.stats_ms += tm.ms();
+        WcSiteOut so;
+        so.state = site_state;
+        so.a = site_a;
+        so.b = site_b;
+        so.sizes = site_pop_sizes;
+        so.pair_a = pair_a;
+        so.pair_b = pair_b;
+        WcWindowTotals t;
+        run_wc(p, {lo}, {hi}, so, lo, ns, t);
         if (site_pos)
             for (size_t i = 0; i < ns; ++i) site_pos[i] = m->pos[lo + i] + 1;  // stats.rs:747
-        // region aggregation (stats.rs:2145-2374): super-batch partials combined in site order
-        double sum_a = 0.0, sum_b = 0.0;
-        uint64_t n_inf = 0, n_maps = 0;
-        for (uint32_t s = 0; s < W.n_super; ++s) {
-            sum_a += h_po[2 * s];
-            sum_b += h_po[2 * s + 1];
-            n_inf += h_pc[2 * s];
-            n_maps += h_pc[2 * s + 1];
-        }
-        *overall = n_inf == 0 ? insufficient(ns) : classify_estimate(sum_a, sum_b, n_inf);
+        // region aggregation (stats.rs:2145-2374)
+        const uint64_t n_inf = t.sites[0];
+        *overall = n_inf == 0 ? insufficient_estimate(ns) : classify_estimate(t.overall[0], t.overall[1], n_inf);
         for (uint32_t k = 0; k < n_pairs; ++k) {
-            double pa = 0.0, pb = 0.0;
-            uint64_t pn = 0;
-            for (uint32_t s = 0; s < W.n_super; ++s) {
-                pa += h_pp[((size_t)s * n_pairs + k) * 2];
-                pb += h_pp[((size_t)s * n_pairs + k) * 2 + 1];
-                pn += h_pn[(size_t)s * n_pairs + k];
-            }
-            if (pair_present) pair_present[k] = n_maps > 0;
-            if (n_maps == 0)
-                pairs[k] = insufficient(0);
+            const uint64_t pn = t.pair_n[k];
+            if (pair_present) pair_present[k] = n_inf > 0;
+            if (n_inf == 0)
+                pairs[k] = insufficient_estimate(0);
             else if (pn > 0)
-                pairs[k] = classify_estimate(pa, pb, pn);
+                pairs[k] = classify_estimate(t.pair[2 * k], t.pair[2 * k + 1], pn);
             else
-                pairs[k] = insufficient(n_maps);  // stats.rs:2342-2356
+                pairs[k] = insufficient_estimate(n_inf);  // stats.rs:2342-2356
         }
         if (n_sites_out) *n_sites_out = ns;
+    });
+}
+
+fm_status fm_wc_window_sums(fm_partition *p, const int64_t *windows, size_t n_windows, uint64_t *n_variants,
+                            double *overall_a, double *overall_b, uint64_t *overall_sites, double *pair_a,
+                            double *pair_b, uint64_t *pair_sites) {
+    return guarded([&] {
+        if (!p || (n_windows && !windows)) fail(FM_ERR_INVALID_ARG, "NULL argument");
+        require_device();
+        if (!n_windows) return;
+        fm_matrix *m = p->m;
+        const uint32_t G = (uint32_t)p->G;
+        const uint32_t n_pairs = G * (G > 0 ? G - 1 : 0) / 2;
+        std::vector<uint32_t> lo, hi;
+        window_ranges(m, windows, n_windows, lo, hi);
+        WcWindowTotals t;
+        run_wc(p, lo, hi, WcSiteOut{}, 0, 0, t);
+        for (size_t w = 0; w < n_windows; ++w) {
+            if (n_variants) n_variants[w] = hi[w] - lo[w];
+            if (overall_a) overall_a[w] = t.overall[2 * w];
+            if (overall_b) overall_b[w] = t.overall[2 * w + 1];
+            if (overall_sites) overall_sites[w] = t.sites[w];
+            for (uint32_t k = 0; k < n_pairs; ++k) {
+                const size_t o = w * n_pairs + k;
+                if (pair_a) pair_a[o] = t.pair[2 * o];
+                if (pair_b) pair_b[o] = t.pair[2 * o + 1];
+                if (pair_sites) pair_sites[o] = t.pair_n[o];
+            }
+        }
     });
 }
 
@@ -1517,6 +1610,50 @@ fm_status fm_hudson_window_sums(fm_group *g1, fm_group *g2, const int64_t *windo
             if (dxy_sum) dxy_sum[i] = h[i * 5 + 2];
             if (pi1_sum) pi1_sum[i] = h[i * 5 + 3];
             if (pi2_sum) pi2_sum[i] = h[i * 5 + 4];
+        }
+    });
+}
+
+// ------------------------------------------------------------------------------------ merged totals
+fm_status fm_pi_from_sums(double pi_sum, uint64_t unc, int64_t L, size_t cap, double *out) {
+    if (!out) return FM_ERR_INVALID_ARG;
+    const double NaN = std::numeric_limits<double>::quiet_NaN();
+    if (cap <= 1) *out = NaN;  // stats.rs:1485-1492
+    else if (L < 0) *out = 0.0;
+    else if (L == 0) *out = std::numeric_limits<double>::infinity();
+    else {
+        const int64_t eff = sat_sub(L, (int64_t)unc);  // :1512-1527
+        *out = eff == 0 ? NaN : pi_sum / (double)eff;
+    }
+    return FM_OK;
+}
+
+fm_status fm_hudson_outcome_from_sums(const fm_hudson_sums *t, int64_t L, size_t cap1, size_t cap2,
+                                      fm_hudson_outcome *out) {
+    return guarded([&] {
+        if (!t || !out) fail(FM_ERR_INVALID_ARG, "NULL argument");
+        std::memset(out, 0, sizeof(*out));
+        if (L <= 0)
+            fail(FM_ERR_INVALID_REGION, "Sequence length must be positive for Hudson FST calculation.");
+        if (t->den > FM_FST_EPSILON) {  // stats.rs:3505-3509
+            out->fst = t->num / t->den;
+            out->some |= 1u;
+        }
+        double p1, p2;
+        fm_pi_from_sums(t->pi1, t->unc1, L, cap1, &p1);
+        fm_pi_from_sums(t->pi2, t->unc2, L, cap2, &p2);
+        if (std::isfinite(p1)) { out->pi_pop1 = p1; out->some |= 4u; }
+        if (std::isfinite(p2)) { out->pi_pop2 = p2; out->some |= 8u; }
+        if (cap1 != 0 && cap2 != 0) {  // dxy_from_summaries (stats.rs:1637-1662)
+            const int64_t eff = sat_sub(L, (int64_t)t->dxy_uncallable);
+            if (eff > 0) {
+                out->d_xy = t->dxy / (double)eff;
+                out->some |= 2u;
+            }
+        }
+        if ((out->some & 12u) == 12u) {
+            out->pi_xy_avg = 0.5 * (out->pi_pop1 + out->pi_pop2);
+            out->some |= 16u;
         }
     });
 }

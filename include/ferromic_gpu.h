@@ -174,6 +174,20 @@ fm_status fm_wc_fst(fm_partition *p, int64_t region_start, int64_t region_end,
                     uint32_t *site_pop_sizes, double *pair_a, double *pair_b, size_t capacity,
                     size_t *n_sites);
 
+/* Shard-mergeable W&C window totals (sums and counts add across site shards; pair order i<j):
+ * per window #variants, overall sum a / sum b / #sites with an estimate, and per pair
+ * [n_windows * n_pairs] sum a / sum b / #informative sites.  Windows are 0-based inclusive
+ * [start,end] position pairs.  Any output pointer may be NULL. */
+fm_status fm_wc_window_sums(fm_partition *p, const int64_t *windows, size_t n_windows,
+                            uint64_t *n_variants, double *overall_a, double *overall_b,
+                            uint64_t *overall_sites, double *pair_a, double *pair_b,
+                            uint64_t *pair_sites);
+/* Region estimate from (merged) totals: the threshold ladder of calculate_overall_fst_wc
+ * (stats.rs:2231-2270, 2290-2356).  informative_sites == 0 -> InsufficientDataForEstimation with
+ * sites = sites_attempted. */
+fm_status fm_fst_estimate_from_sums(double sum_a, double sum_b, uint64_t informative_sites,
+                                    uint64_t sites_attempted, fm_fst_estimate *out);
+
 /* ---- calculate_adjusted_sequence_length (stats.rs:3644-3736); host integer arithmetic ----
  * region is 1-based inclusive; allow/mask are 0-based half-open pairs; NULL <=> None. */
 fm_status fm_adjusted_sequence_length(int64_t region_start, int64_t region_end,
@@ -191,6 +205,22 @@ fm_status fm_group_window_sums(fm_group *g, const int64_t *windows, size_t n_win
 fm_status fm_hudson_window_sums(fm_group *g1, fm_group *g2, const int64_t *windows, size_t n_windows,
                                 double *num_sum, double *den_sum, double *dxy_sum,
                                 uint64_t *dxy_uncallable, double *pi1_sum, double *pi2_sum);
+
+/* ---- finishing merged totals (host scalars; what every rank does after the gather) ----
+ * calculate_pi_from_summary_with_precomputed (stats.rs:1480-1542): pi = pi_sum / (L - uncallable)
+ * with the reference's guard order (haplotype_capacity <= 1 -> NaN; L < 0 -> 0; L == 0 -> +inf;
+ * effective length 0 -> NaN). */
+fm_status fm_pi_from_sums(double pi_sum, uint64_t uncallable_lt2, int64_t sequence_length,
+                          size_t haplotype_capacity, double *out);
+typedef struct {
+    double num, den, dxy, pi1, pi2;       /* sums over the sites of the window / shard          */
+    uint64_t dxy_uncallable, unc1, unc2;  /* #sites with n1==0||n2==0; #sites with n1<2; n2<2   */
+} fm_hudson_sums;
+/* Outcome of calculate_hudson_fst_for_pair_core on the summaries path (stats.rs:3476-3488,
+ * 3505-3566) from merged totals. */
+fm_status fm_hudson_outcome_from_sums(const fm_hudson_sums *sums, int64_t sequence_length,
+                                      size_t haplotype_capacity1, size_t haplotype_capacity2,
+                                      fm_hudson_outcome *out);
 
 /* ---- instrumentation for bench.py (device timings of the last call, milliseconds) ---- */
 typedef struct {
