@@ -53,7 +53,8 @@ class BenchResult(C.Structure):
 EXPORTS = [
     "fm_last_error", "fm_version", "fm_device_count", "fm_set_device", "fm_synchronize", "fm_trim_pool",
     "fm_matrix_create", "fm_matrix_create_device", "fm_matrix_retain", "fm_matrix_release",
-    "fm_matrix_info", "fm_group_create", "fm_group_release", "fm_group_capacity", "fm_group_summary",
+    "fm_matrix_info", "fm_ingest_begin", "fm_ingest_add_group", "fm_ingest_add_partition",
+    "fm_ingest_rows", "fm_ingest_finish", "fm_ingest_abort", "fm_group_create", "fm_group_release", "fm_group_capacity", "fm_group_summary",
     "fm_group_segregating_sites", "fm_group_pi", "fm_harmonic", "fm_watterson_theta",
     "fm_per_site_diversity", "fm_hudson_pair", "fm_hudson_dxy", "fm_partition_create",
     "fm_partition_release", "fm_wc_fst", "fm_wc_window_sums", "fm_fst_estimate_from_sums", "fm_adjusted_sequence_length", "fm_group_window_sums",
@@ -90,6 +91,12 @@ def lib() -> C.CDLL:
     L.fm_matrix_release.argtypes = [vp]
     L.fm_matrix_info.argtypes = [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), C.POINTER(C.c_uint8),
                                  C.POINTER(C.c_int)]
+    L.fm_ingest_begin.argtypes = [sz, sz, sz, C.c_int, C.c_uint8, vp, sz, C.POINTER(vp)]
+    L.fm_ingest_add_group.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
+    L.fm_ingest_add_partition.argtypes = [vp, vp, vp, sz, sz, C.POINTER(sz)]
+    L.fm_ingest_rows.argtypes = [vp, vp, vp, sz, sz]
+    L.fm_ingest_finish.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.fm_ingest_abort.argtypes = [vp]
     L.fm_group_create.argtypes = [vp, vp, vp, sz, C.POINTER(vp)]
     L.fm_group_release.argtypes = [vp]
     L.fm_group_capacity.argtypes = [vp, C.POINTER(sz)]

@@ -158,6 +158,59 @@ class _Matrix:
         self.handle = h
         self._groups: Dict[tuple, "_Group"] = {}
 
+    @classmethod
+    def ingest(cls, alleles: np.ndarray, missing_mask: Optional[np.ndarray], positions: np.ndarray,
+               group_haplotypes: Sequence[Sequence[Tuple[int, int]]], partitions=(), chunk_rows: int = 0,
+               calls: int = 1, always_bitmap: bool = False) -> "_Matrix":
+        """Streaming ingestion (fm_ingest_*): the u8 rows are uploaded in chunks and repacked into
+        the declared groups' bitplanes while the next chunk is in flight; the u8 matrix is never
+        resident.  partitions: (left, right, n_groups) triples; their handles land in
+        `self.partitions`.  calls > 1 pushes the rows in several fm_ingest_rows calls."""
+        a = np.ascontiguousarray(alleles, dtype=np.uint8)
+        assert a.ndim == 3
+        self = cls.__new__(cls)
+        self.V, self.S, self.P = a.shape
+        bits = None
+        if missing_mask is not None and (always_bitmap or missing_mask.any()):
+            bits = _pack_bits(np.ascontiguousarray(missing_mask, dtype=np.uint8).reshape(-1))
+        self.has_missing = bits is not None
+        self.max_allele = int(a.max()) if a.size else 0
+        pos = np.ascontiguousarray(positions, dtype=np.int64)
+        self._groups = {}
+        self.partitions = []
+        self.handle = None
+        L = lib()
+        ih = C.c_void_p()
+        check(L.fm_ingest_begin(self.V, self.S, self.P, int(self.has_missing), self.max_allele, _ptr(pos),
+                                chunk_rows, C.byref(ih)))
+        try:
+            for haps in group_haplotypes:
+                idx = np.asarray([h[0] for h in haps], dtype=np.uint64)
+                side = np.asarray([h[1] for h in haps], dtype=np.uint8)
+                check(L.fm_ingest_add_group(ih, _ptr(idx), _ptr(side), len(haps), None))
+            for left, right, ng in partitions:
+                lft = np.ascontiguousarray(left, dtype=np.uint16)
+                rgt = np.ascontiguousarray(right, dtype=np.uint16)
+                check(L.fm_ingest_add_partition(ih, _ptr(lft), _ptr(rgt), len(lft), ng, None))
+            flat = a.reshape(self.V, -1)
+            cuts = np.linspace(0, self.V, max(1, calls) + 1).astype(int)
+            for r0, r1 in zip(cuts[:-1], cuts[1:]):
+                if r1 > r0:
+                    check(L.fm_ingest_rows(ih, flat[r0:r1].ctypes.data, _ptr(bits), int(r0), int(r1 - r0)))
+            mh = C.c_void_p()
+            gh = (C.c_void_p * max(1, len(group_haplotypes)))()
+            ph = (C.c_void_p * max(1, len(partitions)))()
+            check(L.fm_ingest_finish(ih, C.byref(mh), gh, ph))
+            ih = None
+        finally:
+            if ih is not None:
+                L.fm_ingest_abort(ih)
+        self.handle = mh
+        for i, haps in enumerate(group_haplotypes):
+            self._groups[tuple(haps)] = _Group._adopt(self, haps, C.c_void_p(gh[i]))
+        self.partitions = [C.c_void_p(ph[i]) for i in range(len(partitions))]
+        return self
+
     def group(self, haplotypes: Sequence[Tuple[int, int]]) -> "_Group":
         key = tuple(haplotypes)
         g = self._groups.get(key)
@@ -169,6 +222,9 @@ class _Matrix:
     def __del__(self):
         try:
             self._groups.clear()
+            for ph in getattr(self, "partitions", []):
+                lib().fm_partition_release(ph)
+            self.partitions = []
             if getattr(self, "handle", None):
                 lib().fm_matrix_release(self.handle)
                 self.handle = None
@@ -185,6 +241,14 @@ class _Group:
         h = C.c_void_p()
         check(lib().fm_group_create(matrix.handle, _ptr(idx), _ptr(side), len(haplotypes), C.byref(h)))
         self.handle = h
+
+    @classmethod
+    def _adopt(cls, matrix: _Matrix, haplotypes, handle) -> "_Group":
+        self = cls.__new__(cls)
+        self.matrix = matrix
+        self.raw_n = len(haplotypes)
+        self.handle = handle
+        return self
 
     @property
     def capacity(self) -> int:

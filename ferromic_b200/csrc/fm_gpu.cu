@@ -12,8 +12,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <map>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 namespace {
@@ -77,31 +79,94 @@ void require_device() {
 
 cudaStream_t stream() { return cudaStreamPerThread; }
 
-// Device memory comes from the device's stream-ordered pool with the release threshold lifted, so
-// the bitplanes / u8 matrix of a released handle are reused by the next one instead of going back
-// to the driver (cudaMalloc + cudaFree of a 5 GB matrix cost far more than the kernels).
-// fm_trim_pool() hands the cached memory back.
-void pool_setup(int device) {
-    static std::mutex mu;
-    static bool done[64] = {};
-    std::lock_guard<std::mutex> lk(mu);
-    if (device < 0 || device >= 64 || done[device]) return;
-    cudaMemPool_t pool;
-    CK(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t thr = UINT64_MAX;
-    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-    done[device] = true;
+// Caching device allocator.  A released handle's bitplanes / staging buffers go to a per-device
+// free list keyed by (rounded) size and are handed to the next request instead of back to the
+// driver: cudaMalloc + cudaFree of multi-GB buffers cost far more than the kernels and vary by
+// 10x between calls.  Every cached block carries an event recorded on the freeing thread's
+// stream; the next owner's stream waits on it, so reuse is safe across threads.
+// fm_trim_pool() returns the cached memory to the driver.
+struct CachedBlock {
+    void *p;
+    cudaEvent_t ev;
+};
+struct DeviceCache {
+    std::mutex mu;
+    std::multimap<size_t, CachedBlock> free_blocks;  // rounded size -> block
+    std::unordered_map<const void *, size_t> live;    // live pointer -> rounded size
+};
+DeviceCache &cache_of(int device) {
+    static DeviceCache caches[64];
+    return caches[(device >= 0 && device < 64) ? device : 0];
+}
+size_t round_alloc(size_t bytes) {
+    if (bytes < ((size_t)1 << 20)) return (std::max<size_t>(bytes, 16) + 511) & ~(size_t)511;
+    return (bytes + (((size_t)2 << 20) - 1)) & ~(((size_t)2 << 20) - 1);
+}
+void cache_release_all(int device) {
+    DeviceCache &c = cache_of(device);
+    std::lock_guard<std::mutex> lk(c.mu);
+    for (auto &kv : c.free_blocks) {
+        cudaEventSynchronize(kv.second.ev);
+        cudaEventDestroy(kv.second.ev);
+        cudaFree(kv.second.p);
+    }
+    c.free_blocks.clear();
 }
 void *dev_alloc(size_t bytes) {
     int dev = 0;
     CK(cudaGetDevice(&dev));
-    pool_setup(dev);
+    const size_t want = round_alloc(bytes);
+    DeviceCache &c = cache_of(dev);
+    {
+        std::unique_lock<std::mutex> lk(c.mu);
+        auto it = c.free_blocks.lower_bound(want);
+        if (it != c.free_blocks.end() && it->first <= want + want / 4 + 4096) {
+            CachedBlock b = it->second;
+            const size_t sz = it->first;
+            c.free_blocks.erase(it);
+            c.live[b.p] = sz;
+            lk.unlock();
+            cudaStreamWaitEvent(stream(), b.ev, 0);  // work of the previous owner
+            cudaEventDestroy(b.ev);
+            return b.p;
+        }
+    }
     void *p = nullptr;
-    CK(cudaMallocAsync(&p, std::max<size_t>(bytes, 16), stream()));
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaErrorMemoryAllocation) {  // give the cached blocks back and retry once
+        cudaGetLastError();
+        cache_release_all(dev);
+        e = cudaMalloc(&p, want);
+    }
+    CK(e);
+    std::lock_guard<std::mutex> lk(c.mu);
+    c.live[p] = want;
     return p;
 }
 void dev_free(const void *p) {
-    if (p) cudaFreeAsync(const_cast<void *>(p), stream());
+    if (!p) return;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    DeviceCache &c = cache_of(dev);
+    size_t sz = 0;
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        auto it = c.live.find(p);
+        if (it == c.live.end()) return;  // not ours (caller-owned device buffers are never freed here)
+        sz = it->second;
+        c.live.erase(it);
+    }
+    CachedBlock b{const_cast<void *>(p), nullptr};
+    if (cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventRecord(b.ev, stream()) != cudaSuccess) {
+        cudaGetLastError();
+        if (b.ev) cudaEventDestroy(b.ev);
+        cudaDeviceSynchronize();
+        cudaFree(b.p);
+        return;
+    }
+    std::lock_guard<std::mutex> lk(c.mu);
+    c.free_blocks.emplace(sz, b);
 }
 
 struct Timer {
@@ -189,6 +254,8 @@ struct fm_matrix {
     int device = 0;
     const uint8_t *d_data = nullptr;
     const uint64_t *d_missing = nullptr;
+    bool has_missing = false;  // matrix carries a missing bitmap (d_missing is null after a streaming ingest)
+    bool streamed = false;     // u8 data was never resident: groups had to be declared before ingest
     bool owns = true;
     size_t V = 0, S = 0, ploidy = 0, stride = 0;
     uint8_t max_allele = 0;
@@ -205,6 +272,7 @@ struct fm_group {
     uint4 *d_allele = nullptr;
     uint4 *d_called = nullptr;
     double *d_tab = nullptr;   // 3 x (n+1) doubles: 1/k, k/(k-1), 1/H_{k-1}
+    uint32_t *d_off = nullptr; // device copy of `off` (K1)
     std::mutex mu;
     bool have_counts = false;
     uint32_t *d_alt = nullptr, *d_cnt = nullptr;
@@ -560,7 +628,7 @@ void merge_intervals(const int64_t *iv, size_t n, std::vector<int64_t> &out) {
     }
 }
 
-int dense_variant(const fm_matrix *m) { return m->d_missing ? FM_HV_DENSE_MISSING : FM_HV_DENSE_NOMISSING; }
+int dense_variant(const fm_matrix *m) { return m->has_missing ? FM_HV_DENSE_MISSING : FM_HV_DENSE_NOMISSING; }
 
 }  // namespace
 
@@ -603,9 +671,7 @@ fm_status fm_trim_pool(void) {
         require_device();
         CK(cudaSetDevice(t_device));
         CK(cudaStreamSynchronize(stream()));
-        cudaMemPool_t pool;
-        CK(cudaDeviceGetDefaultMemPool(&pool, t_device));
-        CK(cudaMemPoolTrimTo(pool, 0));
+        cache_release_all(t_device);
     });
 }
 
@@ -662,6 +728,7 @@ fm_status fm_matrix_create(const uint8_t *data, const uint64_t *missing, size_t 
                 const size_t words = (total + 63) / 64;
                 uint64_t *dm = static_cast<uint64_t *>(dev_alloc(std::max<size_t>(words, 2) * 8));
                 m->d_missing = dm;
+                m->has_missing = true;
                 if (words) CK(cudaMemcpyAsync(dm, missing, words * 8, cudaMemcpyHostToDevice, stream()));
             }
             m->d_pos = static_cast<int64_t *>(dev_alloc(std::max<size_t>(V, 1) * 8));
@@ -688,6 +755,7 @@ fm_status fm_matrix_create_device(const uint8_t *d_data, const uint64_t *d_missi
         m->owns = false;
         m->d_data = d_data;
         m->d_missing = d_missing;
+        m->has_missing = d_missing != nullptr;
         try {
             m->d_pos = static_cast<int64_t *>(dev_alloc(std::max<size_t>(V, 1) * 8));
             if (V) CK(cudaMemcpyAsync(m->d_pos, m->pos.data(), V * 8, cudaMemcpyHostToDevice, stream()));
@@ -727,13 +795,13 @@ fm_status fm_matrix_info(const fm_matrix *m, size_t *V, size_t *S, size_t *ploid
     if (S) *S = m->S;
     if (ploidy) *ploidy = m->ploidy;
     if (max_allele) *max_allele = m->max_allele;
-    if (has_missing) *has_missing = m->d_missing != nullptr;
+    if (has_missing) *has_missing = m->has_missing;
     return FM_OK;
 }
 
 // ------------------------------------------------------------------------------------ group
-// Repack the matrix columns listed in `off` (sorted, unique) into a group's bitplanes (K1).
-static fm_group *make_group(fm_matrix *m, std::vector<uint32_t> &&off) {
+// Allocate a group's bitplanes and lookup tables for the columns listed in `off` (sorted, unique).
+static fm_group *alloc_group(fm_matrix *m, std::vector<uint32_t> &&off) {
     if (m->max_allele > 1)
         fail(FM_ERR_UNSUPPORTED, "multi-allelic matrices (max_allele > 1) are not on the GPU path yet");
     set_dev(m);
@@ -746,7 +814,7 @@ static fm_group *make_group(fm_matrix *m, std::vector<uint32_t> &&off) {
         g->wq = std::max<uint32_t>(1, (g->n + 127) / 128);
         const size_t plane_u4 = std::max<size_t>(m->V, 1) * g->wq;
         g->d_allele = static_cast<uint4 *>(dev_alloc(plane_u4 * 16));
-        if (m->d_missing) g->d_called = static_cast<uint4 *>(dev_alloc(plane_u4 * 16));
+        if (m->has_missing) g->d_called = static_cast<uint4 *>(dev_alloc(plane_u4 * 16));
         // per-n tables: 1/n, n/(n-1) (stats.rs:2728-2732) and 1/H_{n-1} with the harmonic number
         // by forward summation exactly like stats.rs:4234-4240 / 4718-4719
         const size_t tn = (size_t)g->n + 1;
@@ -761,19 +829,44 @@ static fm_group *make_group(fm_matrix *m, std::vector<uint32_t> &&off) {
         }
         g->d_tab = static_cast<double *>(dev_alloc(T.size() * 8));
         CK(cudaMemcpyAsync(g->d_tab, T.data(), T.size() * 8, cudaMemcpyHostToDevice, stream()));
-        DevBuf<uint32_t> d_off(std::max<size_t>(g->n, 1));
-        d_off.upload(g->off.data(), g->n);
+        g->d_off = static_cast<uint32_t *>(dev_alloc(std::max<size_t>(g->n, 1) * 4));
+        if (g->n) CK(cudaMemcpyAsync(g->d_off, g->off.data(), (size_t)g->n * 4, cudaMemcpyHostToDevice, stream()));
+        CK(cudaStreamSynchronize(stream()));  // T and off are host temporaries / may be moved
+    } catch (...) {
+        fm_group_release(g);
+        throw;
+    }
+    return g;
+}
+
+// K1 for rows [v_lo, v_hi) of a group: `data` / `missing` point at the u8 row v_base and at the
+// bitmap word word_base (resident matrix: v_base = word_base = 0; streaming ingest: the staged chunk).
+static void launch_repack(const fm_group *g, const uint8_t *data, const uint64_t *missing, uint32_t v_base,
+                          uint64_t word_base, uint32_t v_lo, uint32_t v_hi, cudaStream_t st) {
+    const fm_matrix *m = g->m;
+    if (v_hi <= v_lo) return;
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>(
+        (uint64_t)sm_count(m->device) * 8,
+        std::max<uint64_t>(1, ((uint64_t)(v_hi - v_lo) * ((g->wq * 4 + 31) / 32) + 7) / 8));
+    fm::fm_k_repack<<<blocks, 256, 0, st>>>(data, missing, m->stride, g->d_off, g->n, g->wq, v_base, word_base,
+                                            v_lo, v_hi, reinterpret_cast<uint32_t *>(g->d_allele),
+                                            reinterpret_cast<uint32_t *>(g->d_called));
+    CK(cudaGetLastError());
+    g_launches++;
+}
+
+// Repack the resident matrix columns listed in `off` into a new group's bitplanes.
+static fm_group *make_group(fm_matrix *m, std::vector<uint32_t> &&off) {
+    if (m->streamed)
+        fail(FM_ERR_UNSUPPORTED,
+             "this matrix was ingested in streaming mode (its u8 rows are not resident): declare groups "
+             "with fm_ingest_add_group / fm_ingest_add_partition before fm_ingest_rows");
+    fm_group *g = alloc_group(m, std::move(off));
+    try {
         if (m->V) {
             Timer tm;
             tm.start();
-            const uint32_t blocks = (uint32_t)std::min<uint64_t>(
-                (uint64_t)sm_count(m->device) * 8,
-                std::max<uint64_t>(1, ((uint64_t)m->V * ((g->wq * 4 + 31) / 32) + 7) / 8));
-            fm::fm_k_repack<<<blocks, 256, 0, stream()>>>(
-                m->d_data, m->d_missing, m->stride, d_off.p, g->n, g->wq, 0, (uint32_t)m->V,
-                reinterpret_cast<uint32_t *>(g->d_allele), reinterpret_cast<uint32_t *>(g->d_called));
-            CK(cudaGetLastError());
-            g_launches++;
+            launch_repack(g, m->d_data, m->d_missing, 0, 0, 0, (uint32_t)m->V, stream());
             tm.stop();
             t_tim.repack_ms += tm.ms();
         }
@@ -785,6 +878,53 @@ static fm_group *make_group(fm_matrix *m, std::vector<uint32_t> &&off) {
     return g;
 }
 
+// DenseMembership::build (stats.rs:1251-1284): sorted, de-duplicated offsets
+static std::vector<uint32_t> membership_offsets(const fm_matrix *m, const uint64_t *sample_idx, const uint8_t *side,
+                                                size_t n) {
+    std::vector<uint8_t> left(m->S, 0), right(m->S, 0);
+    std::vector<uint32_t> off;
+    off.reserve(n);
+    for (size_t i = 0; i < n; ++i) {
+        const uint64_t s = sample_idx[i];
+        if (s >= m->S) continue;
+        if (side[i] == 0) {
+            if (!left[s]) {
+                left[s] = 1;
+                off.push_back((uint32_t)(s * m->ploidy));
+            }
+        } else {
+            if (m->ploidy <= 1) continue;
+            if (!right[s]) {
+                right[s] = 1;
+                off.push_back((uint32_t)(s * m->ploidy + 1));
+            }
+        }
+    }
+    std::sort(off.begin(), off.end());
+    return off;
+}
+
+// SubpopulationMembership (stats.rs:1093-1150): Left -> genotype[0], Right -> genotype[1];
+// slot n_groups collects the haplotypes without a group
+static std::vector<std::vector<uint32_t>> partition_columns(const fm_matrix *m, const uint16_t *left,
+                                                            const uint16_t *right, size_t n_samples,
+                                                            size_t n_groups) {
+    std::vector<std::vector<uint32_t>> cols(n_groups + 1);
+    const size_t P = m->ploidy;
+    for (size_t s = 0; s < m->S; ++s) {
+        for (size_t k = 0; k < P; ++k) {
+            uint16_t g = 0xFFFF;
+            if (s < n_samples) {
+                if (k == 0) g = left[s];
+                else if (k == 1) g = right[s];
+            }
+            const size_t slot = (g != 0xFFFF && g < n_groups) ? g : n_groups;
+            cols[slot].push_back((uint32_t)(s * P + k));
+        }
+    }
+    return cols;
+}
+
 fm_status fm_group_create(fm_matrix *m, const uint64_t *sample_idx, const uint8_t *side, size_t n,
                           fm_group **out) {
     return guarded([&] {
@@ -792,27 +932,7 @@ fm_status fm_group_create(fm_matrix *m, const uint64_t *sample_idx, const uint8_
         *out = nullptr;
         if (n && (!sample_idx || !side)) fail(FM_ERR_INVALID_ARG, "haplotype arrays are NULL");
         require_device();
-        // DenseMembership::build (stats.rs:1251-1284)
-        std::vector<uint8_t> left(m->S, 0), right(m->S, 0);
-        std::vector<uint32_t> off;
-        off.reserve(n);
-        for (size_t i = 0; i < n; ++i) {
-            const uint64_t s = sample_idx[i];
-            if (s >= m->S) continue;
-            if (side[i] == 0) {
-                if (!left[s]) {
-                    left[s] = 1;
-                    off.push_back((uint32_t)(s * m->ploidy));
-                }
-            } else {
-                if (m->ploidy <= 1) continue;
-                if (!right[s]) {
-                    right[s] = 1;
-                    off.push_back((uint32_t)(s * m->ploidy + 1));
-                }
-            }
-        }
-        std::sort(off.begin(), off.end());
+        std::vector<uint32_t> off = membership_offsets(m, sample_idx, side, n);
         *out = make_group(m, std::move(off));
     });
 }
@@ -823,6 +943,7 @@ fm_status fm_group_release(fm_group *g) {
     dev_free(g->d_allele);
     dev_free(g->d_called);
     dev_free(g->d_tab);
+    dev_free(g->d_off);
     dev_free(g->d_alt);
     dev_free(g->d_cnt);
     fm_matrix_release(g->m);
@@ -888,7 +1009,7 @@ fm_status fm_group_pi(fm_group *g, int64_t L, int path, size_t raw_n, double *ou
         set_dev(g->m);
         double pi_sum;
         uint64_t skipped;
-        if (path == FM_PI_SUMMARY || (path == FM_PI_DENSE && g->m->d_missing)) {
+        if (path == FM_PI_SUMMARY || (path == FM_PI_DENSE && g->m->has_missing)) {
             pi_sum = g->pi_sum;  // dense_pi_from_counts form
             skipped = g->unc;
         } else {
@@ -975,6 +1096,201 @@ fm_status fm_per_site_diversity(fm_group *g, size_t raw_n, int64_t rs, int64_t r
     });
 }
 
+// ------------------------------------------------------------------------------------ streaming ingest
+// the u8 matrix is handed over in row chunks, staged in two device buffers and
+// repacked straight into the bitplanes of every declared group while the next chunk is still
+// on the PCIe bus.  The u8 rows are never resident (1.125 B/genotype of HBM and the separate
+// repack pass are saved).
+struct fm_ingest {
+    fm_matrix *m = nullptr;
+    std::vector<fm_group *> groups;       // declared with fm_ingest_add_group (owned until finish)
+    std::vector<fm_partition *> parts;    // declared with fm_ingest_add_partition
+    std::vector<fm_group *> all;          // every group that receives rows
+    size_t chunk_rows = 0, rows_done = 0;
+    uint8_t *stage[2] = {nullptr, nullptr};
+    uint64_t *stage_m[2] = {nullptr, nullptr};
+    size_t stage_words = 0;
+    cudaStream_t copy_s = nullptr, comp_s = nullptr;
+    cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+    cudaEvent_t t_copy0 = nullptr, t_copy1 = nullptr, t_comp0 = nullptr, t_comp1 = nullptr;
+    bool used[2] = {false, false};
+    bool timing_started = false;
+    int next = 0;
+};
+
+static void ingest_destroy(fm_ingest *h, bool release_handles) {
+    if (!h) return;
+    if (h->m) cudaSetDevice(h->m->device);
+    if (h->copy_s) cudaStreamSynchronize(h->copy_s);
+    if (h->comp_s) cudaStreamSynchronize(h->comp_s);
+    for (int i = 0; i < 2; ++i) {
+        dev_free(h->stage[i]);
+        dev_free(h->stage_m[i]);
+        if (h->copied[i]) cudaEventDestroy(h->copied[i]);
+        if (h->consumed[i]) cudaEventDestroy(h->consumed[i]);
+    }
+    for (cudaEvent_t e : {h->t_copy0, h->t_copy1, h->t_comp0, h->t_comp1})
+        if (e) cudaEventDestroy(e);
+    if (h->copy_s) cudaStreamDestroy(h->copy_s);
+    if (h->comp_s) cudaStreamDestroy(h->comp_s);
+    if (release_handles) {
+        for (fm_group *g : h->groups) fm_group_release(g);
+        for (fm_partition *p : h->parts) fm_partition_release(p);
+        fm_matrix_release(h->m);
+    }
+    delete h;
+}
+
+fm_status fm_ingest_begin(size_t V, size_t S, size_t ploidy, int has_missing, uint8_t max_allele,
+                          const int64_t *positions, size_t chunk_rows, fm_ingest **out) {
+    return guarded([&] {
+        if (!out) fail(FM_ERR_INVALID_ARG, "out is NULL");
+        *out = nullptr;
+        require_device();
+        CK(cudaSetDevice(t_device));
+        fm_ingest *h = new fm_ingest();
+        try {
+            h->m = matrix_common(V, S, ploidy, max_allele, positions);
+            h->m->has_missing = has_missing != 0;
+            h->m->streamed = true;
+            h->m->d_pos = static_cast<int64_t *>(dev_alloc(std::max<size_t>(V, 1) * 8));
+            if (V) CK(cudaMemcpyAsync(h->m->d_pos, h->m->pos.data(), V * 8, cudaMemcpyHostToDevice, stream()));
+            const size_t stride = std::max<size_t>(h->m->stride, 1);
+            if (chunk_rows == 0) chunk_rows = std::max<size_t>(32, ((size_t)64 << 20) / stride);
+            chunk_rows = std::min(std::max<size_t>(chunk_rows, 1), std::max<size_t>(V, 1));
+            h->chunk_rows = chunk_rows;
+            h->stage_words = (chunk_rows * stride + 63) / 64 + 2;
+            for (int i = 0; i < 2; ++i) {
+                h->stage[i] = static_cast<uint8_t *>(dev_alloc(chunk_rows * stride));
+                if (has_missing) h->stage_m[i] = static_cast<uint64_t *>(dev_alloc(h->stage_words * 8));
+                CK(cudaEventCreateWithFlags(&h->copied[i], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&h->consumed[i], cudaEventDisableTiming));
+            }
+            CK(cudaEventCreate(&h->t_copy0));
+            CK(cudaEventCreate(&h->t_copy1));
+            CK(cudaEventCreate(&h->t_comp0));
+            CK(cudaEventCreate(&h->t_comp1));
+            CK(cudaStreamCreateWithFlags(&h->copy_s, cudaStreamNonBlocking));
+            CK(cudaStreamCreateWithFlags(&h->comp_s, cudaStreamNonBlocking));
+            CK(cudaStreamSynchronize(stream()));  // staging buffers are now usable from any stream
+        } catch (...) {
+            ingest_destroy(h, true);
+            throw;
+        }
+        *out = h;
+    });
+}
+
+fm_status fm_ingest_add_group(fm_ingest *h, const uint64_t *sample_idx, const uint8_t *side, size_t n,
+                              size_t *group_index) {
+    return guarded([&] {
+        if (!h) fail(FM_ERR_INVALID_ARG, "ingest handle is NULL");
+        if (n && (!sample_idx || !side)) fail(FM_ERR_INVALID_ARG, "haplotype arrays are NULL");
+        if (h->rows_done) fail(FM_ERR_INVALID_ARG, "groups must be declared before the first fm_ingest_rows");
+        fm_group *g = alloc_group(h->m, membership_offsets(h->m, sample_idx, side, n));
+        h->groups.push_back(g);
+        h->all.push_back(g);
+        if (group_index) *group_index = h->groups.size() - 1;
+    });
+}
+
+fm_status fm_ingest_add_partition(fm_ingest *h, const uint16_t *left, const uint16_t *right, size_t n_samples,
+                                  size_t n_groups, size_t *partition_index) {
+    return guarded([&] {
+        if (!h) fail(FM_ERR_INVALID_ARG, "ingest handle is NULL");
+        if (n_samples && (!left || !right)) fail(FM_ERR_INVALID_ARG, "membership arrays are NULL");
+        if (n_groups >= 0xFFFF) fail(FM_ERR_INVALID_ARG, "too many groups");
+        if (h->rows_done) fail(FM_ERR_INVALID_ARG, "partitions must be declared before the first fm_ingest_rows");
+        fm_partition *p = new fm_partition();
+        p->m = h->m;
+        p->G = n_groups;
+        fm_matrix_retain(h->m);
+        try {
+            std::vector<std::vector<uint32_t>> cols = partition_columns(h->m, left, right, n_samples, n_groups);
+            for (size_t g = 0; g <= n_groups; ++g) p->groups.push_back(alloc_group(h->m, std::move(cols[g])));
+        } catch (...) {
+            fm_partition_release(p);
+            throw;
+        }
+        h->parts.push_back(p);
+        for (fm_group *g : p->groups) h->all.push_back(g);
+        if (partition_index) *partition_index = h->parts.size() - 1;
+    });
+}
+
+fm_status fm_ingest_rows(fm_ingest *h, const uint8_t *rows, const uint64_t *missing_whole, size_t first_row,
+                         size_t n_rows) {
+    return guarded([&] {
+        if (!h) fail(FM_ERR_INVALID_ARG, "ingest handle is NULL");
+        fm_matrix *m = h->m;
+        if (first_row > m->V || n_rows > m->V - first_row) fail(FM_ERR_INVALID_ARG, "row range outside the matrix");
+        if (n_rows && m->stride && !rows) fail(FM_ERR_INVALID_ARG, "rows is NULL");
+        if (m->has_missing && !missing_whole) fail(FM_ERR_INVALID_ARG, "matrix was declared with a missing bitmap");
+        set_dev(m);
+        const size_t stride = m->stride;
+        if (!h->timing_started && n_rows) {
+            CK(cudaEventRecord(h->t_copy0, h->copy_s));
+            CK(cudaEventRecord(h->t_comp0, h->comp_s));
+            h->timing_started = true;
+        }
+        for (size_t r0 = first_row; r0 < first_row + n_rows; r0 += h->chunk_rows) {
+            const size_t r1 = std::min(first_row + n_rows, r0 + h->chunk_rows);
+            const int b = h->next;
+            h->next ^= 1;
+            if (h->used[b]) CK(cudaStreamWaitEvent(h->copy_s, h->consumed[b], 0));
+            if (stride)
+                CK(cudaMemcpyAsync(h->stage[b], rows + (r0 - first_row) * stride, (r1 - r0) * stride,
+                                   cudaMemcpyHostToDevice, h->copy_s));
+            uint64_t w0 = 0;
+            if (m->has_missing && stride) {
+                w0 = (uint64_t)(r0 * stride) >> 6;
+                const uint64_t w1 = ((uint64_t)(r1 * stride) + 63) >> 6;
+                CK(cudaMemcpyAsync(h->stage_m[b], missing_whole + w0, (w1 - w0) * 8, cudaMemcpyHostToDevice,
+                                   h->copy_s));
+            }
+            CK(cudaEventRecord(h->copied[b], h->copy_s));
+            CK(cudaStreamWaitEvent(h->comp_s, h->copied[b], 0));
+            for (fm_group *g : h->all)
+                launch_repack(g, h->stage[b], m->has_missing ? h->stage_m[b] : nullptr, (uint32_t)r0, w0,
+                              (uint32_t)r0, (uint32_t)r1, h->comp_s);
+            CK(cudaEventRecord(h->consumed[b], h->comp_s));
+            h->used[b] = true;
+        }
+        h->rows_done += n_rows;
+        CK(cudaEventRecord(h->t_copy1, h->copy_s));
+        CK(cudaEventRecord(h->t_comp1, h->comp_s));
+        CK(cudaStreamSynchronize(h->copy_s));  // the caller's buffers are free again on return
+    });
+}
+
+fm_status fm_ingest_finish(fm_ingest *h, fm_matrix **matrix_out, fm_group **groups_out, fm_partition **parts_out) {
+    return guarded([&] {
+        if (!h) fail(FM_ERR_INVALID_ARG, "ingest handle is NULL");
+        if (h->rows_done != h->m->V)
+            fail(FM_ERR_INVALID_ARG, "fm_ingest_finish before every row was ingested");
+        if ((!groups_out && !h->groups.empty()) || (!parts_out && !h->parts.empty()) || !matrix_out)
+            fail(FM_ERR_INVALID_ARG, "output arrays are NULL");
+        set_dev(h->m);
+        CK(cudaStreamSynchronize(h->comp_s));
+        if (h->timing_started) {
+            float a = 0.f, b = 0.f;
+            CK(cudaEventElapsedTime(&a, h->t_copy0, h->t_copy1));
+            CK(cudaEventElapsedTime(&b, h->t_comp0, h->t_comp1));
+            t_tim.h2d_ms += a;      // span of the copy stream
+            t_tim.repack_ms += b;   // span of the repack stream (overlaps the copies)
+        }
+        *matrix_out = h->m;
+        for (size_t i = 0; i < h->groups.size(); ++i) groups_out[i] = h->groups[i];
+        for (size_t i = 0; i < h->parts.size(); ++i) parts_out[i] = h->parts[i];
+        ingest_destroy(h, false);
+    });
+}
+
+fm_status fm_ingest_abort(fm_ingest *h) {
+    ingest_destroy(h, true);
+    return FM_OK;
+}
+
 // ------------------------------------------------------------------------------------ Hudson
 static void check_pair(fm_group *g1, fm_group *g2, bool allow_distinct_matrices = false) {
     if (!g1 || !g2) fail(FM_ERR_INVALID_ARG, "group is NULL");
@@ -1034,7 +1350,7 @@ static double pi_outcome(int path, fm_group *g, int64_t L, size_t raw_n, double 
     if (L < 0) return 0.0;
     if (L == 0) return std::numeric_limits<double>::infinity();
     if (path == FM_HUDSON_SPARSE && g->n <= 1) return NaN;
-    const uint64_t skipped = (path == FM_HUDSON_DENSE && !g->m->d_missing) ? 0 : unc;
+    const uint64_t skipped = (path == FM_HUDSON_DENSE && !g->m->has_missing) ? 0 : unc;
     const int64_t eff = sat_sub(L, (int64_t)skipped);
     if (eff == 0) return NaN;
     return pi_sum / (double)eff;
@@ -1195,20 +1511,7 @@ fm_status fm_partition_create(fm_matrix *m, const uint16_t *left, const uint16_t
         p->G = n_groups;
         fm_matrix_retain(m);
         try {
-            // SubpopulationMembership (stats.rs:1093-1150): Left -> genotype[0], Right -> genotype[1]
-            std::vector<std::vector<uint32_t>> cols(n_groups + 1);
-            const size_t P = m->ploidy;
-            for (size_t s = 0; s < m->S; ++s) {
-                for (size_t k = 0; k < P; ++k) {
-                    uint16_t g = 0xFFFF;
-                    if (s < n_samples) {
-                        if (k == 0) g = left[s];
-                        else if (k == 1) g = right[s];
-                    }
-                    const size_t slot = (g != 0xFFFF && g < n_groups) ? g : n_groups;
-                    cols[slot].push_back((uint32_t)(s * P + k));
-                }
-            }
+            std::vector<std::vector<uint32_t>> cols = partition_columns(m, left, right, n_samples, n_groups);
             for (size_t g = 0; g <= n_groups; ++g) p->groups.push_back(make_group(m, std::move(cols[g])));
         } catch (...) {
             fm_partition_release(p);

@@ -34,11 +34,12 @@ constexpr int kBatchRing = 8;                    // claimed-batch ring per warp 
 // the group (offset table `off`, sorted/de-duplicated exactly like DenseMembership::build,
 // stats.rs:1251-1284).  allele bit = (byte != 0) & called, called bit = !missing (or k < n
 // when the matrix has no bitmap).  Words are written 32 at a time (one per lane, 128 B).
-// Plane row = wq uint4 = 4*wq words; padding bits are zero.
+// Plane row = wq uint4 = 4*wq words; padding bits are zero.  `data` starts at row v_base and
+// `missing` at bitmap word word_base, so a staged chunk of rows can be repacked in place.
 __global__ void __launch_bounds__(256)
 fm_k_repack(const uint8_t *__restrict__ data, const uint64_t *__restrict__ missing, size_t stride,
-            const uint32_t *__restrict__ off, uint32_t n, uint32_t wq, uint32_t v_lo, uint32_t v_hi,
-            uint32_t *__restrict__ allele, uint32_t *__restrict__ called) {
+            const uint32_t *__restrict__ off, uint32_t n, uint32_t wq, uint32_t v_base, uint64_t word_base,
+            uint32_t v_lo, uint32_t v_hi, uint32_t *__restrict__ allele, uint32_t *__restrict__ called) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -48,7 +49,8 @@ fm_k_repack(const uint8_t *__restrict__ data, const uint64_t *__restrict__ missi
     for (uint64_t item = warp; item < total; item += nwarps) {
         const uint32_t v = v_lo + (uint32_t)(item / wgroups);
         const uint32_t wg = (uint32_t)(item % wgroups);
-        const size_t base = (size_t)v * stride;
+        const size_t base = (size_t)(v - v_base) * stride;  // offset inside `data` (row v_base first)
+        const size_t bit_base = (size_t)v * stride;          // bit index in the whole-matrix bitmap
         uint32_t my_a = 0, my_c = 0;
 #pragma unroll 4
         for (uint32_t i = 0; i < 32; ++i) {
@@ -57,10 +59,13 @@ fm_k_repack(const uint8_t *__restrict__ data, const uint64_t *__restrict__ missi
             const uint32_t k = w * 32 + lane;
             bool a = false, c = false;
             if (k < n) {
-                const size_t idx = base + off[k];
+                const uint32_t o = off[k];
                 c = true;
-                if (missing) c = !((missing[idx >> 6] >> (idx & 63)) & 1ull);
-                a = c && (data[idx] != 0);
+                if (missing) {
+                    const size_t bit = bit_base + o;
+                    c = !((missing[(bit >> 6) - word_base] >> (bit & 63)) & 1ull);
+                }
+                a = c && (data[base + o] != 0);
             }
             const uint32_t wa = __ballot_sync(0xffffffffu, a);
             const uint32_t wc = __ballot_sync(0xffffffffu, c);

@@ -47,7 +47,7 @@ const char *fm_version(void);
 fm_status fm_device_count(int *count);
 fm_status fm_set_device(int device); /* device used by handles created afterwards on this thread */
 fm_status fm_synchronize(void);
-/* Device buffers come from the device's stream-ordered memory pool and are kept for reuse when a
+/* Device buffers come from a caching allocator inside the library and are kept for reuse when a
  * handle is released; this returns the cached memory of the current device to the driver. */
 fm_status fm_trim_pool(void);
 
@@ -68,6 +68,32 @@ fm_status fm_matrix_retain(fm_matrix *m);
 fm_status fm_matrix_release(fm_matrix *m);
 fm_status fm_matrix_info(const fm_matrix *m, size_t *n_variants, size_t *n_samples, size_t *ploidy,
                          uint8_t *max_allele, int *has_missing);
+
+/* ---- streaming ingest (direct-to-bitplane ingestion) ----
+ * For callers that can hand the matrix over in row chunks (process.rs:2602-2660 builds it row by
+ * row; lib.rs:1135-1227 converts numpy row by row).  Declare every group / partition first, then
+ * push rows; each chunk is staged in one of two device buffers and repacked into the declared
+ * groups' bitplanes while the next chunk is copied, so upload and repack overlap and the u8
+ * matrix is never resident.  The resulting matrix handle has no u8 data: fm_group_create /
+ * fm_partition_create on it fail with FM_ERR_UNSUPPORTED.
+ *   rows          -> u8 of row `first_row` (n_rows * n_samples * ploidy bytes, reference layout)
+ *   missing_whole -> base of the WHOLE matrix's packed bitmap (stats.rs:1298-1302) or NULL when the
+ *                    matrix was begun with has_missing == 0; only the words of the rows are read.
+ * Host buffers are free again when fm_ingest_rows returns.  fm_ingest_finish hands out the
+ * handles (groups in declaration order) and destroys the ingest handle. */
+typedef struct fm_ingest fm_ingest;
+fm_status fm_ingest_begin(size_t n_variants, size_t n_samples, size_t ploidy, int has_missing,
+                          uint8_t max_allele, const int64_t *positions_or_null, size_t chunk_rows_or_0,
+                          fm_ingest **out);
+fm_status fm_ingest_add_group(fm_ingest *h, const uint64_t *sample_idx, const uint8_t *side, size_t n,
+                              size_t *group_index);
+fm_status fm_ingest_add_partition(fm_ingest *h, const uint16_t *left, const uint16_t *right,
+                                  size_t n_samples, size_t n_groups, size_t *partition_index);
+fm_status fm_ingest_rows(fm_ingest *h, const uint8_t *rows, const uint64_t *missing_whole_or_null,
+                         size_t first_row, size_t n_rows);
+fm_status fm_ingest_finish(fm_ingest *h, fm_matrix **matrix_out, fm_group **groups_out,
+                           fm_partition **partitions_out);
+fm_status fm_ingest_abort(fm_ingest *h);
 
 /* ---- group: replaces DenseMembership::build (stats.rs:1251-1284) + the per-group gather ----
  * haplotypes are (sample index, side 0=Left/1=Right); duplicates are counted once, out-of-range

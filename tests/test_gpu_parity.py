@@ -395,3 +395,52 @@ def test_wc_fst_public_api_and_edge_cases():
         F.wc_fst(variants, [], groups, (0, 100))
     with pytest.raises(ValueError):
         F.wc_fst(variants, names, groups, (10, 5))
+
+
+# ------------------------------------------------------------------ streaming ingest (f1)
+@pytest.mark.parametrize("chunk_rows,calls,missing", [(0, 1, 0.1), (37, 3, 0.1), (1, 2, 0.0), (5000, 1, 0.3)])
+def test_streaming_ingest_equals_resident_matrix(chunk_rows, calls, missing):
+    """fm_ingest_* (chunked upload overlapped with the repack, u8 never resident) must build the
+    same bitplanes as fm_matrix_create + fm_group_create: identical counts, summaries and W&C."""
+    import ctypes as C
+    from ferromic_b200 import _lib
+    from ferromic_b200.api import _Matrix
+    g, pos, pops = make_cohort(1500, 45, n_pops=3, missing_rate=missing, seed=7 + chunk_rows)
+    miss = g < 0
+    alle = np.where(miss, 0, g).astype(np.uint8)
+    hap_lists = [both_sides(pops[0]), both_sides(pops[1]) + [(pops[2][0], 1)], [(s, 0) for s in pops[2]]]
+    left = np.full(45, 0xFFFF, dtype=np.uint16)
+    for p, members in enumerate(pops):
+        left[members] = p
+    resident = _Matrix(alle, miss, pos, max_allele=1)
+    streamed = _Matrix.ingest(alle, miss, pos, hap_lists, partitions=[(left, left, 3)], chunk_rows=chunk_rows,
+                              calls=calls)
+    for haps in hap_lists:
+        a, b = resident.group(haps).summary(True), streamed.group(haps).summary(True)
+        assert np.array_equal(a["alt"], b["alt"]) and np.array_equal(a["called"], b["called"])
+        assert a["segregating_sites"] == b["segregating_sites"] and a["pi_sum"] == b["pi_sum"]
+        assert a["uncallable_lt2"] == b["uncallable_lt2"]
+    # oracle cross-check of one group
+    vs, d = orc.from_numpy(g, pos)
+    s0 = orc.build_summary(d, hap_lists[0])
+    got = streamed.group(hap_lists[0]).summary(True)
+    assert np.array_equal(got["alt"], s0.alt) and np.array_equal(got["called"], s0.called)
+    # the partition declared at ingest time gives the same W&C totals as one built afterwards
+    L = _lib.lib()
+    ph = C.c_void_p()
+    _lib.check(L.fm_partition_create(resident.handle, left.ctypes.data, left.ctypes.data, 45, 3, C.byref(ph)))
+    w = np.array([int(pos[0]), int(pos[-1])], dtype=np.int64)
+
+    def totals(handle):
+        oa, ob = np.zeros(1), np.zeros(1)
+        pa, pb = np.zeros(3), np.zeros(3)
+        pn, osz, nv = np.zeros(3, dtype=np.uint64), np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint64)
+        _lib.check(L.fm_wc_window_sums(handle, w.ctypes.data, 1, nv.ctypes.data, oa.ctypes.data, ob.ctypes.data,
+                                       osz.ctypes.data, pa.ctypes.data, pb.ctypes.data, pn.ctypes.data))
+        return (oa[0], ob[0], int(osz[0]), pa.tolist(), pb.tolist(), pn.tolist())
+
+    assert totals(ph) == totals(streamed.partitions[0])
+    L.fm_partition_release(ph)
+    # a streamed matrix has no resident u8 rows: late group creation must fail loudly
+    with pytest.raises(NotImplementedError):
+        streamed.group([(0, 0), (1, 1)])
