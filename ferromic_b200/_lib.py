@@ -58,7 +58,7 @@ EXPORTS = [
     "fm_group_segregating_sites", "fm_group_pi", "fm_harmonic", "fm_watterson_theta",
     "fm_per_site_diversity", "fm_hudson_pair", "fm_hudson_dxy", "fm_partition_create",
     "fm_partition_release", "fm_wc_fst", "fm_wc_window_sums", "fm_fst_estimate_from_sums", "fm_adjusted_sequence_length", "fm_group_window_sums",
-    "fm_hudson_window_sums", "fm_pi_from_sums", "fm_hudson_outcome_from_sums", "fm_timings_reset", "fm_timings_get", "fm_bench_diversity",
+    "fm_hudson_window_sums", "fm_pi_from_sums", "fm_hudson_outcome_from_sums", "fm_synth_fill", "fm_timings_reset", "fm_timings_get", "fm_bench_diversity",
     "fm_bench_hudson",
 ]
 
@@ -120,6 +120,7 @@ def lib() -> C.CDLL:
     L.fm_hudson_window_sums.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, vp, vp]
     L.fm_pi_from_sums.argtypes = [dbl, u64, i64, sz, C.POINTER(dbl)]
     L.fm_hudson_outcome_from_sums.argtypes = [C.POINTER(HudsonSums), i64, sz, sz, C.POINTER(HudsonOutcome)]
+    L.fm_synth_fill.argtypes = [vp, vp, sz, sz, sz, u64, u64, vp, dbl, dbl]
     L.fm_timings_get.argtypes = [C.POINTER(Timings)]
     L.fm_bench_diversity.argtypes = [C.POINTER(vp), sz, C.c_int, vp, sz, C.c_int, C.POINTER(BenchResult)]
     L.fm_bench_hudson.argtypes = [vp, vp, C.c_int, C.POINTER(BenchResult)]

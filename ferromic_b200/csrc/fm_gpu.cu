@@ -1961,6 +1961,36 @@ fm_status fm_hudson_outcome_from_sums(const fm_hudson_sums *t, int64_t L, size_t
     });
 }
 
+// ------------------------------------------------------------------------------------ synthetic cohorts
+fm_status fm_synth_fill(uint8_t *d_data, uint64_t *d_missing, size_t V, size_t S, size_t ploidy,
+                        uint64_t first_variant, uint64_t seed, const uint16_t *pop_of_sample, double sigma,
+                        double missing_rate) {
+    return guarded([&] {
+        require_device();
+        CK(cudaSetDevice(t_device));
+        const uint64_t stride = (uint64_t)S * ploidy;
+        const uint64_t total = (uint64_t)V * stride;
+        if (total == 0) return;
+        if (!d_data) fail(FM_ERR_INVALID_ARG, "d_data is NULL");
+        if (stride >= (1ull << 32)) fail(FM_ERR_UNSUPPORTED, "row stride exceeds 2^32 entries");
+        if ((reinterpret_cast<uintptr_t>(d_data) & 15u) != 0) fail(FM_ERR_INVALID_ARG, "d_data must be 16-byte aligned");
+        DevBuf<uint16_t> d_pop;
+        if (pop_of_sample) {
+            d_pop.alloc(S);
+            d_pop.upload(pop_of_sample, S);
+        }
+        const uint32_t sigma_q = (uint32_t)std::min(65536.0, std::max(0.0, sigma * 65536.0));
+        const uint32_t miss_q = (uint32_t)std::min(65536.0, std::max(0.0, missing_rate * 65536.0 + 0.5));
+        const uint64_t n_words = (total + 63) / 64;
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_words + 255) / 256, 64ull * sm_count(t_device));
+        fm::fm_k_synth<<<blocks, 256, 0, stream()>>>(d_data, d_missing, total, (uint32_t)stride, (uint32_t)ploidy,
+                                                     first_variant, seed, pop_of_sample ? d_pop.p : nullptr,
+                                                     sigma_q, miss_q);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(stream()));
+    });
+}
+
 // ------------------------------------------------------------------------------------ bench hooks
 namespace {
 struct EventPairs {

@@ -82,6 +82,82 @@ fm_k_repack(const uint8_t *__restrict__ data, const uint64_t *__restrict__ missi
     }
 }
 
+// ------------------------------------------------------------------------------ synthetic cohorts
+// Counter-based generator for benchmarks and full-size parity tests: every matrix entry is a pure
+// integer function of (seed, site, column), so any slice can be re-evaluated on the CPU
+// (tests/synth.py::synth_rows) without moving the matrix.  Site base frequency is U-shaped
+// (x^2 mirrored), each population gets a uniform offset scaled by sigma_q, alleles are Bernoulli.
+__host__ __device__ __forceinline__ uint64_t fm_splitmix64(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t fm_mix(uint64_t seed, uint64_t a, uint64_t b) {
+    return fm_splitmix64(fm_splitmix64(seed + a) + b);
+}
+__host__ __device__ __forceinline__ uint32_t fm_synth_threshold(uint64_t seed, uint64_t v, uint32_t pop,
+                                                                uint32_t sigma_q) {
+    const uint64_t hs = fm_mix(seed, v, 0);
+    const uint32_t x = (uint32_t)(hs & 0xFFFFu);
+    uint32_t y = (x * x) >> 16;
+    if ((hs >> 16) & 1u) y = 65535u - y;
+    const uint64_t hp = fm_mix(seed, v, 1u + pop);
+    const int32_t d = ((int32_t)(hp & 0x1FFFu) - 4096) * (int32_t)sigma_q / 4096;
+    int32_t t = (int32_t)y + d;
+    t = t < 66 ? 66 : (t > 65470 ? 65470 : t);
+    return (uint32_t)t;
+}
+
+// One thread per bitmap word = 64 consecutive entries of the linear layout.
+__global__ void __launch_bounds__(256)
+fm_k_synth(uint8_t *__restrict__ data, uint64_t *__restrict__ missing, uint64_t total, uint32_t stride,
+           uint32_t ploidy, uint64_t first_variant, uint64_t seed, const uint16_t *__restrict__ pop_of_sample,
+           uint32_t sigma_q, uint32_t miss_q) {
+    const uint64_t n_words = (total + 63) / 64;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words;
+         w += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t e0 = w * 64;
+        uint64_t v = e0 / stride;
+        uint32_t col = (uint32_t)(e0 - v * stride);
+        uint64_t bits = 0;
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) packed[i] = 0;
+        uint32_t cur_pop = 0xFFFFFFFFu, thr = 0;
+        uint64_t cur_v = ~0ull;
+#pragma unroll 4
+        for (uint32_t i = 0; i < 64; ++i) {
+            if (e0 + i < total) {
+                const uint32_t pop = pop_of_sample ? pop_of_sample[col / ploidy] : 0u;
+                if (pop != cur_pop || v != cur_v) {
+                    thr = fm_synth_threshold(seed, first_variant + v, pop, sigma_q);
+                    cur_pop = pop;
+                    cur_v = v;
+                }
+                const uint64_t he = fm_mix(seed, first_variant + v, 0x10000ull + col);
+                const bool miss = (uint32_t)((he >> 32) & 0xFFFFu) < miss_q;
+                const bool allele = (uint32_t)(he & 0xFFFFu) < thr;
+                if (miss) bits |= 1ull << i;
+                if (allele && !miss) packed[i >> 2] |= 1u << ((i & 3) * 8);
+            }
+            if (++col == stride) {
+                col = 0;
+                ++v;
+            }
+        }
+        if (e0 + 64 <= total) {
+            uint4 *dst = reinterpret_cast<uint4 *>(data + e0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        } else {
+            for (uint32_t i = 0; e0 + i < total; ++i) data[e0 + i] = (uint8_t)((packed[i >> 2] >> ((i & 3) * 8)) & 0xFFu);
+        }
+        if (missing) missing[w] = bits;
+    }
+}
+
 // ------------------------------------------------------------------------------ plane pass
 struct GroupPlanes {
     const uint4 *allele;

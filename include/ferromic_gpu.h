@@ -248,6 +248,17 @@ fm_status fm_hudson_outcome_from_sums(const fm_hudson_sums *sums, int64_t sequen
                                       size_t haplotype_capacity1, size_t haplotype_capacity2,
                                       fm_hudson_outcome *out);
 
+/* ---- synthetic cohorts for benchmarks and full-size parity tests ----
+ * Fills a device-resident u8 matrix (reference layout) and, when d_missing != NULL, its packed
+ * missing bitmap with a counter-based generator: entry (site, column) is a pure integer function
+ * of (seed, first_variant + site, column), so any slice can be re-evaluated on the CPU
+ * (tests/synth.py::synth_rows) and shards generated with the right first_variant tile one cohort.
+ * pop_of_sample (host, [n_samples] or NULL) selects the population whose frequency offset
+ * (uniform in +-sigma around the U-shaped site frequency) applies to a sample. */
+fm_status fm_synth_fill(uint8_t *d_data, uint64_t *d_missing_or_null, size_t n_variants, size_t n_samples,
+                        size_t ploidy, uint64_t first_variant, uint64_t seed,
+                        const uint16_t *pop_of_sample_or_null, double sigma, double missing_rate);
+
 /* ---- instrumentation for bench.py (device timings of the last call, milliseconds) ---- */
 typedef struct {
     float h2d_ms, repack_ms, stats_ms, reduce_ms, d2h_ms;
