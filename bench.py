@@ -222,6 +222,9 @@ def workload_config(args):
 
 # ----------------------------------------------------------------------------- our arm
 def run_ours(args):
+    # libraries (NCCL's version banner) may write to fd 1: keep the real stdout for the one JSON line
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
@@ -269,24 +272,34 @@ def run_ours(args):
     groups = make_groups_on(m)
     garr = (C.c_void_p * 2)(*[g.value for g in groups])
     res = _lib.BenchResult()
-    _lib.check(L.fm_bench_diversity(garr, 2, 1, mask.ctypes.data, mask.size // 2, max(args.warmup, 3), C.byref(res)))
+    # N > 1: every step ends with the exchange of the groups' region totals (S, sum pi, uncallable
+    # sites) -- a fused fold + P2P mailbox kernel over NVLink (csrc/fm_comm.cuh); torch.distributed
+    # only carries the 64-byte mailbox handles at start-up and the barriers.
+    comm = None
+    if world == 1 and os.environ.get("FM_BENCH_SELF_COMM"):  # diagnostic: the exchange kernel alone
+        comm = C.c_void_p()
+        _lib.check(L.fm_comm_create(0, 1, C.byref(comm)))
+    if world > 1:
+        comm = C.c_void_p()
+        _lib.check(L.fm_comm_create(rank, world, C.byref(comm)))
+        hb = (C.c_uint8 * 64)()
+        _lib.check(L.fm_comm_export(comm, hb))
+        mine = torch.tensor(list(hb), dtype=torch.uint8, device=device)
+        allh = torch.empty(world * 64, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(allh, mine)
+        handles = np.ascontiguousarray(allh.cpu().numpy())
+        _lib.check(L.fm_comm_connect(comm, handles.ctypes.data))
+        dist.barrier()
+    _lib.check(L.fm_bench_diversity(garr, 2, 1, mask.ctypes.data, mask.size // 2, max(args.warmup, 3), comm,
+                                    C.byref(res)))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     with ClockSampler(local) as clocks:
         wall0 = time.perf_counter()
-        _lib.check(L.fm_bench_diversity(garr, 2, 1, mask.ctypes.data, mask.size // 2, args.steps, C.byref(res)))
+        _lib.check(L.fm_bench_diversity(garr, 2, 1, mask.ctypes.data, mask.size // 2, args.steps, comm,
+                                        C.byref(res)))
         dev_ms = res.step_ms_avg * args.steps
-        if world > 1:
-            part = torch.zeros(8, dtype=torch.float64, device=device)
-            gathered = [torch.zeros_like(part) for _ in range(world)]
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(args.steps):  # per-step combine of the tiny per-region partial buffer
-                dist.all_gather(gathered, part)
-            e1.record()
-            torch.cuda.synchronize()
-            dev_ms += e0.elapsed_time(e1)
         torch.cuda.synchronize()
         wall_ms = (time.perf_counter() - wall0) * 1e3
         if world > 1:
@@ -295,7 +308,7 @@ def run_ours(args):
         # sampler has seen the clocks under this load a few times
         t_keep = time.perf_counter()
         while len(clocks.samples) < 8 and time.perf_counter() - t_keep < 4.0:
-            _lib.check(L.fm_bench_diversity(garr, 2, 1, mask.ctypes.data, mask.size // 2, 200,
+            _lib.check(L.fm_bench_diversity(garr, 2, 1, mask.ctypes.data, mask.size // 2, 200, None,
                                             C.byref(_lib.BenchResult())))
     tmax = torch.tensor([dev_ms], dtype=torch.float64, device=device)
     if world > 1:
@@ -330,6 +343,10 @@ def run_ours(args):
     for g in groups:
         L.fm_group_release(g)
     L.fm_matrix_release(m)
+    if comm is not None:
+        if world > 1:
+            dist.barrier()  # nobody may still be writing into a mailbox that is about to be freed
+        L.fm_comm_destroy(comm)
 
     # ---------------- end to end through the C ABI with host (pinned) buffers
     e2e = None
@@ -429,8 +446,11 @@ def run_ours(args):
                 "data": "synthetic", "config": workload_config(args), "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": e2e, "gpu_launches": int(res.plane_launches + res.other_launches),
                 "clocks": clocks.summary(), "wall_ms_per_step": wall_ms / args.steps,
+                "exchange_ms_per_step": res.comm_ms_avg if comm is not None else None,
+                "collective": None if world == 1 else "per step: fused fold + P2P mailbox exchange of region totals "
+                                                      "(fm_k_comm_exchange over NVLink peer memory), inside the timed region",
                 "timing": "CUDA events on the launching stream (cudaStreamPerThread), max over ranks"}
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -47,7 +47,7 @@ class Timings(C.Structure):
 class BenchResult(C.Structure):
     _fields_ = [("step_ms_avg", C.c_float), ("plane_ms_avg", C.c_float), ("plane_launches", C.c_uint64),
                 ("other_launches", C.c_uint64), ("plane_bytes_per_step", C.c_uint64),
-                ("group_ms_avg", C.c_float * 8), ("group_bytes", C.c_uint64 * 8)]
+                ("group_ms_avg", C.c_float * 8), ("group_bytes", C.c_uint64 * 8), ("comm_ms_avg", C.c_float)]
 
 
 EXPORTS = [
@@ -58,7 +58,8 @@ EXPORTS = [
     "fm_group_segregating_sites", "fm_group_pi", "fm_harmonic", "fm_watterson_theta",
     "fm_per_site_diversity", "fm_hudson_pair", "fm_hudson_dxy", "fm_partition_create",
     "fm_partition_release", "fm_wc_fst", "fm_wc_window_sums", "fm_fst_estimate_from_sums", "fm_adjusted_sequence_length", "fm_group_window_sums",
-    "fm_hudson_window_sums", "fm_pi_from_sums", "fm_hudson_outcome_from_sums", "fm_synth_fill", "fm_timings_reset", "fm_timings_get", "fm_bench_diversity",
+    "fm_hudson_window_sums", "fm_pi_from_sums", "fm_hudson_outcome_from_sums", "fm_comm_create", "fm_comm_export", "fm_comm_connect", "fm_comm_connect_local", "fm_comm_allgather", "fm_comm_set_timeout_ms",
+    "fm_comm_destroy", "fm_synth_fill", "fm_timings_reset", "fm_timings_get", "fm_bench_diversity",
     "fm_bench_hudson",
 ]
 
@@ -122,7 +123,14 @@ def lib() -> C.CDLL:
     L.fm_hudson_outcome_from_sums.argtypes = [C.POINTER(HudsonSums), i64, sz, sz, C.POINTER(HudsonOutcome)]
     L.fm_synth_fill.argtypes = [vp, vp, sz, sz, sz, u64, u64, vp, dbl, dbl]
     L.fm_timings_get.argtypes = [C.POINTER(Timings)]
-    L.fm_bench_diversity.argtypes = [C.POINTER(vp), sz, C.c_int, vp, sz, C.c_int, C.POINTER(BenchResult)]
+    L.fm_bench_diversity.argtypes = [C.POINTER(vp), sz, C.c_int, vp, sz, C.c_int, vp, C.POINTER(BenchResult)]
+    L.fm_comm_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
+    L.fm_comm_export.argtypes = [vp, vp]
+    L.fm_comm_connect.argtypes = [vp, vp]
+    L.fm_comm_connect_local.argtypes = [vp, C.POINTER(vp)]
+    L.fm_comm_allgather.argtypes = [vp, vp, sz, sz, vp, vp]
+    L.fm_comm_set_timeout_ms.argtypes = [vp, u64]
+    L.fm_comm_destroy.argtypes = [vp]
     L.fm_bench_hudson.argtypes = [vp, vp, C.c_int, C.POINTER(BenchResult)]
     for name in EXPORTS:
         fn = getattr(L, name)

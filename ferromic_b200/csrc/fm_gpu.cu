@@ -4,6 +4,7 @@
 #include "../../include/ferromic_gpu.h"
 #include "fm_kernels.cuh"
 #include "fm_wc.cuh"
+#include "fm_comm.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -1961,6 +1962,167 @@ fm_status fm_hudson_outcome_from_sums(const fm_hudson_sums *t, int64_t L, size_t
     });
 }
 
+// ------------------------------------------------------------------------------------ peer mailbox exchange
+struct fm_comm {
+    int rank = 0, world = 1, device = 0;
+    fm::CommMailbox *mine = nullptr;
+    fm::CommMailbox *peers[fm::kCommMaxRanks] = {};
+    bool ipc_opened[fm::kCommMaxRanks] = {};
+    bool connected = false;
+    unsigned long long step = 0;
+    uint32_t *d_status = nullptr;
+    unsigned long long *d_local = nullptr, *d_gathered = nullptr, *d_merged = nullptr;
+    unsigned long long timeout_ns = 5000000000ull;
+};
+
+namespace {
+// Enqueue one exchange on the calling thread's stream (asynchronous).
+void comm_launch(fm_comm *c, const unsigned long long *d_local, uint32_t n_words, uint32_t n_double,
+                 const fm::CommFold *folds, uint32_t n_fold) {
+    if (!c->connected) fail(FM_ERR_INVALID_ARG, "fm_comm is not connected");
+    if (n_words > fm::kCommMaxValues) fail(FM_ERR_INVALID_ARG, "too many values for one exchange");
+    fm::CommParams P{};
+    for (int r = 0; r < c->world; ++r) P.peers[r] = c->peers[r];
+    P.rank = (uint32_t)c->rank;
+    P.world = (uint32_t)c->world;
+    P.step = ++c->step;
+    P.n_words = n_words;
+    P.n_double = n_double;
+    P.local = d_local;
+    P.n_fold = n_fold;
+    for (uint32_t f = 0; f < n_fold; ++f) P.fold[f] = folds[f];
+    P.gathered = c->d_gathered;
+    P.merged = c->d_merged;
+    P.status = c->d_status;
+    P.timeout_ns = c->timeout_ns;
+    fm::fm_k_comm_exchange<<<1, 128, 0, stream()>>>(P);
+    CK(cudaGetLastError());
+    g_launches++;
+}
+void comm_check_status(fm_comm *c) {
+    uint32_t st = 0;
+    CK(cudaMemcpyAsync(&st, c->d_status, 4, cudaMemcpyDeviceToHost, stream()));
+    CK(cudaStreamSynchronize(stream()));
+    if (st != 0) fail(FM_ERR_CUDA, "peer exchange timed out waiting for another rank");
+}
+}  // namespace
+
+fm_status fm_comm_create(int rank, int world, fm_comm **out) {
+    return guarded([&] {
+        if (!out) fail(FM_ERR_INVALID_ARG, "out is NULL");
+        *out = nullptr;
+        if (world < 1 || world > (int)fm::kCommMaxRanks || rank < 0 || rank >= world)
+            fail(FM_ERR_INVALID_ARG, "bad rank / world size");
+        require_device();
+        CK(cudaSetDevice(t_device));
+        fm_comm *c = new fm_comm();
+        c->rank = rank;
+        c->world = world;
+        c->device = t_device;
+        try {
+            // plain cudaMalloc (not the cache): the allocation is exported through cudaIpc
+            CK(cudaMalloc((void **)&c->mine, sizeof(fm::CommMailbox)));
+            CK(cudaMemset(c->mine, 0, sizeof(fm::CommMailbox)));
+            CK(cudaMalloc((void **)&c->d_status, 256));
+            CK(cudaMemset(c->d_status, 0, 256));
+            CK(cudaMalloc((void **)&c->d_local, fm::kCommMaxValues * 8));
+            CK(cudaMalloc((void **)&c->d_merged, fm::kCommMaxValues * 8));
+            CK(cudaMalloc((void **)&c->d_gathered, (size_t)world * fm::kCommMaxValues * 8));
+            CK(cudaDeviceSynchronize());
+            c->peers[rank] = c->mine;
+            if (world == 1) c->connected = true;
+        } catch (...) {
+            fm_comm_destroy(c);
+            throw;
+        }
+        *out = c;
+    });
+}
+
+fm_status fm_comm_export(fm_comm *c, uint8_t *handle_out) {
+    return guarded([&] {
+        if (!c || !handle_out) fail(FM_ERR_INVALID_ARG, "NULL argument");
+        static_assert(sizeof(cudaIpcMemHandle_t) == FM_COMM_HANDLE_BYTES, "handle size");
+        CK(cudaSetDevice(c->device));
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, c->mine));
+        std::memcpy(handle_out, &h, sizeof(h));
+    });
+}
+
+fm_status fm_comm_connect(fm_comm *c, const uint8_t *handles) {
+    return guarded([&] {
+        if (!c || !handles) fail(FM_ERR_INVALID_ARG, "NULL argument");
+        CK(cudaSetDevice(c->device));
+        for (int r = 0; r < c->world; ++r) {
+            if (r == c->rank) continue;
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, handles + (size_t)r * FM_COMM_HANDLE_BYTES, sizeof(h));
+            void *p = nullptr;
+            CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            c->peers[r] = static_cast<fm::CommMailbox *>(p);
+            c->ipc_opened[r] = true;
+        }
+        c->connected = true;
+    });
+}
+
+fm_status fm_comm_connect_local(fm_comm *c, fm_comm *const *all) {
+    return guarded([&] {
+        if (!c || !all) fail(FM_ERR_INVALID_ARG, "NULL argument");
+        CK(cudaSetDevice(c->device));
+        for (int r = 0; r < c->world; ++r) {
+            if (!all[r] || all[r]->world != c->world || all[r]->rank != r)
+                fail(FM_ERR_INVALID_ARG, "peer list does not match the communicator");
+            if (all[r]->device != c->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(all[r]->device, 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else CK(e);
+            }
+            c->peers[r] = all[r]->mine;
+        }
+        c->connected = true;
+    });
+}
+
+fm_status fm_comm_allgather(fm_comm *c, const void *local, size_t n_words, size_t n_double, void *gathered_out,
+                            void *merged_out) {
+    return guarded([&] {
+        if (!c || (n_words && !local)) fail(FM_ERR_INVALID_ARG, "NULL argument");
+        if (n_words > fm::kCommMaxValues) fail(FM_ERR_INVALID_ARG, "too many values for one exchange");
+        CK(cudaSetDevice(c->device));
+        if (n_words) CK(cudaMemcpyAsync(c->d_local, local, n_words * 8, cudaMemcpyHostToDevice, stream()));
+        comm_launch(c, c->d_local, (uint32_t)n_words, (uint32_t)std::min(n_double, n_words), nullptr, 0);
+        if (gathered_out && n_words)
+            CK(cudaMemcpyAsync(gathered_out, c->d_gathered, (size_t)c->world * n_words * 8, cudaMemcpyDeviceToHost,
+                               stream()));
+        if (merged_out && n_words)
+            CK(cudaMemcpyAsync(merged_out, c->d_merged, n_words * 8, cudaMemcpyDeviceToHost, stream()));
+        comm_check_status(c);
+    });
+}
+
+fm_status fm_comm_set_timeout_ms(fm_comm *c, uint64_t ms) {
+    if (!c) return FM_ERR_INVALID_ARG;
+    c->timeout_ns = ms * 1000000ull;
+    return FM_OK;
+}
+
+fm_status fm_comm_destroy(fm_comm *c) {
+    if (!c) return FM_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < c->world; ++r)
+        if (c->ipc_opened[r]) cudaIpcCloseMemHandle(c->peers[r]);
+    cudaFree(c->mine);
+    cudaFree(c->d_status);
+    cudaFree(c->d_local);
+    cudaFree(c->d_merged);
+    cudaFree(c->d_gathered);
+    delete c;
+    return FM_OK;
+}
+
 // ------------------------------------------------------------------------------------ synthetic cohorts
 fm_status fm_synth_fill(uint8_t *d_data, uint64_t *d_missing, size_t V, size_t S, size_t ploidy,
                         uint64_t first_variant, uint64_t seed, const uint16_t *pop_of_sample, double sigma,
@@ -2018,7 +2180,7 @@ void launch_reduce(const double *pd, int nd, const uint32_t *pu, int nu, const f
 }  // namespace
 
 fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode, const int64_t *mask_iv,
-                             size_t n_mask, int iterations, fm_bench_result *out) {
+                             size_t n_mask, int iterations, fm_comm *comm, fm_bench_result *out) {
     return guarded([&] {
         if (!groups || !n_groups || !out || iterations < 1) fail(FM_ERR_INVALID_ARG, "bad argument");
         require_device();
@@ -2076,7 +2238,7 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
             pg[i].P.div = e;
         }
         EventPairs evs;
-        std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans;
+        std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans, comm_spans;
         cudaEvent_t t0 = evs.next(), t1 = evs.next();
         CK(cudaStreamSynchronize(stream()));
         CK(cudaEventRecord(t0, stream()));
@@ -2102,6 +2264,25 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
                     out->other_launches++;
                 }
             }
+            if (comm) {  // fold the region totals of every group and exchange them with all ranks
+                fm::CommFold folds[4];
+                uint32_t nf = 0, words = 0;
+                for (size_t i = 0; i < n_groups && nf < 4; ++i) {
+                    const fm::PassGeom &G = pg[i].P.geom;
+                    if (!G.n_batches) continue;
+                    const uint32_t s_lo = G.b_lo / fm::kSuperBatches;
+                    const uint32_t n_super = (G.b_lo + G.n_batches + fm::kSuperBatches - 1) / fm::kSuperBatches - s_lo;
+                    folds[nf++] = fm::CommFold{pg[i].sd.p, reinterpret_cast<const unsigned long long *>(pg[i].su.p),
+                                               n_super, 1u, 2u};
+                    words += 3;
+                }
+                cudaEvent_t a = evs.next(), b = evs.next();
+                CK(cudaEventRecord(a, stream()));
+                comm_launch(comm, nullptr, words, 0, folds, nf);
+                CK(cudaEventRecord(b, stream()));
+                comm_spans.emplace_back(a, b);
+                out->other_launches++;
+            }
         }
         CK(cudaEventRecord(t1, stream()));
         CK(cudaEventSynchronize(t1));
@@ -2113,6 +2294,12 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
             plane += t;
             const size_t gi = si % n_groups;
             if (gi < 8) out->group_ms_avg[gi] += t / (float)iterations;
+        }
+        if (comm) comm_check_status(comm);
+        for (auto &sp : comm_spans) {
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, sp.first, sp.second));
+            out->comm_ms_avg += t / (float)comm_spans.size();
         }
         out->step_ms_avg = total / (float)iterations;
         out->plane_ms_avg = spans.empty() ? 0.f : plane / (float)spans.size();

@@ -70,6 +70,83 @@ def merge_in_rank_order(parts: Sequence[WindowTotals]) -> WindowTotals:
     return WindowTotals(f, u, parts[0].f_names, parts[0].u_names)
 
 
+class PeerComm:
+    """The library's NVLink mailbox exchange (include/ferromic_gpu.h fm_comm_*, csrc/fm_comm.cuh):
+    one small kernel stores this rank's words into every peer's mailbox with P2P stores and
+    returns everybody's words.  Handles are swapped once through `exchange_handles`, a callable
+    bytes -> list[bytes] over all ranks (torch.distributed.all_gather_object, MPI, ...)."""
+
+    def __init__(self, rank: int, world: int, exchange_handles=None, device: Optional[int] = None):
+        L = lib()
+        if device is not None:
+            check(L.fm_set_device(device))
+        self.rank, self.world = rank, world
+        self.handle = C.c_void_p()
+        check(L.fm_comm_create(rank, world, C.byref(self.handle)))
+        if world > 1:
+            if exchange_handles is None:
+                raise ValueError("exchange_handles is required for world > 1")
+            hb = (C.c_uint8 * 64)()
+            check(L.fm_comm_export(self.handle, hb))
+            allh = exchange_handles(bytes(hb))
+            buf = np.frombuffer(b"".join(allh), dtype=np.uint8).copy()
+            check(L.fm_comm_connect(self.handle, buf.ctypes.data))
+
+    @classmethod
+    def connect_in_process(cls, comms: Sequence["PeerComm"]):
+        """Wire communicators that live in one process (one host thread per GPU)."""
+        arr = (C.c_void_p * len(comms))(*[c.handle.value for c in comms])
+        for c in comms:
+            check(lib().fm_comm_connect_local(c.handle, arr))
+
+    @classmethod
+    def _bare(cls, rank: int, world: int) -> "PeerComm":
+        self = cls.__new__(cls)
+        self.rank, self.world = rank, world
+        self.handle = C.c_void_p()
+        check(lib().fm_comm_create(rank, world, C.byref(self.handle)))
+        return self
+
+    def allgather_words(self, words: np.ndarray, n_double: int = 0):
+        """words: 8-byte elements (float64 / uint64 view).  Returns (gathered [world, n], merged [n])
+        as uint64 bit patterns; the first n_double words of `merged` are FP64 sums in rank order."""
+        w = np.ascontiguousarray(words).view(np.uint64).reshape(-1)
+        gathered = np.empty((self.world, w.size), dtype=np.uint64)
+        merged = np.empty(w.size, dtype=np.uint64)
+        check(lib().fm_comm_allgather(self.handle, w.ctypes.data, w.size, n_double, gathered.ctypes.data,
+                                      merged.ctypes.data))
+        return gathered, merged
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().fm_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def peer_gather_totals(local: WindowTotals, comm: PeerComm) -> WindowTotals:
+    """all_gather_totals over the NVLink mailbox instead of torch.distributed (chunks of
+    FM_COMM_MAX_WORDS words); the rank-ordered sum is the same merge_in_rank_order."""
+    nf, nu = local.f.size, local.u.size
+    buf = np.empty(nf + nu, dtype=np.uint64)
+    buf[:nf] = local.f.reshape(-1).view(np.uint64)
+    buf[nf:] = local.u.reshape(-1)
+    rows = []
+    for o in range(0, max(buf.size, 1), 2048):
+        g, _ = comm.allgather_words(buf[o:o + 2048])
+        rows.append(g)
+    allw = np.concatenate(rows, axis=1) if rows else np.zeros((comm.world, 0), dtype=np.uint64)
+    parts = [WindowTotals(allw[r, :nf].view(np.float64).reshape(local.f.shape).copy(),
+                          allw[r, nf:].reshape(local.u.shape).copy(), local.f_names, local.u_names)
+             for r in range(comm.world)]
+    return merge_in_rank_order(parts)
+
+
 def all_gather_totals(local: WindowTotals, group=None, device=None) -> WindowTotals:
     """One all_gather of the packed totals, then the rank-ordered sum.  `device` is the CUDA
     device of this rank for the NCCL backend (None: CPU tensors, gloo)."""
@@ -162,10 +239,12 @@ class CohortShard:
     genotypes: u8/int8 array [v_hi - v_lo, S, ploidy] of the shard (negative = missing) or a
     pre-built api._Matrix; positions: 0-based positions of the shard's sites (ascending)."""
 
-    def __init__(self, genotypes, positions, rank: int = 0, world: int = 1, device: Optional[int] = None):
+    def __init__(self, genotypes, positions, rank: int = 0, world: int = 1, device: Optional[int] = None,
+                 comm: Optional[PeerComm] = None):
         from .api import _Matrix
 
         self.rank, self.world = rank, world
+        self.comm = comm
         if device is not None:
             check(lib().fm_set_device(device))
         self.device = device
@@ -239,6 +318,8 @@ class CohortShard:
 
     # ---- merged results (one gather each) ------------------------------------------------
     def _gather(self, t: WindowTotals, group=None) -> WindowTotals:
+        if self.comm is not None:
+            return peer_gather_totals(t, self.comm)
         dev = None
         if self.device is not None:
             import torch

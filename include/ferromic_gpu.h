@@ -248,6 +248,29 @@ fm_status fm_hudson_outcome_from_sums(const fm_hudson_sums *sums, int64_t sequen
                                       size_t haplotype_capacity1, size_t haplotype_capacity2,
                                       fm_hudson_outcome *out);
 
+/* ---- region-total exchange over NVLink peer memory (the path's only exchange step) ----
+ * One process (or host thread) per GPU creates a communicator on its device; the 64-byte handles
+ * are swapped through whatever the host already has (torch.distributed, MPI, a pipe) and every
+ * rank maps every peer's mailbox (cudaIpc).  fm_comm_allgather then runs ONE small kernel that
+ * stores this rank's words into every peer's mailbox with P2P stores, publishes a step flag,
+ * waits for all peers' flags and returns the gathered words plus their rank-ordered sum (the
+ * first n_double words are summed as FP64, the rest as u64) -- bit-identical on every rank.
+ * Ranks must issue the same sequence of exchanges.  A peer that does not arrive within 5 s makes
+ * the call fail with FM_ERR_CUDA instead of hanging the GPU. */
+typedef struct fm_comm fm_comm;
+#define FM_COMM_HANDLE_BYTES 64
+#define FM_COMM_MAX_WORDS 2048
+fm_status fm_comm_create(int rank, int world, fm_comm **out);
+fm_status fm_comm_export(fm_comm *c, uint8_t *handle_out /* [FM_COMM_HANDLE_BYTES] */);
+fm_status fm_comm_connect(fm_comm *c, const uint8_t *handles /* [world][FM_COMM_HANDLE_BYTES] */);
+/* Same-process variant (one host thread per GPU, or tests): all[r] is rank r's communicator. */
+fm_status fm_comm_connect_local(fm_comm *c, fm_comm *const *all);
+fm_status fm_comm_allgather(fm_comm *c, const void *local_words, size_t n_words, size_t n_double,
+                            void *gathered_out_or_null /* [world][n_words] */,
+                            void *merged_out_or_null /* [n_words] */);
+fm_status fm_comm_set_timeout_ms(fm_comm *c, uint64_t milliseconds); /* default 5000 */
+fm_status fm_comm_destroy(fm_comm *c);
+
 /* ---- synthetic cohorts for benchmarks and full-size parity tests ----
  * Fills a device-resident u8 matrix (reference layout) and, when d_missing != NULL, its packed
  * missing bitmap with a counter-based generator: entry (site, column) is a pure integer function
@@ -274,7 +297,8 @@ fm_status fm_timings_get(fm_timings *out);
  * (mode 0: counts + summary partials; mode 1: + per-site pi/theta tracks with the mask applied)
  * and folds the per-batch partials on device.  Timing uses CUDA events on the launching stream:
  * step_ms_avg brackets all `iterations` steps, plane_ms_avg is the mean duration of one
- * plane-pass launch (events around every launch). */
+ * plane-pass launch (events around every launch).  With a communicator every step ends with the
+ * fused fold + peer exchange of the groups' region totals (S, sum pi, uncallable sites). */
 typedef struct {
     float step_ms_avg;
     float plane_ms_avg;
@@ -283,10 +307,11 @@ typedef struct {
     uint64_t plane_bytes_per_step; /* algorithmic bytes: plane rows read + per-site outputs written */
     float group_ms_avg[8];         /* mean plane-pass duration per listed group (first 8) */
     uint64_t group_bytes[8];       /* algorithmic bytes of one launch per listed group */
+    float comm_ms_avg;             /* mean duration of the fused fold + peer exchange kernel (incl. waiting) */
 } fm_bench_result;
 fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
                              const int64_t *mask_iv_or_null, size_t n_mask, int iterations,
-                             fm_bench_result *out);
+                             fm_comm *comm_or_null, fm_bench_result *out);
 /* Same for the fused two-group Hudson pass (K3). */
 fm_status fm_bench_hudson(fm_group *g1, fm_group *g2, int iterations, fm_bench_result *out);
 

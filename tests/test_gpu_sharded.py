@@ -111,3 +111,83 @@ def test_wc_window_sums_26_populations_match_region_calls():
         assert _close(prs[0][k].sum_a, ref["pairs"][k]["sum_a"], 1e-9), k
         assert _close(prs[0][k].sum_b, ref["pairs"][k]["sum_b"], 1e-9), k
     cohort.close()
+
+
+def test_peer_mailbox_exchange_two_ranks_in_one_process():
+    """fm_comm_* (P2P mailbox all-gather, csrc/fm_comm.cuh): two communicators on this GPU wired in
+    process, driven from two host threads like two ranks would; gathered words are exact and the
+    rank-ordered FP64 sum has identical bits on both ranks."""
+    import threading
+    from ferromic_b200 import sharded
+    comms = [sharded.PeerComm._bare(r, 2) for r in range(2)]
+    sharded.PeerComm.connect_in_process(comms)
+    rng = np.random.default_rng(11)
+    out = {}
+
+    def run(r):
+        res = []
+        for step in range(6):
+            n = [7, 2048, 1, 300, 64, 5][step]
+            f = np.random.default_rng(100 * step + r).normal(size=n)
+            res.append((f,) + comms[r].allgather_words(f, n_double=n // 2))
+        out[r] = res
+
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=60)
+    assert set(out) == {0, 1}
+    for step in range(6):
+        f0, g0, m0 = out[0][step]
+        f1, g1, m1 = out[1][step]
+        assert np.array_equal(g0, g1) and np.array_equal(m0, m1)
+        assert np.array_equal(g0[0], f0.view(np.uint64)) and np.array_equal(g0[1], f1.view(np.uint64))
+        nd = len(f0) // 2
+        assert np.array_equal(m0[:nd].view(np.float64), f0[:nd] + f1[:nd])
+        with np.errstate(over="ignore"):
+            assert np.array_equal(m0[nd:], f0[nd:].view(np.uint64) + f1[nd:].view(np.uint64))
+    # totals of two cohort shards through the mailbox == the rank-ordered merge on the host
+    g, pos, pops, left = _cohort(V=17000)
+    windows = _windows(pos)[:4]
+    h1 = both_sides(pops[0])
+    cuts = sharded.shard_bounds(len(pos), 2)
+    shards = [sharded.CohortShard(g[a:b], pos[a:b], rank=r, world=2, comm=comms[r])
+              for r, (a, b) in enumerate(zip(cuts[:-1], cuts[1:]))]
+    local = [s.diversity_totals(h1, windows) for s in shards]
+    ref = sharded.merge_in_rank_order(local)
+    got = {}
+
+    def gather(r):
+        got[r] = sharded.peer_gather_totals(local[r], comms[r])
+
+    ts = [threading.Thread(target=gather, args=(r,)) for r in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=60)
+    for r in range(2):
+        assert np.array_equal(got[r].f, ref.f) and np.array_equal(got[r].u, ref.u)
+    for s in shards:
+        s.close()
+    for c in comms:
+        c.close()
+
+
+def test_peer_mailbox_single_rank_and_timeout():
+    from ferromic_b200 import FerromicGpuError, sharded
+    c = sharded.PeerComm(0, 1)
+    w = np.arange(10, dtype=np.float64)
+    g, m = c.allgather_words(w, n_double=10)
+    assert np.array_equal(g[0].view(np.float64), w) and np.array_equal(m.view(np.float64), w)
+    c.close()
+    # a peer that never shows up: the exchange gives up instead of hanging the GPU
+    a, b = sharded.PeerComm._bare(0, 2), sharded.PeerComm._bare(1, 2)
+    sharded.PeerComm.connect_in_process([a, b])
+    import ctypes as C
+    from ferromic_b200 import _lib
+    assert _lib.lib().fm_comm_set_timeout_ms(a.handle, 200) == 0
+    with pytest.raises(FerromicGpuError):
+        a.allgather_words(w)
+    a.close()
+    b.close()
