@@ -93,35 +93,38 @@ fm_k_comm_exchange(const CommParams P) {
     if (P.n_fold == 0) {
         for (uint32_t i = tid; i < P.n_words; i += nt) vals[i] = P.local[i];
     } else {
-        // rows are staged through shared memory by the whole CTA (coalesced, latency overlapped);
-        // thread c then adds column c in super-batch order -- the association of the host finish
-        uint32_t base = 0;
-        for (uint32_t f = 0; f < P.n_fold; ++f) {
-            const CommFold &F = P.fold[f];
+        // warp f folds column group f: its rows are staged through shared memory by the warp's 32
+        // lanes (coalesced, latencies overlapped), then lane c adds column c in super-batch order --
+        // the association of the single-GPU host finish.  The folds run concurrently.
+        const uint32_t warp = tid >> 5, lane = tid & 31;
+        if (warp < P.n_fold) {
+            uint32_t base = 0;
+            for (uint32_t f = 0; f < warp; ++f) base += P.fold[f].nd + P.fold[f].nu;
+            const CommFold &F = P.fold[warp];
             const uint32_t W = F.nd + F.nu;
-            const uint32_t CH = kCommStageWords / W;
+            unsigned long long *st = stage + warp * (kCommStageWords / 4);
+            const uint32_t CH = (kCommStageWords / 4) / W;
             double accd = 0.0;
             unsigned long long accu = 0;
             for (uint32_t s0 = 0; s0 < F.n_super; s0 += CH) {
                 const uint32_t n = min(CH, F.n_super - s0);
-                for (uint32_t i = tid; i < n * W; i += nt) {
+                for (uint32_t i = lane; i < n * W; i += 32) {
                     const uint32_t row = i / W, col = i - row * W;
-                    stage[i] = col < F.nd
-                                   ? (unsigned long long)__double_as_longlong(F.sd[(size_t)(s0 + row) * F.nd + col])
-                                   : F.su[(size_t)(s0 + row) * F.nu + (col - F.nd)];
+                    st[i] = col < F.nd
+                                ? (unsigned long long)__double_as_longlong(F.sd[(size_t)(s0 + row) * F.nd + col])
+                                : F.su[(size_t)(s0 + row) * F.nu + (col - F.nd)];
                 }
-                __syncthreads();
-                if (tid < W) {
-                    if (tid < F.nd)
-                        for (uint32_t r = 0; r < n; ++r) accd += __longlong_as_double((long long)stage[r * W + tid]);
+                __syncwarp();
+                if (lane < W) {
+                    if (lane < F.nd)
+                        for (uint32_t r = 0; r < n; ++r) accd += __longlong_as_double((long long)st[r * W + lane]);
                     else
-                        for (uint32_t r = 0; r < n; ++r) accu += stage[r * W + tid];
+                        for (uint32_t r = 0; r < n; ++r) accu += st[r * W + lane];
                 }
-                __syncthreads();
+                __syncwarp();
             }
-            if (tid < W)
-                vals[base + tid] = tid < F.nd ? (unsigned long long)__double_as_longlong(accd) : accu;
-            base += W;
+            if (lane < W)
+                vals[base + lane] = lane < F.nd ? (unsigned long long)__double_as_longlong(accd) : accu;
         }
     }
     __syncthreads();
@@ -130,9 +133,11 @@ fm_k_comm_exchange(const CommParams P) {
         unsigned long long *dst = P.peers[p]->data[buf][P.rank];
         for (uint32_t i = tid; i < P.n_words; i += nt) dst[i] = vals[i];
     }
-    __threadfence_system();  // every thread's slot stores are visible system-wide ...
-    __syncthreads();         // ... before any flag is published (one fence per thread, none per flag)
-    if (tid < P.world) fm_st_relaxed_sys(&P.peers[tid]->flags[P.rank * 16], P.step);
+    // slot stores -> CTA barrier -> release store of the flag by the publishing thread: the
+    // barrier orders every thread's stores before the publisher's release (fence cumulativity, the
+    // pattern of a grid-wide barrier), so one system-scope release per flag is enough
+    __syncthreads();
+    if (tid < P.world) fm_st_release_sys(&P.peers[tid]->flags[P.rank * 16], P.step);
     // ---- 3. wait for every rank's contribution to land in OUR mailbox
     CommMailbox *mine = P.peers[P.rank];
     if (tid < P.world) {
@@ -144,7 +149,7 @@ fm_k_comm_exchange(const CommParams P) {
             }
             __nanosleep(32);
         }
-        __threadfence_system();  // acquire: the slot loads below are ordered after the flag
+        (void)fm_ld_acquire_sys(&mine->flags[tid * 16]);  // acquire: slot loads below are ordered after the flag
     }
     __syncthreads();
     if (timed_out) {

@@ -460,6 +460,17 @@ fm::GroupPlanes planes_of(const fm_group *g) {
     return fm::GroupPlanes{g->d_allele, g->d_called, g->wq, g->n};
 }
 
+// K5a: mask / filtered-position bit per site, one word per batch
+void launch_site_flags(const fm_matrix *m, uint32_t v_lo, uint32_t v_hi, uint32_t b_lo, uint32_t n_batches,
+                       const int64_t *d_mask, uint32_t n_mask, const int64_t *d_filt, uint32_t n_filt,
+                       uint32_t *d_flags) {
+    const uint32_t fb = std::max(1u, std::min<uint32_t>((n_batches + 7) / 8, 8u * (uint32_t)sm_count(m->device)));
+    fm::fm_k_site_flags<<<fb, 256, 0, stream()>>>(m->d_pos, v_lo, v_hi, b_lo, n_batches, d_mask, n_mask, d_filt,
+                                                   n_filt, d_flags);
+    CK(cudaGetLastError());
+    g_launches++;
+}
+
 struct DivResult {
     double pi_sum;
     uint64_t seg, unc;
@@ -485,11 +496,7 @@ DivResult run_diversity(fm_group *g, uint32_t v_lo, uint32_t v_hi, int pi_form, 
     tm.start();
     if (d_pi && (d_mask || d_filt)) {  // K5a: mask / filtered-position bits, one word per batch
         flags.alloc(G.n_batches);
-        const uint32_t fb = std::min<uint32_t>((G.n_batches + 7) / 8, 8u * sm_count(g->m->device));
-        fm::fm_k_site_flags<<<fb, 256, 0, stream()>>>(g->m->d_pos, v_lo, v_hi, G.b_lo, G.n_batches, d_mask,
-                                                       n_mask, d_filt, n_filt, flags.p);
-        CK(cudaGetLastError());
-        g_launches++;
+        launch_site_flags(g->m, v_lo, v_hi, G.b_lo, G.n_batches, d_mask, n_mask, d_filt, n_filt, flags.p);
         e.site_flags = flags.p;
     }
     e.pi_form = pi_form;
@@ -1644,17 +1651,25 @@ void run_wc(fm_partition *p, const std::vector<uint32_t> &wlo, const std::vector
     W.part_pair = d_pp.p;
     W.part_pair_n = d_pn.p;
 
-    const size_t per_warp = fm::fm_wc_warp_smem(G, n_pairs);
-    int warps = fm::kWcWarpsPerCta;
-    while (warps > 1 && per_warp * warps > 200 * 1024) --warps;
-    if (per_warp > 200 * 1024) fail(FM_ERR_UNSUPPORTED, "too many populations for the W&C kernel's staging");
-    const size_t smem = per_warp * warps;
-    CK(cudaFuncSetAttribute(fm::fm_k_wc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint32_t blocks = std::max<uint32_t>(
-        1, std::min<uint32_t>((n_seg + warps - 1) / warps, 16u * sm_count(m->device)));
+    // CTA geometry: pair warps (lane = pair, KP pairs per lane in registers) + one overall warp
+    uint32_t n_pw = std::max(1u, std::min<uint32_t>(fm::kWcMaxPairWarps, (n_pairs + 31) / 32));
+    const uint32_t kp_need = std::max(1u, (n_pairs + n_pw * 32 - 1) / (n_pw * 32));
+    if (kp_need > fm::kWcMaxKP) fail(FM_ERR_UNSUPPORTED, "too many populations for the W&C kernel (pairs per lane)");
+    const size_t smem = fm::fm_wc_cta_smem(G);
+    if (smem > 200 * 1024) fail(FM_ERR_UNSUPPORTED, "too many populations for the W&C kernel's staging");
+    W.n_pair_warps = n_pw;
+    const uint32_t threads = (n_pw + 1) * 32;
+    const uint32_t blocks = std::max<uint32_t>(1, std::min<uint32_t>(n_seg, 8u * sm_count(m->device)));
     Timer tm;
     tm.start();
-    fm::fm_k_wc<<<blocks, warps * 32, smem, stream()>>>(W);
+    auto launch = [&](auto kern) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<blocks, threads, smem, stream()>>>(W);
+    };
+    if (kp_need <= 1) launch(fm::fm_k_wc<1>);
+    else if (kp_need <= 2) launch(fm::fm_k_wc<2>);
+    else if (kp_need <= 4) launch(fm::fm_k_wc<4>);
+    else launch(fm::fm_k_wc<8>);
     CK(cudaGetLastError());
     g_launches++;
     DevBuf<double> d_oo(nw * 2), d_op(nw * std::max(n_pairs, 1u) * 2);
@@ -1978,7 +1993,8 @@ struct fm_comm {
 namespace {
 // Enqueue one exchange on the calling thread's stream (asynchronous).
 void comm_launch(fm_comm *c, const unsigned long long *d_local, uint32_t n_words, uint32_t n_double,
-                 const fm::CommFold *folds, uint32_t n_fold) {
+                 const fm::CommFold *folds, uint32_t n_fold, cudaStream_t st = nullptr) {
+    if (!st) st = stream();
     if (!c->connected) fail(FM_ERR_INVALID_ARG, "fm_comm is not connected");
     if (n_words > fm::kCommMaxValues) fail(FM_ERR_INVALID_ARG, "too many values for one exchange");
     fm::CommParams P{};
@@ -1990,12 +2006,15 @@ void comm_launch(fm_comm *c, const unsigned long long *d_local, uint32_t n_words
     P.n_double = n_double;
     P.local = d_local;
     P.n_fold = n_fold;
-    for (uint32_t f = 0; f < n_fold; ++f) P.fold[f] = folds[f];
+    for (uint32_t f = 0; f < n_fold; ++f) {
+        if (folds[f].nd + folds[f].nu > 32) fail(FM_ERR_INVALID_ARG, "fold has more than 32 columns");
+        P.fold[f] = folds[f];
+    }
     P.gathered = c->d_gathered;
     P.merged = c->d_merged;
     P.status = c->d_status;
     P.timeout_ns = c->timeout_ns;
-    fm::fm_k_comm_exchange<<<1, 128, 0, stream()>>>(P);
+    fm::fm_k_comm_exchange<<<1, 128, 0, st>>>(P);
     CK(cudaGetLastError());
     g_launches++;
 }
@@ -2190,9 +2209,9 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
         const uint32_t V = (uint32_t)m->V;
         struct PerGroup {
             fm::PassParams<1> P;
-            DevBuf<double> part_pi, pi, theta, sd;
-            DevBuf<uint32_t> part_u;
-            DevBuf<uint64_t> su;
+            DevBuf<double> part_pi, pi, theta, sd[2];  // super-batch partials double-buffered by step parity:
+            DevBuf<uint32_t> part_u;                    // the exchange of step i overlaps step i+1
+            DevBuf<uint64_t> su[2];
         };
         std::vector<PerGroup> pg(n_groups);
         DevBuf<int64_t> d_mask;
@@ -2214,8 +2233,10 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
             const size_t nb = std::max<uint32_t>(G.n_batches, 1);
             pg[i].part_pi.alloc(nb);
             pg[i].part_u.alloc(nb * 2);
-            pg[i].sd.alloc(nb / fm::kSuperBatches + 2);
-            pg[i].su.alloc(2 * (nb / fm::kSuperBatches + 2));
+            for (int k = 0; k < 2; ++k) {
+                pg[i].sd[k].alloc(nb / fm::kSuperBatches + 2);
+                pg[i].su[k].alloc(2 * (nb / fm::kSuperBatches + 2));
+            }
             fm::DivEpilogue e{};
             set_tables(e, g);
             e.pi_form = FM_PIFORM_COUNTS;
@@ -2240,16 +2261,24 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
         EventPairs evs;
         std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans, comm_spans;
         cudaEvent_t t0 = evs.next(), t1 = evs.next();
+        // The exchange runs on its own stream: the step's kernels never wait for a peer, and the
+        // one-CTA exchange kernel of step i hides under the plane passes of step i+1.
+        struct SideStream {
+            cudaStream_t s = nullptr;
+            ~SideStream() {
+                if (s) cudaStreamDestroy(s);
+            }
+        } side;
+        std::vector<cudaEvent_t> exchanged;  // exchange of step i finished reading buffer i & 1
+        if (comm) CK(cudaStreamCreateWithFlags(&side.s, cudaStreamNonBlocking));
         CK(cudaStreamSynchronize(stream()));
         CK(cudaEventRecord(t0, stream()));
         for (int it = 0; it < iterations; ++it) {
+            const int pb = it & 1;
+            if (comm && it >= 2) CK(cudaStreamWaitEvent(stream(), exchanged[it - 2], 0));
             if (mode == 1 && mask_iv && nb_all) {  // the mask lookup is part of every step
-                const uint32_t fb = std::min<uint32_t>((nb_all + 7) / 8, 8u * sm_count(m->device));
-                fm::fm_k_site_flags<<<fb, 256, 0, stream()>>>(m->d_pos, 0, V, 0, nb_all, d_mask.p,
-                                                               (uint32_t)(merged.size() / 2), nullptr, 0,
-                                                               d_flags.p);
-                CK(cudaGetLastError());
-                g_launches++;
+                launch_site_flags(m, 0, V, 0, nb_all, d_mask.p, (uint32_t)(merged.size() / 2), nullptr, 0,
+                                  d_flags.p);
                 out->other_launches++;
             }
             for (size_t i = 0; i < n_groups; ++i) {
@@ -2260,7 +2289,7 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
                 spans.emplace_back(a, b);
                 out->plane_launches++;
                 if (pg[i].P.geom.n_batches) {
-                    launch_reduce(pg[i].part_pi.p, 1, pg[i].part_u.p, 2, pg[i].P.geom, pg[i].sd.p, pg[i].su.p);
+                    launch_reduce(pg[i].part_pi.p, 1, pg[i].part_u.p, 2, pg[i].P.geom, pg[i].sd[pb].p, pg[i].su[pb].p);
                     out->other_launches++;
                 }
             }
@@ -2272,18 +2301,23 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
                     if (!G.n_batches) continue;
                     const uint32_t s_lo = G.b_lo / fm::kSuperBatches;
                     const uint32_t n_super = (G.b_lo + G.n_batches + fm::kSuperBatches - 1) / fm::kSuperBatches - s_lo;
-                    folds[nf++] = fm::CommFold{pg[i].sd.p, reinterpret_cast<const unsigned long long *>(pg[i].su.p),
-                                               n_super, 1u, 2u};
+                    folds[nf++] = fm::CommFold{pg[i].sd[pb].p,
+                                               reinterpret_cast<const unsigned long long *>(pg[i].su[pb].p), n_super, 1u,
+                                               2u};
                     words += 3;
                 }
-                cudaEvent_t a = evs.next(), b = evs.next();
-                CK(cudaEventRecord(a, stream()));
-                comm_launch(comm, nullptr, words, 0, folds, nf);
-                CK(cudaEventRecord(b, stream()));
+                cudaEvent_t ready = evs.next(), a = evs.next(), b = evs.next();
+                CK(cudaEventRecord(ready, stream()));
+                CK(cudaStreamWaitEvent(side.s, ready, 0));
+                CK(cudaEventRecord(a, side.s));
+                comm_launch(comm, nullptr, words, 0, folds, nf, side.s);
+                CK(cudaEventRecord(b, side.s));
                 comm_spans.emplace_back(a, b);
+                exchanged.push_back(b);
                 out->other_launches++;
             }
         }
+        if (comm && !exchanged.empty()) CK(cudaStreamWaitEvent(stream(), exchanged.back(), 0));  // last exchange is inside the timed region
         CK(cudaEventRecord(t1, stream()));
         CK(cudaEventSynchronize(t1));
         float total = 0.f, plane = 0.f;
