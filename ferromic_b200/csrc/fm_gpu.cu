@@ -318,8 +318,21 @@ fm::PassGeom make_geom(const fm_group *const *gs, int ng, uint32_t v_lo, uint32_
         max_wq = std::max(max_wq, gs[i]->wq);
     }
     static const uint32_t step_target = env_u32("FM_STEP_BYTES", fm::kStepBytesTarget);
-    static const uint32_t warp_smem = std::min(env_u32("FM_WARP_SMEM", fm::kWarpSmemBytes), fm::kWarpSmemBytes);
+    static const uint32_t base_warps = std::max(1u, std::min<uint32_t>(env_u32("FM_WARPS", fm::kWarpsPerCta), fm::kWarpsPerCta));
+    uint32_t warp_smem = (fm::kWarpsPerCta * fm::kWarpSmemBytes / base_warps) & ~127u;
     static const uint32_t force_lg = env_u32("FM_FORCE_LG", 99);
+    G.warps = base_warps;
+    // rows wider than a warp's ring (biobank cohorts) are consumed in column chunks: fewer warps
+    // with deeper rings keep more bytes in flight per warp and amortise the per-step bookkeeping
+    static const uint32_t chunk_warps = std::min<uint32_t>(env_u32("FM_CHUNK_WARPS", 8), fm::kWarpsPerCta);
+    static const uint32_t chunk_step = env_u32("FM_CHUNK_STEP_BYTES", 14336);  // swept on B200: profiles/r01_sweep_chunked.txt
+    const bool chunked = (uint64_t)row_bytes * 2 > fm::kWarpSmemBytes;
+    uint32_t step_goal = step_target;
+    if (chunked) {
+        G.warps = chunk_warps;
+        warp_smem = (fm::kWarpsPerCta * fm::kWarpSmemBytes / chunk_warps) & ~127u;
+        step_goal = chunk_step;
+    }
     G.warp_smem_bytes = warp_smem;
     static const uint32_t dbg = env_u32("FM_DEBUG", 0);
     G.debug = dbg;
@@ -342,7 +355,7 @@ fm::PassGeom make_geom(const fm_group *const *gs, int ng, uint32_t v_lo, uint32_
         step_bytes = round_bytes * G.rounds;
     } else {
         if (row_bytes * 2 > warp_smem) {  // a single row does not fit twice: chunk its columns
-            G.cq = std::max(1u, step_target / (16u * planes));
+            G.cq = std::max(1u, step_goal / (16u * planes));
             G.n_chunks = (max_wq + G.cq - 1) / G.cq;
         }
         step_bytes = G.cq * 16u * planes;
@@ -386,7 +399,7 @@ template <int NG, int LG, bool HC>
 void launch_plane_pass_t(const fm::PassParams<NG> &P, uint32_t grid, size_t smem) {
     CK(cudaFuncSetAttribute(fm::fm_k_plane_pass<NG, LG, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)smem));
-    fm::fm_k_plane_pass<NG, LG, HC><<<grid, fm::kWarpsPerCta * 32, smem, stream()>>>(P);
+    fm::fm_k_plane_pass<NG, LG, HC><<<grid, P.geom.warps * 32, smem, stream()>>>(P);
 }
 
 template <int NG, bool HC>
@@ -405,8 +418,8 @@ template <int NG>
 void launch_plane_pass(fm::PassParams<NG> P, int device) {
     if (P.geom.n_batches == 0) return;
     P.geom.batch_counter = t_counters.take(device);
-    const size_t smem = (size_t)fm::kWarpsPerCta * P.geom.warp_smem_bytes;
-    const uint32_t need = (P.geom.n_batches + fm::kWarpsPerCta - 1) / fm::kWarpsPerCta;
+    const size_t smem = (size_t)P.geom.warps * P.geom.warp_smem_bytes;
+    const uint32_t need = (P.geom.n_batches + P.geom.warps - 1) / P.geom.warps;
     const uint32_t grid = std::min<uint32_t>((uint32_t)sm_count(device), need);
     bool hc = P.g[0].called != nullptr;
     for (int g = 1; g < NG; ++g)

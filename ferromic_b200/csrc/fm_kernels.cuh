@@ -175,6 +175,7 @@ struct PassGeom {
     uint32_t n_stages;    // pipeline depth of the per-warp ring (2..kMaxStages)
     uint32_t stage_bytes; // bytes reserved per stage (multiple of 128)
     uint32_t warp_smem_bytes;  // private staging ring of one warp (n_stages * stage_bytes <= this)
+    uint32_t warps;            // warps per CTA (<= kWarpsPerCta); warps * warp_smem_bytes <= 224 KB
     uint32_t v_lo, v_hi;
     uint32_t b_lo, n_batches;  // global batch range (batch b = sites [32b, 32b+32))
     uint32_t n_sites_total;    // V (rows available in the planes)
