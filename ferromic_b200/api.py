@@ -495,16 +495,23 @@ class Population:
     # --- path selection: OwnedPopulationContext::as_population_context (lib.rs:777-799)
     def _summary_group(self) -> Optional[_Group]:
         dm = self._shared.dense_matrix()
-        if dm is None:
+        if dm is None or dm.max_allele > 1:  # no summary for multi-allelic matrices (lib.rs:779)
             return None
-        if dm.max_allele > 1:
-            raise NotImplementedError("multi-allelic dense matrices (max_allele > 1) are not on the GPU path yet")
         return dm.group(self._haps)
+
+    def _dense_group(self) -> Optional[_Group]:
+        """dense_genotypes of the context (ploidy-2 numpy input); for a multi-allelic matrix it
+        comes without a summary and the reference takes its general dense paths."""
+        dm = self._shared.dense_matrix()
+        return None if dm is None else dm.group(self._haps)
 
     def segregating_sites(self) -> int:  # lib.rs:636 -> stats.rs:3831-3851
         g = self._summary_group()
         if g is not None:
             return g.summary()["segregating_sites"]
+        g = self._dense_group()
+        if g is not None:  # count_segregating_sites_dense (stats.rs:3891-4026)
+            return g.segregating_sites()
         # sparse: count_segregating_sites_for_haplotypes (raw list; duplicates are harmless)
         vs = self._shared.variants
         if vs.n_variants == 0:
@@ -515,6 +522,9 @@ class Population:
         g = self._summary_group()
         if g is not None:
             return g.pi(self._L, _lib.FM_PI_SUMMARY)
+        g = self._dense_group()
+        if g is not None:  # calculate_pi_dense (stats.rs:4534-4597)
+            return g.pi(self._L, _lib.FM_PI_DENSE)
         return _sparse_pi(self._shared.variants, self._haps, self._L)
 
     @property
@@ -726,6 +736,10 @@ def _hudson_dxy_value(p1: Population, p2: Population):  # calculate_d_xy_hudson 
     if s1 is not None and s2 is not None:
         check(lib().fm_hudson_dxy(s1.handle, s2.handle, p1._L, p2._L, _lib.FM_HUDSON_SUMMARIES, len(p1._haps),
                                   len(p2._haps), C.byref(d), C.byref(some)))
+    elif p1._shared is p2._shared and p1._dense_group() is not None:
+        # same dense matrix, ploidy 2, no summaries: calculate_dxy_dense (stats.rs:2456-2470, 2526-2611)
+        check(lib().fm_hudson_dxy(p1._dense_group().handle, p2._dense_group().handle, p1._L, p2._L,
+                                  _lib.FM_HUDSON_DENSE, len(p1._haps), len(p2._haps), C.byref(d), C.byref(some)))
     else:
         if p1._shared.variants.n_variants == 0:
             return 0.0 / p1._L if p1._L > 0 else None
@@ -781,6 +795,14 @@ def _hudson_core(p1: Population, p2: Population, region):
         n = C.c_size_t()
         check(lib().fm_hudson_pair(s1.handle, s2.handle, p1._L, p2._L, _lib.FM_HUDSON_SUMMARIES, 0, 0, 0,
                                    len(p1._haps), len(p2._haps), C.byref(out), None, C.byref(n)))
+        return HudsonFstResult(_opt(out.fst, out.some, 0), _opt(out.d_xy, out.some, 1), _opt(out.pi_pop1, out.some, 2),
+                               _opt(out.pi_pop2, out.some, 3), _opt(out.pi_xy_avg, out.some, 4), p1._id, p2._id), sites
+    if region is None and p1._shared is p2._shared and p1._dense_group() is not None:
+        # shared dense matrix without summaries (multi-allelic): dense_hudson_sites (stats.rs:3481-3489)
+        n = C.c_size_t()
+        check(lib().fm_hudson_pair(p1._dense_group().handle, p2._dense_group().handle, p1._L, p2._L,
+                                   _lib.FM_HUDSON_DENSE, 0, 0, 0, len(p1._haps), len(p2._haps), C.byref(out), None,
+                                   C.byref(n)))
         return HudsonFstResult(_opt(out.fst, out.some, 0), _opt(out.d_xy, out.some, 1), _opt(out.pi_pop1, out.some, 2),
                                _opt(out.pi_pop2, out.some, 3), _opt(out.pi_xy_avg, out.some, 4), p1._id, p2._id), sites
     # per-site sparse path (region) or whole-slice sparse path

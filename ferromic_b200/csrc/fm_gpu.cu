@@ -5,6 +5,7 @@
 #include "fm_kernels.cuh"
 #include "fm_wc.cuh"
 #include "fm_comm.cuh"
+#include "fm_multi.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -277,6 +278,8 @@ struct fm_group {
     std::mutex mu;
     bool have_counts = false;
     uint32_t *d_alt = nullptr, *d_cnt = nullptr;
+    uint32_t n_bits = 1;            // allele bitplanes (1 = biallelic; 2..4 = multi-allelic matrix)
+    uint32_t *d_acount = nullptr;   // multi-allelic: cached per-allele counts [V][1 << n_bits]
     uint64_t seg = 0, unc = 0;
     double pi_sum = 0.0;  // dense_pi_from_counts form over all sites
 };
@@ -489,11 +492,96 @@ struct DivResult {
     uint64_t seg, unc;
 };
 
+void ensure_counts(fm_group *g);
+
+// Multi-allelic groups (fm_multi.cuh): diversity statistics of [v_lo, v_hi) from the cached
+// per-allele counts.  form: FM_MULTI_DENSE (calculate_pi_dense general) or FM_MULTI_SPARSE.
+DivResult run_multi_diversity(fm_group *g, uint32_t v_lo, uint32_t v_hi, int form, double *d_pi, double *d_theta,
+                              const int64_t *d_mask, uint32_t n_mask, const int64_t *d_filt, uint32_t n_filt) {
+    DivResult r{0.0, 0, 0};
+    fm::PassGeom G{};
+    G.b_lo = v_lo / 32;
+    G.n_batches = v_hi > v_lo ? (v_hi + 31) / 32 - G.b_lo : 0;
+    if (G.n_batches == 0) return r;
+    DevBuf<double> part_pi(G.n_batches);
+    DevBuf<uint32_t> part_u((size_t)G.n_batches * 2);
+    fm::DivEpilogue e{};
+    e.pi_out = d_pi;
+    e.theta_out = d_theta;
+    set_tables(e, g);
+    e.part_pi = part_pi.p;
+    e.part_u = part_u.p;
+    DevBuf<uint32_t> flags;
+    Timer tm;
+    tm.start();
+    if (d_pi && (d_mask || d_filt)) {
+        flags.alloc(G.n_batches);
+        launch_site_flags(g->m, v_lo, v_hi, G.b_lo, G.n_batches, d_mask, n_mask, d_filt, n_filt, flags.p);
+        e.site_flags = flags.p;
+    }
+    const uint32_t blocks = std::min<uint32_t>((G.n_batches + 7) / 8, 8u * sm_count(g->m->device));
+    fm::fm_k_multi_div_from_counts<<<blocks, 256, 0, stream()>>>(g->d_acount, g->d_cnt, 1u << g->n_bits, form, e, v_lo,
+                                                                  v_hi, G.b_lo, G.n_batches);
+    CK(cudaGetLastError());
+    g_launches++;
+    tm.stop();
+    double od[1];
+    uint64_t ou[2];
+    finish_partials(part_pi.p, 1, part_u.p, 2, G, od, ou);
+    t_tim.stats_ms += tm.ms();
+    r.pi_sum = od[0];
+    r.seg = ou[0];
+    r.unc = ou[1];
+    return r;
+}
+
+// per-allele counts of a multi-allelic group (K2m) + the general dense summary scalars
+void ensure_multi_counts_locked(fm_group *g) {
+    set_dev(g->m);
+    const size_t V = g->m->V;
+    const uint32_t A = 1u << g->n_bits;
+    if (!g->d_acount) {
+        g->d_acount = static_cast<uint32_t *>(dev_alloc(std::max<size_t>(V, 1) * A * sizeof(uint32_t)));
+        g->d_cnt = static_cast<uint32_t *>(dev_alloc(std::max<size_t>(V, 1) * sizeof(uint32_t)));
+    }
+    if (V) {
+        uint32_t lg = 0;
+        while ((1u << lg) < std::min(g->wq, 32u)) ++lg;
+        const uint32_t sps = 32u >> lg;
+        const uint64_t warps_needed = ((uint64_t)V + sps - 1) / sps;
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>((warps_needed + 7) / 8, 16ull * sm_count(g->m->device));
+        const size_t ps = std::max<size_t>(V, 1) * g->wq;
+        Timer tm;
+        tm.start();
+        switch (g->n_bits) {
+            case 2: fm::fm_k_allele_counts<2><<<blocks, 256, 0, stream()>>>(g->d_allele, ps, g->d_called, g->wq, g->n, lg, 0, (uint32_t)V, g->d_acount, g->d_cnt); break;
+            case 3: fm::fm_k_allele_counts<3><<<blocks, 256, 0, stream()>>>(g->d_allele, ps, g->d_called, g->wq, g->n, lg, 0, (uint32_t)V, g->d_acount, g->d_cnt); break;
+            default: fm::fm_k_allele_counts<4><<<blocks, 256, 0, stream()>>>(g->d_allele, ps, g->d_called, g->wq, g->n, lg, 0, (uint32_t)V, g->d_acount, g->d_cnt); break;
+        }
+        CK(cudaGetLastError());
+        g_launches++;
+        t_tim.stats_launches++;
+        t_tim.stats_bytes = (uint64_t)V * g->wq * 16u * (g->n_bits + (g->d_called ? 1u : 0u));
+        tm.stop();
+        t_tim.stats_ms += tm.ms();
+    }
+    g->have_counts = true;  // run_multi_diversity reads the cached counts
+    DivResult r = run_multi_diversity(g, 0, (uint32_t)V, FM_MULTI_DENSE, nullptr, nullptr, nullptr, 0, nullptr, 0);
+    g->seg = r.seg;
+    g->unc = r.unc;
+    g->pi_sum = r.pi_sum;
+}
+
 // Run the diversity statistics for sites [v_lo, v_hi): fused plane pass when counts are not
 // cached (optionally caching them when the range is the whole matrix), light kernel otherwise.
 DivResult run_diversity(fm_group *g, uint32_t v_lo, uint32_t v_hi, int pi_form, double *d_pi,
                         double *d_theta, const int64_t *d_mask, uint32_t n_mask, const int64_t *d_filt,
                         uint32_t n_filt, bool store_counts, bool force_plane_pass = false) {
+    if (g->n_bits > 1) {  // multi-allelic: always from the cached per-allele counts
+        if (!g->have_counts) ensure_multi_counts_locked(g);
+        return run_multi_diversity(g, v_lo, v_hi, pi_form == FM_PIFORM_COMPONENTS ? FM_MULTI_SPARSE : FM_MULTI_DENSE,
+                                   d_pi, d_theta, d_mask, n_mask, d_filt, n_filt);
+    }
     const fm_group *gs[1] = {g};
     fm::PassGeom G = make_geom(gs, 1, v_lo, v_hi);
     DivResult r{0.0, 0, 0};
@@ -550,6 +638,10 @@ DivResult run_diversity(fm_group *g, uint32_t v_lo, uint32_t v_hi, int pi_form, 
 void ensure_counts(fm_group *g) {
     std::lock_guard<std::mutex> lk(g->mu);
     if (g->have_counts) return;
+    if (g->n_bits > 1) {
+        ensure_multi_counts_locked(g);
+        return;
+    }
     set_dev(g->m);
     const size_t V = g->m->V;
     if (!g->d_alt) {
@@ -584,8 +676,16 @@ HudsonTotals run_hudson_counts(fm_group *g1, fm_group *g2, uint32_t v_lo, uint32
     Timer tm;
     tm.start();
     const uint32_t blocks = std::min<uint32_t>((G.n_batches + 7) / 8, 8u * sm_count(g1->m->device));
-    fm::fm_k_hudson_from_counts<<<blocks, 256, 0, stream()>>>(g1->d_alt, g1->d_cnt, g2->d_alt, g2->d_cnt,
-                                                               e, v_lo, v_hi, G.b_lo, G.n_batches);
+    if (g1->n_bits > 1) {
+        if (variant < 0)
+            fail(FM_ERR_UNSUPPORTED, "the summaries path does not exist for multi-allelic matrices (lib.rs:779)");
+        if (g2->n_bits != g1->n_bits) fail(FM_ERR_INVALID_ARG, "groups of one pass must share a matrix");
+        fm::fm_k_multi_hudson_from_counts<<<blocks, 256, 0, stream()>>>(
+            g1->d_acount, g1->d_cnt, g2->d_acount, g2->d_cnt, 1u << g1->n_bits,
+            variant == FM_HV_SPARSE ? FM_MULTI_SPARSE : FM_MULTI_DENSE, e, v_lo, v_hi, G.b_lo, G.n_batches);
+    } else
+        fm::fm_k_hudson_from_counts<<<blocks, 256, 0, stream()>>>(g1->d_alt, g1->d_cnt, g2->d_alt, g2->d_cnt,
+                                                                   e, v_lo, v_hi, G.b_lo, G.n_batches);
     CK(cudaGetLastError());
     g_launches++;
     tm.stop();
@@ -823,8 +923,10 @@ fm_status fm_matrix_info(const fm_matrix *m, size_t *V, size_t *S, size_t *ploid
 // ------------------------------------------------------------------------------------ group
 // Allocate a group's bitplanes and lookup tables for the columns listed in `off` (sorted, unique).
 static fm_group *alloc_group(fm_matrix *m, std::vector<uint32_t> &&off) {
-    if (m->max_allele > 1)
-        fail(FM_ERR_UNSUPPORTED, "multi-allelic matrices (max_allele > 1) are not on the GPU path yet");
+    uint32_t n_bits = 1;
+    while ((1u << n_bits) <= m->max_allele) ++n_bits;
+    if (n_bits > 4)
+        fail(FM_ERR_UNSUPPORTED, "allele indices above 15 are not supported on the GPU path (max_allele <= 15)");
     set_dev(m);
     fm_group *g = new fm_group();
     g->m = m;
@@ -833,8 +935,9 @@ static fm_group *alloc_group(fm_matrix *m, std::vector<uint32_t> &&off) {
         g->off = std::move(off);
         g->n = (uint32_t)g->off.size();
         g->wq = std::max<uint32_t>(1, (g->n + 127) / 128);
+        g->n_bits = n_bits;
         const size_t plane_u4 = std::max<size_t>(m->V, 1) * g->wq;
-        g->d_allele = static_cast<uint4 *>(dev_alloc(plane_u4 * 16));
+        g->d_allele = static_cast<uint4 *>(dev_alloc(plane_u4 * 16 * n_bits));
         if (m->has_missing) g->d_called = static_cast<uint4 *>(dev_alloc(plane_u4 * 16));
         // per-n tables: 1/n, n/(n-1) (stats.rs:2728-2732) and 1/H_{n-1} with the harmonic number
         // by forward summation exactly like stats.rs:4234-4240 / 4718-4719
@@ -871,7 +974,8 @@ static void launch_repack(const fm_group *g, const uint8_t *data, const uint64_t
         std::max<uint64_t>(1, ((uint64_t)(v_hi - v_lo) * ((g->wq * 4 + 31) / 32) + 7) / 8));
     fm::fm_k_repack<<<blocks, 256, 0, st>>>(data, missing, m->stride, g->d_off, g->n, g->wq, v_base, word_base,
                                             v_lo, v_hi, reinterpret_cast<uint32_t *>(g->d_allele),
-                                            reinterpret_cast<uint32_t *>(g->d_called));
+                                            reinterpret_cast<uint32_t *>(g->d_called), g->n_bits,
+                                            std::max<size_t>(m->V, 1) * g->wq * 4);
     CK(cudaGetLastError());
     g_launches++;
 }
@@ -967,6 +1071,7 @@ fm_status fm_group_release(fm_group *g) {
     dev_free(g->d_off);
     dev_free(g->d_alt);
     dev_free(g->d_cnt);
+    dev_free(g->d_acount);
     fm_matrix_release(g->m);
     delete g;
     return FM_OK;
@@ -983,6 +1088,10 @@ fm_status fm_group_summary(fm_group *g, uint32_t *alt_out, uint32_t *called_out,
     return guarded([&] {
         if (!g) fail(FM_ERR_INVALID_ARG, "group is NULL");
         require_device();
+        if (g->n_bits > 1 && alt_out)
+            fail(FM_ERR_UNSUPPORTED,
+                 "alt counts are undefined for a multi-allelic matrix (the reference builds no summary when "
+                 "max_allele > 1, lib.rs:779)");
         ensure_counts(g);
         set_dev(g->m);
         Timer tm;
@@ -1026,6 +1135,8 @@ fm_status fm_group_pi(fm_group *g, int64_t L, int path, size_t raw_n, double *ou
         if (L < 0) { *out = 0.0; return; }
         if (L == 0) { *out = Inf; return; }
         if (path == FM_PI_SPARSE && g->n <= 1) { *out = NaN; return; }  // :4365
+        if (g->n_bits > 1 && path == FM_PI_SUMMARY)
+            fail(FM_ERR_UNSUPPORTED, "no dense summary exists for a multi-allelic matrix (lib.rs:779)");
         ensure_counts(g);
         set_dev(g->m);
         double pi_sum;
@@ -1221,6 +1332,8 @@ fm_status fm_ingest_add_partition(fm_ingest *h, const uint16_t *left, const uint
         if (!h) fail(FM_ERR_INVALID_ARG, "ingest handle is NULL");
         if (n_samples && (!left || !right)) fail(FM_ERR_INVALID_ARG, "membership arrays are NULL");
         if (n_groups >= 0xFFFF) fail(FM_ERR_INVALID_ARG, "too many groups");
+        if (h->m->max_allele > 1)
+            fail(FM_ERR_UNSUPPORTED, "Weir & Cockerham on multi-allelic matrices is not on the GPU path yet");
         if (h->rows_done) fail(FM_ERR_INVALID_ARG, "partitions must be declared before the first fm_ingest_rows");
         fm_partition *p = new fm_partition();
         p->m = h->m;
@@ -1428,7 +1541,7 @@ fm_status fm_hudson_pair(fm_group *g1, fm_group *g2, int64_t L1, int64_t L2, int
         // counts: fused two-group sweep when nothing is cached yet and the main pass covers the
         // whole matrix; otherwise per-group plane passes (cached) + light kernels on the counts.
         bool fused = false;
-        if (g1 != g2 && g1->m == g2->m && lo == 0 && hi == V && V > 0) {
+        if (g1 != g2 && g1->m == g2->m && lo == 0 && hi == V && V > 0 && g1->n_bits == 1) {
             std::unique_lock<std::mutex> l1(g1->mu, std::defer_lock), l2(g2->mu, std::defer_lock);
             std::lock(l1, l2);
             if (!g1->have_counts && !g2->have_counts) {
@@ -1526,6 +1639,8 @@ fm_status fm_partition_create(fm_matrix *m, const uint16_t *left, const uint16_t
         *out = nullptr;
         if (n_samples && (!left || !right)) fail(FM_ERR_INVALID_ARG, "membership arrays are NULL");
         if (n_groups >= 0xFFFF) fail(FM_ERR_INVALID_ARG, "too many groups");
+        if (m->max_allele > 1)
+            fail(FM_ERR_UNSUPPORTED, "Weir & Cockerham on multi-allelic matrices is not on the GPU path yet");
         require_device();
         fm_partition *p = new fm_partition();
         p->m = m;
@@ -1886,6 +2001,7 @@ fm_status fm_group_window_sums(fm_group *g, const int64_t *windows, size_t n_win
         if (!g || (n_windows && !windows)) fail(FM_ERR_INVALID_ARG, "NULL argument");
         require_device();
         if (!n_windows) return;
+        if (g->n_bits > 1) fail(FM_ERR_UNSUPPORTED, "window sums are biallelic-only on the GPU path");
         ensure_counts(g);
         set_dev(g->m);
         std::vector<uint32_t> lo, hi;
@@ -1917,6 +2033,7 @@ fm_status fm_hudson_window_sums(fm_group *g1, fm_group *g2, const int64_t *windo
         if (n_windows && !windows) fail(FM_ERR_INVALID_ARG, "NULL argument");
         require_device();
         if (!n_windows) return;
+        if (g1->n_bits > 1) fail(FM_ERR_UNSUPPORTED, "window sums are biallelic-only on the GPU path");
         ensure_counts(g1);
         ensure_counts(g2);
         set_dev(g1->m);

@@ -39,7 +39,8 @@ constexpr int kBatchRing = 8;                    // claimed-batch ring per warp 
 __global__ void __launch_bounds__(256)
 fm_k_repack(const uint8_t *__restrict__ data, const uint64_t *__restrict__ missing, size_t stride,
             const uint32_t *__restrict__ off, uint32_t n, uint32_t wq, uint32_t v_base, uint64_t word_base,
-            uint32_t v_lo, uint32_t v_hi, uint32_t *__restrict__ allele, uint32_t *__restrict__ called) {
+            uint32_t v_lo, uint32_t v_hi, uint32_t *__restrict__ allele, uint32_t *__restrict__ called,
+            uint32_t n_bits, size_t plane_stride_words) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -51,13 +52,14 @@ fm_k_repack(const uint8_t *__restrict__ data, const uint64_t *__restrict__ missi
         const uint32_t wg = (uint32_t)(item % wgroups);
         const size_t base = (size_t)(v - v_base) * stride;  // offset inside `data` (row v_base first)
         const size_t bit_base = (size_t)v * stride;          // bit index in the whole-matrix bitmap
-        uint32_t my_a = 0, my_c = 0;
+        uint32_t my_a[4] = {0, 0, 0, 0}, my_c = 0;
 #pragma unroll 4
         for (uint32_t i = 0; i < 32; ++i) {
             const uint32_t w = wg * 32 + i;
             if (w >= words) break;  // warp-uniform
             const uint32_t k = w * 32 + lane;
-            bool a = false, c = false;
+            uint32_t byte = 0;
+            bool c = false;
             if (k < n) {
                 const uint32_t o = off[k];
                 c = true;
@@ -65,18 +67,23 @@ fm_k_repack(const uint8_t *__restrict__ data, const uint64_t *__restrict__ missi
                     const size_t bit = bit_base + o;
                     c = !((missing[(bit >> 6) - word_base] >> (bit & 63)) & 1ull);
                 }
-                a = c && (data[base + o] != 0);
+                byte = c ? data[base + o] : 0u;
             }
-            const uint32_t wa = __ballot_sync(0xffffffffu, a);
             const uint32_t wc = __ballot_sync(0xffffffffu, c);
-            if (i == lane) {
-                my_a = wa;
-                my_c = wc;
+            if (n_bits == 1) {  // biallelic: any non-zero allele index is the alternate allele
+                const uint32_t wa = __ballot_sync(0xffffffffu, byte != 0);
+                if (i == lane) my_a[0] = wa;
+            } else {            // bit b of the allele index goes to plane b
+                for (uint32_t b = 0; b < n_bits; ++b) {
+                    const uint32_t wa = __ballot_sync(0xffffffffu, (byte >> b) & 1u);
+                    if (i == lane) my_a[b] = wa;
+                }
             }
+            if (i == lane) my_c = wc;
         }
         const uint32_t w = wg * 32 + lane;
         if (w < words) {
-            allele[(size_t)v * words + w] = my_a;
+            for (uint32_t b = 0; b < n_bits; ++b) allele[b * plane_stride_words + (size_t)v * words + w] = my_a[b];
             if (called) called[(size_t)v * words + w] = my_c;
         }
     }

@@ -444,3 +444,114 @@ def test_streaming_ingest_equals_resident_matrix(chunk_rows, calls, missing):
     # a streamed matrix has no resident u8 rows: late group creation must fail loudly
     with pytest.raises(NotImplementedError):
         streamed.group([(0, 0), (1, 1)])
+
+
+# ------------------------------------------------------------------ multi-allelic sites (general paths)
+def make_multi_cohort(V, S, max_allele, missing, seed):
+    rng = np.random.default_rng(seed)
+    A = max_allele + 1
+    w = rng.dirichlet(np.full(A, 0.6), size=V)                       # per-site allele frequencies
+    cdf = np.cumsum(w, axis=1)
+    u = rng.random((V, S, 2))
+    g = (u[..., None] > cdf[:, None, None, :]).sum(axis=3).clip(0, max_allele).astype(np.int8)
+    g[0] = 0                                                          # monomorphic
+    g[1, :, :] = np.arange(S * 2).reshape(S, 2) % A                   # every allele present
+    if missing > 0:
+        g[rng.random(g.shape) < missing] = -1
+    g[2] = -1                                                         # no data
+    g[3, 1:, :] = -1                                                  # a single called sample
+    g[4].flat[0] = max_allele                                         # make sure max_allele is reached
+    pos = np.cumsum(rng.integers(1, 40, size=V, dtype=np.int64))
+    return g, pos
+
+
+@pytest.mark.parametrize("max_allele,missing", [(2, 0.0), (3, 0.12), (7, 0.05), (15, 0.1)])
+def test_multi_allelic_dense_population_paths(max_allele, missing):
+    """Population.from_numpy with max_allele > 1: the reference builds no summary (lib.rs:779) and takes
+    count_segregating_sites_dense / calculate_pi_dense / dense_hudson_sites_general / calculate_dxy_dense."""
+    F = fm()
+    S = 22
+    g, pos = make_multi_cohort(700, S, max_allele, missing, seed=90 + max_allele)
+    L = int(pos[-1] - pos[0] + 1)
+    names = [f"s{i}" for i in range(S)]
+    h1 = both_sides(range(0, S // 2)) + [(S - 1, 0)]
+    h2 = both_sides(range(S // 2, S - 1)) + [(S - 1, 1), (S // 2, 0)]  # one duplicate
+    base = F.Population.from_numpy("all", g, pos, h1 + h2, L, sample_names=names)
+    p1, p2 = base.with_haplotypes("p1", h1), base.with_haplotypes("p2", h2)
+    vs, d = orc.from_numpy(g, pos)
+    assert d.max_allele == max_allele
+    o1 = orc.Pop(h1, vs, S, L, dense=d)
+    o2 = orc.Pop(h2, vs, S, L, dense=d)
+    assert p1.segregating_sites() == orc.count_segregating_sites_for_population(o1)
+    assert p2.segregating_sites() == orc.count_segregating_sites_for_population(o2)
+    assert close(p1.nucleotide_diversity(), orc.pi_for_population(o1))
+    assert close(p2.nucleotide_diversity(), orc.pi_for_population(o2))
+    rc, ref, _ = orc.hudson_pair(o1, o2)
+    got = F.hudson_fst(p1, p2)
+    assert rc == 0
+    for k in ("fst", "d_xy", "pi_pop1", "pi_pop2", "pi_xy_avg"):
+        assert close(getattr(got, k), ref[k]), k
+    assert close(F.hudson_dxy(p1, p2).d_xy, orc.dxy_hudson(o1, o2)[1])
+    # region => sparse per-site values + dense auxiliary pi / Dxy (stats.rs:3473-3475, 3562-3565)
+    region = (int(pos[5]), int(pos[-7]))
+    rc, ref, rsites = orc.hudson_pair(o1, o2, region=region)
+    out, sites = F.hudson_fst_with_sites(p1, p2, region)
+    assert rc == 0 and len(sites) == len(rsites)
+    for k in ("fst", "d_xy", "pi_pop1", "pi_pop2", "pi_xy_avg"):
+        assert close(getattr(out, k), ref[k]), k
+    for s, r in zip(sites, rsites):
+        assert s.position == r["position"] and s.n1_called == r["n1_called"] and s.n2_called == r["n2_called"]
+        for a in ("fst", "d_xy", "pi_pop1", "pi_pop2", "numerator_component", "denominator_component"):
+            assert close(getattr(s, a), r[a], 1e-12), (s.position, a)
+
+
+@pytest.mark.parametrize("max_allele", [2, 5])
+def test_multi_allelic_sparse_paths(max_allele):
+    """Variant-list inputs (no dense matrix): calculate_pi, per-site diversity, cohort segregating sites and
+    the sparse Hudson path on multi-allelic sites, incl. the reference's tri-allelic golden."""
+    F = fm()
+    S = 14
+    g, pos = make_multi_cohort(300, S, max_allele, 0.1, seed=5 + max_allele)
+    g[:, :, 1][g[:, :, 0] < 0] = -1
+    g[:, :, 0][g[:, :, 1] < 0] = -1
+    L = int(pos[-1] - pos[0] + 1)
+    variants = _to_python_variants(g, pos)
+    vs = orc.variants_from_python(variants, S)
+    haps = both_sides(range(0, 9)) + [(9, 0)]
+    assert F.segregating_sites(variants) == orc.count_segregating_sites(vs)
+    assert close(F.nucleotide_diversity(variants, haps, L), orc.pi_sparse(vs, haps, L))
+    region = (int(pos[2]), int(pos[-3]))
+    gp, gpi, gth = F.per_site_diversity_arrays(variants, haps, region, mask=[(int(pos[50]), int(pos[60]))])
+    rp, rpi, rth = orc.per_site_diversity(vs, haps, region, mask=[(int(pos[50]), int(pos[60]))])
+    assert np.array_equal(gp, rp)
+    assert_arrays_close(gpi, rpi, 1e-12)
+    assert_arrays_close(gth, rth, 1e-12)
+    names = [f"s{i}" for i in range(S)]
+    h1, h2 = both_sides(range(0, 7)), both_sides(range(7, S))
+    d1 = {"id": 0, "haplotypes": h1, "variants": variants, "sequence_length": L, "sample_names": names}
+    d2 = {"id": 1, "haplotypes": h2, "variants": variants, "sequence_length": L, "sample_names": names}
+    o1, o2 = orc.Pop(h1, vs, S, L), orc.Pop(h2, vs, S, L)
+    rc, ref, _ = orc.hudson_pair(o1, o2)
+    got = F.hudson_fst(d1, d2)
+    for k in ("fst", "d_xy", "pi_pop1", "pi_pop2"):
+        assert close(getattr(got, k), ref[k]), k
+    # tests/hudson_fst_tests.rs:877-1006
+    tri = [{"position": 100, "genotypes": [[0, 0], [1, 2], [0, 1], [2, 2]]}]
+    a = {"id": 0, "haplotypes": both_sides([0, 1]), "variants": tri, "sequence_length": 1, "sample_names": names[:4]}
+    b = {"id": 1, "haplotypes": both_sides([2, 3]), "variants": tri, "sequence_length": 1, "sample_names": names[:4]}
+    _, sites = F.hudson_fst_with_sites(a, b, (100, 100))
+    exp_pi = (4.0 / 3.0) * 0.625
+    assert abs(sites[0].d_xy - 0.6875) < 1e-12 and abs(sites[0].pi_pop1 - exp_pi) < 1e-12
+    assert abs(sites[0].fst - (0.6875 - exp_pi) / 0.6875) < 1e-12
+
+
+def test_multi_allelic_unsupported_corners_fail_loudly():
+    F = fm()
+    g, pos = make_multi_cohort(50, 6, 20, 0.0, seed=1)  # allele index 20 > 15
+    with pytest.raises(NotImplementedError):
+        F.Population.from_numpy("x", g, pos, both_sides(range(6)), 100).segregating_sites()
+    g, pos = make_multi_cohort(50, 6, 3, 0.0, seed=2)
+    variants = _to_python_variants(g, pos)
+    with pytest.raises(NotImplementedError):  # W&C over multi-allelic sites is not on the GPU path yet
+        F.wc_fst(variants, [f"s{i}" for i in range(6)], {f"s{i}": (i % 2, i % 2) for i in range(6)},
+                 (0, int(pos[-1])))
