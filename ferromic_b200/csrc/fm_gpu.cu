@@ -1332,8 +1332,6 @@ fm_status fm_ingest_add_partition(fm_ingest *h, const uint16_t *left, const uint
         if (!h) fail(FM_ERR_INVALID_ARG, "ingest handle is NULL");
         if (n_samples && (!left || !right)) fail(FM_ERR_INVALID_ARG, "membership arrays are NULL");
         if (n_groups >= 0xFFFF) fail(FM_ERR_INVALID_ARG, "too many groups");
-        if (h->m->max_allele > 1)
-            fail(FM_ERR_UNSUPPORTED, "Weir & Cockerham on multi-allelic matrices is not on the GPU path yet");
         if (h->rows_done) fail(FM_ERR_INVALID_ARG, "partitions must be declared before the first fm_ingest_rows");
         fm_partition *p = new fm_partition();
         p->m = h->m;
@@ -1639,8 +1637,6 @@ fm_status fm_partition_create(fm_matrix *m, const uint16_t *left, const uint16_t
         *out = nullptr;
         if (n_samples && (!left || !right)) fail(FM_ERR_INVALID_ARG, "membership arrays are NULL");
         if (n_groups >= 0xFFFF) fail(FM_ERR_INVALID_ARG, "too many groups");
-        if (m->max_allele > 1)
-            fail(FM_ERR_UNSUPPORTED, "Weir & Cockerham on multi-allelic matrices is not on the GPU path yet");
         require_device();
         fm_partition *p = new fm_partition();
         p->m = m;
@@ -1722,9 +1718,11 @@ void run_wc(fm_partition *p, const std::vector<uint32_t> &wlo, const std::vector
     if (n_seg == 0) return;
     for (fm_group *g : p->groups) ensure_counts(g);
     set_dev(m);
+    const bool multi = p->groups[0]->n_bits > 1;
+    const uint32_t A = multi ? 1u << p->groups[0]->n_bits : 2u;
     std::vector<const uint32_t *> h_alt(G + 1), h_cnt(G + 1);
     for (uint32_t g = 0; g <= G; ++g) {
-        h_alt[g] = p->groups[g]->d_alt;
+        h_alt[g] = multi ? p->groups[g]->d_acount : p->groups[g]->d_alt;
         h_cnt[g] = p->groups[g]->d_cnt;
     }
     DevBuf<const uint32_t *> d_alt(G + 1), d_cnt(G + 1);
@@ -1748,7 +1746,9 @@ void run_wc(fm_partition *p, const std::vector<uint32_t> &wlo, const std::vector
     d_wseg.upload(wseg.data(), nw + 1);
 
     fm::WcParams W{};
-    W.alt = d_alt.p;
+    W.alt = multi ? nullptr : d_alt.p;
+    W.acount = multi ? d_alt.p : nullptr;
+    W.A = A;
     W.cnt = d_cnt.p;
     W.G = G;
     W.n_pairs = n_pairs;
@@ -1783,7 +1783,7 @@ void run_wc(fm_partition *p, const std::vector<uint32_t> &wlo, const std::vector
     uint32_t n_pw = std::max(1u, std::min<uint32_t>(fm::kWcMaxPairWarps, (n_pairs + 31) / 32));
     const uint32_t kp_need = std::max(1u, (n_pairs + n_pw * 32 - 1) / (n_pw * 32));
     if (kp_need > fm::kWcMaxKP) fail(FM_ERR_UNSUPPORTED, "too many populations for the W&C kernel (pairs per lane)");
-    const size_t smem = fm::fm_wc_cta_smem(G);
+    const size_t smem = multi ? fm::fm_wc_multi_cta_smem(G, A) : fm::fm_wc_cta_smem(G);
     if (smem > 200 * 1024) fail(FM_ERR_UNSUPPORTED, "too many populations for the W&C kernel's staging");
     W.n_pair_warps = n_pw;
     const uint32_t threads = (n_pw + 1) * 32;
@@ -1794,7 +1794,12 @@ void run_wc(fm_partition *p, const std::vector<uint32_t> &wlo, const std::vector
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<blocks, threads, smem, stream()>>>(W);
     };
-    if (kp_need <= 1) launch(fm::fm_k_wc<1>);
+    if (multi) {
+        if (kp_need <= 1) launch(fm::fm_k_wc_multi<1>);
+        else if (kp_need <= 2) launch(fm::fm_k_wc_multi<2>);
+        else if (kp_need <= 4) launch(fm::fm_k_wc_multi<4>);
+        else launch(fm::fm_k_wc_multi<8>);
+    } else if (kp_need <= 1) launch(fm::fm_k_wc<1>);
     else if (kp_need <= 2) launch(fm::fm_k_wc<2>);
     else if (kp_need <= 4) launch(fm::fm_k_wc<4>);
     else launch(fm::fm_k_wc<8>);

@@ -40,6 +40,8 @@ constexpr uint32_t kWcMaxKP = 8;         // pairs per lane (template parameter K
 struct WcParams {
     const uint32_t *const *alt;  // [G + 1] device pointers, each [V]; index G = haplotypes with no group
     const uint32_t *const *cnt;  // [G + 1]
+    const uint32_t *const *acount;  // multi-allelic: [G + 1] pointers to per-allele counts [V][A] (else nullptr)
+    uint32_t A;                  // alleles per site slot (2 for biallelic, 2^NB for multi-allelic)
     uint32_t G, n_pairs;
     uint32_t n_pair_warps;            // pair warps per CTA (block = (n_pair_warps + 1) * 32 threads)
     const uint16_t *pair_i, *pair_j;  // [n_pairs], i < j in label order
@@ -261,6 +263,215 @@ fm_k_wc(const WcParams P) {
                                 }
                             }
                             acc_a[k] += pa;  // site order: stats.rs:2288-2289
+                            acc_b[k] += pb;
+                            acc_n[k] += 1;
+                        }
+                        if (P.pair_a) {
+                            const uint32_t p = warp * 32 + lane + (uint32_t)k * NW * 32;
+                            const size_t o = (size_t)(v0 + s - P.out_base) * NP + p;
+                            P.pair_a[o] = has ? pa : fm_nan();
+                            P.pair_b[o] = has ? pb : fm_nan();
+                        }
+                    }
+                }
+            }
+        }
+        if (overall_warp) {
+            if (lane == 0) {
+                P.part_overall[2 * (size_t)si] = sum_a;
+                P.part_overall[2 * (size_t)si + 1] = sum_b;
+                P.part_counts[si] = n_informative;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                if (!pvalid[k]) continue;
+                const uint32_t p = warp * 32 + lane + (uint32_t)k * NW * 32;
+                P.part_pair[((size_t)si * NP + p) * 2] = acc_a[k];
+                P.part_pair[((size_t)si * NP + p) * 2 + 1] = acc_b[k];
+                P.part_pair_n[(size_t)si * NP + p] = acc_n[k];
+            }
+        }
+    }
+}
+
+// Multi-allelic variant (max_allele 2..15): same decomposition, with the reference's loop over
+// every allele present at the site (stats.rs:1849-1859, 1939-1983) instead of the two alleles of
+// a biallelic site.  An allele that is absent from a pair, or fixed in it, contributes exactly
+// (+0, +0) and is skipped.
+__host__ __device__ inline size_t fm_wc_multi_cta_smem(uint32_t G, uint32_t A) {
+    // freq [32][G][A] f64 | cn [32][G+1] u32 | ca [32][G+1][A] u32 | info [32] u32
+    return (size_t)32 * G * A * 8 + (size_t)32 * (G + 1) * 4 + (size_t)32 * (G + 1) * A * 4 + 32 * 4 + 16;
+}
+
+template <int KP>
+__global__ void __launch_bounds__((kWcMaxPairWarps + 1) * 32, 1)
+fm_k_wc_multi(const WcParams P) {
+    extern __shared__ __align__(16) uint8_t wc_smem[];
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+    const uint32_t G = P.G, G1 = P.G + 1, NP = P.n_pairs, A = P.A;
+    const uint32_t NW = P.n_pair_warps;
+    double *freq = reinterpret_cast<double *>(wc_smem);                          // [32][G][A]
+    uint32_t *cn = reinterpret_cast<uint32_t *>(freq + (size_t)32 * G * A);      // [32][G1] called
+    uint32_t *ca = cn + (size_t)32 * G1;                                         // [32][G1][A] allele counts
+    uint32_t *info = ca + (size_t)32 * G1 * A;                                   // [32] mask of alleles present
+    const bool overall_warp = warp == NW;
+    uint32_t pi[KP], pj[KP];
+    bool pvalid[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        const uint32_t p = warp * 32 + lane + (uint32_t)k * NW * 32;
+        pvalid[k] = !overall_warp && p < NP;
+        pi[k] = pvalid[k] ? __ldg(P.pair_i + p) : 0u;
+        pj[k] = pvalid[k] ? __ldg(P.pair_j + p) : 0u;
+    }
+    for (uint32_t si = blockIdx.x; si < P.n_seg; si += gridDim.x) {
+        const uint32_t lo = P.seg_lo[si], hi = P.seg_hi[si];
+        double acc_a[KP], acc_b[KP];
+        uint32_t acc_n[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            acc_a[k] = 0.0;
+            acc_b[k] = 0.0;
+            acc_n[k] = 0;
+        }
+        double sum_a = 0.0, sum_b = 0.0;
+        uint32_t n_informative = 0;
+        for (uint32_t v0 = lo; v0 < hi; v0 += 32) {
+            const uint32_t nb = min(32u, hi - v0);
+            __syncthreads();
+            for (uint32_t g = warp; g < G1; g += (nt >> 5))
+                if (lane < nb) {
+                    cn[lane * G1 + g] = __ldg(P.cnt[g] + v0 + lane);
+                    const uint32_t *src = P.acount[g] + (size_t)(v0 + lane) * A;
+                    for (uint32_t a = 0; a < A; ++a) ca[(lane * G1 + g) * A + a] = __ldg(src + a);
+                }
+            __syncthreads();
+            for (uint32_t i = tid; i < nb * G * A; i += nt) {
+                const uint32_t s = i / (G * A), r = i - s * G * A, g = r / A, a = r - g * A;
+                const uint32_t n = cn[s * G1 + g];
+                if (n > 0) freq[(s * G + g) * A + a] = (double)ca[(s * G1 + g) * A + a] / (double)n;
+            }
+            if (warp == 0 && lane < nb) {  // alleles present over ALL samples (stats.rs:1826-1837)
+                uint32_t mask = 0;
+                for (uint32_t a = 0; a < A; ++a) {
+                    uint32_t t = 0;
+                    for (uint32_t g = 0; g < G1; ++g) t += ca[(lane * G1 + g) * A + a];
+                    if (t) mask |= 1u << a;
+                }
+                info[lane] = mask;
+            }
+            __syncthreads();
+            if (overall_warp) {
+                double site_a = 0.0, site_b = 0.0;
+                int state = 3;
+                bool any = false;
+                if (lane < nb) {
+                    const uint32_t *sn = cn + lane * G1;
+                    const uint32_t *sa = ca + (size_t)lane * G1 * A;
+                    const double *fr = freq + (size_t)lane * G * A;
+                    const uint32_t present = info[lane];
+                    any = present != 0;
+                    uint32_t m_n = 0, m_r = 0;
+                    for (uint32_t g = 0; g < G; ++g)
+                        if (sn[g] > 0) {
+                            m_n += sn[g];
+                            m_r += 1;
+                        }
+                    if (any && m_r >= 2) {
+                        const double r = (double)m_r;
+                        const double n_bar = (double)m_n / r;
+                        if (!((n_bar - 1.0) < 1e-9)) {
+                            double ssd = 0.0;
+                            for (uint32_t g = 0; g < G; ++g)
+                                if (sn[g] > 0) {
+                                    const double d = (double)sn[g] - n_bar;
+                                    ssd += d * d;
+                                }
+                            const double c_squared = ssd / (r * n_bar * n_bar);
+                            const double a_den = 1.0 - (c_squared / (r - 1.0));
+                            const double nb_ratio = n_bar / (n_bar - 1.0);
+                            const bool s_ok = (r - 1.0) > 1e-9 && n_bar > 1e-9;
+                            for (uint32_t a = 0; a < A; ++a) {  // ascending allele order (stats.rs:1859)
+                                if (!((present >> a) & 1u)) continue;
+                                uint32_t m_t = 0;
+                                for (uint32_t g = 0; g < G; ++g)
+                                    if (sn[g] > 0) m_t += sa[g * A + a];
+                                const double gp = (double)m_t / (double)m_n;
+                                double ns = 0.0;
+                                for (uint32_t g = 0; g < G; ++g)
+                                    if (sn[g] > 0) {
+                                        const double q = fr[g * A + a] - gp;
+                                        ns += (double)sn[g] * q * q;
+                                    }
+                                const double s2 = s_ok ? ns / ((r - 1.0) * n_bar) : 0.0;
+                                const double x = gp * (1.0 - gp) - ((r - 1.0) / r) * s2;
+                                site_a += (s2 - (x / (n_bar - 1.0))) / a_den;
+                                site_b += nb_ratio * x;
+                            }
+                        }
+                    }
+                    if (any) state = fm_fst_state(site_a, site_b);
+                    const uint32_t o = v0 + lane - P.out_base;
+                    if (P.site_state) P.site_state[o] = state;
+                    if (P.site_a) P.site_a[o] = site_a;
+                    if (P.site_b) P.site_b[o] = site_b;
+                    if (P.site_sizes)
+                        for (uint32_t g = 0; g < G; ++g) P.site_sizes[(size_t)o * G + g] = any ? sn[g] : 0u;
+                }
+                const uint32_t any_mask = __ballot_sync(0xffffffffu, any);
+                for (uint32_t s = 0; s < nb; ++s) {
+                    const double a_s = __shfl_sync(0xffffffffu, site_a, s);
+                    const double b_s = __shfl_sync(0xffffffffu, site_b, s);
+                    if ((any_mask >> s) & 1u) {
+                        sum_a += a_s;
+                        sum_b += b_s;
+                        ++n_informative;
+                    }
+                }
+            } else {
+                for (uint32_t s = 0; s < nb; ++s) {
+                    const uint32_t *sn = cn + s * G1;
+                    const uint32_t *sa = ca + (size_t)s * G1 * A;
+                    const double *fr = freq + (size_t)s * G * A;
+                    const uint32_t present = info[s];
+                    const bool any = present != 0;
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) {
+                        if (!pvalid[k]) continue;
+                        const uint32_t i = pi[k], j = pj[k];
+                        const uint32_t ni = sn[i], nj = sn[j];
+                        double pa = 0.0, pb = 0.0;
+                        const bool has = any && ni > 0 && nj > 0;
+                        if (has) {
+                            const uint32_t nsum = ni + nj;
+                            const double n1 = (double)ni, n2 = (double)nj, nsd = (double)nsum;
+                            const double n_bar = nsd / 2.0;
+                            if (!((n_bar - 1.0) < 1e-9)) {
+                                const double d1 = n1 - n_bar, d2 = n2 - n_bar;
+                                double ssd = 0.0;
+                                ssd += d1 * d1;
+                                ssd += d2 * d2;
+                                const double c_squared = ssd / (2.0 * n_bar * n_bar);
+                                const double a_den = 1.0 - (c_squared / 1.0);
+                                const double nb_ratio = n_bar / (n_bar - 1.0);
+                                for (uint32_t a = 0; a < A; ++a) {
+                                    if (!((present >> a) & 1u)) continue;
+                                    const uint32_t asum = sa[i * A + a] + sa[j * A + a];
+                                    if (asum == 0 || asum == nsum) continue;  // exactly (+0, +0)
+                                    const double gp = (double)asum / nsd;
+                                    const double q1 = fr[i * A + a] - gp, q2 = fr[j * A + a] - gp;
+                                    double num = 0.0;
+                                    num += n1 * q1 * q1;
+                                    num += n2 * q2 * q2;
+                                    const double s2 = num / (1.0 * n_bar);
+                                    const double x = gp * (1.0 - gp) - (1.0 / 2.0) * s2;
+                                    pa += (s2 - (x / (n_bar - 1.0))) / a_den;
+                                    pb += nb_ratio * x;
+                                }
+                            }
+                            acc_a[k] += pa;
                             acc_b[k] += pb;
                             acc_n[k] += 1;
                         }

@@ -550,8 +550,23 @@ def test_multi_allelic_unsupported_corners_fail_loudly():
     g, pos = make_multi_cohort(50, 6, 20, 0.0, seed=1)  # allele index 20 > 15
     with pytest.raises(NotImplementedError):
         F.Population.from_numpy("x", g, pos, both_sides(range(6)), 100).segregating_sites()
-    g, pos = make_multi_cohort(50, 6, 3, 0.0, seed=2)
-    variants = _to_python_variants(g, pos)
-    with pytest.raises(NotImplementedError):  # W&C over multi-allelic sites is not on the GPU path yet
-        F.wc_fst(variants, [f"s{i}" for i in range(6)], {f"s{i}": (i % 2, i % 2) for i in range(6)},
-                 (0, int(pos[-1])))
+
+
+@pytest.mark.parametrize("max_allele,n_pops", [(2, 2), (3, 4), (9, 3)])
+def test_wc_fst_multi_allelic_matches_oracle(max_allele, n_pops):
+    """W&C sums over EVERY allele present at a site (stats.rs:1849-1859): multi-allelic K4 variant."""
+    F = fm()
+    S = 36
+    g, pos = make_multi_cohort(500, S, max_allele, 0.08, seed=31 + max_allele)
+    g[:, :, 1][g[:, :, 0] < 0] = -1
+    g[:, :, 0][g[:, :, 1] < 0] = -1
+    bounds = np.linspace(0, S, n_pops + 1).astype(int)
+    left = np.full(S, 0xFFFF, dtype=np.uint16)
+    for p in range(n_pops):
+        left[bounds[p]:bounds[p + 1]] = p
+    right = left.copy()
+    left[3] = 0xFFFF                      # a haplotype without a group still defines "alleles present"
+    right[5] = (right[5] + 1) % n_pops
+    labels = sorted(str(i) for i in range(n_pops))
+    vs, _ = orc.from_numpy(g, pos)
+    _wc_compare(F, _to_python_variants(g, pos), vs, left, right, labels, (int(pos[1]), int(pos[-2])))
