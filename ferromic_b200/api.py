@@ -290,15 +290,19 @@ def _dense_from_variants(vs: _Variants, sample_count: int):
     if vs.n_variants == 0:
         return None
     valid = np.logical_and.accumulate(vs.gt != MISSING, axis=2)
-    ploidy = int(valid.sum(axis=2).max()) if valid.size else 0
-    if ploidy == 0:
+    found = int(valid.sum(axis=2).max()) if valid.size else 0
+    if found == 0:
         return None
+    # The sparse paths test membership with HapMembership (Left / Right per sample, stats.rs:1211-1238),
+    # which counts a Right haplotype even when every genotype is haploid; keep two sides so that the
+    # group capacity equals HapMembership::total and the absent side is simply missing.
+    ploidy = max(found, 2)
     V, S = vs.n_variants, vs.n_samples
     alle = np.zeros((V, sample_count, ploidy), dtype=np.uint8)
     miss = np.ones((V, sample_count, ploidy), dtype=bool)
     k = min(S, sample_count)
-    alle[:, :k, :] = np.where(valid[:, :k, :ploidy], vs.gt[:, :k, :ploidy], 0)
-    miss[:, :k, :] = ~valid[:, :k, :ploidy]
+    alle[:, :k, :found] = np.where(valid[:, :k, :found], vs.gt[:, :k, :found], 0)
+    miss[:, :k, :found] = ~valid[:, :k, :found]
     return alle, miss
 
 
@@ -309,9 +313,9 @@ def _sparse_matrix(vs: _Variants, sample_count: Optional[int] = None) -> Optiona
     if m is None:
         d = _dense_from_variants(vs, sc)
         if d is None:
-            # no genotype data at all: a 1-ploid all-missing matrix keeps every count at zero
-            alle = np.zeros((vs.n_variants, sc, 1), dtype=np.uint8)
-            miss = np.ones((vs.n_variants, sc, 1), dtype=bool)
+            # no genotype data at all: an all-missing two-sided matrix keeps every count at zero
+            alle = np.zeros((vs.n_variants, sc, 2), dtype=np.uint8)
+            miss = np.ones((vs.n_variants, sc, 2), dtype=bool)
             d = (alle, miss)
         m = _Matrix(d[0], d[1], vs.positions, always_bitmap=True)
         vs._dense_cache[sc] = m
