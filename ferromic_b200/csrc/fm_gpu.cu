@@ -963,21 +963,92 @@ static fm_group *alloc_group(fm_matrix *m, std::vector<uint32_t> &&off) {
     return g;
 }
 
-// K1 for rows [v_lo, v_hi) of a group: `data` / `missing` point at the u8 row v_base and at the
-// bitmap word word_base (resident matrix: v_base = word_base = 0; streaming ingest: the staged chunk).
-static void launch_repack(const fm_group *g, const uint8_t *data, const uint64_t *missing, uint32_t v_base,
-                          uint64_t word_base, uint32_t v_lo, uint32_t v_hi, cudaStream_t st) {
-    const fm_matrix *m = g->m;
-    if (v_hi <= v_lo) return;
-    const uint32_t blocks = (uint32_t)std::min<uint64_t>(
-        (uint64_t)sm_count(m->device) * 8,
-        std::max<uint64_t>(1, ((uint64_t)(v_hi - v_lo) * ((g->wq * 4 + 31) / 32) + 7) / 8));
-    fm::fm_k_repack<<<blocks, 256, 0, st>>>(data, missing, m->stride, g->d_off, g->n, g->wq, v_base, word_base,
-                                            v_lo, v_hi, reinterpret_cast<uint32_t *>(g->d_allele),
-                                            reinterpret_cast<uint32_t *>(g->d_called), g->n_bits,
-                                            std::max<size_t>(m->V, 1) * g->wq * 4);
-    CK(cudaGetLastError());
-    g_launches++;
+// K1 for rows [v_lo, v_hi) of a set of groups of one matrix: `data` / `missing` point at the u8 row
+// v_base and at the bitmap word word_base (resident matrix: v_base = word_base = 0; streaming
+// ingest: the staged chunk).  Rows that fit a warp's shared-memory slice take the row-staged
+// multi-group kernel (the u8 matrix is read once for all groups); wider rows (biobank cohorts)
+// fall back to the per-group gather kernel.
+struct RepackSet {  // device-resident descriptor table of the groups one launch repacks
+    std::vector<fm_group *> gs;
+    fm::RepackGroup *d_desc = nullptr;
+    void build(const std::vector<fm_group *> &groups) {
+        gs = groups;
+        if (gs.empty()) return;
+        const fm_matrix *m = gs[0]->m;
+        std::vector<fm::RepackGroup> h(gs.size());
+        for (size_t i = 0; i < gs.size(); ++i) {
+            const fm_group *g = gs[i];
+            h[i] = fm::RepackGroup{g->d_off, g->n, g->wq, g->n_bits, reinterpret_cast<uint32_t *>(g->d_allele),
+                                   reinterpret_cast<uint32_t *>(g->d_called), std::max<size_t>(m->V, 1) * g->wq * 4};
+        }
+        d_desc = static_cast<fm::RepackGroup *>(dev_alloc(h.size() * sizeof(fm::RepackGroup)));
+        CK(cudaMemcpyAsync(d_desc, h.data(), h.size() * sizeof(fm::RepackGroup), cudaMemcpyHostToDevice, stream()));
+        CK(cudaStreamSynchronize(stream()));
+    }
+    void release() {
+        dev_free(d_desc);
+        d_desc = nullptr;
+        gs.clear();
+    }
+};
+
+static void launch_repack(const RepackSet &set, const uint8_t *data, size_t data_bytes, const uint64_t *missing,
+                          uint32_t v_base, uint64_t word_base, uint32_t v_lo, uint32_t v_hi, cudaStream_t st) {
+    const std::vector<fm_group *> &gs = set.gs;
+    if (gs.empty() || v_hi <= v_lo) return;
+    const fm_matrix *m = gs[0]->m;
+    const size_t stride = m->stride;
+    const uint32_t row_buf = (uint32_t)(((stride + 15) & ~(size_t)15) + 16);
+    const uint32_t bit_buf = missing ? (uint32_t)(((stride + 63) / 64 + 2) * 8) : 0u;
+    const uint32_t warp_smem = (row_buf + bit_buf + 15u) & ~15u;
+    static const uint32_t force_v1 = env_u32("FM_REPACK_V1", 0);
+    if (warp_smem <= 24 * 1024 && !force_v1) {
+        const uint32_t warps = std::max(1u, std::min(8u, (200u * 1024u) / warp_smem));
+        const size_t smem = (size_t)warps * warp_smem;
+        static std::once_flag attr_once;
+        std::call_once(attr_once, [] {
+            cudaFuncSetAttribute(fm::fm_k_repack_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        });
+        const uint32_t rows = v_hi - v_lo;
+        const uint32_t per_sm = std::max(1u, std::min(8u, (uint32_t)((220u * 1024u) / smem)));
+        const uint32_t blocks = std::max(1u, std::min<uint32_t>((rows + warps - 1) / warps,
+                                                                per_sm * (uint32_t)sm_count(m->device)));
+        fm::fm_k_repack_rows<<<blocks, warps * 32, smem, st>>>(data, data_bytes, missing, stride, v_base, word_base, v_lo,
+                                                               v_hi, set.d_desc, (uint32_t)gs.size(), warp_smem, row_buf);
+        CK(cudaGetLastError());
+        g_launches++;
+        return;
+    }
+    for (const fm_group *g : gs) {
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>(
+            (uint64_t)sm_count(m->device) * 8,
+            std::max<uint64_t>(1, ((uint64_t)(v_hi - v_lo) * ((g->wq * 4 + 31) / 32) + 7) / 8));
+        fm::fm_k_repack<<<blocks, 256, 0, st>>>(data, missing, m->stride, g->d_off, g->n, g->wq, v_base, word_base, v_lo,
+                                                v_hi, reinterpret_cast<uint32_t *>(g->d_allele),
+                                                reinterpret_cast<uint32_t *>(g->d_called), g->n_bits,
+                                                std::max<size_t>(m->V, 1) * g->wq * 4);
+        CK(cudaGetLastError());
+        g_launches++;
+    }
+}
+
+// Repack the resident matrix into freshly allocated groups (one pass over the u8 rows for all).
+static void repack_resident(fm_matrix *m, const std::vector<fm_group *> &gs) {
+    if (!m->V || gs.empty()) return;
+    RepackSet set;
+    set.build(gs);
+    Timer tm;
+    tm.start();
+    try {
+        launch_repack(set, m->d_data, m->V * m->stride, m->d_missing, 0, 0, 0, (uint32_t)m->V, stream());
+        tm.stop();
+        t_tim.repack_ms += tm.ms();
+        CK(cudaStreamSynchronize(stream()));
+    } catch (...) {
+        set.release();
+        throw;
+    }
+    set.release();
 }
 
 // Repack the resident matrix columns listed in `off` into a new group's bitplanes.
@@ -988,14 +1059,7 @@ static fm_group *make_group(fm_matrix *m, std::vector<uint32_t> &&off) {
              "with fm_ingest_add_group / fm_ingest_add_partition before fm_ingest_rows");
     fm_group *g = alloc_group(m, std::move(off));
     try {
-        if (m->V) {
-            Timer tm;
-            tm.start();
-            launch_repack(g, m->d_data, m->d_missing, 0, 0, 0, (uint32_t)m->V, stream());
-            tm.stop();
-            t_tim.repack_ms += tm.ms();
-        }
-        CK(cudaStreamSynchronize(stream()));
+        repack_resident(m, {g});
     } catch (...) {
         fm_group_release(g);
         throw;
@@ -1247,6 +1311,7 @@ struct fm_ingest {
     cudaEvent_t t_copy0 = nullptr, t_copy1 = nullptr, t_comp0 = nullptr, t_comp1 = nullptr;
     bool used[2] = {false, false};
     bool timing_started = false;
+    RepackSet set;                        // descriptor table of `all`, built at the first fm_ingest_rows
     int next = 0;
 };
 
@@ -1255,6 +1320,7 @@ static void ingest_destroy(fm_ingest *h, bool release_handles) {
     if (h->m) cudaSetDevice(h->m->device);
     if (h->copy_s) cudaStreamSynchronize(h->copy_s);
     if (h->comp_s) cudaStreamSynchronize(h->comp_s);
+    h->set.release();
     for (int i = 0; i < 2; ++i) {
         dev_free(h->stage[i]);
         dev_free(h->stage_m[i]);
@@ -1360,6 +1426,7 @@ fm_status fm_ingest_rows(fm_ingest *h, const uint8_t *rows, const uint64_t *miss
         if (m->has_missing && !missing_whole) fail(FM_ERR_INVALID_ARG, "matrix was declared with a missing bitmap");
         set_dev(m);
         const size_t stride = m->stride;
+        if (!h->set.d_desc && !h->all.empty()) h->set.build(h->all);  // groups are final from here on
         if (!h->timing_started && n_rows) {
             CK(cudaEventRecord(h->t_copy0, h->copy_s));
             CK(cudaEventRecord(h->t_comp0, h->comp_s));
@@ -1382,9 +1449,8 @@ fm_status fm_ingest_rows(fm_ingest *h, const uint8_t *rows, const uint64_t *miss
             }
             CK(cudaEventRecord(h->copied[b], h->copy_s));
             CK(cudaStreamWaitEvent(h->comp_s, h->copied[b], 0));
-            for (fm_group *g : h->all)
-                launch_repack(g, h->stage[b], m->has_missing ? h->stage_m[b] : nullptr, (uint32_t)r0, w0,
-                              (uint32_t)r0, (uint32_t)r1, h->comp_s);
+            launch_repack(h->set, h->stage[b], (r1 - r0) * stride, m->has_missing ? h->stage_m[b] : nullptr,
+                          (uint32_t)r0, w0, (uint32_t)r0, (uint32_t)r1, h->comp_s);
             CK(cudaEventRecord(h->consumed[b], h->comp_s));
             h->used[b] = true;
         }
@@ -1643,8 +1709,12 @@ fm_status fm_partition_create(fm_matrix *m, const uint16_t *left, const uint16_t
         p->G = n_groups;
         fm_matrix_retain(m);
         try {
+            if (m->streamed)
+                fail(FM_ERR_UNSUPPORTED,
+                     "this matrix was ingested in streaming mode: declare partitions with fm_ingest_add_partition");
             std::vector<std::vector<uint32_t>> cols = partition_columns(m, left, right, n_samples, n_groups);
-            for (size_t g = 0; g <= n_groups; ++g) p->groups.push_back(make_group(m, std::move(cols[g])));
+            for (size_t g = 0; g <= n_groups; ++g) p->groups.push_back(alloc_group(m, std::move(cols[g])));
+            repack_resident(m, p->groups);  // the u8 matrix is read once for all G + 1 groups
         } catch (...) {
             fm_partition_release(p);
             throw;

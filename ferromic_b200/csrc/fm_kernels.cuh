@@ -74,17 +74,123 @@ fm_k_repack(const uint8_t *__restrict__ data, const uint64_t *__restrict__ missi
                 const uint32_t wa = __ballot_sync(0xffffffffu, byte != 0);
                 if (i == lane) my_a[0] = wa;
             } else {            // bit b of the allele index goes to plane b
-                for (uint32_t b = 0; b < n_bits; ++b) {
-                    const uint32_t wa = __ballot_sync(0xffffffffu, (byte >> b) & 1u);
-                    if (i == lane) my_a[b] = wa;
+#pragma unroll
+                for (uint32_t b = 0; b < 4; ++b) {  // compile-time indices keep my_a in registers
+                    if (b < n_bits) {
+                        const uint32_t wa = __ballot_sync(0xffffffffu, (byte >> b) & 1u);
+                        if (i == lane) my_a[b] = wa;
+                    }
                 }
             }
             if (i == lane) my_c = wc;
         }
         const uint32_t w = wg * 32 + lane;
         if (w < words) {
-            for (uint32_t b = 0; b < n_bits; ++b) allele[b * plane_stride_words + (size_t)v * words + w] = my_a[b];
+#pragma unroll
+            for (uint32_t b = 0; b < 4; ++b)
+                if (b < n_bits) allele[b * plane_stride_words + (size_t)v * words + w] = my_a[b];
             if (called) called[(size_t)v * words + w] = my_c;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ K1 v2 repack
+// Row-staged, multi-group repack: one warp owns one matrix row at a time.  It pulls the row's
+// u8 cells (128-bit loads) and the row's slice of the missing bitmap into its shared-memory
+// slice once, then builds the bitplane words of EVERY listed group from shared memory with
+// __ballot_sync -- the u8 matrix is read exactly once however many groups (a 27-group W&C
+// partition, the two orientation groups of a per-site call) are repacked, and the per-lane byte
+// gathers hit shared memory instead of paying an L2 round trip each (K1 v1 ran at ~0.4 TB/s).
+struct RepackGroup {
+    const uint32_t *off;       // sorted, de-duplicated column offsets (DenseMembership, stats.rs:1251-1284)
+    uint32_t n, wq, n_bits;
+    uint32_t *allele, *called; // called == nullptr when the matrix has no bitmap
+    size_t plane_stride_words; // distance between allele bit planes (multi-allelic groups)
+};
+
+__global__ void __launch_bounds__(256)
+fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint64_t *__restrict__ missing,
+                 size_t stride, uint32_t v_base, uint64_t word_base, uint32_t v_lo, uint32_t v_hi,
+                 const RepackGroup *__restrict__ groups, uint32_t n_groups, uint32_t warp_smem_bytes,
+                 uint32_t row_buf_bytes) {
+    extern __shared__ __align__(16) uint8_t rp_smem[];
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *rowb = rp_smem + (size_t)warp * warp_smem_bytes;                       // staged row bytes
+    uint64_t *bits = reinterpret_cast<uint64_t *>(rowb + row_buf_bytes);             // staged bitmap words
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t GW = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t v = v_lo + gw; v < v_hi; v += GW) {
+        // ---- stage the row: aligned 16-byte loads over [a0, a1) covering [row0, row0 + stride)
+        const size_t row0 = (size_t)(v - v_base) * stride;
+        const size_t a0 = row0 & ~(size_t)15;
+        const uint32_t delta = (uint32_t)(row0 - a0);
+        const size_t a1 = (row0 + stride + 15) & ~(size_t)15;
+        const uint32_t nq = (uint32_t)((a1 - a0) >> 4);
+        __syncwarp();
+        for (uint32_t q = lane; q < nq; q += 32) {
+            const size_t at = a0 + ((size_t)q << 4);
+            uint4 x;
+            if (at + 16 <= data_bytes) {
+                x = *reinterpret_cast<const uint4 *>(data + at);
+            } else {  // last bytes of the buffer: never read past its end
+                uint32_t w[4] = {0, 0, 0, 0};
+                for (uint32_t b = 0; b < 16 && at + b < data_bytes; ++b) w[b >> 2] |= (uint32_t)data[at + b] << ((b & 3) * 8);
+                x = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            *reinterpret_cast<uint4 *>(rowb + ((size_t)q << 4)) = x;
+        }
+        const size_t bit0 = (size_t)v * stride;
+        const uint64_t w0 = bit0 >> 6;
+        if (missing) {
+            const uint32_t nw = (uint32_t)(((bit0 + stride + 63) >> 6) - w0);
+            for (uint32_t q = lane; q < nw; q += 32) bits[q] = missing[w0 - word_base + q];
+        }
+        __syncwarp();
+        // ---- every group's words from the staged row
+        for (uint32_t gi = 0; gi < n_groups; ++gi) {
+            const RepackGroup G = groups[gi];
+            const uint32_t words = G.wq * 4;
+            for (uint32_t wb = 0; wb < words; wb += 32) {
+                uint32_t my_a[4] = {0, 0, 0, 0}, my_c = 0;
+                const uint32_t lim = min(32u, words - wb);
+#pragma unroll 4
+                for (uint32_t i = 0; i < lim; ++i) {
+                    const uint32_t k = (wb + i) * 32 + lane;
+                    uint32_t byte = 0;
+                    bool c = false;
+                    if (k < G.n) {
+                        const uint32_t o = __ldg(G.off + k);
+                        c = true;
+                        if (missing) {
+                            const size_t bit = bit0 + o;
+                            c = !((bits[(bit >> 6) - w0] >> (bit & 63)) & 1ull);
+                        }
+                        byte = c ? rowb[delta + o] : 0u;
+                    }
+                    const uint32_t wc = __ballot_sync(FULL, c);
+                    if (G.n_bits == 1) {
+                        const uint32_t wa = __ballot_sync(FULL, byte != 0);
+                        if (i == lane) my_a[0] = wa;
+                    } else {
+#pragma unroll
+                        for (uint32_t b = 0; b < 4; ++b) {  // compile-time indices keep my_a in registers
+                            if (b < G.n_bits) {
+                                const uint32_t wa = __ballot_sync(FULL, (byte >> b) & 1u);
+                                if (i == lane) my_a[b] = wa;
+                            }
+                        }
+                    }
+                    if (i == lane) my_c = wc;
+                }
+                if (lane < lim) {
+                    const size_t o = (size_t)v * words + wb + lane;
+#pragma unroll
+                    for (uint32_t b = 0; b < 4; ++b)
+                        if (b < G.n_bits) G.allele[b * G.plane_stride_words + o] = my_a[b];
+                    if (G.called) G.called[o] = my_c;
+                }
+            }
         }
     }
 }
