@@ -479,9 +479,10 @@ fm::GroupPlanes planes_of(const fm_group *g) {
 // K5a: mask / filtered-position bit per site, one word per batch
 void launch_site_flags(const fm_matrix *m, uint32_t v_lo, uint32_t v_hi, uint32_t b_lo, uint32_t n_batches,
                        const int64_t *d_mask, uint32_t n_mask, const int64_t *d_filt, uint32_t n_filt,
-                       uint32_t *d_flags) {
+                       uint32_t *d_flags, cudaStream_t st = nullptr) {
+    if (!st) st = stream();
     const uint32_t fb = std::max(1u, std::min<uint32_t>((n_batches + 7) / 8, 8u * (uint32_t)sm_count(m->device)));
-    fm::fm_k_site_flags<<<fb, 256, 0, stream()>>>(m->d_pos, v_lo, v_hi, b_lo, n_batches, d_mask, n_mask, d_filt,
+    fm::fm_k_site_flags<<<fb, 256, 0, st>>>(m->d_pos, v_lo, v_hi, b_lo, n_batches, d_mask, n_mask, d_filt,
                                                    n_filt, d_flags);
     CK(cudaGetLastError());
     g_launches++;
@@ -2393,11 +2394,12 @@ struct EventPairs {
 };
 
 void launch_reduce(const double *pd, int nd, const uint32_t *pu, int nu, const fm::PassGeom &G, double *sd,
-                   uint64_t *su) {
+                   uint64_t *su, cudaStream_t st = nullptr) {
+    if (!st) st = stream();
     const uint32_t s_lo = G.b_lo / fm::kSuperBatches;
     const uint32_t n_super = (G.b_lo + G.n_batches + fm::kSuperBatches - 1) / fm::kSuperBatches - s_lo;
-    fm::fm_k_reduce_partials<<<(n_super + 3) / 4, 128, 0, stream()>>>(pd, nd, pu, nu, G.b_lo, G.n_batches,
-                                                                       s_lo, n_super, sd, su);
+    fm::fm_k_reduce_partials<<<(n_super + 3) / 4, 128, 0, st>>>(pd, nd, pu, nu, G.b_lo, G.n_batches,
+                                                                 s_lo, n_super, sd, su);
     CK(cudaGetLastError());
     g_launches++;
 }
@@ -2420,7 +2422,7 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
         };
         std::vector<PerGroup> pg(n_groups);
         DevBuf<int64_t> d_mask;
-        DevBuf<uint32_t> d_flags;
+        DevBuf<uint32_t> d_flags, d_flags2;  // double-buffered by step parity
         std::vector<int64_t> merged;
         const uint32_t nb_all = V ? (V + 31) / 32 : 0;
         if (mode == 1 && mask_iv) {
@@ -2428,6 +2430,7 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
             d_mask.alloc(std::max<size_t>(merged.size(), 2));
             d_mask.upload(merged.data(), merged.size());
             d_flags.alloc(std::max<uint32_t>(nb_all, 1));
+            d_flags2.alloc(std::max<uint32_t>(nb_all, 1));
         }
         uint64_t bytes = 0;
         for (size_t i = 0; i < n_groups; ++i) {
@@ -2466,37 +2469,64 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
         EventPairs evs;
         std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans, comm_spans;
         cudaEvent_t t0 = evs.next(), t1 = evs.next();
-        // The exchange runs on its own stream: the step's kernels never wait for a peer, and the
-        // one-CTA exchange kernel of step i hides under the plane passes of step i+1.
+        // Two streams: the plane passes run back to back on the main stream; everything small --
+        // the mask lookup of the NEXT step, the partial reductions and the peer exchange of THIS
+        // step -- runs on a side stream underneath them (partials / flags are double-buffered by
+        // step parity).  The step's kernels never wait for a peer.
         struct SideStream {
             cudaStream_t s = nullptr;
             ~SideStream() {
                 if (s) cudaStreamDestroy(s);
             }
         } side;
-        std::vector<cudaEvent_t> exchanged;  // exchange of step i finished reading buffer i & 1
-        if (comm) CK(cudaStreamCreateWithFlags(&side.s, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&side.s, cudaStreamNonBlocking));
+        const bool use_flags = mode == 1 && mask_iv && nb_all;
+        uint32_t *flagbuf[2] = {d_flags.p, d_flags2.p};
+        std::vector<cudaEvent_t> flags_ready(iterations, nullptr), side_done(iterations, nullptr);
+        std::vector<cudaEvent_t> reduced(n_groups, nullptr);  // last reduction of group i's per-batch partials
+        auto ev = [&]() {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            evs.ev.push_back(e);
+            return e;
+        };
+        auto launch_flags = [&](int it) {  // on the side stream, into buffer it & 1
+            launch_site_flags(m, 0, V, 0, nb_all, d_mask.p, (uint32_t)(merged.size() / 2), nullptr, 0, flagbuf[it & 1],
+                              side.s);
+            flags_ready[it] = ev();
+            CK(cudaEventRecord(flags_ready[it], side.s));
+            out->other_launches++;
+        };
         CK(cudaStreamSynchronize(stream()));
         CK(cudaEventRecord(t0, stream()));
+        if (use_flags) {
+            CK(cudaStreamWaitEvent(side.s, t0, 0));
+            launch_flags(0);
+        }
         for (int it = 0; it < iterations; ++it) {
             const int pb = it & 1;
-            if (comm && it >= 2) CK(cudaStreamWaitEvent(stream(), exchanged[it - 2], 0));
-            if (mode == 1 && mask_iv && nb_all) {  // the mask lookup is part of every step
-                launch_site_flags(m, 0, V, 0, nb_all, d_mask.p, (uint32_t)(merged.size() / 2), nullptr, 0,
-                                  d_flags.p);
-                out->other_launches++;
-            }
+            // buffers of parity pb were last read by the side work of step it - 2
+            if (it >= 2) CK(cudaStreamWaitEvent(stream(), side_done[it - 2], 0));
+            if (use_flags) CK(cudaStreamWaitEvent(stream(), flags_ready[it], 0));
             for (size_t i = 0; i < n_groups; ++i) {
+                if (use_flags) pg[i].P.div.site_flags = flagbuf[pb];
+                if (reduced[i]) CK(cudaStreamWaitEvent(stream(), reduced[i], 0));  // its per-batch partials are reused
                 cudaEvent_t a = evs.next(), b = evs.next();
                 CK(cudaEventRecord(a, stream()));
                 launch_plane_pass<1>(pg[i].P, m->device);
                 CK(cudaEventRecord(b, stream()));
                 spans.emplace_back(a, b);
                 out->plane_launches++;
+                // side stream: reduce this group's partials while the next pass streams
+                CK(cudaStreamWaitEvent(side.s, b, 0));
                 if (pg[i].P.geom.n_batches) {
-                    launch_reduce(pg[i].part_pi.p, 1, pg[i].part_u.p, 2, pg[i].P.geom, pg[i].sd[pb].p, pg[i].su[pb].p);
+                    launch_reduce(pg[i].part_pi.p, 1, pg[i].part_u.p, 2, pg[i].P.geom, pg[i].sd[pb].p, pg[i].su[pb].p,
+                                  side.s);
                     out->other_launches++;
+                    reduced[i] = ev();
+                    CK(cudaEventRecord(reduced[i], side.s));
                 }
+                if (i == 0 && use_flags && it + 1 < iterations) launch_flags(it + 1);  // next step's mask bits
             }
             if (comm) {  // fold the region totals of every group and exchange them with all ranks
                 fm::CommFold folds[4];
@@ -2511,18 +2541,17 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
                                                2u};
                     words += 3;
                 }
-                cudaEvent_t ready = evs.next(), a = evs.next(), b = evs.next();
-                CK(cudaEventRecord(ready, stream()));
-                CK(cudaStreamWaitEvent(side.s, ready, 0));
+                cudaEvent_t a = evs.next(), b = evs.next();
                 CK(cudaEventRecord(a, side.s));
                 comm_launch(comm, nullptr, words, 0, folds, nf, side.s);
                 CK(cudaEventRecord(b, side.s));
                 comm_spans.emplace_back(a, b);
-                exchanged.push_back(b);
                 out->other_launches++;
             }
+            side_done[it] = ev();
+            CK(cudaEventRecord(side_done[it], side.s));
         }
-        if (comm && !exchanged.empty()) CK(cudaStreamWaitEvent(stream(), exchanged.back(), 0));  // last exchange is inside the timed region
+        CK(cudaStreamWaitEvent(stream(), side_done[iterations - 1], 0));  // all side work is inside the timed region
         CK(cudaEventRecord(t1, stream()));
         CK(cudaEventSynchronize(t1));
         float total = 0.f, plane = 0.f;
