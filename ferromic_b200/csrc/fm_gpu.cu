@@ -280,6 +280,7 @@ struct fm_group {
     uint32_t *d_alt = nullptr, *d_cnt = nullptr;
     uint32_t n_bits = 1;            // allele bitplanes (1 = biallelic; 2..4 = multi-allelic matrix)
     uint32_t *d_acount = nullptr;   // multi-allelic: cached per-allele counts [V][1 << n_bits]
+    bool count_only = false;        // no bitplanes: counts are produced straight from the u8 rows (partitions)
     uint64_t seg = 0, unc = 0;
     double pi_sum = 0.0;  // dense_pi_from_counts form over all sites
 };
@@ -615,6 +616,7 @@ DivResult run_diversity(fm_group *g, uint32_t v_lo, uint32_t v_hi, int pi_form, 
             e.alt_out = g->d_alt;
             e.called_out = g->d_cnt;
         }
+        if (g->count_only) fail(FM_ERR_INVALID_ARG, "internal: a count-only group has no bitplanes to stream");
         fm::PassParams<1> P{};
         P.g[0] = planes_of(g);
         P.geom = G;
@@ -923,7 +925,14 @@ fm_status fm_matrix_info(const fm_matrix *m, size_t *V, size_t *S, size_t *ploid
 
 // ------------------------------------------------------------------------------------ group
 // Allocate a group's bitplanes and lookup tables for the columns listed in `off` (sorted, unique).
-static fm_group *alloc_group(fm_matrix *m, std::vector<uint32_t> &&off) {
+// Can a warp stage one u8 row (+ its bitmap slice) in shared memory?  (row-staged K1 v2)
+static bool row_fits_smem(const fm_matrix *m) {
+    const size_t row_buf = ((m->stride + 15) & ~(size_t)15) + 16;
+    const size_t bit_buf = m->has_missing ? ((m->stride + 63) / 64 + 2) * 8 : 0;
+    return row_buf + bit_buf + 15 <= 24 * 1024;
+}
+
+static fm_group *alloc_group(fm_matrix *m, std::vector<uint32_t> &&off, bool count_only = false) {
     uint32_t n_bits = 1;
     while ((1u << n_bits) <= m->max_allele) ++n_bits;
     if (n_bits > 4)
@@ -937,9 +946,15 @@ static fm_group *alloc_group(fm_matrix *m, std::vector<uint32_t> &&off) {
         g->n = (uint32_t)g->off.size();
         g->wq = std::max<uint32_t>(1, (g->n + 127) / 128);
         g->n_bits = n_bits;
+        g->count_only = count_only && n_bits == 1 && row_fits_smem(m);
         const size_t plane_u4 = std::max<size_t>(m->V, 1) * g->wq;
-        g->d_allele = static_cast<uint4 *>(dev_alloc(plane_u4 * 16 * n_bits));
-        if (m->has_missing) g->d_called = static_cast<uint4 *>(dev_alloc(plane_u4 * 16));
+        if (g->count_only) {
+            g->d_alt = static_cast<uint32_t *>(dev_alloc(std::max<size_t>(m->V, 1) * sizeof(uint32_t)));
+            g->d_cnt = static_cast<uint32_t *>(dev_alloc(std::max<size_t>(m->V, 1) * sizeof(uint32_t)));
+        } else {
+            g->d_allele = static_cast<uint4 *>(dev_alloc(plane_u4 * 16 * n_bits));
+            if (m->has_missing) g->d_called = static_cast<uint4 *>(dev_alloc(plane_u4 * 16));
+        }
         // per-n tables: 1/n, n/(n-1) (stats.rs:2728-2732) and 1/H_{n-1} with the harmonic number
         // by forward summation exactly like stats.rs:4234-4240 / 4718-4719
         const size_t tn = (size_t)g->n + 1;
@@ -980,7 +995,8 @@ struct RepackSet {  // device-resident descriptor table of the groups one launch
         for (size_t i = 0; i < gs.size(); ++i) {
             const fm_group *g = gs[i];
             h[i] = fm::RepackGroup{g->d_off, g->n, g->wq, g->n_bits, reinterpret_cast<uint32_t *>(g->d_allele),
-                                   reinterpret_cast<uint32_t *>(g->d_called), std::max<size_t>(m->V, 1) * g->wq * 4};
+                                   reinterpret_cast<uint32_t *>(g->d_called), std::max<size_t>(m->V, 1) * g->wq * 4,
+                                   g->count_only ? g->d_alt : nullptr, g->count_only ? g->d_cnt : nullptr};
         }
         d_desc = static_cast<fm::RepackGroup *>(dev_alloc(h.size() * sizeof(fm::RepackGroup)));
         CK(cudaMemcpyAsync(d_desc, h.data(), h.size() * sizeof(fm::RepackGroup), cudaMemcpyHostToDevice, stream()));
@@ -1003,7 +1019,9 @@ static void launch_repack(const RepackSet &set, const uint8_t *data, size_t data
     const uint32_t bit_buf = missing ? (uint32_t)(((stride + 63) / 64 + 2) * 8) : 0u;
     const uint32_t warp_smem = (row_buf + bit_buf + 15u) & ~15u;
     static const uint32_t force_v1 = env_u32("FM_REPACK_V1", 0);
-    if (warp_smem <= 24 * 1024 && !force_v1) {
+    bool any_count_only = false;
+    for (const fm_group *g : gs) any_count_only |= g->count_only;
+    if (warp_smem <= 24 * 1024 && (!force_v1 || any_count_only)) {
         const uint32_t warps = std::max(1u, std::min(8u, (200u * 1024u) / warp_smem));
         const size_t smem = (size_t)warps * warp_smem;
         static std::once_flag attr_once;
@@ -1021,6 +1039,7 @@ static void launch_repack(const RepackSet &set, const uint8_t *data, size_t data
         return;
     }
     for (const fm_group *g : gs) {
+        if (g->count_only) fail(FM_ERR_INVALID_ARG, "internal: count-only groups need the row-staged repack");
         const uint32_t blocks = (uint32_t)std::min<uint64_t>(
             (uint64_t)sm_count(m->device) * 8,
             std::max<uint64_t>(1, ((uint64_t)(v_hi - v_lo) * ((g->wq * 4 + 31) / 32) + 7) / 8));
@@ -1045,6 +1064,8 @@ static void repack_resident(fm_matrix *m, const std::vector<fm_group *> &gs) {
         tm.stop();
         t_tim.repack_ms += tm.ms();
         CK(cudaStreamSynchronize(stream()));
+        for (fm_group *g : gs)
+            if (g->count_only) g->have_counts = true;
     } catch (...) {
         set.release();
         throw;
@@ -1406,7 +1427,7 @@ fm_status fm_ingest_add_partition(fm_ingest *h, const uint16_t *left, const uint
         fm_matrix_retain(h->m);
         try {
             std::vector<std::vector<uint32_t>> cols = partition_columns(h->m, left, right, n_samples, n_groups);
-            for (size_t g = 0; g <= n_groups; ++g) p->groups.push_back(alloc_group(h->m, std::move(cols[g])));
+            for (size_t g = 0; g <= n_groups; ++g) p->groups.push_back(alloc_group(h->m, std::move(cols[g]), true));
         } catch (...) {
             fm_partition_release(p);
             throw;
@@ -1478,6 +1499,8 @@ fm_status fm_ingest_finish(fm_ingest *h, fm_matrix **matrix_out, fm_group **grou
             t_tim.h2d_ms += a;      // span of the copy stream
             t_tim.repack_ms += b;   // span of the repack stream (overlaps the copies)
         }
+        for (fm_group *g : h->all)
+            if (g->count_only) g->have_counts = true;
         *matrix_out = h->m;
         for (size_t i = 0; i < h->groups.size(); ++i) groups_out[i] = h->groups[i];
         for (size_t i = 0; i < h->parts.size(); ++i) parts_out[i] = h->parts[i];
@@ -1714,7 +1737,7 @@ fm_status fm_partition_create(fm_matrix *m, const uint16_t *left, const uint16_t
                 fail(FM_ERR_UNSUPPORTED,
                      "this matrix was ingested in streaming mode: declare partitions with fm_ingest_add_partition");
             std::vector<std::vector<uint32_t>> cols = partition_columns(m, left, right, n_samples, n_groups);
-            for (size_t g = 0; g <= n_groups; ++g) p->groups.push_back(alloc_group(m, std::move(cols[g])));
+            for (size_t g = 0; g <= n_groups; ++g) p->groups.push_back(alloc_group(m, std::move(cols[g]), true));
             repack_resident(m, p->groups);  // the u8 matrix is read once for all G + 1 groups
         } catch (...) {
             fm_partition_release(p);

@@ -106,6 +106,9 @@ struct RepackGroup {
     uint32_t n, wq, n_bits;
     uint32_t *allele, *called; // called == nullptr when the matrix has no bitmap
     size_t plane_stride_words; // distance between allele bit planes (multi-allelic groups)
+    // count-only groups (the subpopulations of a W&C partition): no bitplanes are kept, the
+    // per-site alt / called counts -- all K4 ever reads -- are produced straight from the staged row
+    uint32_t *alt_out, *cnt_out;
 };
 
 __global__ void __launch_bounds__(256)
@@ -147,14 +150,97 @@ fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint
             for (uint32_t q = lane; q < nw; q += 32) bits[q] = missing[w0 - word_base + q];
         }
         __syncwarp();
+        // 32-bit views for the inner loops: bit (brel + o) of the staged bitmap slice, byte rb[o]
+        const uint32_t brel = (uint32_t)(bit0 - (w0 << 6));
+        const uint32_t *bits32 = reinterpret_cast<const uint32_t *>(bits);
+        const uint8_t *rb = rowb + delta;
         // ---- every group's words from the staged row
         for (uint32_t gi = 0; gi < n_groups; ++gi) {
             const RepackGroup G = groups[gi];
+            if (G.alt_out) {  // dense_sum_alt_with_missing / _no_missing (stats.rs:1665-1697) for this row
+                uint32_t ac = 0;  // alt | called << 16 (n < 65536) or two counters
+                uint32_t a = 0, c = 0;
+                for (uint32_t k = lane; k < G.n; k += 32) {
+                    const uint32_t o = __ldg(G.off + k);
+                    uint32_t cc = 1u;
+                    if (missing) {
+                        const uint32_t r = brel + o;
+                        cc = ~(bits32[r >> 5] >> (r & 31u)) & 1u;
+                    }
+                    c += cc;
+                    a += cc & (rb[o] != 0 ? 1u : 0u);
+                }
+                if (G.n < 65536u) {
+                    ac = a | (c << 16);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) ac += __shfl_xor_sync(FULL, ac, o);
+                    a = ac & 0xffffu;
+                    c = ac >> 16;
+                } else {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        a += __shfl_xor_sync(FULL, a, o);
+                        c += __shfl_xor_sync(FULL, c, o);
+                    }
+                }
+                if (lane == 0) {
+                    G.alt_out[v] = a;
+                    G.cnt_out[v] = c;
+                }
+                continue;
+            }
             const uint32_t words = G.wq * 4;
-            for (uint32_t wb = 0; wb < words; wb += 32) {
+            if (G.n_bits == 1) {
+                // biallelic fast path: words whose 32 haplotypes all exist run a branch-free loop
+                // (one offset load, one bit test, one byte test, two ballots per word)
+                const uint32_t full_words = G.n >> 5;
+                for (uint32_t wb = 0; wb < words; wb += 32) {
+                    uint32_t my_a = 0, my_c = 0;
+                    const uint32_t lim = min(32u, words - wb);
+                    const uint32_t nfull = full_words > wb ? min(lim, full_words - wb) : 0u;
+                    const uint32_t *offp = G.off + (size_t)wb * 32 + lane;
+#pragma unroll 8
+                    for (uint32_t i = 0; i < nfull; ++i) {
+                        const uint32_t o = __ldg(offp + i * 32);
+                        uint32_t cbit = 1u;
+                        if (missing) {
+                            const uint32_t r = brel + o;
+                            cbit = ~(bits32[r >> 5] >> (r & 31u)) & 1u;
+                        }
+                        const uint32_t abit = cbit & (rb[o] != 0 ? 1u : 0u);
+                        const uint32_t wc = __ballot_sync(FULL, cbit);
+                        const uint32_t wa = __ballot_sync(FULL, abit);
+                        my_c = (i == lane) ? wc : my_c;
+                        my_a = (i == lane) ? wa : my_a;
+                    }
+                    for (uint32_t i = nfull; i < lim; ++i) {  // the partial word and the zero padding
+                        const uint32_t k = (wb + i) * 32 + lane;
+                        uint32_t cbit = 0u, abit = 0u;
+                        if (k < G.n) {
+                            const uint32_t o = __ldg(G.off + k);
+                            cbit = 1u;
+                            if (missing) {
+                                const uint32_t r = brel + o;
+                                cbit = ~(bits32[r >> 5] >> (r & 31u)) & 1u;
+                            }
+                            abit = cbit & (rb[o] != 0 ? 1u : 0u);
+                        }
+                        const uint32_t wc = __ballot_sync(FULL, cbit);
+                        const uint32_t wa = __ballot_sync(FULL, abit);
+                        my_c = (i == lane) ? wc : my_c;
+                        my_a = (i == lane) ? wa : my_a;
+                    }
+                    if (lane < lim) {
+                        const size_t o = (size_t)v * words + wb + lane;
+                        G.allele[o] = my_a;
+                        if (G.called) G.called[o] = my_c;
+                    }
+                }
+                continue;
+            }
+            for (uint32_t wb = 0; wb < words; wb += 32) {  // multi-allelic: bit b of the allele index -> plane b
                 uint32_t my_a[4] = {0, 0, 0, 0}, my_c = 0;
                 const uint32_t lim = min(32u, words - wb);
-#pragma unroll 4
                 for (uint32_t i = 0; i < lim; ++i) {
                     const uint32_t k = (wb + i) * 32 + lane;
                     uint32_t byte = 0;
@@ -163,22 +249,17 @@ fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint
                         const uint32_t o = __ldg(G.off + k);
                         c = true;
                         if (missing) {
-                            const size_t bit = bit0 + o;
-                            c = !((bits[(bit >> 6) - w0] >> (bit & 63)) & 1ull);
+                            const uint32_t r = brel + o;
+                            c = !((bits32[r >> 5] >> (r & 31u)) & 1u);
                         }
-                        byte = c ? rowb[delta + o] : 0u;
+                        byte = c ? rb[o] : 0u;
                     }
                     const uint32_t wc = __ballot_sync(FULL, c);
-                    if (G.n_bits == 1) {
-                        const uint32_t wa = __ballot_sync(FULL, byte != 0);
-                        if (i == lane) my_a[0] = wa;
-                    } else {
 #pragma unroll
-                        for (uint32_t b = 0; b < 4; ++b) {  // compile-time indices keep my_a in registers
-                            if (b < G.n_bits) {
-                                const uint32_t wa = __ballot_sync(FULL, (byte >> b) & 1u);
-                                if (i == lane) my_a[b] = wa;
-                            }
+                    for (uint32_t b = 0; b < 4; ++b) {  // compile-time indices keep my_a in registers
+                        if (b < G.n_bits) {
+                            const uint32_t wa = __ballot_sync(FULL, (byte >> b) & 1u);
+                            if (i == lane) my_a[b] = wa;
                         }
                     }
                     if (i == lane) my_c = wc;
