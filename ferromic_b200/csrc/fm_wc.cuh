@@ -34,7 +34,7 @@
 namespace fm {
 
 constexpr uint32_t kWcSegSites = 1024;   // segment granularity (== 32 batches)
-constexpr uint32_t kWcMaxPairWarps = 15; // + 1 overall warp = 512 threads
+constexpr uint32_t kWcMaxPairWarps = 11; // + 1 overall warp = 384 threads (3 CTAs per SM at <= 56 registers)
 constexpr uint32_t kWcMaxKP = 8;         // pairs per lane (template parameter KP <= this)
 
 struct WcParams {
@@ -66,7 +66,7 @@ __host__ __device__ inline size_t fm_wc_cta_smem(uint32_t G) {
 }
 
 template <int KP>
-__global__ void __launch_bounds__((kWcMaxPairWarps + 1) * 32, 2)
+__global__ void __launch_bounds__(384, 3)
 fm_k_wc(const WcParams P) {
     extern __shared__ __align__(16) uint8_t wc_smem[];
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
