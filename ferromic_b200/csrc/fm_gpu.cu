@@ -875,6 +875,8 @@ fm_status fm_matrix_create_device(const uint8_t *d_data, const uint64_t *d_missi
         *out = nullptr;
         require_device();
         CK(cudaSetDevice(t_device));
+        if ((reinterpret_cast<uintptr_t>(d_data) & 15u) || (reinterpret_cast<uintptr_t>(d_missing) & 7u))
+            fail(FM_ERR_INVALID_ARG, "device matrix must be 16-byte aligned (bitmap 8-byte aligned)");
         fm_matrix *m = matrix_common(V, S, ploidy, max_allele, positions);
         m->owns = false;
         m->d_data = d_data;
@@ -926,11 +928,15 @@ fm_status fm_matrix_info(const fm_matrix *m, size_t *V, size_t *S, size_t *ploid
 // ------------------------------------------------------------------------------------ group
 // Allocate a group's bitplanes and lookup tables for the columns listed in `off` (sorted, unique).
 // Can a warp stage one u8 row (+ its bitmap slice) in shared memory?  (row-staged K1 v2)
-static bool row_fits_smem(const fm_matrix *m) {
-    const size_t row_buf = ((m->stride + 15) & ~(size_t)15) + 16;
+static size_t repack_warp_smem(const fm_matrix *m, uint32_t *row_buf_out, uint32_t *bit_buf_out) {
+    const size_t row_buf = ((m->stride + 15) & ~(size_t)15) + 32;
     const size_t bit_buf = m->has_missing ? ((m->stride + 63) / 64 + 2) * 8 : 0;
-    return row_buf + bit_buf + 15 <= 24 * 1024;
+    const size_t cnt_buf = 2 * ((m->stride + 31) / 32 + 1) * 4;  // full-row allele / called bit words
+    if (row_buf_out) *row_buf_out = (uint32_t)row_buf;
+    if (bit_buf_out) *bit_buf_out = (uint32_t)bit_buf;
+    return (row_buf + bit_buf + cnt_buf + 15) & ~(size_t)15;
 }
+static bool row_fits_smem(const fm_matrix *m) { return repack_warp_smem(m, nullptr, nullptr) <= 24 * 1024; }
 
 static fm_group *alloc_group(fm_matrix *m, std::vector<uint32_t> &&off, bool count_only = false) {
     uint32_t n_bits = 1;
@@ -984,28 +990,78 @@ static fm_group *alloc_group(fm_matrix *m, std::vector<uint32_t> &&off, bool cou
 // ingest: the staged chunk).  Rows that fit a warp's shared-memory slice take the row-staged
 // multi-group kernel (the u8 matrix is read once for all groups); wider rows (biobank cohorts)
 // fall back to the per-group gather kernel.
-struct RepackSet {  // device-resident descriptor table of the groups one launch repacks
-    std::vector<fm_group *> gs;
+struct RepackSet {  // device-resident descriptor tables of the groups one launch repacks / counts
+    std::vector<fm_group *> gs;        // every group
+    std::vector<fm_group *> plane_gs;  // groups that keep bitplanes
     fm::RepackGroup *d_desc = nullptr;
+    // count-only groups: sparse (row word, mask) membership lists
+    fm::CountTable ct{};
+    uint32_t *d_ent = nullptr;         // ent_start | ent_word | ent_mask
+    uint32_t **d_outs = nullptr;       // alt_out[n] | cnt_out[n]
     void build(const std::vector<fm_group *> &groups) {
         gs = groups;
         if (gs.empty()) return;
         const fm_matrix *m = gs[0]->m;
-        std::vector<fm::RepackGroup> h(gs.size());
-        for (size_t i = 0; i < gs.size(); ++i) {
-            const fm_group *g = gs[i];
-            h[i] = fm::RepackGroup{g->d_off, g->n, g->wq, g->n_bits, reinterpret_cast<uint32_t *>(g->d_allele),
-                                   reinterpret_cast<uint32_t *>(g->d_called), std::max<size_t>(m->V, 1) * g->wq * 4,
-                                   g->count_only ? g->d_alt : nullptr, g->count_only ? g->d_cnt : nullptr};
+        std::vector<fm::RepackGroup> h;
+        std::vector<uint32_t> ent_start{0}, ent_word, ent_mask;
+        std::vector<uint32_t *> outs_a, outs_c;
+        for (fm_group *g : gs) {
+            if (g->count_only) {
+                for (size_t k = 0; k < g->off.size();) {  // offsets are sorted: one entry per row word
+                    const uint32_t w = g->off[k] >> 5;
+                    uint32_t mask = 0;
+                    while (k < g->off.size() && (g->off[k] >> 5) == w) mask |= 1u << (g->off[k++] & 31u);
+                    ent_word.push_back(w);
+                    ent_mask.push_back(mask);
+                }
+                ent_start.push_back((uint32_t)ent_word.size());
+                outs_a.push_back(g->d_alt);
+                outs_c.push_back(g->d_cnt);
+            } else {
+                plane_gs.push_back(g);
+                h.push_back(fm::RepackGroup{g->d_off, g->n, g->wq, g->n_bits, reinterpret_cast<uint32_t *>(g->d_allele),
+                                            reinterpret_cast<uint32_t *>(g->d_called),
+                                            std::max<size_t>(m->V, 1) * g->wq * 4, nullptr, nullptr});
+            }
         }
-        d_desc = static_cast<fm::RepackGroup *>(dev_alloc(h.size() * sizeof(fm::RepackGroup)));
-        CK(cudaMemcpyAsync(d_desc, h.data(), h.size() * sizeof(fm::RepackGroup), cudaMemcpyHostToDevice, stream()));
+        if (!h.empty()) {
+            d_desc = static_cast<fm::RepackGroup *>(dev_alloc(h.size() * sizeof(fm::RepackGroup)));
+            CK(cudaMemcpyAsync(d_desc, h.data(), h.size() * sizeof(fm::RepackGroup), cudaMemcpyHostToDevice, stream()));
+        }
+        const uint32_t ncg = (uint32_t)outs_a.size();
+        if (ncg) {
+            const size_t ne = ent_word.size();
+            std::vector<uint32_t> packed;
+            packed.insert(packed.end(), ent_start.begin(), ent_start.end());
+            packed.insert(packed.end(), ent_word.begin(), ent_word.end());
+            packed.insert(packed.end(), ent_mask.begin(), ent_mask.end());
+            d_ent = static_cast<uint32_t *>(dev_alloc(packed.size() * 4));
+            CK(cudaMemcpyAsync(d_ent, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, stream()));
+            std::vector<uint32_t *> outs(outs_a);
+            outs.insert(outs.end(), outs_c.begin(), outs_c.end());
+            d_outs = static_cast<uint32_t **>(dev_alloc(outs.size() * sizeof(uint32_t *)));
+            CK(cudaMemcpyAsync(d_outs, outs.data(), outs.size() * sizeof(uint32_t *), cudaMemcpyHostToDevice, stream()));
+            ct.ent_start = d_ent;
+            ct.ent_word = d_ent + ncg + 1;
+            ct.ent_mask = d_ent + ncg + 1 + ne;
+            ct.alt_out = d_outs;
+            ct.cnt_out = d_outs + ncg;
+            ct.n_groups = ncg;
+            CK(cudaStreamSynchronize(stream()));
+            return;
+        }
         CK(cudaStreamSynchronize(stream()));
     }
     void release() {
         dev_free(d_desc);
+        dev_free(d_ent);
+        dev_free(d_outs);
         d_desc = nullptr;
+        d_ent = nullptr;
+        d_outs = nullptr;
+        ct = fm::CountTable{};
         gs.clear();
+        plane_gs.clear();
     }
 };
 
@@ -1014,14 +1070,10 @@ static void launch_repack(const RepackSet &set, const uint8_t *data, size_t data
     const std::vector<fm_group *> &gs = set.gs;
     if (gs.empty() || v_hi <= v_lo) return;
     const fm_matrix *m = gs[0]->m;
-    const size_t stride = m->stride;
-    const uint32_t row_buf = (uint32_t)(((stride + 15) & ~(size_t)15) + 16);
-    const uint32_t bit_buf = missing ? (uint32_t)(((stride + 63) / 64 + 2) * 8) : 0u;
-    const uint32_t warp_smem = (row_buf + bit_buf + 15u) & ~15u;
+    uint32_t row_buf = 0, bit_buf = 0;
+    const uint32_t warp_smem = (uint32_t)repack_warp_smem(m, &row_buf, &bit_buf);
     static const uint32_t force_v1 = env_u32("FM_REPACK_V1", 0);
-    bool any_count_only = false;
-    for (const fm_group *g : gs) any_count_only |= g->count_only;
-    if (warp_smem <= 24 * 1024 && (!force_v1 || any_count_only)) {
+    if (warp_smem <= 24 * 1024 && (!force_v1 || set.ct.n_groups)) {
         const uint32_t warps = std::max(1u, std::min(8u, (200u * 1024u) / warp_smem));
         const size_t smem = (size_t)warps * warp_smem;
         static std::once_flag attr_once;
@@ -1032,14 +1084,15 @@ static void launch_repack(const RepackSet &set, const uint8_t *data, size_t data
         const uint32_t per_sm = std::max(1u, std::min(8u, (uint32_t)((220u * 1024u) / smem)));
         const uint32_t blocks = std::max(1u, std::min<uint32_t>((rows + warps - 1) / warps,
                                                                 per_sm * (uint32_t)sm_count(m->device)));
-        fm::fm_k_repack_rows<<<blocks, warps * 32, smem, st>>>(data, data_bytes, missing, stride, v_base, word_base, v_lo,
-                                                               v_hi, set.d_desc, (uint32_t)gs.size(), warp_smem, row_buf);
+        fm::fm_k_repack_rows<<<blocks, warps * 32, smem, st>>>(data, data_bytes, missing, m->stride, v_base, word_base,
+                                                               v_lo, v_hi, set.d_desc, (uint32_t)set.plane_gs.size(),
+                                                               warp_smem, row_buf, bit_buf, set.ct);
         CK(cudaGetLastError());
         g_launches++;
         return;
     }
-    for (const fm_group *g : gs) {
-        if (g->count_only) fail(FM_ERR_INVALID_ARG, "internal: count-only groups need the row-staged repack");
+    if (set.ct.n_groups) fail(FM_ERR_INVALID_ARG, "internal: count-only groups need the row-staged repack");
+    for (const fm_group *g : set.plane_gs) {
         const uint32_t blocks = (uint32_t)std::min<uint64_t>(
             (uint64_t)sm_count(m->device) * 8,
             std::max<uint64_t>(1, ((uint64_t)(v_hi - v_lo) * ((g->wq * 4 + 31) / 32) + 7) / 8));

@@ -111,11 +111,25 @@ struct RepackGroup {
     uint32_t *alt_out, *cnt_out;
 };
 
+// Count-only groups (W&C subpopulations): the row is packed ONCE into full-row allele / called
+// bit words in matrix column order (4 cells per lane and step, no gather); group g then owns a
+// sparse list of (row word, membership mask) entries, lane = group, and its alt / called counts
+// are masked popcounts -- the cost follows the number of row words a group touches (7 for a
+// contiguous 190-haplotype population), not the number of haplotypes.
+struct CountTable {
+    const uint32_t *ent_start;  // [n_groups + 1]
+    const uint32_t *ent_word;   // [n_entries] row word index (column >> 5)
+    const uint32_t *ent_mask;   // [n_entries] member columns inside that word
+    uint32_t *const *alt_out;   // [n_groups] -> [V]
+    uint32_t *const *cnt_out;   // [n_groups] -> [V]
+    uint32_t n_groups;
+};
+
 __global__ void __launch_bounds__(256)
 fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint64_t *__restrict__ missing,
                  size_t stride, uint32_t v_base, uint64_t word_base, uint32_t v_lo, uint32_t v_hi,
                  const RepackGroup *__restrict__ groups, uint32_t n_groups, uint32_t warp_smem_bytes,
-                 uint32_t row_buf_bytes) {
+                 uint32_t row_buf_bytes, uint32_t bit_buf_bytes, CountTable ct) {
     extern __shared__ __align__(16) uint8_t rp_smem[];
     constexpr uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -131,64 +145,80 @@ fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint
         const size_t a1 = (row0 + stride + 15) & ~(size_t)15;
         const uint32_t nq = (uint32_t)((a1 - a0) >> 4);
         __syncwarp();
+        // asynchronous 16-byte copies straight into shared memory: every chunk of the row is in
+        // flight at once (no register staging, no per-iteration load latency)
         for (uint32_t q = lane; q < nq; q += 32) {
             const size_t at = a0 + ((size_t)q << 4);
-            uint4 x;
             if (at + 16 <= data_bytes) {
-                x = *reinterpret_cast<const uint4 *>(data + at);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(fm_smem_u32(rowb + ((size_t)q << 4))),
+                             "l"(data + at)
+                             : "memory");
             } else {  // last bytes of the buffer: never read past its end
                 uint32_t w[4] = {0, 0, 0, 0};
                 for (uint32_t b = 0; b < 16 && at + b < data_bytes; ++b) w[b >> 2] |= (uint32_t)data[at + b] << ((b & 3) * 8);
-                x = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4 *>(rowb + ((size_t)q << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            *reinterpret_cast<uint4 *>(rowb + ((size_t)q << 4)) = x;
         }
         const size_t bit0 = (size_t)v * stride;
         const uint64_t w0 = bit0 >> 6;
         if (missing) {
             const uint32_t nw = (uint32_t)(((bit0 + stride + 63) >> 6) - w0);
-            for (uint32_t q = lane; q < nw; q += 32) bits[q] = missing[w0 - word_base + q];
+            for (uint32_t q = lane; q < nw; q += 32)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(fm_smem_u32(bits + q)),
+                             "l"(missing + (w0 - word_base + q))
+                             : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         // 32-bit views for the inner loops: bit (brel + o) of the staged bitmap slice, byte rb[o]
         const uint32_t brel = (uint32_t)(bit0 - (w0 << 6));
         const uint32_t *bits32 = reinterpret_cast<const uint32_t *>(bits);
         const uint8_t *rb = rowb + delta;
-        // ---- every group's words from the staged row
+        // ---- count-only groups: full-row bit words + masked popcounts
+        if (ct.n_groups) {
+            const uint32_t rw = (uint32_t)((stride + 31) >> 5);
+            uint32_t *arow = reinterpret_cast<uint32_t *>(rowb + row_buf_bytes + bit_buf_bytes);
+            uint32_t *crow = arow + rw + 1;
+            const uint32_t *row32 = reinterpret_cast<const uint32_t *>(rowb + (delta & ~3u));
+            const uint32_t sh8 = (delta & 3u) * 8u;
+            for (uint32_t i = 0; i * 128u < (uint32_t)stride; ++i) {
+                const uint32_t col = (i * 32u + lane) * 4u;  // first of this lane's 4 columns
+                uint32_t x = 0;
+                if (col < (uint32_t)stride) {
+                    const uint32_t q = i * 32u + lane;
+                    x = __funnelshift_r(row32[q], row32[q + 1], sh8);
+                    const uint32_t left = (uint32_t)stride - col;  // columns that exist
+                    if (left < 4u) x &= (1u << (8u * left)) - 1u;
+                }
+                const uint32_t y = __vcmpne4(x, 0u) & 0x01010101u;
+                uint32_t wv = (((y * 0x01020408u) >> 24) & 0xFu) << (4u * (lane & 7u));
+                wv |= __shfl_xor_sync(FULL, wv, 1);
+                wv |= __shfl_xor_sync(FULL, wv, 2);
+                wv |= __shfl_xor_sync(FULL, wv, 4);
+                const uint32_t w = i * 4u + (lane >> 3);
+                if ((lane & 7u) == 0 && w < rw) arow[w] = wv;
+            }
+            const uint32_t qb = brel >> 5, sb = brel & 31u;
+            for (uint32_t w = lane; w < rw; w += 32)
+                crow[w] = missing ? ~__funnelshift_r(bits32[w + qb], bits32[w + qb + 1], sb) : FULL;
+            __syncwarp();
+            for (uint32_t g = lane; g < ct.n_groups; g += 32) {
+                uint32_t a = 0, c = 0;
+                const uint32_t e1 = __ldg(ct.ent_start + g + 1);
+                for (uint32_t e = __ldg(ct.ent_start + g); e < e1; ++e) {
+                    const uint32_t w = __ldg(ct.ent_word + e);
+                    const uint32_t cw = crow[w] & __ldg(ct.ent_mask + e);
+                    c += __popc(cw);
+                    a += __popc(arow[w] & cw);
+                }
+                ct.alt_out[g][v] = a;  // dense_sum_alt_with_missing / _no_missing (stats.rs:1665-1697)
+                ct.cnt_out[g][v] = c;
+            }
+        }
+        // ---- every plane group's words from the staged row
         for (uint32_t gi = 0; gi < n_groups; ++gi) {
             const RepackGroup G = groups[gi];
-            if (G.alt_out) {  // dense_sum_alt_with_missing / _no_missing (stats.rs:1665-1697) for this row
-                uint32_t ac = 0;  // alt | called << 16 (n < 65536) or two counters
-                uint32_t a = 0, c = 0;
-                for (uint32_t k = lane; k < G.n; k += 32) {
-                    const uint32_t o = __ldg(G.off + k);
-                    uint32_t cc = 1u;
-                    if (missing) {
-                        const uint32_t r = brel + o;
-                        cc = ~(bits32[r >> 5] >> (r & 31u)) & 1u;
-                    }
-                    c += cc;
-                    a += cc & (rb[o] != 0 ? 1u : 0u);
-                }
-                if (G.n < 65536u) {
-                    ac = a | (c << 16);
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) ac += __shfl_xor_sync(FULL, ac, o);
-                    a = ac & 0xffffu;
-                    c = ac >> 16;
-                } else {
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        a += __shfl_xor_sync(FULL, a, o);
-                        c += __shfl_xor_sync(FULL, c, o);
-                    }
-                }
-                if (lane == 0) {
-                    G.alt_out[v] = a;
-                    G.cnt_out[v] = c;
-                }
-                continue;
-            }
             const uint32_t words = G.wq * 4;
             if (G.n_bits == 1) {
                 // biallelic fast path: words whose 32 haplotypes all exist run a branch-free loop

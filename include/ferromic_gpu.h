@@ -59,7 +59,7 @@ fm_status fm_matrix_create(const uint8_t *data, const uint64_t *missing_or_null,
                            size_t n_samples, size_t ploidy, uint8_t max_allele,
                            const int64_t *positions_or_null, fm_matrix **out);
 /* Same, but data/missing already live in device memory of the current device (not copied, not
- * freed; must outlive the handle).  positions is a host pointer. */
+ * freed; must outlive the handle; d_data 16-byte aligned).  positions is a host pointer. */
 fm_status fm_matrix_create_device(const uint8_t *d_data, const uint64_t *d_missing_or_null,
                                   size_t n_variants, size_t n_samples, size_t ploidy,
                                   uint8_t max_allele, const int64_t *positions_or_null,
