@@ -17,6 +17,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -80,6 +81,13 @@ void require_device() {
 }
 
 cudaStream_t stream() { return cudaStreamPerThread; }
+
+uint32_t env_u32_early(const char *name, uint32_t dflt) {
+    const char *v = getenv(name);
+    if (!v || !*v) return dflt;
+    const long x = strtol(v, nullptr, 10);
+    return x > 0 ? (uint32_t)x : dflt;
+}
 
 // Caching device allocator.  A released handle's bitplanes / staging buffers go to a per-device
 // free list keyed by (rounded) size and are handed to the next request instead of back to the
@@ -169,6 +177,84 @@ void dev_free(const void *p) {
     }
     std::lock_guard<std::mutex> lk(c.mu);
     c.free_blocks.emplace(sz, b);
+}
+
+// Host -> device copies of caller memory.  Pinned (page-locked / registered) buffers go straight to
+// the copy engine.  Pageable buffers -- a Rust Vec<u8>, a numpy array -- would be staged by the
+// driver through one internal bounce buffer with a single-threaded memcpy (5-10 GB/s); instead the
+// library keeps a few pinned bounce buffers per process, fills them with several host threads and
+// lets the DMA of piece i overlap the memcpy of piece i+1.  On return the source is no longer
+// referenced; the device side of the copy is ordered on `st`.
+struct BouncePool {
+    static constexpr size_t kPiece = (size_t)32 << 20;
+    static constexpr int kBuffers = 4;
+    std::mutex mu;
+    uint8_t *buf[kBuffers] = {};
+    cudaEvent_t ev[kBuffers] = {};
+    bool busy[kBuffers] = {};
+    int next = 0;
+    int threads = 0;
+    ~BouncePool() {
+        for (int i = 0; i < kBuffers; ++i) {
+            if (buf[i]) cudaFreeHost(buf[i]);
+            if (ev[i]) cudaEventDestroy(ev[i]);
+        }
+    }
+    void copy(void *dst, const void *src, size_t bytes, cudaStream_t st) {
+        std::lock_guard<std::mutex> lk(mu);  // one pageable upload at a time per process
+        if (!threads) {
+            const unsigned hw = std::thread::hardware_concurrency();
+            threads = (int)std::max(1u, std::min(8u, env_u32_early("FM_HOST_THREADS", hw ? hw / 2 : 4)));
+        }
+        const uint8_t *s8 = static_cast<const uint8_t *>(src);
+        uint8_t *d8 = static_cast<uint8_t *>(dst);
+        for (size_t o = 0; o < bytes; o += kPiece) {
+            const size_t n = std::min(kPiece, bytes - o);
+            const int b = next;
+            next = (next + 1) % kBuffers;
+            if (!buf[b]) {
+                CK(cudaHostAlloc((void **)&buf[b], kPiece, cudaHostAllocDefault));
+                CK(cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming));
+            }
+            if (busy[b]) CK(cudaEventSynchronize(ev[b]));  // its previous DMA has drained
+            const int T = (int)std::min<size_t>((size_t)threads, (n + ((size_t)4 << 20) - 1) / ((size_t)4 << 20));
+            if (T <= 1) {
+                std::memcpy(buf[b], s8 + o, n);
+            } else {
+                std::vector<std::thread> pool;
+                const size_t slice = ((n + T - 1) / T + 63) & ~(size_t)63;
+                for (int t = 1; t < T; ++t) {
+                    const size_t lo = std::min(n, slice * t), hi = std::min(n, slice * (t + 1));
+                    if (hi > lo) pool.emplace_back([=] { std::memcpy(buf[b] + lo, s8 + o + lo, hi - lo); });
+                }
+                std::memcpy(buf[b], s8 + o, std::min(n, slice));
+                for (auto &th : pool) th.join();
+            }
+            CK(cudaMemcpyAsync(d8 + o, buf[b], n, cudaMemcpyHostToDevice, st));
+            CK(cudaEventRecord(ev[b], st));
+            busy[b] = true;
+        }
+    }
+};
+BouncePool g_bounce;
+
+bool host_is_pinned(const void *p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+// copy caller memory to the device on `st`; the source may be reused as soon as this returns
+// only if the caller synchronises `st` (pinned) -- pageable sources are already released.
+void h2d(void *dst, const void *src, size_t bytes, cudaStream_t st) {
+    if (!bytes) return;
+    if (bytes < ((size_t)1 << 20) || host_is_pinned(src))
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    else
+        g_bounce.copy(dst, src, bytes, st);
 }
 
 struct Timer {
@@ -847,13 +933,13 @@ fm_status fm_matrix_create(const uint8_t *data, const uint64_t *missing, size_t 
             tm.start();
             uint8_t *dd = static_cast<uint8_t *>(dev_alloc(std::max<size_t>(total, 16)));
             m->d_data = dd;
-            if (total) CK(cudaMemcpyAsync(dd, data, total, cudaMemcpyHostToDevice, stream()));
+            h2d(dd, data, total, stream());
             if (missing) {
                 const size_t words = (total + 63) / 64;
                 uint64_t *dm = static_cast<uint64_t *>(dev_alloc(std::max<size_t>(words, 2) * 8));
                 m->d_missing = dm;
                 m->has_missing = true;
-                if (words) CK(cudaMemcpyAsync(dm, missing, words * 8, cudaMemcpyHostToDevice, stream()));
+                h2d(dm, missing, words * 8, stream());
             }
             m->d_pos = static_cast<int64_t *>(dev_alloc(std::max<size_t>(V, 1) * 8));
             if (V) CK(cudaMemcpyAsync(m->d_pos, m->pos.data(), V * 8, cudaMemcpyHostToDevice, stream()));
@@ -1513,14 +1599,12 @@ fm_status fm_ingest_rows(fm_ingest *h, const uint8_t *rows, const uint64_t *miss
             h->next ^= 1;
             if (h->used[b]) CK(cudaStreamWaitEvent(h->copy_s, h->consumed[b], 0));
             if (stride)
-                CK(cudaMemcpyAsync(h->stage[b], rows + (r0 - first_row) * stride, (r1 - r0) * stride,
-                                   cudaMemcpyHostToDevice, h->copy_s));
+                h2d(h->stage[b], rows + (r0 - first_row) * stride, (r1 - r0) * stride, h->copy_s);
             uint64_t w0 = 0;
             if (m->has_missing && stride) {
                 w0 = (uint64_t)(r0 * stride) >> 6;
                 const uint64_t w1 = ((uint64_t)(r1 * stride) + 63) >> 6;
-                CK(cudaMemcpyAsync(h->stage_m[b], missing_whole + w0, (w1 - w0) * 8, cudaMemcpyHostToDevice,
-                                   h->copy_s));
+                h2d(h->stage_m[b], missing_whole + w0, (w1 - w0) * 8, h->copy_s);
             }
             CK(cudaEventRecord(h->copied[b], h->copy_s));
             CK(cudaStreamWaitEvent(h->comp_s, h->copied[b], 0));
