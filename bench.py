@@ -70,7 +70,7 @@ def make_groups(n_samples, seed):
     return g0, g1
 
 
-def gen_device(n_sites, n_samples, seed, device, missing_rate=MISSING_RATE):
+def gen_device(n_sites, n_samples, seed, device, missing_rate=MISSING_RATE, inband=None):
     """u8 matrix [V, S, 2] + packed missing bitmap generated on the GPU (host never has to
     synthesise 5 GB with numpy).  Beta(0.8, 0.8) site frequencies, Bernoulli alleles."""
     import torch
@@ -94,6 +94,10 @@ def gen_device(n_sites, n_samples, seed, device, missing_rate=MISSING_RATE):
         miss = torch.rand((n, stride), generator=gen, device=device) < missing_rate
         a &= ~miss
         data[s0 * stride:s1 * stride] = a.reshape(-1).to(torch.uint8)
+        if inband is not None:  # the same cohort as an int8 array: missing cells are negative (0xFF)
+            a8 = a.to(torch.uint8)
+            a8[miss] = 255
+            inband[s0 * stride:s1 * stride] = a8.reshape(-1)
         flat = miss.reshape(-1)
         e0 = s0 * stride  # multiple of 64 because chunk is
         pad = (-flat.numel()) % 64
@@ -249,7 +253,16 @@ def run_ours(args):
     mask = make_mask(pos, seed)
     g0, g1 = make_groups(S, N_SITES + N_SAMPLES)
     t0 = time.perf_counter()
-    d_data, d_bitmap = gen_device(V, S, seed, device)
+    h_i8 = None
+    if not args.skip_e2e and not args.skip_inband:
+        d_i8 = torch.empty(V * S * 2, dtype=torch.uint8, device=device)
+        d_data, d_bitmap = gen_device(V, S, seed, device, inband=d_i8)
+        h_i8 = torch.empty(d_i8.numel(), dtype=torch.uint8, pin_memory=True)
+        h_i8.copy_(d_i8)
+        torch.cuda.synchronize()
+        del d_i8
+    else:
+        d_data, d_bitmap = gen_device(V, S, seed, device)
     torch.cuda.synchronize()
     log(f"[rank {rank}] generated {V}x{S * 2} u8 matrix on device in {time.perf_counter() - t0:.1f}s")
 
@@ -365,7 +378,7 @@ def run_ours(args):
 
         phases = {}
 
-        def e2e_step():
+        def e2e_step(inband=False):
             # streaming ingest: chunked H2D overlapped with the repack into both groups' bitplanes
             t = [time.perf_counter()]
 
@@ -374,11 +387,14 @@ def run_ours(args):
                 phases[name] = phases.get(name, 0.0) + (t[-1] - t[-2]) * 1e3
 
             ih = C.c_void_p()
-            _lib.check(L.fm_ingest_begin(V, S, 2, 1, 1, pos.ctypes.data, 0, C.byref(ih)))
+            _lib.check(L.fm_ingest_begin(V, S, 2, 2 if inband else 1, 1, pos.ctypes.data, 0, C.byref(ih)))
             for idx, side in garrs:
                 _lib.check(L.fm_ingest_add_group(ih, idx.ctypes.data, side.ctypes.data, len(idx), None))
             lap("begin+declare_groups")
-            _lib.check(L.fm_ingest_rows(ih, h_data.data_ptr(), h_bitmap.data_ptr(), 0, V))
+            if inband:  # the caller's int8 array as it is: negative cells are missing, no bitmap
+                _lib.check(L.fm_ingest_rows(ih, h_i8.data_ptr(), None, 0, V))
+            else:
+                _lib.check(L.fm_ingest_rows(ih, h_data.data_ptr(), h_bitmap.data_ptr(), 0, V))
             lap("ingest_rows")
             mh = C.c_void_p()
             gh = (C.c_void_p * 2)()
@@ -413,6 +429,19 @@ def run_ours(args):
         tim = _lib.Timings()
         L.fm_timings_get(C.byref(tim))
         phases_timed = dict(phases)
+        inband_info = None
+        if h_i8 is not None:
+            e2e_step(inband=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(k):
+                e2e_step(inband=True)
+            torch.cuda.synchronize()
+            t_in = (time.perf_counter() - t0) / k
+            inband_info = {"value": geno_per_rank / t_in, "ms_per_step": t_in * 1e3,
+                           "h2d_bytes_per_step": int(h_i8.numel() + V * 8),
+                           "what": "same step from the int8 array Population.from_numpy receives (negative = missing, "
+                                   "FM_MISSING_IN_BAND): no bitmap, no host conversion pass; per rank"}
         # the same call with PAGEABLE host memory (what a Rust Vec<u8> or a numpy array is): the library
         # fills pinned bounce buffers with several host threads and overlaps them with the DMA
         pageable_ms = None
@@ -445,7 +474,7 @@ def run_ours(args):
                                          "stats": tim.stats_ms / k, "reduce": tim.reduce_ms / k,
                                          "d2h": tim.d2h_ms / k},
                "host_phase_ms_per_step": {k_: v_ / k for k_, v_ in phases_timed.items()},
-               "pageable_host_ms_per_step": pageable_ms,
+               "pageable_host_ms_per_step": pageable_ms, "inband_int8": inband_info,
                "api": "fm_ingest_begin/add_group/rows/finish (chunked H2D overlapped with repack) + "
                       "fm_per_site_diversity per group; h2d and repack spans overlap",
                "timing": "wall clock around synchronous C-ABI calls, cuda-synchronised on both sides"}
@@ -492,6 +521,7 @@ def main():
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-pageable", action="store_true")
+    ap.add_argument("--skip-inband", action="store_true")
     ap.add_argument("--free-device-copy", action="store_true", default=True)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -52,7 +52,7 @@ class BenchResult(C.Structure):
 
 EXPORTS = [
     "fm_last_error", "fm_version", "fm_device_count", "fm_set_device", "fm_synchronize", "fm_trim_pool",
-    "fm_matrix_create", "fm_matrix_create_device", "fm_matrix_retain", "fm_matrix_release",
+    "fm_matrix_create", "fm_matrix_create_inband", "fm_matrix_create_device", "fm_matrix_retain", "fm_matrix_release",
     "fm_matrix_info", "fm_ingest_begin", "fm_ingest_add_group", "fm_ingest_add_partition",
     "fm_ingest_rows", "fm_ingest_finish", "fm_ingest_abort", "fm_group_create", "fm_group_release", "fm_group_capacity", "fm_group_summary",
     "fm_group_segregating_sites", "fm_group_pi", "fm_harmonic", "fm_watterson_theta",
@@ -87,6 +87,7 @@ def lib() -> C.CDLL:
     L.fm_device_count.argtypes = [C.POINTER(C.c_int)]
     L.fm_set_device.argtypes = [C.c_int]
     L.fm_matrix_create.argtypes = [vp, vp, sz, sz, sz, C.c_uint8, vp, C.POINTER(vp)]
+    L.fm_matrix_create_inband.argtypes = [vp, sz, sz, sz, C.c_uint8, vp, C.POINTER(vp)]
     L.fm_matrix_create_device.argtypes = [vp, vp, sz, sz, sz, C.c_uint8, vp, C.POINTER(vp)]
     L.fm_matrix_retain.argtypes = [vp]
     L.fm_matrix_release.argtypes = [vp]

@@ -159,6 +159,25 @@ class _Matrix:
         self._groups: Dict[tuple, "_Group"] = {}
 
     @classmethod
+    def from_int8(cls, genotypes: np.ndarray, positions: np.ndarray, max_allele: int) -> "_Matrix":
+        """Dense matrix straight from the caller's int8 array (negative = missing): the buffer is
+        uploaded as it is and missingness stays in band (fm_matrix_create_inband) -- no host-side
+        conversion pass, no bitmap packing (lib.rs:1135-1227 does both serially)."""
+        g = np.ascontiguousarray(genotypes)
+        assert g.ndim == 3 and g.dtype == np.int8
+        self = cls.__new__(cls)
+        self.V, self.S, self.P = g.shape
+        self.has_missing = True
+        self.max_allele = int(max_allele)
+        pos = np.ascontiguousarray(positions, dtype=np.int64)
+        h = C.c_void_p()
+        check(lib().fm_matrix_create_inband(g.ctypes.data, self.V, self.S, self.P, self.max_allele, _ptr(pos),
+                                            C.byref(h)))
+        self.handle = h
+        self._groups = {}
+        return self
+
+    @classmethod
     def ingest(cls, alleles: np.ndarray, missing_mask: Optional[np.ndarray], positions: np.ndarray,
                group_haplotypes: Sequence[Sequence[Tuple[int, int]]], partitions=(), chunk_rows: int = 0,
                calls: int = 1, always_bitmap: bool = False) -> "_Matrix":
@@ -453,8 +472,13 @@ class _Shared:
         if self.dense is None:
             return None
         if self._dense_matrix is None:
-            a, miss, max_allele = self.dense
-            self._dense_matrix = _Matrix(a, miss, self.variants.positions, max_allele=max_allele)
+            a, miss, max_allele = self.dense[:3]
+            raw = self.dense[3] if len(self.dense) > 3 else None
+            if raw is not None and max_allele <= 127:
+                # int8 input with missing cells: hand the caller's buffer over as it is (in-band missingness)
+                self._dense_matrix = _Matrix.from_int8(raw, self.variants.positions, max_allele)
+            else:
+                self._dense_matrix = _Matrix(a, miss, self.variants.positions, max_allele=max_allele)
         return self._dense_matrix
 
     def sparse_matrix(self, sample_count: Optional[int] = None) -> _Matrix:
@@ -588,7 +612,8 @@ def _shared_from_numpy(genotypes, positions) -> _Shared:
     variants = _Variants(pos, gt)
     dense = None
     if P == 2:  # lib.rs:1208
-        dense = (alle, miss, int(alle.max()) if alle.size else 0)
+        raw = g if (g.dtype == np.int8 and miss.any()) else None  # bitmap only when needed (lib.rs:1209-1213)
+        dense = (alle, miss, int(alle.max()) if alle.size else 0, raw)
     return _Shared(variants, dense)
 
 

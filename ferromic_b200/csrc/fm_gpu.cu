@@ -342,7 +342,8 @@ struct fm_matrix {
     int device = 0;
     const uint8_t *d_data = nullptr;
     const uint64_t *d_missing = nullptr;
-    bool has_missing = false;  // matrix carries a missing bitmap (d_missing is null after a streaming ingest)
+    bool has_missing = false;  // matrix carries missingness (d_missing is null after a streaming ingest)
+    bool in_band = false;      // missingness is in band: cells >= 0x80 (negative int8) are missing, no bitmap
     bool streamed = false;     // u8 data was never resident: groups had to be declared before ingest
     bool owns = true;
     size_t V = 0, S = 0, ploidy = 0, stride = 0;
@@ -953,6 +954,37 @@ fm_status fm_matrix_create(const uint8_t *data, const uint64_t *missing, size_t 
     });
 }
 
+fm_status fm_matrix_create_inband(const uint8_t *data, size_t V, size_t S, size_t ploidy, uint8_t max_allele,
+                                  const int64_t *positions, fm_matrix **out) {
+    return guarded([&] {
+        if (!out) fail(FM_ERR_INVALID_ARG, "out is NULL");
+        *out = nullptr;
+        if (max_allele > 127) fail(FM_ERR_INVALID_ARG, "in-band missingness needs allele indices <= 127");
+        require_device();
+        CK(cudaSetDevice(t_device));
+        fm_matrix *m = matrix_common(V, S, ploidy, max_allele, positions);
+        m->has_missing = true;
+        m->in_band = true;
+        try {
+            const size_t total = V * m->stride;
+            if (total && !data) fail(FM_ERR_INVALID_ARG, "data is NULL");
+            Timer tm;
+            tm.start();
+            uint8_t *dd = static_cast<uint8_t *>(dev_alloc(std::max<size_t>(total, 16)));
+            m->d_data = dd;
+            h2d(dd, data, total, stream());
+            m->d_pos = static_cast<int64_t *>(dev_alloc(std::max<size_t>(V, 1) * 8));
+            if (V) CK(cudaMemcpyAsync(m->d_pos, m->pos.data(), V * 8, cudaMemcpyHostToDevice, stream()));
+            tm.stop();
+            t_tim.h2d_ms += tm.ms();
+        } catch (...) {
+            fm_matrix_release(m);
+            throw;
+        }
+        *out = m;
+    });
+}
+
 fm_status fm_matrix_create_device(const uint8_t *d_data, const uint64_t *d_missing, size_t V, size_t S,
                                   size_t ploidy, uint8_t max_allele, const int64_t *positions,
                                   fm_matrix **out) {
@@ -1016,7 +1048,7 @@ fm_status fm_matrix_info(const fm_matrix *m, size_t *V, size_t *S, size_t *ploid
 // Can a warp stage one u8 row (+ its bitmap slice) in shared memory?  (row-staged K1 v2)
 static size_t repack_warp_smem(const fm_matrix *m, uint32_t *row_buf_out, uint32_t *bit_buf_out) {
     const size_t row_buf = ((m->stride + 15) & ~(size_t)15) + 32;
-    const size_t bit_buf = m->has_missing ? ((m->stride + 63) / 64 + 2) * 8 : 0;
+    const size_t bit_buf = (m->has_missing && !m->in_band) ? ((m->stride + 63) / 64 + 2) * 8 : 0;
     const size_t cnt_buf = 2 * ((m->stride + 31) / 32 + 1) * 4;  // full-row allele / called bit words
     if (row_buf_out) *row_buf_out = (uint32_t)row_buf;
     if (bit_buf_out) *bit_buf_out = (uint32_t)bit_buf;
@@ -1172,7 +1204,7 @@ static void launch_repack(const RepackSet &set, const uint8_t *data, size_t data
                                                                 per_sm * (uint32_t)sm_count(m->device)));
         fm::fm_k_repack_rows<<<blocks, warps * 32, smem, st>>>(data, data_bytes, missing, m->stride, v_base, word_base,
                                                                v_lo, v_hi, set.d_desc, (uint32_t)set.plane_gs.size(),
-                                                               warp_smem, row_buf, bit_buf, set.ct);
+                                                               warp_smem, row_buf, bit_buf, set.ct, m->in_band ? 1u : 0u);
         CK(cudaGetLastError());
         g_launches++;
         return;
@@ -1185,7 +1217,7 @@ static void launch_repack(const RepackSet &set, const uint8_t *data, size_t data
         fm::fm_k_repack<<<blocks, 256, 0, st>>>(data, missing, m->stride, g->d_off, g->n, g->wq, v_base, word_base, v_lo,
                                                 v_hi, reinterpret_cast<uint32_t *>(g->d_allele),
                                                 reinterpret_cast<uint32_t *>(g->d_called), g->n_bits,
-                                                std::max<size_t>(m->V, 1) * g->wq * 4);
+                                                std::max<size_t>(m->V, 1) * g->wq * 4, m->in_band ? 1u : 0u);
         CK(cudaGetLastError());
         g_launches++;
     }
@@ -1511,6 +1543,9 @@ fm_status fm_ingest_begin(size_t V, size_t S, size_t ploidy, int has_missing, ui
         try {
             h->m = matrix_common(V, S, ploidy, max_allele, positions);
             h->m->has_missing = has_missing != 0;
+            h->m->in_band = has_missing == FM_MISSING_IN_BAND;
+            if (h->m->in_band && max_allele > 127)
+                fail(FM_ERR_INVALID_ARG, "in-band missingness needs allele indices <= 127");
             h->m->streamed = true;
             h->m->d_pos = static_cast<int64_t *>(dev_alloc(std::max<size_t>(V, 1) * 8));
             if (V) CK(cudaMemcpyAsync(h->m->d_pos, h->m->pos.data(), V * 8, cudaMemcpyHostToDevice, stream()));
@@ -1521,7 +1556,7 @@ fm_status fm_ingest_begin(size_t V, size_t S, size_t ploidy, int has_missing, ui
             h->stage_words = (chunk_rows * stride + 63) / 64 + 2;
             for (int i = 0; i < 2; ++i) {
                 h->stage[i] = static_cast<uint8_t *>(dev_alloc(chunk_rows * stride));
-                if (has_missing) h->stage_m[i] = static_cast<uint64_t *>(dev_alloc(h->stage_words * 8));
+                if (has_missing == FM_MISSING_BITMAP) h->stage_m[i] = static_cast<uint64_t *>(dev_alloc(h->stage_words * 8));
                 CK(cudaEventCreateWithFlags(&h->copied[i], cudaEventDisableTiming));
                 CK(cudaEventCreateWithFlags(&h->consumed[i], cudaEventDisableTiming));
             }
@@ -1584,7 +1619,8 @@ fm_status fm_ingest_rows(fm_ingest *h, const uint8_t *rows, const uint64_t *miss
         fm_matrix *m = h->m;
         if (first_row > m->V || n_rows > m->V - first_row) fail(FM_ERR_INVALID_ARG, "row range outside the matrix");
         if (n_rows && m->stride && !rows) fail(FM_ERR_INVALID_ARG, "rows is NULL");
-        if (m->has_missing && !missing_whole) fail(FM_ERR_INVALID_ARG, "matrix was declared with a missing bitmap");
+        const bool bitmap = m->has_missing && !m->in_band;
+        if (bitmap && !missing_whole) fail(FM_ERR_INVALID_ARG, "matrix was declared with a missing bitmap");
         set_dev(m);
         const size_t stride = m->stride;
         if (!h->set.d_desc && !h->all.empty()) h->set.build(h->all);  // groups are final from here on
@@ -1601,14 +1637,14 @@ fm_status fm_ingest_rows(fm_ingest *h, const uint8_t *rows, const uint64_t *miss
             if (stride)
                 h2d(h->stage[b], rows + (r0 - first_row) * stride, (r1 - r0) * stride, h->copy_s);
             uint64_t w0 = 0;
-            if (m->has_missing && stride) {
+            if (bitmap && stride) {
                 w0 = (uint64_t)(r0 * stride) >> 6;
                 const uint64_t w1 = ((uint64_t)(r1 * stride) + 63) >> 6;
                 h2d(h->stage_m[b], missing_whole + w0, (w1 - w0) * 8, h->copy_s);
             }
             CK(cudaEventRecord(h->copied[b], h->copy_s));
             CK(cudaStreamWaitEvent(h->comp_s, h->copied[b], 0));
-            launch_repack(h->set, h->stage[b], (r1 - r0) * stride, m->has_missing ? h->stage_m[b] : nullptr,
+            launch_repack(h->set, h->stage[b], (r1 - r0) * stride, bitmap ? h->stage_m[b] : nullptr,
                           (uint32_t)r0, w0, (uint32_t)r0, (uint32_t)r1, h->comp_s);
             CK(cudaEventRecord(h->consumed[b], h->comp_s));
             h->used[b] = true;

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256)
 fm_k_repack(const uint8_t *__restrict__ data, const uint64_t *__restrict__ missing, size_t stride,
             const uint32_t *__restrict__ off, uint32_t n, uint32_t wq, uint32_t v_base, uint64_t word_base,
             uint32_t v_lo, uint32_t v_hi, uint32_t *__restrict__ allele, uint32_t *__restrict__ called,
-            uint32_t n_bits, size_t plane_stride_words) {
+            uint32_t n_bits, size_t plane_stride_words, uint32_t in_band) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -67,7 +67,9 @@ fm_k_repack(const uint8_t *__restrict__ data, const uint64_t *__restrict__ missi
                     const size_t bit = bit_base + o;
                     c = !((missing[(bit >> 6) - word_base] >> (bit & 63)) & 1ull);
                 }
-                byte = c ? data[base + o] : 0u;
+                byte = data[base + o];
+                if (in_band) c = byte < 0x80u;  // in-band missingness: a negative int8 cell
+                if (!c) byte = 0u;
             }
             const uint32_t wc = __ballot_sync(0xffffffffu, c);
             if (n_bits == 1) {  // biallelic: any non-zero allele index is the alternate allele
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(256)
 fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint64_t *__restrict__ missing,
                  size_t stride, uint32_t v_base, uint64_t word_base, uint32_t v_lo, uint32_t v_hi,
                  const RepackGroup *__restrict__ groups, uint32_t n_groups, uint32_t warp_smem_bytes,
-                 uint32_t row_buf_bytes, uint32_t bit_buf_bytes, CountTable ct) {
+                 uint32_t row_buf_bytes, uint32_t bit_buf_bytes, CountTable ct, uint32_t in_band) {
     extern __shared__ __align__(16) uint8_t rp_smem[];
     constexpr uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -198,10 +200,19 @@ fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint
                 wv |= __shfl_xor_sync(FULL, wv, 4);
                 const uint32_t w = i * 4u + (lane >> 3);
                 if ((lane & 7u) == 0 && w < rw) arow[w] = wv;
+                if (in_band) {  // called = cell < 0x80 (a non-negative int8)
+                    const uint32_t z = (~x >> 7) & 0x01010101u;
+                    uint32_t cv = (((z * 0x01020408u) >> 24) & 0xFu) << (4u * (lane & 7u));
+                    cv |= __shfl_xor_sync(FULL, cv, 1);
+                    cv |= __shfl_xor_sync(FULL, cv, 2);
+                    cv |= __shfl_xor_sync(FULL, cv, 4);
+                    if ((lane & 7u) == 0 && w < rw) crow[w] = cv;
+                }
             }
             const uint32_t qb = brel >> 5, sb = brel & 31u;
-            for (uint32_t w = lane; w < rw; w += 32)
-                crow[w] = missing ? ~__funnelshift_r(bits32[w + qb], bits32[w + qb + 1], sb) : FULL;
+            if (!in_band)
+                for (uint32_t w = lane; w < rw; w += 32)
+                    crow[w] = missing ? ~__funnelshift_r(bits32[w + qb], bits32[w + qb + 1], sb) : FULL;
             __syncwarp();
             for (uint32_t g = lane; g < ct.n_groups; g += 32) {
                 uint32_t a = 0, c = 0;
@@ -232,12 +243,15 @@ fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint
 #pragma unroll 8
                     for (uint32_t i = 0; i < nfull; ++i) {
                         const uint32_t o = __ldg(offp + i * 32);
+                        const uint32_t cell = rb[o];
                         uint32_t cbit = 1u;
                         if (missing) {
                             const uint32_t r = brel + o;
                             cbit = ~(bits32[r >> 5] >> (r & 31u)) & 1u;
+                        } else if (in_band) {
+                            cbit = cell < 0x80u ? 1u : 0u;
                         }
-                        const uint32_t abit = cbit & (rb[o] != 0 ? 1u : 0u);
+                        const uint32_t abit = cbit & (cell != 0 ? 1u : 0u);
                         const uint32_t wc = __ballot_sync(FULL, cbit);
                         const uint32_t wa = __ballot_sync(FULL, abit);
                         my_c = (i == lane) ? wc : my_c;
@@ -248,12 +262,15 @@ fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint
                         uint32_t cbit = 0u, abit = 0u;
                         if (k < G.n) {
                             const uint32_t o = __ldg(G.off + k);
+                            const uint32_t cell = rb[o];
                             cbit = 1u;
                             if (missing) {
                                 const uint32_t r = brel + o;
                                 cbit = ~(bits32[r >> 5] >> (r & 31u)) & 1u;
+                            } else if (in_band) {
+                                cbit = cell < 0x80u ? 1u : 0u;
                             }
-                            abit = cbit & (rb[o] != 0 ? 1u : 0u);
+                            abit = cbit & (cell != 0 ? 1u : 0u);
                         }
                         const uint32_t wc = __ballot_sync(FULL, cbit);
                         const uint32_t wa = __ballot_sync(FULL, abit);
@@ -278,11 +295,14 @@ fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint
                     if (k < G.n) {
                         const uint32_t o = __ldg(G.off + k);
                         c = true;
+                        byte = rb[o];
                         if (missing) {
                             const uint32_t r = brel + o;
                             c = !((bits32[r >> 5] >> (r & 31u)) & 1u);
+                        } else if (in_band) {
+                            c = byte < 0x80u;
                         }
-                        byte = c ? rb[o] : 0u;
+                        if (!c) byte = 0u;
                     }
                     const uint32_t wc = __ballot_sync(FULL, c);
 #pragma unroll

@@ -58,6 +58,10 @@ fm_status fm_trim_pool(void);
 fm_status fm_matrix_create(const uint8_t *data, const uint64_t *missing_or_null, size_t n_variants,
                            size_t n_samples, size_t ploidy, uint8_t max_allele,
                            const int64_t *positions_or_null, fm_matrix **out);
+/* Same layout with in-band missingness: cells >= 0x80 (negative int8) are missing, no bitmap --
+ * the int8 numpy array of Population.from_numpy as it is (lib.rs:1168-1199); see FM_MISSING_IN_BAND. */
+fm_status fm_matrix_create_inband(const uint8_t *data, size_t n_variants, size_t n_samples, size_t ploidy,
+                                  uint8_t max_allele, const int64_t *positions_or_null, fm_matrix **out);
 /* Same, but data/missing already live in device memory of the current device (not copied, not
  * freed; must outlive the handle; d_data 16-byte aligned).  positions is a host pointer. */
 fm_status fm_matrix_create_device(const uint8_t *d_data, const uint64_t *d_missing_or_null,
@@ -80,7 +84,16 @@ fm_status fm_matrix_info(const fm_matrix *m, size_t *n_variants, size_t *n_sampl
  *   missing_whole -> base of the WHOLE matrix's packed bitmap (stats.rs:1298-1302) or NULL when the
  *                    matrix was begun with has_missing == 0; only the words of the rows are read.
  * Host buffers are free again when fm_ingest_rows returns.  fm_ingest_finish hands out the
- * handles (groups in declaration order) and destroys the ingest handle. */
+ * handles (groups in declaration order) and destroys the ingest handle.
+ *
+ * has_missing: FM_MISSING_NONE, FM_MISSING_BITMAP (the reference's packed bitmap) or
+ * FM_MISSING_IN_BAND: cells >= 0x80 are missing and no bitmap exists -- exactly the int8 numpy
+ * array Population.from_numpy receives (negative = missing, lib.rs:1168-1199), so the host hands
+ * the caller's buffer over as it is: no convert_numeric_array pass, no bitmap packing, 11 % fewer
+ * bytes over PCIe. */
+#define FM_MISSING_NONE 0
+#define FM_MISSING_BITMAP 1
+#define FM_MISSING_IN_BAND 2
 typedef struct fm_ingest fm_ingest;
 fm_status fm_ingest_begin(size_t n_variants, size_t n_samples, size_t ploidy, int has_missing,
                           uint8_t max_allele, const int64_t *positions_or_null, size_t chunk_rows_or_0,

@@ -570,3 +570,69 @@ def test_wc_fst_multi_allelic_matches_oracle(max_allele, n_pops):
     labels = sorted(str(i) for i in range(n_pops))
     vs, _ = orc.from_numpy(g, pos)
     _wc_compare(F, _to_python_variants(g, pos), vs, left, right, labels, (int(pos[1]), int(pos[-2])))
+
+
+# ------------------------------------------------------------------ in-band missingness (int8 cells < 0)
+@pytest.mark.parametrize("max_allele", [1, 3])
+def test_inband_missing_equals_bitmap(max_allele):
+    """FM_MISSING_IN_BAND / fm_matrix_create_inband: the int8 array as the caller holds it (negative =
+    missing) must give the same planes and counts as the converted u8 matrix + packed bitmap."""
+    import ctypes as C
+    from ferromic_b200 import _lib
+    from ferromic_b200.api import _Matrix
+    if max_allele == 1:
+        g, pos, pops = make_cohort(2100, 37, n_pops=3, missing_rate=0.15, seed=77)
+    else:
+        g, pos = make_multi_cohort(900, 37, max_allele, 0.15, seed=78)
+        pops = [list(range(0, 12)), list(range(12, 25)), list(range(25, 37))]
+    miss = g < 0
+    alle = np.where(miss, 0, g).astype(np.uint8)
+    haps = [both_sides(pops[0]), both_sides(pops[1]) + [(pops[2][0], 1)], [(s, 1) for s in pops[2]]]
+    bitmap = _Matrix(alle, miss, pos, max_allele=max_allele)
+    inband = _Matrix.from_int8(g.astype(np.int8), pos, max_allele)
+    for h in haps:
+        a, b = bitmap.group(h), inband.group(h)
+        if max_allele == 1:
+            sa, sb = a.summary(True), b.summary(True)
+            assert np.array_equal(sa["alt"], sb["alt"]) and np.array_equal(sa["called"], sb["called"])
+            assert sa["pi_sum"] == sb["pi_sum"] and sa["segregating_sites"] == sb["segregating_sites"]
+        else:
+            assert a.segregating_sites() == b.segregating_sites()
+            assert a.pi(5000, _lib.FM_PI_DENSE) == b.pi(5000, _lib.FM_PI_DENSE)
+    if max_allele == 1:  # count-only partition groups (full-row bit words) and the streaming ingest
+        left = np.full(37, 0xFFFF, dtype=np.uint16)
+        for p, members in enumerate(pops):
+            left[members] = p
+        L = _lib.lib()
+        w = np.array([int(pos[0]), int(pos[-1])], dtype=np.int64)
+
+        def totals(m):
+            ph = C.c_void_p()
+            _lib.check(L.fm_partition_create(m.handle, left.ctypes.data, left.ctypes.data, 37, 3, C.byref(ph)))
+            oa, ob = np.zeros(1), np.zeros(1)
+            pa, pb = np.zeros(3), np.zeros(3)
+            pn, osz, nv = np.zeros(3, dtype=np.uint64), np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint64)
+            _lib.check(L.fm_wc_window_sums(ph, w.ctypes.data, 1, nv.ctypes.data, oa.ctypes.data, ob.ctypes.data,
+                                           osz.ctypes.data, pa.ctypes.data, pb.ctypes.data, pn.ctypes.data))
+            L.fm_partition_release(ph)
+            return (oa[0], ob[0], int(osz[0]), pa.tolist(), pb.tolist(), pn.tolist())
+
+        assert totals(bitmap) == totals(inband)
+        ih = C.c_void_p()
+        g8 = np.ascontiguousarray(g.astype(np.int8))
+        _lib.check(L.fm_ingest_begin(g.shape[0], 37, 2, 2, 1, pos.ctypes.data, 100, C.byref(ih)))  # FM_MISSING_IN_BAND
+        idx = np.asarray([h[0] for h in haps[0]], dtype=np.uint64)
+        side = np.asarray([h[1] for h in haps[0]], dtype=np.uint8)
+        _lib.check(L.fm_ingest_add_group(ih, idx.ctypes.data, side.ctypes.data, len(idx), None))
+        _lib.check(L.fm_ingest_rows(ih, g8.ctypes.data, None, 0, g.shape[0]))
+        mh, gh = C.c_void_p(), (C.c_void_p * 1)()
+        _lib.check(L.fm_ingest_finish(ih, C.byref(mh), gh, None))
+        alt = np.zeros(g.shape[0], dtype=np.uint32)
+        cnt = np.zeros(g.shape[0], dtype=np.uint32)
+        seg, unc, pis = C.c_uint64(), C.c_uint64(), C.c_double()
+        _lib.check(L.fm_group_summary(C.c_void_p(gh[0]), alt.ctypes.data, cnt.ctypes.data, C.byref(seg), C.byref(pis),
+                                      C.byref(unc)))
+        ref = bitmap.group(haps[0]).summary(True)
+        assert np.array_equal(alt, ref["alt"]) and np.array_equal(cnt, ref["called"]) and pis.value == ref["pi_sum"]
+        L.fm_group_release(C.c_void_p(gh[0]))
+        L.fm_matrix_release(mh)
