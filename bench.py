@@ -337,21 +337,27 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    plane_launch_bytes = res.plane_bytes_per_step / 2.0  # two plane-pass launches per step
+    launches_per_step = max(1, int(round(res.plane_launches / args.steps)))
+    plane_launch_bytes = res.plane_bytes_per_step / launches_per_step
     achieved = plane_launch_bytes / (res.plane_ms_avg * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic_plane_pass.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get("dram_bytes_per_launch")
+            if tj.get("launches_per_step") and tj["launches_per_step"] != launches_per_step:
+                traffic = traffic * tj["launches_per_step"] / launches_per_step  # same bytes, other launch split
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "fm_k_plane_pass<1>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    kname = ("fm_k_plane_pass_seq (both groups' planes streamed by one persistent launch)" if launches_per_step == 1
+             else "fm_k_plane_pass<1>")
+    roofline = {"bound": "hbm", "kernel": kname, "launches_per_step": launches_per_step, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0, "peak_source": peak_src,
                 "traffic": traffic, "bytes_per_launch": plane_launch_bytes, "ms_per_launch": res.plane_ms_avg,
-                "per_group": [{"haplotypes": len(h), "ms": res.group_ms_avg[i],
-                               "GBps": res.group_bytes[i] / (res.group_ms_avg[i] * 1e-3) / 1e9}
-                              for i, h in enumerate((g0, g1))]}
+                "per_group": None if launches_per_step == 1 else
+                [{"haplotypes": len(h), "ms": res.group_ms_avg[i],
+                  "GBps": res.group_bytes[i] / (res.group_ms_avg[i] * 1e-3) / 1e9} for i, h in enumerate((g0, g1))]}
 
     for g in groups:
         L.fm_group_release(g)

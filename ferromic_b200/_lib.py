@@ -56,7 +56,7 @@ EXPORTS = [
     "fm_matrix_info", "fm_ingest_begin", "fm_ingest_add_group", "fm_ingest_add_partition",
     "fm_ingest_rows", "fm_ingest_finish", "fm_ingest_abort", "fm_group_create", "fm_group_release", "fm_group_capacity", "fm_group_summary",
     "fm_group_segregating_sites", "fm_group_pi", "fm_harmonic", "fm_watterson_theta",
-    "fm_per_site_diversity", "fm_hudson_pair", "fm_hudson_dxy", "fm_partition_create",
+    "fm_per_site_diversity", "fm_per_site_diversity_multi", "fm_hudson_pair", "fm_hudson_dxy", "fm_partition_create",
     "fm_partition_release", "fm_wc_fst", "fm_wc_window_sums", "fm_fst_estimate_from_sums", "fm_adjusted_sequence_length", "fm_group_window_sums",
     "fm_hudson_window_sums", "fm_pi_from_sums", "fm_hudson_outcome_from_sums", "fm_comm_create", "fm_comm_export", "fm_comm_connect", "fm_comm_connect_local", "fm_comm_allgather", "fm_comm_set_timeout_ms",
     "fm_comm_destroy", "fm_synth_fill", "fm_timings_reset", "fm_timings_get", "fm_bench_diversity",
@@ -108,6 +108,7 @@ def lib() -> C.CDLL:
     L.fm_harmonic.argtypes = [sz, C.POINTER(dbl)]
     L.fm_watterson_theta.argtypes = [sz, sz, i64, C.POINTER(dbl)]
     L.fm_per_site_diversity.argtypes = [vp, sz, i64, i64, vp, sz, vp, sz, vp, vp, vp, sz, C.POINTER(sz)]
+    L.fm_per_site_diversity_multi.argtypes = [C.POINTER(vp), vp, sz, i64, i64, vp, sz, vp, sz, vp, vp, vp, sz, C.POINTER(sz)]
     L.fm_hudson_pair.argtypes = [vp, vp, i64, i64, C.c_int, C.c_int, i64, i64, sz, sz,
                                  C.POINTER(HudsonOutcome), C.POINTER(HudsonSites), C.POINTER(sz)]
     L.fm_hudson_dxy.argtypes = [vp, vp, i64, i64, C.c_int, sz, sz, C.POINTER(dbl), C.POINTER(C.c_int)]

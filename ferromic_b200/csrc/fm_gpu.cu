@@ -528,6 +528,88 @@ void launch_plane_pass(fm::PassParams<NG> P, int device) {
     t_tim.stats_bytes = bytes;
 }
 
+fm::GroupPlanes planes_of(const fm_group *g);
+
+// Several groups of one matrix over one site range in ONE persistent launch (fm_k_plane_pass_seq).
+// Returns false when the groups cannot share a launch (column-chunked rows, mixed bitmap / no
+// bitmap, more than kMaxSeq groups): the caller then launches per group.
+bool make_seq_params(fm_group *const *gs, size_t n, uint32_t v_lo, uint32_t v_hi, fm::SeqParams &P) {
+    if (n < 2 || n > (size_t)fm::kMaxSeq) return false;
+    static const uint32_t step_target = env_u32("FM_STEP_BYTES", fm::kStepBytesTarget);
+    static const uint32_t disable = env_u32("FM_NO_SEQ", 0);
+    if (disable) return false;
+    const uint32_t warp_smem = fm::kWarpSmemBytes;
+    const bool hc = gs[0]->d_called != nullptr;
+    uint32_t max_wq = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (gs[i]->m != gs[0]->m || (gs[i]->d_called != nullptr) != hc || gs[i]->n_bits != 1 || gs[i]->count_only)
+            return false;
+        max_wq = std::max(max_wq, gs[i]->wq);
+    }
+    uint32_t lg = 0;
+    while ((1u << lg) < std::min(max_wq, 8u)) ++lg;
+    const uint32_t planes = hc ? 2u : 1u;
+    while (lg < 5 && (uint64_t)max_wq * 16u * planes * (32u >> lg) * 2 > warp_smem) ++lg;
+    if (lg >= 5) return false;
+    P = fm::SeqParams{};
+    P.n_seg = (uint32_t)n;
+    uint32_t max_step = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t round_bytes = gs[i]->wq * 16u * planes * (32u >> lg);
+        uint32_t rounds = 1;
+        while (rounds * 2 <= (1u << lg) && round_bytes * rounds * 2 <= step_target) rounds *= 2;
+        P.seg[i].g = planes_of(gs[i]);
+        P.seg[i].rounds = rounds;
+        max_step = std::max(max_step, round_bytes * rounds);
+    }
+    fm::PassGeom &G = P.geom;
+    G.lps_log2 = lg;
+    G.lps = 1u << lg;
+    G.warps = fm::kWarpsPerCta;
+    G.warp_smem_bytes = warp_smem;
+    G.stage_bytes = (max_step + 127u) & ~127u;
+    G.n_stages = std::min<uint32_t>(fm::kMaxStages, warp_smem / G.stage_bytes);
+    if (G.n_stages < 2) return false;
+    G.v_lo = v_lo;
+    G.v_hi = v_hi;
+    G.b_lo = v_lo / 32;
+    G.n_batches = v_hi > v_lo ? (v_hi + 31) / 32 - G.b_lo : 0;  // per group
+    G.n_sites_total = (uint32_t)gs[0]->m->V;
+    return true;
+}
+
+template <int LG, bool HC>
+void launch_plane_pass_seq_t(const fm::SeqParams &P, uint32_t grid, size_t smem) {
+    CK(cudaFuncSetAttribute(fm::fm_k_plane_pass_seq<LG, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fm::fm_k_plane_pass_seq<LG, HC><<<grid, fm::kWarpsPerCta * 32, smem, stream()>>>(P);
+}
+
+void launch_plane_pass_seq(fm::SeqParams P, int device) {
+    if (P.geom.n_batches == 0) return;
+    P.geom.batch_counter = t_counters.take(device);
+    const size_t smem = (size_t)fm::kWarpsPerCta * P.geom.warp_smem_bytes;
+    const uint32_t total = P.geom.n_batches * P.n_seg;
+    const uint32_t grid = std::min<uint32_t>((uint32_t)sm_count(device), (total + fm::kWarpsPerCta - 1) / fm::kWarpsPerCta);
+    const bool hc = P.seg[0].g.called != nullptr;
+#define FM_SEQ_CASE(L)                                                   \
+    case L:                                                              \
+        if (hc) launch_plane_pass_seq_t<L, true>(P, grid, smem);         \
+        else launch_plane_pass_seq_t<L, false>(P, grid, smem);           \
+        break;
+    switch (P.geom.lps_log2) {
+        FM_SEQ_CASE(0) FM_SEQ_CASE(1) FM_SEQ_CASE(2) FM_SEQ_CASE(3) FM_SEQ_CASE(4)
+        default: fail(FM_ERR_INVALID_ARG, "internal: bad sequential pass geometry");
+    }
+#undef FM_SEQ_CASE
+    CK(cudaGetLastError());
+    g_launches++;
+    t_tim.stats_launches++;
+    uint64_t bytes = 0;
+    for (uint32_t i = 0; i < P.n_seg; ++i)
+        bytes += (uint64_t)(P.geom.v_hi - P.geom.v_lo) * P.seg[i].g.wq * 16u * (P.seg[i].g.called ? 2u : 1u);
+    t_tim.stats_bytes = bytes;
+}
+
 // reduce per-batch partials to per-super-batch on device, finish sequentially on the host
 void finish_partials(const double *d_pd, int nd, const uint32_t *d_pu, int nu, const fm::PassGeom &G,
                      double *out_d, uint64_t *out_u) {
@@ -723,6 +805,57 @@ DivResult run_diversity(fm_group *g, uint32_t v_lo, uint32_t v_hi, int pi_form, 
     t_tim.stats_ms += tm.ms();
     t_tim.reduce_ms += tr.ms();
     return r;
+}
+
+// Diversity statistics of several groups of one matrix over [v_lo, v_hi).  Groups whose counts
+// are not cached yet and whose rows fit the non-chunked geometry share ONE plane-pass launch
+// (fm_k_plane_pass_seq); everything else goes group by group through run_diversity.
+void run_diversity_multi(fm_group *const *gs, size_t n, uint32_t v_lo, uint32_t v_hi, int pi_form,
+                         double *const *d_pi, double *const *d_theta, const int64_t *d_mask, uint32_t n_mask,
+                         const int64_t *d_filt, uint32_t n_filt, DivResult *out) {
+    fm::SeqParams P{};
+    bool fuse = v_hi > v_lo;
+    for (size_t i = 0; i < n && fuse; ++i) fuse = !gs[i]->have_counts;
+    if (fuse) fuse = make_seq_params(gs, n, v_lo, v_hi, P);
+    if (!fuse) {
+        for (size_t i = 0; i < n; ++i)
+            out[i] = run_diversity(gs[i], v_lo, v_hi, pi_form, d_pi ? d_pi[i] : nullptr, d_theta ? d_theta[i] : nullptr,
+                                   d_mask, n_mask, d_filt, n_filt, false);
+        return;
+    }
+    const fm::PassGeom &G = P.geom;
+    std::vector<DevBuf<double>> part_pi(n);
+    std::vector<DevBuf<uint32_t>> part_u(n);
+    DevBuf<uint32_t> flags;
+    Timer tm;
+    tm.start();
+    const bool tracks = d_pi != nullptr;
+    if (tracks && (d_mask || d_filt)) {
+        flags.alloc(G.n_batches);
+        launch_site_flags(gs[0]->m, v_lo, v_hi, G.b_lo, G.n_batches, d_mask, n_mask, d_filt, n_filt, flags.p);
+    }
+    for (size_t i = 0; i < n; ++i) {
+        part_pi[i].alloc(G.n_batches);
+        part_u[i].alloc((size_t)G.n_batches * 2);
+        fm::DivEpilogue e{};
+        e.pi_out = tracks ? d_pi[i] : nullptr;
+        e.theta_out = tracks ? d_theta[i] : nullptr;
+        set_tables(e, gs[i]);
+        e.site_flags = flags.p;
+        e.pi_form = pi_form;
+        e.part_pi = part_pi[i].p;
+        e.part_u = part_u[i].p;
+        P.seg[i].div = e;
+    }
+    launch_plane_pass_seq(P, gs[0]->m->device);
+    tm.stop();
+    for (size_t i = 0; i < n; ++i) {
+        double od[1];
+        uint64_t ou[2];
+        finish_partials(part_pi[i].p, 1, part_u[i].p, 2, G, od, ou);
+        out[i] = DivResult{od[0], ou[0], ou[1]};
+    }
+    t_tim.stats_ms += tm.ms();
 }
 
 void ensure_counts(fm_group *g) {
@@ -1481,6 +1614,85 @@ fm_status fm_per_site_diversity(fm_group *g, size_t raw_n, int64_t rs, int64_t r
         CK(cudaStreamSynchronize(stream()));
         t_tim.d2h_ms += tm.ms();
         for (size_t i = 0; i < n; ++i) pos_out[i] = g->m->pos[lo + i] + 1;  // stats.rs:4746
+        *n_out = n;
+    });
+}
+
+fm_status fm_per_site_diversity_multi(fm_group *const *groups, const size_t *raw_n, size_t n_groups, int64_t rs,
+                                      int64_t re, const int64_t *mask_iv, size_t n_mask, const int64_t *filtered,
+                                      size_t n_filt, int64_t *pos_out, double *pi_out, double *theta_out,
+                                      size_t capacity, size_t *n_out) {
+    return guarded([&] {
+        if (!groups || !n_groups || !n_out || !raw_n) fail(FM_ERR_INVALID_ARG, "NULL argument");
+        *n_out = 0;
+        require_device();
+        fm_matrix *m = groups[0]->m;
+        for (size_t i = 0; i < n_groups; ++i)
+            if (!groups[i] || groups[i]->m != m) fail(FM_ERR_INVALID_ARG, "groups must share one matrix");
+        if (region_len(rs, re) <= 0) return;  // stats.rs:4656-4666
+        set_dev(m);
+        uint32_t lo, hi;
+        site_range(m, rs, re, lo, hi);
+        const size_t n = hi - lo;
+        if (n == 0) return;
+        if (n > capacity) fail(FM_ERR_INVALID_ARG, "output capacity too small");
+        if (!pos_out || !pi_out || !theta_out) fail(FM_ERR_INVALID_ARG, "output arrays are NULL");
+        std::vector<int64_t> merged, fs;
+        DevBuf<int64_t> d_mask, d_filt;
+        if (mask_iv) {
+            merge_intervals(mask_iv, n_mask, merged);
+            d_mask.alloc(std::max<size_t>(merged.size(), 2));
+            d_mask.upload(merged.data(), merged.size());
+        }
+        if (filtered && n_filt) {
+            fs.assign(filtered, filtered + n_filt);
+            std::sort(fs.begin(), fs.end());
+            d_filt.alloc(fs.size());
+            d_filt.upload(fs.data(), fs.size());
+        }
+        // groups with fewer than two listed haplotypes yield no sites in the reference
+        // (stats.rs:4675-4681): their rows are NaN here
+        std::vector<fm_group *> act;
+        std::vector<size_t> act_idx;
+        for (size_t i = 0; i < n_groups; ++i)
+            if (raw_n[i] >= 2) {
+                act.push_back(groups[i]);
+                act_idx.push_back(i);
+            }
+        std::vector<DevBuf<double>> d_pi(act.size()), d_th(act.size());
+        std::vector<double *> ppi(act.size()), pth(act.size());
+        for (size_t i = 0; i < act.size(); ++i) {
+            d_pi[i].alloc(n);
+            d_th[i].alloc(n);
+            ppi[i] = d_pi[i].p;
+            pth[i] = d_th[i].p;
+        }
+        std::vector<DivResult> res(act.size());
+        {
+            std::vector<std::unique_lock<std::mutex>> locks;
+            std::vector<fm_group *> order(act);
+            std::sort(order.begin(), order.end());
+            order.erase(std::unique(order.begin(), order.end()), order.end());
+            for (fm_group *g : order) locks.emplace_back(g->mu);  // address order: no lock inversion
+            if (!act.empty())
+                run_diversity_multi(act.data(), act.size(), lo, hi, FM_PIFORM_COMPONENTS, ppi.data(), pth.data(),
+                                    mask_iv ? d_mask.p : nullptr, (uint32_t)(merged.size() / 2),
+                                    fs.empty() ? nullptr : d_filt.p, (uint32_t)fs.size(), res.data());
+        }
+        Timer tm;
+        tm.start();
+        for (size_t i = 0; i < act.size(); ++i) {
+            d_pi[i].download(pi_out + act_idx[i] * capacity, n);
+            d_th[i].download(theta_out + act_idx[i] * capacity, n);
+        }
+        tm.stop();
+        CK(cudaStreamSynchronize(stream()));
+        t_tim.d2h_ms += tm.ms();
+        const double NaN = std::numeric_limits<double>::quiet_NaN();
+        for (size_t i = 0; i < n_groups; ++i)
+            if (raw_n[i] < 2)
+                for (size_t k = 0; k < n; ++k) pi_out[i * capacity + k] = theta_out[i * capacity + k] = NaN;
+        for (size_t i = 0; i < n; ++i) pos_out[i] = m->pos[lo + i] + 1;  // stats.rs:4746
         *n_out = n;
     });
 }
@@ -2612,8 +2824,8 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
         const uint32_t V = (uint32_t)m->V;
         struct PerGroup {
             fm::PassParams<1> P;
-            DevBuf<double> part_pi, pi, theta, sd[2];  // super-batch partials double-buffered by step parity:
-            DevBuf<uint32_t> part_u;                    // the exchange of step i overlaps step i+1
+            DevBuf<double> part_pi[2], pi, theta, sd[2];  // batch / super-batch partials double-buffered by step
+            DevBuf<uint32_t> part_u[2];                    // parity: reductions and exchange of step i overlap step i+1
             DevBuf<uint64_t> su[2];
         };
         std::vector<PerGroup> pg(n_groups);
@@ -2635,17 +2847,17 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
             const fm_group *gs[1] = {g};
             fm::PassGeom G = make_geom(gs, 1, 0, V);
             const size_t nb = std::max<uint32_t>(G.n_batches, 1);
-            pg[i].part_pi.alloc(nb);
-            pg[i].part_u.alloc(nb * 2);
             for (int k = 0; k < 2; ++k) {
+                pg[i].part_pi[k].alloc(nb);
+                pg[i].part_u[k].alloc(nb * 2);
                 pg[i].sd[k].alloc(nb / fm::kSuperBatches + 2);
                 pg[i].su[k].alloc(2 * (nb / fm::kSuperBatches + 2));
             }
             fm::DivEpilogue e{};
             set_tables(e, g);
             e.pi_form = FM_PIFORM_COUNTS;
-            e.part_pi = pg[i].part_pi.p;
-            e.part_u = pg[i].part_u.p;
+            e.part_pi = pg[i].part_pi[0].p;
+            e.part_u = pg[i].part_u[0].p;
             bytes += (uint64_t)V * g->wq * 16u * (g->d_called ? 2u : 1u);
             if (i < 8) out->group_bytes[i] = (uint64_t)V * g->wq * 16u * (g->d_called ? 2u : 1u) + (mode == 1 ? (uint64_t)V * 16u : 0);
             if (mode == 1) {
@@ -2674,9 +2886,12 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
             ~SideStream() {
                 if (s) cudaStreamDestroy(s);
             }
-        } side;
+        } side, xchg;  // side: mask lookup + reductions; xchg: the peer exchange (may wait for other ranks)
         CK(cudaStreamCreateWithFlags(&side.s, cudaStreamNonBlocking));
+        if (comm) CK(cudaStreamCreateWithFlags(&xchg.s, cudaStreamNonBlocking));
         const bool use_flags = mode == 1 && mask_iv && nb_all;
+        fm::SeqParams SP{};
+        const bool fused = make_seq_params(groups, n_groups, 0, V, SP);
         uint32_t *flagbuf[2] = {d_flags.p, d_flags2.p};
         std::vector<cudaEvent_t> flags_ready(iterations, nullptr), side_done(iterations, nullptr);
         std::vector<cudaEvent_t> reduced(n_groups, nullptr);  // last reduction of group i's per-batch partials
@@ -2704,9 +2919,35 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
             // buffers of parity pb were last read by the side work of step it - 2
             if (it >= 2) CK(cudaStreamWaitEvent(stream(), side_done[it - 2], 0));
             if (use_flags) CK(cudaStreamWaitEvent(stream(), flags_ready[it], 0));
+            if (fused) {
+                // all groups in ONE persistent launch (fm_k_plane_pass_seq)
+                for (size_t i = 0; i < n_groups; ++i) {
+                    SP.seg[i].div = pg[i].P.div;
+                    SP.seg[i].div.part_pi = pg[i].part_pi[pb].p;
+                    SP.seg[i].div.part_u = pg[i].part_u[pb].p;
+                    if (use_flags) SP.seg[i].div.site_flags = flagbuf[pb];
+                }
+                if (use_flags && it + 1 < iterations) launch_flags(it + 1);  // next step's mask bits, under this pass
+                cudaEvent_t a = evs.next(), b = evs.next();
+                CK(cudaEventRecord(a, stream()));
+                launch_plane_pass_seq(SP, m->device);
+                CK(cudaEventRecord(b, stream()));
+                spans.emplace_back(a, b);
+                out->plane_launches++;
+                CK(cudaStreamWaitEvent(side.s, b, 0));
+                for (size_t i = 0; i < n_groups; ++i) {
+                    if (!pg[i].P.geom.n_batches) continue;
+                    launch_reduce(pg[i].part_pi[pb].p, 1, pg[i].part_u[pb].p, 2, pg[i].P.geom, pg[i].sd[pb].p,
+                                  pg[i].su[pb].p, side.s);
+                    out->other_launches++;
+                    reduced[i] = ev();
+                    CK(cudaEventRecord(reduced[i], side.s));
+                }
+            } else
             for (size_t i = 0; i < n_groups; ++i) {
                 if (use_flags) pg[i].P.div.site_flags = flagbuf[pb];
-                if (reduced[i]) CK(cudaStreamWaitEvent(stream(), reduced[i], 0));  // its per-batch partials are reused
+                pg[i].P.div.part_pi = pg[i].part_pi[pb].p;
+                pg[i].P.div.part_u = pg[i].part_u[pb].p;
                 cudaEvent_t a = evs.next(), b = evs.next();
                 CK(cudaEventRecord(a, stream()));
                 launch_plane_pass<1>(pg[i].P, m->device);
@@ -2716,8 +2957,8 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
                 // side stream: reduce this group's partials while the next pass streams
                 CK(cudaStreamWaitEvent(side.s, b, 0));
                 if (pg[i].P.geom.n_batches) {
-                    launch_reduce(pg[i].part_pi.p, 1, pg[i].part_u.p, 2, pg[i].P.geom, pg[i].sd[pb].p, pg[i].su[pb].p,
-                                  side.s);
+                    launch_reduce(pg[i].part_pi[pb].p, 1, pg[i].part_u[pb].p, 2, pg[i].P.geom, pg[i].sd[pb].p,
+                                  pg[i].su[pb].p, side.s);
                     out->other_launches++;
                     reduced[i] = ev();
                     CK(cudaEventRecord(reduced[i], side.s));
@@ -2737,15 +2978,19 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
                                                2u};
                     words += 3;
                 }
-                cudaEvent_t a = evs.next(), b = evs.next();
-                CK(cudaEventRecord(a, side.s));
-                comm_launch(comm, nullptr, words, 0, folds, nf, side.s);
-                CK(cudaEventRecord(b, side.s));
+                cudaEvent_t red = ev(), a = evs.next(), b = evs.next();
+                CK(cudaEventRecord(red, side.s));  // this step's reductions
+                CK(cudaStreamWaitEvent(xchg.s, red, 0));
+                CK(cudaEventRecord(a, xchg.s));
+                comm_launch(comm, nullptr, words, 0, folds, nf, xchg.s);
+                CK(cudaEventRecord(b, xchg.s));
                 comm_spans.emplace_back(a, b);
                 out->other_launches++;
+                side_done[it] = b;  // buffers of this parity are free once the exchange has read them
+            } else {
+                side_done[it] = ev();
+                CK(cudaEventRecord(side_done[it], side.s));
             }
-            side_done[it] = ev();
-            CK(cudaEventRecord(side_done[it], side.s));
         }
         CK(cudaStreamWaitEvent(stream(), side_done[iterations - 1], 0));  // all side work is inside the timed region
         CK(cudaEventRecord(t1, stream()));
@@ -2756,7 +3001,7 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
             float t = 0.f;
             CK(cudaEventElapsedTime(&t, spans[si].first, spans[si].second));
             plane += t;
-            const size_t gi = si % n_groups;
+            const size_t gi = fused ? 0 : si % n_groups;
             if (gi < 8) out->group_ms_avg[gi] += t / (float)iterations;
         }
         if (comm) comm_check_status(comm);

@@ -983,6 +983,220 @@ fm_k_plane_pass(const __grid_constant__ PassParams<NG> P) {
     }
 }
 
+// ------------------------------------------------------------------------------ plane pass, several groups
+// fm_k_plane_pass_seq: ONE persistent launch streams the planes of up to kMaxSeq groups one after
+// the other over the same site range (the two orientation groups of a per-site diversity call).
+// Same per-warp TMA rings, same dynamic scheduler and the same per-batch arithmetic as
+// fm_k_plane_pass<1>; the batch index space is the concatenation of the groups' batch ranges, so
+// the launch ramp-up and the end-of-kernel quantisation (a warp's last batch) are paid once, not
+// once per group, and the finer batches of the smallest group fill the tail.
+constexpr int kMaxSeq = 4;
+
+struct SeqGroup {
+    GroupPlanes g;
+    DivEpilogue div;
+    uint32_t rounds;  // rounds of (32/lps) sites per pipeline step for this group's row width
+};
+
+struct SeqParams {
+    SeqGroup seg[kMaxSeq];
+    uint32_t n_seg;
+    PassGeom geom;  // lps, n_stages, stage_bytes (max over groups), warps, site range, scheduler counters
+};
+
+template <int LG, bool HC>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 1)
+fm_k_plane_pass_seq(const __grid_constant__ SeqParams P) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[kWarpsPerCta * kMaxStages];
+    __shared__ uint32_t batch_ring[kWarpsPerCta * kBatchRing];
+    static_assert(LG < 5, "column-chunked rows take the per-group kernel");
+    constexpr uint32_t LPS = 1u << LG;
+    constexpr uint32_t SPS = 32u >> LG;
+    constexpr uint32_t NPL = HC ? 2u : 1u;
+    constexpr uint32_t FULL = 0xffffffffu;
+
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = __shfl_sync(FULL, threadIdx.x >> 5, 0);
+    const PassGeom &G = P.geom;
+    const uint32_t n_stages = G.n_stages;
+    const uint32_t stage_bytes = G.stage_bytes;
+    const uint32_t n_sites_total = G.n_sites_total;
+    const uint32_t nb_seg = G.n_batches;              // batches per group (same site range for all)
+    const uint32_t n_batches = nb_seg * P.n_seg;      // concatenated batch space
+
+    const uint32_t smem_base = fm_smem_u32(smem_raw) + warp * G.warp_smem_bytes;
+    const uint32_t bar_base = fm_smem_u32(bars + warp * kMaxStages);
+    uint32_t *my_ring = batch_ring + warp * kBatchRing;
+    if (lane == 0) {
+        for (uint32_t s = 0; s < n_stages; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_base + 8u * s));
+        fm_fence_mbar_init();
+    }
+    __syncwarp();
+
+    uint32_t sched_j = blockIdx.x % kSchedCounters, sched_tried = 0;
+    auto range_lo = [&](uint32_t j) { return (uint32_t)(((uint64_t)n_batches * j) / kSchedCounters); };
+    uint32_t prefetched = 0;
+    if (lane == 0) prefetched = atomicAdd(G.batch_counter + sched_j * kSchedStrideWords, 1u);
+    auto claim = [&]() -> uint32_t {
+        for (;;) {
+            const uint32_t idx = __shfl_sync(FULL, prefetched, 0);
+            const uint32_t lo = range_lo(sched_j), hi = range_lo(sched_j + 1);
+            if (idx < hi - lo) {
+                if (lane == 0) prefetched = atomicAdd(G.batch_counter + sched_j * kSchedStrideWords, 1u);
+                return lo + idx;
+            }
+            if (++sched_tried == kSchedCounters) return 0xffffffffu;
+            sched_j = (sched_j + 1 == kSchedCounters) ? 0 : sched_j + 1;
+            if (lane == 0) prefetched = atomicAdd(G.batch_counter + sched_j * kSchedStrideWords, 1u);
+        }
+    };
+
+    // ---- issue side: per-group context of the batch being issued
+    uint32_t iss_ring = 0, iss_k = 0, iss_spb = 0, iss_stage = 0, iss_batch = 0;
+    uint32_t iss_w16 = 0, iss_step_sites = 1, iss_seg = 0, iss_lb = 0;
+    auto issue = [&](uint32_t stage) {  // lane 0 only: TMA bulk copies of step iss_k of batch iss_lb of group iss_seg
+        const uint32_t bar = bar_base + 8u * stage;
+        const uint32_t dst = smem_base + stage * stage_bytes;
+        const uint32_t v0 = (G.b_lo + iss_lb) * 32 + iss_k * iss_step_sites;
+        const uint32_t nsites = (v0 < n_sites_total) ? min(iss_step_sites, n_sites_total - v0) : 0u;
+        if (nsites == 0) {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+            return;
+        }
+        const uint32_t bytes = nsites * iss_w16;
+        const uint32_t slot = iss_step_sites * iss_w16;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * NPL) : "memory");
+        const size_t off = (size_t)v0 * iss_w16;
+        const GroupPlanes &gp = P.seg[iss_seg].g;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(reinterpret_cast<const uint8_t *>(gp.allele) + off), "r"(bytes), "r"(bar)
+                     : "memory");
+        if constexpr (HC)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             dst + slot),
+                         "l"(reinterpret_cast<const uint8_t *>(gp.called) + off), "r"(bytes), "r"(bar)
+                         : "memory");
+    };
+    auto issue_next = [&]() {
+        if (iss_k == iss_spb) {
+            if (iss_ring != 0 && iss_batch >= n_batches) return;  // scheduler drained
+            iss_batch = claim();
+            iss_k = 0;
+            if (lane == 0) my_ring[iss_ring & (kBatchRing - 1)] = iss_batch;
+            ++iss_ring;
+            if (iss_batch >= n_batches) {
+                iss_spb = 0;
+                return;
+            }
+            iss_seg = iss_batch / nb_seg;
+            iss_lb = iss_batch - iss_seg * nb_seg;
+            const uint32_t r = P.seg[iss_seg].rounds;
+            iss_w16 = P.seg[iss_seg].g.wq * 16u;
+            iss_step_sites = SPS * r;
+            iss_spb = LPS / r;
+        }
+        if (lane == 0) issue(iss_stage);
+        ++iss_k;
+        iss_stage = (iss_stage + 1 == n_stages) ? 0 : iss_stage + 1;
+    };
+    for (uint32_t s = 0; s < n_stages; ++s) issue_next();
+    __syncwarp();
+
+    const uint32_t slot_in_round = lane >> LG;
+    const uint32_t phase = lane & (LPS - 1);
+    const uint32_t xfer_from = (lane & (SPS - 1)) << LG;
+    const uint32_t xfer_round = lane >> (5 - LG);
+
+    uint32_t con_ring = 0, stage = 0, parity = 0;
+    for (;;) {
+        const uint32_t gb = my_ring[con_ring & (kBatchRing - 1)];
+        ++con_ring;
+        if (gb >= n_batches) break;
+        // ---- consume side: this batch's group
+        const uint32_t sg = gb / nb_seg;
+        const uint32_t bl = gb - sg * nb_seg;
+        const SeqGroup &S = P.seg[sg];
+        const uint32_t w = S.g.wq, w16 = w * 16u, rounds = S.rounds;
+        const uint32_t step_sites = SPS * rounds, spb = LPS / rounds;
+        const uint32_t nit = (w + LPS - 1) / LPS;
+        const uint32_t nfull = nit - 1, last_cols = w - nfull * LPS;
+        const uint32_t pb = step_sites * w16;  // distance allele -> called plane inside a stage
+        const uint32_t b = G.b_lo + bl;
+        uint32_t site_ac = 0;
+        for (uint32_t k = 0; k < spb; ++k) {
+            {
+                const uint32_t bar = bar_base + 8u * stage;
+                uint32_t ok;
+                do {
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\t"
+                        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                        "selp.u32 %0, 1, 0, p;\n\t}"
+                        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+                } while (!ok);
+            }
+            const uint32_t sbase = smem_base + stage * stage_bytes;
+            const uint32_t v0 = b * 32 + k * step_sites;
+            auto round_body = [&](uint32_t r) {
+                const uint32_t site_local = r * SPS + slot_in_round;
+                const bool live = (v0 + site_local) < n_sites_total;
+                const uint32_t ra = sbase + site_local * w16;
+                uint32_t a = 0, c = 0;
+                if (live) {
+                    uint32_t p = ra + phase * 16u;
+#pragma unroll 2
+                    for (uint32_t j = 0; j < nfull; ++j) {
+                        a += fm_popc4(fm_lds128(p));
+                        if constexpr (HC) c += fm_popc4(fm_lds128(p + pb));
+                        p += LPS * 16u;
+                    }
+                    if (phase < last_cols) {
+                        a += fm_popc4(fm_lds128(p));
+                        if constexpr (HC) c += fm_popc4(fm_lds128(p + pb));
+                    }
+                }
+                uint32_t ac = HC ? (a | (c << 16)) : a;
+#pragma unroll
+                for (uint32_t o = LPS >> 1; o > 0; o >>= 1) ac += __shfl_xor_sync(FULL, ac, o);
+                const uint32_t t = __shfl_sync(FULL, ac, xfer_from);
+                if (xfer_round == k * rounds + r) site_ac = t;
+            };
+            if (rounds == 1) {
+                round_body(0);
+            } else {
+                for (uint32_t r = 0; r < rounds; r += 2) {
+                    round_body(r);
+                    round_body(r + 1);
+                }
+            }
+            __syncwarp();
+            issue_next();
+            stage = (stage + 1 == n_stages) ? 0 : stage + 1;
+            parity ^= (stage == 0);
+        }
+        // ---- batch epilogue: lane i <-> site 32b + i
+        {
+            const uint32_t alt = HC ? (site_ac & 0xffffu) : site_ac;
+            const uint32_t cnt = HC ? (site_ac >> 16) : S.g.cap;
+            const uint32_t v = b * 32 + lane;
+            const bool valid = (v >= G.v_lo) && (v < G.v_hi);
+            double pi_part = 0.0;
+            uint32_t seg = 0, unc = 0;
+            const uint32_t flags = S.div.site_flags ? __ldg(S.div.site_flags + bl) : 0u;
+            if (valid) fm_div_site(S.div, v, G.v_lo, cnt, alt, (flags >> lane) & 1u, pi_part, seg, unc);
+            const double s_pi = fm_warp_sum(pi_part);
+            const uint32_t s_u = fm_warp_sum_u(seg | (unc << 16));
+            if (lane == 0) {
+                S.div.part_pi[bl] = s_pi;
+                S.div.part_u[2 * bl] = s_u & 0xffffu;
+                S.div.part_u[2 * bl + 1] = s_u >> 16;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------ light kernels
 // Same per-site functions evaluated from cached count arrays (8 B per site and group).
 // One warp per batch of 32 sites so that the per-batch partials are bit-identical to the

@@ -152,6 +152,17 @@ fm_status fm_per_site_diversity(fm_group *g, size_t raw_haplotype_count, int64_t
                                 const int64_t *filtered_pos, size_t n_filtered, int64_t *pos_out,
                                 double *pi_out, double *theta_out, size_t capacity, size_t *n_out);
 
+/* The same for several groups of one matrix over one region (the inversion-orientation groups
+ * of a config entry, process.rs:1158): groups whose counts are not cached yet share ONE plane-pass
+ * launch that streams their planes one after the other.  pi_out / theta_out are
+ * [n_groups][capacity]; a group with fewer than two listed haplotypes (empty result in the
+ * reference, stats.rs:4675-4681) gets NaN rows.  Values are bit-identical to per-group calls. */
+fm_status fm_per_site_diversity_multi(fm_group *const *groups, const size_t *raw_haplotype_counts,
+                                      size_t n_groups, int64_t region_start, int64_t region_end,
+                                      const int64_t *mask_iv_or_null, size_t n_mask,
+                                      const int64_t *filtered_pos, size_t n_filtered, int64_t *pos_out,
+                                      double *pi_out, double *theta_out, size_t capacity, size_t *n_out);
+
 /* ---- Hudson FST / Dxy (stats.rs:2403-2611, 2969-3278, 3435-3641) ---- */
 typedef struct {
     double fst, d_xy, pi_pop1, pi_pop2, pi_xy_avg;

@@ -636,3 +636,56 @@ def test_inband_missing_equals_bitmap(max_allele):
         assert np.array_equal(alt, ref["alt"]) and np.array_equal(cnt, ref["called"]) and pis.value == ref["pi_sum"]
         L.fm_group_release(C.c_void_p(gh[0]))
         L.fm_matrix_release(mh)
+
+
+# ------------------------------------------------------------------ several groups in one launch
+@pytest.mark.parametrize("S,missing,n_groups", [(40, 0.1, 2), (700, 0.02, 3), (2504, 0.01, 2), (300, 0.0, 4)])
+def test_per_site_diversity_multi_equals_per_group_calls(S, missing, n_groups):
+    """fm_per_site_diversity_multi streams every group's planes in ONE persistent launch
+    (fm_k_plane_pass_seq); per-site values must equal the per-group calls bit for bit."""
+    import ctypes as C
+    from ferromic_b200 import _lib
+    from ferromic_b200.api import _Matrix
+    V = 3000 if S < 1000 else 900
+    g, pos, _ = make_cohort(V, S, missing_rate=missing, seed=S + n_groups)
+    miss = g < 0
+    alle = np.where(miss, 0, g).astype(np.uint8)
+    rng = np.random.default_rng(S)
+    lab = rng.integers(0, n_groups, size=(S, 2))
+    lab[: max(2, S // 20), :] = 0          # group 0 is never tiny
+    hap_lists = [[(s, k) for s in range(S) for k in (0, 1) if lab[s, k] == gi] for gi in range(n_groups)]
+    hap_lists[-1] = hap_lists[-1][: max(1, len(hap_lists[-1]) // 7)]  # a much narrower group (different row width)
+    region = (int(pos[37]), int(pos[-41]))
+    mask = np.array([[int(pos[100]), int(pos[180])], [int(pos[500]), int(pos[505])]], dtype=np.int64)
+    L = _lib.lib()
+    per_group = []
+    m1 = _Matrix(alle, miss, pos, max_allele=1)
+    for haps in hap_lists:
+        grp = m1.group(haps)
+        pp = np.zeros(V, dtype=np.int64)
+        pi, th = np.zeros(V), np.zeros(V)
+        n = C.c_size_t()
+        _lib.check(L.fm_per_site_diversity(grp.handle, len(haps), region[0], region[1], mask.ctypes.data, len(mask), None,
+                                           0, pp.ctypes.data, pi.ctypes.data, th.ctypes.data, V, C.byref(n)))
+        per_group.append((pp[:n.value].copy(), pi[:n.value].copy(), th[:n.value].copy()))
+    m2 = _Matrix(alle, miss, pos, max_allele=1)  # fresh groups: nothing cached, the fused launch is taken
+    groups = [m2.group(h) for h in hap_lists]
+    arr = (C.c_void_p * n_groups)(*[g_.handle.value for g_ in groups])
+    raw = (C.c_size_t * n_groups)(*[len(h) for h in hap_lists])
+    pp = np.zeros(V, dtype=np.int64)
+    pi, th = np.zeros((n_groups, V)), np.zeros((n_groups, V))
+    n = C.c_size_t()
+    L.fm_timings_reset()
+    _lib.check(L.fm_per_site_diversity_multi(arr, raw, n_groups, region[0], region[1], mask.ctypes.data, len(mask), None, 0,
+                                             pp.ctypes.data, pi.ctypes.data, th.ctypes.data, V, C.byref(n)))
+    tim = _lib.Timings()
+    L.fm_timings_get(C.byref(tim))
+    assert tim.stats_launches == 1, "the groups were expected to share one plane-pass launch"
+    for gi in range(n_groups):
+        rp, rpi, rth = per_group[gi]
+        assert n.value == len(rp) and np.array_equal(pp[:n.value], rp)
+        if len(hap_lists[gi]) < 2:
+            assert np.isnan(pi[gi, :n.value]).all()
+            continue
+        assert np.array_equal(pi[gi, :n.value], rpi, equal_nan=True)
+        assert np.array_equal(th[gi, :n.value], rth, equal_nan=True)

@@ -9,7 +9,7 @@ import json,sys
 cfg, rc = sys.argv[1], sys.argv[2]
 try:
     d=json.load(open("gpurun_out/b.json")); r=d["roofline"]
-    print(cfg, "rc", rc, "ms/step %.4f"%d["ms_per_step"], "value %.3e"%d["value"], [(g["haplotypes"], round(g["ms"],4), round(g["GBps"])) for g in r["per_group"]])
+    print(cfg, "rc", rc, "ms/step %.4f"%d["ms_per_step"], "value %.3e"%d["value"], r["per_group"] and [(g["haplotypes"], round(g["ms"],4), round(g["GBps"])) for g in r["per_group"]], round(r["achieved"]))
 except Exception as e:
     print(cfg, "rc", rc, "FAILED", open("gpurun_out/b.err").read()[-300:].replace("\n"," | "))
 PY
