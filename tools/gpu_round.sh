@@ -11,6 +11,6 @@ python bench.py > $O/bench.json 2> $O/bench.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_ref.json 2> $O/bench_ref.err; echo "ref rc=$?"
 if [ -z "$NO_NCU" ]; then
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv python bench.py --steps 2 --warmup 3 --skip-e2e --skip-cpu > $O/ncu_list.log 2>&1; echo "ncu list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:fm_k_plane_pass -s 8 -c 2 -o $O/prof_plane -f python bench.py --steps 2 --warmup 3 --skip-e2e --skip-cpu > $O/ncu_full.log 2>&1; echo "ncu full rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:fm_k_plane_pass -s 4 -c 1 -o $O/prof_plane -f python bench.py --steps 2 --warmup 3 --skip-e2e --skip-cpu > $O/ncu_full.log 2>&1; echo "ncu full rc=$?"
 fi
 cat $O/bench.json
