@@ -76,17 +76,32 @@ def cfg3(L, dev, scale):
     res = _lib.BenchResult()
     for it in (5, 30):
         _lib.check(L.fm_bench_hudson(g1, g2, it, C.byref(res)))
-    line("cfg3 Hudson FST/Dxy fused two-group pass (8-GPU shard of 10M sites), no bitmap", V, 2 * S, res.plane_ms_avg,
+    line("cfg3 Hudson per-site fused two-group kernel (NG=2; kept for reference, no longer the product path)", V, 2 * S, res.plane_ms_avg,
          res.plane_bytes_per_step, {"step_ms": res.step_ms_avg})
-    # end to end through the public entry point (counts cached by the fused pass, summaries path)
+    # the product path of fm_hudson_pair's first call: ONE sequential launch over both groups' planes
+    # (counts + summary scalars cached) + the light Hudson kernel on the counts; device time by events
     o = _lib.HudsonOutcome()
     n = C.c_size_t()
     Lr = int(pos[-1] - pos[0] + 1)
-    L.fm_timings_reset()
-    t0 = time.perf_counter()
-    _lib.check(L.fm_hudson_pair(g1, g2, Lr, Lr, 0, 0, 0, 0, S, S, C.byref(o), None, C.byref(n)))
-    dt = time.perf_counter() - t0
-    print(json.dumps({"config": "cfg3 fm_hudson_pair (first call: fused pass + summary scalars)", "wall_ms": dt * 1e3,
+    best = None
+    tim = _lib.Timings()
+    for rep in range(3):
+        for g in (g1, g2):
+            L.fm_group_release(g)
+        g1 = group_handle(L, m, [(s, k) for s in range(S // 2) for k in (0, 1)])
+        g2 = group_handle(L, m, [(s, k) for s in range(S // 2, S) for k in (0, 1)])
+        L.fm_timings_reset()
+        t0 = time.perf_counter()
+        _lib.check(L.fm_hudson_pair(g1, g2, Lr, Lr, 0, 0, 0, 0, S, S, C.byref(o), None, C.byref(n)))
+        dt = time.perf_counter() - t0
+        L.fm_timings_get(C.byref(tim))
+        if best is None or tim.stats_ms < best[0]:
+            best = (tim.stats_ms, dt * 1e3, tim.kernel_launches)
+    plane_bytes = res.plane_bytes_per_step
+    print(json.dumps({"config": "cfg3 fm_hudson_pair first call (sequential count launch over both groups + light "
+                                "Hudson kernel + reductions)", "device_ms": best[0], "wall_ms": best[1],
+                      "kernel_launches": best[2], "genotypes_per_s": V * 2 * S / (best[0] * 1e-3),
+                      "plane_GBps_incl_light_kernels": plane_bytes / (best[0] * 1e-3) / 1e9,
                       "fst": o.fst, "d_xy": o.d_xy}), flush=True)
     for g in (g1, g2):
         L.fm_group_release(g)
