@@ -59,7 +59,7 @@ EXPORTS = [
     "fm_per_site_diversity", "fm_per_site_diversity_multi", "fm_hudson_pair", "fm_hudson_dxy", "fm_partition_create",
     "fm_partition_release", "fm_wc_fst", "fm_wc_window_sums", "fm_fst_estimate_from_sums", "fm_adjusted_sequence_length", "fm_group_window_sums",
     "fm_hudson_window_sums", "fm_pi_from_sums", "fm_hudson_outcome_from_sums", "fm_comm_create", "fm_comm_export", "fm_comm_connect", "fm_comm_connect_local", "fm_comm_allgather", "fm_comm_set_timeout_ms",
-    "fm_comm_destroy", "fm_synth_fill", "fm_timings_reset", "fm_timings_get", "fm_bench_diversity",
+    "fm_comm_destroy", "fm_falsta_track", "fm_falsta_tracks", "fm_falsta_format_value", "fm_synth_fill", "fm_timings_reset", "fm_timings_get", "fm_bench_diversity",
     "fm_bench_hudson",
 ]
 
@@ -123,6 +123,9 @@ def lib() -> C.CDLL:
     L.fm_hudson_window_sums.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, vp, vp]
     L.fm_pi_from_sums.argtypes = [dbl, u64, i64, sz, C.POINTER(dbl)]
     L.fm_hudson_outcome_from_sums.argtypes = [C.POINTER(HudsonSums), i64, sz, sz, C.POINTER(HudsonOutcome)]
+    L.fm_falsta_track.argtypes = [vp, vp, sz, i64, i64, C.c_int, vp, sz, C.POINTER(sz)]
+    L.fm_falsta_tracks.argtypes = [vp, vp, sz, sz, i64, i64, C.c_int, vp, sz, vp, C.POINTER(sz)]
+    L.fm_falsta_format_value.argtypes = [dbl, C.c_int, vp, sz, C.POINTER(sz)]
     L.fm_synth_fill.argtypes = [vp, vp, sz, sz, sz, u64, u64, vp, dbl, dbl]
     L.fm_timings_get.argtypes = [C.POINTER(Timings)]
     L.fm_bench_diversity.argtypes = [C.POINTER(vp), sz, C.c_int, vp, sz, C.c_int, vp, C.POINTER(BenchResult)]

@@ -6,6 +6,9 @@
 #include "fm_wc.cuh"
 #include "fm_comm.cuh"
 #include "fm_multi.cuh"
+#include "fm_falsta.cuh"
+
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <atomic>
@@ -2727,6 +2730,87 @@ fm_status fm_comm_destroy(fm_comm *c) {
     cudaFree(c->d_gathered);
     delete c;
     return FM_OK;
+}
+
+// ------------------------------------------------------------------------------------ FALSTA track bodies
+fm_status fm_falsta_format_value(double value, int mode, char *buf, size_t capacity, size_t *len_out) {
+    if (!buf || !len_out || capacity < 56) return FM_ERR_INVALID_ARG;
+    if (mode != FM_FALSTA_DIVERSITY && mode != FM_FALSTA_FST) return FM_ERR_INVALID_ARG;
+    *len_out = fm::fm_falsta_token(value, mode, buf);  // the same __host__ __device__ routine the kernels run
+    return FM_OK;
+}
+
+fm_status fm_falsta_tracks(const int64_t *pos1, const double *values, size_t n, size_t n_tracks, int64_t region_start,
+                           int64_t region_end, int mode, char *out, size_t capacity, size_t *line_len,
+                           size_t *len_out) {
+    return guarded([&] {
+        if (!len_out) fail(FM_ERR_INVALID_ARG, "len_out is NULL");
+        *len_out = 0;
+        if (n_tracks == 0) return;
+        if (n && (!pos1 || !values)) fail(FM_ERR_INVALID_ARG, "record arrays are NULL");
+        if (mode != FM_FALSTA_DIVERSITY && mode != FM_FALSTA_FST) fail(FM_ERR_INVALID_ARG, "unknown track mode");
+        if (n >= (1ull << 31)) fail(FM_ERR_UNSUPPORTED, "more than 2^31 records per track");
+        if (n_tracks > 64) fail(FM_ERR_UNSUPPORTED, "more than 64 tracks per call");
+        require_device();
+        CK(cudaSetDevice(t_device));
+        // ZeroBasedHalfOpen::from_1based_inclusive (process.rs:193-206)
+        int64_t s1 = region_start < 1 ? 1 : region_start;
+        int64_t e1 = region_end < s1 ? s1 : region_end;
+        const uint64_t rs = (uint64_t)(s1 - 1), re = (uint64_t)e1;
+        const uint64_t L = re - rs;  // >= 1 by construction
+        const uint64_t T = L * n_tracks;
+        DevBuf<int> d_idx(L);
+        DevBuf<uint32_t> d_len(T);
+        DevBuf<uint64_t> d_off(T);
+        DevBuf<int64_t> d_pos(std::max<size_t>(n, 1));
+        DevBuf<double> d_val(std::max<size_t>(n * n_tracks, 1));
+        CK(cudaMemsetAsync(d_idx.p, 0xFF, L * sizeof(int), stream()));
+        h2d(d_pos.p, pos1, n * 8, stream());
+        h2d(d_val.p, values, n * n_tracks * 8, stream());
+        const int dev_sms = sm_count(t_device);
+        if (n) {
+            const uint32_t b = (uint32_t)std::min<uint64_t>((n + 255) / 256, 8ull * dev_sms);
+            fm::fm_k_falsta_scatter<<<b, 256, 0, stream()>>>(d_pos.p, (uint32_t)n, rs, re, d_idx.p);
+            CK(cudaGetLastError());
+            g_launches++;
+        }
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>((T + 255) / 256, 16ull * dev_sms);
+        fm::fm_k_falsta_lengths<<<blocks, 256, 0, stream()>>>(d_idx.p, d_val.p, n, L, (uint32_t)n_tracks, mode,
+                                                               d_len.p);
+        CK(cudaGetLastError());
+        g_launches++;
+        size_t tmp_bytes = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_len.p, d_off.p, (int64_t)T, stream()));
+        DevBuf<uint8_t> d_tmp(std::max<size_t>(tmp_bytes, 16));
+        CK(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, d_len.p, d_off.p, (int64_t)T, stream()));
+        // line t starts at off[t*L]; the call ends at off[T-1] + len[T-1]
+        std::vector<uint64_t> starts(n_tracks + 1);
+        for (size_t t = 0; t < n_tracks; ++t)
+            CK(cudaMemcpyAsync(&starts[t], d_off.p + t * L, 8, cudaMemcpyDeviceToHost, stream()));
+        uint32_t last_len = 0;
+        CK(cudaMemcpyAsync(&starts[n_tracks], d_off.p + (T - 1), 8, cudaMemcpyDeviceToHost, stream()));
+        CK(cudaMemcpyAsync(&last_len, d_len.p + (T - 1), 4, cudaMemcpyDeviceToHost, stream()));
+        CK(cudaStreamSynchronize(stream()));
+        const uint64_t total = starts[n_tracks] + last_len;
+        starts[n_tracks] = total + 1;  // as if a separator followed the last line too
+        if (line_len)
+            for (size_t t = 0; t < n_tracks; ++t) line_len[t] = (size_t)(starts[t + 1] - starts[t] - 1);
+        *len_out = (size_t)total;
+        if (!out) return;  // length query
+        if (total > capacity) fail(FM_ERR_INVALID_ARG, "output capacity too small for the track lines");
+        DevBuf<char> d_out(std::max<uint64_t>(total, 1));
+        fm::fm_k_falsta_write<<<blocks, 256, 0, stream()>>>(d_idx.p, d_val.p, n, L, (uint32_t)n_tracks, mode, d_off.p,
+                                                             d_out.p);
+        CK(cudaGetLastError());
+        g_launches++;
+        CK(cudaMemcpyAsync(out, d_out.p, total, cudaMemcpyDeviceToHost, stream()));
+        CK(cudaStreamSynchronize(stream()));
+    });
+}
+
+fm_status fm_falsta_track(const int64_t *pos1, const double *values, size_t n, int64_t region_start,
+                          int64_t region_end, int mode, char *out, size_t capacity, size_t *len_out) {
+    return fm_falsta_tracks(pos1, values, n, 1, region_start, region_end, mode, out, capacity, nullptr, len_out);
 }
 
 // ------------------------------------------------------------------------------------ synthetic cohorts

@@ -295,6 +295,29 @@ fm_status fm_comm_allgather(fm_comm *c, const void *local_words, size_t n_words,
 fm_status fm_comm_set_timeout_ms(fm_comm *c, uint64_t milliseconds); /* default 5000 */
 fm_status fm_comm_destroy(fm_comm *c);
 
+/* ---- FALSTA per-site track bodies (process.rs:3740-4041) ----
+ * A track body is ONE comma-joined line of region_len tokens (region is 1-based inclusive, clamped
+ * like ZeroBasedHalfOpen::from_1based_inclusive, process.rs:193-206): positions without a record
+ * get the default token, a record's value prints as NaN -> "NA", 0.0 -> "0", otherwise Rust's
+ * `{:.6}` (exactly, incl. round-half-even on the binary value); the last record at a position
+ * wins (process.rs:3782-3795 overwrites line[idx] in record order).
+ *   FM_FALSTA_DIVERSITY  default "0"   (append_diversity_falsta: pi / theta tracks, :3777-3793)
+ *   FM_FALSTA_FST        default "NA", +-inf -> "Infinity" / "-Infinity"  (append_fst_falsta, :3842-3856)
+ * pos1 are 1-based positions as in the per-site outputs.  fm_falsta_tracks renders n_tracks lines
+ * that share the record positions (values[t*n + i] is record i of track t; e.g. pi and theta of one
+ * group, or FST / numerator / denominator), separated by '\n'; line_len[t] (may be NULL) receives
+ * each line's length.  out == NULL only queries the lengths; there is no trailing newline and no
+ * terminating NUL.  The lines are rendered by the GPU (scatter -> token lengths -> scan -> write);
+ * fm_falsta_format_value is the host instance of the same token routine (buf >= 56 bytes). */
+#define FM_FALSTA_DIVERSITY 0
+#define FM_FALSTA_FST 1
+fm_status fm_falsta_track(const int64_t *pos1, const double *values, size_t n, int64_t region_start,
+                          int64_t region_end, int mode, char *out, size_t capacity, size_t *len_out);
+fm_status fm_falsta_tracks(const int64_t *pos1, const double *values, size_t n, size_t n_tracks,
+                           int64_t region_start, int64_t region_end, int mode, char *out, size_t capacity,
+                           size_t *line_len, size_t *len_out);
+fm_status fm_falsta_format_value(double value, int mode, char *buf, size_t capacity, size_t *len_out);
+
 /* ---- synthetic cohorts for benchmarks and full-size parity tests ----
  * Fills a device-resident u8 matrix (reference layout) and, when d_missing != NULL, its packed
  * missing bitmap with a counter-based generator: entry (site, column) is a pure integer function
