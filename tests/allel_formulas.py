@@ -40,3 +40,35 @@ def hudson_fst(ac1, ac2):
     within = (mean_pairwise_difference(ac1) + mean_pairwise_difference(ac2)) / 2
     between = mean_pairwise_difference_between(ac1, ac2)
     return between - within, between
+
+
+def weir_cockerham_ab_haploid(ac_by_pop):
+    """Weir & Cockerham (1984) eqs. 2-3 as scikit-allel's `weir_cockerham_fst` evaluates them
+    (a, b summed over alleles), for haploid observations: observed heterozygosity h-bar = 0, so
+    c = 0.  `ac_by_pop` = list over populations of allele-count arrays [V, n_alleles].
+    Populations without called haplotypes at a site are left out of that site (r counts the rest).
+    Returns per-site (a, b) summed over alleles.  Independent of the oracle's code."""
+    ac = np.stack([np.asarray(x, dtype=np.float64) for x in ac_by_pop])  # [P, V, A]
+    n = ac.sum(axis=2)  # [P, V]
+    P, V, A = ac.shape
+    a_out, b_out = np.zeros(V), np.zeros(V)
+    for v in range(V):
+        use = n[:, v] > 0
+        r = int(use.sum())
+        if r < 2:
+            continue
+        ni = n[use, v]
+        n_bar = ni.sum() / r
+        if n_bar <= 1:
+            continue
+        n_c = (r * n_bar - (ni ** 2).sum() / (r * n_bar)) / (r - 1)
+        for al in range(A):
+            p = ac[use, v, al] / ni
+            p_bar = (ni * p).sum() / (r * n_bar)
+            s2 = (ni * (p - p_bar) ** 2).sum() / ((r - 1) * n_bar)
+            h_bar = 0.0
+            a = (n_bar / n_c) * (s2 - (1 / (n_bar - 1)) * (p_bar * (1 - p_bar) - (r - 1) / r * s2 - h_bar / 4))
+            b = (n_bar / (n_bar - 1)) * (p_bar * (1 - p_bar) - (r - 1) / r * s2 - (2 * n_bar - 1) / (4 * n_bar) * h_bar)
+            a_out[v] += a
+            b_out[v] += b
+    return a_out, b_out

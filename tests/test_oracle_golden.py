@@ -291,6 +291,47 @@ def test_wc_derived_kats():
     assert list(r["pop_sizes"][0]) == [6, 2]
 
 
+def test_wc_matches_published_weir_cockerham_1984():
+    """Independent check of the restatement: the reference's (a, b) are Weir & Cockerham (1984) eqs. 2-3
+    with h-bar = 0 summed over alleles (stats.rs:2033-2127 comments; `1 - c^2/(r-1)` with c^2 over r equals
+    the published n_c / n-bar).  tests/allel_formulas.py evaluates the published form the way scikit-allel's
+    weir_cockerham_fst does; unequal group sizes, missing calls, a third allele.  1e-9 relative."""
+    from tests import allel_formulas as af
+    rng = np.random.default_rng(1984)
+    Vn, S, G = 400, 37, 3
+    freq = rng.beta(0.7, 0.7, size=Vn)
+    g = rng.binomial(1, freq[:, None, None], size=(Vn, S, 2)).astype(np.int64)
+    g[(rng.random(g.shape) < 0.03) & (g == 1)] = 2  # some tri-allelic sites
+    missing = rng.random((Vn, S)) < 0.08  # whole-sample missing calls (sparse semantics)
+    label = np.array([0] * 9 + [1] * 17 + [2] * 11)
+    variants = [V(10 + 3 * v, [None if missing[v, s] else [int(g[v, s, 0]), int(g[v, s, 1])] for s in range(S)])
+                for v in range(Vn)]
+    vs = orc.variants_from_python(variants)
+    r = orc.wc_fst(vs, label, label, G, (0, 10 + 3 * Vn))
+    assert r["n_sites"] == Vn
+    acs = []
+    for k in range(G):
+        ac = np.zeros((Vn, 3))
+        for al in range(3):
+            ac[:, al] = ((g[:, label == k, :] == al) & ~missing[:, label == k, None]).sum(axis=(1, 2))
+        acs.append(ac)
+    a, b = af.weir_cockerham_ab_haploid(acs)
+    scale = np.maximum(np.abs(a) + np.abs(b), 1e-300)
+    assert np.max(np.abs(r["a"] - a) / scale) < 1e-9
+    assert np.max(np.abs(r["b"] - b) / scale) < 1e-9
+    assert r["overall"]["state"] == "calculable"
+    assert r["overall"]["value"] == pytest.approx(a.sum() / (a.sum() + b.sum()), rel=1e-9)
+    # every pair is the same estimator restricted to two populations
+    k = 0
+    for i in range(G):
+        for j in range(i + 1, G):
+            pa, pb = af.weir_cockerham_ab_haploid([acs[i], acs[j]])
+            assert np.allclose(r["pair_a"][:, k], pa, rtol=1e-9, atol=1e-12)
+            assert np.allclose(r["pair_b"][:, k], pb, rtol=1e-9, atol=1e-12)
+            assert r["pairs"][k]["value"] == pytest.approx(pa.sum() / (pa.sum() + pb.sum()), rel=1e-9)
+            k += 1
+
+
 def test_wc_state_rules():
     lr = [0, 0, 1, 1]
     # all samples missing -> InsufficientData{sites_attempted: 1}, empty maps (stats.rs:1987-2001)
