@@ -50,6 +50,14 @@ class BenchResult(C.Structure):
                 ("group_ms_avg", C.c_float * 8), ("group_bytes", C.c_uint64 * 8), ("comm_ms_avg", C.c_float)]
 
 
+class VcfInfo(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in (
+        "n_lines", "n_variants", "n_errors", "n_samples", "max_ploidy", "total_variants", "filtered_variants",
+        "filtered_due_to_mask", "filtered_due_to_allow", "missing_data_variants", "low_gq_variants", "mnp_variants",
+        "total_data_points", "missing_data_points", "n_positions_with_missing", "n_filtered_positions")] + [
+        ("h2d_ms", C.c_float), ("index_ms", C.c_float), ("parse_ms", C.c_float)]
+
+
 EXPORTS = [
     "fm_last_error", "fm_version", "fm_device_count", "fm_set_device", "fm_synchronize", "fm_trim_pool",
     "fm_matrix_create", "fm_matrix_create_inband", "fm_matrix_create_device", "fm_matrix_retain", "fm_matrix_release",
@@ -59,7 +67,9 @@ EXPORTS = [
     "fm_per_site_diversity", "fm_per_site_diversity_multi", "fm_hudson_pair", "fm_hudson_dxy", "fm_partition_create",
     "fm_partition_release", "fm_wc_fst", "fm_wc_window_sums", "fm_fst_estimate_from_sums", "fm_adjusted_sequence_length", "fm_group_window_sums",
     "fm_hudson_window_sums", "fm_pi_from_sums", "fm_hudson_outcome_from_sums", "fm_comm_create", "fm_comm_export", "fm_comm_connect", "fm_comm_connect_local", "fm_comm_allgather", "fm_comm_set_timeout_ms",
-    "fm_comm_destroy", "fm_falsta_track", "fm_falsta_tracks", "fm_falsta_format_value", "fm_synth_fill", "fm_timings_reset", "fm_timings_get", "fm_bench_diversity",
+    "fm_comm_destroy", "fm_falsta_track", "fm_falsta_tracks", "fm_falsta_format_value", "fm_vcf_parse", "fm_vcf_parse_device", "fm_vcf_batch_info",
+    "fm_vcf_batch_variants", "fm_vcf_batch_genotypes", "fm_vcf_batch_positions", "fm_vcf_batch_errors", "fm_vcf_batch_matrix",
+    "fm_vcf_batch_release", "fm_synth_fill", "fm_timings_reset", "fm_timings_get", "fm_bench_diversity",
     "fm_bench_hudson",
 ]
 
@@ -126,6 +136,18 @@ def lib() -> C.CDLL:
     L.fm_falsta_track.argtypes = [vp, vp, sz, i64, i64, C.c_int, vp, sz, C.POINTER(sz)]
     L.fm_falsta_tracks.argtypes = [vp, vp, sz, sz, i64, i64, C.c_int, vp, sz, vp, C.POINTER(sz)]
     L.fm_falsta_format_value.argtypes = [dbl, C.c_int, vp, sz, C.POINTER(sz)]
+    u16 = C.c_uint16
+    L.fm_vcf_parse.argtypes = [C.c_char_p, sz, C.c_char_p, vp, sz, vp, sz, u16, C.c_int, vp, sz, C.c_int, vp, sz, sz,
+                               C.POINTER(vp)]
+    L.fm_vcf_parse_device.argtypes = [vp, sz, C.c_char, C.c_char_p, vp, sz, vp, sz, u16, C.c_int, vp, sz, C.c_int, vp,
+                                      sz, sz, C.POINTER(vp)]
+    L.fm_vcf_batch_info.argtypes = [vp, C.POINTER(VcfInfo)]
+    L.fm_vcf_batch_variants.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.fm_vcf_batch_genotypes.argtypes = [vp, vp]
+    L.fm_vcf_batch_positions.argtypes = [vp, C.c_int, vp, sz]
+    L.fm_vcf_batch_errors.argtypes = [vp, vp, vp, vp, sz]
+    L.fm_vcf_batch_matrix.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.fm_vcf_batch_release.argtypes = [vp]
     L.fm_synth_fill.argtypes = [vp, vp, sz, sz, sz, u64, u64, vp, dbl, dbl]
     L.fm_timings_get.argtypes = [C.POINTER(Timings)]
     L.fm_bench_diversity.argtypes = [C.POINTER(vp), sz, C.c_int, vp, sz, C.c_int, vp, C.POINTER(BenchResult)]

@@ -7,6 +7,7 @@
 #include "fm_comm.cuh"
 #include "fm_multi.cuh"
 #include "fm_falsta.cuh"
+#include "fm_vcf.cuh"
 
 #include <cub/device/device_scan.cuh>
 
@@ -18,6 +19,7 @@
 #include <cstring>
 #include <limits>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -2811,6 +2813,457 @@ fm_status fm_falsta_tracks(const int64_t *pos1, const double *values, size_t n, 
 fm_status fm_falsta_track(const int64_t *pos1, const double *values, size_t n, int64_t region_start,
                           int64_t region_end, int mode, char *out, size_t capacity, size_t *len_out) {
     return fm_falsta_tracks(pos1, values, n, 1, region_start, region_end, mode, out, capacity, nullptr, len_out);
+}
+
+// ------------------------------------------------------------------------------------ VCF parse/filter stage
+struct fm_vcf_batch {
+    int device = 0;
+    size_t n_lines = 0, S = 0, P = 0, n_rows = 0;
+    uint8_t *d_gt = nullptr;       // [n_rows][S][P], rows in line order of the variant-producing lines
+    uint32_t *d_order = nullptr;   // [n_variants] row index per output variant
+    std::vector<fm::VcfLine> var;  // per output variant (output order)
+    std::vector<uint32_t> order;   // row index per output variant
+    std::vector<int64_t> pos_missing, pos_filtered;
+    std::vector<uint64_t> err_line;
+    std::vector<int32_t> err_code;
+    std::vector<int64_t> err_aux;
+    fm_vcf_info info{};
+};
+
+namespace {
+
+// (start, end) pairs -> merged, sorted, disjoint unsigned [s, e); `any` over half-open intervals only
+// depends on their union.  as_usize: the mask path casts both ends to usize (process.rs:4566-4577).
+std::vector<uint64_t> vcf_normalise_intervals(const int64_t *iv, size_t n, bool as_usize) {
+    std::vector<std::pair<uint64_t, uint64_t>> v;
+    v.reserve(n);
+    for (size_t i = 0; i < n; ++i) {
+        const int64_t s = iv[2 * i], e = iv[2 * i + 1];
+        uint64_t us, ue;
+        if (as_usize) {
+            us = (uint64_t)s;
+            ue = (uint64_t)e;
+        } else {  // pos >= s && pos < e with pos >= 0
+            if (e <= 0) continue;
+            us = s < 0 ? 0 : (uint64_t)s;
+            ue = (uint64_t)e;
+        }
+        if (us < ue) v.emplace_back(us, ue);
+    }
+    std::sort(v.begin(), v.end());
+    std::vector<uint64_t> out;
+    for (auto &p : v) {
+        if (!out.empty() && p.first <= out[out.size() - 1]) {
+            if (p.second > out[out.size() - 1]) out[out.size() - 1] = p.second;
+        } else {
+            out.push_back(p.first);
+            out.push_back(p.second);
+        }
+    }
+    return out;
+}
+
+__global__ void __launch_bounds__(256)
+fm_k_vcf_rowflag(const fm::VcfLine *__restrict__ recs, uint32_t n, uint32_t *__restrict__ flag) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = (recs[i].status == fm::VCF_CAND && !(recs[i].indel & 1)) ? 1u : 0u;
+}
+
+void vcf_parse_impl(const uint8_t *d_text, size_t n_bytes, char last_byte, const char *chr, const int64_t *regions,
+                    size_t n_regions, const uint32_t *kept, size_t n_kept, uint16_t min_gq, int allow_mode,
+                    const int64_t *allow, size_t n_allow, int mask_mode, const int64_t *mask, size_t n_mask,
+                    size_t max_ploidy, float h2d_ms, fm_vcf_batch **out) {
+    if (!chr) fail(FM_ERR_INVALID_ARG, "chr is NULL");
+    if (n_regions && !regions) fail(FM_ERR_INVALID_ARG, "regions is NULL");
+    if (n_kept && !kept) fail(FM_ERR_INVALID_ARG, "kept_col_indices is NULL");
+    if (max_ploidy < 1 || max_ploidy > (size_t)fm::VCF_MAX_PLOIDY) fail(FM_ERR_INVALID_ARG, "max_ploidy must be 1..8");
+    if ((unsigned)allow_mode > 2u || (unsigned)mask_mode > 2u) fail(FM_ERR_INVALID_ARG, "unknown allow/mask mode");
+    if ((allow_mode == FM_VCF_INTERVALS && n_allow && !allow) || (mask_mode == FM_VCF_INTERVALS && n_mask && !mask))
+        fail(FM_ERR_INVALID_ARG, "interval list is NULL");
+    for (size_t i = 0; i < n_kept; ++i) {
+        if (kept[i] < 9) fail(FM_ERR_INVALID_ARG, "kept column index below 9 (the first sample column)");
+        if (i && kept[i] <= kept[i - 1]) fail(FM_ERR_INVALID_ARG, "kept_col_indices must be strictly increasing");
+    }
+    if (n_kept && kept[n_kept - 1] >= (1u << 30)) fail(FM_ERR_UNSUPPORTED, "column index too large");
+    for (size_t i = 1; i < n_regions; ++i)
+        if (regions[2 * i] < regions[2 * i - 2] || regions[2 * i + 1] < regions[2 * i - 1])
+            fail(FM_ERR_INVALID_ARG, "regions must be sorted (process_vcf passes merged, sorted regions)");
+
+    fm::VcfParams P{};
+    {  // normalize_chr_prefix(chr.trim())
+        std::string c(chr);
+        auto ws = [](char x) { return x == ' ' || (x >= 9 && x <= 13); };
+        size_t a = 0, b = c.size();
+        while (a < b && ws(c[a])) ++a;
+        while (b > a && ws(c[b - 1])) --b;
+        c = c.substr(a, b - a);
+        if (c.rfind("chr", 0) == 0 || c.rfind("Chr", 0) == 0 || c.rfind("CHR", 0) == 0) c = c.substr(3);
+        if (c.size() > 63) fail(FM_ERR_INVALID_ARG, "chromosome name longer than 63 bytes");
+        memcpy(P.chr, c.data(), c.size());
+        P.chr_len = (uint32_t)c.size();
+    }
+    auto b = std::unique_ptr<fm_vcf_batch, void (*)(fm_vcf_batch *)>(new fm_vcf_batch(), [](fm_vcf_batch *x) {
+        fm_vcf_batch_release(x);
+    });
+    b->device = t_device;
+    b->S = n_kept;
+    b->P = max_ploidy;
+    b->info.n_samples = n_kept;
+    b->info.max_ploidy = max_ploidy;
+    b->info.h2d_ms = h2d_ms;
+    if (n_bytes == 0) {
+        *out = b.release();
+        return;
+    }
+    const int sms = sm_count(t_device);
+    Timer t_index, t_parse;
+    // ---- line index
+    const uint64_t n16 = (n_bytes + 15) / 16;
+    const uint32_t n_tiles = (uint32_t)((n16 + 255) / 256);
+    DevBuf<uint32_t> d_tile(4 * (size_t)n_tiles);  // nl, tab, nl_before, tab_before
+    uint32_t *t_nl = d_tile.p, *t_tab = d_tile.p + n_tiles, *t_nlb = d_tile.p + 2 * (size_t)n_tiles,
+             *t_tabb = d_tile.p + 3 * (size_t)n_tiles;
+    t_index.start();
+    fm::fm_k_vcf_count<<<n_tiles, 256, 0, stream()>>>(reinterpret_cast<const uint4 *>(d_text), n16, t_nl, t_tab);
+    CK(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, t_nl, t_nlb, (int)n_tiles, stream()));
+    DevBuf<uint8_t> d_tmp(std::max<size_t>(tmp_bytes, 16));
+    CK(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, t_nl, t_nlb, (int)n_tiles, stream()));
+    CK(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, t_tab, t_tabb, (int)n_tiles, stream()));
+    uint32_t last4[4];
+    CK(cudaMemcpyAsync(&last4[0], t_nl + (n_tiles - 1), 4, cudaMemcpyDeviceToHost, stream()));
+    CK(cudaMemcpyAsync(&last4[1], t_tab + (n_tiles - 1), 4, cudaMemcpyDeviceToHost, stream()));
+    CK(cudaMemcpyAsync(&last4[2], t_nlb + (n_tiles - 1), 4, cudaMemcpyDeviceToHost, stream()));
+    CK(cudaMemcpyAsync(&last4[3], t_tabb + (n_tiles - 1), 4, cudaMemcpyDeviceToHost, stream()));
+    CK(cudaStreamSynchronize(stream()));
+    const uint32_t nl_total = last4[0] + last4[2], tab_total = last4[1] + last4[3];
+    const size_t n_lines = (size_t)nl_total + (last_byte != '\n' ? 1 : 0);
+    DevBuf<uint32_t> d_ls(n_lines + 1), d_tb(n_lines + 1);
+    {
+        const uint32_t zero = 0, endv[2] = {(uint32_t)n_bytes, tab_total};
+        CK(cudaMemcpyAsync(d_ls.p, &zero, 4, cudaMemcpyHostToDevice, stream()));
+        CK(cudaMemcpyAsync(d_tb.p, &zero, 4, cudaMemcpyHostToDevice, stream()));
+        // an unterminated last line ends at the end of the text (a terminated one wrote the same values)
+        CK(cudaMemcpyAsync(d_ls.p + n_lines, &endv[0], 4, cudaMemcpyHostToDevice, stream()));
+        CK(cudaMemcpyAsync(d_tb.p + n_lines, &endv[1], 4, cudaMemcpyHostToDevice, stream()));
+    }
+    fm::fm_k_vcf_index<<<n_tiles, 256, 0, stream()>>>(reinterpret_cast<const uint4 *>(d_text), n16, t_nlb, t_tabb,
+                                                      d_ls.p, d_tb.p);
+    CK(cudaGetLastError());
+    t_index.stop();
+    g_launches += 2;
+    // ---- parameters
+    std::vector<uint64_t> allow_n, mask_n;
+    if (allow_mode == FM_VCF_INTERVALS) allow_n = vcf_normalise_intervals(allow, n_allow, false);
+    if (mask_mode == FM_VCF_INTERVALS) mask_n = vcf_normalise_intervals(mask, n_mask, true);
+    DevBuf<int64_t> d_regions(std::max<size_t>(2 * n_regions, 2));
+    DevBuf<uint64_t> d_allow(std::max<size_t>(allow_n.size(), 2)), d_mask(std::max<size_t>(mask_n.size(), 2));
+    d_regions.upload(regions, 2 * n_regions);
+    d_allow.upload(allow_n.data(), allow_n.size());
+    d_mask.upload(mask_n.data(), mask_n.size());
+    const int32_t max_idx = n_kept ? (int32_t)kept[n_kept - 1] : -1;
+    std::vector<int32_t> col2slot((size_t)(max_idx + 1), -1);
+    for (size_t i = 0; i < n_kept; ++i) col2slot[kept[i]] = (int32_t)i;
+    DevBuf<int32_t> d_c2s(std::max<size_t>(col2slot.size(), 1));
+    d_c2s.upload(col2slot.data(), col2slot.size());
+    P.text = d_text;
+    P.line_start = d_ls.p;
+    P.tabs_before = d_tb.p;
+    P.n_lines = (uint32_t)n_lines;
+    P.regions = d_regions.p;
+    P.n_regions = (uint32_t)n_regions;
+    P.allow_mode = allow_mode;
+    P.mask_mode = mask_mode;
+    P.allow = d_allow.p;
+    P.mask = d_mask.p;
+    P.n_allow = (uint32_t)(allow_n.size() / 2);
+    P.n_mask = (uint32_t)(mask_n.size() / 2);
+    P.max_idx = max_idx;
+    P.min_gq = min_gq;
+    P.n_samples = (uint32_t)n_kept;
+    P.max_ploidy = (uint32_t)max_ploidy;
+    P.col2slot = d_c2s.p;
+    // ---- fixed fields, row assignment, sample fields
+    DevBuf<fm::VcfLine> d_recs(n_lines);
+    DevBuf<uint32_t> d_flag(n_lines), d_row(n_lines);
+    t_parse.start();
+    {
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_lines + 7) / 8, 32ull * sms);
+        fm::fm_k_vcf_fixed<<<blocks, 256, 0, stream()>>>(P, d_recs.p);
+        CK(cudaGetLastError());
+        fm_k_vcf_rowflag<<<(uint32_t)((n_lines + 255) / 256), 256, 0, stream()>>>(d_recs.p, (uint32_t)n_lines, d_flag.p);
+        CK(cudaGetLastError());
+    }
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_flag.p, d_row.p, (int)n_lines, stream()));
+    DevBuf<uint8_t> d_tmp2(std::max<size_t>(tmp_bytes, 16));
+    CK(cub::DeviceScan::ExclusiveSum(d_tmp2.p, tmp_bytes, d_flag.p, d_row.p, (int)n_lines, stream()));
+    uint32_t lastrow[2];
+    CK(cudaMemcpyAsync(&lastrow[0], d_flag.p + (n_lines - 1), 4, cudaMemcpyDeviceToHost, stream()));
+    CK(cudaMemcpyAsync(&lastrow[1], d_row.p + (n_lines - 1), 4, cudaMemcpyDeviceToHost, stream()));
+    CK(cudaStreamSynchronize(stream()));
+    const size_t n_rows = (size_t)lastrow[0] + lastrow[1];
+    const size_t row_bytes = n_kept * max_ploidy;
+    b->n_lines = n_lines;
+    b->n_rows = n_rows;
+    b->d_gt = static_cast<uint8_t *>(dev_alloc(std::max<size_t>(n_rows * row_bytes, 16)));
+    {
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>(n_lines, 16ull * sms);
+        fm::fm_k_vcf_samples<<<blocks, 256, 0, stream()>>>(P, d_recs.p, d_row.p, b->d_gt);
+        CK(cudaGetLastError());
+    }
+    t_parse.stop();
+    g_launches += 3;
+    // ---- host: statistics, errors, output order
+    std::vector<fm::VcfLine> recs(n_lines);
+    std::vector<uint32_t> rows(n_lines);
+    d_recs.download(recs.data(), n_lines);
+    d_row.download(rows.data(), n_lines);
+    CK(cudaStreamSynchronize(stream()));
+    fm_vcf_info &I = b->info;
+    I.n_lines = n_lines;
+    I.index_ms = t_index.ms();
+    I.parse_ms = t_parse.ms();
+    std::vector<uint32_t> keep;  // line indices of the variants
+    for (size_t li = 0; li < n_lines; ++li) {
+        const fm::VcfLine &r = recs[li];
+        if (r.status == fm::VCF_SKIP) continue;
+        if (r.status != fm::VCF_CAND) {
+            b->err_line.push_back(li);
+            b->err_code.push_back(r.status);
+            // field count for the two format errors, the offending 1-based POS otherwise
+            b->err_aux.push_back(r.status <= fm::VCF_E_MISSING_COLUMN ? r.pos0 : (int64_t)((uint64_t)r.pos0 + 1));
+            continue;
+        }
+        const bool indel = r.indel & 1;
+        I.total_variants++;
+        if (r.flags & 2) I.filtered_due_to_allow++;
+        if (r.flags & 1) I.filtered_due_to_mask++;
+        if (r.indel & 2) I.mnp_variants++;
+        if (r.flags & 4) I.low_gq_variants++;
+        if (r.flags & 8) I.missing_data_variants++;
+        I.total_data_points += n_kept;
+        I.missing_data_points += r.missing_points;
+        if (r.missing_points) b->pos_missing.push_back(r.pos0);
+        if (r.flags != 0 || indel) {
+            I.filtered_variants++;
+            b->pos_filtered.push_back(r.pos0);
+        }
+        if (!indel) keep.push_back((uint32_t)li);
+    }
+    auto uniq = [](std::vector<int64_t> &v) {
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());
+    };
+    uniq(b->pos_missing);
+    uniq(b->pos_filtered);
+    I.n_positions_with_missing = b->pos_missing.size();
+    I.n_filtered_positions = b->pos_filtered.size();
+    I.n_errors = b->err_line.size();
+    // sort by position (stable), ties by the variant's compressed genotype bytes (process.rs:4377-4386)
+    std::stable_sort(keep.begin(), keep.end(), [&](uint32_t x, uint32_t y) { return recs[x].pos0 < recs[y].pos0; });
+    for (size_t i = 0; i < keep.size();) {
+        size_t j = i + 1;
+        while (j < keep.size() && recs[keep[j]].pos0 == recs[keep[i]].pos0) ++j;
+        if (j - i > 1 && row_bytes) {
+            std::unordered_map<uint32_t, std::vector<uint8_t>> data;  // compact CompressedGenotypes::data
+            std::vector<uint8_t> raw(row_bytes);
+            for (size_t k = i; k < j; ++k) {
+                const uint32_t li = keep[k];
+                CK(cudaMemcpy(raw.data(), b->d_gt + (size_t)rows[li] * row_bytes, row_bytes, cudaMemcpyDeviceToHost));
+                const size_t st = std::max<size_t>(recs[li].stride, 1);
+                std::vector<uint8_t> c(n_kept * st);
+                for (size_t s = 0; s < n_kept; ++s)
+                    for (size_t q = 0; q < st; ++q) c[s * st + q] = raw[s * max_ploidy + q];
+                data.emplace(li, std::move(c));
+            }
+            std::stable_sort(keep.begin() + i, keep.begin() + j,
+                             [&](uint32_t x, uint32_t y) { return data[x] < data[y]; });
+        }
+        i = j;
+    }
+    b->var.resize(keep.size());
+    b->order.resize(keep.size());
+    for (size_t i = 0; i < keep.size(); ++i) {
+        b->var[i] = recs[keep[i]];
+        if (b->var[i].stride == 0 && n_kept) b->var[i].stride = 1;  // CompressedGenotypes::new: max_ploidy.max(1)
+        b->order[i] = rows[keep[i]];
+    }
+    I.n_variants = keep.size();
+    b->d_order = static_cast<uint32_t *>(dev_alloc(std::max<size_t>(keep.size(), 4) * 4));
+    if (!keep.empty())
+        CK(cudaMemcpyAsync(b->d_order, b->order.data(), keep.size() * 4, cudaMemcpyHostToDevice, stream()));
+    CK(cudaStreamSynchronize(stream()));
+    *out = b.release();
+}
+
+}  // namespace
+
+fm_status fm_vcf_parse_device(const char *d_text, size_t n_bytes, char host_last_byte, const char *chr,
+                              const int64_t *regions, size_t n_regions, const uint32_t *kept_col_indices,
+                              size_t n_kept, uint16_t min_gq, int allow_mode, const int64_t *allow, size_t n_allow,
+                              int mask_mode, const int64_t *mask, size_t n_mask, size_t max_ploidy,
+                              fm_vcf_batch **out) {
+    return guarded([&] {
+        if (!out) fail(FM_ERR_INVALID_ARG, "out is NULL");
+        *out = nullptr;
+        if (n_bytes && !d_text) fail(FM_ERR_INVALID_ARG, "text is NULL");
+        if (n_bytes >= (1ull << 31)) fail(FM_ERR_UNSUPPORTED, "more than 2^31 bytes per call: chunk on line boundaries");
+        if (reinterpret_cast<uintptr_t>(d_text) & 15u) fail(FM_ERR_INVALID_ARG, "device text must be 16-byte aligned");
+        require_device();
+        CK(cudaSetDevice(t_device));
+        vcf_parse_impl(reinterpret_cast<const uint8_t *>(d_text), n_bytes, host_last_byte, chr, regions, n_regions,
+                       kept_col_indices, n_kept, min_gq, allow_mode, allow, n_allow, mask_mode, mask, n_mask,
+                       max_ploidy, 0.f, out);
+    });
+}
+
+fm_status fm_vcf_parse(const char *text, size_t n_bytes, const char *chr, const int64_t *regions, size_t n_regions,
+                       const uint32_t *kept_col_indices, size_t n_kept, uint16_t min_gq, int allow_mode,
+                       const int64_t *allow, size_t n_allow, int mask_mode, const int64_t *mask, size_t n_mask,
+                       size_t max_ploidy, fm_vcf_batch **out) {
+    return guarded([&] {
+        if (!out) fail(FM_ERR_INVALID_ARG, "out is NULL");
+        *out = nullptr;
+        if (n_bytes && !text) fail(FM_ERR_INVALID_ARG, "text is NULL");
+        if (n_bytes >= (1ull << 31)) fail(FM_ERR_UNSUPPORTED, "more than 2^31 bytes per call: chunk on line boundaries");
+        require_device();
+        CK(cudaSetDevice(t_device));
+        const size_t padded = ((n_bytes + 15) / 16) * 16 + 32;
+        DevBuf<uint8_t> d_text(padded);
+        Timer tm;
+        tm.start();
+        CK(cudaMemsetAsync(d_text.p + (padded - 48), 0, 48, stream()));
+        h2d(d_text.p, text, n_bytes, stream());
+        tm.stop();
+        const float ms = tm.ms();
+        t_tim.h2d_ms += ms;
+        vcf_parse_impl(d_text.p, n_bytes, n_bytes ? text[n_bytes - 1] : '\n', chr, regions, n_regions,
+                       kept_col_indices, n_kept, min_gq, allow_mode, allow, n_allow, mask_mode, mask, n_mask,
+                       max_ploidy, ms, out);
+    });
+}
+
+fm_status fm_vcf_batch_info(const fm_vcf_batch *b, fm_vcf_info *out) {
+    if (!b || !out) return FM_ERR_INVALID_ARG;
+    *out = b->info;
+    return FM_OK;
+}
+
+fm_status fm_vcf_batch_variants(const fm_vcf_batch *b, int64_t *pos0, uint8_t *flags, uint8_t *stride, uint8_t *ref,
+                                uint8_t *n_alt, uint8_t *alts) {
+    if (!b) return FM_ERR_INVALID_ARG;
+    for (size_t i = 0; i < b->var.size(); ++i) {
+        const fm::VcfLine &r = b->var[i];
+        if (pos0) pos0[i] = r.pos0;
+        if (flags) flags[i] = r.flags;
+        if (stride) stride[i] = r.stride;
+        if (ref) ref[i] = r.ref;
+        if (n_alt) n_alt[i] = r.n_alt;
+        if (alts) memcpy(alts + i * fm::VCF_MAX_ALTS, r.alts, fm::VCF_MAX_ALTS);
+    }
+    return FM_OK;
+}
+
+fm_status fm_vcf_batch_genotypes(const fm_vcf_batch *b, uint8_t *gt) {
+    return guarded([&] {
+        if (!b || !gt) fail(FM_ERR_INVALID_ARG, "batch or output is NULL");
+        const size_t n = b->var.size(), row_bytes = b->S * b->P;
+        if (!n || !row_bytes) return;
+        CK(cudaSetDevice(b->device));
+        DevBuf<uint8_t> d_out(n * row_bytes);
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>((n * row_bytes + 255) / 256, 32ull * sm_count(b->device));
+        fm::fm_k_vcf_gather_rows<<<blocks, 256, 0, stream()>>>(b->d_gt, b->d_order, n, (uint32_t)row_bytes, d_out.p);
+        CK(cudaGetLastError());
+        g_launches++;
+        CK(cudaMemcpyAsync(gt, d_out.p, n * row_bytes, cudaMemcpyDeviceToHost, stream()));
+        CK(cudaStreamSynchronize(stream()));
+    });
+}
+
+fm_status fm_vcf_batch_positions(const fm_vcf_batch *b, int which, int64_t *out, size_t capacity) {
+    if (!b || (which != 0 && which != 1)) return FM_ERR_INVALID_ARG;
+    const std::vector<int64_t> &v = which ? b->pos_filtered : b->pos_missing;
+    if (capacity < v.size() || (!out && !v.empty())) return FM_ERR_INVALID_ARG;
+    if (!v.empty()) memcpy(out, v.data(), v.size() * 8);
+    return FM_OK;
+}
+
+fm_status fm_vcf_batch_errors(const fm_vcf_batch *b, uint64_t *line_index, int32_t *code, int64_t *aux,
+                              size_t capacity) {
+    if (!b || capacity < b->err_line.size()) return FM_ERR_INVALID_ARG;
+    for (size_t i = 0; i < b->err_line.size(); ++i) {
+        if (line_index) line_index[i] = b->err_line[i];
+        if (code) code[i] = b->err_code[i];
+        if (aux) aux[i] = b->err_aux[i];
+    }
+    return FM_OK;
+}
+
+fm_status fm_vcf_batch_matrix(const fm_vcf_batch *b, int pass_only, fm_matrix **out) {
+    return guarded([&] {
+        if (!b || !out) fail(FM_ERR_INVALID_ARG, "batch or out is NULL");
+        *out = nullptr;
+        CK(cudaSetDevice(b->device));
+        std::vector<uint32_t> order;
+        std::vector<int64_t> pos;
+        size_t ploidy = 0;
+        for (size_t i = 0; i < b->var.size(); ++i) {
+            if (pass_only && b->var[i].flags != 0) continue;
+            order.push_back(b->order[i]);
+            pos.push_back(b->var[i].pos0);
+            // from_variants: longest genotype over all variants; a variant without genotypes has length 0
+            // (its recorded stride of 1 is the CompressedGenotypes floor, all cells are the sentinel)
+        }
+        if (order.empty() || b->S == 0) return;  // from_variants: None
+        // max genotype length over the selected rows = max stride of rows that hold a genotype; rows whose
+        // samples are all None report stride 1 by the floor only, so recompute from missing_points
+        for (size_t i = 0, k = 0; i < b->var.size(); ++i) {
+            if (pass_only && b->var[i].flags != 0) continue;
+            ++k;
+            if (b->var[i].missing_points < b->S) ploidy = std::max<size_t>(ploidy, b->var[i].stride);
+        }
+        if (ploidy == 0) return;  // effectively no data (stats.rs:362-365)
+        const size_t V = order.size(), S = b->S;
+        DevBuf<uint32_t> d_ord(V), d_max(1);
+        d_ord.upload(order.data(), V);
+        CK(cudaMemsetAsync(d_max.p, 0, 4, stream()));
+        uint8_t *d_data = static_cast<uint8_t *>(dev_alloc(std::max<size_t>(V * S * ploidy, 16)));
+        fm_matrix *m = nullptr;
+        try {
+            const uint32_t blocks = (uint32_t)std::min<uint64_t>((V * S + 255) / 256, 32ull * sm_count(b->device));
+            fm::fm_k_vcf_to_matrix<<<blocks, 256, 0, stream()>>>(b->d_gt, d_ord.p, V, (uint32_t)S, (uint32_t)b->P,
+                                                                 (uint32_t)ploidy, d_data, d_max.p);
+            CK(cudaGetLastError());
+            g_launches++;
+            uint32_t mx = 0;
+            CK(cudaMemcpyAsync(&mx, d_max.p, 4, cudaMemcpyDeviceToHost, stream()));
+            CK(cudaStreamSynchronize(stream()));
+            if (mx > 127) fail(FM_ERR_UNSUPPORTED, "allele index above 127 in a VCF batch matrix");
+            m = matrix_common(V, S, ploidy, (uint8_t)mx, pos.data());
+            m->d_data = d_data;
+            d_data = nullptr;
+            m->has_missing = true;  // from_variants always returns Some(missing)
+            m->in_band = true;
+            m->d_pos = static_cast<int64_t *>(dev_alloc(std::max<size_t>(V, 1) * 8));
+            CK(cudaMemcpyAsync(m->d_pos, m->pos.data(), V * 8, cudaMemcpyHostToDevice, stream()));
+            CK(cudaStreamSynchronize(stream()));
+        } catch (...) {
+            if (d_data) dev_free(d_data);
+            if (m) fm_matrix_release(m);
+            throw;
+        }
+        *out = m;
+    });
+}
+
+fm_status fm_vcf_batch_release(fm_vcf_batch *b) {
+    if (!b) return FM_OK;
+    cudaSetDevice(b->device);
+    if (b->d_gt) dev_free(b->d_gt);
+    if (b->d_order) dev_free(b->d_order);
+    delete b;
+    return FM_OK;
 }
 
 // ------------------------------------------------------------------------------------ synthetic cohorts

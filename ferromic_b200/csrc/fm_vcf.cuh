@@ -1,0 +1,528 @@
+// fm_vcf.cuh -- SURVEY §8(f4): the VCF parse/filter stage (process_variant, process.rs:4471-4768)
+// as device kernels over a chunk of raw VCF text.  Byte work, HBM/L2-bound; no tensor cores.
+//
+//   fm_k_vcf_count   per 4 KB tile: number of '\n' and '\t'            (text read #1)
+//   fm_k_vcf_index   line starts + tabs-before-line from the scanned tile counts (text read #2, L2)
+//   fm_k_vcf_fixed   one warp per line: the nine fixed fields -> chr / POS / region / allow / mask /
+//                    REF-ALT length guard / allele info / GQ index in FORMAT   (first ~100 B of a line)
+//   fm_k_vcf_samples one CTA per candidate line: tab ranks by block scan, every kept sample field
+//                    parsed by the thread that owns its leading tab -> u8 genotype row, GQ / missing flags
+//   fm_k_vcf_to_matrix  DenseGenotypeMatrix::from_variants (stats.rs:339-500) on the device, in output order
+//
+// A line is what BufRead::read_line yields: it INCLUDES its terminating '\n' (the last field carries it,
+// exactly as in the reference, where "0|1\n" fails u8 parsing and GQ strings are trimmed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fm {
+
+constexpr int VCF_TILE = 4096;  // bytes per CTA tile = 256 threads x 16 B
+constexpr int VCF_MAX_ALTS = 7;
+constexpr int VCF_MAX_PLOIDY = 8;
+
+enum : uint8_t {
+    VCF_CAND = 0,   // reached the genotype loop
+    VCF_SKIP = 1,   // Ok(None) before any statistic: other chromosome / outside the regions
+    VCF_E_FEW_FIELDS = 10,
+    VCF_E_MISSING_COLUMN = 11,
+    VCF_E_INVALID_POS = 12,
+    VCF_E_POS_LT1 = 13,
+    VCF_E_NO_GQ_FORMAT = 14,
+    VCF_E_GQ_MISSING = 15,
+    VCF_E_PLOIDY = 16,         // genotype longer than the caller's max_ploidy (unsupported, not a reference error)
+    VCF_E_TOO_MANY_ALTS = 17,  // more than VCF_MAX_ALTS single-base ALT alleles (unsupported)
+};
+
+struct VcfLine {  // 32 bytes per text line
+    int64_t pos0;             // POS - 1
+    uint32_t sample_off;      // byte after the 9th tab (line end when the line has exactly nine fields)
+    uint32_t missing_points;  // kept samples whose genotype is None
+    uint16_t gq_index;
+    uint8_t status, flags, indel /* bit0 length guard hit, bit1 counted as MNP */, stride, ref, n_alt;
+    uint8_t alts[VCF_MAX_ALTS];
+    uint8_t pad;
+};
+static_assert(sizeof(VcfLine) == 32, "VcfLine layout");
+
+struct VcfParams {
+    const uint8_t *text;
+    const uint32_t *line_start;   // [n_lines + 1]
+    const uint32_t *tabs_before;  // [n_lines + 1]
+    uint32_t n_lines;
+    uint8_t chr[64];  // target chromosome, trimmed and prefix-stripped (process.rs:4501-4514)
+    uint32_t chr_len;
+    const int64_t *regions;  // [n_regions][2] ZeroBasedHalfOpen (start, end), sorted
+    uint32_t n_regions;
+    int allow_mode, mask_mode;        // 0 = None, 1 = intervals of this chromosome, 2 = chromosome absent from the map
+    const uint64_t *allow, *mask;     // merged, sorted, disjoint [s, e) (host-normalised)
+    uint32_t n_allow, n_mask;
+    int32_t max_idx;  // largest kept column index, -1 when no sample is kept
+    uint16_t min_gq;
+    uint32_t n_samples, max_ploidy;
+    const int32_t *col2slot;  // [max_idx + 1] column -> kept sample slot or -1
+};
+
+__device__ __forceinline__ uint32_t vcf_eq4(uint32_t w, uint32_t pat) {
+    // bit i = byte i of w equals the pattern byte
+    const uint32_t t = __vcmpeq4(w, pat) & 0x01010101u;
+    return ((t * 0x01020408u) >> 24) & 0xFu;
+}
+__device__ __forceinline__ uint32_t vcf_eq16(uint4 v, uint32_t pat) {
+    return vcf_eq4(v.x, pat) | (vcf_eq4(v.y, pat) << 4) | (vcf_eq4(v.z, pat) << 8) | (vcf_eq4(v.w, pat) << 12);
+}
+constexpr uint32_t VCF_NL = 0x0A0A0A0Au, VCF_TAB = 0x09090909u;
+
+// block-wide exclusive scan of a packed pair of 16-bit counts (each total <= 4096); 256 threads
+__device__ __forceinline__ uint32_t vcf_block_scan(uint32_t v, uint32_t *smem /*[9]*/, uint32_t &total) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (uint32_t)d) inc += o;
+    }
+    __syncthreads();  // protects smem reuse across calls
+    if (lane == 31) smem[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const uint32_t s = smem[w];
+        if ((uint32_t)w < warp) base += s;
+        tot += s;
+    }
+    total = tot;
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(256)
+fm_k_vcf_count(const uint4 *__restrict__ text16, uint64_t n16, uint32_t *__restrict__ tile_nl,
+               uint32_t *__restrict__ tile_tab) {
+    __shared__ uint32_t s[8];
+    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    uint32_t c = 0;
+    if (i < n16) {
+        const uint4 v = text16[i];  // padding bytes are zero: neither '\n' nor '\t'
+        c = __popc(vcf_eq16(v, VCF_NL)) | (__popc(vcf_eq16(v, VCF_TAB)) << 16);
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < 8; ++w) t += s[w];
+        tile_nl[blockIdx.x] = t & 0xFFFFu;
+        tile_tab[blockIdx.x] = t >> 16;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+fm_k_vcf_index(const uint4 *__restrict__ text16, uint64_t n16, const uint32_t *__restrict__ nl_before_tile,
+               const uint32_t *__restrict__ tab_before_tile, uint32_t *__restrict__ line_start,
+               uint32_t *__restrict__ tabs_before) {
+    __shared__ uint32_t s[9];
+    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    uint32_t nlm = 0, tbm = 0;
+    if (i < n16) {
+        const uint4 v = text16[i];
+        nlm = vcf_eq16(v, VCF_NL);
+        tbm = vcf_eq16(v, VCF_TAB);
+    }
+    uint32_t total;
+    const uint32_t ex = vcf_block_scan(__popc(nlm) | (__popc(tbm) << 16), s, total);
+    uint32_t k = nl_before_tile[blockIdx.x] + (ex & 0xFFFFu);
+    const uint32_t tb = tab_before_tile[blockIdx.x] + (ex >> 16);
+    while (nlm) {
+        const int b = __ffs(nlm) - 1;
+        nlm &= nlm - 1;
+        ++k;  // line k starts after this newline
+        line_start[k] = (uint32_t)(i * 16 + b + 1);
+        tabs_before[k] = tb + __popc(tbm & ((1u << b) - 1u));
+    }
+}
+
+// ---------------------------------------------------------------------------------- fixed fields
+__device__ __forceinline__ bool vcf_is_ws(uint8_t c) {  // ASCII members of char::is_whitespace
+    return c == ' ' || (c >= 9 && c <= 13);
+}
+__device__ __forceinline__ uint8_t vcf_nuc(uint8_t c) {  // process.rs:4621-4640
+    switch (c) {
+        case 'A': case 'a': return 'A';
+        case 'C': case 'c': return 'C';
+        case 'G': case 'g': return 'G';
+        case 'T': case 't': return 'T';
+        default: return 'N';
+    }
+}
+// partition_point(|r| r.end <= pos) then start <= pos (process.rs:746-760)
+__device__ inline bool vcf_in_regions(int64_t pos, const int64_t *r, uint32_t n) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (r[2 * mid + 1] <= pos) lo = mid + 1; else hi = mid;
+    }
+    return lo < n && r[2 * lo] <= pos;
+}
+// membership in merged, sorted, disjoint unsigned intervals
+__device__ inline bool vcf_in_intervals(uint64_t pos, const uint64_t *iv, uint32_t n) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (iv[2 * mid + 1] <= pos) lo = mid + 1; else hi = mid;
+    }
+    return lo < n && iv[2 * lo] <= pos;
+}
+
+__global__ void __launch_bounds__(256)
+fm_k_vcf_fixed(VcfParams P, VcfLine *__restrict__ recs) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const uint8_t *__restrict__ tx = P.text;
+    for (uint32_t line = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; line < P.n_lines; line += warps) {
+        const uint32_t b = P.line_start[line], e = P.line_start[line + 1];
+        const uint32_t n_tabs = P.tabs_before[line + 1] - P.tabs_before[line];
+        const uint32_t n_fields = n_tabs + 1;
+        VcfLine r;
+        r.pos0 = (int64_t)n_fields;  // E_FEW_FIELDS / E_MISSING_COLUMN report the field count here
+        r.sample_off = e;
+        r.missing_points = 0;
+        r.gq_index = 0;
+        r.status = VCF_CAND;
+        r.flags = 0;
+        r.indel = 0;
+        r.stride = 0;
+        r.ref = 'N';
+        r.n_alt = 0;
+        for (int k = 0; k < VCF_MAX_ALTS; ++k) r.alts[k] = 0;
+        r.pad = 0;
+        if (n_fields < 9) {
+            r.status = VCF_E_FEW_FIELDS;
+        } else if (P.max_idx >= 0 && n_fields <= (uint32_t)P.max_idx) {
+            r.status = VCF_E_MISSING_COLUMN;
+        }
+        if (r.status != VCF_CAND) {
+            if (lane == 0) recs[line] = r;
+            continue;
+        }
+        // the first min(9, n_tabs) tab positions, found 32 bytes at a time by the whole warp
+        uint32_t tab[9];
+        const uint32_t want = n_tabs < 9 ? n_tabs : 9;  // >= 8
+        uint32_t found = 0;
+        for (uint32_t base = b; found < want && base < e; base += 32) {
+            const uint32_t p = base + lane;
+            uint32_t m = __ballot_sync(0xffffffffu, p < e && tx[p] == '\t');
+            while (m && found < want) {
+                const uint32_t bit = __ffs(m) - 1;
+                m &= m - 1;
+#pragma unroll
+                for (int k = 0; k < 9; ++k)
+                    if ((uint32_t)k == found) tab[k] = base + bit;
+                ++found;
+            }
+        }
+        if (lane != 0) continue;
+        if (want < 9) tab[8] = e;  // exactly nine fields: FORMAT runs to the end of the line (incl. '\n')
+        r.sample_off = want == 9 ? tab[8] + 1 : e;
+        // ---- CHROM: trim, strip one of chr / Chr / CHR, compare (process.rs:4501-4518)
+        uint32_t c0 = b, c1 = tab[0];
+        while (c0 < c1 && vcf_is_ws(tx[c0])) ++c0;
+        while (c1 > c0 && vcf_is_ws(tx[c1 - 1])) --c1;
+        if (c1 - c0 >= 3) {
+            const uint8_t x = tx[c0], y = tx[c0 + 1], z = tx[c0 + 2];
+            if ((x == 'c' && y == 'h' && z == 'r') || (x == 'C' && y == 'h' && z == 'r') ||
+                (x == 'C' && y == 'H' && z == 'R'))
+                c0 += 3;
+        }
+        bool same = (c1 - c0) == P.chr_len;
+        for (uint32_t k = 0; same && k < P.chr_len; ++k) same = tx[c0 + k] == P.chr[k];
+        if (!same) {
+            r.status = VCF_SKIP;
+            recs[line] = r;
+            continue;
+        }
+        // ---- POS: i64::from_str (optional sign, digits, overflow is an error)
+        {
+            uint32_t p = tab[0] + 1;
+            const uint32_t pe = tab[1];
+            bool neg = false, ok = true;
+            if (p < pe && (tx[p] == '+' || tx[p] == '-')) {
+                neg = tx[p] == '-';
+                ++p;
+            }
+            if (p >= pe) ok = false;
+            uint64_t mag = 0;
+            const uint64_t lim = neg ? (1ull << 63) : (1ull << 63) - 1;
+            for (; ok && p < pe; ++p) {
+                const uint32_t d = (uint32_t)tx[p] - '0';
+                if (d > 9) ok = false;
+                else if (mag > (lim - d) / 10) ok = false;
+                else mag = mag * 10 + d;
+            }
+            if (!ok) {
+                r.status = VCF_E_INVALID_POS;
+                recs[line] = r;
+                continue;
+            }
+            const int64_t p1 = neg ? (int64_t)(0 - mag) : (int64_t)mag;
+            r.pos0 = p1 - 1;  // p1 >= 1 below, or reported as the offending value - 1
+            if (p1 < 1) {
+                r.status = VCF_E_POS_LT1;
+                recs[line] = r;
+                continue;
+            }
+        }
+        if (!vcf_in_regions(r.pos0, P.regions, P.n_regions)) {
+            r.status = VCF_SKIP;
+            recs[line] = r;
+            continue;
+        }
+        // ---- allow / mask (process.rs:4549-4593)
+        if (P.allow_mode == 2 || (P.allow_mode == 1 && !vcf_in_intervals((uint64_t)r.pos0, P.allow, P.n_allow)))
+            r.flags |= 2;  // FLAG_ALLOW
+        if (P.mask_mode == 1 && vcf_in_intervals((uint64_t)r.pos0, P.mask, P.n_mask)) r.flags |= 1;  // FLAG_MASK
+        // ---- length guard + allele info (process.rs:4595-4644)
+        {
+            const uint32_t r0 = tab[2] + 1, r1 = tab[3];  // REF
+            const uint32_t a0 = tab[3] + 1, a1 = tab[4];  // ALT
+            bool indel = (r1 - r0) != 1, longer = false, not_one = false;
+            uint32_t n_alt = 0, seg = a0;
+            for (uint32_t p = a0; p <= a1; ++p) {
+                if (p == a1 || tx[p] == ',') {
+                    const uint32_t len = p - seg;
+                    if (len != 1) not_one = true;
+                    if (len > 1) longer = true;
+                    if (n_alt < VCF_MAX_ALTS) r.alts[n_alt] = len ? vcf_nuc(tx[seg]) : 'N';
+                    ++n_alt;
+                    seg = p + 1;
+                }
+            }
+            if (!indel && not_one) {
+                indel = true;
+                if (longer) r.indel |= 2;
+            }
+            if (indel) r.indel |= 1;
+            r.ref = (r1 > r0) ? vcf_nuc(tx[r0]) : 'N';
+            r.n_alt = (uint8_t)(n_alt < 255 ? n_alt : 255);
+            if (!indel && n_alt > VCF_MAX_ALTS) r.status = VCF_E_TOO_MANY_ALTS;
+        }
+        // ---- FORMAT: index of the "GQ" key (process.rs:4646-4650)
+        {
+            const uint32_t f0 = tab[7] + 1, f1 = tab[8];
+            uint32_t idx = 0, seg = f0;
+            bool have = false;
+            for (uint32_t p = f0; p <= f1 && !have; ++p) {
+                if (p == f1 || tx[p] == ':') {
+                    if (p - seg == 2 && tx[seg] == 'G' && tx[seg + 1] == 'Q') have = true;
+                    else {
+                        ++idx;
+                        seg = p + 1;
+                    }
+                }
+            }
+            if (!have) r.status = VCF_E_NO_GQ_FORMAT;
+            r.gq_index = (uint16_t)(idx < 65535 ? idx : 65535);
+        }
+        recs[line] = r;
+    }
+}
+
+// ---------------------------------------------------------------------------------- sample fields
+// One kept sample field starting at p (field end = next '\t' or line end e).  Returns the number of
+// alleles (0 = genotype is None) and sets low_gq / gq_missing.
+__device__ __forceinline__ uint32_t vcf_parse_sample(const uint8_t *__restrict__ tx, uint32_t p, uint32_t e,
+                                                     uint32_t gq_index, uint32_t min_gq, uint32_t max_ploidy,
+                                                     uint8_t *al, bool &low_gq, bool &gq_missing, bool &too_long) {
+    // alleles_str = field up to the first ':' (process.rs:4659)
+    uint32_t q = p;
+    uint32_t n_tok = 0, val = 0, digits = 0;
+    bool ok = true, plus = false;
+    for (; q < e; ++q) {
+        const uint8_t c = tx[q];
+        if (c == ':' || c == '\t') break;
+        if (c == '|' || c == '/') {
+            if (digits == 0) ok = false;
+            if (ok && n_tok < VCF_MAX_PLOIDY) al[n_tok] = (uint8_t)val;
+            ++n_tok;
+            val = 0;
+            digits = 0;
+            plus = false;
+        } else if (c >= '0' && c <= '9') {
+            val = val * 10 + (c - '0');
+            if (val > 255) {
+                ok = false;
+                val = 256;  // stays out of range without overflowing
+            }
+            ++digits;
+        } else if (c == '+' && digits == 0 && !plus) {
+            plus = true;  // u8::from_str accepts one leading '+'
+        } else {
+            ok = false;  // includes ".", "./.", ".|." (None by name in the reference) and a trailing '\n'
+        }
+    }
+    if (digits == 0) ok = false;
+    if (ok && n_tok < VCF_MAX_PLOIDY) al[n_tok] = (uint8_t)val;
+    ++n_tok;
+    if (!ok) return 0;  // every genotype that fails u8 parsing is None (process.rs:4668-4677)
+    if (n_tok > max_ploidy) {
+        too_long = true;
+        return 0;
+    }
+    // GQ: the gq_index-th ':'-separated part of the whole field, trimmed (process.rs:4694-4728)
+    uint32_t part = 0, g0 = p;
+    uint32_t k = p;
+    for (; k < e; ++k) {
+        const uint8_t d = tx[k];
+        if (d == '\t') break;
+        if (d == ':') {
+            if (part == gq_index) break;
+            ++part;
+            g0 = k + 1;
+        }
+    }
+    if (part != gq_index) {
+        gq_missing = true;
+        return n_tok;
+    }
+    uint32_t g1 = k;
+    while (g0 < g1 && vcf_is_ws(tx[g0])) ++g0;
+    while (g1 > g0 && vcf_is_ws(tx[g1 - 1])) --g1;
+    uint32_t gq = 0;
+    if (!(g1 == g0 || (g1 - g0 == 1 && tx[g0] == '.'))) {
+        uint32_t s = g0;
+        if (tx[s] == '+') ++s;
+        bool gok = s < g1;
+        for (; gok && s < g1; ++s) {
+            const uint32_t d = (uint32_t)tx[s] - '0';
+            if (d > 9) gok = false;
+            else {
+                gq = gq * 10 + d;
+                if (gq > 65535) gok = false;
+            }
+        }
+        if (!gok) gq = 0;  // unparsable GQ is treated as 0
+    }
+    if (gq < min_gq) low_gq = true;
+    return n_tok;
+}
+
+__global__ void __launch_bounds__(256)
+fm_k_vcf_samples(VcfParams P, VcfLine *recs, const uint32_t *__restrict__ row_of_line,
+                 uint8_t *__restrict__ gt) {
+    __shared__ uint32_t s_scan[9];
+    __shared__ uint32_t s_missing, s_low, s_stride, s_err;
+    const uint8_t *__restrict__ tx = P.text;
+    const uint32_t mp = P.max_ploidy;
+    for (uint32_t line = blockIdx.x; line < P.n_lines; line += gridDim.x) {
+        const VcfLine r = recs[line];
+        if (r.status != VCF_CAND) continue;  // uniform across the CTA
+        if (threadIdx.x == 0) {
+            s_missing = 0;
+            s_low = 0;
+            s_stride = 0;
+            s_err = 0;
+        }
+        __syncthreads();
+        const uint32_t e = P.line_start[line + 1];
+        const bool write = !(r.indel & 1);
+        uint8_t *__restrict__ row = write ? gt + (size_t)row_of_line[line] * P.n_samples * mp : nullptr;
+        if (P.max_idx >= 9) {
+            // the 9th tab (at sample_off - 1) opens field 9
+            const uint32_t first = r.sample_off - 1;
+            uint32_t carry = 8;  // tabs of this line before `first`
+            for (uint32_t t0 = first & ~15u; t0 < e; t0 += VCF_TILE) {
+                const uint32_t my = t0 + threadIdx.x * 16;
+                uint32_t tbm = 0;
+                if (my < e) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(tx + my);
+                    tbm = vcf_eq16(v, VCF_TAB);
+                    if (my < first) tbm &= ~((1u << (first - my)) - 1u);          // bytes before the 9th tab
+                    if (e - my < 16) tbm &= (1u << (e - my)) - 1u;                // bytes of the next line
+                }
+                uint32_t total;
+                uint32_t f = carry + vcf_block_scan(__popc(tbm), s_scan, total) + 1;  // field opened by my first tab
+                carry += total;
+                uint32_t miss = 0, stride = 0, err = 0;
+                bool low = false;
+                while (tbm) {
+                    const int bit = __ffs(tbm) - 1;
+                    tbm &= tbm - 1;
+                    if (f <= (uint32_t)P.max_idx) {
+                        const int32_t slot = P.col2slot[f];
+                        if (slot >= 0) {
+                            uint8_t al[VCF_MAX_PLOIDY];
+                            bool gq_missing = false, too_long = false;
+                            const uint32_t n = vcf_parse_sample(tx, my + bit + 1, e, r.gq_index, P.min_gq, mp, al, low,
+                                                                gq_missing, too_long);
+                            if (too_long) err = VCF_E_PLOIDY > err ? VCF_E_PLOIDY : err;
+                            else if (gq_missing) err = err ? err : VCF_E_GQ_MISSING;
+                            if (n == 0) ++miss;
+                            stride = n > stride ? n : stride;
+                            if (write) {
+                                uint8_t *dst = row + (size_t)slot * mp;
+                                for (uint32_t k = 0; k < mp; ++k) dst[k] = k < n ? al[k] : (uint8_t)0xFF;
+                            }
+                        }
+                    }
+                    ++f;
+                }
+                if (miss) atomicAdd(&s_missing, miss);
+                if (low) atomicOr(&s_low, 1u);
+                if (stride) atomicMax(&s_stride, stride);
+                if (err) atomicMax(&s_err, err);
+                if (carry > (uint32_t)P.max_idx) break;  // every kept column has been seen (uniform)
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            VcfLine o = r;
+            o.missing_points = s_missing;
+            o.stride = (uint8_t)s_stride;
+            if (s_low) o.flags |= 4;      // FLAG_LOW_GQ
+            if (s_missing) o.flags |= 8;  // FLAG_MISSING
+            if (s_err) o.status = (uint8_t)s_err;
+            recs[line] = o;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------- from_variants on the device
+// gt rows [*][S][P] with the CompressedGenotypes sentinel (0xFF in slot 0 = None, a later 0xFF ends the
+// genotype) -> reference-layout u8 matrix with in-band missingness (cells >= 0x80 missing), rows in
+// output order.  max_allele = largest valid allele byte.
+__global__ void __launch_bounds__(256)
+fm_k_vcf_to_matrix(const uint8_t *__restrict__ gt, const uint32_t *__restrict__ order, uint64_t n_rows, uint32_t S,
+                   uint32_t P, uint32_t ploidy, uint8_t *__restrict__ data, uint32_t *__restrict__ max_allele) {
+    const uint64_t total = n_rows * S;
+    uint32_t mx = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / S;
+        const uint32_t s = (uint32_t)(i - r * S);
+        const uint8_t *src = gt + ((size_t)order[r] * S + s) * P;
+        uint8_t *dst = data + i * ploidy;
+        bool valid = true;
+        for (uint32_t k = 0; k < ploidy; ++k) {
+            const uint8_t a = k < P ? src[k] : (uint8_t)0xFF;
+            valid = valid && a != 0xFF;
+            dst[k] = valid ? a : (uint8_t)0x80;
+            if (valid && a > mx) mx = a;
+        }
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_allele, mx);
+}
+
+__global__ void __launch_bounds__(256)
+fm_k_vcf_gather_rows(const uint8_t *__restrict__ gt, const uint32_t *__restrict__ order, uint64_t n_rows,
+                     uint32_t row_bytes, uint8_t *__restrict__ out) {
+    const uint64_t total = n_rows * row_bytes;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / row_bytes;
+        out[i] = gt[(size_t)order[r] * row_bytes + (i - r * row_bytes)];
+    }
+}
+
+}  // namespace fm

@@ -318,6 +318,72 @@ fm_status fm_falsta_tracks(const int64_t *pos1, const double *values, size_t n, 
                            size_t *line_len, size_t *len_out);
 fm_status fm_falsta_format_value(double value, int mode, char *buf, size_t capacity, size_t *len_out);
 
+/* ---- VCF parse/filter stage: process_variant over a chunk of raw text ----
+ * Replaces the per-line work of process_vcf (process.rs:4262-4400) + process_variant (:4471-4768):
+ * `text` holds VCF DATA lines (header already consumed by the host, :4181-4215), each terminated by
+ * '\n' as BufRead::read_line frames them (a final unterminated line is a line).  Every line goes
+ * through the reference's checks in the reference's order: field counts, chromosome match
+ * (chr/Chr/CHR prefix stripped), POS, regions (ZeroBasedHalfOpen pairs, sorted as process_vcf passes
+ * them), allow / mask flags, the REF/ALT length guard (MNP counter), the GQ key in FORMAT, genotypes
+ * of the kept columns (None for ".", "./.", ".|." and anything u8 parsing rejects), GQ < min_gq,
+ * missing data.  Line-local statistics are merged only for lines that returned Ok, a line that
+ * returned Err is reported (fm_vcf_batch_errors) and skipped, and the surviving variants are sorted
+ * by (position, compressed genotype bytes) exactly like process.rs:4377-4386.
+ *   allow_mode / mask_mode: FM_VCF_NONE (Option is None), FM_VCF_INTERVALS (the map's (start, end)
+ *   pairs of this chromosome), FM_VCF_CHR_ABSENT (a map was given but lacks this chromosome).
+ *   max_ploidy: longest genotype the batch can hold (1..8); a longer one fails its line with
+ *   FM_VCF_E_PLOIDY.  n_bytes < 2^31 per call (chunk on line boundaries; statistics are additive).
+ * Genotypes stay on the device: gt[n_variants][n_kept][max_ploidy] u8 with the CompressedGenotypes
+ * sentinel (0xFF in slot 0 = None, a later 0xFF ends the genotype, process.rs:430-478). */
+typedef struct fm_vcf_batch fm_vcf_batch;
+#define FM_VCF_NONE 0
+#define FM_VCF_INTERVALS 1
+#define FM_VCF_CHR_ABSENT 2
+#define FM_VCF_E_FEW_FIELDS 10     /* "Invalid VCF line format: expected at least 9 fixed fields, found {aux}" */
+#define FM_VCF_E_MISSING_COLUMN 11 /* "... expected genotype field at column {max+1}, found {aux} columns"     */
+#define FM_VCF_E_INVALID_POS 12    /* "Invalid position"                                                       */
+#define FM_VCF_E_POS_LT1 13        /* "Invalid 1-based pos: {aux}"                                             */
+#define FM_VCF_E_NO_GQ_FORMAT 14   /* "GQ field not found in FORMAT"                                           */
+#define FM_VCF_E_GQ_MISSING 15     /* "GQ value missing in sample genotype field at chr{chr}:{aux}"            */
+#define FM_VCF_E_PLOIDY 16         /* unsupported: genotype longer than max_ploidy (aux = 1-based POS)         */
+#define FM_VCF_E_TOO_MANY_ALTS 17  /* unsupported: more than 7 single-base ALT alleles (aux = 1-based POS)     */
+typedef struct {
+    uint64_t n_lines, n_variants, n_errors, n_samples, max_ploidy;
+    /* FilteringStats (process.rs:406-416) and MissingDataInfo (:543-548) */
+    uint64_t total_variants, filtered_variants, filtered_due_to_mask, filtered_due_to_allow,
+        missing_data_variants, low_gq_variants, mnp_variants, total_data_points, missing_data_points,
+        n_positions_with_missing, n_filtered_positions;
+    float h2d_ms, index_ms, parse_ms; /* device time of the upload, line index and the two parse kernels */
+} fm_vcf_info;
+fm_status fm_vcf_parse(const char *text, size_t n_bytes, const char *chr, const int64_t *regions,
+                       size_t n_regions, const uint32_t *kept_col_indices, size_t n_kept, uint16_t min_gq,
+                       int allow_mode, const int64_t *allow, size_t n_allow, int mask_mode,
+                       const int64_t *mask, size_t n_mask, size_t max_ploidy, fm_vcf_batch **out);
+/* Same over text that already lives in device memory of the current device (16-byte aligned, at
+ * least 16 readable zero bytes after n_bytes; host_last_byte = text[n_bytes-1]). */
+fm_status fm_vcf_parse_device(const char *d_text, size_t n_bytes, char host_last_byte, const char *chr,
+                              const int64_t *regions, size_t n_regions, const uint32_t *kept_col_indices,
+                              size_t n_kept, uint16_t min_gq, int allow_mode, const int64_t *allow,
+                              size_t n_allow, int mask_mode, const int64_t *mask, size_t n_mask,
+                              size_t max_ploidy, fm_vcf_batch **out);
+fm_status fm_vcf_batch_info(const fm_vcf_batch *b, fm_vcf_info *out);
+/* per-variant arrays in output order (any pointer may be NULL): 0-based position, flags
+ * (1 mask | 2 allow | 4 low GQ | 8 missing, process.rs:785-789), the variant's own genotype stride,
+ * allele info (ref, number of ALT alleles, alts[n][7]) */
+fm_status fm_vcf_batch_variants(const fm_vcf_batch *b, int64_t *pos0, uint8_t *flags, uint8_t *stride,
+                                uint8_t *ref, uint8_t *n_alt, uint8_t *alts);
+fm_status fm_vcf_batch_genotypes(const fm_vcf_batch *b, uint8_t *gt); /* [n_variants][n_samples][max_ploidy] */
+/* sorted, de-duplicated members of MissingDataInfo::positions_with_missing / FilteringStats::filtered_positions */
+fm_status fm_vcf_batch_positions(const fm_vcf_batch *b, int which /*0 missing, 1 filtered*/, int64_t *out,
+                                 size_t capacity);
+fm_status fm_vcf_batch_errors(const fm_vcf_batch *b, uint64_t *line_index, int32_t *code, int64_t *aux,
+                              size_t capacity);
+/* DenseGenotypeMatrix::from_variants (stats.rs:339-500) over the batch's variants (pass_only != 0:
+ * only those with flags == 0, the CLI's "filtered" set) without leaving the device.  *out is NULL
+ * when from_variants would return None (no variants / no genotype data). */
+fm_status fm_vcf_batch_matrix(const fm_vcf_batch *b, int pass_only, fm_matrix **out);
+fm_status fm_vcf_batch_release(fm_vcf_batch *b);
+
 /* ---- synthetic cohorts for benchmarks and full-size parity tests ----
  * Fills a device-resident u8 matrix (reference layout) and, when d_missing != NULL, its packed
  * missing bitmap with a counter-based generator: entry (site, column) is a pure integer function
