@@ -3129,11 +3129,12 @@ fm_status fm_vcf_parse(const char *text, size_t n_bytes, const char *chr, const 
         if (n_bytes >= (1ull << 31)) fail(FM_ERR_UNSUPPORTED, "more than 2^31 bytes per call: chunk on line boundaries");
         require_device();
         CK(cudaSetDevice(t_device));
-        const size_t padded = ((n_bytes + 15) / 16) * 16 + 32;
+        const size_t body = ((n_bytes + 15) / 16) * 16, padded = body + 32;
         DevBuf<uint8_t> d_text(padded);
         Timer tm;
         tm.start();
-        CK(cudaMemsetAsync(d_text.p + (padded - 48), 0, 48, stream()));
+        const size_t tail = body >= 16 ? body - 16 : 0;  // the partial last 16-byte word and the padding read zero
+        CK(cudaMemsetAsync(d_text.p + tail, 0, padded - tail, stream()));
         h2d(d_text.p, text, n_bytes, stream());
         tm.stop();
         const float ms = tm.ms();

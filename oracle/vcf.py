@@ -213,7 +213,7 @@ def compressed(raw: Sequence[Optional[Sequence[int]]]) -> Tuple[bytes, int]:
 
 
 def process_lines(lines: Sequence[str], chr_: str, regions, kept_col_indices, min_gq,
-                  allow_regions=None, mask_regions=None):
+                  allow_regions=None, mask_regions=None, skip=()):
     """The data-line part of process_vcf (process.rs:4262-4400): every line through process_variant with
     line-local statistics that are merged only when the line returned Ok; a line that returns Err is
     reported and skipped; the surviving variants are sorted by (position, compressed genotype bytes).
@@ -222,6 +222,8 @@ def process_lines(lines: Sequence[str], chr_: str, regions, kept_col_indices, mi
     miss, stats = MissingDataInfo(), FilteringStats()
     out, errors = [], []
     for li, line in enumerate(lines):
+        if li in skip:  # lines the device path reports as unsupported (tests only)
+            continue
         lm, ls = MissingDataInfo(), FilteringStats()
         try:
             r = process_variant(line, chr_, regions, lm, kept_col_indices, min_gq, ls, allow_regions, mask_regions)

@@ -89,7 +89,8 @@ ODD_GQ = [".", "", " 40", "40 ", "+35", "x", "-5", "65535", "65536", "99999", "0
 
 
 def make_vcf(rng, n_lines, n_cols, odd=0.05, chrs=("chr1", "1", "Chr1", "CHR1", "chr2", " chr1 ", "chr11"),
-             pos_lo=900, pos_hi=2200, formats=("GT:GQ", "GT:GQ:DP", "GT:DP:GQ", "GQ:GT"), crlf=False, sort=False):
+             pos_lo=900, pos_hi=2200, formats=("GT:GQ", "GT:GQ:DP", "GT:DP:GQ", "GQ:GT"), crlf=False, sort=False, odd_gt=None):
+    odd_gt = ODD_GT if odd_gt is None else odd_gt
     lines = []
     positions = rng.integers(pos_lo, pos_hi, size=n_lines)
     if sort:
@@ -113,7 +114,7 @@ def make_vcf(rng, n_lines, n_cols, odd=0.05, chrs=("chr1", "1", "Chr1", "CHR1", 
         keys = fmt.split(":")
         cols = []
         for _ in range(n_cols):
-            gt = GT_POOL[rng.integers(len(GT_POOL))] if rng.random() > odd else ODD_GT[rng.integers(len(ODD_GT))]
+            gt = GT_POOL[rng.integers(len(GT_POOL))] if rng.random() > odd else odd_gt[rng.integers(len(odd_gt))]
             gq = str(int(rng.integers(25, 99))) if rng.random() > odd else ODD_GQ[rng.integers(len(ODD_GQ))]
             parts = []
             for k in keys:
@@ -140,11 +141,16 @@ def make_vcf(rng, n_lines, n_cols, odd=0.05, chrs=("chr1", "1", "Chr1", "CHR1", 
 def check_against_oracle(text, chr_, regions, kept, min_gq, allow=None, mask=None, max_ploidy=3):
     from ferromic_b200 import vcf
     b = vcf.process_lines(text.encode(), chr_, regions, kept, min_gq, allow, mask, max_ploidy=max_ploidy)
-    out, miss, stats, errors = ov.process_lines(ov.split_lines(text), chr_, regions, kept, min_gq, allow, mask)
-    # lines the device rejects as unsupported are dropped from the oracle's view the same way
+    # lines the device reports as unsupported (> 7 single-base ALT alleles, genotype longer than max_ploidy)
+    # are left out of the oracle's input; they must be exactly the lines with those properties
     unsupported = {l for l, m in b.errors if m.startswith("unsupported")}
-    assert not unsupported, "generator produced an unsupported line"
-    assert b.errors == errors
+    lines = ov.split_lines(text)
+    for l in unsupported:
+        f = lines[l].split("\t")
+        assert f[4].count(",") >= 7 or any(c.split(":")[0].count("|") + c.split(":")[0].count("/") >= max_ploidy
+                                           for c in f[9:])
+    out, miss, stats, errors = ov.process_lines(lines, chr_, regions, kept, min_gq, allow, mask, skip=unsupported)
+    assert [e for e in b.errors if e[0] not in unsupported] == errors
     assert int(b.info.n_lines) == len(ov.split_lines(text))
     assert b.n_variants == len(out)
     assert list(b.positions) == [v[0] for v in out]
@@ -230,14 +236,16 @@ def test_vcf_text_to_estimators_without_host_round_trip():
     n_cols, n_lines = 24, 800
     text = "##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + \
         "\t".join(f"S{i}" for i in range(n_cols)) + "\n" + \
-        make_vcf(rng, n_lines, n_cols, odd=0.01, chrs=("chr1",), sort=True, formats=("GT:GQ",))
+        make_vcf(rng, n_lines, n_cols, odd=0.01, chrs=("chr1",), sort=True, formats=("GT:GQ",),
+                 odd_gt=[".", "./.", ".|.", "0", "1", "x", "0|."])  # biallelic, with None and haploid calls
     regions = [(900, 2300)]
     batch, names = vcf.process_vcf_text(text.encode(), "1", regions, 30, exclusion_set={"S3", "S7"})
     assert len(names) == n_cols - 2
     kept = [9 + i for i in range(n_cols) if i not in (3, 7)]
     body = text.split("\n", 2)[2]
-    out, _, _, _ = ov.process_lines(ov.split_lines(body), "1", regions, kept, 30)
-    assert list(batch.positions) == [v[0] for v in out]
+    unsupported = {l for l, msg in batch.errors if msg.startswith("unsupported")}
+    out, _, _, _ = ov.process_lines(ov.split_lines(body), "1", regions, kept, 30, skip=unsupported)
+    assert list(batch.positions) == [v[0] for v in out] and len(out) > 300
     S = len(kept)
     for pass_only in (False, True):
         sel = [v for v in out if (v[2] == 0 or not pass_only)]
