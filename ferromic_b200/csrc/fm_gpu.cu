@@ -3009,7 +3009,8 @@ void vcf_parse_impl(const uint8_t *d_text, size_t n_bytes, char last_byte, const
     b->d_gt = static_cast<uint8_t *>(dev_alloc(std::max<size_t>(n_rows * row_bytes, 16)));
     {
         const uint32_t blocks = (uint32_t)std::min<uint64_t>(n_lines, 16ull * sms);
-        fm::fm_k_vcf_samples<<<blocks, 256, 0, stream()>>>(P, d_recs.p, d_row.p, b->d_gt);
+        fm::fm_k_vcf_samples<<<blocks, 256, 0, stream()>>>(P, d_recs.p, d_row.p, b->d_gt,
+                                                             (uint32_t)(((n_bytes + 15) / 16) * 16 + 16));
         CK(cudaGetLastError());
     }
     t_parse.stop();

@@ -406,11 +406,41 @@ __device__ __forceinline__ uint32_t vcf_parse_sample(const uint8_t *__restrict__
     return n_tok;
 }
 
+// Fast path for the field shape that makes up almost all of a 1000-Genomes-style VCF: "a|b:QQ<tab or :>"
+// with one-digit alleles and a 1-3 digit GQ as the second key.  w0 / w1 = the field's first eight bytes.
+// Returns false when the field is anything else (the general parser then decides).
+__device__ __forceinline__ bool vcf_fast_sample(uint32_t w0, uint32_t w1, uint32_t room, uint32_t min_gq,
+                                                uint32_t &a0, uint32_t &a1, bool &low_gq) {
+    const uint32_t b0 = (w0 & 0xFFu) - '0', b1 = (w0 >> 8) & 0xFFu, b2 = ((w0 >> 16) & 0xFFu) - '0', b3 = w0 >> 24;
+    if (b0 > 9u || b2 > 9u || b3 != ':' || (b1 != '|' && b1 != '/')) return false;
+    const uint32_t d0 = (w1 & 0xFFu) - '0', c1 = (w1 >> 8) & 0xFFu, c2 = (w1 >> 16) & 0xFFu, c3 = w1 >> 24;
+    if (d0 > 9u) return false;
+    uint32_t gq = d0, term = c1, used = 6;  // bytes consumed including the terminator
+    if (c1 - '0' <= 9u) {
+        gq = gq * 10 + (c1 - '0');
+        term = c2;
+        used = 7;
+        if (c2 - '0' <= 9u) {
+            gq = gq * 10 + (c2 - '0');
+            term = c3;
+            used = 8;
+        }
+    }
+    if ((term != '\t' && term != ':') || used > room) return false;
+    a0 = b0;
+    a1 = b2;
+    if (gq < min_gq) low_gq = true;
+    return true;
+}
+
 __global__ void __launch_bounds__(256)
-fm_k_vcf_samples(VcfParams P, VcfLine *recs, const uint32_t *__restrict__ row_of_line,
-                 uint8_t *__restrict__ gt) {
+fm_k_vcf_samples(VcfParams P, VcfLine *recs, const uint32_t *__restrict__ row_of_line, uint8_t *__restrict__ gt,
+                 uint32_t text_cap) {
     __shared__ uint32_t s_scan[9];
     __shared__ uint32_t s_missing, s_low, s_stride, s_err;
+    // the tile + 16 bytes of look-ahead, double-buffered: a thread that is done with tile i writes tile i+1 into
+    // the other buffer and then waits in the scan's barrier, so no reader of tile i is ever overtaken
+    __shared__ uint4 s_tile2[2][VCF_TILE / 16 + 1];
     const uint8_t *__restrict__ tx = P.text;
     const uint32_t mp = P.max_ploidy;
     for (uint32_t line = blockIdx.x; line < P.n_lines; line += gridDim.x) {
@@ -425,21 +455,32 @@ fm_k_vcf_samples(VcfParams P, VcfLine *recs, const uint32_t *__restrict__ row_of
         __syncthreads();
         const uint32_t e = P.line_start[line + 1];
         const bool write = !(r.indel & 1);
+        const bool fast_ok = r.gq_index == 1 && mp >= 2;
         uint8_t *__restrict__ row = write ? gt + (size_t)row_of_line[line] * P.n_samples * mp : nullptr;
         if (P.max_idx >= 9) {
             // the 9th tab (at sample_off - 1) opens field 9
             const uint32_t first = r.sample_off - 1;
             uint32_t carry = 8;  // tabs of this line before `first`
-            for (uint32_t t0 = first & ~15u; t0 < e; t0 += VCF_TILE) {
+            uint32_t buf = 0;
+            for (uint32_t t0 = first & ~15u; t0 < e; t0 += VCF_TILE, buf ^= 1u) {
+                uint4 *s_tile = s_tile2[buf];
+                const uint32_t *s_w = reinterpret_cast<const uint32_t *>(s_tile);
                 const uint32_t my = t0 + threadIdx.x * 16;
                 uint32_t tbm = 0;
+                uint4 v = make_uint4(0, 0, 0, 0);
                 if (my < e) {
-                    const uint4 v = *reinterpret_cast<const uint4 *>(tx + my);
+                    v = *reinterpret_cast<const uint4 *>(tx + my);
                     tbm = vcf_eq16(v, VCF_TAB);
                     if (my < first) tbm &= ~((1u << (first - my)) - 1u);          // bytes before the 9th tab
                     if (e - my < 16) tbm &= (1u << (e - my)) - 1u;                // bytes of the next line
                 }
-                uint32_t total;
+                s_tile[threadIdx.x] = v;
+                if (threadIdx.x == 0) {
+                    const uint32_t la = t0 + VCF_TILE;
+                    s_tile[VCF_TILE / 16] = (la < e && la + 16 <= text_cap) ? *reinterpret_cast<const uint4 *>(tx + la)
+                                                                             : make_uint4(0, 0, 0, 0);
+                }
+                uint32_t total;  // the scan's barriers also publish s_tile
                 uint32_t f = carry + vcf_block_scan(__popc(tbm), s_scan, total) + 1;  // field opened by my first tab
                 carry += total;
                 uint32_t miss = 0, stride = 0, err = 0;
@@ -450,17 +491,36 @@ fm_k_vcf_samples(VcfParams P, VcfLine *recs, const uint32_t *__restrict__ row_of
                     if (f <= (uint32_t)P.max_idx) {
                         const int32_t slot = P.col2slot[f];
                         if (slot >= 0) {
-                            uint8_t al[VCF_MAX_PLOIDY];
-                            bool gq_missing = false, too_long = false;
-                            const uint32_t n = vcf_parse_sample(tx, my + bit + 1, e, r.gq_index, P.min_gq, mp, al, low,
-                                                                gq_missing, too_long);
-                            if (too_long) err = VCF_E_PLOIDY > err ? VCF_E_PLOIDY : err;
-                            else if (gq_missing) err = err ? err : VCF_E_GQ_MISSING;
-                            if (n == 0) ++miss;
-                            stride = n > stride ? n : stride;
-                            if (write) {
-                                uint8_t *dst = row + (size_t)slot * mp;
-                                for (uint32_t k = 0; k < mp; ++k) dst[k] = k < n ? al[k] : (uint8_t)0xFF;
+                            const uint32_t p = my + bit + 1;  // first byte of the field
+                            const uint32_t o = p - t0, sh = (o & 3u) * 8u;
+                            const uint32_t x0 = s_w[o >> 2], x1 = s_w[(o >> 2) + 1], x2 = s_w[(o >> 2) + 2];
+                            uint32_t a0, a1;
+                            if (fast_ok && vcf_fast_sample(__funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh),
+                                                           e - p, P.min_gq, a0, a1, low)) {
+                                stride = stride > 2u ? stride : 2u;
+                                if (write) {
+                                    uint8_t *dst = row + (size_t)slot * mp;
+                                    if (mp == 2) {
+                                        *reinterpret_cast<uint16_t *>(dst) = (uint16_t)(a0 | (a1 << 8));
+                                    } else {
+                                        dst[0] = (uint8_t)a0;
+                                        dst[1] = (uint8_t)a1;
+                                        for (uint32_t k = 2; k < mp; ++k) dst[k] = 0xFF;
+                                    }
+                                }
+                            } else {
+                                uint8_t al[VCF_MAX_PLOIDY];
+                                bool gq_missing = false, too_long = false;
+                                const uint32_t n = vcf_parse_sample(tx, p, e, r.gq_index, P.min_gq, mp, al, low,
+                                                                    gq_missing, too_long);
+                                if (too_long) err = VCF_E_PLOIDY > err ? VCF_E_PLOIDY : err;
+                                else if (gq_missing) err = err ? err : VCF_E_GQ_MISSING;
+                                if (n == 0) ++miss;
+                                stride = n > stride ? n : stride;
+                                if (write) {
+                                    uint8_t *dst = row + (size_t)slot * mp;
+                                    for (uint32_t k = 0; k < mp; ++k) dst[k] = k < n ? al[k] : (uint8_t)0xFF;
+                                }
                             }
                         }
                     }

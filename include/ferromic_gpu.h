@@ -360,7 +360,8 @@ fm_status fm_vcf_parse(const char *text, size_t n_bytes, const char *chr, const 
                        int allow_mode, const int64_t *allow, size_t n_allow, int mask_mode,
                        const int64_t *mask, size_t n_mask, size_t max_ploidy, fm_vcf_batch **out);
 /* Same over text that already lives in device memory of the current device (16-byte aligned, at
- * least 16 readable zero bytes after n_bytes; host_last_byte = text[n_bytes-1]). */
+ * least 32 readable bytes after n_bytes, zero up to the next 16-byte boundary; host_last_byte =
+ * text[n_bytes-1]). */
 fm_status fm_vcf_parse_device(const char *d_text, size_t n_bytes, char host_last_byte, const char *chr,
                               const int64_t *regions, size_t n_regions, const uint32_t *kept_col_indices,
                               size_t n_kept, uint16_t min_gq, int allow_mode, const int64_t *allow,

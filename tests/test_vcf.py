@@ -189,7 +189,8 @@ def test_device_parser_reference_cases():
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed,n_lines,n_cols,odd,crlf", [(1, 60, 3, 0.12, False), (2, 400, 7, 0.06, False),
                                                            (3, 300, 40, 0.03, True), (4, 50, 700, 0.01, False),
-                                                           (5, 1500, 5, 0.0, False), (6, 8, 3000, 0.002, False)])
+                                                           (5, 1500, 5, 0.0, False), (6, 8, 3000, 0.002, False),
+                                                           (7, 96, 2600, 0.0, False), (8, 40, 2504, 0.0005, True)])
 def test_device_parser_matches_oracle(seed, n_lines, n_cols, odd, crlf):
     rng = np.random.default_rng(seed)
     text = make_vcf(rng, n_lines, n_cols, odd=odd, crlf=crlf)

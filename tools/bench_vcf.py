@@ -1,0 +1,108 @@
+"""Times the device VCF parse/filter stage (fm_vcf_parse) on 1000-Genomes-shaped text:
+2,504 samples, GT:GQ sample fields, one chromosome.  Prints one JSON line.
+usage: python tools/bench_vcf.py [--lines N] [--samples S] [--reps R]"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def synth_text(n_lines: int, n_samples: int, seed: int = 1) -> bytes:
+    """'chr1\\tPOS\\t.\\tA\\tG\\t.\\tPASS\\tAC=..\\tGT:GQ' + n_samples x 'a|b:QQ' fields, built with numpy byte ops."""
+    rng = np.random.default_rng(seed)
+    field = 7  # "a|b:QQ\t"
+    pos = np.cumsum(rng.integers(1, 40, size=n_lines)) + 10000
+    fixed = [f"chr1\t{int(p)}\t.\tA\tG\t.\tPASS\tAC=12;AF=0.0024;AN=5008;NS=2504;DP=20000\tGT:GQ\t".encode() for p in pos]
+    flen = np.array([len(f) for f in fixed])
+    line_len = flen + n_samples * field
+    starts = np.concatenate([[0], np.cumsum(line_len)])
+    buf = np.empty(int(starts[-1]), dtype=np.uint8)
+    freq = rng.beta(0.3, 1.5, size=n_lines)
+    for i in range(n_lines):
+        o = int(starts[i])
+        buf[o:o + flen[i]] = np.frombuffer(fixed[i], dtype=np.uint8)
+        o += int(flen[i])
+        a = (rng.random((n_samples, 2)) < freq[i]).astype(np.uint8) + ord("0")
+        gq = rng.integers(30, 100, size=n_samples)
+        blk = np.empty((n_samples, field), dtype=np.uint8)
+        blk[:, 0] = a[:, 0]
+        blk[:, 1] = ord("|")
+        blk[:, 2] = a[:, 1]
+        blk[:, 3] = ord(":")
+        blk[:, 4] = gq // 10 + ord("0")
+        blk[:, 5] = gq % 10 + ord("0")
+        blk[:, 6] = ord("\t")
+        miss = rng.random(n_samples) < 0.002
+        blk[miss, 0] = ord(".")
+        blk[miss, 2] = ord(".")
+        blk[-1, 6] = ord("\n")
+        buf[o:o + n_samples * field] = blk.reshape(-1)
+    return buf.tobytes()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--lines", type=int, default=20000)
+    ap.add_argument("--samples", type=int, default=2504)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--cpu-lines", type=int, default=200)
+    a = ap.parse_args()
+    import torch
+
+    from ferromic_b200 import _lib, vcf
+    text = synth_text(a.lines, a.samples)
+    pinned = torch.empty(len(text), dtype=torch.uint8).pin_memory()
+    pinned.numpy()[:] = np.frombuffer(text, dtype=np.uint8)
+    kept = np.arange(9, 9 + a.samples, dtype=np.uint32)
+    reg = np.array([[0, 1 << 40]], dtype=np.int64)
+    L = _lib.lib()
+    p = lambda x: x.ctypes.data_as(C.c_void_p)
+    best = None
+    for rep in range(a.reps + 1):
+        h = C.c_void_p()
+        t0 = time.perf_counter()
+        _lib.check(L.fm_vcf_parse(C.cast(pinned.data_ptr(), C.c_char_p), len(text), b"1", p(reg), 1, p(kept), len(kept), 30,
+                                  0, None, 0, 0, None, 0, 2, C.byref(h)))
+        wall = (time.perf_counter() - t0) * 1e3
+        info = _lib.VcfInfo()
+        _lib.check(L.fm_vcf_batch_info(h, C.byref(info)))
+        t1 = time.perf_counter()
+        mh = C.c_void_p()
+        _lib.check(L.fm_vcf_batch_matrix(h, 0, C.byref(mh)))
+        L.fm_synchronize()
+        mat_ms = (time.perf_counter() - t1) * 1e3
+        L.fm_matrix_release(mh)
+        L.fm_vcf_batch_release(h)
+        if rep == 0:
+            continue  # warm-up (allocator, first-touch)
+        r = dict(wall_ms=wall, h2d_ms=info.h2d_ms, index_ms=info.index_ms, parse_ms=info.parse_ms, matrix_ms=mat_ms)
+        if best is None or r["wall_ms"] < best["wall_ms"]:
+            best = r
+    assert info.n_variants == a.lines and info.n_errors == 0 and info.low_gq_variants == 0  # every GQ is >= 30
+    gb = len(text) / 1e9
+    out = {"what": "fm_vcf_parse on 1000G-shaped text", "lines": a.lines, "samples": a.samples, "text_GB": gb,
+           "genotype_calls": a.lines * a.samples, **{k: round(v, 3) for k, v in best.items()},
+           "parse_GBps_text": gb / (best["parse_ms"] / 1e3), "index_GBps_text": gb / (best["index_ms"] / 1e3),
+           "h2d_GBps": gb / (best["h2d_ms"] / 1e3), "e2e_GBps_text": gb / (best["wall_ms"] / 1e3),
+           "e2e_sample_genotypes_per_s": a.lines * a.samples / (best["wall_ms"] / 1e3),
+           "low_gq_variants": int(info.low_gq_variants), "missing_data_variants": int(info.missing_data_variants)}
+    # CPU port (pure-Python restatement, one core) on a bounded sample -- a reported baseline, not the target
+    if a.cpu_lines > 0:
+        from oracle import vcf as ov
+        lines = ov.split_lines(text[: 40 * 1024 * 1024].decode())[: a.cpu_lines]
+        t0 = time.perf_counter()
+        o, _, _, _ = ov.process_lines(lines, "1", [(0, 1 << 40)], kept.tolist(), 30)
+        dt = time.perf_counter() - t0
+        out["cpu_port"] = {"kind": "port (pure Python, 1 core)", "lines": len(lines), "seconds": dt,
+                           "sample_genotypes_per_s": len(lines) * a.samples / dt}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
