@@ -2867,12 +2867,52 @@ __global__ void __launch_bounds__(256)
 fm_k_vcf_rowflag(const fm::VcfLine *__restrict__ recs, uint32_t n, uint32_t *__restrict__ flag) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) flag[i] = (recs[i].status == fm::VCF_CAND && !(recs[i].indel & 1)) ? 1u : 0u;
+    else if (i == n) flag[i] = 0u;
 }
 
-void vcf_parse_impl(const uint8_t *d_text, size_t n_bytes, char last_byte, const char *chr, const int64_t *regions,
-                    size_t n_regions, const uint32_t *kept, size_t n_kept, uint16_t min_gq, int allow_mode,
-                    const int64_t *allow, size_t n_allow, int mask_mode, const int64_t *mask, size_t n_mask,
-                    size_t max_ploidy, float h2d_ms, fm_vcf_batch **out) {
+// Per-thread pinned host scratch: device -> host reads of counters and per-line records land here with truly
+// asynchronous copies (a pageable destination makes every small cudaMemcpyAsync a blocking driver round trip).
+struct PinnedScratch {
+    uint8_t *p = nullptr;
+    size_t cap = 0;
+    uint8_t *ensure(size_t bytes) {
+        if (bytes > cap) {
+            if (p) cudaFreeHost(p);
+            p = nullptr;
+            cap = 0;
+            const size_t want = std::max<size_t>(bytes + bytes / 2, (size_t)1 << 20);
+            CK(cudaHostAlloc((void **)&p, want, cudaHostAllocDefault));
+            cap = want;
+        }
+        return p;
+    }
+    ~PinnedScratch() {
+        if (p) cudaFreeHost(p);
+    }
+};
+thread_local PinnedScratch t_pinned;
+
+__global__ void fm_k_vcf_index_ends(uint32_t *line_start, uint32_t *tabs_before, uint32_t n_lines, uint32_t n_bytes,
+                                    uint32_t tab_total) {
+    // line 0 starts at byte 0; an unterminated last line ends at the end of the text (a terminated one wrote the
+    // same values itself)
+    line_start[0] = 0;
+    tabs_before[0] = 0;
+    line_start[n_lines] = n_bytes;
+    tabs_before[n_lines] = tab_total;
+}
+
+struct VcfShared {  // validated parameters + their device copies, shared by every chunk of a call
+    fm::VcfParams P{};
+    size_t n_kept = 0, max_ploidy = 0;
+    DevBuf<int64_t> d_regions;
+    DevBuf<uint64_t> d_allow, d_mask;
+    DevBuf<int32_t> d_c2s;
+};
+
+void vcf_prepare(VcfShared &sh, const char *chr, const int64_t *regions, size_t n_regions, const uint32_t *kept,
+                 size_t n_kept, uint16_t min_gq, int allow_mode, const int64_t *allow, size_t n_allow, int mask_mode,
+                 const int64_t *mask, size_t n_mask, size_t max_ploidy) {
     if (!chr) fail(FM_ERR_INVALID_ARG, "chr is NULL");
     if (n_regions && !regions) fail(FM_ERR_INVALID_ARG, "regions is NULL");
     if (n_kept && !kept) fail(FM_ERR_INVALID_ARG, "kept_col_indices is NULL");
@@ -2888,8 +2928,7 @@ void vcf_parse_impl(const uint8_t *d_text, size_t n_bytes, char last_byte, const
     for (size_t i = 1; i < n_regions; ++i)
         if (regions[2 * i] < regions[2 * i - 2] || regions[2 * i + 1] < regions[2 * i - 1])
             fail(FM_ERR_INVALID_ARG, "regions must be sorted (process_vcf passes merged, sorted regions)");
-
-    fm::VcfParams P{};
+    fm::VcfParams &P = sh.P;
     {  // normalize_chr_prefix(chr.trim())
         std::string c(chr);
         auto ws = [](char x) { return x == ' ' || (x >= 9 && x <= 13); };
@@ -2902,158 +2941,208 @@ void vcf_parse_impl(const uint8_t *d_text, size_t n_bytes, char last_byte, const
         memcpy(P.chr, c.data(), c.size());
         P.chr_len = (uint32_t)c.size();
     }
-    auto b = std::unique_ptr<fm_vcf_batch, void (*)(fm_vcf_batch *)>(new fm_vcf_batch(), [](fm_vcf_batch *x) {
-        fm_vcf_batch_release(x);
-    });
-    b->device = t_device;
-    b->S = n_kept;
-    b->P = max_ploidy;
-    b->info.n_samples = n_kept;
-    b->info.max_ploidy = max_ploidy;
-    b->info.h2d_ms = h2d_ms;
-    if (n_bytes == 0) {
-        *out = b.release();
-        return;
-    }
-    const int sms = sm_count(t_device);
-    Timer t_index, t_parse;
-    // ---- line index
-    const uint64_t n16 = (n_bytes + 15) / 16;
-    const uint32_t n_tiles = (uint32_t)((n16 + 255) / 256);
-    DevBuf<uint32_t> d_tile(4 * (size_t)n_tiles);  // nl, tab, nl_before, tab_before
-    uint32_t *t_nl = d_tile.p, *t_tab = d_tile.p + n_tiles, *t_nlb = d_tile.p + 2 * (size_t)n_tiles,
-             *t_tabb = d_tile.p + 3 * (size_t)n_tiles;
-    t_index.start();
-    fm::fm_k_vcf_count<<<n_tiles, 256, 0, stream()>>>(reinterpret_cast<const uint4 *>(d_text), n16, t_nl, t_tab);
-    CK(cudaGetLastError());
-    size_t tmp_bytes = 0;
-    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, t_nl, t_nlb, (int)n_tiles, stream()));
-    DevBuf<uint8_t> d_tmp(std::max<size_t>(tmp_bytes, 16));
-    CK(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, t_nl, t_nlb, (int)n_tiles, stream()));
-    CK(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, t_tab, t_tabb, (int)n_tiles, stream()));
-    uint32_t last4[4];
-    CK(cudaMemcpyAsync(&last4[0], t_nl + (n_tiles - 1), 4, cudaMemcpyDeviceToHost, stream()));
-    CK(cudaMemcpyAsync(&last4[1], t_tab + (n_tiles - 1), 4, cudaMemcpyDeviceToHost, stream()));
-    CK(cudaMemcpyAsync(&last4[2], t_nlb + (n_tiles - 1), 4, cudaMemcpyDeviceToHost, stream()));
-    CK(cudaMemcpyAsync(&last4[3], t_tabb + (n_tiles - 1), 4, cudaMemcpyDeviceToHost, stream()));
-    CK(cudaStreamSynchronize(stream()));
-    const uint32_t nl_total = last4[0] + last4[2], tab_total = last4[1] + last4[3];
-    const size_t n_lines = (size_t)nl_total + (last_byte != '\n' ? 1 : 0);
-    DevBuf<uint32_t> d_ls(n_lines + 1), d_tb(n_lines + 1);
-    {
-        const uint32_t zero = 0, endv[2] = {(uint32_t)n_bytes, tab_total};
-        CK(cudaMemcpyAsync(d_ls.p, &zero, 4, cudaMemcpyHostToDevice, stream()));
-        CK(cudaMemcpyAsync(d_tb.p, &zero, 4, cudaMemcpyHostToDevice, stream()));
-        // an unterminated last line ends at the end of the text (a terminated one wrote the same values)
-        CK(cudaMemcpyAsync(d_ls.p + n_lines, &endv[0], 4, cudaMemcpyHostToDevice, stream()));
-        CK(cudaMemcpyAsync(d_tb.p + n_lines, &endv[1], 4, cudaMemcpyHostToDevice, stream()));
-    }
-    fm::fm_k_vcf_index<<<n_tiles, 256, 0, stream()>>>(reinterpret_cast<const uint4 *>(d_text), n16, t_nlb, t_tabb,
-                                                      d_ls.p, d_tb.p);
-    CK(cudaGetLastError());
-    t_index.stop();
-    g_launches += 2;
-    // ---- parameters
     std::vector<uint64_t> allow_n, mask_n;
     if (allow_mode == FM_VCF_INTERVALS) allow_n = vcf_normalise_intervals(allow, n_allow, false);
     if (mask_mode == FM_VCF_INTERVALS) mask_n = vcf_normalise_intervals(mask, n_mask, true);
-    DevBuf<int64_t> d_regions(std::max<size_t>(2 * n_regions, 2));
-    DevBuf<uint64_t> d_allow(std::max<size_t>(allow_n.size(), 2)), d_mask(std::max<size_t>(mask_n.size(), 2));
-    d_regions.upload(regions, 2 * n_regions);
-    d_allow.upload(allow_n.data(), allow_n.size());
-    d_mask.upload(mask_n.data(), mask_n.size());
+    sh.d_regions.alloc(std::max<size_t>(2 * n_regions, 2));
+    sh.d_allow.alloc(std::max<size_t>(allow_n.size(), 2));
+    sh.d_mask.alloc(std::max<size_t>(mask_n.size(), 2));
+    sh.d_regions.upload(regions, 2 * n_regions);
+    sh.d_allow.upload(allow_n.data(), allow_n.size());
+    sh.d_mask.upload(mask_n.data(), mask_n.size());
     const int32_t max_idx = n_kept ? (int32_t)kept[n_kept - 1] : -1;
     std::vector<int32_t> col2slot((size_t)(max_idx + 1), -1);
     for (size_t i = 0; i < n_kept; ++i) col2slot[kept[i]] = (int32_t)i;
-    DevBuf<int32_t> d_c2s(std::max<size_t>(col2slot.size(), 1));
-    d_c2s.upload(col2slot.data(), col2slot.size());
-    P.text = d_text;
-    P.line_start = d_ls.p;
-    P.tabs_before = d_tb.p;
-    P.n_lines = (uint32_t)n_lines;
-    P.regions = d_regions.p;
+    sh.d_c2s.alloc(std::max<size_t>(col2slot.size(), 1));
+    sh.d_c2s.upload(col2slot.data(), col2slot.size());
+    CK(cudaStreamSynchronize(stream()));  // the host vectors above go out of scope
+    P.regions = sh.d_regions.p;
     P.n_regions = (uint32_t)n_regions;
     P.allow_mode = allow_mode;
     P.mask_mode = mask_mode;
-    P.allow = d_allow.p;
-    P.mask = d_mask.p;
+    P.allow = sh.d_allow.p;
+    P.mask = sh.d_mask.p;
     P.n_allow = (uint32_t)(allow_n.size() / 2);
     P.n_mask = (uint32_t)(mask_n.size() / 2);
     P.max_idx = max_idx;
     P.min_gq = min_gq;
     P.n_samples = (uint32_t)n_kept;
     P.max_ploidy = (uint32_t)max_ploidy;
-    P.col2slot = d_c2s.p;
-    // ---- fixed fields, row assignment, sample fields
+    P.col2slot = sh.d_c2s.p;
+    sh.n_kept = n_kept;
+    sh.max_ploidy = max_ploidy;
+}
+
+struct VcfChunkOut {
+    std::vector<fm::VcfLine> recs;  // per line of the chunk
+    std::vector<uint32_t> rows;     // chunk-local row of every line
+    uint8_t *d_gt = nullptr;        // [n_rows][S][P]
+    size_t n_rows = 0;
+    float index_ms = 0.f, parse_ms = 0.f;
+};
+
+// One chunk of whole lines resident at d_text (16-byte aligned, zero-padded): line index, fixed fields, rows, samples.
+void vcf_chunk(const VcfShared &sh, const uint8_t *d_text, size_t n_bytes, char last_byte, VcfChunkOut &out) {
+    if (n_bytes == 0) return;
+    const int sms = sm_count(t_device);
+    Timer t_index, t_parse;
+    const uint64_t n16 = (n_bytes + 15) / 16;
+    const uint32_t n_tiles = (uint32_t)((n16 + 255) / 256);
+    // tile counts with one zero element appended, so that the exclusive scans end in the totals
+    const size_t nt1 = (size_t)n_tiles + 1;
+    DevBuf<uint32_t> d_tile(4 * nt1);  // nl, tab, nl_before, tab_before
+    uint32_t *t_nl = d_tile.p, *t_tab = d_tile.p + nt1, *t_nlb = d_tile.p + 2 * nt1, *t_tabb = d_tile.p + 3 * nt1;
+    uint32_t *h_tot = reinterpret_cast<uint32_t *>(t_pinned.ensure(64));
+    t_index.start();
+    CK(cudaMemsetAsync(t_nl + n_tiles, 0, 4, stream()));
+    CK(cudaMemsetAsync(t_tab + n_tiles, 0, 4, stream()));
+    fm::fm_k_vcf_count<<<n_tiles, 256, 0, stream()>>>(reinterpret_cast<const uint4 *>(d_text), n16, t_nl, t_tab);
+    CK(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, t_nl, t_nlb, (int)(2 * nt1), stream()));
+    DevBuf<uint8_t> d_tmp(std::max<size_t>(tmp_bytes, 16));
+    // one scan over [nl..., 0, tab..., 0]: nl_before[k] for the first half; the second half is offset by the
+    // newline total, which fm_k_vcf_index subtracts through tab_before[0]
+    CK(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, t_nl, t_nlb, (int)(2 * nt1), stream()));
+    CK(cudaMemcpyAsync(h_tot, t_nlb + n_tiles, 4, cudaMemcpyDeviceToHost, stream()));            // newline total
+    CK(cudaMemcpyAsync(h_tot + 1, t_tabb + n_tiles, 4, cudaMemcpyDeviceToHost, stream()));        // + tab total
+    CK(cudaStreamSynchronize(stream()));
+    const uint32_t nl_total = h_tot[0], tab_total = h_tot[1] - h_tot[0];
+    const size_t n_lines = (size_t)nl_total + (last_byte != '\n' ? 1 : 0);
+    DevBuf<uint32_t> d_ls(n_lines + 1), d_tb(n_lines + 1);
+    fm_k_vcf_index_ends<<<1, 1, 0, stream()>>>(d_ls.p, d_tb.p, (uint32_t)n_lines, (uint32_t)n_bytes, tab_total);
+    CK(cudaGetLastError());
+    fm::fm_k_vcf_index<<<n_tiles, 256, 0, stream()>>>(reinterpret_cast<const uint4 *>(d_text), n16, t_nlb, t_tabb,
+                                                      nl_total, d_ls.p, d_tb.p);
+    CK(cudaGetLastError());
+    t_index.stop();
+    g_launches += 3;
+    fm::VcfParams P = sh.P;
+    P.text = d_text;
+    P.line_start = d_ls.p;
+    P.tabs_before = d_tb.p;
+    P.n_lines = (uint32_t)n_lines;
     DevBuf<fm::VcfLine> d_recs(n_lines);
-    DevBuf<uint32_t> d_flag(n_lines), d_row(n_lines);
+    DevBuf<uint32_t> d_flag(n_lines + 1), d_row(n_lines + 1);  // one zero flag appended: the scan ends in the total
     t_parse.start();
     {
         const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_lines + 7) / 8, 32ull * sms);
         fm::fm_k_vcf_fixed<<<blocks, 256, 0, stream()>>>(P, d_recs.p);
         CK(cudaGetLastError());
-        fm_k_vcf_rowflag<<<(uint32_t)((n_lines + 255) / 256), 256, 0, stream()>>>(d_recs.p, (uint32_t)n_lines, d_flag.p);
+        fm_k_vcf_rowflag<<<(uint32_t)((n_lines + 256) / 256), 256, 0, stream()>>>(d_recs.p, (uint32_t)n_lines, d_flag.p);
         CK(cudaGetLastError());
     }
-    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_flag.p, d_row.p, (int)n_lines, stream()));
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_flag.p, d_row.p, (int)(n_lines + 1), stream()));
     DevBuf<uint8_t> d_tmp2(std::max<size_t>(tmp_bytes, 16));
-    CK(cub::DeviceScan::ExclusiveSum(d_tmp2.p, tmp_bytes, d_flag.p, d_row.p, (int)n_lines, stream()));
-    uint32_t lastrow[2];
-    CK(cudaMemcpyAsync(&lastrow[0], d_flag.p + (n_lines - 1), 4, cudaMemcpyDeviceToHost, stream()));
-    CK(cudaMemcpyAsync(&lastrow[1], d_row.p + (n_lines - 1), 4, cudaMemcpyDeviceToHost, stream()));
+    CK(cub::DeviceScan::ExclusiveSum(d_tmp2.p, tmp_bytes, d_flag.p, d_row.p, (int)(n_lines + 1), stream()));
+    CK(cudaMemcpyAsync(h_tot + 2, d_row.p + n_lines, 4, cudaMemcpyDeviceToHost, stream()));
     CK(cudaStreamSynchronize(stream()));
-    const size_t n_rows = (size_t)lastrow[0] + lastrow[1];
-    const size_t row_bytes = n_kept * max_ploidy;
-    b->n_lines = n_lines;
-    b->n_rows = n_rows;
-    b->d_gt = static_cast<uint8_t *>(dev_alloc(std::max<size_t>(n_rows * row_bytes, 16)));
+    out.n_rows = h_tot[2];
+    const size_t row_bytes = sh.n_kept * sh.max_ploidy;
+    out.d_gt = static_cast<uint8_t *>(dev_alloc(std::max<size_t>(out.n_rows * row_bytes, 16)));
     {
         const uint32_t blocks = (uint32_t)std::min<uint64_t>(n_lines, 16ull * sms);
-        fm::fm_k_vcf_samples<<<blocks, 256, 0, stream()>>>(P, d_recs.p, d_row.p, b->d_gt,
-                                                             (uint32_t)(((n_bytes + 15) / 16) * 16 + 16));
+        fm::fm_k_vcf_samples<<<blocks, 256, 0, stream()>>>(P, d_recs.p, d_row.p, out.d_gt,
+                                                           (uint32_t)(((n_bytes + 15) / 16) * 16 + 16));
         CK(cudaGetLastError());
     }
     t_parse.stop();
     g_launches += 3;
-    // ---- host: statistics, errors, output order
-    std::vector<fm::VcfLine> recs(n_lines);
-    std::vector<uint32_t> rows(n_lines);
-    d_recs.download(recs.data(), n_lines);
-    d_row.download(rows.data(), n_lines);
-    CK(cudaStreamSynchronize(stream()));
+    {
+        uint8_t *hp = t_pinned.ensure(64 + n_lines * (sizeof(fm::VcfLine) + 4));  // h_tot was consumed above
+        CK(cudaMemcpyAsync(hp, d_recs.p, n_lines * sizeof(fm::VcfLine), cudaMemcpyDeviceToHost, stream()));
+        CK(cudaMemcpyAsync(hp + n_lines * sizeof(fm::VcfLine), d_row.p, n_lines * 4, cudaMemcpyDeviceToHost, stream()));
+        CK(cudaStreamSynchronize(stream()));
+        const fm::VcfLine *hr = reinterpret_cast<const fm::VcfLine *>(hp);
+        const uint32_t *hw = reinterpret_cast<const uint32_t *>(hp + n_lines * sizeof(fm::VcfLine));
+        out.recs.assign(hr, hr + n_lines);
+        out.rows.assign(hw, hw + n_lines);
+    }
+    out.index_ms = t_index.ms();
+    out.parse_ms = t_parse.ms();
+}
+
+// Statistics, errors and the output order over the chunks of a call (in text order).
+void vcf_finish(const VcfShared &sh, std::vector<VcfChunkOut> &chunks, float h2d_ms, fm_vcf_batch **out) {
+    const size_t n_kept = sh.n_kept, max_ploidy = sh.max_ploidy, row_bytes = n_kept * max_ploidy;
+    auto b = std::unique_ptr<fm_vcf_batch, void (*)(fm_vcf_batch *)>(new fm_vcf_batch(), [](fm_vcf_batch *x) {
+        fm_vcf_batch_release(x);
+    });
+    b->device = t_device;
+    b->S = n_kept;
+    b->P = max_ploidy;
     fm_vcf_info &I = b->info;
+    I.n_samples = n_kept;
+    I.max_ploidy = max_ploidy;
+    I.h2d_ms = h2d_ms;
+    size_t n_lines = 0, n_rows = 0;
+    for (auto &c : chunks) {
+        n_lines += c.recs.size();
+        n_rows += c.n_rows;
+        I.index_ms += c.index_ms;
+        I.parse_ms += c.parse_ms;
+    }
+    b->n_lines = n_lines;
+    b->n_rows = n_rows;
     I.n_lines = n_lines;
-    I.index_ms = t_index.ms();
-    I.parse_ms = t_parse.ms();
-    std::vector<uint32_t> keep;  // line indices of the variants
-    for (size_t li = 0; li < n_lines; ++li) {
-        const fm::VcfLine &r = recs[li];
-        if (r.status == fm::VCF_SKIP) continue;
-        if (r.status != fm::VCF_CAND) {
-            b->err_line.push_back(li);
-            b->err_code.push_back(r.status);
-            // field count for the two format errors, the offending 1-based POS otherwise
-            b->err_aux.push_back(r.status <= fm::VCF_E_MISSING_COLUMN ? r.pos0 : (int64_t)((uint64_t)r.pos0 + 1));
-            continue;
+    // genotype rows of all chunks in one buffer
+    if (chunks.size() == 1) {
+        b->d_gt = chunks[0].d_gt;
+        chunks[0].d_gt = nullptr;
+    } else if (!chunks.empty()) {
+        b->d_gt = static_cast<uint8_t *>(dev_alloc(std::max<size_t>(n_rows * row_bytes, 16)));
+        size_t r0 = 0;
+        for (auto &c : chunks) {
+            if (c.n_rows && row_bytes)
+                CK(cudaMemcpyAsync(b->d_gt + r0 * row_bytes, c.d_gt, c.n_rows * row_bytes, cudaMemcpyDeviceToDevice,
+                                   stream()));
+            r0 += c.n_rows;
         }
-        const bool indel = r.indel & 1;
-        I.total_variants++;
-        if (r.flags & 2) I.filtered_due_to_allow++;
-        if (r.flags & 1) I.filtered_due_to_mask++;
-        if (r.indel & 2) I.mnp_variants++;
-        if (r.flags & 4) I.low_gq_variants++;
-        if (r.flags & 8) I.missing_data_variants++;
-        I.total_data_points += n_kept;
-        I.missing_data_points += r.missing_points;
-        if (r.missing_points) b->pos_missing.push_back(r.pos0);
-        if (r.flags != 0 || indel) {
-            I.filtered_variants++;
-            b->pos_filtered.push_back(r.pos0);
+        CK(cudaStreamSynchronize(stream()));
+        for (auto &c : chunks) {
+            dev_free(c.d_gt);
+            c.d_gt = nullptr;
         }
-        if (!indel) keep.push_back((uint32_t)li);
+    }
+    struct Kept {
+        const fm::VcfLine *r;
+        uint32_t row;
+    };
+    std::vector<Kept> keep;
+    keep.reserve(n_rows);
+    size_t line0 = 0, row0 = 0;
+    for (auto &c : chunks) {
+        for (size_t li = 0; li < c.recs.size(); ++li) {
+            const fm::VcfLine &r = c.recs[li];
+            if (r.status == fm::VCF_SKIP) continue;
+            if (r.status != fm::VCF_CAND) {
+                b->err_line.push_back(line0 + li);
+                b->err_code.push_back(r.status);
+                // field count for the two format errors, the offending 1-based POS otherwise
+                b->err_aux.push_back(r.status <= fm::VCF_E_MISSING_COLUMN ? r.pos0 : (int64_t)((uint64_t)r.pos0 + 1));
+                continue;
+            }
+            const bool indel = r.indel & 1;
+            I.total_variants++;
+            if (r.flags & 2) I.filtered_due_to_allow++;
+            if (r.flags & 1) I.filtered_due_to_mask++;
+            if (r.indel & 2) I.mnp_variants++;
+            if (r.flags & 4) I.low_gq_variants++;
+            if (r.flags & 8) I.missing_data_variants++;
+            I.total_data_points += n_kept;
+            I.missing_data_points += r.missing_points;
+            if (r.missing_points) b->pos_missing.push_back(r.pos0);
+            if (r.flags != 0 || indel) {
+                I.filtered_variants++;
+                b->pos_filtered.push_back(r.pos0);
+            }
+            if (!indel) keep.push_back(Kept{&r, (uint32_t)(row0 + c.rows[li])});
+        }
+        line0 += c.recs.size();
+        row0 += c.n_rows;
     }
     auto uniq = [](std::vector<int64_t> &v) {
-        std::sort(v.begin(), v.end());
+        if (!std::is_sorted(v.begin(), v.end())) std::sort(v.begin(), v.end());
         v.erase(std::unique(v.begin(), v.end()), v.end());
     };
     uniq(b->pos_missing);
@@ -3061,34 +3150,35 @@ void vcf_parse_impl(const uint8_t *d_text, size_t n_bytes, char last_byte, const
     I.n_positions_with_missing = b->pos_missing.size();
     I.n_filtered_positions = b->pos_filtered.size();
     I.n_errors = b->err_line.size();
-    // sort by position (stable), ties by the variant's compressed genotype bytes (process.rs:4377-4386)
-    std::stable_sort(keep.begin(), keep.end(), [&](uint32_t x, uint32_t y) { return recs[x].pos0 < recs[y].pos0; });
+    // sort by position (stable), ties by the variant's compressed genotype bytes (process.rs:4377-4386);
+    // a position-sorted VCF only needs the tie scan
+    auto by_pos = [](const Kept &x, const Kept &y) { return x.r->pos0 < y.r->pos0; };
+    if (!std::is_sorted(keep.begin(), keep.end(), by_pos)) std::stable_sort(keep.begin(), keep.end(), by_pos);
     for (size_t i = 0; i < keep.size();) {
         size_t j = i + 1;
-        while (j < keep.size() && recs[keep[j]].pos0 == recs[keep[i]].pos0) ++j;
+        while (j < keep.size() && keep[j].r->pos0 == keep[i].r->pos0) ++j;
         if (j - i > 1 && row_bytes) {
-            std::unordered_map<uint32_t, std::vector<uint8_t>> data;  // compact CompressedGenotypes::data
+            std::unordered_map<uint32_t, std::vector<uint8_t>> data;  // row -> compact CompressedGenotypes::data
             std::vector<uint8_t> raw(row_bytes);
             for (size_t k = i; k < j; ++k) {
-                const uint32_t li = keep[k];
-                CK(cudaMemcpy(raw.data(), b->d_gt + (size_t)rows[li] * row_bytes, row_bytes, cudaMemcpyDeviceToHost));
-                const size_t st = std::max<size_t>(recs[li].stride, 1);
-                std::vector<uint8_t> c(n_kept * st);
+                CK(cudaMemcpy(raw.data(), b->d_gt + (size_t)keep[k].row * row_bytes, row_bytes, cudaMemcpyDeviceToHost));
+                const size_t st = std::max<size_t>(keep[k].r->stride, 1);
+                std::vector<uint8_t> cdat(n_kept * st);
                 for (size_t s = 0; s < n_kept; ++s)
-                    for (size_t q = 0; q < st; ++q) c[s * st + q] = raw[s * max_ploidy + q];
-                data.emplace(li, std::move(c));
+                    for (size_t q = 0; q < st; ++q) cdat[s * st + q] = raw[s * max_ploidy + q];
+                data.emplace(keep[k].row, std::move(cdat));
             }
             std::stable_sort(keep.begin() + i, keep.begin() + j,
-                             [&](uint32_t x, uint32_t y) { return data[x] < data[y]; });
+                             [&](const Kept &x, const Kept &y) { return data[x.row] < data[y.row]; });
         }
         i = j;
     }
     b->var.resize(keep.size());
     b->order.resize(keep.size());
     for (size_t i = 0; i < keep.size(); ++i) {
-        b->var[i] = recs[keep[i]];
+        b->var[i] = *keep[i].r;
         if (b->var[i].stride == 0 && n_kept) b->var[i].stride = 1;  // CompressedGenotypes::new: max_ploidy.max(1)
-        b->order[i] = rows[keep[i]];
+        b->order[i] = keep[i].row;
     }
     I.n_variants = keep.size();
     b->d_order = static_cast<uint32_t *>(dev_alloc(std::max<size_t>(keep.size(), 4) * 4));
@@ -3097,6 +3187,14 @@ void vcf_parse_impl(const uint8_t *d_text, size_t n_bytes, char last_byte, const
     CK(cudaStreamSynchronize(stream()));
     *out = b.release();
 }
+
+struct VcfChunkGuard {  // frees chunk buffers on every exit path
+    std::vector<VcfChunkOut> v;
+    ~VcfChunkGuard() {
+        for (auto &c : v)
+            if (c.d_gt) dev_free(c.d_gt);
+    }
+};
 
 }  // namespace
 
@@ -3109,16 +3207,24 @@ fm_status fm_vcf_parse_device(const char *d_text, size_t n_bytes, char host_last
         if (!out) fail(FM_ERR_INVALID_ARG, "out is NULL");
         *out = nullptr;
         if (n_bytes && !d_text) fail(FM_ERR_INVALID_ARG, "text is NULL");
-        if (n_bytes >= (1ull << 31)) fail(FM_ERR_UNSUPPORTED, "more than 2^31 bytes per call: chunk on line boundaries");
+        if (n_bytes >= (1ull << 31)) fail(FM_ERR_UNSUPPORTED, "more than 2^31 bytes of device text per call");
         if (reinterpret_cast<uintptr_t>(d_text) & 15u) fail(FM_ERR_INVALID_ARG, "device text must be 16-byte aligned");
         require_device();
         CK(cudaSetDevice(t_device));
-        vcf_parse_impl(reinterpret_cast<const uint8_t *>(d_text), n_bytes, host_last_byte, chr, regions, n_regions,
-                       kept_col_indices, n_kept, min_gq, allow_mode, allow, n_allow, mask_mode, mask, n_mask,
-                       max_ploidy, 0.f, out);
+        VcfShared sh;
+        vcf_prepare(sh, chr, regions, n_regions, kept_col_indices, n_kept, min_gq, allow_mode, allow, n_allow, mask_mode,
+                    mask, n_mask, max_ploidy);
+        VcfChunkGuard g;
+        if (n_bytes) {
+            g.v.resize(1);
+            vcf_chunk(sh, reinterpret_cast<const uint8_t *>(d_text), n_bytes, host_last_byte, g.v[0]);
+        }
+        vcf_finish(sh, g.v, 0.f, out);
     });
 }
 
+// Host text: cut into chunks of whole lines; an upload thread copies chunk after chunk on its own stream while
+// this thread indexes and parses the chunks that have arrived (the stage is PCIe-bound: parse hides under the copy).
 fm_status fm_vcf_parse(const char *text, size_t n_bytes, const char *chr, const int64_t *regions, size_t n_regions,
                        const uint32_t *kept_col_indices, size_t n_kept, uint16_t min_gq, int allow_mode,
                        const int64_t *allow, size_t n_allow, int mask_mode, const int64_t *mask, size_t n_mask,
@@ -3127,22 +3233,95 @@ fm_status fm_vcf_parse(const char *text, size_t n_bytes, const char *chr, const 
         if (!out) fail(FM_ERR_INVALID_ARG, "out is NULL");
         *out = nullptr;
         if (n_bytes && !text) fail(FM_ERR_INVALID_ARG, "text is NULL");
-        if (n_bytes >= (1ull << 31)) fail(FM_ERR_UNSUPPORTED, "more than 2^31 bytes per call: chunk on line boundaries");
+        if (n_bytes >= (1ull << 40)) fail(FM_ERR_UNSUPPORTED, "more than 2^40 bytes per call");
         require_device();
         CK(cudaSetDevice(t_device));
-        const size_t body = ((n_bytes + 15) / 16) * 16, padded = body + 32;
-        DevBuf<uint8_t> d_text(padded);
-        Timer tm;
-        tm.start();
-        const size_t tail = body >= 16 ? body - 16 : 0;  // the partial last 16-byte word and the padding read zero
-        CK(cudaMemsetAsync(d_text.p + tail, 0, padded - tail, stream()));
-        h2d(d_text.p, text, n_bytes, stream());
-        tm.stop();
-        const float ms = tm.ms();
-        t_tim.h2d_ms += ms;
-        vcf_parse_impl(d_text.p, n_bytes, n_bytes ? text[n_bytes - 1] : '\n', chr, regions, n_regions,
-                       kept_col_indices, n_kept, min_gq, allow_mode, allow, n_allow, mask_mode, mask, n_mask,
-                       max_ploidy, ms, out);
+        VcfShared sh;
+        vcf_prepare(sh, chr, regions, n_regions, kept_col_indices, n_kept, min_gq, allow_mode, allow, n_allow, mask_mode,
+                    mask, n_mask, max_ploidy);
+        // chunk boundaries on line ends
+        const size_t target = (size_t)env_u32_early("FM_VCF_CHUNK_MB", 64) << 20;
+        std::vector<size_t> cut{0};
+        while (cut.back() < n_bytes) {
+            size_t end = cut.back() + target;
+            if (end >= n_bytes) {
+                end = n_bytes;
+            } else {
+                const void *nl = memchr(text + end, '\n', std::min<size_t>(n_bytes - end, (size_t)1 << 30));
+                end = nl ? (size_t)(static_cast<const char *>(nl) - text) + 1 : n_bytes;
+            }
+            if (end - cut.back() >= (1ull << 31)) fail(FM_ERR_UNSUPPORTED, "a single line run exceeds 2^31 bytes");
+            cut.push_back(end);
+        }
+        const size_t nc = cut.size() - 1;
+        // device layout: every chunk starts 16-byte aligned and is followed by >= 32 zero bytes
+        std::vector<size_t> doff(nc + 1, 0);
+        for (size_t c = 0; c < nc; ++c) doff[c + 1] = doff[c] + ((cut[c + 1] - cut[c] + 15) / 16) * 16 + 32;
+        DevBuf<uint8_t> d_text(std::max<size_t>(doff[nc], 64));
+        VcfChunkGuard g;
+        g.v.resize(nc);
+        const int dev = t_device;
+        std::vector<cudaEvent_t> ev(nc, nullptr);
+        std::atomic<size_t> recorded{0};
+        std::atomic<int> copy_err{0};
+        std::string copy_msg;
+        float h2d_ms = 0.f;
+        cudaStream_t cs = nullptr;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        auto cleanup = [&] {
+            for (auto &e : ev)
+                if (e) cudaEventDestroy(e);
+            if (e0) cudaEventDestroy(e0);
+            if (e1) cudaEventDestroy(e1);
+            if (cs) cudaStreamDestroy(cs);
+        };
+        try {
+            CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+            CK(cudaEventCreate(&e0));
+            CK(cudaEventCreate(&e1));
+            for (auto &e : ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            CK(cudaStreamSynchronize(stream()));  // d_text may be a recycled block still in use on this stream
+            std::thread uploader([&] {
+                try {
+                    CK(cudaSetDevice(dev));
+                    CK(cudaEventRecord(e0, cs));
+                    for (size_t c = 0; c < nc; ++c) {
+                        const size_t nb = cut[c + 1] - cut[c], body = ((nb + 15) / 16) * 16;
+                        const size_t tail = body >= 16 ? body - 16 : 0;  // partial last word + padding read zero
+                        CK(cudaMemsetAsync(d_text.p + doff[c] + tail, 0, body + 32 - tail, cs));
+                        h2d(d_text.p + doff[c], text + cut[c], nb, cs);
+                        CK(cudaEventRecord(ev[c], cs));
+                        recorded.store(c + 1, std::memory_order_release);
+                    }
+                    CK(cudaEventRecord(e1, cs));
+                    CK(cudaStreamSynchronize(cs));
+                } catch (const FmError &e) {
+                    copy_msg = e.msg;
+                    copy_err.store(e.code ? e.code : FM_ERR_CUDA);
+                    recorded.store(nc, std::memory_order_release);
+                }
+            });
+            try {
+                for (size_t c = 0; c < nc; ++c) {
+                    while (recorded.load(std::memory_order_acquire) <= c && !copy_err.load()) std::this_thread::yield();
+                    if (copy_err.load()) break;
+                    CK(cudaStreamWaitEvent(stream(), ev[c], 0));
+                    vcf_chunk(sh, d_text.p + doff[c], cut[c + 1] - cut[c], text[cut[c + 1] - 1], g.v[c]);
+                }
+            } catch (...) {
+                uploader.join();
+                throw;
+            }
+            uploader.join();
+            if (copy_err.load()) fail(copy_err.load(), copy_msg);
+            if (nc) CK(cudaEventElapsedTime(&h2d_ms, e0, e1));
+        } catch (...) {
+            cleanup();
+            throw;
+        }
+        cleanup();
+        t_tim.h2d_ms += h2d_ms;
+        vcf_finish(sh, g.v, h2d_ms, out);
     });
 }
 

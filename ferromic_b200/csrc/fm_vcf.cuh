@@ -119,8 +119,9 @@ fm_k_vcf_count(const uint4 *__restrict__ text16, uint64_t n16, uint32_t *__restr
 
 __global__ void __launch_bounds__(256)
 fm_k_vcf_index(const uint4 *__restrict__ text16, uint64_t n16, const uint32_t *__restrict__ nl_before_tile,
-               const uint32_t *__restrict__ tab_before_tile, uint32_t *__restrict__ line_start,
+               const uint32_t *__restrict__ tab_before_tile, uint32_t tab_bias, uint32_t *__restrict__ line_start,
                uint32_t *__restrict__ tabs_before) {
+    // tab_before_tile comes from one scan over [newline counts, 0, tab counts, 0]: subtract the newline total
     __shared__ uint32_t s[9];
     const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
     uint32_t nlm = 0, tbm = 0;
@@ -132,7 +133,7 @@ fm_k_vcf_index(const uint4 *__restrict__ text16, uint64_t n16, const uint32_t *_
     uint32_t total;
     const uint32_t ex = vcf_block_scan(__popc(nlm) | (__popc(tbm) << 16), s, total);
     uint32_t k = nl_before_tile[blockIdx.x] + (ex & 0xFFFFu);
-    const uint32_t tb = tab_before_tile[blockIdx.x] + (ex >> 16);
+    const uint32_t tb = tab_before_tile[blockIdx.x] - tab_bias + (ex >> 16);
     while (nlm) {
         const int b = __ffs(nlm) - 1;
         nlm &= nlm - 1;

@@ -63,27 +63,37 @@ def main():
     reg = np.array([[0, 1 << 40]], dtype=np.int64)
     L = _lib.lib()
     p = lambda x: x.ctypes.data_as(C.c_void_p)
-    best = None
-    for rep in range(a.reps + 1):
-        h = C.c_void_p()
-        t0 = time.perf_counter()
-        _lib.check(L.fm_vcf_parse(C.cast(pinned.data_ptr(), C.c_char_p), len(text), b"1", p(reg), 1, p(kept), len(kept), 30,
-                                  0, None, 0, 0, None, 0, 2, C.byref(h)))
-        wall = (time.perf_counter() - t0) * 1e3
-        info = _lib.VcfInfo()
-        _lib.check(L.fm_vcf_batch_info(h, C.byref(info)))
-        t1 = time.perf_counter()
-        mh = C.c_void_p()
-        _lib.check(L.fm_vcf_batch_matrix(h, 0, C.byref(mh)))
-        L.fm_synchronize()
-        mat_ms = (time.perf_counter() - t1) * 1e3
-        L.fm_matrix_release(mh)
-        L.fm_vcf_batch_release(h)
-        if rep == 0:
-            continue  # warm-up (allocator, first-touch)
-        r = dict(wall_ms=wall, h2d_ms=info.h2d_ms, index_ms=info.index_ms, parse_ms=info.parse_ms, matrix_ms=mat_ms)
-        if best is None or r["wall_ms"] < best["wall_ms"]:
-            best = r
+    def run(reps):
+        best = None
+        for rep in range(reps + 1):
+            h = C.c_void_p()
+            t0 = time.perf_counter()
+            _lib.check(L.fm_vcf_parse(C.cast(pinned.data_ptr(), C.c_char_p), len(text), b"1", p(reg), 1, p(kept), len(kept),
+                                      30, 0, None, 0, 0, None, 0, 2, C.byref(h)))
+            wall = (time.perf_counter() - t0) * 1e3
+            info = _lib.VcfInfo()
+            _lib.check(L.fm_vcf_batch_info(h, C.byref(info)))
+            t1 = time.perf_counter()
+            mh = C.c_void_p()
+            _lib.check(L.fm_vcf_batch_matrix(h, 0, C.byref(mh)))
+            L.fm_synchronize()
+            mat_ms = (time.perf_counter() - t1) * 1e3
+            L.fm_matrix_release(mh)
+            L.fm_vcf_batch_release(h)
+            if rep == 0:
+                continue  # warm-up (allocator, first-touch)
+            r = dict(wall_ms=wall, h2d_ms=info.h2d_ms, index_ms=info.index_ms, parse_ms=info.parse_ms, matrix_ms=mat_ms)
+            if best is None or r["wall_ms"] < best["wall_ms"]:
+                best = r
+        return best, info
+
+    # kernel times: the whole text as one chunk (no host round trips inside the event brackets);
+    # end-to-end wall time: the default chunked pipeline (upload thread || index + parse)
+    os.environ["FM_VCF_CHUNK_MB"] = "4000"
+    kern, info = run(a.reps)
+    del os.environ["FM_VCF_CHUNK_MB"]
+    best, info = run(a.reps)
+    best["index_ms"], best["parse_ms"], best["wall_one_chunk_ms"] = kern["index_ms"], kern["parse_ms"], kern["wall_ms"]
     assert info.n_variants == a.lines and info.n_errors == 0 and info.low_gq_variants == 0  # every GQ is >= 30
     gb = len(text) / 1e9
     out = {"what": "fm_vcf_parse on 1000G-shaped text", "lines": a.lines, "samples": a.samples, "text_GB": gb,
