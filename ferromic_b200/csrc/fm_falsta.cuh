@@ -38,7 +38,7 @@ __host__ __device__ inline uint32_t fm_falsta_token(double v, int mode, char *bu
         if (mode == FM_FALSTA_FST) return put(neg ? "-Infinity" : "Infinity");
         return put(neg ? "-inf" : "inf");
     }
-    if (ex == 0 && frac == 0) return put("0");  // v == 0.0 (either sign)
+    if (ex == 0 && frac == 0 && mode != FM_FALSTA_TSV) return put("0");  // v == 0.0 (either sign)
     const unsigned long long m = ex ? (frac | (1ull << 52)) : frac;
     const int e = ex ? (int)ex - 1075 : -1074;
     unsigned __int128 N = (unsigned __int128)m * 1000000u;  // < 2^73

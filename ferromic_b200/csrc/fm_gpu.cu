@@ -2737,7 +2737,7 @@ fm_status fm_comm_destroy(fm_comm *c) {
 // ------------------------------------------------------------------------------------ FALSTA track bodies
 fm_status fm_falsta_format_value(double value, int mode, char *buf, size_t capacity, size_t *len_out) {
     if (!buf || !len_out || capacity < 56) return FM_ERR_INVALID_ARG;
-    if (mode != FM_FALSTA_DIVERSITY && mode != FM_FALSTA_FST) return FM_ERR_INVALID_ARG;
+    if (mode != FM_FALSTA_DIVERSITY && mode != FM_FALSTA_FST && mode != FM_FALSTA_TSV) return FM_ERR_INVALID_ARG;
     *len_out = fm::fm_falsta_token(value, mode, buf);  // the same __host__ __device__ routine the kernels run
     return FM_OK;
 }

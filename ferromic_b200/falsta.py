@@ -15,7 +15,7 @@ import numpy as np
 
 from ._lib import check, lib
 
-DIVERSITY, FST = 0, 1  # FM_FALSTA_DIVERSITY / FM_FALSTA_FST
+DIVERSITY, FST, TSV = 0, 1, 2  # FM_FALSTA_DIVERSITY / FM_FALSTA_FST / FM_FALSTA_TSV
 
 
 def format_value(value: float, mode: int = FST) -> str:
@@ -40,10 +40,17 @@ def track_lines(pos1, values, region_start: int, region_end: int, mode: int) -> 
     lens = (C.c_size_t * T)()
     pp = pos1.ctypes.data_as(C.c_void_p)
     vp = values.ctypes.data_as(C.c_void_p)
-    # worst case per token: sign + 17 integer digits is far beyond these statistics; query instead
-    check(L.fm_falsta_tracks(pp, vp, n, T, region_start, region_end, mode, None, 0, lens, C.byref(total)))
-    out = C.create_string_buffer(max(total.value, 1))
-    check(L.fm_falsta_tracks(pp, vp, n, T, region_start, region_end, mode, out, total.value, lens, C.byref(total)))
+    # one call with a generous capacity (default tokens are 1-2 bytes, `{:.6}` of these statistics stays far below
+    # 24 bytes); an exact-length query + second call only if that was not enough
+    s1 = max(region_start, 1)
+    region_len = max(region_end, s1) - s1 + 1
+    cap = T * (3 * region_len + 26 * min(n, region_len)) + 16
+    out = C.create_string_buffer(cap)
+    st = L.fm_falsta_tracks(pp, vp, n, T, region_start, region_end, mode, out, cap, lens, C.byref(total))
+    if st != 0 and total.value > cap:
+        out = C.create_string_buffer(total.value)
+        st = L.fm_falsta_tracks(pp, vp, n, T, region_start, region_end, mode, out, total.value, lens, C.byref(total))
+    check(st)
     raw = out.raw[: total.value]
     lines, o = [], 0
     for t in range(T):
@@ -122,6 +129,35 @@ def fst_falsta_text(seqname: str, region_start: int, region_end: int,
     return b"".join(out)
 
 
+def _csv_field(f: str) -> str:
+    # csv::Writer, QuoteStyle::Necessary with a tab delimiter
+    if any(c in f for c in '\t"\n\r'):
+        return '"' + f.replace('"', '""') + '"'
+    return f
+
+
+def hudson_tsv_text(rows) -> bytes:
+    """Rows `append_hudson_tsv` writes (process.rs:4006-4041): chr, region_start, region_end, pop1 type, pop1 name,
+    pop2 type, pop2 name, d_xy, pi_pop1, pi_pop2, pi_xy_avg, fst.  rows: (chr, region_start, region_end, pop1_id,
+    pop2_id, d_xy, pi_pop1, pi_pop2, pi_xy_avg, fst); a population id is None, an int (HaplotypeGroup) or a str
+    (Named) (format_population_id, :3692-3698); None / NaN floats print "NA" (format_optional_float, :3702-3713)."""
+    def pop(p):
+        if p is None:
+            return "NA", "NA"
+        if isinstance(p, str):
+            return "NamedPopulation", p
+        return "HaplotypeGroup", str(int(p))
+
+    def flt(v):
+        return "NA" if v is None else format_value(v, TSV)
+
+    out = []
+    for chr_, rs, re_, p1, p2, dxy, pi1, pi2, pixy, fst in rows:
+        f = [str(chr_), str(int(rs)), str(int(re_)), *pop(p1), *pop(p2), flt(dxy), flt(pi1), flt(pi2), flt(pixy), flt(fst)]
+        out.append("\t".join(_csv_field(x) for x in f) + "\n")
+    return "".join(out).encode()
+
+
 def _append_gz(path, text: bytes) -> None:
     # open_append_compressed (process.rs:3723-3729): every call appends one gzip member
     with gzip.open(path, "ab") as f:
@@ -132,6 +168,10 @@ def append_diversity_falsta(path, seqname, region_start, region_end, per_site) -
     if len(per_site) == 0:  # process.rs:3745-3754: warns and returns before the file is opened
         return
     _append_gz(path, diversity_falsta_text(seqname, region_start, region_end, per_site))
+
+
+def append_hudson_tsv(path, rows) -> None:
+    _append_gz(path, hudson_tsv_text(rows))
 
 
 def append_fst_falsta(path, seqname, region_start, region_end, wc_sites, hudson_sites) -> None:

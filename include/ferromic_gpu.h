@@ -311,6 +311,8 @@ fm_status fm_comm_destroy(fm_comm *c);
  * fm_falsta_format_value is the host instance of the same token routine (buf >= 56 bytes). */
 #define FM_FALSTA_DIVERSITY 0
 #define FM_FALSTA_FST 1
+#define FM_FALSTA_TSV 2 /* fm_falsta_format_value only: format_optional_float (process.rs:3702-3713): NaN -> "NA",
+                           everything else `{:.6}` (0.0 -> "0.000000", infinities -> "inf" / "-inf") */
 fm_status fm_falsta_track(const int64_t *pos1, const double *values, size_t n, int64_t region_start,
                           int64_t region_end, int mode, char *out, size_t capacity, size_t *len_out);
 fm_status fm_falsta_tracks(const int64_t *pos1, const double *values, size_t n, size_t n_tracks,

@@ -109,3 +109,29 @@ def fst_falsta_text(seqname: str, region_start: int, region_end: int, wc_sites, 
                                     "hudson_pairwise_fst_hap_0v1_denominator_"), start=1):
             track(head, hudson_sites, col)
     return "".join(out)
+
+
+def format_optional_float(v: Optional[float]) -> str:  # process.rs:3702-3713
+    if v is None or math.isnan(v):
+        return "NA"
+    if math.isinf(v):
+        return "inf" if v > 0 else "-inf"  # Rust's Display for infinities
+    return "%.6f" % v
+
+
+def hudson_tsv_text(rows) -> str:
+    """append_hudson_tsv, process.rs:4006-4041 (csv writer, tab delimiter, no header, quotes only when needed)."""
+    def pop(p):  # format_population_id, process.rs:3692-3698
+        if p is None:
+            return ["NA", "NA"]
+        return ["NamedPopulation", p] if isinstance(p, str) else ["HaplotypeGroup", str(int(p))]
+
+    def q(f):
+        return '"' + f.replace('"', '""') + '"' if any(c in f for c in '\t"\n\r') else f
+
+    out = []
+    for chr_, rs, re_, p1, p2, dxy, pi1, pi2, pixy, fst in rows:
+        f = [str(chr_), str(int(rs)), str(int(re_))] + pop(p1) + pop(p2) + \
+            [format_optional_float(x) for x in (dxy, pi1, pi2, pixy, fst)]
+        out.append("\t".join(q(x) for x in f) + "\n")
+    return "".join(out)

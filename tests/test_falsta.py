@@ -83,6 +83,20 @@ def test_token_routine_matches_correctly_rounded_fixed6():
             assert falsta.format_value(v, falsta.DIVERSITY) == ofa.diversity_token(v), repr(v)
 
 
+def test_hudson_tsv_rows_host_formatting():
+    """append_hudson_tsv (process.rs:4006-4041): host formatting only, through the library's token routine."""
+    from ferromic_b200 import falsta
+    rows = [("chr1", 100, 2000, 0, 1, 0.0123456789, 0.0, None, float("nan"), -0.25),
+            ("7", 1, 5, "EUR", "AFR\tx", 1.0, -0.0, 2.5e-7, float("inf"), 1 / 128),
+            ("X", 10, 20, None, 'q"uote', 0.5, 1e-7, 123456.7890125, -1e-9, 0.9999995)]
+    assert falsta.hudson_tsv_text(rows).decode() == ofa.hudson_tsv_text(rows)
+    first = ofa.hudson_tsv_text(rows).splitlines()[0].split("\t")
+    assert first == ["chr1", "100", "2000", "HaplotypeGroup", "0", "HaplotypeGroup", "1", "0.012346", "0.000000", "NA",
+                     "NA", "-0.250000"]
+    for v in _cases():
+        assert falsta.format_value(v, falsta.TSV) == ofa.format_optional_float(v), repr(v)
+
+
 # ----------------------------------------------------------------------------- device rendering
 def _records(rng, n, lo, hi):
     pos = rng.integers(lo, hi, size=n)
