@@ -45,16 +45,17 @@ def track_lines(pos1, values, region_start: int, region_end: int, mode: int) -> 
     s1 = max(region_start, 1)
     region_len = max(region_end, s1) - s1 + 1
     cap = T * (3 * region_len + 26 * min(n, region_len)) + 16
-    out = C.create_string_buffer(cap)
-    st = L.fm_falsta_tracks(pp, vp, n, T, region_start, region_end, mode, out, cap, lens, C.byref(total))
+    out = np.empty(cap, dtype=np.uint8)  # not zero-filled: the library writes every byte it reports
+    st = L.fm_falsta_tracks(pp, vp, n, T, region_start, region_end, mode, out.ctypes.data_as(C.c_void_p), cap, lens,
+                            C.byref(total))
     if st != 0 and total.value > cap:
-        out = C.create_string_buffer(total.value)
-        st = L.fm_falsta_tracks(pp, vp, n, T, region_start, region_end, mode, out, total.value, lens, C.byref(total))
+        out = np.empty(total.value, dtype=np.uint8)
+        st = L.fm_falsta_tracks(pp, vp, n, T, region_start, region_end, mode, out.ctypes.data_as(C.c_void_p),
+                                total.value, lens, C.byref(total))
     check(st)
-    raw = out.raw[: total.value]
     lines, o = [], 0
     for t in range(T):
-        lines.append(raw[o : o + lens[t]])
+        lines.append(out[o : o + lens[t]].tobytes())
         o += lens[t] + 1
     return lines
 

@@ -27,6 +27,22 @@ def main():
         dt = time.perf_counter() - t0
         best = dt if best is None or dt < best else best
     nbytes = sum(len(l) for l in lines)
+    # the C-ABI call alone (host arrays in, text out into a caller buffer), without the Python line splitting
+    import ctypes as C
+    from ferromic_b200 import _lib
+    L = _lib.lib()
+    cap = nbytes + 64
+    buf = np.empty(cap, dtype=np.uint8)
+    lens = (C.c_size_t * T)()
+    total = C.c_size_t(0)
+    v = np.ascontiguousarray(vals)
+    call = None
+    for _ in range(4):
+        t0 = time.perf_counter()
+        _lib.check(L.fm_falsta_tracks(pos.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), n, T, 1, region_len,
+                                      falsta.FST, buf.ctypes.data_as(C.c_void_p), cap, lens, C.byref(total)))
+        dt = time.perf_counter() - t0
+        call = dt if call is None or dt < call else call
     # CPU: the reference's algorithm (Vec<String> of region length per track, one pass over the records per track)
     small = 200_000
     recs = [(int(p), *vals[:, i]) for i, p in enumerate(pos[pos <= small])]
@@ -36,7 +52,7 @@ def main():
     got = falsta.fst_falsta_text("1", 1, small, recs, []).decode()
     assert got == ref
     print(json.dumps({"what": "fm_falsta_tracks, 6 FST tracks over a 5 Mb region, 150k records", "text_MB": nbytes / 1e6,
-                      "wall_ms": best * 1e3, "text_GBps": nbytes / best / 1e9,
+                      "wall_ms": best * 1e3, "cabi_call_ms": call * 1e3, "text_GBps_cabi": nbytes / call / 1e9,
                       "positions_x_tracks_per_s": region_len * T / best,
                       "cpu_port": {"kind": "port (pure Python)", "region": small, "seconds": cpu_dt,
                                    "positions_x_tracks_per_s": small * T / cpu_dt}}))
