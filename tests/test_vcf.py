@@ -227,6 +227,32 @@ def test_device_parser_edges():
 
 
 @pytest.mark.gpu
+def test_device_parser_alignment_sweep():
+    """Every alignment of the first sample field and of the line end against the 16-byte words / 4 KB tiles the
+    kernels read (INFO padded byte by byte), with lines that span several tiles; text lengths that are exact
+    multiples of 16 and of 4096."""
+    rng = np.random.default_rng(21)
+    n_cols = 1300  # ~9 KB per line: three tiles
+    kept = list(range(9, 9 + n_cols))
+    lines = []
+    for pad in range(0, 40):
+        cols = [GT_POOL[rng.integers(len(GT_POOL))] + ":" + str(int(rng.integers(10, 99))) for _ in range(n_cols)]
+        if pad % 5 == 0:
+            cols[int(rng.integers(n_cols))] = "./.:."
+        lines.append("\t".join(["chr1", str(1000 + pad), ".", "A", "C", ".", "PASS", "I" * pad, "GT:GQ"] + cols))
+    text = "\n".join(lines) + "\n"
+    check_against_oracle(text, "1", REGION, kept, 30)
+    one = lines[0] + "\n"
+    for target in (16 * ((len(one) + 15) // 16 + 1), 4096 * ((len(one) + 4095) // 4096)):
+        f = one.split("\t")
+        f[7] = "I" * (target - len(one))
+        padded = "\t".join(f)
+        assert len(padded) == target
+        check_against_oracle(padded, "1", REGION, kept, 30)
+        check_against_oracle(padded[:-1], "1", REGION, kept, 30)  # unterminated: the last GQ ends the buffer
+
+
+@pytest.mark.gpu
 def test_vcf_text_to_estimators_without_host_round_trip():
     """Raw VCF text -> device parser -> from_variants on the device -> groups -> pi / S / Hudson, against the
     oracle estimators over the oracle-parsed variants."""
