@@ -62,7 +62,7 @@ EXPORTS = [
     "fm_last_error", "fm_version", "fm_device_count", "fm_set_device", "fm_synchronize", "fm_trim_pool",
     "fm_matrix_create", "fm_matrix_create_inband", "fm_matrix_create_device", "fm_matrix_retain", "fm_matrix_release",
     "fm_matrix_info", "fm_ingest_begin", "fm_ingest_add_group", "fm_ingest_add_partition",
-    "fm_ingest_rows", "fm_ingest_finish", "fm_ingest_abort", "fm_group_create", "fm_group_release", "fm_group_capacity", "fm_group_summary",
+    "fm_ingest_rows", "fm_ingest_finish", "fm_ingest_abort", "fm_group_create", "fm_groups_create", "fm_group_release", "fm_group_capacity", "fm_group_summary",
     "fm_group_segregating_sites", "fm_group_pi", "fm_harmonic", "fm_watterson_theta",
     "fm_per_site_diversity", "fm_per_site_diversity_multi", "fm_hudson_pair", "fm_hudson_dxy", "fm_partition_create",
     "fm_partition_release", "fm_wc_fst", "fm_wc_window_sums", "fm_fst_estimate_from_sums", "fm_adjusted_sequence_length", "fm_group_window_sums",
@@ -110,6 +110,7 @@ def lib() -> C.CDLL:
     L.fm_ingest_finish.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.fm_ingest_abort.argtypes = [vp]
     L.fm_group_create.argtypes = [vp, vp, vp, sz, C.POINTER(vp)]
+    L.fm_groups_create.argtypes = [vp, vp, vp, vp, sz, C.POINTER(vp)]
     L.fm_group_release.argtypes = [vp]
     L.fm_group_capacity.argtypes = [vp, C.POINTER(sz)]
     L.fm_group_summary.argtypes = [vp, vp, vp, C.POINTER(u64), C.POINTER(dbl), C.POINTER(u64)]

@@ -238,6 +238,20 @@ class _Matrix:
             self._groups[key] = g
         return g
 
+    def groups(self, lists: Sequence[Sequence[Tuple[int, int]]]) -> List["_Group"]:
+        """Several groups in one pass over the u8 rows (fm_groups_create); cached like `group`."""
+        todo = [tuple(h) for h in lists if tuple(h) not in self._groups]
+        todo = list(dict.fromkeys(todo))
+        if len(todo) > 1:
+            idx = np.asarray([h[0] for hs in todo for h in hs], dtype=np.uint64)
+            side = np.asarray([h[1] for hs in todo for h in hs], dtype=np.uint8)
+            sizes = (C.c_size_t * len(todo))(*[len(hs) for hs in todo])
+            out = (C.c_void_p * len(todo))()
+            check(lib().fm_groups_create(self.handle, _ptr(idx), _ptr(side), sizes, len(todo), out))
+            for hs, h in zip(todo, out):
+                self._groups[hs] = _Group._adopt(self, hs, C.c_void_p(h))
+        return [self.group(h) for h in lists]
+
     def __del__(self):
         try:
             self._groups.clear()

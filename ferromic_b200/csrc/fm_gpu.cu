@@ -1156,7 +1156,8 @@ fm_status fm_matrix_info(const fm_matrix *m, size_t *V, size_t *S, size_t *ploid
 static size_t repack_warp_smem(const fm_matrix *m, uint32_t *row_buf_out, uint32_t *bit_buf_out) {
     const size_t row_buf = ((m->stride + 15) & ~(size_t)15) + 32;
     const size_t bit_buf = (m->has_missing && !m->in_band) ? ((m->stride + 63) / 64 + 2) * 8 : 0;
-    const size_t cnt_buf = 2 * ((m->stride + 31) / 32 + 1) * 4;  // full-row allele / called bit words
+    // full-row allele / called bit words + one group's two plane rows while they are assembled
+    const size_t cnt_buf = 2 * ((m->stride + 31) / 32 + 1) * 4 + 2 * ((m->stride + 127) / 128) * 4 * 4;
     if (row_buf_out) *row_buf_out = (uint32_t)row_buf;
     if (bit_buf_out) *bit_buf_out = (uint32_t)bit_buf;
     return (row_buf + bit_buf + cnt_buf + 15) & ~(size_t)15;
@@ -1223,6 +1224,8 @@ struct RepackSet {  // device-resident descriptor tables of the groups one launc
     fm::CountTable ct{};
     uint32_t *d_ent = nullptr;         // ent_start | ent_word | ent_mask
     uint32_t **d_outs = nullptr;       // alt_out[n] | cnt_out[n]
+    uint4 *d_plan = nullptr;           // compress plans of the biallelic plane groups (two uint4 per touched row word)
+    bool need_row_bits = false;
     void build(const std::vector<fm_group *> &groups) {
         gs = groups;
         if (gs.empty()) return;
@@ -1230,6 +1233,10 @@ struct RepackSet {  // device-resident descriptor tables of the groups one launc
         std::vector<fm::RepackGroup> h;
         std::vector<uint32_t> ent_start{0}, ent_word, ent_mask;
         std::vector<uint32_t *> outs_a, outs_c;
+        std::vector<uint32_t> plan;            // 8 words per entry
+        std::vector<size_t> plan_at, plan_len;  // per plane group: first entry, entries (0 = no plan)
+        static const uint32_t no_plan = env_u32("FM_REPACK_BALLOT", 0);
+        const bool staged = row_fits_smem(m);
         for (fm_group *g : gs) {
             if (g->count_only) {
                 for (size_t k = 0; k < g->off.size();) {  // offsets are sorted: one entry per row word
@@ -1246,14 +1253,50 @@ struct RepackSet {  // device-resident descriptor tables of the groups one launc
                 plane_gs.push_back(g);
                 h.push_back(fm::RepackGroup{g->d_off, g->n, g->wq, g->n_bits, reinterpret_cast<uint32_t *>(g->d_allele),
                                             reinterpret_cast<uint32_t *>(g->d_called),
-                                            std::max<size_t>(m->V, 1) * g->wq * 4, nullptr, nullptr});
+                                            std::max<size_t>(m->V, 1) * g->wq * 4, nullptr, nullptr, nullptr, 0});
+                plan_at.push_back(plan.size() / 8);
+                size_t ne = 0;
+                if (g->n_bits == 1 && staged && !no_plan) {
+                    uint32_t pos = 0;
+                    for (size_t k = 0; k < g->off.size(); ++ne) {  // offsets are sorted: one entry per row word
+                        const uint32_t w = g->off[k] >> 5;
+                        uint32_t mask = 0;
+                        while (k < g->off.size() && (g->off[k] >> 5) == w) mask |= 1u << (g->off[k++] & 31u);
+                        uint32_t mv[5], mm = mask, mk = ~mask << 1;  // Hacker's Delight 7-4: compress move masks
+                        for (int i = 0; i < 5; ++i) {
+                            uint32_t mp = mk ^ (mk << 1);
+                            mp ^= mp << 2;
+                            mp ^= mp << 4;
+                            mp ^= mp << 8;
+                            mp ^= mp << 16;
+                            mv[i] = mp & mm;
+                            mm = (mm ^ mv[i]) | (mv[i] >> (1u << i));
+                            mk &= ~mp;
+                        }
+                        const uint32_t ent[8] = {w, mask, pos, mv[0], mv[1], mv[2], mv[3], mv[4]};
+                        plan.insert(plan.end(), ent, ent + 8);
+                        pos += (uint32_t)__builtin_popcount(mask);
+                    }
+                }
+                plan_len.push_back(ne);
             }
+        }
+        if (!plan.empty()) {
+            d_plan = static_cast<uint4 *>(dev_alloc(plan.size() * 4));
+            CK(cudaMemcpyAsync(d_plan, plan.data(), plan.size() * 4, cudaMemcpyHostToDevice, stream()));
+            for (size_t i = 0; i < h.size(); ++i)
+                if (plan_len[i]) {
+                    h[i].plan = d_plan + 2 * plan_at[i];
+                    h[i].n_ent = (uint32_t)plan_len[i];
+                }
+            need_row_bits = true;
         }
         if (!h.empty()) {
             d_desc = static_cast<fm::RepackGroup *>(dev_alloc(h.size() * sizeof(fm::RepackGroup)));
             CK(cudaMemcpyAsync(d_desc, h.data(), h.size() * sizeof(fm::RepackGroup), cudaMemcpyHostToDevice, stream()));
         }
         const uint32_t ncg = (uint32_t)outs_a.size();
+        if (ncg) need_row_bits = true;
         if (ncg) {
             const size_t ne = ent_word.size();
             std::vector<uint32_t> packed;
@@ -1281,6 +1324,9 @@ struct RepackSet {  // device-resident descriptor tables of the groups one launc
         dev_free(d_desc);
         dev_free(d_ent);
         dev_free(d_outs);
+        dev_free(d_plan);
+        d_plan = nullptr;
+        need_row_bits = false;
         d_desc = nullptr;
         d_ent = nullptr;
         d_outs = nullptr;
@@ -1311,7 +1357,8 @@ static void launch_repack(const RepackSet &set, const uint8_t *data, size_t data
                                                                 per_sm * (uint32_t)sm_count(m->device)));
         fm::fm_k_repack_rows<<<blocks, warps * 32, smem, st>>>(data, data_bytes, missing, m->stride, v_base, word_base,
                                                                v_lo, v_hi, set.d_desc, (uint32_t)set.plane_gs.size(),
-                                                               warp_smem, row_buf, bit_buf, set.ct, m->in_band ? 1u : 0u);
+                                                               warp_smem, row_buf, bit_buf, set.ct, m->in_band ? 1u : 0u,
+                                                               set.need_row_bits ? 1u : 0u);
         CK(cudaGetLastError());
         g_launches++;
         return;
@@ -1423,6 +1470,33 @@ fm_status fm_group_create(fm_matrix *m, const uint64_t *sample_idx, const uint8_
         require_device();
         std::vector<uint32_t> off = membership_offsets(m, sample_idx, side, n);
         *out = make_group(m, std::move(off));
+    });
+}
+
+fm_status fm_groups_create(fm_matrix *m, const uint64_t *sample_idx, const uint8_t *side, const size_t *group_sizes,
+                           size_t n_groups, fm_group **out) {
+    return guarded([&] {
+        if (!out || !m) fail(FM_ERR_INVALID_ARG, "NULL argument");
+        for (size_t g = 0; g < n_groups; ++g) out[g] = nullptr;
+        if (n_groups && !group_sizes) fail(FM_ERR_INVALID_ARG, "group_sizes is NULL");
+        require_device();
+        if (m->streamed)
+            fail(FM_ERR_UNSUPPORTED, "this matrix was ingested in streaming mode: declare groups with fm_ingest_add_group");
+        std::vector<fm_group *> gs;
+        try {
+            size_t at = 0;
+            for (size_t g = 0; g < n_groups; ++g) {
+                const size_t n = group_sizes[g];
+                if (n && (!sample_idx || !side)) fail(FM_ERR_INVALID_ARG, "haplotype arrays are NULL");
+                gs.push_back(alloc_group(m, membership_offsets(m, sample_idx + at, side + at, n)));
+                at += n;
+            }
+            repack_resident(m, gs);  // ONE pass over the u8 rows for all groups
+        } catch (...) {
+            for (fm_group *g : gs) fm_group_release(g);
+            throw;
+        }
+        for (size_t g = 0; g < n_groups; ++g) out[g] = gs[g];
     });
 }
 

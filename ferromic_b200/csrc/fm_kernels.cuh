@@ -111,7 +111,25 @@ struct RepackGroup {
     // count-only groups (the subpopulations of a W&C partition): no bitplanes are kept, the
     // per-site alt / called counts -- all K4 ever reads -- are produced straight from the staged row
     uint32_t *alt_out, *cnt_out;
+    // biallelic plane groups: the group's plane row is a bit COMPRESS of the full-row bit words by the
+    // membership mask (offsets are sorted).  One plan entry (two uint4) per row word the group touches:
+    // {row word, member mask, first output bit, mv0} {mv1, mv2, mv3, mv4} -- mv = the precomputed move masks
+    // of the parallel-suffix compress (Hacker's Delight 7-4), so a lane extracts its word's members in
+    // 5 x 4 logic ops instead of one ballot per 32 haplotypes.
+    const uint4 *plan;
+    uint32_t n_ent;
 };
+
+__device__ __forceinline__ uint32_t fm_compress32(uint32_t x, const uint4 p0, const uint4 p1) {
+    uint32_t t;
+    x &= p0.y;
+    t = x & p0.w; x = (x ^ t) | (t >> 1);
+    t = x & p1.x; x = (x ^ t) | (t >> 2);
+    t = x & p1.y; x = (x ^ t) | (t >> 4);
+    t = x & p1.z; x = (x ^ t) | (t >> 8);
+    t = x & p1.w; x = (x ^ t) | (t >> 16);
+    return x;
+}
 
 // Count-only groups (W&C subpopulations): the row is packed ONCE into full-row allele / called
 // bit words in matrix column order (4 cells per lane and step, no gather); group g then owns a
@@ -131,7 +149,8 @@ __global__ void __launch_bounds__(256)
 fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint64_t *__restrict__ missing,
                  size_t stride, uint32_t v_base, uint64_t word_base, uint32_t v_lo, uint32_t v_hi,
                  const RepackGroup *__restrict__ groups, uint32_t n_groups, uint32_t warp_smem_bytes,
-                 uint32_t row_buf_bytes, uint32_t bit_buf_bytes, CountTable ct, uint32_t in_band) {
+                 uint32_t row_buf_bytes, uint32_t bit_buf_bytes, CountTable ct, uint32_t in_band,
+                 uint32_t need_row_bits) {
     extern __shared__ __align__(16) uint8_t rp_smem[];
     constexpr uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -177,14 +196,52 @@ fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint
         const uint32_t brel = (uint32_t)(bit0 - (w0 << 6));
         const uint32_t *bits32 = reinterpret_cast<const uint32_t *>(bits);
         const uint8_t *rb = rowb + delta;
-        // ---- count-only groups: full-row bit words + masked popcounts
-        if (ct.n_groups) {
-            const uint32_t rw = (uint32_t)((stride + 31) >> 5);
-            uint32_t *arow = reinterpret_cast<uint32_t *>(rowb + row_buf_bytes + bit_buf_bytes);
-            uint32_t *crow = arow + rw + 1;
+        // ---- full-row bit words (allele != 0, called) in matrix column order; count-only groups take
+        //      masked popcounts of them, biallelic plane groups compress them by their membership masks
+        const uint32_t rw = (uint32_t)((stride + 31) >> 5);
+        uint32_t *arow = reinterpret_cast<uint32_t *>(rowb + row_buf_bytes + bit_buf_bytes);
+        uint32_t *crow = arow + rw + 1;
+        uint32_t *outb = crow + rw + 1;  // 2 x out_cap words: one group's plane rows while they are assembled
+        const uint32_t out_cap = (uint32_t)((stride + 127) >> 7) * 4u;
+        if (need_row_bits) {
             const uint32_t *row32 = reinterpret_cast<const uint32_t *>(rowb + (delta & ~3u));
             const uint32_t sh8 = (delta & 3u) * 8u;
-            for (uint32_t i = 0; i * 128u < (uint32_t)stride; ++i) {
+            // rows that start on a 16-byte boundary (stride % 16 == 0, e.g. 5008 or 200000 haplotypes): 16 cells per
+            // lane and step (one LDS.128, four nibbles), two lanes per row word; otherwise 4 cells per lane
+            const bool wide = (delta & 15u) == 0u;
+            if (wide) {
+                const uint4 *row128 = reinterpret_cast<const uint4 *>(rowb + delta);
+                const uint32_t nq16 = ((uint32_t)stride + 15u) >> 4;
+                for (uint32_t base = 0; base < nq16; base += 32) {
+                    const uint32_t q = base + lane;
+                    uint4 x = make_uint4(0, 0, 0, 0);
+                    if (q < nq16) {
+                        x = row128[q];
+                        const uint32_t left = (uint32_t)stride - q * 16u;  // cells that exist in this group
+                        if (left < 16u) {
+                            uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                            for (uint32_t k = 0; k < 4; ++k) {
+                                const uint32_t have = left > 4u * k ? min(4u, left - 4u * k) : 0u;
+                                xs[k] = have >= 4u ? xs[k] : (have ? xs[k] & ((1u << (8u * have)) - 1u) : 0u);
+                            }
+                            x = make_uint4(xs[0], xs[1], xs[2], xs[3]);
+                        }
+                    }
+                    auto nib = [](uint32_t w) { return (((__vcmpne4(w, 0u) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu; };
+                    const uint32_t a16 = nib(x.x) | (nib(x.y) << 4) | (nib(x.z) << 8) | (nib(x.w) << 12);
+                    const uint32_t ao = __shfl_xor_sync(FULL, a16, 1);
+                    const uint32_t w = q >> 1;
+                    if (!(lane & 1u) && w < rw) arow[w] = a16 | (ao << 16);
+                    if (in_band) {  // called = cell < 0x80 (a non-negative int8); absent cells read 0 and are masked below
+                        auto cnib = [](uint32_t w) { return (((~w >> 7) & 0x01010101u) * 0x01020408u >> 24) & 0xFu; };
+                        const uint32_t c16 = cnib(x.x) | (cnib(x.y) << 4) | (cnib(x.z) << 8) | (cnib(x.w) << 12);
+                        const uint32_t co = __shfl_xor_sync(FULL, c16, 1);
+                        if (!(lane & 1u) && w < rw) crow[w] = c16 | (co << 16);
+                    }
+                }
+            }
+            for (uint32_t i = 0; !wide && i * 128u < (uint32_t)stride; ++i) {
                 const uint32_t col = (i * 32u + lane) * 4u;  // first of this lane's 4 columns
                 uint32_t x = 0;
                 if (col < (uint32_t)stride) {
@@ -214,7 +271,7 @@ fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint
                 for (uint32_t w = lane; w < rw; w += 32)
                     crow[w] = missing ? ~__funnelshift_r(bits32[w + qb], bits32[w + qb + 1], sb) : FULL;
             __syncwarp();
-            for (uint32_t g = lane; g < ct.n_groups; g += 32) {
+            for (uint32_t g = lane; g < ct.n_groups; g += 32) {  // count-only groups
                 uint32_t a = 0, c = 0;
                 const uint32_t e1 = __ldg(ct.ent_start + g + 1);
                 for (uint32_t e = __ldg(ct.ent_start + g); e < e1; ++e) {
@@ -231,6 +288,41 @@ fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint
         for (uint32_t gi = 0; gi < n_groups; ++gi) {
             const RepackGroup G = groups[gi];
             const uint32_t words = G.wq * 4;
+            if (G.n_bits == 1 && G.plan) {
+                uint32_t *oa = outb, *oc = outb + out_cap;
+                for (uint32_t i = lane; i < words; i += 32) {
+                    oa[i] = 0;
+                    oc[i] = 0;
+                }
+                __syncwarp();
+                for (uint32_t e = lane; e < G.n_ent; e += 32) {
+                    const uint4 p0 = __ldg(G.plan + 2 * e), p1 = __ldg(G.plan + 2 * e + 1);
+                    const uint32_t cw = crow[p0.x];
+                    const uint32_t xa = fm_compress32(arow[p0.x] & cw, p0, p1);
+                    const uint32_t sh = p0.z & 31u, wi = p0.z >> 5;
+                    if (xa) {
+                        atomicOr(oa + wi, xa << sh);
+                        const uint32_t hi = sh ? xa >> (32u - sh) : 0u;
+                        if (hi) atomicOr(oa + wi + 1, hi);
+                    }
+                    if (G.called) {
+                        const uint32_t xc = fm_compress32(cw, p0, p1);
+                        if (xc) {
+                            atomicOr(oc + wi, xc << sh);
+                            const uint32_t hi = sh ? xc >> (32u - sh) : 0u;
+                            if (hi) atomicOr(oc + wi + 1, hi);
+                        }
+                    }
+                }
+                __syncwarp();
+                for (uint32_t i = lane; i < words; i += 32) {
+                    const size_t o = (size_t)v * words + i;
+                    G.allele[o] = oa[i];
+                    if (G.called) G.called[o] = oc[i];
+                }
+                __syncwarp();
+                continue;
+            }
             if (G.n_bits == 1) {
                 // biallelic fast path: words whose 32 haplotypes all exist run a branch-free loop
                 // (one offset load, one bit test, one byte test, two ballots per word)

@@ -115,6 +115,11 @@ fm_status fm_ingest_abort(fm_ingest *h);
  * missing bitmap) a called bitplane. */
 fm_status fm_group_create(fm_matrix *m, const uint64_t *sample_idx, const uint8_t *side, size_t n,
                           fm_group **out);
+/* Several groups of one matrix at once (e.g. the two haplotype groups of a config entry,
+ * process.rs:3191-3208): the haplotype lists are concatenated, group g takes group_sizes[g] of them.
+ * The u8 rows are read ONCE for all groups (fm_group_create reads them once per group). */
+fm_status fm_groups_create(fm_matrix *m, const uint64_t *sample_idx, const uint8_t *side,
+                           const size_t *group_sizes, size_t n_groups, fm_group **out);
 fm_status fm_group_release(fm_group *g);
 fm_status fm_group_capacity(const fm_group *g, size_t *haplotype_capacity);
 
