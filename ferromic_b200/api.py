@@ -762,7 +762,8 @@ def _hudson_member_haps(p: Population):
 
 def _sparse_pair_groups(p1: Population, p2: Population):
     m = p1._shared.sparse_matrix(max(p1._shared.variants.n_samples, len(p1._names), len(p2._names), 1))
-    return m.group(_hudson_member_haps(p1)), m.group(_hudson_member_haps(p2))
+    g1, g2 = m.groups([_hudson_member_haps(p1), _hudson_member_haps(p2)])  # one pass over the u8 rows for both
+    return g1, g2
 
 
 def _hudson_dxy_value(p1: Population, p2: Population):  # calculate_d_xy_hudson (stats.rs:2403-2524)

@@ -274,7 +274,7 @@ class CohortShard:
                             ("n_variants", "seg_sites", "uncallable"))
 
     def hudson_totals(self, haps1, haps2, windows: np.ndarray) -> WindowTotals:
-        g1, g2 = self.matrix.group(haps1), self.matrix.group(haps2)
+        g1, g2 = self.matrix.groups([haps1, haps2])
         w = np.ascontiguousarray(windows, dtype=np.int64).reshape(-1, 2)
         n = len(w)
         f = np.zeros((5, n))

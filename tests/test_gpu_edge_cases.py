@@ -131,3 +131,28 @@ def test_c_abi_argument_errors_do_not_crash():
     mh = C.c_void_p()
     assert L.fm_ingest_finish(ih, C.byref(mh), None, None) == _lib.FM_ERR_INVALID_ARG     # not all rows pushed
     assert L.fm_ingest_abort(ih) == 0
+
+
+@pytest.mark.parametrize("S,missing", [(37, True), (37, False), (64, True), (200, True)])
+def test_groups_created_together_equal_groups_created_alone(S, missing):
+    """fm_groups_create (one pass over the u8 rows, compress plans) against fm_group_create per group and the
+    oracle's counts: row strides that are / are not multiples of 16 (both row-packing paths), overlapping,
+    empty and single-haplotype groups."""
+    from ferromic_b200.api import _Matrix
+    rng = np.random.default_rng(S)
+    V = 300
+    g = rng.binomial(1, rng.beta(0.6, 0.6, size=V)[:, None, None], size=(V, S, 2)).astype(np.uint8)
+    miss = (rng.random(g.shape) < 0.07) if missing else None
+    pos = np.arange(V, dtype=np.int64) * 3
+    lists = [[(s, int(rng.integers(0, 2))) for s in range(S)], both_sides(range(0, S, 3)), [], [(S - 1, 1)],
+             both_sides(range(S // 2, S))]
+    m1 = _Matrix(g, miss, pos, max_allele=1)
+    together = m1.groups(lists)
+    m2 = _Matrix(g, miss, pos, max_allele=1)
+    d = orc.Dense(g.reshape(-1), None if miss is None else orc.pack_missing_bits(miss.reshape(-1)), V, S, 2, 1)
+    for haps, gt in zip(lists, together):
+        a, b = gt.summary(True), m2.group(haps).summary(True)
+        so = orc.build_summary(d, haps)
+        assert np.array_equal(a["alt"], b["alt"]) and np.array_equal(a["called"], b["called"])
+        assert np.array_equal(a["alt"], so.alt) and np.array_equal(a["called"], so.called)
+        assert a["segregating_sites"] == b["segregating_sites"] == so.seg
