@@ -209,7 +209,7 @@ struct BouncePool {
         std::lock_guard<std::mutex> lk(mu);  // one pageable upload at a time per process
         if (!threads) {
             const unsigned hw = std::thread::hardware_concurrency();
-            threads = (int)std::max(1u, std::min(8u, env_u32_early("FM_HOST_THREADS", hw ? hw / 2 : 4)));
+            threads = (int)std::max(1u, std::min(32u, env_u32_early("FM_HOST_THREADS", hw ? std::min(hw / 2, 8u) : 4)));
         }
         const uint8_t *s8 = static_cast<const uint8_t *>(src);
         uint8_t *d8 = static_cast<uint8_t *>(dst);
@@ -3372,6 +3372,10 @@ fm_status fm_vcf_parse(const char *text, size_t n_bytes, const char *chr, const 
                 } catch (const FmError &e) {
                     copy_msg = e.msg;
                     copy_err.store(e.code ? e.code : FM_ERR_CUDA);
+                    recorded.store(nc, std::memory_order_release);
+                } catch (...) {  // nothing may escape a std::thread
+                    copy_msg = "upload thread failed";
+                    copy_err.store(FM_ERR_CUDA);
                     recorded.store(nc, std::memory_order_release);
                 }
             });

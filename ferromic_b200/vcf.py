@@ -190,3 +190,64 @@ def process_vcf_text(text: bytes, chr_: str, regions, min_gq: int, allow_regions
     if not names:
         raise VcfParseError("No samples remain after applying exclusions")
     return process_lines(text[off:], chr_, regions, kept, min_gq, allow_regions, mask_regions, max_ploidy), names
+
+
+# ------------------------------------------------------------------------------- multi-GPU
+# The stage shards by LINE range: every line is independent, FilteringStats / MissingDataInfo counters add,
+# the two position sets union, and the sorted variant lists of consecutive ranks concatenate (a position-sorted
+# VCF gives every rank a contiguous site range, which is exactly how the estimator path shards).  Each rank
+# uploads its own byte range over its own PCIe link; only the few counters travel.
+STAT_KEYS = ("total_variants", "filtered_variants", "filtered_due_to_mask", "filtered_due_to_allow",
+             "missing_data_variants", "low_gq_variants", "mnp_variants", "total_data_points", "missing_data_points")
+
+
+def text_shard_bounds(text: bytes, world: int) -> List[int]:
+    """Cut points of `world` contiguous byte ranges of data-line text, each ending on a line end."""
+    n = len(text)
+    cuts = [0]
+    for r in range(1, world):
+        c = max(n * r // world, cuts[-1])
+        nl = text.find(b"\n", c - 1) if c > 0 else -1  # a cut right after a '\n' stays where it is
+        c = n if nl < 0 else nl + 1
+        cuts.append(min(max(c, cuts[-1]), n))
+    cuts.append(n)
+    return cuts
+
+
+def merge_shard_stats(per_rank_counters: Sequence[Sequence[int]], per_rank_missing: Sequence[np.ndarray],
+                      per_rank_filtered: Sequence[np.ndarray]) -> Tuple[Dict[str, int], np.ndarray, np.ndarray]:
+    """Totals of a sharded parse: counters add in rank order, position sets union (sorted)."""
+    tot = np.zeros(len(STAT_KEYS), dtype=np.int64)
+    for c in per_rank_counters:
+        tot += np.asarray(c, dtype=np.int64)
+    pm = np.unique(np.concatenate([np.asarray(x, dtype=np.int64) for x in per_rank_missing] or [np.zeros(0, np.int64)]))
+    pf = np.unique(np.concatenate([np.asarray(x, dtype=np.int64) for x in per_rank_filtered] or [np.zeros(0, np.int64)]))
+    return {k: int(v) for k, v in zip(STAT_KEYS, tot)}, pm, pf
+
+
+def gather_shard_stats(counters: Sequence[int], n_lines: int, pos_missing, pos_filtered, group=None):
+    """The exchange step of a line-sharded parse under torch.distributed: ONE all_gather of each rank's nine counters,
+    its line count and its two (small) position lists; merged in rank order on every rank.  Returns (global stats,
+    positions_with_missing, filtered_positions, first global line index of this rank)."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    payload = (list(map(int, counters)) + [int(n_lines)], np.asarray(pos_missing), np.asarray(pos_filtered))
+    gathered: List = [None] * world
+    dist.all_gather_object(gathered, payload, group=group)
+    stats, pm, pf = merge_shard_stats([g[0][:-1] for g in gathered], [g[1] for g in gathered], [g[2] for g in gathered])
+    return stats, pm, pf, sum(g[0][-1] for g in gathered[:rank])
+
+
+def process_lines_sharded(text: bytes, chr_: str, regions, kept_col_indices, min_gq, allow_regions=None,
+                          mask_regions=None, max_ploidy: int = 2, group=None):
+    """One rank of a line-sharded parse (one process per GPU).  Returns (this rank's VcfBatch, global stats dict,
+    global positions_with_missing, global filtered_positions, first global line index of this rank)."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    cuts = text_shard_bounds(text, world)
+    batch = process_lines(text[cuts[rank]:cuts[rank + 1]], chr_, regions, kept_col_indices, min_gq, allow_regions,
+                          mask_regions, max_ploidy)
+    s = batch.stats()
+    stats, pm, pf, line0 = gather_shard_stats([s[k] for k in STAT_KEYS], int(batch.info.n_lines),
+                                              batch.positions_with_missing(), batch.filtered_positions(), group)
+    return batch, stats, pm, pf, line0

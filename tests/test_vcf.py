@@ -293,3 +293,118 @@ def test_vcf_text_to_estimators_without_host_round_trip():
             assert s["segregating_sites"] == so.seg
             got, ref = g.pi(L, _lib.FM_PI_SPARSE), orc.pi_sparse(vs, haps, L)
             assert (np.isnan(got) and np.isnan(ref)) or abs(got - ref) <= 1e-9 * abs(ref)  # FP64: 1e-9 relative
+
+
+# ----------------------------------------------------------------------------- line-sharded parse (multi-GPU)
+def test_text_shard_bounds_cut_on_line_ends():
+    from ferromic_b200 import vcf
+    rng = np.random.default_rng(5)
+    text = make_vcf(rng, 200, 6, odd=0.05).encode()
+    if not text.endswith(b"\n"):
+        text += b"\n"
+    for world in (1, 2, 3, 8, 64, 500):
+        cuts = vcf.text_shard_bounds(text, world)
+        assert cuts[0] == 0 and cuts[-1] == len(text) and len(cuts) == world + 1
+        assert all(a <= b for a, b in zip(cuts, cuts[1:]))
+        assert all(c == 0 or c == len(text) or text[c - 1:c] == b"\n" for c in cuts)
+        assert b"".join(text[a:b] for a, b in zip(cuts, cuts[1:])) == text
+    assert vcf.text_shard_bounds(b"", 4) == [0, 0, 0, 0, 0]
+
+
+def test_sharded_statistics_merge_like_the_whole():
+    """Host logic of the line-sharded parse with the oracle as the per-shard parser: counters add, position sets
+    union, per-shard variant lists concatenate to the whole (position-sorted text)."""
+    from ferromic_b200 import vcf
+    rng = np.random.default_rng(6)
+    text = make_vcf(rng, 300, 5, odd=0.04, sort=True)
+    kept, regions = [9, 10, 12, 13], [(950, 2100)]
+    whole, wm, ws, _ = ov.process_lines(ov.split_lines(text), "1", regions, kept, 30)
+    for world in (2, 5):
+        cuts = vcf.text_shard_bounds(text.encode(), world)
+        cnt, pms, pfs, outs = [], [], [], []
+        for a, b in zip(cuts, cuts[1:]):
+            o, m, s, _ = ov.process_lines(ov.split_lines(text.encode()[a:b].decode()), "1", regions, kept, 30)
+            cnt.append([s.total_variants, s.filtered_variants, s.filtered_due_to_mask, s.filtered_due_to_allow,
+                        s.missing_data_variants, s.low_gq_variants, s.mnp_variants, m.total_data_points,
+                        m.missing_data_points])
+            pms.append(np.array(sorted(m.positions_with_missing), dtype=np.int64))
+            pfs.append(np.array(sorted(s.filtered_positions), dtype=np.int64))
+            outs += o
+        stats, pm, pf = vcf.merge_shard_stats(cnt, pms, pfs)
+        assert stats["total_variants"] == ws.total_variants and stats["low_gq_variants"] == ws.low_gq_variants
+        assert stats["missing_data_points"] == wm.missing_data_points and stats["mnp_variants"] == ws.mnp_variants
+        assert set(pm.tolist()) == wm.positions_with_missing and set(pf.tolist()) == ws.filtered_positions
+        assert [v[0] for v in outs] == [v[0] for v in whole]
+
+
+@pytest.mark.gpu
+def test_device_parser_shards_equal_the_whole():
+    from ferromic_b200 import vcf
+    rng = np.random.default_rng(8)
+    # positions spread out: a tie of equal positions straddling a cut would be ordered by genotype bytes in the
+    # whole parse but not across shards (the merge of two ranks then needs that one comparison)
+    text = make_vcf(rng, 500, 30, odd=0.02, sort=True, pos_lo=1000, pos_hi=900000).encode()
+    kept, regions = list(range(9, 39)), [(950, 1000000)]
+    whole = vcf.process_lines(text, "1", regions, kept, 30, max_ploidy=3)
+    cuts = vcf.text_shard_bounds(text, 3)
+    parts = [vcf.process_lines(text[a:b], "1", regions, kept, 30, max_ploidy=3) for a, b in zip(cuts, cuts[1:])]
+    stats, pm, pf = vcf.merge_shard_stats([[p.stats()[k] for k in vcf.STAT_KEYS] for p in parts],
+                                          [p.positions_with_missing() for p in parts],
+                                          [p.filtered_positions() for p in parts])
+    assert stats == whole.stats()
+    assert np.array_equal(pm, whole.positions_with_missing()) and np.array_equal(pf, whole.filtered_positions())
+    assert np.array_equal(np.concatenate([p.positions for p in parts]), whole.positions)
+    assert np.array_equal(np.concatenate([p.flags for p in parts]), whole.flags)
+    assert np.array_equal(np.concatenate([p.genotypes() for p in parts]), whole.genotypes())
+    line0 = np.cumsum([0] + [int(p.info.n_lines) for p in parts])
+    assert [(l + int(line0[i]), m) for i, p in enumerate(parts) for l, m in p.errors] == whole.errors
+
+
+def _gloo_worker(rank, port, q):
+    import os
+    import torch.distributed as dist
+    from ferromic_b200 import vcf
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=2)
+    try:
+        rng = np.random.default_rng(6)
+        text = make_vcf(rng, 300, 5, odd=0.04, sort=True).encode()
+        cuts = vcf.text_shard_bounds(text, 2)
+        mine = text[cuts[rank]:cuts[rank + 1]].decode()
+        # no device in this container: the oracle parses the local shard, the exchange is the product's
+        o, m, s, errs = ov.process_lines(ov.split_lines(mine), "1", [(950, 2100)], [9, 10, 12, 13], 30)
+        cnt = [s.total_variants, s.filtered_variants, s.filtered_due_to_mask, s.filtered_due_to_allow,
+               s.missing_data_variants, s.low_gq_variants, s.mnp_variants, m.total_data_points, m.missing_data_points]
+        stats, pm, pf, line0 = vcf.gather_shard_stats(cnt, len(ov.split_lines(mine)), sorted(m.positions_with_missing),
+                                                      sorted(s.filtered_positions))
+        q.put((rank, (stats, pm.tolist(), pf.tolist(), line0, [(l + line0, msg) for l, msg in errs])))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_exchange_of_shard_statistics():
+    import socket
+    import torch.multiprocessing as mp
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0][:3] == got[1][:3]  # every rank ends with the same totals
+    rng = np.random.default_rng(6)
+    text = make_vcf(rng, 300, 5, odd=0.04, sort=True)
+    whole, wm, ws, werr = ov.process_lines(ov.split_lines(text), "1", [(950, 2100)], [9, 10, 12, 13], 30)
+    stats, pm, pf = got[0][:3]
+    assert stats["total_variants"] == ws.total_variants and stats["filtered_variants"] == ws.filtered_variants
+    assert stats["total_data_points"] == wm.total_data_points and stats["missing_data_points"] == wm.missing_data_points
+    assert set(pm) == wm.positions_with_missing and set(pf) == ws.filtered_positions
+    assert got[0][3] == 0 and got[0][4] + got[1][4] == werr  # global line numbering of the error lines
