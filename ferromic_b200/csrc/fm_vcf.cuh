@@ -5,8 +5,9 @@
 //   fm_k_vcf_index   line starts + tabs-before-line from the scanned tile counts (text read #2, L2)
 //   fm_k_vcf_fixed   one warp per line: the nine fixed fields -> chr / POS / region / allow / mask /
 //                    REF-ALT length guard / allele info / GQ index in FORMAT   (first ~100 B of a line)
-//   fm_k_vcf_samples one CTA per candidate line: tab ranks by block scan, every kept sample field
-//                    parsed by the thread that owns its leading tab -> u8 genotype row, GQ / missing flags
+//   fm_k_vcf_samples one CTA per candidate line: the sample region is cut into 256 contiguous spans, one block scan
+//                    per line gives every span its first column index, each thread parses its span's kept
+//                    fields in order -> u8 genotype row, GQ / missing flags
 //   fm_k_vcf_to_matrix  DenseGenotypeMatrix::from_variants (stats.rs:339-500) on the device, in output order
 //
 // A line is what BufRead::read_line yields: it INCLUDES its terminating '\n' (the last field carries it,
@@ -434,16 +435,28 @@ __device__ __forceinline__ bool vcf_fast_sample(uint32_t w0, uint32_t w1, uint32
     return true;
 }
 
-__global__ void __launch_bounds__(256)
+// Unaligned 8-byte window at byte p of the text (two words), from three aligned 32-bit loads (L1 hits: the
+// owning thread has just scanned these bytes).
+__device__ __forceinline__ void vcf_load8(const uint8_t *__restrict__ tx, uint32_t p, uint32_t &w0, uint32_t &w1) {
+    const uint32_t *a = reinterpret_cast<const uint32_t *>(tx + (p & ~3u));
+    const uint32_t x0 = __ldg(a), x1 = __ldg(a + 1), x2 = __ldg(a + 2);
+    const uint32_t sh = (p & 3u) * 8u;
+    w0 = __funnelshift_r(x0, x1, sh);
+    w1 = __funnelshift_r(x1, x2, sh);
+}
+
+// One CTA per candidate line.  The sample region [9th tab, line end) is cut into 256 contiguous spans of whole
+// 16-byte words, one per thread: pass 1 counts the span's tabs, ONE block scan per line turns the counts into
+// the column index of every span's first field, pass 2 walks the span's tabs in order and parses the kept
+// fields (fast path for a|b:QQ, general parser otherwise).  Two barriers per line, no shared-memory staging.
+__global__ void __launch_bounds__(256, 4)
 fm_k_vcf_samples(VcfParams P, VcfLine *recs, const uint32_t *__restrict__ row_of_line, uint8_t *__restrict__ gt,
                  uint32_t text_cap) {
     __shared__ uint32_t s_scan[9];
     __shared__ uint32_t s_missing, s_low, s_stride, s_err;
-    // the tile + 16 bytes of look-ahead, double-buffered: a thread that is done with tile i writes tile i+1 into
-    // the other buffer and then waits in the scan's barrier, so no reader of tile i is ever overtaken
-    __shared__ uint4 s_tile2[2][VCF_TILE / 16 + 1];
     const uint8_t *__restrict__ tx = P.text;
     const uint32_t mp = P.max_ploidy;
+    (void)text_cap;
     for (uint32_t line = blockIdx.x; line < P.n_lines; line += gridDim.x) {
         const VcfLine r = recs[line];
         if (r.status != VCF_CAND) continue;  // uniform across the CTA
@@ -453,87 +466,80 @@ fm_k_vcf_samples(VcfParams P, VcfLine *recs, const uint32_t *__restrict__ row_of
             s_stride = 0;
             s_err = 0;
         }
-        __syncthreads();
         const uint32_t e = P.line_start[line + 1];
         const bool write = !(r.indel & 1);
         const bool fast_ok = r.gq_index == 1 && mp >= 2;
         uint8_t *__restrict__ row = write ? gt + (size_t)row_of_line[line] * P.n_samples * mp : nullptr;
+        uint32_t miss = 0, stride = 0, err = 0;
+        bool low = false;
         if (P.max_idx >= 9) {
             // the 9th tab (at sample_off - 1) opens field 9
             const uint32_t first = r.sample_off - 1;
-            uint32_t carry = 8;  // tabs of this line before `first`
-            uint32_t buf = 0;
-            for (uint32_t t0 = first & ~15u; t0 < e; t0 += VCF_TILE, buf ^= 1u) {
-                uint4 *s_tile = s_tile2[buf];
-                const uint32_t *s_w = reinterpret_cast<const uint32_t *>(s_tile);
-                const uint32_t my = t0 + threadIdx.x * 16;
-                uint32_t tbm = 0;
-                uint4 v = make_uint4(0, 0, 0, 0);
-                if (my < e) {
-                    v = *reinterpret_cast<const uint4 *>(tx + my);
-                    tbm = vcf_eq16(v, VCF_TAB);
-                    if (my < first) tbm &= ~((1u << (first - my)) - 1u);          // bytes before the 9th tab
-                    if (e - my < 16) tbm &= (1u << (e - my)) - 1u;                // bytes of the next line
-                }
-                s_tile[threadIdx.x] = v;
-                if (threadIdx.x == 0) {
-                    const uint32_t la = t0 + VCF_TILE;
-                    s_tile[VCF_TILE / 16] = (la < e && la + 16 <= text_cap) ? *reinterpret_cast<const uint4 *>(tx + la)
-                                                                             : make_uint4(0, 0, 0, 0);
-                }
-                uint32_t total;  // the scan's barriers also publish s_tile
-                uint32_t f = carry + vcf_block_scan(__popc(tbm), s_scan, total) + 1;  // field opened by my first tab
-                carry += total;
-                uint32_t miss = 0, stride = 0, err = 0;
-                bool low = false;
-                while (tbm) {
+            const uint32_t t0 = first & ~15u;
+            const uint32_t n16 = (e - t0 + 15u) >> 4;          // 16-byte words of the sample region
+            const uint32_t per = (n16 + 255u) >> 8;            // words per thread
+            const uint32_t q0 = threadIdx.x * per, q1 = min(n16, q0 + per);
+            // ---- pass 1: tabs in my span
+            uint32_t cnt = 0;
+            for (uint32_t q = q0; q < q1; ++q) {
+                const uint32_t my = t0 + q * 16u;
+                uint32_t tbm = vcf_eq16(*reinterpret_cast<const uint4 *>(tx + my), VCF_TAB);
+                if (my < first) tbm &= ~((1u << (first - my)) - 1u);  // bytes before the 9th tab
+                if (e - my < 16u) tbm &= (1u << (e - my)) - 1u;       // bytes of the next line
+                cnt += __popc(tbm);
+            }
+            uint32_t total;  // the scan's barriers also order the s_* resets above
+            uint32_t f = 8u + vcf_block_scan(cnt, s_scan, total) + 1u;  // field opened by my first tab
+            // ---- pass 2: my fields, in order
+            for (uint32_t q = q0; q < q1 && f <= (uint32_t)P.max_idx; ++q) {
+                const uint32_t my = t0 + q * 16u;
+                uint32_t tbm = vcf_eq16(*reinterpret_cast<const uint4 *>(tx + my), VCF_TAB);
+                if (my < first) tbm &= ~((1u << (first - my)) - 1u);
+                if (e - my < 16u) tbm &= (1u << (e - my)) - 1u;
+                while (tbm && f <= (uint32_t)P.max_idx) {
                     const int bit = __ffs(tbm) - 1;
                     tbm &= tbm - 1;
-                    if (f <= (uint32_t)P.max_idx) {
-                        const int32_t slot = P.col2slot[f];
-                        if (slot >= 0) {
-                            const uint32_t p = my + bit + 1;  // first byte of the field
-                            const uint32_t o = p - t0, sh = (o & 3u) * 8u;
-                            const uint32_t x0 = s_w[o >> 2], x1 = s_w[(o >> 2) + 1], x2 = s_w[(o >> 2) + 2];
-                            uint32_t a0, a1;
-                            if (fast_ok && vcf_fast_sample(__funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh),
-                                                           e - p, P.min_gq, a0, a1, low)) {
-                                stride = stride > 2u ? stride : 2u;
-                                if (write) {
-                                    uint8_t *dst = row + (size_t)slot * mp;
-                                    if (mp == 2) {
-                                        *reinterpret_cast<uint16_t *>(dst) = (uint16_t)(a0 | (a1 << 8));
-                                    } else {
-                                        dst[0] = (uint8_t)a0;
-                                        dst[1] = (uint8_t)a1;
-                                        for (uint32_t k = 2; k < mp; ++k) dst[k] = 0xFF;
-                                    }
-                                }
+                    const int32_t slot = P.col2slot[f];
+                    ++f;
+                    if (slot < 0) continue;
+                    const uint32_t p = my + bit + 1;  // first byte of the field
+                    uint32_t w0, w1, a0, a1;
+                    vcf_load8(tx, p, w0, w1);  // stays inside the padded buffer: p < e <= n_bytes
+                    if (fast_ok && vcf_fast_sample(w0, w1, e - p, P.min_gq, a0, a1, low)) {
+                        stride = stride > 2u ? stride : 2u;
+                        if (write) {
+                            uint8_t *dst = row + (size_t)slot * mp;
+                            if (mp == 2) {
+                                *reinterpret_cast<uint16_t *>(dst) = (uint16_t)(a0 | (a1 << 8));
                             } else {
-                                uint8_t al[VCF_MAX_PLOIDY];
-                                bool gq_missing = false, too_long = false;
-                                const uint32_t n = vcf_parse_sample(tx, p, e, r.gq_index, P.min_gq, mp, al, low,
-                                                                    gq_missing, too_long);
-                                if (too_long) err = VCF_E_PLOIDY > err ? VCF_E_PLOIDY : err;
-                                else if (gq_missing) err = err ? err : VCF_E_GQ_MISSING;
-                                if (n == 0) ++miss;
-                                stride = n > stride ? n : stride;
-                                if (write) {
-                                    uint8_t *dst = row + (size_t)slot * mp;
-                                    for (uint32_t k = 0; k < mp; ++k) dst[k] = k < n ? al[k] : (uint8_t)0xFF;
-                                }
+                                dst[0] = (uint8_t)a0;
+                                dst[1] = (uint8_t)a1;
+                                for (uint32_t k = 2; k < mp; ++k) dst[k] = 0xFF;
                             }
                         }
+                    } else {
+                        uint8_t al[VCF_MAX_PLOIDY];
+                        bool gq_missing = false, too_long = false;
+                        const uint32_t n = vcf_parse_sample(tx, p, e, r.gq_index, P.min_gq, mp, al, low, gq_missing,
+                                                            too_long);
+                        if (too_long) err = VCF_E_PLOIDY > err ? VCF_E_PLOIDY : err;
+                        else if (gq_missing) err = err ? err : VCF_E_GQ_MISSING;
+                        if (n == 0) ++miss;
+                        stride = n > stride ? n : stride;
+                        if (write) {
+                            uint8_t *dst = row + (size_t)slot * mp;
+                            for (uint32_t k = 0; k < mp; ++k) dst[k] = k < n ? al[k] : (uint8_t)0xFF;
+                        }
                     }
-                    ++f;
                 }
-                if (miss) atomicAdd(&s_missing, miss);
-                if (low) atomicOr(&s_low, 1u);
-                if (stride) atomicMax(&s_stride, stride);
-                if (err) atomicMax(&s_err, err);
-                if (carry > (uint32_t)P.max_idx) break;  // every kept column has been seen (uniform)
             }
+        } else {
+            __syncthreads();  // orders the s_* resets like the scan does
         }
+        if (miss) atomicAdd(&s_missing, miss);
+        if (low) atomicOr(&s_low, 1u);
+        if (stride) atomicMax(&s_stride, stride);
+        if (err) atomicMax(&s_err, err);
         __syncthreads();
         if (threadIdx.x == 0) {
             VcfLine o = r;
