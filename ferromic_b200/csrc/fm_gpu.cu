@@ -2537,7 +2537,6 @@ fm_status fm_group_window_sums(fm_group *g, const int64_t *windows, size_t n_win
         if (!g || (n_windows && !windows)) fail(FM_ERR_INVALID_ARG, "NULL argument");
         require_device();
         if (!n_windows) return;
-        if (g->n_bits > 1) fail(FM_ERR_UNSUPPORTED, "window sums are biallelic-only on the GPU path");
         ensure_counts(g);
         set_dev(g->m);
         std::vector<uint32_t> lo, hi;
@@ -2548,8 +2547,13 @@ fm_status fm_group_window_sums(fm_group *g, const int64_t *windows, size_t n_win
         DevBuf<uint64_t> dseg(n_windows), dunc(n_windows);
         DevBuf<double> dpi(n_windows);
         const uint32_t blocks = (uint32_t)std::min<size_t>((n_windows + 7) / 8, 8u * sm_count(g->m->device));
-        fm::fm_k_window_div<<<blocks, 256, 0, stream()>>>(g->d_alt, g->d_cnt, dlo.p, dhi.p, (uint32_t)n_windows,
-                                                           FM_PIFORM_COUNTS, dseg.p, dpi.p, dunc.p);
+        if (g->n_bits > 1)  // multi-allelic: general dense forms over the cached per-allele counts
+            fm::fm_k_window_div_multi<<<blocks, 256, 0, stream()>>>(g->d_acount, g->d_cnt, 1u << g->n_bits, FM_MULTI_DENSE,
+                                                                     dlo.p, dhi.p, (uint32_t)n_windows, dseg.p, dpi.p,
+                                                                     dunc.p);
+        else
+            fm::fm_k_window_div<<<blocks, 256, 0, stream()>>>(g->d_alt, g->d_cnt, dlo.p, dhi.p, (uint32_t)n_windows,
+                                                               FM_PIFORM_COUNTS, dseg.p, dpi.p, dunc.p);
         CK(cudaGetLastError());
         g_launches++;
         if (seg) dseg.download(seg, n_windows);
@@ -2569,7 +2573,6 @@ fm_status fm_hudson_window_sums(fm_group *g1, fm_group *g2, const int64_t *windo
         if (n_windows && !windows) fail(FM_ERR_INVALID_ARG, "NULL argument");
         require_device();
         if (!n_windows) return;
-        if (g1->n_bits > 1) fail(FM_ERR_UNSUPPORTED, "window sums are biallelic-only on the GPU path");
         ensure_counts(g1);
         ensure_counts(g2);
         set_dev(g1->m);
@@ -2581,8 +2584,13 @@ fm_status fm_hudson_window_sums(fm_group *g1, fm_group *g2, const int64_t *windo
         DevBuf<double> dd(n_windows * 5);
         DevBuf<uint64_t> ds(n_windows);
         const uint32_t blocks = (uint32_t)std::min<size_t>((n_windows + 7) / 8, 8u * sm_count(g1->m->device));
-        fm::fm_k_window_hudson<<<blocks, 256, 0, stream()>>>(g1->d_alt, g1->d_cnt, g2->d_alt, g2->d_cnt, dlo.p,
-                                                              dhi.p, (uint32_t)n_windows, dd.p, ds.p);
+        if (g1->n_bits > 1)
+            fm::fm_k_window_hudson_multi<<<blocks, 256, 0, stream()>>>(g1->d_acount, g1->d_cnt, g2->d_acount, g2->d_cnt,
+                                                                        1u << g1->n_bits, FM_MULTI_DENSE, dlo.p, dhi.p,
+                                                                        (uint32_t)n_windows, dd.p, ds.p);
+        else
+            fm::fm_k_window_hudson<<<blocks, 256, 0, stream()>>>(g1->d_alt, g1->d_cnt, g2->d_alt, g2->d_cnt, dlo.p,
+                                                                  dhi.p, (uint32_t)n_windows, dd.p, ds.p);
         CK(cudaGetLastError());
         g_launches++;
         std::vector<double> h(n_windows * 5);

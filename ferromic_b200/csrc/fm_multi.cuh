@@ -171,6 +171,42 @@ fm_k_multi_div_from_counts(const uint32_t *__restrict__ acount, const uint32_t *
     }
 }
 
+// One site of the general (multi-allelic) Hudson estimator from two groups' per-allele counts
+// (stats.rs:2557-2591 / 3106-3140 / 2907-2935): accumulator contributions + the per-site values.
+__device__ __forceinline__ void fm_multi_hudson_site(const uint32_t *__restrict__ c1, uint32_t n1,
+                                                     const uint32_t *__restrict__ c2, uint32_t n2, uint32_t A,
+                                                     int form, HudsonAcc &acc, fm_hudson_vals &o, MultiSite &s1,
+                                                     MultiSite &s2) {
+    s1 = fm_multi_site(c1, A, n1);
+    s2 = fm_multi_site(c2, A, n2);
+    double p1 = 0.0, p2 = 0.0, d = 0.0;
+    const bool has1 = form == FM_MULTI_DENSE ? fm_pi_general_dense(s1, p1) : fm_pi_general_components(s1, p1);
+    const bool has2 = form == FM_MULTI_DENSE ? fm_pi_general_dense(s2, p2) : fm_pi_general_components(s2, p2);
+    const bool has_d = s1.n != 0 && s2.n != 0;
+    if (has_d) {
+        const double inv1 = 1.0 / (double)s1.n, inv2 = 1.0 / (double)s2.n;
+        double dot = 0.0;
+        for (uint32_t a = 0; a < A; ++a)
+            if (c1[a] && c2[a]) dot += ((double)c1[a] * inv1) * ((double)c2[a] * inv2);
+        d = 1.0 - dot;
+        d = d > 0.0 ? d : 0.0;
+        d = d < 1.0 ? d : 1.0;
+    }
+    fm_hudson_components(has_d, d, has1, p1, has2, p2, o);
+    acc.unc1 = s1.n < 2;
+    acc.unc2 = s2.n < 2;
+    if (o.num == o.num && o.den == o.den) {
+        acc.num = o.num;
+        acc.den = o.den;
+    }
+    if (has_d)
+        acc.dxy = d;
+    else
+        acc.skipped = 1;
+    if (has1) acc.pi1 = p1;
+    if (has2) acc.pi2 = p2;
+}
+
 // Hudson per-site values and regional partials from two groups' cached per-allele counts.
 __global__ void __launch_bounds__(256)
 fm_k_multi_hudson_from_counts(const uint32_t *__restrict__ ac1, const uint32_t *__restrict__ n1v,
@@ -185,35 +221,9 @@ fm_k_multi_hudson_from_counts(const uint32_t *__restrict__ ac1, const uint32_t *
         const bool valid = v >= v_lo && v < v_hi;
         HudsonAcc acc{0.0, 0.0, 0.0, 0.0, 0.0, 0u, 0u, 0u};
         if (valid) {
-            const uint32_t *c1 = ac1 + (size_t)v * A, *c2 = ac2 + (size_t)v * A;
-            const MultiSite s1 = fm_multi_site(c1, A, n1v[v]), s2 = fm_multi_site(c2, A, n2v[v]);
-            double p1 = 0.0, p2 = 0.0, d = 0.0;
-            const bool has1 = form == FM_MULTI_DENSE ? fm_pi_general_dense(s1, p1) : fm_pi_general_components(s1, p1);
-            const bool has2 = form == FM_MULTI_DENSE ? fm_pi_general_dense(s2, p2) : fm_pi_general_components(s2, p2);
-            const bool has_d = s1.n != 0 && s2.n != 0;
-            if (has_d) {  // stats.rs:2557-2591 / 3106-3140 / 2907-2935
-                const double inv1 = 1.0 / (double)s1.n, inv2 = 1.0 / (double)s2.n;
-                double dot = 0.0;
-                for (uint32_t a = 0; a < A; ++a)
-                    if (c1[a] && c2[a]) dot += ((double)c1[a] * inv1) * ((double)c2[a] * inv2);
-                d = 1.0 - dot;
-                d = d > 0.0 ? d : 0.0;
-                d = d < 1.0 ? d : 1.0;
-            }
+            MultiSite s1, s2;
             fm_hudson_vals o;
-            fm_hudson_components(has_d, d, has1, p1, has2, p2, o);
-            acc.unc1 = s1.n < 2;
-            acc.unc2 = s2.n < 2;
-            if (o.num == o.num && o.den == o.den) {
-                acc.num = o.num;
-                acc.den = o.den;
-            }
-            if (has_d)
-                acc.dxy = d;
-            else
-                acc.skipped = 1;
-            if (has1) acc.pi1 = p1;
-            if (has2) acc.pi2 = p2;
+            fm_multi_hudson_site(ac1 + (size_t)v * A, n1v[v], ac2 + (size_t)v * A, n2v[v], A, form, acc, o, s1, s2);
             if (e.fst) {
                 const uint32_t i = v - v_lo;
                 e.fst[i] = o.fst;
@@ -234,6 +244,65 @@ fm_k_multi_hudson_from_counts(const uint32_t *__restrict__ ac1, const uint32_t *
             pd[0] = r0; pd[1] = r1; pd[2] = r2; pd[3] = r3; pd[4] = r4;
             uint32_t *pu = e.part_u + (size_t)bi * 3;
             pu[0] = u0; pu[1] = u1; pu[2] = u2;
+        }
+    }
+}
+
+// Window totals (one warp per window [lo, hi) of site indices) for multi-allelic groups, from the cached
+// per-allele counts: the same per-site forms as the region calls above, fixed-shape butterfly per window.
+__global__ void __launch_bounds__(256)
+fm_k_window_div_multi(const uint32_t *__restrict__ acount, const uint32_t *__restrict__ cnt, uint32_t A, int form,
+                      const uint32_t *__restrict__ win_lo, const uint32_t *__restrict__ win_hi, uint32_t n_windows,
+                      uint64_t *__restrict__ seg_out, double *__restrict__ pi_out, uint64_t *__restrict__ unc_out) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t GW = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t w = gw; w < n_windows; w += GW) {
+        double pi = 0.0;
+        uint32_t seg = 0, unc = 0;
+        for (uint32_t v = win_lo[w] + lane; v < win_hi[w]; v += 32) {
+            const MultiSite s = fm_multi_site(acount + (size_t)v * A, A, cnt[v]);
+            seg += s.distinct > 1;
+            unc += s.n < 2;
+            double val = 0.0;
+            if (form == FM_MULTI_DENSE ? fm_pi_general_dense(s, val) : fm_pi_general_components(s, val)) pi += val;
+        }
+        pi = fm_warp_sum(pi);
+        seg = fm_warp_sum_u(seg);
+        unc = fm_warp_sum_u(unc);
+        if (lane == 0) {
+            seg_out[w] = seg;
+            pi_out[w] = pi;
+            unc_out[w] = unc;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+fm_k_window_hudson_multi(const uint32_t *__restrict__ ac1, const uint32_t *__restrict__ n1v,
+                         const uint32_t *__restrict__ ac2, const uint32_t *__restrict__ n2v, uint32_t A, int form,
+                         const uint32_t *__restrict__ win_lo, const uint32_t *__restrict__ win_hi, uint32_t n_windows,
+                         double *__restrict__ out_d /*[n][5]*/, uint64_t *__restrict__ out_skipped) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t GW = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t w = gw; w < n_windows; w += GW) {
+        double s[5] = {0, 0, 0, 0, 0};
+        uint32_t skipped = 0;
+        for (uint32_t v = win_lo[w] + lane; v < win_hi[w]; v += 32) {
+            HudsonAcc acc{0.0, 0.0, 0.0, 0.0, 0.0, 0u, 0u, 0u};
+            MultiSite s1, s2;
+            fm_hudson_vals o;
+            fm_multi_hudson_site(ac1 + (size_t)v * A, n1v[v], ac2 + (size_t)v * A, n2v[v], A, form, acc, o, s1, s2);
+            s[0] += acc.num; s[1] += acc.den; s[2] += acc.dxy; s[3] += acc.pi1; s[4] += acc.pi2;
+            skipped += acc.skipped;
+        }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) s[i] = fm_warp_sum(s[i]);
+        skipped = fm_warp_sum_u(skipped);
+        if (lane == 0) {
+            for (int i = 0; i < 5; ++i) out_d[(size_t)w * 5 + i] = s[i];
+            out_skipped[w] = skipped;
         }
     }
 }

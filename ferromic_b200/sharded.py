@@ -254,7 +254,9 @@ class CohortShard:
             g = np.asarray(genotypes)
             miss = g < 0 if g.dtype.kind == "i" else None
             alle = np.where(miss, 0, g).astype(np.uint8) if miss is not None else g.astype(np.uint8)
-            self.matrix = _Matrix(alle, miss, np.asarray(positions, dtype=np.int64), max_allele=1)
+            # max_allele > 1: the multi-allelic general forms (per-allele counts) serve the same window totals
+            self.matrix = _Matrix(alle, miss, np.asarray(positions, dtype=np.int64),
+                                  max_allele=int(alle.max()) if alle.size else 0)
         self.positions = np.asarray(positions, dtype=np.int64)
         self._partitions: Dict[int, C.c_void_p] = {}
 

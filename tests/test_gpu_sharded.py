@@ -191,3 +191,48 @@ def test_peer_mailbox_single_rank_and_timeout():
         a.allgather_words(w)
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("max_allele,missing", [(2, 0.0), (5, 0.1)])
+def test_multi_allelic_window_totals_match_region_calls_and_merge(max_allele, missing):
+    """Window totals of a multi-allelic cohort (general dense forms over per-allele counts): every window equals
+    the oracle's dense region calls on that window's sub-cohort (calculate_pi_dense / count_segregating_sites_dense /
+    Hudson from the dense matrix), and two site shards merge to the single-shard totals."""
+    from ferromic_b200 import sharded
+    from tests.test_gpu_parity import make_multi_cohort
+    S = 20
+    g, pos = make_multi_cohort(16384 + 700, S, max_allele, missing, seed=300 + max_allele)
+    h1, h2 = both_sides(range(0, S // 2)), both_sides(range(S // 2, S)) + [(0, 1)]
+    cutsw = [0, 300, 301, 5000, 9000, len(pos) - 1]
+    windows = np.array([(int(pos[a]), int(pos[b]) - (1 if b < len(pos) - 1 else 0)) for a, b in zip(cutsw, cutsw[1:])] +
+                       [(int(pos[-1]) + 5, int(pos[-1]) + 50)], dtype=np.int64)
+    lengths = [int(we - ws + 1) for ws, we in windows]
+    whole = sharded.CohortShard(g, pos)
+    div = whole.diversity_totals(h1, windows)
+    hud = whole.hudson_totals(h1, h2, windows)
+    pi, theta = sharded.finish_diversity(div, lengths, len(h1))
+    hres = sharded.finish_hudson(hud, lengths, len(h1), len(set(h2)))
+    for w, (ws, we) in enumerate(windows):
+        sel = np.nonzero((pos >= ws) & (pos <= we))[0]
+        assert int(div.col("n_variants")[w]) == len(sel)
+        if len(sel) == 0:
+            continue
+        vs, d = orc.from_numpy(g[sel], pos[sel])
+        o1 = orc.Pop(h1, vs, S, lengths[w], dense=d)
+        o2 = orc.Pop(h2, vs, S, lengths[w], dense=d)
+        assert int(div.col("seg_sites")[w]) == orc.count_segregating_sites_for_population(o1)
+        assert _close(float(pi[w]), orc.pi_for_population(o1), 1e-9), w
+        rc, ref, _ = orc.hudson_pair(o1, o2)
+        assert rc == 0
+        for k in ("fst", "d_xy", "pi_pop1", "pi_pop2", "pi_xy_avg"):
+            assert _close(hres[w][k], ref[k], 1e-9), (w, k, hres[w][k], ref[k])
+    cuts = sharded.shard_bounds(len(pos), 2)
+    shards = [sharded.CohortShard(g[a:b], pos[a:b], rank=r, world=2) for r, (a, b) in enumerate(zip(cuts[:-1], cuts[1:]))]
+    # a shard whose rows happen to miss the largest allele still has to use the same number of allele planes
+    for name, fn in (("div", lambda c: c.diversity_totals(h1, windows)), ("hudson", lambda c: c.hudson_totals(h1, h2, windows))):
+        ref = fn(whole)
+        got = sharded.merge_in_rank_order([fn(s) for s in shards])
+        assert np.array_equal(ref.u, got.u), name
+        assert np.allclose(ref.f, got.f, rtol=1e-12, atol=1e-300), name
+    for s in shards + [whole]:
+        s.close()
