@@ -65,9 +65,11 @@ struct VcfParams {
 };
 
 __device__ __forceinline__ uint32_t vcf_eq4(uint32_t w, uint32_t pat) {
-    // bit i = byte i of w equals the pattern byte
-    const uint32_t t = __vcmpeq4(w, pat) & 0x01010101u;
-    return ((t * 0x01020408u) >> 24) & 0xFu;
+    // bit i = byte i of w equals the pattern byte: exact zero-byte test on w ^ pat (no carries cross bytes
+    // because the add only sees 7-bit fields), then the four flag bits are gathered by one multiply
+    const uint32_t t = w ^ pat;
+    const uint32_t z = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u;  // 0x80 in every zero byte
+    return ((z >> 7) * 0x01020408u) >> 24;
 }
 __device__ __forceinline__ uint32_t vcf_eq16(uint4 v, uint32_t pat) {
     return vcf_eq4(v.x, pat) | (vcf_eq4(v.y, pat) << 4) | (vcf_eq4(v.z, pat) << 8) | (vcf_eq4(v.w, pat) << 12);

@@ -408,3 +408,29 @@ def test_two_rank_gloo_exchange_of_shard_statistics():
     assert stats["total_data_points"] == wm.total_data_points and stats["missing_data_points"] == wm.missing_data_points
     assert set(pm) == wm.positions_with_missing and set(pf) == ws.filtered_positions
     assert got[0][3] == 0 and got[0][4] + got[1][4] == werr  # global line numbering of the error lines
+
+
+@pytest.mark.gpu
+def test_device_resident_text_entry_point():
+    """fm_vcf_parse_device: text already in device memory (16-byte aligned, zero padding) gives the same batch."""
+    import ctypes as C
+    import torch
+    from ferromic_b200 import _lib, vcf
+    rng = np.random.default_rng(33)
+    text = make_vcf(rng, 300, 12, odd=0.03).encode()
+    kept = np.arange(9, 21, dtype=np.uint32)
+    reg = np.array([[950, 2100]], dtype=np.int64)
+    host = vcf.process_lines(text, "1", [(950, 2100)], kept.tolist(), 30, max_ploidy=3)
+    n = len(text)
+    buf = torch.zeros(((n + 15) // 16) * 16 + 32, dtype=torch.uint8, device="cuda")
+    buf[:n] = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+    torch.cuda.synchronize()
+    assert buf.data_ptr() % 16 == 0
+    h = C.c_void_p()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    _lib.check(_lib.lib().fm_vcf_parse_device(buf.data_ptr(), n, text[-1:], b"1", p(reg), 1, p(kept), len(kept), 30,
+                                              0, None, 0, 0, None, 0, 3, C.byref(h)))
+    dev = vcf.VcfBatch(h, "1", 20)
+    assert dev.stats() == host.stats() and dev.errors == host.errors
+    assert np.array_equal(dev.positions, host.positions) and np.array_equal(dev.flags, host.flags)
+    assert np.array_equal(dev.genotypes(), host.genotypes())
