@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -3270,6 +3271,17 @@ void vcf_finish(const VcfShared &sh, std::vector<VcfChunkOut> &chunks, float h2d
     *out = b.release();
 }
 
+struct VcfTrace {  // FM_VCF_TRACE=1: wall-clock phases of fm_vcf_parse on stderr
+    bool on = env_u32_early("FM_VCF_TRACE", 0) != 0;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void mark(const char *what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[fm_vcf] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 struct VcfChunkGuard {  // frees chunk buffers on every exit path
     std::vector<VcfChunkOut> v;
     ~VcfChunkGuard() {
@@ -3318,9 +3330,11 @@ fm_status fm_vcf_parse(const char *text, size_t n_bytes, const char *chr, const 
         if (n_bytes >= (1ull << 40)) fail(FM_ERR_UNSUPPORTED, "more than 2^40 bytes per call");
         require_device();
         CK(cudaSetDevice(t_device));
+        VcfTrace tr;
         VcfShared sh;
         vcf_prepare(sh, chr, regions, n_regions, kept_col_indices, n_kept, min_gq, allow_mode, allow, n_allow, mask_mode,
                     mask, n_mask, max_ploidy);
+        tr.mark("prepare");
         // chunk boundaries on line ends
         const size_t target = (size_t)env_u32_early("FM_VCF_CHUNK_MB", 64) << 20;
         std::vector<size_t> cut{0};
@@ -3363,6 +3377,7 @@ fm_status fm_vcf_parse(const char *text, size_t n_bytes, const char *chr, const 
             CK(cudaEventCreate(&e1));
             for (auto &e : ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             CK(cudaStreamSynchronize(stream()));  // d_text may be a recycled block still in use on this stream
+            tr.mark("alloc + streams");
             std::thread uploader([&] {
                 try {
                     CK(cudaSetDevice(dev));
@@ -3398,6 +3413,7 @@ fm_status fm_vcf_parse(const char *text, size_t n_bytes, const char *chr, const 
                 uploader.join();
                 throw;
             }
+            tr.mark("chunks parsed");
             uploader.join();
             if (copy_err.load()) fail(copy_err.load(), copy_msg);
             if (nc) CK(cudaEventElapsedTime(&h2d_ms, e0, e1));
@@ -3406,8 +3422,10 @@ fm_status fm_vcf_parse(const char *text, size_t n_bytes, const char *chr, const 
             throw;
         }
         cleanup();
+        tr.mark("join + cleanup");
         t_tim.h2d_ms += h2d_ms;
         vcf_finish(sh, g.v, h2d_ms, out);
+        tr.mark("finish");
     });
 }
 
@@ -3474,22 +3492,16 @@ fm_status fm_vcf_batch_matrix(const fm_vcf_batch *b, int pass_only, fm_matrix **
         CK(cudaSetDevice(b->device));
         std::vector<uint32_t> order;
         std::vector<int64_t> pos;
-        size_t ploidy = 0;
+        size_t ploidy = 0;  // from_variants: longest genotype over the selected variants (stats.rs:349-359)
         for (size_t i = 0; i < b->var.size(); ++i) {
             if (pass_only && b->var[i].flags != 0) continue;
             order.push_back(b->order[i]);
             pos.push_back(b->var[i].pos0);
-            // from_variants: longest genotype over all variants; a variant without genotypes has length 0
-            // (its recorded stride of 1 is the CompressedGenotypes floor, all cells are the sentinel)
-        }
-        if (order.empty() || b->S == 0) return;  // from_variants: None
-        // max genotype length over the selected rows = max stride of rows that hold a genotype; rows whose
-        // samples are all None report stride 1 by the floor only, so recompute from missing_points
-        for (size_t i = 0, k = 0; i < b->var.size(); ++i) {
-            if (pass_only && b->var[i].flags != 0) continue;
-            ++k;
+            // a variant whose samples are all None has no genotype at all: its recorded stride of 1 is only the
+            // CompressedGenotypes floor and does not count
             if (b->var[i].missing_points < b->S) ploidy = std::max<size_t>(ploidy, b->var[i].stride);
         }
+        if (order.empty() || b->S == 0) return;  // from_variants: None
         if (ploidy == 0) return;  // effectively no data (stats.rs:362-365)
         const size_t V = order.size(), S = b->S;
         DevBuf<uint32_t> d_ord(V), d_max(1);
