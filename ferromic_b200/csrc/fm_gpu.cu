@@ -3336,7 +3336,8 @@ fm_status fm_vcf_parse(const char *text, size_t n_bytes, const char *chr, const 
                     mask, n_mask, max_ploidy);
         tr.mark("prepare");
         // chunk boundaries on line ends
-        const size_t target = (size_t)env_u32_early("FM_VCF_CHUNK_MB", 64) << 20;
+        size_t target = (size_t)env_u32_early("FM_VCF_CHUNK_MB", 64) << 20;
+        if (const uint32_t tb = env_u32_early("FM_VCF_CHUNK_BYTES", 0)) target = tb;  // tests: many tiny chunks
         std::vector<size_t> cut{0};
         while (cut.back() < n_bytes) {
             size_t end = cut.back() + target;
