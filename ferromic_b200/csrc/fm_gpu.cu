@@ -3511,9 +3511,16 @@ fm_status fm_vcf_batch_matrix(const fm_vcf_batch *b, int pass_only, fm_matrix **
         uint8_t *d_data = static_cast<uint8_t *>(dev_alloc(std::max<size_t>(V * S * ploidy, 16)));
         fm_matrix *m = nullptr;
         try {
-            const uint32_t blocks = (uint32_t)std::min<uint64_t>((V * S + 255) / 256, 32ull * sm_count(b->device));
-            fm::fm_k_vcf_to_matrix<<<blocks, 256, 0, stream()>>>(b->d_gt, d_ord.p, V, (uint32_t)S, (uint32_t)b->P,
-                                                                 (uint32_t)ploidy, d_data, d_max.p);
+            if (b->P == 2 && ploidy == 2 && (S * 2) % 16 == 0) {  // whole 16-byte words per row: eight samples per thread
+                const uint32_t row_u4 = (uint32_t)(S * 2 / 16);
+                const uint32_t blocks = (uint32_t)std::min<uint64_t>((V * row_u4 + 255) / 256, 32ull * sm_count(b->device));
+                fm::fm_k_vcf_to_matrix_p2<<<blocks, 256, 0, stream()>>>(reinterpret_cast<const uint4 *>(b->d_gt), d_ord.p, V,
+                                                                        row_u4, reinterpret_cast<uint4 *>(d_data), d_max.p);
+            } else {
+                const uint32_t blocks = (uint32_t)std::min<uint64_t>((V * S + 255) / 256, 32ull * sm_count(b->device));
+                fm::fm_k_vcf_to_matrix<<<blocks, 256, 0, stream()>>>(b->d_gt, d_ord.p, V, (uint32_t)S, (uint32_t)b->P,
+                                                                     (uint32_t)ploidy, d_data, d_max.p);
+            }
             CK(cudaGetLastError());
             g_launches++;
             uint32_t mx = 0;

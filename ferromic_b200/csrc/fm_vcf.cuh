@@ -583,6 +583,35 @@ fm_k_vcf_to_matrix(const uint8_t *__restrict__ gt, const uint32_t *__restrict__ 
     if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_allele, mx);
 }
 
+// Diploid batches (P == ploidy == 2) whose rows are whole 16-byte words: eight samples per thread, byte-parallel
+// within each 32-bit word -- 0xFF bytes (and the second byte of a pair whose first is 0xFF) become 0x80.
+__global__ void __launch_bounds__(256)
+fm_k_vcf_to_matrix_p2(const uint4 *__restrict__ gt, const uint32_t *__restrict__ order, uint64_t n_rows,
+                      uint32_t row_u4, uint4 *__restrict__ data, uint32_t *__restrict__ max_allele) {
+    const uint64_t total = n_rows * row_u4;
+    uint32_t mx = 0;  // per-byte running maximum
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / row_u4;
+        const uint4 x = gt[(size_t)order[r] * row_u4 + (i - r * row_u4)];
+        uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t t = ~w[k];                                                       // zero byte <=> 0xFF cell
+            const uint32_t z = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u;
+            uint32_t m = (z >> 7) * 0xFFu;                                                  // 0xFF in every sentinel byte
+            m |= (m & 0x00FF00FFu) << 8;                                                    // ... and in the byte after a pair's first
+            const uint32_t v = w[k] & ~m;
+            mx = __vmaxu4(mx, v);
+            w[k] = v | (0x80808080u & m);
+        }
+        data[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    mx = max(max(mx & 0xFFu, (mx >> 8) & 0xFFu), max((mx >> 16) & 0xFFu, mx >> 24));
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_allele, mx);
+}
+
 __global__ void __launch_bounds__(256)
 fm_k_vcf_gather_rows(const uint8_t *__restrict__ gt, const uint32_t *__restrict__ order, uint64_t n_rows,
                      uint32_t row_bytes, uint8_t *__restrict__ out) {
