@@ -228,7 +228,10 @@ fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint
                             x = make_uint4(xs[0], xs[1], xs[2], xs[3]);
                         }
                     }
-                    auto nib = [](uint32_t w) { return (((__vcmpne4(w, 0u) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu; };
+                    // bit 7 of every non-zero byte (the add only sees 7-bit fields: no carry crosses bytes), gathered by one multiply
+                    auto nib = [](uint32_t w) {
+                        return (((((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w) >> 7 & 0x01010101u) * 0x01020408u) >> 24;
+                    };
                     const uint32_t a16 = nib(x.x) | (nib(x.y) << 4) | (nib(x.z) << 8) | (nib(x.w) << 12);
                     const uint32_t ao = __shfl_xor_sync(FULL, a16, 1);
                     const uint32_t w = q >> 1;
