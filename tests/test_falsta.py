@@ -177,3 +177,39 @@ def test_device_tracks_from_gpu_estimators():
     rs, re = region[0] + 1, region[1] + 1
     assert falsta.diversity_falsta_text("9", rs, re, recs_gpu).decode() == \
         ofa.diversity_falsta_text("9", rs, re, recs_cpu)
+
+
+def test_format_value_argument_checks():
+    import ctypes as C
+    from ferromic_b200 import _lib
+    L = _lib.lib()
+    buf, n = C.create_string_buffer(64), C.c_size_t()
+    assert L.fm_falsta_format_value(1.5, 7, buf, 64, C.byref(n)) == _lib.FM_ERR_INVALID_ARG  # unknown mode
+    assert L.fm_falsta_format_value(1.5, 1, buf, 8, C.byref(n)) == _lib.FM_ERR_INVALID_ARG   # buffer below 56 bytes
+    assert L.fm_falsta_format_value(1.5, 1, buf, 64, C.byref(n)) == 0 and buf.raw[: n.value] == b"1.500000"
+
+
+@pytest.mark.gpu
+def test_track_capacity_and_argument_errors():
+    import ctypes as C
+    from ferromic_b200 import _lib
+    L = _lib.lib()
+    pos = np.array([2, 4], dtype=np.int64)
+    val = np.array([0.5, np.nan])
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    total = C.c_size_t()
+    out = C.create_string_buffer(64)
+    # length query, then a buffer that is too small: the required length is still reported
+    assert L.fm_falsta_tracks(p(pos), p(val), 2, 1, 1, 5, 1, None, 0, None, C.byref(total)) == 0
+    assert total.value == len("NA,0.500000,NA,NA,NA")
+    assert L.fm_falsta_tracks(p(pos), p(val), 2, 1, 1, 5, 1, out, 5, None, C.byref(total)) == _lib.FM_ERR_INVALID_ARG
+    assert total.value == len("NA,0.500000,NA,NA,NA")
+    assert L.fm_falsta_tracks(p(pos), p(val), 2, 1, 1, 5, 1, out, 64, None, C.byref(total)) == 0
+    assert out.raw[: total.value] == b"NA,0.500000,NA,NA,NA"
+    assert L.fm_falsta_tracks(p(pos), p(val), 2, 1, 1, 5, 9, out, 64, None, C.byref(total)) == _lib.FM_ERR_INVALID_ARG
+    assert L.fm_falsta_tracks(None, None, 2, 1, 1, 5, 1, out, 64, None, C.byref(total)) == _lib.FM_ERR_INVALID_ARG
+    # region clamping (from_1based_inclusive): end < start gives one position; start < 1 starts at 1
+    assert L.fm_falsta_tracks(p(pos), p(val), 2, 1, 4, 2, 0, out, 64, None, C.byref(total)) == 0
+    assert out.raw[: total.value] == b"NA"
+    assert L.fm_falsta_tracks(p(pos), p(val), 2, 1, -3, 3, 0, out, 64, None, C.byref(total)) == 0
+    assert out.raw[: total.value] == b"0,0.500000,0"
