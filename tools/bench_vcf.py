@@ -1,6 +1,8 @@
 """Times the device VCF parse/filter stage (fm_vcf_parse) on 1000-Genomes-shaped text:
 2,504 samples, GT:GQ sample fields, one chromosome.  Prints one JSON line.
-usage: python tools/bench_vcf.py [--lines N] [--samples S] [--reps R]"""
+usage: python tools/bench_vcf.py [--lines N] [--samples S] [--reps R]
+Under torchrun (one process per GPU) every rank parses its own line range of the same text over its own PCIe link
+(vcf.text_shard_bounds), the counters are exchanged once, and rank 0 reports the aggregate."""
 import argparse
 import ctypes as C
 import json
@@ -56,7 +58,16 @@ def main():
     import torch
 
     from ferromic_b200 import _lib, vcf
-    text = synth_text(a.lines, a.samples)
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+        _lib.check(_lib.lib().fm_set_device(int(os.environ.get("LOCAL_RANK", rank))))
+        dist.init_process_group("nccl")
+    whole = synth_text(a.lines * world, a.samples)  # weak scaling: a.lines per GPU
+    cuts = vcf.text_shard_bounds(whole, world)
+    text = whole[cuts[rank]:cuts[rank + 1]]
+    a.lines = text.count(b"\n")
     pinned = torch.empty(len(text), dtype=torch.uint8).pin_memory()
     pinned.numpy()[:] = np.frombuffer(text, dtype=np.uint8)
     kept = np.arange(9, 9 + a.samples, dtype=np.uint32)
@@ -95,6 +106,22 @@ def main():
     best, info = run(a.reps)
     best["index_ms"], best["parse_ms"], best["wall_one_chunk_ms"] = kern["index_ms"], kern["parse_ms"], kern["wall_ms"]
     assert info.n_variants == a.lines and info.n_errors == 0 and info.low_gq_variants == 0  # every GQ is >= 30
+    if world > 1:
+        # one exchange of the counters (the stage's only collective), then max-over-ranks wall time
+        st, pm, pf, line0 = vcf.gather_shard_stats([int(getattr(info, k)) for k in vcf.STAT_KEYS], int(info.n_lines),
+                                                   np.zeros(0, np.int64), np.zeros(0, np.int64))
+        t = torch.tensor([best["wall_ms"]], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tb = torch.tensor([float(len(text))], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tb)
+        if rank == 0:
+            print(json.dumps({"what": "line-sharded fm_vcf_parse, one process per GPU", "n_gpus": world,
+                              "lines_per_gpu": a.lines, "total_text_GB": tb.item() / 1e9, "wall_ms_max_over_ranks": t.item(),
+                              "aggregate_GBps_text": tb.item() / 1e9 / (t.item() / 1e3),
+                              "aggregate_sample_genotypes_per_s": st["total_data_points"] / (t.item() / 1e3),
+                              "total_variants": st["total_variants"]}))
+        dist.destroy_process_group()
+        return
     gb = len(text) / 1e9
     out = {"what": "fm_vcf_parse on 1000G-shaped text", "lines": a.lines, "samples": a.samples, "text_GB": gb,
            "genotype_calls": a.lines * a.samples, **{k: round(v, 3) for k, v in best.items()},
