@@ -255,3 +255,53 @@ def split_lines(text: str) -> List[str]:
     if lines[-1] != "":
         out.append(lines[-1])
     return out
+
+
+# ----------------------------------------------------------------------------- compiled sibling (vcf_oracle.c)
+def c_process_lines(text: bytes, chr_: str, regions, kept_col_indices, min_gq, allow_regions=None, mask_regions=None,
+                    max_ploidy: int = 2, threads: int = 1):
+    """oracle/vcf_oracle.c through ctypes: the same stage in plain C with pthreads (cross-check of this module and
+    the CPU baseline of tools/bench_vcf.py).  Returns a dict of arrays in output order + counters + error lines."""
+    import ctypes as C
+    import os
+    import subprocess
+
+    import numpy as np
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = os.path.join(here, "_build", "libvcf_oracle.so")
+    src = os.path.join(here, "vcf_oracle.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", here, "-s"])
+    L = C.CDLL(so)
+    L.orc_vcf_process_lines.restype = C.c_size_t
+    key = _normalize_chr_prefix(_rust_trim(chr_))
+
+    def mode(m):
+        if m is None:
+            return 0, np.zeros((0, 2), dtype=np.int64)
+        if key in m:
+            return 1, np.ascontiguousarray(np.asarray(m[key], dtype=np.int64).reshape(-1, 2))
+        return 2, np.zeros((0, 2), dtype=np.int64)
+
+    am, av = mode(allow_regions)
+    mm, mv = mode(mask_regions)
+    reg = np.ascontiguousarray(np.asarray(regions, dtype=np.int64).reshape(-1, 2))
+    kept = np.ascontiguousarray(kept_col_indices, dtype=np.uint32)
+    n_lines_cap = text.count(b"\n") + 1
+    S, P = len(kept), max_ploidy
+    counters = np.zeros(9, dtype=np.uint64)
+    pos0 = np.zeros(n_lines_cap, dtype=np.int64)
+    flags = np.zeros(n_lines_cap, dtype=np.uint8)
+    stride = np.zeros(n_lines_cap, dtype=np.uint8)
+    gt = np.zeros((n_lines_cap, S, P), dtype=np.uint8)
+    err_line = np.zeros(n_lines_cap, dtype=np.uint64)
+    err_code = np.zeros(n_lines_cap, dtype=np.int32)
+    nv, ne = C.c_size_t(), C.c_size_t()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    n_lines = L.orc_vcf_process_lines(text, C.c_size_t(len(text)), key.encode(), p(reg), C.c_size_t(len(reg)), p(kept),
+                                      C.c_size_t(S), C.c_uint32(min_gq), am, p(av), C.c_size_t(len(av)), mm, p(mv),
+                                      C.c_size_t(len(mv)), C.c_size_t(P), int(threads), p(counters), C.byref(nv), p(pos0),
+                                      p(flags), p(stride), p(gt), C.byref(ne), p(err_line), p(err_code))
+    n = nv.value
+    return dict(n_lines=n_lines, positions=pos0[:n], flags=flags[:n], stride=stride[:n], gt=gt[:n],
+                counters=counters, err_line=err_line[: ne.value], err_code=err_code[: ne.value])

@@ -81,6 +81,33 @@ def test_oracle_rules():
     assert r[2] == ov.FLAG_ALLOW  # chromosome absent from both maps: not allowed, not masked
 
 
+def test_compiled_oracle_agrees_with_the_python_restatement():
+    """oracle/vcf_oracle.c (pthreads; the CPU baseline of tools/bench_vcf.py) against oracle/vcf.py on generated
+    text that reaches every branch; 1 and 3 threads."""
+    for seed, n_lines, n_cols, odd in ((1, 80, 4, 0.15), (2, 400, 9, 0.05), (3, 60, 300, 0.01)):
+        rng = np.random.default_rng(seed)
+        text = make_vcf(rng, n_lines, n_cols, odd=odd, crlf=bool(seed & 1))
+        kept = sorted(rng.choice(np.arange(9, 9 + n_cols), size=max(1, n_cols * 3 // 4), replace=False).tolist())
+        regions = [(950, 1200), (1200, 1300), (1500, 2100)]
+        allow = {"1": [(1000, 1100), (1050, 1250), (1600, 1900), (-5, 3), (7, 2)]}
+        mask = {"1": [(1020, 1030), (1700, 1705), (-1, 5), (1990, -1)]}
+        for threads in (1, 3):
+            c = ov.c_process_lines(text.encode(), "chr1", regions, kept, 30, allow, mask, max_ploidy=4, threads=threads)
+            skip = {int(l) for l, code in zip(c["err_line"], c["err_code"]) if code == 16}  # genotype longer than 4
+            out, miss, stats, errors = ov.process_lines(ov.split_lines(text), "chr1", regions, kept, 30, allow, mask,
+                                                        skip=skip)
+            assert c["n_lines"] == len(ov.split_lines(text))
+            assert [int(l) for l, code in zip(c["err_line"], c["err_code"]) if code != 16] == [l for l, _ in errors]
+            assert list(c["positions"]) == [v[0] for v in out] and list(c["flags"]) == [v[2] for v in out]
+            for i, v in enumerate(out):
+                data, stride = ov.compressed(v[1])
+                assert int(c["stride"][i]) == stride and c["gt"][i, :, :stride].tobytes() == data
+            assert list(map(int, c["counters"])) == [stats.total_variants, stats.filtered_variants,
+                                                     stats.filtered_due_to_mask, stats.filtered_due_to_allow,
+                                                     stats.missing_data_variants, stats.low_gq_variants,
+                                                     stats.mnp_variants, miss.total_data_points, miss.missing_data_points]
+
+
 # ----------------------------------------------------------------------------- generated VCF text
 GT_POOL = ["0|0", "0|1", "1|0", "1|1", "0/1", "1/1", "0|0", "0|0", "0|1", "1|1"]
 ODD_GT = [".", "./.", ".|.", "0|.", ".|1", "", "x", "0|x", "2|1", "10|3", "255|0", "0|255", "256|0", "+1|0", "1|+0",

@@ -53,7 +53,7 @@ def main():
     ap.add_argument("--lines", type=int, default=20000)
     ap.add_argument("--samples", type=int, default=2504)
     ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--cpu-lines", type=int, default=200)
+    ap.add_argument("--cpu-lines", type=int, default=4000)
     a = ap.parse_args()
     import torch
 
@@ -129,15 +129,26 @@ def main():
            "h2d_GBps": gb / (best["h2d_ms"] / 1e3), "e2e_GBps_text": gb / (best["wall_ms"] / 1e3),
            "e2e_sample_genotypes_per_s": a.lines * a.samples / (best["wall_ms"] / 1e3),
            "low_gq_variants": int(info.low_gq_variants), "missing_data_variants": int(info.missing_data_variants)}
-    # CPU port (pure-Python restatement, one core) on a bounded sample -- a reported baseline, not the target
+    # CPU port on a bounded sample: oracle/vcf_oracle.c (plain C, pthreads over lines, all host threads) -- a
+    # reported baseline, not the target; the Rust reference (producer / consumer threads around process_variant)
+    # cannot be built in this image
     if a.cpu_lines > 0:
         from oracle import vcf as ov
-        lines = ov.split_lines(text[: 40 * 1024 * 1024].decode())[: a.cpu_lines]
-        t0 = time.perf_counter()
-        o, _, _, _ = ov.process_lines(lines, "1", [(0, 1 << 40)], kept.tolist(), 30)
-        dt = time.perf_counter() - t0
-        out["cpu_port"] = {"kind": "port (pure Python, 1 core)", "lines": len(lines), "seconds": dt,
-                           "sample_genotypes_per_s": len(lines) * a.samples / dt}
+        nth = os.cpu_count() or 1
+        cut = 0
+        for _ in range(min(a.cpu_lines, a.lines)):
+            cut = text.index(b"\n", cut) + 1
+        sample = text[:cut]
+        bestc = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            c = ov.c_process_lines(sample, "1", [(0, 1 << 40)], kept.tolist(), 30, max_ploidy=2, threads=nth)
+            dt = time.perf_counter() - t0
+            bestc = dt if bestc is None or dt < bestc else bestc
+        assert len(c["positions"]) == c["n_lines"]
+        out["cpu_port"] = {"kind": "port (C, pthreads)", "cores": nth, "lines": int(c["n_lines"]), "seconds": bestc,
+                           "text_GBps": len(sample) / bestc / 1e9,
+                           "sample_genotypes_per_s": int(c["n_lines"]) * a.samples / bestc}
     print(json.dumps(out))
 
 
