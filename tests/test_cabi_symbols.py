@@ -51,6 +51,22 @@ def test_compute_fails_loudly_without_device():
     assert "no CPU fallback" in str(exc.value)
 
 
+def test_adjacent_stages_fail_loudly_without_device():
+    """The VCF parser and the FALSTA renderer are device code too: no CPU path behind them."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    import ferromic_b200 as fm
+    from ferromic_b200 import _lib, falsta, vcf
+    with pytest.raises(fm.FerromicGpuError) as exc:
+        vcf.process_lines(b"1\t5\t.\tA\tC\t.\t.\t.\tGT:GQ\t0|1:40\n", "1", [(0, 10)], [9], 30)
+    assert exc.value.code == _lib.FM_ERR_NO_DEVICE
+    with pytest.raises(fm.FerromicGpuError) as exc:
+        falsta.track_lines([2], [0.5], 1, 3, falsta.FST)
+    assert exc.value.code == _lib.FM_ERR_NO_DEVICE
+    assert falsta.format_value(0.5, falsta.FST) == "0.500000"  # the token routine itself is host code
+
+
 def test_product_package_never_imports_the_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "ferromic_b200")):
         for f in files:
