@@ -326,7 +326,8 @@ def count_segregating_sites_for_population(p: Pop) -> int:
 
 
 def pi_sparse(vs: Variants, haplotypes, L: int) -> float:
-    return lib().orc_pi_sparse(vs.c(), Haps(haplotypes).c(), L)
+    h = Haps(haplotypes)  # keep the arrays alive across the call (a temporary would be freed before it)
+    return lib().orc_pi_sparse(vs.c(), h.c(), L)
 
 
 def pi_for_population(p: Pop) -> float:
@@ -340,7 +341,8 @@ def per_site_diversity(vs: Variants, haplotypes, region, filtered=(), mask=None)
     th = np.zeros(n, dtype=np.float64)
     filt = np.asarray(list(filtered), dtype=np.int64)
     miv = np.asarray(mask if mask is not None else [], dtype=np.int64).reshape(-1)
-    k = lib().orc_per_site_diversity(vs.c(), Haps(haplotypes).c(), C.c_int64(region[0]),
+    h = Haps(haplotypes)  # keep the arrays alive across the call
+    k = lib().orc_per_site_diversity(vs.c(), h.c(), C.c_int64(region[0]),
                                      C.c_int64(region[1]), _ptr(filt), C.c_size_t(filt.size), _ptr(miv),
                                      C.c_size_t(miv.size // 2), C.c_int(mask is not None), _ptr(pos),
                                      _ptr(pi), _ptr(th))

@@ -1,0 +1,111 @@
+#!/usr/bin/env python
+"""The whole chain of the path and its two adjacent stages on one GPU, from raw VCF text to FALSTA text:
+   fm_vcf_parse (text -> variants, device-resident genotypes)          SURVEY 8f rank 4
+-> fm_vcf_batch_matrix (from_variants on the device)                    a1
+-> fm_groups_create (two haplotype groups, one pass over the u8 rows)   a2/a3
+-> fm_per_site_diversity per group (pi / theta tracks) + Hudson pair    a9, a10-a13
+-> fm_falsta_tracks (track bodies rendered on the device)               SURVEY 8f rank 3
+1000-Genomes-shaped text (20k lines x 2504 samples by default).  Wall time per stage, one JSON line.
+A 200-line prefix of the same text goes through the CPU oracles end to end and must give the same FALSTA text."""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def chain(text, S, check_oracle=False):
+    from ferromic_b200 import _lib, falsta, vcf
+    L = _lib.lib()
+    T = {}
+    t0 = time.perf_counter()
+    kept = list(range(9, 9 + S))
+    batch = vcf.process_lines(text, "1", [(0, 1 << 40)], kept, 30)
+    T["vcf_parse"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    m = batch.matrix(pass_only=False)
+    T["from_variants"] = time.perf_counter() - t0
+    rng = np.random.default_rng(3)
+    orient = rng.integers(0, 2, size=S)
+    haps0 = [(s, int(orient[s])) for s in range(S)]
+    haps1 = [(s, 1 - int(orient[s])) for s in range(S)]
+    t0 = time.perf_counter()
+    g0, g1 = m.groups([haps0, haps1])
+    T["groups"] = time.perf_counter() - t0
+    V = m.V
+    pos = np.zeros(V, dtype=np.int64)
+    region = (int(batch.positions[0]), int(batch.positions[-1]))
+    t0 = time.perf_counter()
+    recs = {}
+    for gid, (g, haps) in enumerate(((g0, haps0), (g1, haps1))):
+        pi, th = np.zeros(V), np.zeros(V)
+        n = C.c_size_t()
+        _lib.check(L.fm_per_site_diversity(g.handle, len(haps), region[0], region[1], None, 0, None, 0,
+                                           pos.ctypes.data_as(C.c_void_p), pi.ctypes.data_as(C.c_void_p),
+                                           th.ctypes.data_as(C.c_void_p), V, C.byref(n)))
+        recs[gid] = (pos[: n.value].copy(), pi[: n.value], th[: n.value])
+    T["per_site_diversity_x2"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    rs, re_ = region[0] + 1, region[1] + 1
+    lines = {gid: falsta.track_lines(p, np.stack([a, b]), rs, re_, falsta.DIVERSITY) for gid, (p, a, b) in recs.items()}
+    T["falsta_tracks"] = time.perf_counter() - t0
+    out_bytes = sum(len(x) for v in lines.values() for x in v)
+    if check_oracle:
+        from oracle import falsta as ofa
+        from oracle import pyoracle as orc
+        from oracle import vcf as ov
+        out, _, _, _ = ov.process_lines(ov.split_lines(text.decode()), "1", [(0, 1 << 40)], kept, 30)
+        assert [v[0] for v in out] == batch.positions.tolist()
+        vs = orc.variants_from_python([{"position": v[0], "genotypes": v[1]} for v in out], S)
+        per_site = []
+        for gid, haps in ((0, haps0), (1, haps1)):
+            rp, rpi, rth = orc.per_site_diversity(vs, haps, region)
+            per_site += [(int(p), float(a), float(b), gid, False) for p, a, b in zip(rp, rpi, rth)]
+        ref = ofa.diversity_falsta_text("1", rs, re_, per_site).splitlines()
+        got = [lines[0][0], lines[0][1], lines[1][0], lines[1][1]]
+        for k, (gl, rl) in enumerate(zip([l.decode() for l in got], [ref[1], ref[3], ref[5], ref[7]])):
+            if gl != rl:
+                ga, ra = gl.split(","), rl.split(",")
+                bad = [(i, x, y) for i, (x, y) in enumerate(zip(ga, ra)) if x != y][:5]
+                raise AssertionError(f"FALSTA track {k} differs from the oracle chain: {len(ga)} vs {len(ra)} tokens, {bad}")
+    return T, V, out_bytes
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--lines", type=int, default=20000)
+    ap.add_argument("--samples", type=int, default=2504)
+    a = ap.parse_args()
+    import torch
+
+    from tools.bench_vcf import synth_text
+    text = synth_text(a.lines, a.samples)
+    pinned = torch.empty(len(text), dtype=torch.uint8).pin_memory()
+    pinned.numpy()[:] = np.frombuffer(text, dtype=np.uint8)
+    # parity of the whole chain on a prefix the pure-Python oracles finish in seconds
+    cut = 0
+    for _ in range(200):
+        cut = text.index(b"\n", cut) + 1
+    chain(text[:cut], a.samples, check_oracle=True)
+    best = None
+    buf = (C.c_char * len(text)).from_address(pinned.data_ptr())  # bytes-like view of the pinned buffer
+    for rep in range(3):
+        T, V, out_bytes = chain(buf, a.samples)
+        if best is None or sum(T.values()) < sum(best.values()):
+            best = T
+    total = sum(best.values())
+    print(json.dumps({"what": "VCF text -> variants -> matrix -> two groups -> per-site pi/theta -> FALSTA text, one GPU",
+                      "lines": a.lines, "samples": a.samples, "text_GB": len(text) / 1e9, "variants": V,
+                      "falsta_MB": out_bytes / 1e6, "oracle_chain_parity_on_200_lines": True,
+                      "stage_ms": {k: round(v * 1e3, 3) for k, v in best.items()}, "total_ms": round(total * 1e3, 3),
+                      "sample_genotypes_per_s": a.lines * a.samples / total}))
+
+
+if __name__ == "__main__":
+    main()
