@@ -26,6 +26,17 @@ def format_value(value: float, mode: int = FST) -> str:
     return buf.raw[: n.value].decode("ascii")
 
 
+_SCRATCH = [np.empty(0, dtype=np.uint8)]
+
+
+def _scratch(n: int) -> np.ndarray:
+    """Grow-only host buffer for the rendered text: a writer renders track after track of similar size, and
+    first-touch page faults of a fresh 100 MB buffer cost several times the rendering itself."""
+    if _SCRATCH[0].size < n:
+        _SCRATCH[0] = np.empty(int(n * 1.25) + 4096, dtype=np.uint8)
+    return _SCRATCH[0]
+
+
 def track_lines(pos1, values, region_start: int, region_end: int, mode: int) -> List[bytes]:
     """Bodies of the tracks `values[t]` (all sharing the 1-based record positions `pos1`)."""
     pos1 = np.ascontiguousarray(pos1, dtype=np.int64)
@@ -45,11 +56,11 @@ def track_lines(pos1, values, region_start: int, region_end: int, mode: int) -> 
     s1 = max(region_start, 1)
     region_len = max(region_end, s1) - s1 + 1
     cap = T * (3 * region_len + 26 * min(n, region_len)) + 16
-    out = np.empty(cap, dtype=np.uint8)  # not zero-filled: the library writes every byte it reports
+    out = _scratch(cap)  # not zero-filled: the library writes every byte it reports
     st = L.fm_falsta_tracks(pp, vp, n, T, region_start, region_end, mode, out.ctypes.data_as(C.c_void_p), cap, lens,
                             C.byref(total))
     if st != 0 and total.value > cap:
-        out = np.empty(total.value, dtype=np.uint8)
+        out = _scratch(total.value)
         st = L.fm_falsta_tracks(pp, vp, n, T, region_start, region_end, mode, out.ctypes.data_as(C.c_void_p),
                                 total.value, lens, C.byref(total))
     check(st)
