@@ -1343,9 +1343,19 @@ static void launch_repack(const RepackSet &set, const uint8_t *data, size_t data
     if (gs.empty() || v_hi <= v_lo) return;
     const fm_matrix *m = gs[0]->m;
     uint32_t row_buf = 0, bit_buf = 0;
-    const uint32_t warp_smem = (uint32_t)repack_warp_smem(m, &row_buf, &bit_buf);
+    uint32_t warp_smem = (uint32_t)repack_warp_smem(m, &row_buf, &bit_buf);
     static const uint32_t force_v1 = env_u32("FM_REPACK_V1", 0);
     if (warp_smem <= 24 * 1024 && (!force_v1 || set.ct.n_groups)) {
+        // direct mode: nothing reads the raw bytes of the row after the full-row bit words are built
+        static const uint32_t no_direct = env_u32("FM_REPACK_STAGED", 0);
+        bool direct = !no_direct && set.need_row_bits && m->stride % 16 == 0 &&
+                      (reinterpret_cast<uintptr_t>(data) & 15u) == 0;
+        for (const fm_group *g : set.plane_gs) direct = direct && g->n_bits == 1;  // ballot gathers read the staged row
+        if (direct && !set.plane_gs.empty() && !set.d_plan) direct = false;
+        if (direct) {
+            warp_smem -= row_buf;
+            row_buf = 0;
+        }
         const uint32_t warps = std::max(1u, std::min(8u, (200u * 1024u) / warp_smem));
         const size_t smem = (size_t)warps * warp_smem;
         static std::once_flag attr_once;
@@ -1359,7 +1369,7 @@ static void launch_repack(const RepackSet &set, const uint8_t *data, size_t data
         fm::fm_k_repack_rows<<<blocks, warps * 32, smem, st>>>(data, data_bytes, missing, m->stride, v_base, word_base,
                                                                v_lo, v_hi, set.d_desc, (uint32_t)set.plane_gs.size(),
                                                                warp_smem, row_buf, bit_buf, set.ct, m->in_band ? 1u : 0u,
-                                                               set.need_row_bits ? 1u : 0u);
+                                                               set.need_row_bits ? 1u : 0u, direct ? 1u : 0u);
         CK(cudaGetLastError());
         g_launches++;
         return;

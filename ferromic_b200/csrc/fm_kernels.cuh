@@ -150,7 +150,10 @@ fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint
                  size_t stride, uint32_t v_base, uint64_t word_base, uint32_t v_lo, uint32_t v_hi,
                  const RepackGroup *__restrict__ groups, uint32_t n_groups, uint32_t warp_smem_bytes,
                  uint32_t row_buf_bytes, uint32_t bit_buf_bytes, CountTable ct, uint32_t in_band,
-                 uint32_t need_row_bits) {
+                 uint32_t need_row_bits, uint32_t direct_rows) {
+    // direct_rows: every group is served from the full-row bit words (compress plans / count tables) and rows are
+    // whole 16-byte words, so the u8 row is packed straight from global memory (coalesced 16-byte loads) and is
+    // never staged: row_buf_bytes == 0, three times the resident warps per SM
     extern __shared__ __align__(16) uint8_t rp_smem[];
     constexpr uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -168,7 +171,7 @@ fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint
         __syncwarp();
         // asynchronous 16-byte copies straight into shared memory: every chunk of the row is in
         // flight at once (no register staging, no per-iteration load latency)
-        for (uint32_t q = lane; q < nq; q += 32) {
+        for (uint32_t q = lane; !direct_rows && q < nq; q += 32) {
             const size_t at = a0 + ((size_t)q << 4);
             if (at + 16 <= data_bytes) {
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(fm_smem_u32(rowb + ((size_t)q << 4))),
@@ -208,39 +211,51 @@ fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint
             const uint32_t sh8 = (delta & 3u) * 8u;
             // rows that start on a 16-byte boundary (stride % 16 == 0, e.g. 5008 or 200000 haplotypes): 16 cells per
             // lane and step (one LDS.128, four nibbles), two lanes per row word; otherwise 4 cells per lane
-            const bool wide = (delta & 15u) == 0u;
+            const bool wide = direct_rows || (delta & 15u) == 0u;
             if (wide) {
-                const uint4 *row128 = reinterpret_cast<const uint4 *>(rowb + delta);
+                const uint4 *row128 = direct_rows ? reinterpret_cast<const uint4 *>(data + row0)
+                                                  : reinterpret_cast<const uint4 *>(rowb + delta);
                 const uint32_t nq16 = ((uint32_t)stride + 15u) >> 4;
-                for (uint32_t base = 0; base < nq16; base += 32) {
-                    const uint32_t q = base + lane;
-                    uint4 x = make_uint4(0, 0, 0, 0);
-                    if (q < nq16) {
-                        x = row128[q];
-                        const uint32_t left = (uint32_t)stride - q * 16u;  // cells that exist in this group
-                        if (left < 16u) {
-                            uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+                // bit 7 of every non-zero byte (the add only sees 7-bit fields: no carry crosses bytes), gathered by one multiply
+                auto nib = [](uint32_t w) {
+                    return (((((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w) >> 7 & 0x01010101u) * 0x01020408u) >> 24;
+                };
+                auto cnib = [](uint32_t w) { return (((~w >> 7) & 0x01010101u) * 0x01020408u >> 24) & 0xFu; };
+                // four 16-byte loads per lane are issued before the first is consumed (direct mode reads global memory)
+                for (uint32_t base = 0; base < nq16; base += 128) {
+                    uint4 xq[4];
 #pragma unroll
-                            for (uint32_t k = 0; k < 4; ++k) {
-                                const uint32_t have = left > 4u * k ? min(4u, left - 4u * k) : 0u;
-                                xs[k] = have >= 4u ? xs[k] : (have ? xs[k] & ((1u << (8u * have)) - 1u) : 0u);
-                            }
-                            x = make_uint4(xs[0], xs[1], xs[2], xs[3]);
-                        }
+                    for (uint32_t u = 0; u < 4; ++u) {
+                        const uint32_t q = base + u * 32u + lane;
+                        xq[u] = make_uint4(0, 0, 0, 0);
+                        if (q < nq16) xq[u] = direct_rows ? __ldg(row128 + q) : row128[q];
                     }
-                    // bit 7 of every non-zero byte (the add only sees 7-bit fields: no carry crosses bytes), gathered by one multiply
-                    auto nib = [](uint32_t w) {
-                        return (((((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w) >> 7 & 0x01010101u) * 0x01020408u) >> 24;
-                    };
-                    const uint32_t a16 = nib(x.x) | (nib(x.y) << 4) | (nib(x.z) << 8) | (nib(x.w) << 12);
-                    const uint32_t ao = __shfl_xor_sync(FULL, a16, 1);
-                    const uint32_t w = q >> 1;
-                    if (!(lane & 1u) && w < rw) arow[w] = a16 | (ao << 16);
-                    if (in_band) {  // called = cell < 0x80 (a non-negative int8); absent cells read 0 and are masked below
-                        auto cnib = [](uint32_t w) { return (((~w >> 7) & 0x01010101u) * 0x01020408u >> 24) & 0xFu; };
-                        const uint32_t c16 = cnib(x.x) | (cnib(x.y) << 4) | (cnib(x.z) << 8) | (cnib(x.w) << 12);
-                        const uint32_t co = __shfl_xor_sync(FULL, c16, 1);
-                        if (!(lane & 1u) && w < rw) crow[w] = c16 | (co << 16);
+#pragma unroll
+                    for (uint32_t u = 0; u < 4; ++u) {
+                        const uint32_t q = base + u * 32u + lane;
+                        if (base + u * 32u >= nq16) break;  // warp-uniform
+                        uint4 x = xq[u];
+                        if (q < nq16) {
+                            const uint32_t left = (uint32_t)stride - q * 16u;  // cells that exist in this group
+                            if (left < 16u) {
+                                uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                                for (uint32_t k = 0; k < 4; ++k) {
+                                    const uint32_t have = left > 4u * k ? min(4u, left - 4u * k) : 0u;
+                                    xs[k] = have >= 4u ? xs[k] : (have ? xs[k] & ((1u << (8u * have)) - 1u) : 0u);
+                                }
+                                x = make_uint4(xs[0], xs[1], xs[2], xs[3]);
+                            }
+                        }
+                        const uint32_t a16 = nib(x.x) | (nib(x.y) << 4) | (nib(x.z) << 8) | (nib(x.w) << 12);
+                        const uint32_t ao = __shfl_xor_sync(FULL, a16, 1);
+                        const uint32_t w = q >> 1;
+                        if (!(lane & 1u) && w < rw) arow[w] = a16 | (ao << 16);
+                        if (in_band) {  // called = cell < 0x80 (a non-negative int8); absent cells read 0 and are masked below
+                            const uint32_t c16 = cnib(x.x) | (cnib(x.y) << 4) | (cnib(x.z) << 8) | (cnib(x.w) << 12);
+                            const uint32_t co = __shfl_xor_sync(FULL, c16, 1);
+                            if (!(lane & 1u) && w < rw) crow[w] = c16 | (co << 16);
+                        }
                     }
                 }
             }
