@@ -378,7 +378,7 @@ def run_ours(args):
         if args.free_device_copy:
             del d_data, d_bitmap
             torch.cuda.empty_cache()
-        out_pos = np.zeros(V, dtype=np.int64)
+        out_pos = torch.empty(V, dtype=torch.int64, pin_memory=True).numpy()  # caller-owned result buffers are pinned
         out_pi = torch.empty((2, V), dtype=torch.float64, pin_memory=True).numpy()
         out_th = torch.empty((2, V), dtype=torch.float64, pin_memory=True).numpy()
 
