@@ -91,7 +91,9 @@ def gen_device(n_sites, n_samples, seed, device, missing_rate=MISSING_RATE, inba
         torch.manual_seed(seed * 1_000_003 + s0)
         f = beta.sample((n,)).to(device).clamp_(0.001, 0.999)
         a = (torch.rand((n, stride), generator=gen, device=device) < f[:, None])
-        miss = torch.rand((n, stride), generator=gen, device=device) < missing_rate
+        # whole genotypes are missing ("./." in a VCF): the dense per-allele bitmap then carries exactly the
+        # sparse missingness calculate_per_site_diversity sees
+        miss = (torch.rand((n, n_samples), generator=gen, device=device) < missing_rate).repeat_interleave(2, dim=1)
         a &= ~miss
         data[s0 * stride:s1 * stride] = a.reshape(-1).to(torch.uint8)
         if inband is not None:  # the same cohort as an int8 array: missing cells are negative (0xFF)
@@ -119,7 +121,7 @@ def gen_host_sample(n_sites, n_samples, seed):
     for s0 in range(0, n_sites, step):
         s1 = min(n_sites, s0 + step)
         r = rng.random((s1 - s0, stride), dtype=np.float32)
-        m = rng.random((s1 - s0, stride), dtype=np.float32) < MISSING_RATE
+        m = np.repeat(rng.random((s1 - s0, n_samples), dtype=np.float32) < MISSING_RATE, 2, axis=1)
         data[s0:s1] = (r < f[s0:s1, None]) & ~m
         miss[s0:s1] = m
     return data, miss
@@ -225,6 +227,109 @@ def workload_config(args):
 
 
 # ----------------------------------------------------------------------------- our arm
+def group_arrays(haps):
+    return (np.asarray([h[0] for h in haps], dtype=np.uint64), np.asarray([h[1] for h in haps], dtype=np.uint8))
+
+
+def load_peaks():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        peaks = {}
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    return peak, src
+
+
+def parity_of_run(L, _lib, groups, g_lists, pos, mask, d_data, d_bitmap, V, S, res, rank, world, dist, device):
+    """SURVEY 8(d) "parity check per run": (1) the public call (same fused kernel as the timed steps) against the
+    CPU oracle on a 10^4-site slice of THIS rank's shard: positions and NaN pattern exact, pi / theta <= 1e-9
+    relative, alt / called counts and S bit-exact; (2) the timed loop's own last-step region totals against the
+    public call; (3) N > 1: the totals that came out of the peer exchange against a rank-ordered sum of every
+    rank's local totals gathered with torch.distributed (bit-equal).  Raises on any mismatch."""
+    import torch
+    from oracle import pyoracle as orc  # the checker, never the thing measured
+
+    garr = (C.c_void_p * 2)(*[g.value for g in groups])
+    raw_n = (C.c_size_t * 2)(*[len(h) for h in g_lists])
+    out_pos = np.empty(V, dtype=np.int64)
+    out_pi = np.empty((2, V), dtype=np.float64)
+    out_th = np.empty((2, V), dtype=np.float64)
+    n = C.c_size_t()
+    _lib.check(L.fm_per_site_diversity_multi(garr, raw_n, 2, int(pos[0]), int(pos[-1]), mask.ctypes.data,
+                                             mask.size // 2, None, 0, out_pos.ctypes.data, out_pi.ctypes.data,
+                                             out_th.ctypes.data, V, C.byref(n)))
+    assert n.value == V, "per-site call returned a wrong number of sites"
+    ns = min(10_000, V)
+    s0 = ((V // 3) // 64) * 64
+    s0 = max(0, min(s0, V - ns))
+    stride = S * 2
+    rows = d_data[s0 * stride:(s0 + ns) * stride].cpu().numpy().reshape(ns, S, 2)
+    e0 = s0 * stride
+    w0, w1 = e0 // 64, ((s0 + ns) * stride + 63) // 64
+    words = d_bitmap[w0:w1].cpu().numpy().view(np.uint64)
+    bits = np.unpackbits(words.view(np.uint8), bitorder="little")[e0 - w0 * 64:e0 - w0 * 64 + ns * stride]
+    miss = bits.reshape(ns, S, 2).astype(bool)
+    gt = rows.copy()
+    gt[miss] = 0xFF
+    assert np.array_equal(miss[:, :, 0], miss[:, :, 1]), "generator must drop whole genotypes"
+    spos = np.ascontiguousarray(pos[s0:s0 + ns])
+    vs = orc.Variants(spos, gt)
+    dense = orc.Dense(rows.reshape(-1), orc.pack_missing_bits(miss.reshape(-1)), ns, S, 2, 1)
+    region = (int(spos[0]), int(spos[-1]))
+    checked = 0
+    for k, haps in enumerate(g_lists):
+        rp, rpi, rth = orc.per_site_diversity(vs, haps, region, mask=mask.reshape(-1, 2))
+        gp, gpi, gth = out_pos[s0:s0 + ns], out_pi[k, s0:s0 + ns], out_th[k, s0:s0 + ns]
+        if not np.array_equal(gp, rp):
+            raise RuntimeError("parity: per-site positions differ from the oracle")
+        for got, ref, name in ((gpi, rpi, "pi"), (gth, rth, "theta")):
+            if not np.array_equal(np.isnan(got), np.isnan(ref)):
+                raise RuntimeError(f"parity: NaN pattern of {name} differs from the oracle (group {k})")
+            ok = ~np.isnan(ref)
+            if not np.all(np.abs(got[ok] - ref[ok]) <= 1e-9 * np.abs(ref[ok])):
+                raise RuntimeError(f"parity: {name} differs from the oracle by more than 1e-9 relative (group {k})")
+        checked += 2 * ns
+        # integer side: counts of the slice window through the public window call vs the oracle's dense summary
+        summ = orc.build_summary(dense, haps)
+        w = np.array([region[0], region[1]], dtype=np.int64)
+        nv, seg, unc = (np.zeros(1, dtype=np.uint64) for _ in range(3))
+        pis = np.zeros(1)
+        _lib.check(L.fm_group_window_sums(groups[k], w.ctypes.data, 1, nv.ctypes.data, seg.ctypes.data, pis.ctypes.data,
+                                          unc.ctypes.data))
+        if int(nv[0]) != ns or int(seg[0]) != int(summ.seg) or int(unc[0]) != int((summ.called < 2).sum()):
+            raise RuntimeError(f"parity: window S / uncallable counts differ from the oracle (group {k})")
+        if abs(pis[0] - summ.pi_sum) > 1e-9 * abs(summ.pi_sum):
+            raise RuntimeError(f"parity: window sum of pi differs from the oracle (group {k})")
+    # (2) the timed loop's last step against the public call over the whole shard
+    local = []
+    for k in range(2):
+        seg, unc, pis = C.c_uint64(), C.c_uint64(), C.c_double()
+        _lib.check(L.fm_group_summary(groups[k], None, None, C.byref(seg), C.byref(pis), C.byref(unc)))
+        if res.last_seg[k] != seg.value or res.last_unc[k] != unc.value:
+            raise RuntimeError(f"parity: timed step totals (S {res.last_seg[k]}, uncallable {res.last_unc[k]}) differ "
+                               f"from the public call ({seg.value}, {unc.value}) for group {k}")
+        if abs(res.last_pi_sum[k] - pis.value) > 1e-9 * abs(pis.value):
+            raise RuntimeError(f"parity: timed step sum of pi differs from the public call for group {k}")
+        local += [res.last_pi_sum[k], float(res.last_seg[k]), float(res.last_unc[k])]
+    exchange = None
+    if world > 1:  # (3) what the mailbox exchange delivered == rank-ordered sum of all ranks' local totals
+        mine = torch.tensor(local, dtype=torch.float64, device=device)
+        allv = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        tot = np.zeros(6)
+        for r in range(world):  # rank order, like fm_k_comm_exchange
+            tot = tot + allv[r].cpu().numpy()
+        for k in range(2):
+            if (res.merged_pi_sum[k] != tot[3 * k] or float(res.merged_seg[k]) != tot[3 * k + 1] or
+                    float(res.merged_unc[k]) != tot[3 * k + 2]):
+                raise RuntimeError(f"parity: exchanged totals differ from the rank-ordered sum on rank {rank} "
+                                   f"(group {k}: {res.merged_pi_sum[k]!r} vs {tot[3 * k]!r})")
+        exchange = "merged totals bit-equal to the rank-ordered all_gather sum on every rank"
+    return {"status": "ok", "oracle_slice_sites": ns, "values_checked": checked, "tolerance": "ints exact, f64 1e-9 rel",
+            "timed_step_totals": "equal to the public call", "exchange": exchange}
+
+
 def run_ours(args):
     # libraries (NCCL's version banner) may write to fd 1: keep the real stdout for the one JSON line
     json_fd = os.dup(1)
@@ -232,7 +337,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    import ferromic_b200 as fm
+    import ferromic_b200 as fm  # noqa: F401  (fails loudly when the CUDA library is missing)
     from ferromic_b200 import _lib
 
     rank = int(os.environ.get("RANK", "0"))
@@ -252,37 +357,22 @@ def run_ours(args):
     pos = make_positions(V, seed)
     mask = make_mask(pos, seed)
     g0, g1 = make_groups(S, N_SITES + N_SAMPLES)
+    g_lists = (g0, g1)
+    garrs = [group_arrays(h) for h in g_lists]
     t0 = time.perf_counter()
-    h_i8 = None
-    if not args.skip_e2e and not args.skip_inband:
-        d_i8 = torch.empty(V * S * 2, dtype=torch.uint8, device=device)
-        d_data, d_bitmap = gen_device(V, S, seed, device, inband=d_i8)
-        h_i8 = torch.empty(d_i8.numel(), dtype=torch.uint8, pin_memory=True)
-        h_i8.copy_(d_i8)
-        torch.cuda.synchronize()
-        del d_i8
-    else:
-        d_data, d_bitmap = gen_device(V, S, seed, device)
+    d_data, d_bitmap = gen_device(V, S, seed, device)
     torch.cuda.synchronize()
     log(f"[rank {rank}] generated {V}x{S * 2} u8 matrix on device in {time.perf_counter() - t0:.1f}s")
-
-    def group_arrays(haps):
-        return (np.asarray([h[0] for h in haps], dtype=np.uint64), np.asarray([h[1] for h in haps], dtype=np.uint8))
-
-    def make_groups_on(matrix):
-        hs = []
-        for haps in (g0, g1):
-            idx, side = group_arrays(haps)
-            h = C.c_void_p()
-            _lib.check(L.fm_group_create(matrix, idx.ctypes.data, side.ctypes.data, len(haps), C.byref(h)))
-            hs.append(h)
-        return hs
 
     # ---------------- device-resident (value)
     m = C.c_void_p()
     _lib.check(L.fm_matrix_create_device(d_data.data_ptr(), d_bitmap.data_ptr(), V, S, 2, 1, pos.ctypes.data,
                                          C.byref(m)))
-    groups = make_groups_on(m)
+    groups = []
+    for idx, side in garrs:
+        h = C.c_void_p()
+        _lib.check(L.fm_group_create(m, idx.ctypes.data, side.ctypes.data, len(idx), C.byref(h)))
+        groups.append(h)
     garr = (C.c_void_p * 2)(*[g.value for g in groups])
     res = _lib.BenchResult()
     # N > 1: every step ends with the exchange of the groups' region totals (S, sum pi, uncallable
@@ -303,8 +393,8 @@ def run_ours(args):
         handles = np.ascontiguousarray(allh.cpu().numpy())
         _lib.check(L.fm_comm_connect(comm, handles.ctypes.data))
         dist.barrier()
-    _lib.check(L.fm_bench_diversity(garr, 2, 1, mask.ctypes.data, mask.size // 2, max(args.warmup, 3), comm,
-                                    C.byref(res)))
+    warm = max(args.warmup, 3)
+    _lib.check(L.fm_bench_diversity(garr, 2, 1, mask.ctypes.data, mask.size // 2, warm, comm, C.byref(res)))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -315,12 +405,13 @@ def run_ours(args):
         dev_ms = res.step_ms_avg * args.steps
         torch.cuda.synchronize()
         wall_ms = (time.perf_counter() - wall0) * 1e3
+        timed_samples = len(clocks.samples)
         if world > 1:
             dist.barrier()
         # the timed region is a few milliseconds: keep the same kernels running (untimed) until the
         # sampler has seen the clocks under this load a few times
         t_keep = time.perf_counter()
-        while len(clocks.samples) < 8 and time.perf_counter() - t_keep < 4.0:
+        while len(clocks.samples) < timed_samples + 8 and time.perf_counter() - t_keep < 4.0:
             _lib.check(L.fm_bench_diversity(garr, 2, 1, mask.ctypes.data, mask.size // 2, 200, None,
                                             C.byref(_lib.BenchResult())))
     tmax = torch.tensor([dev_ms], dtype=torch.float64, device=device)
@@ -330,17 +421,16 @@ def run_ours(args):
     geno_per_rank = V * S * 2
     value = world * geno_per_rank * args.steps / (dev_ms_max * 1e-3)
 
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    # ---------------- roofline of the dominant kernel: UNPADDED algorithmic bytes: 2 bits per
+    # genotype of the analysed groups + 16 B of tracks per site and group; the 16-byte row padding of the
+    # planes shows up in traffic / algorithmic, not in `achieved`
+    peak, peak_src = load_peaks()
     launches_per_step = max(1, int(round(res.plane_launches / args.steps)))
-    plane_launch_bytes = res.plane_bytes_per_step / launches_per_step
-    achieved = plane_launch_bytes / (res.plane_ms_avg * 1e-3) / 1e9
-    traffic = None
+    n_hap = len(g0) + len(g1)
+    algorithmic = (V * n_hap * 2) / 8.0 + 2 * 16.0 * V
+    padded = float(res.plane_bytes_per_step)
+    achieved = algorithmic / launches_per_step / (res.plane_ms_avg * 1e-3) / 1e9
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic_plane_pass.json")
     if os.path.exists(tpath):
         try:
@@ -348,16 +438,55 @@ def run_ours(args):
             traffic = tj.get("dram_bytes_per_launch")
             if tj.get("launches_per_step") and tj["launches_per_step"] != launches_per_step:
                 traffic = traffic * tj["launches_per_step"] / launches_per_step  # same bytes, other launch split
+            traffic_src = "static: ncu --set full capture " + str(tj.get("capture", "profiles/traffic_plane_pass.json")) + \
+                          " (not measured in this run)"
         except Exception:
             traffic = None
     kname = ("fm_k_plane_pass_seq (both groups' planes streamed by one persistent launch)" if launches_per_step == 1
              else "fm_k_plane_pass<1>")
-    roofline = {"bound": "hbm", "kernel": kname, "launches_per_step": launches_per_step, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0, "peak_source": peak_src,
-                "traffic": traffic, "bytes_per_launch": plane_launch_bytes, "ms_per_launch": res.plane_ms_avg,
+    roofline = {"bound": "hbm", "kernel": kname, "launches_per_step": launches_per_step, "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0,
+                "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
+                "traffic_over_algorithmic": (traffic / (algorithmic / launches_per_step)) if traffic else None,
+                "bytes_per_launch": algorithmic / launches_per_step,
+                "bytes_per_launch_def": "V*H*0.25 (allele + called bit of every analysed haplotype) + 2 groups * 16 B/site "
+                                        "of pi/theta tracks; row padding excluded",
+                "padded_bytes_per_launch": padded / launches_per_step, "ms_per_launch": res.plane_ms_avg,
                 "per_group": None if launches_per_step == 1 else
                 [{"haplotypes": len(h), "ms": res.group_ms_avg[i],
                   "GBps": res.group_bytes[i] / (res.group_ms_avg[i] * 1e-3) / 1e9} for i, h in enumerate((g0, g1))]}
+
+    # ---------------- parity of this run (oracle = checker only)
+    parity = None
+    if not args.skip_parity:
+        parity = parity_of_run(L, _lib, groups, g_lists, pos, mask, d_data, d_bitmap, V, S, res, rank, world, dist,
+                               device)
+
+    # ---------------- K1 + stats from the device-resident u8 matrix (secondary, like-for-like with the CPU arm's
+    # input: the reference layout with its bitmap, already in HBM)
+    from_u8 = None
+    if not args.skip_from_u8:
+        def one():
+            hs = (C.c_void_p * 2)()
+            idx = np.concatenate([a[0] for a in garrs])
+            side = np.concatenate([a[1] for a in garrs])
+            sizes = (C.c_size_t * 2)(len(g0), len(g1))
+            _lib.check(L.fm_groups_create(m, idx.ctypes.data, side.ctypes.data, sizes, 2, hs))
+            r = _lib.BenchResult()
+            _lib.check(L.fm_bench_diversity(hs, 2, 1, mask.ctypes.data, mask.size // 2, 1, None, C.byref(r)))
+            for h in hs:
+                L.fm_group_release(C.c_void_p(h))
+        one()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            one()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        from_u8 = {"value": geno_per_rank / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
+                   "what": "fm_groups_create (K1 repack of both groups from the device-resident u8 matrix + bitmap) + one "
+                           "fused per-site pass, wall clock, per rank"}
 
     for g in groups:
         L.fm_group_release(g)
@@ -367,25 +496,35 @@ def run_ours(args):
             dist.barrier()  # nobody may still be writing into a mailbox that is about to be freed
         L.fm_comm_destroy(comm)
 
-    # ---------------- end to end through the C ABI with host (pinned) buffers
+    # ---------------- end to end through the C ABI with HOST buffers
     e2e = None
     if not args.skip_e2e:
+        stride = S * 2
         h_data = torch.empty(d_data.numel(), dtype=torch.uint8, pin_memory=True)
         h_bitmap = torch.empty(d_bitmap.numel(), dtype=torch.int64, pin_memory=True)
         h_data.copy_(d_data)
         h_bitmap.copy_(d_bitmap)
         torch.cuda.synchronize()
-        if args.free_device_copy:
-            del d_data, d_bitmap
-            torch.cuda.empty_cache()
+        del d_data, d_bitmap
+        torch.cuda.empty_cache()
+        rw = (stride + 31) // 32
+        # the packed rows a parser would write directly (2 bits per genotype); produced here by the library's own
+        # host packer, timed separately
+        h_ab = torch.empty(V * rw, dtype=torch.int32, pin_memory=True)
+        h_cb = torch.empty(V * rw, dtype=torch.int32, pin_memory=True)
+        threads = os.cpu_count() or 1
+        pack_ms = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            _lib.check(L.fm_pack_rows(h_data.data_ptr(), h_bitmap.data_ptr(), 1, 0, V, V, stride, h_ab.data_ptr(),
+                                      h_cb.data_ptr(), 0))
+            pack_ms.append((time.perf_counter() - t0) * 1e3)
         out_pos = torch.empty(V, dtype=torch.int64, pin_memory=True).numpy()  # caller-owned result buffers are pinned
         out_pi = torch.empty((2, V), dtype=torch.float64, pin_memory=True).numpy()
         out_th = torch.empty((2, V), dtype=torch.float64, pin_memory=True).numpy()
+        raw_n = (C.c_size_t * 2)(len(g0), len(g1))
 
-        phases = {}
-
-        def e2e_step(inband=False):
-            # streaming ingest: chunked H2D overlapped with the repack into both groups' bitplanes
+        def e2e_step(mode, phases, src=None):
             t = [time.perf_counter()]
 
             def lap(name):
@@ -393,97 +532,97 @@ def run_ours(args):
                 phases[name] = phases.get(name, 0.0) + (t[-1] - t[-2]) * 1e3
 
             ih = C.c_void_p()
-            _lib.check(L.fm_ingest_begin(V, S, 2, 2 if inband else 1, 1, pos.ctypes.data, 0, C.byref(ih)))
+            _lib.check(L.fm_ingest_begin(V, S, 2, 1, 1, pos.ctypes.data, 0, C.byref(ih)))
             for idx, side in garrs:
                 _lib.check(L.fm_ingest_add_group(ih, idx.ctypes.data, side.ctypes.data, len(idx), None))
             lap("begin+declare_groups")
-            if inband:  # the caller's int8 array as it is: negative cells are missing, no bitmap
-                _lib.check(L.fm_ingest_rows(ih, h_i8.data_ptr(), None, 0, V))
-            else:
-                _lib.check(L.fm_ingest_rows(ih, h_data.data_ptr(), h_bitmap.data_ptr(), 0, V))
+            if mode == "packed":      # 2-bit rows over PCIe, compressed into both groups' planes chunk by chunk
+                _lib.check(L.fm_ingest_rows_packed(ih, h_ab.data_ptr(), h_cb.data_ptr(), 0, V))
+            elif mode == "u8_pack":   # u8 + bitmap in, the library packs on the host while the previous chunk uploads
+                d, b = src or (h_data.data_ptr(), h_bitmap.data_ptr())
+                _lib.check(L.fm_ingest_rows_pack(ih, d, b, 0, V, 0))
+            else:                     # round-1 path: the u8 matrix itself crosses PCIe
+                d, b = src or (h_data.data_ptr(), h_bitmap.data_ptr())
+                _lib.check(L.fm_ingest_rows(ih, d, b, 0, V))
             lap("ingest_rows")
             mh = C.c_void_p()
             gh = (C.c_void_p * 2)()
             _lib.check(L.fm_ingest_finish(ih, C.byref(mh), gh, None))
-            gs = [C.c_void_p(gh[0]), C.c_void_p(gh[1])]
             lap("finish")
             n = C.c_size_t()
-            for k, (g, haps) in enumerate(zip(gs, (g0, g1))):
-                _lib.check(L.fm_per_site_diversity(g, len(haps), int(pos[0]), int(pos[-1]), mask.ctypes.data,
-                                                   mask.size // 2, None, 0, out_pos.ctypes.data,
-                                                   out_pi[k].ctypes.data, out_th[k].ctypes.data, V, C.byref(n)))
-            lap("per_site_diversity_x2")
-            for g in gs:
-                L.fm_group_release(g)
+            _lib.check(L.fm_per_site_diversity_multi(gh, raw_n, 2, int(pos[0]), int(pos[-1]), mask.ctypes.data,
+                                                     mask.size // 2, None, 0, out_pos.ctypes.data, out_pi.ctypes.data,
+                                                     out_th.ctypes.data, V, C.byref(n)))
+            lap("per_site_diversity_multi")
+            for g in gh:
+                L.fm_group_release(C.c_void_p(g))
             L.fm_matrix_release(mh)
             lap("release")
             return n.value
 
-        garrs = [group_arrays(h) for h in (g0, g1)]
-        e2e_step()  # warm-up
-        phases.clear()
-        k = max(1, min(args.steps, args.e2e_steps))
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        L.fm_timings_reset()
-        t0 = time.perf_counter()
-        for _ in range(k):
-            e2e_step()
-        torch.cuda.synchronize()
-        t_e2e = time.perf_counter() - t0
-        tim = _lib.Timings()
-        L.fm_timings_get(C.byref(tim))
-        phases_timed = dict(phases)
-        inband_info = None
-        if h_i8 is not None:
-            e2e_step(inband=True)
+        def timed(mode, k, src=None):
+            e2e_step(mode, {}, src)  # warm-up
+            if world > 1:
+                dist.barrier()
             torch.cuda.synchronize()
+            L.fm_timings_reset()
+            phases = {}
             t0 = time.perf_counter()
             for _ in range(k):
-                e2e_step(inband=True)
+                e2e_step(mode, phases, src)
             torch.cuda.synchronize()
-            t_in = (time.perf_counter() - t0) / k
-            inband_info = {"value": geno_per_rank / t_in, "ms_per_step": t_in * 1e3,
-                           "h2d_bytes_per_step": int(h_i8.numel() + V * 8),
-                           "what": "same step from the int8 array Population.from_numpy receives (negative = missing, "
-                                   "FM_MISSING_IN_BAND): no bitmap, no host conversion pass; per rank"}
-        # the same call with PAGEABLE host memory (what a Rust Vec<u8> or a numpy array is): the library
-        # fills pinned bounce buffers with several host threads and overlaps them with the DMA
-        pageable_ms = None
+            dt = time.perf_counter() - t0
+            tim = _lib.Timings()
+            L.fm_timings_get(C.byref(tim))
+            te = torch.tensor([dt], dtype=torch.float64, device=device)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dt = float(te.item())
+            return {"value": world * geno_per_rank * k / dt, "ms_per_step": dt / k * 1e3,
+                    "breakdown_ms_per_step": {"h2d": tim.h2d_ms / k, "repack": tim.repack_ms / k, "pack_host": tim.pack_ms / k,
+                                              "stats": tim.stats_ms / k, "reduce": tim.reduce_ms / k, "d2h": tim.d2h_ms / k},
+                    "host_phase_ms_per_step": {k_: v_ / k for k_, v_ in phases.items()}}
+
+        k = max(1, min(args.steps, args.e2e_steps))
+        r_packed = timed("packed", k)
+        check_pi = out_pi.copy()
+        r_u8pack = timed("u8_pack", k)
+        same = bool(np.array_equal(np.isnan(check_pi), np.isnan(out_pi)) and
+                    np.array_equal(check_pi[~np.isnan(check_pi)], out_pi[~np.isnan(out_pi)]))
+        r_u8 = timed("u8", k) if not args.skip_u8 else None
+        if r_u8 is not None:
+            same = same and bool(np.array_equal(check_pi[~np.isnan(check_pi)], out_pi[~np.isnan(out_pi)]))
+        if not same:
+            raise RuntimeError("parity: the packed, pack-on-host and u8 ingests produced different per-site tracks")
+        pageable = None
         if rank == 0 and world == 1 and not args.skip_pageable:
-            p_data = np.array(h_data.numpy(), copy=True)
+            p_data = np.array(h_data.numpy(), copy=True)   # what a Rust Vec<u8> / numpy array is: pageable
             p_bitmap = np.array(h_bitmap.numpy(), copy=True)
-            pinned_ptrs = (h_data, h_bitmap)
-
-            class _P:  # minimal stand-in exposing data_ptr() like the pinned tensors
-                def __init__(self, a):
-                    self.a = a
-
-                def data_ptr(self):
-                    return self.a.ctypes.data
-            h_data, h_bitmap = _P(p_data), _P(p_bitmap)
-            e2e_step()
-            t0 = time.perf_counter()
-            e2e_step()
-            torch.cuda.synchronize()
-            pageable_ms = (time.perf_counter() - t0) * 1e3
-            h_data, h_bitmap = pinned_ptrs
+            src = (p_data.ctypes.data, p_bitmap.ctypes.data)
+            pageable = {"u8_pack_ms_per_step": timed("u8_pack", 1, src)["ms_per_step"],
+                        "u8_ms_per_step": None if args.skip_u8 else timed("u8", 1, src)["ms_per_step"]}
             del p_data, p_bitmap
-        te = torch.tensor([t_e2e], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * geno_per_rank * k / float(te.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(h_data.numel() + h_bitmap.numel() * 8 + V * 8),
-               "d2h_bytes_per_step": int(2 * 2 * V * 8), "steps": k, "ms_per_step": float(te.item()) / k * 1e3,
-               "breakdown_ms_per_step": {"h2d": tim.h2d_ms / k, "repack": tim.repack_ms / k,
-                                         "stats": tim.stats_ms / k, "reduce": tim.reduce_ms / k,
-                                         "d2h": tim.d2h_ms / k},
-               "host_phase_ms_per_step": {k_: v_ / k for k_, v_ in phases_timed.items()},
-               "pageable_host_ms_per_step": pageable_ms, "inband_int8": inband_info,
-               "api": "fm_ingest_begin/add_group/rows/finish (chunked H2D overlapped with repack) + "
-                      "fm_per_site_diversity per group; h2d and repack spans overlap",
-               "timing": "wall clock around synchronous C-ABI calls, cuda-synchronised on both sides"}
+        h2d_packed = int(2 * V * rw * 4 + V * 8 + mask.size * 8)
+        e2e = {"value": r_packed["value"], "unit": UNIT, "h2d_bytes_per_step": h2d_packed,
+               "d2h_bytes_per_step": int(2 * 2 * V * 8), "steps": k, "ms_per_step": r_packed["ms_per_step"],
+               "breakdown_ms_per_step": r_packed["breakdown_ms_per_step"],
+               "host_phase_ms_per_step": r_packed["host_phase_ms_per_step"],
+               "api": "fm_ingest_begin / add_group x2 / fm_ingest_rows_packed (2-bit rows from pinned host memory; chunked "
+                      "H2D overlapped with the compress pass K1p) / finish + fm_per_site_diversity_multi (one fused launch, "
+                      "tracks D2H into pinned host memory); per rank",
+               "input": "packed rows: allele bit + called bit per genotype, as a parser emits them (include/ferromic_gpu.h)",
+               "packer": {"ms": min(pack_ms), "cores": threads, "u8_GBps": V * stride / (min(pack_ms) * 1e-3) / 1e9,
+                          "what": "fm_pack_rows over the pinned u8 matrix + bitmap (AVX2, all host threads), outside the "
+                                  "timed region of `value` above; inside it for from_u8_pack_on_host"},
+               "from_u8_pack_on_host": {**r_u8pack, "h2d_bytes_per_step": h2d_packed,
+                                        "what": "fm_ingest_rows_pack: the caller holds the reference's u8 matrix + bitmap "
+                                                "(pinned); the library packs chunk i+1 on the host while chunk i uploads"},
+               "from_u8_over_pcie": None if r_u8 is None else
+               {**r_u8, "h2d_bytes_per_step": int(h_data.numel() + h_bitmap.numel() * 8 + V * 8),
+                "what": "round-1 path: fm_ingest_rows, the u8 matrix + bitmap cross PCIe and are repacked on the device"},
+               "pageable_host": pageable,
+               "tracks_identical_across_ingests": same,
+               "timing": "wall clock around synchronous C-ABI calls, cuda-synchronised on both sides, max over ranks"}
 
     # ---------------- CPU baseline (rank 0, N = 1 only)
     cpu = None
@@ -498,17 +637,30 @@ def run_ours(args):
                "sample": f"{n} of {V} sites x {S * 2} haplotypes, both groups (oracle port: threaded dense summary "
                          "+ serial per-site track loop, as in the reference)"}
 
+    extra = {}
+    if not args.skip_configs:
+        try:
+            import bench_configs
+            extra = bench_configs.run(L, _lib, args, rank, world, local, device, dist if world > 1 else None, peak)
+        except Exception as e:  # the headline line must still be printed
+            extra = {"configs_error": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
+        cl = clocks.summary()
+        cl["sampling"] = (f"{timed_samples} samples inside the {dev_ms:.1f} ms timed region, the rest during an untimed "
+                          "keep-alive loop of the same kernels right after it")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+                "warmup": warm, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8 -> 1-bit planes, popcount u32 + f64",
                 "data": "synthetic", "config": workload_config(args), "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": e2e, "gpu_launches": int(res.plane_launches + res.other_launches),
-                "clocks": clocks.summary(), "wall_ms_per_step": wall_ms / args.steps,
+                "parity": parity, "value_from_resident_u8": from_u8,
+                "clocks": cl, "wall_ms_per_step": wall_ms / args.steps,
                 "exchange_ms_per_step": res.comm_ms_avg if comm is not None else None,
                 "collective": None if world == 1 else "per step: fused fold + P2P mailbox exchange of region totals "
                                                       "(fm_k_comm_exchange over NVLink peer memory), inside the timed region",
                 "timing": "CUDA events on the launching stream (cudaStreamPerThread), max over ranks"}
+        line.update(extra)
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
@@ -527,8 +679,10 @@ def main():
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-pageable", action="store_true")
-    ap.add_argument("--skip-inband", action="store_true")
-    ap.add_argument("--free-device-copy", action="store_true", default=True)
+    ap.add_argument("--skip-u8", action="store_true", help="skip the round-1 u8-over-PCIe e2e variant")
+    ap.add_argument("--skip-parity", action="store_true")
+    ap.add_argument("--skip-from-u8", action="store_true")
+    ap.add_argument("--skip-configs", action="store_true", help="skip configs 1/3/4/5 and the strong-scaling block")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -41,13 +41,15 @@ class HudsonSums(C.Structure):
 class Timings(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("repack_ms", C.c_float), ("stats_ms", C.c_float),
                 ("reduce_ms", C.c_float), ("d2h_ms", C.c_float), ("stats_launches", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("stats_bytes", C.c_uint64)]
+                ("kernel_launches", C.c_uint64), ("stats_bytes", C.c_uint64), ("pack_ms", C.c_float)]
 
 
 class BenchResult(C.Structure):
     _fields_ = [("step_ms_avg", C.c_float), ("plane_ms_avg", C.c_float), ("plane_launches", C.c_uint64),
                 ("other_launches", C.c_uint64), ("plane_bytes_per_step", C.c_uint64),
-                ("group_ms_avg", C.c_float * 8), ("group_bytes", C.c_uint64 * 8), ("comm_ms_avg", C.c_float)]
+                ("group_ms_avg", C.c_float * 8), ("group_bytes", C.c_uint64 * 8), ("comm_ms_avg", C.c_float),
+                ("last_pi_sum", C.c_double * 8), ("last_seg", C.c_uint64 * 8), ("last_unc", C.c_uint64 * 8),
+                ("merged_pi_sum", C.c_double * 8), ("merged_seg", C.c_uint64 * 8), ("merged_unc", C.c_uint64 * 8)]
 
 
 class VcfInfo(C.Structure):
@@ -62,7 +64,8 @@ EXPORTS = [
     "fm_last_error", "fm_version", "fm_device_count", "fm_set_device", "fm_synchronize", "fm_trim_pool",
     "fm_matrix_create", "fm_matrix_create_inband", "fm_matrix_create_device", "fm_matrix_retain", "fm_matrix_release",
     "fm_matrix_info", "fm_ingest_begin", "fm_ingest_add_group", "fm_ingest_add_partition",
-    "fm_ingest_rows", "fm_ingest_finish", "fm_ingest_abort", "fm_group_create", "fm_groups_create", "fm_group_release", "fm_group_capacity", "fm_group_summary",
+    "fm_ingest_rows", "fm_ingest_finish", "fm_ingest_abort", "fm_packed_row_words", "fm_ingest_rows_packed",
+    "fm_matrix_create_packed", "fm_pack_rows", "fm_pack_rows_generic", "fm_ingest_rows_pack", "fm_group_create", "fm_groups_create", "fm_group_release", "fm_group_capacity", "fm_group_summary",
     "fm_group_segregating_sites", "fm_group_pi", "fm_harmonic", "fm_watterson_theta",
     "fm_per_site_diversity", "fm_per_site_diversity_multi", "fm_hudson_pair", "fm_hudson_dxy", "fm_partition_create",
     "fm_partition_release", "fm_wc_fst", "fm_wc_window_sums", "fm_fst_estimate_from_sums", "fm_adjusted_sequence_length", "fm_group_window_sums",
@@ -107,6 +110,12 @@ def lib() -> C.CDLL:
     L.fm_ingest_add_group.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
     L.fm_ingest_add_partition.argtypes = [vp, vp, vp, sz, sz, C.POINTER(sz)]
     L.fm_ingest_rows.argtypes = [vp, vp, vp, sz, sz]
+    L.fm_packed_row_words.argtypes = [sz, sz, C.POINTER(sz)]
+    L.fm_ingest_rows_packed.argtypes = [vp, vp, vp, sz, sz]
+    L.fm_ingest_rows_pack.argtypes = [vp, vp, vp, sz, sz, C.c_int]
+    L.fm_matrix_create_packed.argtypes = [vp, vp, sz, sz, sz, vp, C.POINTER(vp)]
+    L.fm_pack_rows.argtypes = [vp, vp, C.c_int, sz, sz, sz, sz, vp, vp, C.c_int]
+    L.fm_pack_rows_generic.argtypes = [vp, vp, C.c_int, sz, sz, sz, sz, vp, vp]
     L.fm_ingest_finish.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.fm_ingest_abort.argtypes = [vp]
     L.fm_group_create.argtypes = [vp, vp, vp, sz, C.POINTER(vp)]

@@ -8,6 +8,7 @@ would take (dense summary / dense / sparse)."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
@@ -139,10 +140,41 @@ def _pack_bits(mask_flat: np.ndarray) -> np.ndarray:
     return np.packbits(padded.reshape(words, 64), axis=1, bitorder="little").view(np.uint64).reshape(-1)
 
 
+def _ingest_mode(max_allele: int) -> str:
+    """How a host matrix reaches the device: "packed" (2 bits per genotype: the library's multi-threaded
+    packer fm_pack_rows + fm_matrix_create_packed, biallelic matrices) or "u8" (the reference layout as it
+    is, repacked on the device).  FERROMIC_GPU_INGEST overrides the default ("packed" when possible)."""
+    mode = os.environ.get("FERROMIC_GPU_INGEST", "packed")
+    if mode not in ("packed", "u8"):
+        raise ValueError("FERROMIC_GPU_INGEST must be 'packed' or 'u8'")
+    return mode if max_allele <= 1 else "u8"
+
+
+def pack_rows(alleles2d: np.ndarray, missing_mode: int, bitmap: Optional[np.ndarray] = None, first_row: int = 0,
+              n_total_rows: Optional[int] = None, threads: int = 0, generic: bool = False):
+    """fm_pack_rows over a [rows, stride] u8 block -> (allele_bits, called_bits or None), each
+    [rows, ceil(stride / 32)] u32 (the 2-bit ingest format)."""
+    a = np.ascontiguousarray(alleles2d).view(np.uint8)
+    assert a.ndim == 2
+    rows, stride = a.shape
+    rw = (stride + 31) // 32
+    ab = np.zeros((rows, rw), dtype=np.uint32)
+    cb = np.zeros((rows, rw), dtype=np.uint32) if missing_mode != 0 else None
+    total = rows + first_row if n_total_rows is None else n_total_rows
+    L = lib()
+    if generic:
+        check(L.fm_pack_rows_generic(_ptr(a), _ptr(bitmap), missing_mode, first_row, rows, total, stride, _ptr(ab),
+                                     _ptr(cb)))
+    else:
+        check(L.fm_pack_rows(_ptr(a), _ptr(bitmap), missing_mode, first_row, rows, total, stride, _ptr(ab), _ptr(cb),
+                             threads))
+    return ab, cb
+
+
 # --------------------------------------------------------------------------- device handles
 class _Matrix:
     def __init__(self, alleles: np.ndarray, missing_mask: Optional[np.ndarray], positions: np.ndarray,
-                 max_allele: Optional[int] = None, always_bitmap: bool = False):
+                 max_allele: Optional[int] = None, always_bitmap: bool = False, ingest: Optional[str] = None):
         a = np.ascontiguousarray(alleles, dtype=np.uint8)
         assert a.ndim == 3
         self.V, self.S, self.P = a.shape
@@ -153,13 +185,21 @@ class _Matrix:
         self.max_allele = int(a.max()) if (max_allele is None and a.size) else int(max_allele or 0)
         pos = np.ascontiguousarray(positions, dtype=np.int64)
         h = C.c_void_p()
-        check(lib().fm_matrix_create(_ptr(a), _ptr(bits), self.V, self.S, self.P, self.max_allele, _ptr(pos),
-                                     C.byref(h)))
+        self.ingest_mode = ingest or _ingest_mode(self.max_allele)
+        if self.ingest_mode == "packed":
+            # convert_numeric_array / from_variants seam (lib.rs:1135-1227, stats.rs:339-500): the host packs
+            # bit words (several threads) and only 0.25 B per genotype cross PCIe
+            ab, cb = pack_rows(a.reshape(self.V, self.S * self.P), 1 if bits is not None else 0, bits)
+            check(lib().fm_matrix_create_packed(_ptr(ab), _ptr(cb), self.V, self.S, self.P, _ptr(pos), C.byref(h)))
+        else:
+            check(lib().fm_matrix_create(_ptr(a), _ptr(bits), self.V, self.S, self.P, self.max_allele, _ptr(pos),
+                                         C.byref(h)))
         self.handle = h
         self._groups: Dict[tuple, "_Group"] = {}
 
     @classmethod
-    def from_int8(cls, genotypes: np.ndarray, positions: np.ndarray, max_allele: int) -> "_Matrix":
+    def from_int8(cls, genotypes: np.ndarray, positions: np.ndarray, max_allele: int,
+                  ingest: Optional[str] = None) -> "_Matrix":
         """Dense matrix straight from the caller's int8 array (negative = missing): the buffer is
         uploaded as it is and missingness stays in band (fm_matrix_create_inband) -- no host-side
         conversion pass, no bitmap packing (lib.rs:1135-1227 does both serially)."""
@@ -171,8 +211,13 @@ class _Matrix:
         self.max_allele = int(max_allele)
         pos = np.ascontiguousarray(positions, dtype=np.int64)
         h = C.c_void_p()
-        check(lib().fm_matrix_create_inband(g.ctypes.data, self.V, self.S, self.P, self.max_allele, _ptr(pos),
-                                            C.byref(h)))
+        self.ingest_mode = ingest or _ingest_mode(self.max_allele)
+        if self.ingest_mode == "packed":  # packed straight from the int8 cells: sign bit = missing
+            ab, cb = pack_rows(g.reshape(self.V, self.S * self.P), 2)
+            check(lib().fm_matrix_create_packed(_ptr(ab), _ptr(cb), self.V, self.S, self.P, _ptr(pos), C.byref(h)))
+        else:
+            check(lib().fm_matrix_create_inband(g.ctypes.data, self.V, self.S, self.P, self.max_allele, _ptr(pos),
+                                                C.byref(h)))
         self.handle = h
         self._groups = {}
         return self
@@ -180,7 +225,7 @@ class _Matrix:
     @classmethod
     def ingest(cls, alleles: np.ndarray, missing_mask: Optional[np.ndarray], positions: np.ndarray,
                group_haplotypes: Sequence[Sequence[Tuple[int, int]]], partitions=(), chunk_rows: int = 0,
-               calls: int = 1, always_bitmap: bool = False) -> "_Matrix":
+               calls: int = 1, always_bitmap: bool = False, packed: bool = False) -> "_Matrix":
         """Streaming ingestion (fm_ingest_*): the u8 rows are uploaded in chunks and repacked into
         the declared groups' bitplanes while the next chunk is in flight; the u8 matrix is never
         resident.  partitions: (left, right, n_groups) triples; their handles land in
@@ -214,7 +259,13 @@ class _Matrix:
             flat = a.reshape(self.V, -1)
             cuts = np.linspace(0, self.V, max(1, calls) + 1).astype(int)
             for r0, r1 in zip(cuts[:-1], cuts[1:]):
-                if r1 > r0:
+                if r1 <= r0:
+                    continue
+                if packed:  # fm_pack_rows on the host, 2 bits per genotype over PCIe (fm_ingest_rows_packed)
+                    ab, cb = pack_rows(flat[r0:r1], 1 if bits is not None else 0, bits, first_row=int(r0),
+                                       n_total_rows=self.V)
+                    check(L.fm_ingest_rows_packed(ih, _ptr(ab), _ptr(cb), int(r0), int(r1 - r0)))
+                else:
                     check(L.fm_ingest_rows(ih, flat[r0:r1].ctypes.data, _ptr(bits), int(r0), int(r1 - r0)))
             mh = C.c_void_p()
             gh = (C.c_void_p * max(1, len(group_haplotypes)))()

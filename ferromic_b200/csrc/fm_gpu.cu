@@ -27,6 +27,14 @@
 #include <unordered_map>
 #include <vector>
 
+// fm_host_pack.cpp (plain host code): u8 rows -> packed bit words
+const char *fm_host_pack_rows(const uint8_t *rows, const uint64_t *missing_whole_or_null, int missing_mode,
+                              size_t first_row, size_t n_rows, size_t n_total_rows, size_t stride,
+                              uint32_t *allele_bits, uint32_t *called_bits_or_null, int n_threads);
+const char *fm_host_pack_rows_generic(const uint8_t *rows, const uint64_t *missing, int mode, size_t first_row,
+                                      size_t n_rows, size_t n_total_rows, size_t stride, uint32_t *abits,
+                                      uint32_t *cbits);
+
 namespace {
 
 thread_local std::string t_err;
@@ -244,6 +252,33 @@ struct BouncePool {
 };
 BouncePool g_bounce;
 
+// Pinned host buffers for the pack-and-upload ingest (fm_ingest_rows_pack): cudaHostAlloc of tens of MB costs
+// milliseconds, so buffers are kept for the life of the process and handed from one ingest to the next.
+struct PinnedPool {
+    static constexpr size_t kBytes = (size_t)32 << 20;
+    std::mutex mu;
+    std::vector<uint8_t *> free_list;
+    uint8_t *take() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (!free_list.empty()) {
+                uint8_t *p = free_list.back();
+                free_list.pop_back();
+                return p;
+            }
+        }
+        uint8_t *p = nullptr;
+        CK(cudaHostAlloc((void **)&p, kBytes, cudaHostAllocDefault));
+        return p;
+    }
+    void give(uint8_t *p) {
+        if (!p) return;
+        std::lock_guard<std::mutex> lk(mu);
+        free_list.push_back(p);
+    }
+};
+PinnedPool g_pinned;
+
 bool host_is_pinned(const void *p) {
     cudaPointerAttributes at{};
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
@@ -352,6 +387,11 @@ struct fm_matrix {
     bool in_band = false;      // missingness is in band: cells >= 0x80 (negative int8) are missing, no bitmap
     bool streamed = false;     // u8 data was never resident: groups had to be declared before ingest
     bool owns = true;
+    // packed rows (2-bit ingest format, fm_ingest_rows_packed / fm_matrix_create_packed): full-row allele /
+    // called bit words stay resident (0.25 B per genotype), so groups can be created at any time
+    bool packed = false;
+    uint32_t *d_abits = nullptr, *d_cbits = nullptr;
+    uint32_t rw = 0;           // u32 words per packed row = ceil(stride / 32)
     size_t V = 0, S = 0, ploidy = 0, stride = 0;
     uint8_t max_allele = 0;
     std::vector<int64_t> pos;
@@ -1134,6 +1174,8 @@ fm_status fm_matrix_release(fm_matrix *m) {
             dev_free(m->d_data);
             dev_free(m->d_missing);
         }
+        dev_free(m->d_abits);
+        dev_free(m->d_cbits);
         dev_free(m->d_pos);
         delete m;
     }
@@ -1155,15 +1197,17 @@ fm_status fm_matrix_info(const fm_matrix *m, size_t *V, size_t *S, size_t *ploid
 // Allocate a group's bitplanes and lookup tables for the columns listed in `off` (sorted, unique).
 // Can a warp stage one u8 row (+ its bitmap slice) in shared memory?  (row-staged K1 v2)
 static size_t repack_warp_smem(const fm_matrix *m, uint32_t *row_buf_out, uint32_t *bit_buf_out) {
-    const size_t row_buf = ((m->stride + 15) & ~(size_t)15) + 32;
-    const size_t bit_buf = (m->has_missing && !m->in_band) ? ((m->stride + 63) / 64 + 2) * 8 : 0;
+    // packed rows arrive as bit words: neither the u8 row nor the bitmap slice is staged
+    const size_t row_buf = m->packed ? 0 : ((m->stride + 15) & ~(size_t)15) + 32;
+    const size_t bit_buf = (!m->packed && m->has_missing && !m->in_band) ? ((m->stride + 63) / 64 + 2) * 8 : 0;
     // full-row allele / called bit words + one group's two plane rows while they are assembled
     const size_t cnt_buf = 2 * ((m->stride + 31) / 32 + 1) * 4 + 2 * ((m->stride + 127) / 128) * 4 * 4;
     if (row_buf_out) *row_buf_out = (uint32_t)row_buf;
     if (bit_buf_out) *bit_buf_out = (uint32_t)bit_buf;
     return (row_buf + bit_buf + cnt_buf + 15) & ~(size_t)15;
 }
-static bool row_fits_smem(const fm_matrix *m) { return repack_warp_smem(m, nullptr, nullptr) <= 24 * 1024; }
+static size_t repack_smem_limit(const fm_matrix *m) { return m->packed ? 100 * 1024 : 24 * 1024; }
+static bool row_fits_smem(const fm_matrix *m) { return repack_warp_smem(m, nullptr, nullptr) <= repack_smem_limit(m); }
 
 static fm_group *alloc_group(fm_matrix *m, std::vector<uint32_t> &&off, bool count_only = false) {
     uint32_t n_bits = 1;
@@ -1257,7 +1301,7 @@ struct RepackSet {  // device-resident descriptor tables of the groups one launc
                                             std::max<size_t>(m->V, 1) * g->wq * 4, nullptr, nullptr, nullptr, 0});
                 plan_at.push_back(plan.size() / 8);
                 size_t ne = 0;
-                if (g->n_bits == 1 && staged && !no_plan) {
+                if (g->n_bits == 1 && ((staged && !no_plan) || m->packed)) {
                     uint32_t pos = 0;
                     for (size_t k = 0; k < g->off.size(); ++ne) {  // offsets are sorted: one entry per row word
                         const uint32_t w = g->off[k] >> 5;
@@ -1282,11 +1326,12 @@ struct RepackSet {  // device-resident descriptor tables of the groups one launc
                 plan_len.push_back(ne);
             }
         }
+        if (m->packed && plan.empty() && !h.empty()) plan.resize(8, 0u);  // empty groups still take the plan path
         if (!plan.empty()) {
             d_plan = static_cast<uint4 *>(dev_alloc(plan.size() * 4));
             CK(cudaMemcpyAsync(d_plan, plan.data(), plan.size() * 4, cudaMemcpyHostToDevice, stream()));
             for (size_t i = 0; i < h.size(); ++i)
-                if (plan_len[i]) {
+                if (plan_len[i] || (m->packed && h[i].n_bits == 1)) {
                     h[i].plan = d_plan + 2 * plan_at[i];
                     h[i].n_ent = (uint32_t)plan_len[i];
                 }
@@ -1345,6 +1390,31 @@ static void launch_repack(const RepackSet &set, const uint8_t *data, size_t data
     uint32_t row_buf = 0, bit_buf = 0;
     uint32_t warp_smem = (uint32_t)repack_warp_smem(m, &row_buf, &bit_buf);
     static const uint32_t force_v1 = env_u32("FM_REPACK_V1", 0);
+    if (m->packed) {  // K1p: groups from the resident packed rows (data / missing are unused)
+        if (warp_smem > repack_smem_limit(m))
+            fail(FM_ERR_UNSUPPORTED, "packed rows wider than the repack kernel's shared-memory slice");
+        for (const fm_group *g : set.plane_gs)
+            if (g->n_bits != 1 || !set.d_plan) fail(FM_ERR_INVALID_ARG, "internal: packed rows need compress plans");
+        (void)row_buf;
+        (void)bit_buf;
+        const uint32_t warps = std::max(1u, std::min(8u, (200u * 1024u) / warp_smem));
+        const size_t smem = (size_t)warps * warp_smem;
+        static std::once_flag attr_once_p;
+        std::call_once(attr_once_p, [] {
+            cudaFuncSetAttribute(fm::fm_k_repack_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        });
+        const uint32_t rows = v_hi - v_lo;
+        const uint32_t per_sm = std::max(1u, std::min(8u, (uint32_t)((220u * 1024u) / smem)));
+        const uint32_t blocks = std::max(1u, std::min<uint32_t>((rows + warps - 1) / warps,
+                                                                per_sm * (uint32_t)sm_count(m->device)));
+        const fm::PackedRows pk{m->d_abits, m->d_cbits, m->rw};
+        fm::fm_k_repack_rows<<<blocks, warps * 32, smem, st>>>(nullptr, 0, nullptr, m->stride, 0, 0, v_lo, v_hi,
+                                                               set.d_desc, (uint32_t)set.plane_gs.size(), warp_smem, 0, 0,
+                                                               set.ct, 0u, 1u, 0u, pk);
+        CK(cudaGetLastError());
+        g_launches++;
+        return;
+    }
     if (warp_smem <= 24 * 1024 && (!force_v1 || set.ct.n_groups)) {
         // direct mode: nothing reads the raw bytes of the row after the full-row bit words are built
         static const uint32_t no_direct = env_u32("FM_REPACK_STAGED", 0);
@@ -1369,7 +1439,8 @@ static void launch_repack(const RepackSet &set, const uint8_t *data, size_t data
         fm::fm_k_repack_rows<<<blocks, warps * 32, smem, st>>>(data, data_bytes, missing, m->stride, v_base, word_base,
                                                                v_lo, v_hi, set.d_desc, (uint32_t)set.plane_gs.size(),
                                                                warp_smem, row_buf, bit_buf, set.ct, m->in_band ? 1u : 0u,
-                                                               set.need_row_bits ? 1u : 0u, direct ? 1u : 0u);
+                                                               set.need_row_bits ? 1u : 0u, direct ? 1u : 0u,
+                                                               fm::PackedRows{nullptr, nullptr, 0});
         CK(cudaGetLastError());
         g_launches++;
         return;
@@ -1411,7 +1482,7 @@ static void repack_resident(fm_matrix *m, const std::vector<fm_group *> &gs) {
 
 // Repack the resident matrix columns listed in `off` into a new group's bitplanes.
 static fm_group *make_group(fm_matrix *m, std::vector<uint32_t> &&off) {
-    if (m->streamed)
+    if (m->streamed && !m->packed)
         fail(FM_ERR_UNSUPPORTED,
              "this matrix was ingested in streaming mode (its u8 rows are not resident): declare groups "
              "with fm_ingest_add_group / fm_ingest_add_partition before fm_ingest_rows");
@@ -1491,7 +1562,7 @@ fm_status fm_groups_create(fm_matrix *m, const uint64_t *sample_idx, const uint8
         for (size_t g = 0; g < n_groups; ++g) out[g] = nullptr;
         if (n_groups && !group_sizes) fail(FM_ERR_INVALID_ARG, "group_sizes is NULL");
         require_device();
-        if (m->streamed)
+        if (m->streamed && !m->packed)
             fail(FM_ERR_UNSUPPORTED, "this matrix was ingested in streaming mode: declare groups with fm_ingest_add_group");
         std::vector<fm_group *> gs;
         try {
@@ -1777,6 +1848,10 @@ struct fm_ingest {
     bool timing_started = false;
     RepackSet set;                        // descriptor table of `all`, built at the first fm_ingest_rows
     int next = 0;
+    uint8_t *pin[2] = {nullptr, nullptr};  // fm_ingest_rows_pack: pinned staging of packed chunks
+    cudaEvent_t pin_free[2] = {nullptr, nullptr};
+    bool pin_used[2] = {false, false};
+    float pack_ms = 0.f;                   // host time spent in the packer (fm_ingest_rows_pack)
 };
 
 static void ingest_destroy(fm_ingest *h, bool release_handles) {
@@ -1791,8 +1866,9 @@ static void ingest_destroy(fm_ingest *h, bool release_handles) {
         if (h->copied[i]) cudaEventDestroy(h->copied[i]);
         if (h->consumed[i]) cudaEventDestroy(h->consumed[i]);
     }
-    for (cudaEvent_t e : {h->t_copy0, h->t_copy1, h->t_comp0, h->t_comp1})
+    for (cudaEvent_t e : {h->t_copy0, h->t_copy1, h->t_comp0, h->t_comp1, h->pin_free[0], h->pin_free[1]})
         if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) g_pinned.give(h->pin[i]);  // the copy stream was synchronised above
     if (h->copy_s) cudaStreamDestroy(h->copy_s);
     if (h->comp_s) cudaStreamDestroy(h->comp_s);
     if (release_handles) {
@@ -1825,9 +1901,7 @@ fm_status fm_ingest_begin(size_t V, size_t S, size_t ploidy, int has_missing, ui
             chunk_rows = std::min(std::max<size_t>(chunk_rows, 1), std::max<size_t>(V, 1));
             h->chunk_rows = chunk_rows;
             h->stage_words = (chunk_rows * stride + 63) / 64 + 2;
-            for (int i = 0; i < 2; ++i) {
-                h->stage[i] = static_cast<uint8_t *>(dev_alloc(chunk_rows * stride));
-                if (has_missing == FM_MISSING_BITMAP) h->stage_m[i] = static_cast<uint64_t *>(dev_alloc(h->stage_words * 8));
+            for (int i = 0; i < 2; ++i) {  // the u8 staging buffers are allocated by the first fm_ingest_rows
                 CK(cudaEventCreateWithFlags(&h->copied[i], cudaEventDisableTiming));
                 CK(cudaEventCreateWithFlags(&h->consumed[i], cudaEventDisableTiming));
             }
@@ -1892,8 +1966,16 @@ fm_status fm_ingest_rows(fm_ingest *h, const uint8_t *rows, const uint64_t *miss
         if (n_rows && m->stride && !rows) fail(FM_ERR_INVALID_ARG, "rows is NULL");
         const bool bitmap = m->has_missing && !m->in_band;
         if (bitmap && !missing_whole) fail(FM_ERR_INVALID_ARG, "matrix was declared with a missing bitmap");
+        if (m->packed) fail(FM_ERR_INVALID_ARG, "this ingest already received packed rows (fm_ingest_rows_packed)");
         set_dev(m);
         const size_t stride = m->stride;
+        if (!h->stage[0]) {
+            for (int i = 0; i < 2; ++i) {
+                h->stage[i] = static_cast<uint8_t *>(dev_alloc(std::max<size_t>(h->chunk_rows * std::max<size_t>(stride, 1), 16)));
+                if (bitmap) h->stage_m[i] = static_cast<uint64_t *>(dev_alloc(h->stage_words * 8));
+            }
+            CK(cudaStreamSynchronize(stream()));  // staging buffers are now usable from any stream
+        }
         if (!h->set.d_desc && !h->all.empty()) h->set.build(h->all);  // groups are final from here on
         if (!h->timing_started && n_rows) {
             CK(cudaEventRecord(h->t_copy0, h->copy_s));
@@ -1927,6 +2009,184 @@ fm_status fm_ingest_rows(fm_ingest *h, const uint8_t *rows, const uint64_t *miss
     });
 }
 
+// Packed rows (2 bits per genotype): the host hands over the full-row bit words a parser or the
+// library's own packer (fm_pack_rows) produced.  They are copied straight into the resident packed matrix --
+// no staging, no u8 on PCIe -- and every declared group is compressed out of them chunk by chunk (K1p) while
+// the next chunk is on the bus.
+static void ensure_packed_storage(fm_matrix *m, bool with_called) {
+    if (m->max_allele > 1)
+        fail(FM_ERR_UNSUPPORTED, "packed rows carry one allele bit per cell: max_allele must be <= 1 (use the u8 ingest)");
+    if (m->d_abits) return;
+    m->rw = (uint32_t)((m->stride + 31) / 32);
+    const size_t words = std::max<size_t>(m->V * (size_t)m->rw, 4);
+    m->d_abits = static_cast<uint32_t *>(dev_alloc(words * 4));
+    if (with_called) m->d_cbits = static_cast<uint32_t *>(dev_alloc(words * 4));
+    m->packed = true;
+}
+
+fm_status fm_packed_row_words(size_t n_samples, size_t ploidy, size_t *row_words) {
+    if (!row_words) return FM_ERR_INVALID_ARG;
+    *row_words = (n_samples * ploidy + 31) / 32;
+    return FM_OK;
+}
+
+fm_status fm_pack_rows(const uint8_t *rows, const uint64_t *missing_whole, int missing_mode, size_t first_row,
+                       size_t n_rows, size_t n_total_rows, size_t stride, uint32_t *allele_bits, uint32_t *called_bits,
+                       int n_threads) {
+    return guarded([&] {  // host only: works without a CUDA device
+        const char *err = fm_host_pack_rows(rows, missing_whole, missing_mode, first_row, n_rows, n_total_rows, stride,
+                                            allele_bits, called_bits, n_threads);
+        if (err) fail(FM_ERR_INVALID_ARG, err);
+    });
+}
+
+fm_status fm_pack_rows_generic(const uint8_t *rows, const uint64_t *missing_whole, int missing_mode, size_t first_row,
+                               size_t n_rows, size_t n_total_rows, size_t stride, uint32_t *allele_bits,
+                               uint32_t *called_bits) {
+    return guarded([&] {
+        const char *err = fm_host_pack_rows_generic(rows, missing_whole, missing_mode, first_row, n_rows, n_total_rows,
+                                                    stride, allele_bits, called_bits);
+        if (err) fail(FM_ERR_INVALID_ARG, err);
+    });
+}
+
+fm_status fm_ingest_rows_packed(fm_ingest *h, const uint32_t *allele_bits, const uint32_t *called_bits,
+                                size_t first_row, size_t n_rows) {
+    return guarded([&] {
+        if (!h) fail(FM_ERR_INVALID_ARG, "ingest handle is NULL");
+        fm_matrix *m = h->m;
+        if (first_row > m->V || n_rows > m->V - first_row) fail(FM_ERR_INVALID_ARG, "row range outside the matrix");
+        if (h->stage[0]) fail(FM_ERR_INVALID_ARG, "this ingest already received u8 rows (fm_ingest_rows)");
+        if (m->in_band) fail(FM_ERR_INVALID_ARG, "packed rows carry their own called bits: begin with FM_MISSING_BITMAP or _NONE");
+        if (n_rows && m->stride && !allele_bits) fail(FM_ERR_INVALID_ARG, "allele_bits is NULL");
+        if (m->has_missing && n_rows && m->stride && !called_bits)
+            fail(FM_ERR_INVALID_ARG, "matrix was declared with missing data: called_bits is required");
+        if (!m->has_missing && called_bits)
+            fail(FM_ERR_INVALID_ARG, "matrix was declared without missing data: called_bits must be NULL");
+        set_dev(m);
+        const bool first_call = !m->d_abits;
+        ensure_packed_storage(m, m->has_missing);
+        if (first_call) CK(cudaStreamSynchronize(stream()));  // storage (and a cached block's previous owner) is settled
+        if (!h->set.d_desc && !h->all.empty()) h->set.build(h->all);  // groups are final from here on
+        if (!h->timing_started && n_rows) {
+            CK(cudaEventRecord(h->t_copy0, h->copy_s));
+            CK(cudaEventRecord(h->t_comp0, h->comp_s));
+            h->timing_started = true;
+        }
+        const size_t rw = m->rw;
+        // chunk = ~32 MB of bit words: small enough that the last chunk's compress pass is short
+        const size_t per_row = std::max<size_t>(rw * 4 * (m->has_missing ? 2 : 1), 1);
+        const size_t chunk = std::max<size_t>(32, ((size_t)32 << 20) / per_row);
+        for (size_t r0 = first_row; r0 < first_row + n_rows; r0 += chunk) {
+            const size_t r1 = std::min(first_row + n_rows, r0 + chunk);
+            if (rw) {
+                h2d(m->d_abits + r0 * rw, allele_bits + (r0 - first_row) * rw, (r1 - r0) * rw * 4, h->copy_s);
+                if (m->has_missing)
+                    h2d(m->d_cbits + r0 * rw, called_bits + (r0 - first_row) * rw, (r1 - r0) * rw * 4, h->copy_s);
+            }
+            const int b = h->next;
+            h->next ^= 1;
+            CK(cudaEventRecord(h->copied[b], h->copy_s));
+            CK(cudaStreamWaitEvent(h->comp_s, h->copied[b], 0));
+            launch_repack(h->set, nullptr, 0, nullptr, 0, 0, (uint32_t)r0, (uint32_t)r1, h->comp_s);
+        }
+        h->rows_done += n_rows;
+        CK(cudaEventRecord(h->t_copy1, h->copy_s));
+        CK(cudaEventRecord(h->t_comp1, h->comp_s));
+        CK(cudaStreamSynchronize(h->copy_s));  // the caller's buffers are free again on return
+    });
+}
+
+// u8 rows in, 2 bits per genotype over PCIe: the library packs chunk i+1 on the host (fm_pack_rows, several
+// threads, reading the caller's buffer where it lies -- pageable memory needs no bounce copy) while the DMA of
+// chunk i and the compress pass of chunk i-1 run.  Same arguments and semantics as fm_ingest_rows.
+fm_status fm_ingest_rows_pack(fm_ingest *h, const uint8_t *rows, const uint64_t *missing_whole, size_t first_row,
+                              size_t n_rows, int n_threads) {
+    return guarded([&] {
+        if (!h) fail(FM_ERR_INVALID_ARG, "ingest handle is NULL");
+        fm_matrix *m = h->m;
+        if (first_row > m->V || n_rows > m->V - first_row) fail(FM_ERR_INVALID_ARG, "row range outside the matrix");
+        if (h->stage[0]) fail(FM_ERR_INVALID_ARG, "this ingest already received u8 rows (fm_ingest_rows)");
+        if (n_rows && m->stride && !rows) fail(FM_ERR_INVALID_ARG, "rows is NULL");
+        const int mode = m->in_band ? FM_MISSING_IN_BAND : (m->has_missing ? FM_MISSING_BITMAP : FM_MISSING_NONE);
+        if (mode == FM_MISSING_BITMAP && !missing_whole) fail(FM_ERR_INVALID_ARG, "matrix was declared with a missing bitmap");
+        set_dev(m);
+        const bool first_call = !m->d_abits;
+        ensure_packed_storage(m, m->has_missing);
+        if (first_call) CK(cudaStreamSynchronize(stream()));
+        if (!h->set.d_desc && !h->all.empty()) h->set.build(h->all);
+        if (!h->timing_started && n_rows) {
+            CK(cudaEventRecord(h->t_copy0, h->copy_s));
+            CK(cudaEventRecord(h->t_comp0, h->comp_s));
+            h->timing_started = true;
+        }
+        const size_t rw = m->rw, stride = m->stride;
+        if (!rw) {
+            h->rows_done += n_rows;
+            return;
+        }
+        const size_t planes = m->has_missing ? 2 : 1;
+        const size_t chunk = std::max<size_t>(1, PinnedPool::kBytes / (rw * 4 * planes));
+        for (int i = 0; i < 2; ++i)
+            if (!h->pin[i]) {
+                h->pin[i] = g_pinned.take();
+                CK(cudaEventCreateWithFlags(&h->pin_free[i], cudaEventDisableTiming));
+            }
+        int b = 0;
+        for (size_t r0 = first_row; r0 < first_row + n_rows; r0 += chunk, b ^= 1) {
+            const size_t r1 = std::min(first_row + n_rows, r0 + chunk), nr = r1 - r0;
+            if (h->pin_used[b]) CK(cudaEventSynchronize(h->pin_free[b]));  // its previous DMA has drained
+            uint32_t *pa = reinterpret_cast<uint32_t *>(h->pin[b]);
+            uint32_t *pc = m->has_missing ? pa + nr * rw : nullptr;
+            const auto t0 = std::chrono::steady_clock::now();
+            const char *err = fm_host_pack_rows(rows + (r0 - first_row) * stride, missing_whole, mode, r0, nr, m->V, stride,
+                                                pa, pc, n_threads);
+            if (err) fail(FM_ERR_INVALID_ARG, err);
+            h->pack_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            CK(cudaMemcpyAsync(m->d_abits + r0 * rw, pa, nr * rw * 4, cudaMemcpyHostToDevice, h->copy_s));
+            if (pc) CK(cudaMemcpyAsync(m->d_cbits + r0 * rw, pc, nr * rw * 4, cudaMemcpyHostToDevice, h->copy_s));
+            CK(cudaEventRecord(h->pin_free[b], h->copy_s));
+            h->pin_used[b] = true;
+            CK(cudaStreamWaitEvent(h->comp_s, h->pin_free[b], 0));
+            launch_repack(h->set, nullptr, 0, nullptr, 0, 0, (uint32_t)r0, (uint32_t)r1, h->comp_s);
+        }
+        h->rows_done += n_rows;
+        CK(cudaEventRecord(h->t_copy1, h->copy_s));
+        CK(cudaEventRecord(h->t_comp1, h->comp_s));
+        CK(cudaStreamSynchronize(h->copy_s));
+    });
+}
+
+fm_status fm_matrix_create_packed(const uint32_t *allele_bits, const uint32_t *called_bits, size_t V, size_t S,
+                                  size_t ploidy, const int64_t *positions, fm_matrix **out) {
+    return guarded([&] {
+        if (!out) fail(FM_ERR_INVALID_ARG, "out is NULL");
+        *out = nullptr;
+        require_device();
+        CK(cudaSetDevice(t_device));
+        fm_matrix *m = matrix_common(V, S, ploidy, 1, positions);
+        try {
+            m->has_missing = called_bits != nullptr;
+            m->streamed = true;  // no u8 rows: groups come from the packed rows
+            ensure_packed_storage(m, m->has_missing);
+            const size_t words = V * (size_t)m->rw;
+            if (words && !allele_bits) fail(FM_ERR_INVALID_ARG, "allele_bits is NULL");
+            Timer tm;
+            tm.start();
+            h2d(m->d_abits, allele_bits, words * 4, stream());
+            if (called_bits) h2d(m->d_cbits, called_bits, words * 4, stream());
+            m->d_pos = static_cast<int64_t *>(dev_alloc(std::max<size_t>(V, 1) * 8));
+            if (V) CK(cudaMemcpyAsync(m->d_pos, m->pos.data(), V * 8, cudaMemcpyHostToDevice, stream()));
+            tm.stop();
+            t_tim.h2d_ms += tm.ms();
+        } catch (...) {
+            fm_matrix_release(m);
+            throw;
+        }
+        *out = m;
+    });
+}
+
 fm_status fm_ingest_finish(fm_ingest *h, fm_matrix **matrix_out, fm_group **groups_out, fm_partition **parts_out) {
     return guarded([&] {
         if (!h) fail(FM_ERR_INVALID_ARG, "ingest handle is NULL");
@@ -1942,6 +2202,7 @@ fm_status fm_ingest_finish(fm_ingest *h, fm_matrix **matrix_out, fm_group **grou
             CK(cudaEventElapsedTime(&b, h->t_comp0, h->t_comp1));
             t_tim.h2d_ms += a;      // span of the copy stream
             t_tim.repack_ms += b;   // span of the repack stream (overlaps the copies)
+            t_tim.pack_ms += h->pack_ms;  // host packer (fm_ingest_rows_pack), overlaps both
         }
         for (fm_group *g : h->all)
             if (g->count_only) g->have_counts = true;
@@ -2181,7 +2442,7 @@ fm_status fm_partition_create(fm_matrix *m, const uint16_t *left, const uint16_t
         p->G = n_groups;
         fm_matrix_retain(m);
         try {
-            if (m->streamed)
+            if (m->streamed && !m->packed)
                 fail(FM_ERR_UNSUPPORTED,
                      "this matrix was ingested in streaming mode: declare partitions with fm_ingest_add_partition");
             std::vector<std::vector<uint32_t>> cols = partition_columns(m, left, right, n_samples, n_groups);
@@ -3820,6 +4081,36 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
         out->step_ms_avg = total / (float)iterations;
         out->plane_ms_avg = spans.empty() ? 0.f : plane / (float)spans.size();
         out->plane_bytes_per_step = bytes;
+        // region totals of the LAST timed step (parity check of the run: bench.py compares them with the public
+        // call and, for N > 1, the exchanged totals with a rank-ordered sum of every rank's local ones)
+        const int pl = (iterations - 1) & 1;
+        for (size_t i = 0; i < n_groups && i < 8; ++i) {
+            const fm::PassGeom &G = pg[i].P.geom;
+            if (!G.n_batches) continue;
+            const uint32_t s_lo = G.b_lo / fm::kSuperBatches;
+            const uint32_t n_super = (G.b_lo + G.n_batches + fm::kSuperBatches - 1) / fm::kSuperBatches - s_lo;
+            std::vector<double> hd(n_super);
+            std::vector<uint64_t> hu((size_t)n_super * 2);
+            pg[i].sd[pl].download(hd.data(), n_super);
+            pg[i].su[pl].download(hu.data(), (size_t)n_super * 2);
+            CK(cudaStreamSynchronize(stream()));
+            for (uint32_t sb = 0; sb < n_super; ++sb) {
+                out->last_pi_sum[i] += hd[sb];
+                out->last_seg[i] += hu[2 * (size_t)sb];
+                out->last_unc[i] += hu[2 * (size_t)sb + 1];
+            }
+        }
+        if (comm) {
+            unsigned long long w[24] = {};
+            const size_t nw = std::min<size_t>(n_groups, 8) * 3;
+            CK(cudaMemcpyAsync(w, comm->d_merged, nw * 8, cudaMemcpyDeviceToHost, stream()));
+            CK(cudaStreamSynchronize(stream()));
+            for (size_t i = 0; i < n_groups && i < 8; ++i) {
+                std::memcpy(&out->merged_pi_sum[i], &w[3 * i], 8);
+                out->merged_seg[i] = w[3 * i + 1];
+                out->merged_unc[i] = w[3 * i + 2];
+            }
+        }
     });
 }
 

@@ -1,0 +1,193 @@
+// fm_host_pack.cpp -- host side of the packed (2 bits per genotype) ingest format, SURVEY 8 f1.
+//
+// fm_pack_rows turns rows of the reference's dense matrix -- u8 allele indices plus either the
+// packed missing bitmap of DenseGenotypeMatrix (stats.rs:1298-1302), in-band missingness (the
+// negative cells of the int8 array Population.from_numpy receives, lib.rs:1168-1199) or no
+// missing data at all -- into full-row bit words: per row rw = ceil(stride / 32) u32 words of
+// allele bits (cell is called and non-zero) and rw words of called bits, bit c & 31 of word c >> 5
+// for cell c.  That is what fm_ingest_rows_packed / fm_matrix_create_packed take: 0.25 B per
+// genotype over PCIe instead of 1.125 B.  A caller that parses text (process.rs:2602-2660) can
+// write these words directly and never build the u8 matrix; fm_pack_rows is for callers that
+// already hold one (lib.rs:1135-1227).
+//
+// Plain host code: several threads over row ranges, AVX2 compare + movemask when the CPU has it
+// (32 cells per instruction), a 64-bit SWAR gather otherwise.  No CUDA calls.
+#include "../../include/ferromic_gpu.h"
+
+#include <algorithm>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#if defined(__x86_64__) || defined(__i386__)
+#include <immintrin.h>
+#define FM_X86 1
+#else
+#define FM_X86 0
+#endif
+
+namespace {
+
+// 8 cells -> 8 bits (bit i = cell i satisfies the predicate).  t has bit 7 of every byte set where
+// the predicate holds; the multiply gathers those bits into the top byte.
+inline uint32_t gather8(uint64_t t) { return (uint32_t)((((t >> 7) & 0x0101010101010101ull) * 0x0102040810204080ull) >> 56); }
+inline uint64_t nonzero_hi(uint64_t x) {  // bit 7 of every non-zero byte
+    return (((x & 0x7F7F7F7F7F7F7F7Full) + 0x7F7F7F7F7F7F7F7Full) | x) & 0x8080808080808080ull;
+}
+
+// 32 consecutive bits of the LSB-first bitmap starting at absolute bit index `bit`
+inline uint32_t bitmap_u32(const uint64_t *bm, uint64_t bit, uint64_t n_words_total) {
+    const uint64_t w = bit >> 6;
+    const uint32_t sh = (uint32_t)(bit & 63);
+    uint64_t lo = bm[w] >> sh;
+    if (sh > 32 && w + 1 < n_words_total) lo |= bm[w + 1] << (64 - sh);
+    return (uint32_t)lo;
+}
+
+void pack_range_generic(const uint8_t *rows, const uint64_t *missing, uint64_t n_bitmap_words, int mode,
+                        size_t first_row, size_t r_lo, size_t r_hi, size_t stride, uint32_t *abits,
+                        uint32_t *cbits) {
+    const size_t rw = (stride + 31) / 32;
+    for (size_t r = r_lo; r < r_hi; ++r) {
+        const uint8_t *src = rows + r * stride;
+        uint32_t *a = abits + r * rw;
+        uint32_t *c = cbits ? cbits + r * rw : nullptr;
+        const uint64_t bit0 = (uint64_t)(first_row + r) * stride;
+        for (size_t w = 0; w < rw; ++w) {
+            const size_t c0 = w * 32;
+            const size_t n = std::min<size_t>(32, stride - c0);
+            uint32_t nz = 0, neg = 0;
+            size_t i = 0;
+            for (; i + 8 <= n; i += 8) {
+                uint64_t x;
+                std::memcpy(&x, src + c0 + i, 8);
+                nz |= gather8(nonzero_hi(x)) << i;
+                neg |= gather8(x & 0x8080808080808080ull) << i;
+            }
+            for (; i < n; ++i) {
+                const uint8_t b = src[c0 + i];
+                nz |= (uint32_t)(b != 0) << i;
+                neg |= (uint32_t)(b >> 7) << i;
+            }
+            const uint32_t valid = n == 32 ? 0xffffffffu : ((1u << n) - 1u);
+            uint32_t called = valid;
+            if (mode == FM_MISSING_BITMAP)
+                called = ~bitmap_u32(missing, bit0 + c0, n_bitmap_words) & valid;
+            else if (mode == FM_MISSING_IN_BAND)
+                called = ~neg & valid;
+            a[w] = nz & called;
+            if (c) c[w] = called;
+        }
+    }
+}
+
+#if FM_X86
+__attribute__((target("avx2"))) void pack_range_avx2(const uint8_t *rows, const uint64_t *missing,
+                                                     uint64_t n_bitmap_words, int mode, size_t first_row, size_t r_lo,
+                                                     size_t r_hi, size_t stride, uint32_t *abits, uint32_t *cbits) {
+    const size_t rw = (stride + 31) / 32;
+    const size_t full = stride / 32;
+    const __m256i zero = _mm256_setzero_si256();
+    for (size_t r = r_lo; r < r_hi; ++r) {
+        const uint8_t *src = rows + r * stride;
+        uint32_t *a = abits + r * rw;
+        uint32_t *c = cbits ? cbits + r * rw : nullptr;
+        const uint64_t bit0 = (uint64_t)(first_row + r) * stride;
+        for (size_t w = 0; w < full; ++w) {
+            const __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + w * 32));
+            const uint32_t nz = ~(uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(x, zero));
+            uint32_t called = 0xffffffffu;
+            if (mode == FM_MISSING_BITMAP)
+                called = ~bitmap_u32(missing, bit0 + w * 32, n_bitmap_words);
+            else if (mode == FM_MISSING_IN_BAND)
+                called = ~(uint32_t)_mm256_movemask_epi8(x);  // sign bit = negative int8 = missing
+            a[w] = nz & called;
+            if (c) c[w] = called;
+        }
+    }
+    if (full < rw)  // the partial last word of every row
+        for (size_t r = r_lo; r < r_hi; ++r) {
+            const size_t c0 = full * 32, n = stride - c0;
+            const uint8_t *src = rows + r * stride + c0;
+            uint32_t nz = 0, neg = 0;
+            for (size_t i = 0; i < n; ++i) {
+                nz |= (uint32_t)(src[i] != 0) << i;
+                neg |= (uint32_t)(src[i] >> 7) << i;
+            }
+            const uint32_t valid = (1u << n) - 1u;
+            uint32_t called = valid;
+            if (mode == FM_MISSING_BITMAP)
+                called = ~bitmap_u32(missing, (uint64_t)(first_row + r) * stride + c0, n_bitmap_words) & valid;
+            else if (mode == FM_MISSING_IN_BAND)
+                called = ~neg & valid;
+            abits[r * rw + full] = nz & called;
+            if (cbits) cbits[r * rw + full] = called;
+        }
+}
+#endif
+
+}  // namespace
+
+// Returns nullptr on success or a static message for FM_ERR_INVALID_ARG (the C-ABI wrapper fm_pack_rows lives in
+// fm_gpu.cu so that fm_last_error() covers it).
+const char *fm_host_pack_rows(const uint8_t *rows, const uint64_t *missing_whole_or_null, int missing_mode,
+                              size_t first_row, size_t n_rows, size_t n_total_rows, size_t stride,
+                              uint32_t *allele_bits, uint32_t *called_bits_or_null, int n_threads) {
+    if (missing_mode != FM_MISSING_NONE && missing_mode != FM_MISSING_BITMAP && missing_mode != FM_MISSING_IN_BAND)
+        return "fm_pack_rows: bad missing_mode";
+    if (n_rows == 0 || stride == 0) return nullptr;
+    if (!rows || !allele_bits) return "fm_pack_rows: rows / allele_bits is NULL";
+    if (missing_mode == FM_MISSING_BITMAP && !missing_whole_or_null)
+        return "fm_pack_rows: FM_MISSING_BITMAP needs the whole matrix's bitmap";
+    if (missing_mode != FM_MISSING_NONE && !called_bits_or_null)
+        return "fm_pack_rows: called_bits is required when the matrix has missing data";
+    if (first_row > n_total_rows || n_rows > n_total_rows - first_row) return "fm_pack_rows: row range outside the matrix";
+    const uint64_t n_bitmap_words = ((uint64_t)n_total_rows * stride + 63) / 64;
+    unsigned T = n_threads > 0 ? (unsigned)n_threads : std::max(1u, std::thread::hardware_concurrency());
+    T = (unsigned)std::min<size_t>(std::min<unsigned>(T, 64), std::max<size_t>(1, n_rows * stride / (1u << 20)));
+#if FM_X86
+    const bool avx2 = __builtin_cpu_supports("avx2");
+#else
+    const bool avx2 = false;
+#endif
+    auto work = [&](size_t lo, size_t hi) {
+#if FM_X86
+        if (avx2) {
+            pack_range_avx2(rows, missing_whole_or_null, n_bitmap_words, missing_mode, first_row, lo, hi, stride,
+                            allele_bits, called_bits_or_null);
+            return;
+        }
+#endif
+        pack_range_generic(rows, missing_whole_or_null, n_bitmap_words, missing_mode, first_row, lo, hi, stride,
+                           allele_bits, called_bits_or_null);
+    };
+    if (T <= 1) {
+        work(0, n_rows);
+        return nullptr;
+    }
+    std::vector<std::thread> pool;
+    const size_t per = (n_rows + T - 1) / T;
+    try {
+        for (unsigned t = 1; t < T; ++t) {
+            const size_t lo = std::min(n_rows, per * t), hi = std::min(n_rows, per * (t + 1));
+            if (hi > lo) pool.emplace_back(work, lo, hi);
+        }
+    } catch (...) {  // thread creation failed: finish everything on this thread
+        for (auto &th : pool) th.join();
+        work(0, n_rows);
+        return nullptr;
+    }
+    work(0, std::min(n_rows, per));
+    for (auto &th : pool) th.join();
+    return nullptr;
+}
+
+// test hook: the portable SWAR path, whatever the CPU supports
+const char *fm_host_pack_rows_generic(const uint8_t *rows, const uint64_t *missing, int mode, size_t first_row,
+                                      size_t n_rows, size_t n_total_rows, size_t stride, uint32_t *abits,
+                                      uint32_t *cbits) {
+    if (n_rows == 0 || stride == 0) return nullptr;
+    pack_range_generic(rows, missing, ((uint64_t)n_total_rows * stride + 63) / 64, mode, first_row, 0, n_rows, stride,
+                       abits, cbits);
+    return nullptr;
+}

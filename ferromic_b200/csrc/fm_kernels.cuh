@@ -145,12 +145,22 @@ struct CountTable {
     uint32_t n_groups;
 };
 
+// Packed rows (the 2-bit ingest format): row v of the cohort as rw = ceil(stride / 32) u32 words of
+// allele bits (bit c & 31 of word c >> 5: cell c carries a non-zero allele and is called) and, when the matrix
+// has missing data, rw words of called bits.  In this mode the kernel never sees u8 cells: the full-row bit
+// words are loaded as they are (coalesced 4-byte loads) and every group is served from them.
+struct PackedRows {
+    const uint32_t *a;  // [rows][rw] allele bits, row v_base first; nullptr = u8 mode
+    const uint32_t *c;  // [rows][rw] called bits or nullptr (every cell called)
+    uint32_t rw;
+};
+
 __global__ void __launch_bounds__(256)
 fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint64_t *__restrict__ missing,
                  size_t stride, uint32_t v_base, uint64_t word_base, uint32_t v_lo, uint32_t v_hi,
                  const RepackGroup *__restrict__ groups, uint32_t n_groups, uint32_t warp_smem_bytes,
                  uint32_t row_buf_bytes, uint32_t bit_buf_bytes, CountTable ct, uint32_t in_band,
-                 uint32_t need_row_bits, uint32_t direct_rows) {
+                 uint32_t need_row_bits, uint32_t direct_rows, PackedRows pk) {
     // direct_rows: every group is served from the full-row bit words (compress plans / count tables) and rows are
     // whole 16-byte words, so the u8 row is packed straight from global memory (coalesced 16-byte loads) and is
     // never staged: row_buf_bytes == 0, three times the resident warps per SM
@@ -171,7 +181,7 @@ fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint
         __syncwarp();
         // asynchronous 16-byte copies straight into shared memory: every chunk of the row is in
         // flight at once (no register staging, no per-iteration load latency)
-        for (uint32_t q = lane; !direct_rows && q < nq; q += 32) {
+        for (uint32_t q = lane; !direct_rows && !pk.a && q < nq; q += 32) {
             const size_t at = a0 + ((size_t)q << 4);
             if (at + 16 <= data_bytes) {
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(fm_smem_u32(rowb + ((size_t)q << 4))),
@@ -206,7 +216,29 @@ fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint
         uint32_t *crow = arow + rw + 1;
         uint32_t *outb = crow + rw + 1;  // 2 x out_cap words: one group's plane rows while they are assembled
         const uint32_t out_cap = (uint32_t)((stride + 127) >> 7) * 4u;
-        if (need_row_bits) {
+        if (pk.a) {  // packed rows: the full-row bit words arrive ready-made
+            const size_t r0 = (size_t)(v - v_base) * pk.rw;
+            const uint32_t tail = (uint32_t)stride & 31u;
+            for (uint32_t w = lane; w < rw; w += 32) {
+                uint32_t c = pk.c ? __ldg(pk.c + r0 + w) : FULL;
+                if (tail && w == rw - 1) c &= (1u << tail) - 1u;  // bits past the last cell never count
+                crow[w] = c;
+                arow[w] = __ldg(pk.a + r0 + w) & c;
+            }
+            __syncwarp();
+            for (uint32_t g = lane; g < ct.n_groups; g += 32) {  // count-only groups
+                uint32_t a = 0, c = 0;
+                const uint32_t e1 = __ldg(ct.ent_start + g + 1);
+                for (uint32_t e = __ldg(ct.ent_start + g); e < e1; ++e) {
+                    const uint32_t w = __ldg(ct.ent_word + e);
+                    const uint32_t cw = crow[w] & __ldg(ct.ent_mask + e);
+                    c += __popc(cw);
+                    a += __popc(arow[w] & cw);
+                }
+                ct.alt_out[g][v] = a;
+                ct.cnt_out[g][v] = c;
+            }
+        } else if (need_row_bits) {
             const uint32_t *row32 = reinterpret_cast<const uint32_t *>(rowb + (delta & ~3u));
             const uint32_t sh8 = (delta & 3u) * 8u;
             // rows that start on a 16-byte boundary (stride % 16 == 0, e.g. 5008 or 200000 haplotypes): 16 cells per

@@ -104,6 +104,50 @@ fm_status fm_ingest_add_partition(fm_ingest *h, const uint16_t *left, const uint
                                   size_t n_samples, size_t n_groups, size_t *partition_index);
 fm_status fm_ingest_rows(fm_ingest *h, const uint8_t *rows, const uint64_t *missing_whole_or_null,
                          size_t first_row, size_t n_rows);
+/* ---- packed rows: 2 bits per genotype instead of 9 over PCIe ("skip the u8 matrix") ----
+ * Row v of the cohort as row_words = ceil(n_samples * ploidy / 32) u32 words of ALLELE bits followed
+ * (in a second array) by row_words words of CALLED bits: bit (c & 31) of word (c >> 5) describes cell
+ * c = sample * ploidy + side of the reference layout (stats.rs:249-331); allele bit = the cell is called
+ * and carries a non-zero allele index, called bit = the cell is not missing; bits past the last cell are
+ * zero.  Biallelic matrices only (max_allele <= 1).  This is what a parser can emit directly while it
+ * reads genotypes (process.rs:2602-2660 / from_variants, stats.rs:339-500, build the u8 matrix AND the
+ * bitmap today), and what fm_pack_rows produces from an existing u8 / int8 matrix (lib.rs:1135-1227).
+ *
+ * fm_ingest_rows_packed is the packed twin of fm_ingest_rows: rows go straight into the resident
+ * packed matrix (0.25 B per genotype of HBM) and the declared groups / partitions are compressed out
+ * of them chunk by chunk while the next chunk is on the bus.  Because the packed rows stay resident,
+ * fm_group_create / fm_groups_create / fm_partition_create keep working on the finished matrix
+ * (Population.with_haplotypes, lib.rs:622).  called_bits must be NULL iff the ingest was begun with
+ * FM_MISSING_NONE; FM_MISSING_IN_BAND is a u8 notion and is rejected here.  An ingest takes either u8
+ * rows or packed rows, not both. */
+fm_status fm_packed_row_words(size_t n_samples, size_t ploidy, size_t *row_words);
+fm_status fm_ingest_rows_packed(fm_ingest *h, const uint32_t *allele_bits, const uint32_t *called_bits_or_null,
+                                size_t first_row, size_t n_rows);
+/* fm_ingest_rows with the packer inside: same arguments (u8 rows + whole-matrix bitmap, or in-band
+ * cells), but the library packs chunk i+1 on the host with n_threads threads (<= 0: all) while chunk i
+ * crosses PCIe as bit words -- the drop-in for callers that hold the reference's u8 / int8 matrix
+ * (lib.rs:1135-1227) and cannot emit bits themselves.  Pageable sources are read in place. */
+fm_status fm_ingest_rows_pack(fm_ingest *h, const uint8_t *rows, const uint64_t *missing_whole_or_null,
+                              size_t first_row, size_t n_rows, int n_threads);
+/* One-shot form: upload a whole packed matrix (replaces DenseGenotypeMatrix::new, stats.rs:261-296,
+ * for hosts that pack); groups are created afterwards with fm_group_create & co. */
+fm_status fm_matrix_create_packed(const uint32_t *allele_bits, const uint32_t *called_bits_or_null,
+                                  size_t n_variants, size_t n_samples, size_t ploidy,
+                                  const int64_t *positions_or_null, fm_matrix **out);
+/* Host packer (no GPU involved; usable before any device call): rows -> first of n_rows u8 rows of
+ * `stride` = n_samples * ploidy cells (row first_row of a matrix of n_total_rows rows);
+ * missing_mode FM_MISSING_NONE / FM_MISSING_BITMAP (missing_whole = the WHOLE matrix's LSB-first
+ * bitmap, stats.rs:1298-1302) / FM_MISSING_IN_BAND (cells >= 0x80 are missing).  Writes
+ * allele_bits[n_rows][row_words] and, unless missing_mode is FM_MISSING_NONE, called_bits likewise.
+ * n_threads <= 0: one thread per hardware thread.  AVX2 when the CPU has it (runtime check). */
+fm_status fm_pack_rows(const uint8_t *rows, const uint64_t *missing_whole_or_null, int missing_mode,
+                       size_t first_row, size_t n_rows, size_t n_total_rows, size_t stride,
+                       uint32_t *allele_bits, uint32_t *called_bits_or_null, int n_threads);
+/* the portable (non-AVX2) code path of the packer, single-threaded; exported for the parity tests */
+fm_status fm_pack_rows_generic(const uint8_t *rows, const uint64_t *missing_whole_or_null, int missing_mode,
+                               size_t first_row, size_t n_rows, size_t n_total_rows, size_t stride,
+                               uint32_t *allele_bits, uint32_t *called_bits_or_null);
+
 fm_status fm_ingest_finish(fm_ingest *h, fm_matrix **matrix_out, fm_group **groups_out,
                            fm_partition **partitions_out);
 fm_status fm_ingest_abort(fm_ingest *h);
@@ -409,6 +453,7 @@ typedef struct {
     uint64_t stats_launches;   /* launches of the plane-streaming kernels */
     uint64_t kernel_launches;  /* all kernel launches since the counters were reset */
     uint64_t stats_bytes;      /* algorithmic plane bytes streamed by the last stats kernel */
+    float pack_ms;             /* host time inside the packer of fm_ingest_rows_pack (overlaps h2d) */
 } fm_timings;
 fm_status fm_timings_reset(void);
 fm_status fm_timings_get(fm_timings *out);
@@ -429,6 +474,12 @@ typedef struct {
     float group_ms_avg[8];         /* mean plane-pass duration per listed group (first 8) */
     uint64_t group_bytes[8];       /* algorithmic bytes of one launch per listed group */
     float comm_ms_avg;             /* mean duration of the fused fold + peer exchange kernel (incl. waiting) */
+    /* region totals of the last timed step, per listed group (first 8): this rank's, and -- with a
+     * communicator -- the exchanged rank-ordered sums (parity check of the run) */
+    double last_pi_sum[8];
+    uint64_t last_seg[8], last_unc[8];
+    double merged_pi_sum[8];
+    uint64_t merged_seg[8], merged_unc[8];
 } fm_bench_result;
 fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
                              const int64_t *mask_iv_or_null, size_t n_mask, int iterations,

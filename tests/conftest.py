@@ -25,3 +25,12 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(params=["packed", "u8"])
+def both_ingest_modes(request, monkeypatch):
+    """Runs a test once per host->device ingest format of the Python mirror (FERROMIC_GPU_INGEST): the 2-bit
+    packed rows (fm_pack_rows + fm_matrix_create_packed, the default) and the reference-layout u8 upload that is
+    repacked on the device.  Both must give the oracle's results."""
+    monkeypatch.setenv("FERROMIC_GPU_INGEST", request.param)
+    return request.param

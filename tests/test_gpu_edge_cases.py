@@ -11,7 +11,7 @@ from oracle import pyoracle as orc
 from tests.synth import both_sides
 from tests.test_gpu_parity import assert_arrays_close, close
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("both_ingest_modes")]
 
 
 def F():

@@ -10,7 +10,7 @@ import pytest
 from oracle import pyoracle as orc
 from tests.synth import both_sides, make_cohort
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("both_ingest_modes")]
 
 REL = 1e-9
 
