@@ -65,10 +65,10 @@ EXPORTS = [
     "fm_matrix_create", "fm_matrix_create_inband", "fm_matrix_create_device", "fm_matrix_retain", "fm_matrix_release",
     "fm_matrix_info", "fm_ingest_begin", "fm_ingest_add_group", "fm_ingest_add_partition",
     "fm_ingest_rows", "fm_ingest_finish", "fm_ingest_abort", "fm_packed_row_words", "fm_ingest_rows_packed",
-    "fm_matrix_create_packed", "fm_pack_rows", "fm_pack_rows_generic", "fm_ingest_rows_pack", "fm_group_create", "fm_groups_create", "fm_group_release", "fm_group_capacity", "fm_group_summary",
+    "fm_matrix_create_packed", "fm_pack_rows", "fm_pack_rows_generic", "fm_ingest_rows_pack", "fm_group_create", "fm_groups_create", "fm_group_release", "fm_group_capacity", "fm_group_summary", "fm_groups_summary_batch",
     "fm_group_segregating_sites", "fm_group_pi", "fm_harmonic", "fm_watterson_theta",
     "fm_per_site_diversity", "fm_per_site_diversity_multi", "fm_hudson_pair", "fm_hudson_dxy", "fm_partition_create",
-    "fm_partition_release", "fm_wc_fst", "fm_wc_window_sums", "fm_fst_estimate_from_sums", "fm_adjusted_sequence_length", "fm_group_window_sums",
+    "fm_partition_release", "fm_wc_fst", "fm_wc_window_sums", "fm_fst_estimate_from_sums", "fm_wc_arith_probe", "fm_adjusted_sequence_length", "fm_group_window_sums",
     "fm_hudson_window_sums", "fm_pi_from_sums", "fm_hudson_outcome_from_sums", "fm_comm_create", "fm_comm_export", "fm_comm_connect", "fm_comm_connect_local", "fm_comm_allgather", "fm_comm_set_timeout_ms",
     "fm_comm_destroy", "fm_falsta_track", "fm_falsta_tracks", "fm_falsta_format_value", "fm_vcf_parse", "fm_vcf_parse_device", "fm_vcf_batch_info",
     "fm_vcf_batch_variants", "fm_vcf_batch_genotypes", "fm_vcf_batch_positions", "fm_vcf_batch_errors", "fm_vcf_batch_matrix",
@@ -123,6 +123,7 @@ def lib() -> C.CDLL:
     L.fm_group_release.argtypes = [vp]
     L.fm_group_capacity.argtypes = [vp, C.POINTER(sz)]
     L.fm_group_summary.argtypes = [vp, vp, vp, C.POINTER(u64), C.POINTER(dbl), C.POINTER(u64)]
+    L.fm_groups_summary_batch.argtypes = [C.POINTER(vp), sz, vp, vp, vp]
     L.fm_group_segregating_sites.argtypes = [vp, C.POINTER(u64)]
     L.fm_group_pi.argtypes = [vp, i64, C.c_int, sz, C.POINTER(dbl)]
     L.fm_harmonic.argtypes = [sz, C.POINTER(dbl)]
@@ -138,6 +139,7 @@ def lib() -> C.CDLL:
                             C.POINTER(sz)]
     L.fm_wc_window_sums.argtypes = [vp, vp, sz, vp, vp, vp, vp, vp, vp, vp]
     L.fm_fst_estimate_from_sums.argtypes = [dbl, dbl, u64, u64, C.POINTER(FstEstimateC)]
+    L.fm_wc_arith_probe.argtypes = [vp, vp, vp, vp, sz]
     L.fm_adjusted_sequence_length.argtypes = [i64, i64, vp, sz, vp, sz, C.POINTER(i64)]
     L.fm_group_window_sums.argtypes = [vp, vp, sz, vp, vp, vp, vp]
     L.fm_hudson_window_sums.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, vp, vp]

@@ -423,6 +423,9 @@ struct fm_partition {
     size_t G = 0;
     std::vector<fm_group *> groups;  // one bitplane group per subpopulation
     fm_group *rest = nullptr;        // haplotypes with no group (needed for "alleles present")
+    std::mutex mu;
+    double *d_wc_tab = nullptr;      // K4 reciprocal tables: RN(1/n) | RN(2/n^2), n = 0 .. wc_n_max
+    uint32_t wc_n_max = 0;
 };
 
 namespace {
@@ -654,6 +657,109 @@ void launch_plane_pass_seq(fm::SeqParams P, int device) {
     for (uint32_t i = 0; i < P.n_seg; ++i)
         bytes += (uint64_t)(P.geom.v_hi - P.geom.v_lo) * P.seg[i].g.wq * 16u * (P.seg[i].g.called ? 2u : 1u);
     t_tim.stats_bytes = bytes;
+}
+
+// fm_k_plane_pass_tab: an arbitrary list of plane segments (gpu = 1: independent (region, group) units;
+// gpu = 2: Hudson pairs over shared sites) in ONE persistent launch.  Fills rounds / b_lo of every segment,
+// uploads the descriptor table and launches.  Returns false when the segments cannot share a launch
+// (column-chunked rows, mixed bitmap / no bitmap): the caller then goes unit by unit.
+struct TabLaunch {
+    DevBuf<fm::TabSeg> d_segs;
+    DevBuf<uint32_t> d_prefix;
+    DevBuf<fm::HudsonEpilogue> d_hud;
+    std::vector<uint32_t> prefix;  // host copy: batches before unit u
+};
+bool launch_plane_pass_tab(std::vector<fm::TabSeg> &segs, uint32_t gpu, const std::vector<fm::HudsonEpilogue> *hud,
+                           int device, TabLaunch &keep) {
+    if (segs.empty() || (gpu != 1 && gpu != 2) || segs.size() % gpu) return false;
+    static const uint32_t step_target = env_u32("FM_STEP_BYTES", fm::kStepBytesTarget);
+    const uint32_t warp_smem = fm::kWarpSmemBytes;
+    const bool hc = segs[0].g.called != nullptr;
+    uint32_t max_wq = 0;
+    for (const fm::TabSeg &sg : segs) {
+        if ((sg.g.called != nullptr) != hc) return false;
+        max_wq = std::max(max_wq, sg.g.wq);
+    }
+    uint32_t lg = 0;
+    while ((1u << lg) < std::min(max_wq, 8u)) ++lg;
+    const uint32_t planes = hc ? 2u : 1u;
+    while (lg < 5 && (uint64_t)max_wq * 16u * planes * (32u >> lg) * 2 > warp_smem) ++lg;
+    if (lg >= 5) return false;
+    const size_t n_units = segs.size() / gpu;
+    uint32_t max_step = 0;
+    keep.prefix.assign(n_units + 1, 0);
+    uint64_t total = 0, bytes = 0;
+    for (size_t u = 0; u < n_units; ++u) {
+        fm::TabSeg &s0 = segs[u * gpu];
+        const uint32_t nb = s0.v_hi > s0.v_lo ? (s0.v_hi + 31) / 32 - s0.v_lo / 32 : 0;
+        for (uint32_t g = 0; g < gpu; ++g) {
+            fm::TabSeg &sg = segs[u * gpu + g];
+            if (sg.v_lo != s0.v_lo || sg.v_hi != s0.v_hi) return false;
+            const uint32_t round_bytes = sg.g.wq * 16u * planes * (32u >> lg);
+            uint32_t rounds = 1;
+            while (rounds * 2 <= (1u << lg) && round_bytes * rounds * 2 <= step_target) rounds *= 2;
+            sg.rounds = rounds;
+            sg.b_lo = sg.v_lo / 32;
+            max_step = std::max(max_step, round_bytes * rounds);
+            bytes += (uint64_t)(sg.v_hi - sg.v_lo) * sg.g.wq * 16u * planes;
+        }
+        keep.prefix[u] = (uint32_t)total;
+        total += nb;
+        if (total >= (1ull << 31)) return false;
+    }
+    keep.prefix[n_units] = (uint32_t)total;
+    if (total == 0) return true;
+    fm::TabParams P{};
+    fm::PassGeom &G = P.geom;
+    G.lps_log2 = lg;
+    G.lps = 1u << lg;
+    G.warps = fm::kWarpsPerCta;
+    G.warp_smem_bytes = warp_smem;
+    G.stage_bytes = (max_step + 127u) & ~127u;
+    G.n_stages = std::min<uint32_t>(fm::kMaxStages, warp_smem / G.stage_bytes);
+    if (G.n_stages < 2) return false;
+    G.n_batches = (uint32_t)total;
+    G.batch_counter = t_counters.take(device);
+    keep.d_segs.alloc(segs.size());
+    keep.d_segs.upload(segs.data(), segs.size());
+    keep.d_prefix.alloc(n_units + 1);
+    keep.d_prefix.upload(keep.prefix.data(), n_units + 1);
+    if (hud) {
+        if (hud->size() != n_units) fail(FM_ERR_INVALID_ARG, "internal: one Hudson epilogue per unit");
+        keep.d_hud.alloc(n_units);
+        keep.d_hud.upload(hud->data(), n_units);
+        P.hud = keep.d_hud.p;
+    }
+    CK(cudaStreamSynchronize(stream()));  // the descriptor vectors are host temporaries
+    P.segs = keep.d_segs.p;
+    P.unit_prefix = keep.d_prefix.p;
+    P.n_units = (uint32_t)n_units;
+    P.gpu = gpu;
+    const size_t smem = (size_t)fm::kWarpsPerCta * warp_smem;
+    const uint32_t grid = std::min<uint32_t>((uint32_t)sm_count(device),
+                                             (uint32_t)((total * gpu + fm::kWarpsPerCta - 1) / fm::kWarpsPerCta));
+#define FM_TAB_CASE(L)                                                                                              \
+    case L:                                                                                                         \
+        if (hc) {                                                                                                   \
+            CK(cudaFuncSetAttribute(fm::fm_k_plane_pass_tab<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                    (int)smem));                                                                    \
+            fm::fm_k_plane_pass_tab<L, true><<<grid, fm::kWarpsPerCta * 32, smem, stream()>>>(P);                   \
+        } else {                                                                                                    \
+            CK(cudaFuncSetAttribute(fm::fm_k_plane_pass_tab<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    (int)smem));                                                                    \
+            fm::fm_k_plane_pass_tab<L, false><<<grid, fm::kWarpsPerCta * 32, smem, stream()>>>(P);                  \
+        }                                                                                                           \
+        break;
+    switch (lg) {
+        FM_TAB_CASE(0) FM_TAB_CASE(1) FM_TAB_CASE(2) FM_TAB_CASE(3) FM_TAB_CASE(4)
+        default: fail(FM_ERR_INVALID_ARG, "internal: bad table pass geometry");
+    }
+#undef FM_TAB_CASE
+    CK(cudaGetLastError());
+    g_launches++;
+    t_tim.stats_launches++;
+    t_tim.stats_bytes = bytes;
+    return true;
 }
 
 // reduce per-batch partials to per-super-batch on device, finish sequentially on the host
@@ -989,6 +1095,25 @@ void merge_intervals(const int64_t *iv, size_t n, std::vector<int64_t> &out) {
 
 int dense_variant(const fm_matrix *m) { return m->has_missing ? FM_HV_DENSE_MISSING : FM_HV_DENSE_NOMISSING; }
 
+// 1-based output positions of sites [lo, lo + n) (stats.rs:747, 3004, 4746): small ranges are written by the host,
+// large ones come from the device copy of the positions (one kernel + one D2H instead of a million-element host
+// loop).  pos_out == NULL: the caller already knows the positions.  The copy is ordered on stream().
+__global__ void fm_k_pos_plus1(const int64_t *__restrict__ pos, uint32_t lo, uint32_t n, int64_t *__restrict__ out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = pos[lo + i] + 1;
+}
+void download_positions_plus1(const fm_matrix *m, uint32_t lo, size_t n, int64_t *pos_out, DevBuf<int64_t> &scratch) {
+    if (!pos_out || !n) return;
+    if (n < 65536) {
+        for (size_t i = 0; i < n; ++i) pos_out[i] = m->pos[lo + i] + 1;
+        return;
+    }
+    scratch.alloc(n);
+    fm_k_pos_plus1<<<(uint32_t)std::min<size_t>((n + 255) / 256, 2048), 256, 0, stream()>>>(m->d_pos, lo, (uint32_t)n, scratch.p);
+    CK(cudaGetLastError());
+    g_launches++;
+    scratch.download(pos_out, n);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------ library
@@ -1060,8 +1185,12 @@ static fm_matrix *matrix_common(size_t V, size_t S, size_t ploidy, uint8_t max_a
     m->ploidy = ploidy;
     m->stride = S * ploidy;
     m->max_allele = max_allele;
-    m->pos.resize(V);
-    for (size_t i = 0; i < V; ++i) m->pos[i] = positions ? positions[i] : (int64_t)i;
+    if (positions)
+        m->pos.assign(positions, positions + V);
+    else {
+        m->pos.resize(V);
+        for (size_t i = 0; i < V; ++i) m->pos[i] = (int64_t)i;
+    }
     m->sorted = std::is_sorted(m->pos.begin(), m->pos.end());
     return m;
 }
@@ -1629,6 +1758,122 @@ fm_status fm_group_summary(fm_group *g, uint32_t *alt_out, uint32_t *called_out,
     });
 }
 
+// build_dense_population_summary for MANY groups -- normally one per region-sized matrix, the shape of the CLI's
+// loop over config entries (process.rs:2169 -> stats.rs:1367-1470) -- in one persistent launch: groups whose counts
+// are not cached yet become the units of one fm_k_plane_pass_tab pass (per LPS / bitmap class), their partials
+// are folded by one kernel and come back in one copy.  Each group ends up exactly as after fm_group_summary.
+fm_status fm_groups_summary_batch(fm_group *const *groups, size_t n_groups, uint64_t *seg_out, double *pi_sum_out,
+                                  uint64_t *unc_out) {
+    return guarded([&] {
+        if (n_groups && !groups) fail(FM_ERR_INVALID_ARG, "groups is NULL");
+        require_device();
+        if (!n_groups) return;
+        for (size_t i = 0; i < n_groups; ++i) {
+            if (!groups[i]) fail(FM_ERR_INVALID_ARG, "group is NULL");
+            if (groups[i]->m->device != groups[0]->m->device) fail(FM_ERR_INVALID_ARG, "groups must live on one device");
+        }
+        const int device = groups[0]->m->device;
+        CK(cudaSetDevice(device));
+        std::vector<fm_group *> order(groups, groups + n_groups);
+        std::sort(order.begin(), order.end());
+        order.erase(std::unique(order.begin(), order.end()), order.end());
+        std::vector<std::unique_lock<std::mutex>> locks;
+        for (fm_group *g : order) locks.emplace_back(g->mu);  // address order: no lock inversion
+        // classes of groups that can share a launch: biallelic planes, same bitmap presence
+        std::vector<fm_group *> todo[2];
+        for (fm_group *g : order)
+            if (!g->have_counts && g->n_bits == 1 && !g->count_only && g->m->V > 0) todo[g->d_called ? 1 : 0].push_back(g);
+        for (int cls = 0; cls < 2; ++cls) {
+            std::vector<fm_group *> &gs = todo[cls];
+            if (gs.empty()) continue;
+            std::vector<fm::TabSeg> segs(gs.size());
+            std::vector<size_t> part_off(gs.size());
+            size_t total_b = 0;
+            for (size_t i = 0; i < gs.size(); ++i) {
+                const uint32_t V = (uint32_t)gs[i]->m->V;
+                part_off[i] = total_b;
+                total_b += (V + 31) / 32;
+            }
+            DevBuf<double> ppi(total_b);
+            DevBuf<uint32_t> ppu(total_b * 2);
+            std::vector<uint4> ents;
+            for (size_t i = 0; i < gs.size(); ++i) {
+                fm_group *g = gs[i];
+                const uint32_t V = (uint32_t)g->m->V;
+                if (!g->d_alt) {
+                    g->d_alt = static_cast<uint32_t *>(dev_alloc((size_t)V * 4));
+                    g->d_cnt = static_cast<uint32_t *>(dev_alloc((size_t)V * 4));
+                }
+                fm::DivEpilogue de{};
+                set_tables(de, g);
+                de.pi_form = FM_PIFORM_COUNTS;
+                de.part_pi = ppi.p + part_off[i];
+                de.part_u = ppu.p + 2 * part_off[i];
+                de.alt_out = g->d_alt;
+                de.called_out = g->d_cnt;
+                segs[i] = fm::TabSeg{};
+                segs[i].g = planes_of(g);
+                segs[i].div = de;
+                segs[i].v_lo = 0;
+                segs[i].v_hi = V;
+                segs[i].n_sites_total = V;
+                const uint32_t nb = (V + 31) / 32;
+                for (uint32_t sb = 0; sb * fm::kSuperBatches < nb; ++sb)
+                    ents.push_back(make_uint4((uint32_t)part_off[i], 0u, nb, sb));
+            }
+            if (total_b >= (1ull << 31)) fail(FM_ERR_UNSUPPORTED, "too many sites for one batched summary call");
+            TabLaunch keep;
+            Timer tm;
+            tm.start();
+            if (!launch_plane_pass_tab(segs, 1, nullptr, device, keep)) {
+                // rows wider than the table pass handles (column-chunked): one pass per group
+                locks.clear();
+                for (fm_group *g : gs) ensure_counts(g);
+                for (fm_group *g : order) locks.emplace_back(g->mu);
+                continue;
+            }
+            DevBuf<uint4> d_ents(ents.size());
+            d_ents.upload(ents.data(), ents.size());
+            DevBuf<double> sd(ents.size());
+            DevBuf<uint64_t> su(ents.size() * 2);
+            fm::fm_k_reduce_partials_tab<<<(uint32_t)((ents.size() + 3) / 4), 128, 0, stream()>>>(
+                ppi.p, 1, ppu.p, 2, d_ents.p, (uint32_t)ents.size(), sd.p, su.p);
+            CK(cudaGetLastError());
+            g_launches++;
+            tm.stop();
+            std::vector<double> hd(ents.size());
+            std::vector<uint64_t> hu(ents.size() * 2);
+            sd.download(hd.data(), ents.size());
+            su.download(hu.data(), ents.size() * 2);
+            CK(cudaStreamSynchronize(stream()));
+            t_tim.stats_ms += tm.ms();
+            size_t e = 0;
+            for (size_t i = 0; i < gs.size(); ++i) {
+                const uint32_t nb = ((uint32_t)gs[i]->m->V + 31) / 32;
+                double pi = 0.0;
+                uint64_t sg = 0, un = 0;
+                for (uint32_t sb = 0; sb * fm::kSuperBatches < nb; ++sb, ++e) {  // fixed order, like finish_partials
+                    pi += hd[e];
+                    sg += hu[2 * e];
+                    un += hu[2 * e + 1];
+                }
+                gs[i]->pi_sum = pi;
+                gs[i]->seg = sg;
+                gs[i]->unc = un;
+                gs[i]->have_counts = true;
+            }
+        }
+        locks.clear();
+        for (size_t i = 0; i < n_groups; ++i) {
+            fm_group *g = groups[i];
+            if (!g->have_counts) ensure_counts(g);  // multi-allelic / empty matrices / count-only leftovers
+            if (seg_out) seg_out[i] = g->seg;
+            if (pi_sum_out) pi_sum_out[i] = g->pi_sum;
+            if (unc_out) unc_out[i] = g->unc;
+        }
+    });
+}
+
 fm_status fm_group_segregating_sites(fm_group *g, uint64_t *out) {
     return guarded([&] {
         if (!g || !out) fail(FM_ERR_INVALID_ARG, "NULL argument");
@@ -1714,7 +1959,7 @@ fm_status fm_per_site_diversity(fm_group *g, size_t raw_n, int64_t rs, int64_t r
         const size_t n = hi - lo;
         if (n == 0) return;
         if (n > capacity) fail(FM_ERR_INVALID_ARG, "output capacity too small");
-        if (!pos_out || !pi_out || !theta_out) fail(FM_ERR_INVALID_ARG, "output arrays are NULL");
+        if (!pi_out || !theta_out) fail(FM_ERR_INVALID_ARG, "output arrays are NULL");
         std::vector<int64_t> merged;
         DevBuf<int64_t> d_mask, d_filt;
         if (mask_iv) {
@@ -1740,10 +1985,11 @@ fm_status fm_per_site_diversity(fm_group *g, size_t raw_n, int64_t rs, int64_t r
         tm.start();
         d_pi.download(pi_out, n);
         d_theta.download(theta_out, n);
+        DevBuf<int64_t> d_p1;
+        download_positions_plus1(g->m, lo, n, pos_out, d_p1);  // stats.rs:4746
         tm.stop();
         CK(cudaStreamSynchronize(stream()));
         t_tim.d2h_ms += tm.ms();
-        for (size_t i = 0; i < n; ++i) pos_out[i] = g->m->pos[lo + i] + 1;  // stats.rs:4746
         *n_out = n;
     });
 }
@@ -1766,7 +2012,7 @@ fm_status fm_per_site_diversity_multi(fm_group *const *groups, const size_t *raw
         const size_t n = hi - lo;
         if (n == 0) return;
         if (n > capacity) fail(FM_ERR_INVALID_ARG, "output capacity too small");
-        if (!pos_out || !pi_out || !theta_out) fail(FM_ERR_INVALID_ARG, "output arrays are NULL");
+        if (!pi_out || !theta_out) fail(FM_ERR_INVALID_ARG, "output arrays are NULL");
         std::vector<int64_t> merged, fs;
         DevBuf<int64_t> d_mask, d_filt;
         if (mask_iv) {
@@ -1815,6 +2061,8 @@ fm_status fm_per_site_diversity_multi(fm_group *const *groups, const size_t *raw
             d_pi[i].download(pi_out + act_idx[i] * capacity, n);
             d_th[i].download(theta_out + act_idx[i] * capacity, n);
         }
+        DevBuf<int64_t> d_p1;
+        download_positions_plus1(m, lo, n, pos_out, d_p1);  // stats.rs:4746
         tm.stop();
         CK(cudaStreamSynchronize(stream()));
         t_tim.d2h_ms += tm.ms();
@@ -1822,7 +2070,6 @@ fm_status fm_per_site_diversity_multi(fm_group *const *groups, const size_t *raw
         for (size_t i = 0; i < n_groups; ++i)
             if (raw_n[i] < 2)
                 for (size_t k = 0; k < n; ++k) pi_out[i * capacity + k] = theta_out[i * capacity + k] = NaN;
-        for (size_t i = 0; i < n; ++i) pos_out[i] = m->pos[lo + i] + 1;  // stats.rs:4746
         *n_out = n;
     });
 }
@@ -1852,7 +2099,18 @@ struct fm_ingest {
     cudaEvent_t pin_free[2] = {nullptr, nullptr};
     bool pin_used[2] = {false, false};
     float pack_ms = 0.f;                   // host time spent in the packer (fm_ingest_rows_pack)
+    bool pos_uploaded = false;
 };
+
+// Host work that does not depend on the rows -- the upload of the (pageable) position vector -- is done once,
+// after a rows call has queued its asynchronous copies, so it hides under the DMA instead of preceding it.
+static void ingest_late_setup(fm_ingest *h) {
+    if (h->pos_uploaded) return;
+    fm_matrix *m = h->m;
+    if (m->V) CK(cudaMemcpyAsync(m->d_pos, m->pos.data(), m->V * 8, cudaMemcpyHostToDevice, stream()));
+    CK(cudaStreamSynchronize(stream()));
+    h->pos_uploaded = true;
+}
 
 static void ingest_destroy(fm_ingest *h, bool release_handles) {
     if (!h) return;
@@ -1895,7 +2153,7 @@ fm_status fm_ingest_begin(size_t V, size_t S, size_t ploidy, int has_missing, ui
                 fail(FM_ERR_INVALID_ARG, "in-band missingness needs allele indices <= 127");
             h->m->streamed = true;
             h->m->d_pos = static_cast<int64_t *>(dev_alloc(std::max<size_t>(V, 1) * 8));
-            if (V) CK(cudaMemcpyAsync(h->m->d_pos, h->m->pos.data(), V * 8, cudaMemcpyHostToDevice, stream()));
+            // the positions are uploaded by the first rows call, while its DMA is in flight (ingest_late_setup)
             const size_t stride = std::max<size_t>(h->m->stride, 1);
             if (chunk_rows == 0) chunk_rows = std::max<size_t>(32, ((size_t)64 << 20) / stride);
             chunk_rows = std::min(std::max<size_t>(chunk_rows, 1), std::max<size_t>(V, 1));
@@ -2005,6 +2263,7 @@ fm_status fm_ingest_rows(fm_ingest *h, const uint8_t *rows, const uint64_t *miss
         h->rows_done += n_rows;
         CK(cudaEventRecord(h->t_copy1, h->copy_s));
         CK(cudaEventRecord(h->t_comp1, h->comp_s));
+        ingest_late_setup(h);
         CK(cudaStreamSynchronize(h->copy_s));  // the caller's buffers are free again on return
     });
 }
@@ -2093,6 +2352,7 @@ fm_status fm_ingest_rows_packed(fm_ingest *h, const uint32_t *allele_bits, const
         h->rows_done += n_rows;
         CK(cudaEventRecord(h->t_copy1, h->copy_s));
         CK(cudaEventRecord(h->t_comp1, h->comp_s));
+        ingest_late_setup(h);
         CK(cudaStreamSynchronize(h->copy_s));  // the caller's buffers are free again on return
     });
 }
@@ -2153,6 +2413,7 @@ fm_status fm_ingest_rows_pack(fm_ingest *h, const uint8_t *rows, const uint64_t 
         h->rows_done += n_rows;
         CK(cudaEventRecord(h->t_copy1, h->copy_s));
         CK(cudaEventRecord(h->t_comp1, h->comp_s));
+        ingest_late_setup(h);
         CK(cudaStreamSynchronize(h->copy_s));
     });
 }
@@ -2195,6 +2456,7 @@ fm_status fm_ingest_finish(fm_ingest *h, fm_matrix **matrix_out, fm_group **grou
         if ((!groups_out && !h->groups.empty()) || (!parts_out && !h->parts.empty()) || !matrix_out)
             fail(FM_ERR_INVALID_ARG, "output arrays are NULL");
         set_dev(h->m);
+        ingest_late_setup(h);
         CK(cudaStreamSynchronize(h->comp_s));
         if (h->timing_started) {
             float a = 0.f, b = 0.f;
@@ -2343,19 +2605,72 @@ fm_status fm_hudson_pair(fm_group *g1, fm_group *g2, int64_t L1, int64_t L2, int
                         g->d_alt = static_cast<uint32_t *>(dev_alloc((size_t)V * 4));
                         g->d_cnt = static_cast<uint32_t *>(dev_alloc((size_t)V * 4));
                     }
-                // ONE launch streams both groups' planes (fm_k_plane_pass_seq, ~6.4 TB/s against ~5.7 TB/s
-                // for the per-site fused two-group pass), caching their counts and summary scalars; the
-                // Hudson values then come from the counts (16 B/site) with the light kernel.
+                // ONE sweep of both groups' planes (fm_k_plane_pass_tab, pair units): every warp streams a batch of
+                // group 1, then the same batch of group 2, and evaluates the Hudson components in place -- the
+                // groups' counts and summary scalars are cached for later calls AND the Hudson partials (plus the
+                // optional per-site values) come out of the same pass (stats.rs:3179-3278).
                 fm_group *pair[2] = {g1, g2};
-                DivResult r[2];
-                run_diversity_multi(pair, 2, 0, V, FM_PIFORM_COUNTS, nullptr, nullptr, nullptr, 0, nullptr, 0, r, true);
+                const uint32_t nb = (V + 31) / 32;
+                DevBuf<double> ppi[2], pd((size_t)nb * 5);
+                DevBuf<uint32_t> ppu[2], pu((size_t)nb * 3);
+                std::vector<fm::TabSeg> segs(2);
                 for (int k = 0; k < 2; ++k) {
-                    pair[k]->seg = r[k].seg;
-                    pair[k]->unc = r[k].unc;
-                    pair[k]->pi_sum = r[k].pi_sum;
-                    pair[k]->have_counts = true;
+                    ppi[k].alloc(nb);
+                    ppu[k].alloc((size_t)nb * 2);
+                    fm::DivEpilogue de{};
+                    set_tables(de, pair[k]);
+                    de.pi_form = FM_PIFORM_COUNTS;
+                    de.part_pi = ppi[k].p;
+                    de.part_u = ppu[k].p;
+                    de.alt_out = pair[k]->d_alt;
+                    de.called_out = pair[k]->d_cnt;
+                    segs[k] = fm::TabSeg{};
+                    segs[k].g = planes_of(pair[k]);
+                    segs[k].div = de;
+                    segs[k].v_lo = 0;
+                    segs[k].v_hi = V;
+                    segs[k].n_sites_total = V;
                 }
-                main_t = run_hudson_counts(g1, g2, lo, hi, site_variant, e);
+                fm::HudsonEpilogue he = e;
+                he.variant = site_variant;
+                he.part_d = pd.p;
+                he.part_u = pu.p;
+                std::vector<fm::HudsonEpilogue> hv{he};
+                TabLaunch keep;
+                Timer tm;
+                tm.start();
+                static const uint32_t no_tab = env_u32("FM_NO_TAB", 0);
+                const bool ok = !no_tab && launch_plane_pass_tab(segs, 2, &hv, m->device, keep);
+                tm.stop();
+                if (ok) {
+                    fm::PassGeom G{};
+                    G.b_lo = 0;
+                    G.n_batches = nb;
+                    for (int k = 0; k < 2; ++k) {
+                        double od[1];
+                        uint64_t ou[2];
+                        finish_partials(ppi[k].p, 1, ppu[k].p, 2, G, od, ou);
+                        pair[k]->pi_sum = od[0];
+                        pair[k]->seg = ou[0];
+                        pair[k]->unc = ou[1];
+                        pair[k]->have_counts = true;
+                    }
+                    double od[5];
+                    uint64_t ou[3];
+                    finish_partials(pd.p, 5, pu.p, 3, G, od, ou);
+                    main_t = HudsonTotals{od[0], od[1], od[2], od[3], od[4], ou[0], ou[1], ou[2]};
+                    t_tim.stats_ms += tm.ms();
+                } else {  // rows too wide for the table pass: two streamed groups, then the light kernel
+                    DivResult r[2];
+                    run_diversity_multi(pair, 2, 0, V, FM_PIFORM_COUNTS, nullptr, nullptr, nullptr, 0, nullptr, 0, r, true);
+                    for (int k = 0; k < 2; ++k) {
+                        pair[k]->seg = r[k].seg;
+                        pair[k]->unc = r[k].unc;
+                        pair[k]->pi_sum = r[k].pi_sum;
+                        pair[k]->have_counts = true;
+                    }
+                    main_t = run_hudson_counts(g1, g2, lo, hi, site_variant, e);
+                }
                 fused = true;
             }
         }
@@ -2458,6 +2773,8 @@ fm_status fm_partition_create(fm_matrix *m, const uint16_t *left, const uint16_t
 
 fm_status fm_partition_release(fm_partition *p) {
     if (!p) return FM_OK;
+    if (p->m) cudaSetDevice(p->m->device);
+    dev_free(p->d_wc_tab);
     for (fm_group *g : p->groups) fm_group_release(g);
     fm_matrix_release(p->m);
     delete p;
@@ -2492,6 +2809,33 @@ struct WcWindowTotals {  // host copies, one entry per window
     std::vector<double> pair;        // [n_w][n_pairs][2]
     std::vector<uint64_t> pair_n;    // [n_w][n_pairs]
 };
+
+// Reciprocal tables of the biallelic W&C kernels (fm_wc.cuh): every divisor of the pair formulas that depends
+// only on sample sizes is an integer n <= n_i + n_j (or n/2, n/2 - 1, 2 (n/2)^2), so its correctly rounded
+// reciprocal comes from a table built once per partition with IEEE divisions on the host.
+fm::WcTables wc_tables(fm_partition *p) {
+    std::lock_guard<std::mutex> lk(p->mu);
+    if (!p->d_wc_tab) {
+        uint32_t top1 = 0, top2 = 0;  // the two largest group capacities
+        for (size_t g = 0; g < p->G; ++g) {
+            const uint32_t n = p->groups[g]->n;
+            if (n > top1) { top2 = top1; top1 = n; }
+            else if (n > top2) top2 = n;
+        }
+        const uint32_t n_max = std::max(top1 + top2, 2u);
+        std::vector<double> T(2 * ((size_t)n_max + 1), 0.0);
+        for (uint32_t n = 1; n <= n_max; ++n) {
+            const double nd = (double)n, n_bar = nd / 2.0;
+            T[n] = 1.0 / nd;
+            T[(size_t)n_max + 1 + n] = 1.0 / (2.0 * n_bar * n_bar);
+        }
+        p->d_wc_tab = static_cast<double *>(dev_alloc(T.size() * 8));
+        CK(cudaMemcpyAsync(p->d_wc_tab, T.data(), T.size() * 8, cudaMemcpyHostToDevice, stream()));
+        CK(cudaStreamSynchronize(stream()));
+        p->wc_n_max = n_max;
+    }
+    return fm::WcTables{p->d_wc_tab, p->d_wc_tab + p->wc_n_max + 1, p->wc_n_max};
+}
 
 // K4 over a list of windows given as site-index ranges: segments cut at multiples of
 // kWcSegSites, one warp per segment, then the per-window fold.  Per-site outputs (host
@@ -2582,32 +2926,50 @@ void run_wc(fm_partition *p, const std::vector<uint32_t> &wlo, const std::vector
     W.part_pair = d_pp.p;
     W.part_pair_n = d_pn.p;
 
-    // CTA geometry: pair warps (lane = pair, KP pairs per lane in registers) + one overall warp
+    // CTA geometry: pair warps (lane = pair, KP pairs per lane in registers); the multi-allelic kernel adds one
+    // overall warp, the biallelic path evaluates the overall components in its own light kernel
     uint32_t n_pw = std::max(1u, std::min<uint32_t>(fm::kWcMaxPairWarps, (n_pairs + 31) / 32));
     const uint32_t kp_need = std::max(1u, (n_pairs + n_pw * 32 - 1) / (n_pw * 32));
     if (kp_need > fm::kWcMaxKP) fail(FM_ERR_UNSUPPORTED, "too many populations for the W&C kernel (pairs per lane)");
     const size_t smem = multi ? fm::fm_wc_multi_cta_smem(G, A) : fm::fm_wc_cta_smem(G);
     if (smem > 200 * 1024) fail(FM_ERR_UNSUPPORTED, "too many populations for the W&C kernel's staging");
     W.n_pair_warps = n_pw;
-    const uint32_t threads = (n_pw + 1) * 32;
     const uint32_t blocks = std::max<uint32_t>(1, std::min<uint32_t>(n_seg, 8u * sm_count(m->device)));
     Timer tm;
     tm.start();
-    auto launch = [&](auto kern) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<blocks, threads, smem, stream()>>>(W);
-    };
     if (multi) {
+        const uint32_t threads = (n_pw + 1) * 32;
+        auto launch = [&](auto kern) {
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<blocks, threads, smem, stream()>>>(W);
+        };
         if (kp_need <= 1) launch(fm::fm_k_wc_multi<1>);
         else if (kp_need <= 2) launch(fm::fm_k_wc_multi<2>);
         else if (kp_need <= 4) launch(fm::fm_k_wc_multi<4>);
         else launch(fm::fm_k_wc_multi<8>);
-    } else if (kp_need <= 1) launch(fm::fm_k_wc<1>);
-    else if (kp_need <= 2) launch(fm::fm_k_wc<2>);
-    else if (kp_need <= 4) launch(fm::fm_k_wc<4>);
-    else launch(fm::fm_k_wc<8>);
-    CK(cudaGetLastError());
-    g_launches++;
+        CK(cudaGetLastError());
+        g_launches++;
+    } else {
+        const fm::WcTables T = wc_tables(p);
+        if (n_pairs) {
+            auto launch = [&](auto kern) {
+                CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kern<<<blocks, n_pw * 32, smem, stream()>>>(W, T);
+            };
+            static const uint32_t su = env_u32("FM_WC_SITES_PER_STEP", 2);
+            if (kp_need <= 1 && su >= 2) launch(fm::fm_k_wc_pairs<1, 2>);
+            else if (kp_need <= 1) launch(fm::fm_k_wc_pairs<1, 1>);
+            else if (kp_need <= 2) launch(fm::fm_k_wc_pairs<2, 1>);
+            else if (kp_need <= 4) launch(fm::fm_k_wc_pairs<4, 1>);
+            else launch(fm::fm_k_wc_pairs<8, 1>);
+            CK(cudaGetLastError());
+            g_launches++;
+        }
+        const uint32_t ob = std::max<uint32_t>(1, std::min<uint32_t>((n_seg + 3) / 4, 16u * sm_count(m->device)));
+        fm::fm_k_wc_overall<<<ob, 128, 0, stream()>>>(W, T);
+        CK(cudaGetLastError());
+        g_launches++;
+    }
     DevBuf<double> d_oo(nw * 2), d_op(nw * std::max(n_pairs, 1u) * 2);
     DevBuf<uint64_t> d_os(nw), d_on(nw * std::max(n_pairs, 1u));
     {
@@ -2648,6 +3010,25 @@ fm_fst_estimate insufficient_estimate(uint64_t sites) {
     return e;
 }
 }  // namespace
+
+// test hook for the FP64 building blocks of the W&C kernels (fm_wc.cuh): y[i] = fm_recip_rn(b[i]),
+// q[i] = fm_div_recip(a[i], b[i], RN(1 / b[i])); host arrays
+fm_status fm_wc_arith_probe(const double *a, const double *b, double *y, double *q, size_t n) {
+    return guarded([&] {
+        if (n && (!a || !b || !y || !q)) fail(FM_ERR_INVALID_ARG, "NULL argument");
+        require_device();
+        CK(cudaSetDevice(t_device));
+        if (!n) return;
+        DevBuf<double> da(n), db(n), dy(n), dq(n);
+        da.upload(a, n);
+        db.upload(b, n);
+        fm::fm_k_wc_arith_probe<<<1024, 256, 0, stream()>>>(da.p, db.p, dy.p, dq.p, n);
+        CK(cudaGetLastError());
+        dy.download(y, n);
+        dq.download(q, n);
+        CK(cudaStreamSynchronize(stream()));
+    });
+}
 
 fm_status fm_fst_estimate_from_sums(double sum_a, double sum_b, uint64_t informative_sites,
                                     uint64_t sites_attempted, fm_fst_estimate *out) {

@@ -15,6 +15,7 @@
 #include "../../include/ferromic_gpu.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -81,7 +82,74 @@ void pack_range_generic(const uint8_t *rows, const uint64_t *missing, uint64_t n
     }
 }
 
+// 64 consecutive bits of the bitmap starting at absolute bit index `bit`, branch-free: two unaligned 8-byte
+// reads at the bit's byte.  `safe_bytes` = bytes of the bitmap that may be read; the caller keeps the last
+// words of the matrix on the careful path.
+inline uint64_t bitmap_u64_fast(const uint8_t *bm8, uint64_t bit) {
+    const uint64_t byte = bit >> 3;
+    const uint32_t s = (uint32_t)(bit & 7);
+    uint64_t lo, hi;
+    std::memcpy(&lo, bm8 + byte, 8);
+    std::memcpy(&hi, bm8 + byte + 8, 8);
+    return (lo >> s) | ((hi << 1) << (63 - s));
+}
+
 #if FM_X86
+// AVX-512BW: one vptestmb turns 64 cells into 64 allele bits, vpmovb2m gives the in-band sign bits.
+__attribute__((target("avx512f,avx512bw"))) void pack_range_avx512(const uint8_t *rows, const uint64_t *missing,
+                                                                   uint64_t n_bitmap_words, int mode, size_t first_row,
+                                                                   size_t r_lo, size_t r_hi, size_t stride,
+                                                                   uint32_t *abits, uint32_t *cbits) {
+    const size_t rw = (stride + 31) / 32;
+    const size_t n64 = stride / 64;
+    const uint8_t *bm8 = reinterpret_cast<const uint8_t *>(missing);
+    const uint64_t bm_bytes = n_bitmap_words * 8;
+    for (size_t r = r_lo; r < r_hi; ++r) {
+        const uint8_t *src = rows + r * stride;
+        uint32_t *a = abits + r * rw;
+        uint32_t *c = cbits ? cbits + r * rw : nullptr;
+        const uint64_t bit0 = (uint64_t)(first_row + r) * stride;
+        // the fast bitmap read touches 16 bytes from the bit's byte: stay clear of the buffer's end
+        const bool bm_fast = mode != FM_MISSING_BITMAP || ((bit0 + stride) >> 3) + 16 <= bm_bytes;
+        size_t k = 0;
+        if (bm_fast) {
+            for (; k < n64; ++k) {
+                const __m512i x = _mm512_loadu_si512(src + k * 64);
+                const uint64_t nz = _mm512_test_epi8_mask(x, x);
+                uint64_t called = ~0ull;
+                if (mode == FM_MISSING_BITMAP)
+                    called = ~bitmap_u64_fast(bm8, bit0 + k * 64);
+                else if (mode == FM_MISSING_IN_BAND)
+                    called = ~(uint64_t)_mm512_movepi8_mask(x);
+                const uint64_t av = nz & called;
+                a[2 * k] = (uint32_t)av;
+                a[2 * k + 1] = (uint32_t)(av >> 32);
+                if (c) {
+                    c[2 * k] = (uint32_t)called;
+                    c[2 * k + 1] = (uint32_t)(called >> 32);
+                }
+            }
+        }
+        // what is left of the row (everything, near the end of the bitmap): 32 cells at a time, scalar tail
+        for (size_t w = 2 * k; w < rw; ++w) {
+            const size_t c0 = w * 32, n = std::min<size_t>(32, stride - c0);
+            uint32_t nz = 0, neg = 0;
+            for (size_t i = 0; i < n; ++i) {
+                nz |= (uint32_t)(src[c0 + i] != 0) << i;
+                neg |= (uint32_t)(src[c0 + i] >> 7) << i;
+            }
+            const uint32_t valid = n == 32 ? 0xffffffffu : ((1u << n) - 1u);
+            uint32_t called = valid;
+            if (mode == FM_MISSING_BITMAP)
+                called = ~bitmap_u32(missing, bit0 + c0, n_bitmap_words) & valid;
+            else if (mode == FM_MISSING_IN_BAND)
+                called = ~neg & valid;
+            a[w] = nz & called;
+            if (c) c[w] = called;
+        }
+    }
+}
+
 __attribute__((target("avx2"))) void pack_range_avx2(const uint8_t *rows, const uint64_t *missing,
                                                      uint64_t n_bitmap_words, int mode, size_t first_row, size_t r_lo,
                                                      size_t r_hi, size_t stride, uint32_t *abits, uint32_t *cbits) {
@@ -147,11 +215,17 @@ const char *fm_host_pack_rows(const uint8_t *rows, const uint64_t *missing_whole
     T = (unsigned)std::min<size_t>(std::min<unsigned>(T, 64), std::max<size_t>(1, n_rows * stride / (1u << 20)));
 #if FM_X86
     const bool avx2 = __builtin_cpu_supports("avx2");
+    const bool avx512 = __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f") && !getenv("FM_PACK_NO_AVX512");
 #else
     const bool avx2 = false;
 #endif
     auto work = [&](size_t lo, size_t hi) {
 #if FM_X86
+        if (avx512) {
+            pack_range_avx512(rows, missing_whole_or_null, n_bitmap_words, missing_mode, first_row, lo, hi, stride,
+                              allele_bits, called_bits_or_null);
+            return;
+        }
         if (avx2) {
             pack_range_avx2(rows, missing_whole_or_null, n_bitmap_words, missing_mode, first_row, lo, hi, stride,
                             allele_bits, called_bits_or_null);

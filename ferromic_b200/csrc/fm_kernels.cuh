@@ -1339,6 +1339,279 @@ fm_k_plane_pass_seq(const __grid_constant__ SeqParams P) {
     }
 }
 
+// ------------------------------------------------------------------------------ plane pass, segment table
+// fm_k_plane_pass_tab: the same persistent per-warp-ring pass over an arbitrary LIST of plane segments read
+// from a descriptor table in device memory.  Two uses:
+//   * unit = one segment: many (region, group) pairs -- e.g. the per-region matrices the CLI builds one after
+//     the other (process.rs:2169), each with its own population -- share ONE launch, so 64 small regions stream
+//     at the rate of one large one instead of paying 64 launches + ramp-ups (cfg1 x 64);
+//   * unit = two segments over the same sites (gpu == 2): a warp streams the batch of group 1, keeps its
+//     counts in registers, streams the same batch of group 2 and evaluates the Hudson components of the 32
+//     sites in place (stats.rs:3179-3278 / 1554-1623) -- both groups' counts and summary partials AND the
+//     Hudson partials from one sweep of the planes, each group streamed with its own step geometry.
+struct TabSeg {
+    GroupPlanes g;
+    DivEpilogue div;
+    uint32_t rounds;          // rounds of (32/lps) sites per pipeline step for this segment's row width
+    uint32_t v_lo, v_hi;      // site range analysed
+    uint32_t b_lo;            // first batch of the range (v_lo / 32)
+    uint32_t n_sites_total;   // rows available in this segment's planes
+    uint32_t pad;
+};
+
+struct TabParams {
+    const TabSeg *segs;            // [n_units * gpu]
+    const uint32_t *unit_prefix;   // [n_units + 1]: batches of the units before u (unit u has prefix[u+1]-prefix[u])
+    uint32_t n_units, gpu;         // gpu = segments (groups) per unit: 1 or 2
+    const HudsonEpilogue *hud;     // [n_units] Hudson epilogues (gpu == 2) or nullptr
+    PassGeom geom;                 // lps, n_stages, stage_bytes, warps, warp_smem_bytes, n_batches (total), counters
+};
+
+template <int LG, bool HC>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 1)
+fm_k_plane_pass_tab(const __grid_constant__ TabParams P) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[kWarpsPerCta * kMaxStages];
+    __shared__ uint32_t batch_ring[kWarpsPerCta * kBatchRing];
+    static_assert(LG < 5, "column-chunked rows take the per-group kernel");
+    constexpr uint32_t LPS = 1u << LG;
+    constexpr uint32_t SPS = 32u >> LG;
+    constexpr uint32_t NPL = HC ? 2u : 1u;
+    constexpr uint32_t FULL = 0xffffffffu;
+
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = __shfl_sync(FULL, threadIdx.x >> 5, 0);
+    const PassGeom &G = P.geom;
+    const uint32_t n_stages = G.n_stages;
+    const uint32_t stage_bytes = G.stage_bytes;
+    const uint32_t n_batches = G.n_batches;  // whole launch
+    const uint32_t gpu = P.gpu;
+
+    const uint32_t smem_base = fm_smem_u32(smem_raw) + warp * G.warp_smem_bytes;
+    const uint32_t bar_base = fm_smem_u32(bars + warp * kMaxStages);
+    uint32_t *my_ring = batch_ring + warp * kBatchRing;
+    if (lane == 0) {
+        for (uint32_t s = 0; s < n_stages; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_base + 8u * s));
+        fm_fence_mbar_init();
+    }
+    __syncwarp();
+
+    uint32_t sched_j = blockIdx.x % kSchedCounters, sched_tried = 0;
+    auto range_lo = [&](uint32_t j) { return (uint32_t)(((uint64_t)n_batches * j) / kSchedCounters); };
+    uint32_t prefetched = 0;
+    if (lane == 0) prefetched = atomicAdd(G.batch_counter + sched_j * kSchedStrideWords, 1u);
+    auto claim = [&]() -> uint32_t {
+        for (;;) {
+            const uint32_t idx = __shfl_sync(FULL, prefetched, 0);
+            const uint32_t lo = range_lo(sched_j), hi = range_lo(sched_j + 1);
+            if (idx < hi - lo) {
+                if (lane == 0) prefetched = atomicAdd(G.batch_counter + sched_j * kSchedStrideWords, 1u);
+                return lo + idx;
+            }
+            if (++sched_tried == kSchedCounters) return 0xffffffffu;
+            sched_j = (sched_j + 1 == kSchedCounters) ? 0 : sched_j + 1;
+            if (lane == 0) prefetched = atomicAdd(G.batch_counter + sched_j * kSchedStrideWords, 1u);
+        }
+    };
+    // unit of a launch-wide batch index: last u with prefix[u] <= gb (warp-uniform)
+    auto unit_of = [&](uint32_t gb) -> uint32_t {
+        uint32_t lo = 0, hi = P.n_units;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(P.unit_prefix + mid) <= gb) lo = mid; else hi = mid;
+        }
+        return lo;
+    };
+
+    // ---- issue side: context of the (unit batch, group) whose steps are being issued
+    uint32_t iss_ring = 0, iss_k = 0, iss_spb = 0, iss_stage = 0, iss_batch = 0;
+    uint32_t iss_w16 = 0, iss_step_sites = 1, iss_g = 0, iss_unit = 0, iss_b = 0, iss_nst = 0;
+    const uint4 *iss_allele = nullptr, *iss_called = nullptr;
+    bool iss_live = false;
+    auto load_iss_seg = [&]() {
+        const TabSeg &S = P.segs[iss_unit * gpu + iss_g];
+        iss_w16 = S.g.wq * 16u;
+        iss_step_sites = SPS * S.rounds;
+        iss_spb = LPS / S.rounds;
+        iss_nst = S.n_sites_total;
+        iss_allele = S.g.allele;
+        iss_called = S.g.called;
+    };
+    auto issue = [&](uint32_t stage) {  // lane 0 only
+        const uint32_t bar = bar_base + 8u * stage;
+        const uint32_t dst = smem_base + stage * stage_bytes;
+        const uint32_t v0 = iss_b * 32 + iss_k * iss_step_sites;
+        const uint32_t nsites = (v0 < iss_nst) ? min(iss_step_sites, iss_nst - v0) : 0u;
+        if (nsites == 0) {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+            return;
+        }
+        const uint32_t bytes = nsites * iss_w16;
+        const uint32_t slot = iss_step_sites * iss_w16;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * NPL) : "memory");
+        const size_t off = (size_t)v0 * iss_w16;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(reinterpret_cast<const uint8_t *>(iss_allele) + off), "r"(bytes), "r"(bar)
+                     : "memory");
+        if constexpr (HC)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             dst + slot),
+                         "l"(reinterpret_cast<const uint8_t *>(iss_called) + off), "r"(bytes), "r"(bar)
+                         : "memory");
+    };
+    auto issue_next = [&]() {
+        if (iss_k == iss_spb) {
+            if (iss_live && iss_g + 1 < gpu) {  // next group of the same unit batch
+                ++iss_g;
+                iss_k = 0;
+                load_iss_seg();
+            } else {
+                if (iss_ring != 0 && iss_batch >= n_batches) return;  // scheduler drained
+                iss_batch = claim();
+                iss_k = 0;
+                if (lane == 0) my_ring[iss_ring & (kBatchRing - 1)] = iss_batch;
+                ++iss_ring;
+                if (iss_batch >= n_batches) {
+                    iss_spb = 0;
+                    iss_live = false;
+                    return;
+                }
+                iss_live = true;
+                iss_unit = unit_of(iss_batch);
+                iss_g = 0;
+                load_iss_seg();
+                iss_b = P.segs[iss_unit * gpu].b_lo + (iss_batch - __ldg(P.unit_prefix + iss_unit));
+            }
+        }
+        if (lane == 0) issue(iss_stage);
+        ++iss_k;
+        iss_stage = (iss_stage + 1 == n_stages) ? 0 : iss_stage + 1;
+    };
+    for (uint32_t s = 0; s < n_stages; ++s) issue_next();
+    __syncwarp();
+
+    const uint32_t slot_in_round = lane >> LG;
+    const uint32_t phase = lane & (LPS - 1);
+    const uint32_t xfer_from = (lane & (SPS - 1)) << LG;
+    const uint32_t xfer_round = lane >> (5 - LG);
+
+    uint32_t con_ring = 0, stage = 0, parity = 0;
+    for (;;) {
+        const uint32_t gb = my_ring[con_ring & (kBatchRing - 1)];
+        ++con_ring;
+        if (gb >= n_batches) break;
+        const uint32_t unit = unit_of(gb);
+        const uint32_t bl = gb - __ldg(P.unit_prefix + unit);  // batch inside the unit's range
+        uint32_t alt_g0 = 0, cnt_g0 = 0, alt_g1 = 0, cnt_g1 = 0;
+        uint32_t b = 0, u_vlo = 0, u_vhi = 0;
+        for (uint32_t g = 0; g < gpu; ++g) {
+            const TabSeg &S = P.segs[unit * gpu + g];
+            const uint32_t w = S.g.wq, w16 = w * 16u, rounds = S.rounds;
+            const uint32_t step_sites = SPS * rounds, spb = LPS / rounds;
+            const uint32_t nit = (w + LPS - 1) / LPS;
+            const uint32_t nfull = nit - 1, last_cols = w - nfull * LPS;
+            const uint32_t pb = step_sites * w16;
+            const uint32_t nst = S.n_sites_total;
+            b = S.b_lo + bl;
+            u_vlo = S.v_lo;
+            u_vhi = S.v_hi;
+            uint32_t site_ac = 0;
+            for (uint32_t k = 0; k < spb; ++k) {
+                {
+                    const uint32_t bar = bar_base + 8u * stage;
+                    uint32_t ok;
+                    do {
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\t"
+                            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                            "selp.u32 %0, 1, 0, p;\n\t}"
+                            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+                    } while (!ok);
+                }
+                const uint32_t sbase = smem_base + stage * stage_bytes;
+                const uint32_t v0 = b * 32 + k * step_sites;
+                auto round_body = [&](uint32_t r) {
+                    const uint32_t site_local = r * SPS + slot_in_round;
+                    const bool live = (v0 + site_local) < nst;
+                    const uint32_t ra = sbase + site_local * w16;
+                    uint32_t a = 0, c = 0;
+                    if (live) {
+                        uint32_t p = ra + phase * 16u;
+#pragma unroll 2
+                        for (uint32_t j = 0; j < nfull; ++j) {
+                            a += fm_popc4(fm_lds128(p));
+                            if constexpr (HC) c += fm_popc4(fm_lds128(p + pb));
+                            p += LPS * 16u;
+                        }
+                        if (phase < last_cols) {
+                            a += fm_popc4(fm_lds128(p));
+                            if constexpr (HC) c += fm_popc4(fm_lds128(p + pb));
+                        }
+                    }
+                    uint32_t ac = HC ? (a | (c << 16)) : a;
+#pragma unroll
+                    for (uint32_t o = LPS >> 1; o > 0; o >>= 1) ac += __shfl_xor_sync(FULL, ac, o);
+                    const uint32_t t = __shfl_sync(FULL, ac, xfer_from);
+                    if (xfer_round == k * rounds + r) site_ac = t;
+                };
+                if (rounds == 1) {
+                    round_body(0);
+                } else {
+                    for (uint32_t r = 0; r < rounds; r += 2) {
+                        round_body(r);
+                        round_body(r + 1);
+                    }
+                }
+                __syncwarp();
+                issue_next();
+                stage = (stage + 1 == n_stages) ? 0 : stage + 1;
+                parity ^= (stage == 0);
+            }
+            // ---- group epilogue: lane i <-> site 32b + i (counts, summary partials, optional tracks)
+            const uint32_t alt = HC ? (site_ac & 0xffffu) : site_ac;
+            const uint32_t cnt = HC ? (site_ac >> 16) : S.g.cap;
+            if (g == 0) {
+                alt_g0 = alt;
+                cnt_g0 = cnt;
+            } else {
+                alt_g1 = alt;
+                cnt_g1 = cnt;
+            }
+            const uint32_t v = b * 32 + lane;
+            const bool valid = (v >= S.v_lo) && (v < S.v_hi);
+            if (S.div.part_pi) {
+                double pi_part = 0.0;
+                uint32_t seg = 0, unc = 0;
+                const uint32_t flags = S.div.site_flags ? __ldg(S.div.site_flags + bl) : 0u;
+                if (valid) fm_div_site(S.div, v, S.v_lo, cnt, alt, (flags >> lane) & 1u, pi_part, seg, unc);
+                const double s_pi = fm_warp_sum(pi_part);
+                const uint32_t s_u = fm_warp_sum_u(seg | (unc << 16));
+                if (lane == 0) {
+                    S.div.part_pi[bl] = s_pi;
+                    S.div.part_u[2 * bl] = s_u & 0xffffu;
+                    S.div.part_u[2 * bl + 1] = s_u >> 16;
+                }
+            }
+        }
+        if (gpu == 2 && P.hud) {  // ---- Hudson components of the batch from both groups' counts
+            const HudsonEpilogue &H = P.hud[unit];
+            const uint32_t v = b * 32 + lane;
+            HudsonAcc acc{0.0, 0.0, 0.0, 0.0, 0.0, 0u, 0u, 0u};
+            if (v >= u_vlo && v < u_vhi) fm_hudson_contrib(H, v, u_vlo, cnt_g0, alt_g0, cnt_g1, alt_g1, acc);
+            const double r0 = fm_warp_sum(acc.num), r1 = fm_warp_sum(acc.den), r2 = fm_warp_sum(acc.dxy),
+                         r3 = fm_warp_sum(acc.pi1), r4 = fm_warp_sum(acc.pi2);
+            const uint32_t u01 = fm_warp_sum_u(acc.skipped | (acc.unc1 << 8) | (acc.unc2 << 16));
+            if (lane == 0) {
+                double *pd = H.part_d + (size_t)bl * 5;
+                pd[0] = r0; pd[1] = r1; pd[2] = r2; pd[3] = r3; pd[4] = r4;
+                uint32_t *pu = H.part_u + (size_t)bl * 3;
+                pu[0] = u01 & 0xffu; pu[1] = (u01 >> 8) & 0xffu; pu[2] = u01 >> 16;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------ light kernels
 // Same per-site functions evaluated from cached count arrays (8 B per site and group).
 // One warp per batch of 32 sites so that the per-batch partials are bit-identical to the
@@ -1424,6 +1697,42 @@ fm_k_reduce_partials(const double *__restrict__ pd, int nd, const uint32_t *__re
         }
         acc = fm_warp_sum_u(acc);
         if (lane == 0) out_u[(size_t)s * nu + col] = acc;
+    }
+}
+
+// The same fold for many units at once (fm_k_plane_pass_tab launches): entry e = (first partial of the unit in
+// the shared partial arrays, the unit's first global batch, its batch count, the global super-batch index); one
+// warp per entry, the association of fm_k_reduce_partials -- a unit reduced here gives the bits it would give alone.
+__global__ void __launch_bounds__(128)
+fm_k_reduce_partials_tab(const double *__restrict__ pd, int nd, const uint32_t *__restrict__ pu, int nu,
+                         const uint4 *__restrict__ ents, uint32_t n_ent, double *__restrict__ out_d,
+                         uint64_t *__restrict__ out_u) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (e >= n_ent) return;
+    const uint4 E = ents[e];
+    constexpr uint32_t per_lane = kSuperBatches / 32;
+    const uint64_t g0 = (uint64_t)E.w * kSuperBatches + (uint64_t)lane * per_lane;
+    const uint64_t b_lo = E.y, b_hi = (uint64_t)E.y + E.z;
+    for (int col = 0; col < nd; ++col) {
+        double acc = 0.0;
+#pragma unroll
+        for (uint32_t i = 0; i < per_lane; ++i) {
+            const uint64_t b = g0 + i;
+            if (b >= b_lo && b < b_hi) acc += pd[((size_t)E.x + (b - b_lo)) * nd + col];
+        }
+        acc = fm_warp_sum(acc);
+        if (lane == 0) out_d[(size_t)e * nd + col] = acc;
+    }
+    for (int col = 0; col < nu; ++col) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < per_lane; ++i) {
+            const uint64_t b = g0 + i;
+            if (b >= b_lo && b < b_hi) acc += pu[((size_t)E.x + (b - b_lo)) * nu + col];
+        }
+        acc = fm_warp_sum_u(acc);
+        if (lane == 0) out_u[(size_t)e * nu + col] = acc;
     }
 }
 

@@ -34,7 +34,7 @@
 namespace fm {
 
 constexpr uint32_t kWcSegSites = 1024;   // segment granularity (== 32 batches)
-constexpr uint32_t kWcMaxPairWarps = 11; // + 1 overall warp = 384 threads (3 CTAs per SM at <= 56 registers)
+constexpr uint32_t kWcMaxPairWarps = 11; // 352 threads per CTA (>= the 325 pairs of 26 populations)
 constexpr uint32_t kWcMaxKP = 8;         // pairs per lane (template parameter KP <= this)
 
 struct WcParams {
@@ -60,31 +60,100 @@ struct WcParams {
     uint32_t *part_pair_n;       // [n_seg][n_pairs]      informative sites per pair
 };
 
-__host__ __device__ inline size_t fm_wc_cta_smem(uint32_t G) {
-    // freq [32][G] double2 | cnts [32][G+1] uint2 | info [32] u32
-    return (size_t)32 * G * 16 + (size_t)32 * (G + 1) * 8 + 32 * 4 + 16;
+// a / b given y = RN(1 / b): Markstein's correction applied twice.  q0 = a*y is within 1.5 ulp, one
+// residual step makes it faithful, the second makes it the correctly rounded quotient (Markstein 1990; the
+// only excluded divisors have an all-ones significand, which integers, half-integers and their squares below
+// 2^52 never have).  tools/check_recip_div.c: 4e8 random cases, 0 differences from IEEE division.  The FP64
+// pipe sees 5 operations instead of the ~25-instruction division sequence with its slow-path branch.
+__device__ __forceinline__ double fm_div_recip(double a, double b, double y) {
+    double q = a * y;
+    double r = __fma_rn(-b, q, a);
+    q = __fma_rn(r, y, q);
+    r = __fma_rn(-b, q, a);
+    return __fma_rn(r, y, q);
 }
 
-template <int KP>
-__global__ void __launch_bounds__(384, 3)
-fm_k_wc(const WcParams P) {
+struct WcTables {            // indexed by an integer n = 0 .. n_max (n_max >= largest n_i + n_j of any pair)
+    const double *inv_n;     // RN(1 / n)
+    const double *inv_2nb2;  // RN(1 / (2 * (n/2) * (n/2))) = RN(2 / n^2): the c^2 divisor of a pair with n_i + n_j = n
+    uint32_t n_max;
+};
+
+__host__ __device__ inline size_t fm_wc_cta_smem(uint32_t G) {
+    // val [32][G] 4 x f64 (p0, p1, n, alt) | cnts [32][G+1] uint2 | info [32] u32
+    return (size_t)32 * G * 32 + (size_t)32 * (G + 1) * 8 + 32 * 4 + 16;
+}
+
+// RN(1 / b) for a normal b far from the exponent limits (here b = 1 - c^2 in (0, 1]): hardware seed
+// (MUFU.RCP64H, ~23 bits), two Newton steps and one residual correction of the then faithful estimate.  Branch
+// free; tests/test_gpu_wc_arith.py compares it with IEEE 1.0 / b over 2^28 divisors.
+__device__ __forceinline__ double fm_recip_rn(double b) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+    double e = __fma_rn(-b, y, 1.0);
+    y = __fma_rn(y, e, y);
+    e = __fma_rn(-b, y, 1.0);
+    y = __fma_rn(y, e, y);
+    e = __fma_rn(-b, y, 1.0);
+    return __fma_rn(y, e, y);
+}
+
+// One (pair, site) evaluation of calculate_variance_components with r = 2 (stats.rs:2034-2127), summed over
+// both alleles (stats.rs:1939-1983).  Only called for a pair that is polymorphic at the site, so both alleles
+// are present among the samples (has0 && has1) and n_i + n_j >= 3.  Straight-line code: the two alleles (and,
+// in the caller, SU sites) are independent dependency chains the FP64 pipe can interleave.
+// vi / vj: (p0, p1, n, alt) of the two groups as doubles.
+__device__ __forceinline__ void fm_wc_pair_site(const double4 vi, const double4 vj, uint32_t nsum, const WcTables &T,
+                                                double &pa, double &pb) {
+    const double n1 = vi.z, n2 = vj.z;
+    const double nsd = n1 + n2;         // exact: integers
+    const double n_bar = nsd / 2.0;     // exact
+    const double nbm1 = n_bar - 1.0;    // exact
+    const double r_nsd = __ldg(T.inv_n + nsum);
+    const double r_nbar = 2.0 * r_nsd;                        // RN(1 / n_bar), exact scaling
+    const double r_nbm1 = 2.0 * __ldg(T.inv_n + (nsum - 2));  // RN(1 / (n_bar - 1))
+    // size-only terms
+    const double d1 = n1 - n_bar, d2 = n2 - n_bar;
+    const double ssd = d1 * d1 + d2 * d2;  // 0.0 + d1*d1 == d1*d1 (never -0)
+    const double c_squared = fm_div_recip(ssd, 2.0 * n_bar * n_bar, __ldg(T.inv_2nb2 + nsum));
+    const double aden = 1.0 - c_squared;   // c_squared / (r - 1) with r - 1 == 1
+    const double raden = 1.0 / aden;
+    const double ratio = fm_div_recip(n_bar, nbm1, r_nbm1);
+    const double asd = vi.w + vj.w;     // exact
+    // allele 0, then allele 1 (ascending order, stats.rs:1859)
+    const double gp0 = fm_div_recip(nsd - asd, nsd, r_nsd), gp1 = fm_div_recip(asd, nsd, r_nsd);
+    const double q10 = vi.x - gp0, q20 = vj.x - gp0, q11 = vi.y - gp1, q21 = vj.y - gp1;
+    const double num0 = n1 * q10 * q10 + n2 * q20 * q20;  // 0.0 + (n1*q1)*q1, then + (n2*q2)*q2
+    const double num1 = n1 * q11 * q11 + n2 * q21 * q21;
+    const double s20 = fm_div_recip(num0, n_bar, r_nbar), s21 = fm_div_recip(num1, n_bar, r_nbar);
+    const double x0 = gp0 * (1.0 - gp0) - (1.0 / 2.0) * s20, x1 = gp1 * (1.0 - gp1) - (1.0 / 2.0) * s21;
+    const double ta0 = fm_div_recip(s20 - fm_div_recip(x0, nbm1, r_nbm1), aden, raden);
+    const double ta1 = fm_div_recip(s21 - fm_div_recip(x1, nbm1, r_nbm1), aden, raden);
+    pa = ta0 + ta1;  // 0.0 + ta0 == ta0 up to the sign of a zero
+    pb = ratio * x0 + ratio * x1;
+}
+
+// ---- K4 pairs: every warp of the CTA is a pair warp (lane = pair, KP pairs per lane in registers).
+// SU sites are evaluated side by side (independent dependency chains for the FP64 pipe) and then added to the
+// pair's running sums in site order.
+template <int KP, int SU>
+__global__ void __launch_bounds__(352, (KP <= 2 && SU == 1) ? 3 : (KP <= 4 ? 2 : 1))
+fm_k_wc_pairs(const WcParams P, const WcTables T) {
     extern __shared__ __align__(16) uint8_t wc_smem[];
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
     const uint32_t lane = tid & 31, warp = tid >> 5;
     const uint32_t G = P.G, G1 = P.G + 1, NP = P.n_pairs;
-    const uint32_t NW = P.n_pair_warps;
-    double2 *freq = reinterpret_cast<double2 *>(wc_smem);                  // [32][G]: (p allele 0, p allele 1)
-    uint2 *cnts = reinterpret_cast<uint2 *>(freq + (size_t)32 * G);        // [32][G1]: (alt, called)
-    uint32_t *info = reinterpret_cast<uint32_t *>(cnts + (size_t)32 * G1); // [32]: bit0 has0, bit1 has1
-    const bool overall_warp = warp == NW;
+    const uint32_t NW = nt >> 5;
+    double4 *val = reinterpret_cast<double4 *>(wc_smem);                   // [32][G]: p0, p1, n, alt as doubles
+    uint2 *cnts = reinterpret_cast<uint2 *>(val + (size_t)32 * G);         // [32][G1]: (alt, called)
+    uint32_t *info = reinterpret_cast<uint32_t *>(cnts + (size_t)32 * G1); // [32]: != 0 when any allele is present
 
-    // pairs owned by this lane (registers)
     uint32_t pi[KP], pj[KP];
     bool pvalid[KP];
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
         const uint32_t p = warp * 32 + lane + (uint32_t)k * NW * 32;
-        pvalid[k] = !overall_warp && p < NP;
+        pvalid[k] = p < NP;
         pi[k] = pvalid[k] ? __ldg(P.pair_i + p) : 0u;
         pj[k] = pvalid[k] ? __ldg(P.pair_j + p) : 0u;
     }
@@ -93,204 +162,227 @@ fm_k_wc(const WcParams P) {
         const uint32_t lo = P.seg_lo[si], hi = P.seg_hi[si];
         double acc_a[KP], acc_b[KP];
         uint32_t acc_n[KP];
-        // size-only terms of the lane's pairs, reused while (n_i, n_j) repeat from site to site
-        uint32_t c_ni[KP], c_nj[KP];
-        double c_nbar[KP], c_aden[KP], c_ratio[KP];
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
             acc_a[k] = 0.0;
             acc_b[k] = 0.0;
             acc_n[k] = 0;
-            c_ni[k] = 0xffffffffu;
-            c_nj[k] = 0xffffffffu;
-            c_nbar[k] = c_aden[k] = c_ratio[k] = 0.0;
         }
-        double sum_a = 0.0, sum_b = 0.0;  // overall warp: site order, identical in every lane
-        uint32_t n_informative = 0;
         for (uint32_t v0 = lo; v0 < hi; v0 += 32) {
             const uint32_t nb = min(32u, hi - v0);
             __syncthreads();  // previous batch fully consumed
             // ---- stage counts (lane = site: coalesced), one warp per group
-            for (uint32_t g = warp; g < G1; g += (nt >> 5))
+            for (uint32_t g = warp; g < G1; g += NW)
                 if (lane < nb)
                     cnts[lane * G1 + g] = make_uint2(__ldg(P.alt[g] + v0 + lane), __ldg(P.cnt[g] + v0 + lane));
             __syncthreads();
-            // ---- per-group frequencies: one division per (site, group, allele)
-            for (uint32_t i = tid; i < nb * G; i += nt) {
+            // ---- per-(site, group) values: the allele frequencies are divided once per site (not per pair)
+            for (uint32_t i = tid; i < 32 * G; i += nt) {
                 const uint32_t s = i / G, g = i - s * G;
-                const uint2 c = cnts[s * G1 + g];
-                if (c.y > 0) freq[s * G + g] = make_double2((double)(c.y - c.x) / (double)c.y, (double)c.x / (double)c.y);
+                double4 o = make_double4(0.0, 0.0, 1.0, 0.0);  // sites past the segment end: harmless dummies
+                if (s < nb) {
+                    const uint2 c = cnts[s * G1 + g];
+                    o = make_double4(0.0, 0.0, 0.0, 0.0);
+                    if (c.y > 0) {
+                        const double nd = (double)c.y, ad = (double)c.x;
+                        const double y = __ldg(T.inv_n + c.y);
+                        o = make_double4(fm_div_recip((double)(c.y - c.x), nd, y), fm_div_recip(ad, nd, y), nd, ad);
+                    }
+                }
+                val[s * G + g] = o;
             }
             // ---- alleles present over ALL samples, members or not (stats.rs:1826-1837)
-            if (warp == 0 && lane < nb) {
+            if (warp == 0) {
                 uint32_t t_alt = 0, t_n = 0;
-                for (uint32_t g = 0; g < G1; ++g) {
-                    const uint2 c = cnts[lane * G1 + g];
-                    t_alt += c.x;
-                    t_n += c.y;
-                }
-                info[lane] = (t_n > t_alt ? 1u : 0u) | (t_alt > 0 ? 2u : 0u);
+                if (lane < nb)
+                    for (uint32_t g = 0; g < G1; ++g) {
+                        const uint2 c = cnts[lane * G1 + g];
+                        t_alt += c.x;
+                        t_n += c.y;
+                    }
+                info[lane] = (t_n > t_alt ? 1u : 0u) | (t_alt > 0 ? 2u : 0u);  // 0 past the segment end
             }
             __syncthreads();
-            if (overall_warp) {
-                // ---- overall components, one site per lane (calculate_variance_components,
-                // stats.rs:2034-2127, over the groups with data: stats.rs:1907-1918)
-                double site_a = 0.0, site_b = 0.0;
-                int state = 3;  // InsufficientDataForEstimation: no allele at all at this site
-                bool any = false;
-                if (lane < nb) {
-                    const uint2 *sc = cnts + lane * G1;
-                    const double2 *fr = freq + lane * G;
-                    const uint32_t inf = info[lane];
-                    const bool has0 = inf & 1u, has1 = inf & 2u;
-                    any = inf != 0;  // pop_sizes_populated (stats.rs:1919-1923, 1987)
-                    uint32_t m_alt = 0, m_n = 0, m_r = 0;
-                    for (uint32_t g = 0; g < G; ++g) {
-                        const uint2 c = sc[g];
-                        if (c.y > 0) {
-                            m_alt += c.x;
-                            m_n += c.y;
-                            m_r += 1;
-                        }
-                    }
-                    if (any && m_r >= 2) {  // fewer than two groups with data: no allele contributes
-                        const double r = (double)m_r;
-                        const double n_bar = (double)m_n / r;
-                        if (!((n_bar - 1.0) < 1e-9)) {
-                            const double gp0 = (double)(m_n - m_alt) / (double)m_n;
-                            const double gp1 = (double)m_alt / (double)m_n;
-                            double ssd = 0.0, ns0 = 0.0, ns1 = 0.0;  // sums in group order
-                            for (uint32_t g = 0; g < G; ++g) {
-                                const uint32_t n = sc[g].y;
-                                if (n > 0) {
-                                    const double nd = (double)n;
-                                    const double d = nd - n_bar;
-                                    ssd += d * d;
-                                    const double2 f = fr[g];
-                                    const double q0 = f.x - gp0, q1 = f.y - gp1;
-                                    ns0 += nd * q0 * q0;
-                                    ns1 += nd * q1 * q1;
-                                }
-                            }
-                            const double c_squared = ssd / (r * n_bar * n_bar);
-                            const double a_den = 1.0 - (c_squared / (r - 1.0));
-                            const double nb_ratio = n_bar / (n_bar - 1.0);
-                            const bool s_ok = (r - 1.0) > 1e-9 && n_bar > 1e-9;
-                            // sum over alleles in ascending order: allele 0 first (stats.rs:1859, 1939-1940)
-                            if (has0) {
-                                const double s2 = s_ok ? ns0 / ((r - 1.0) * n_bar) : 0.0;
-                                const double x = gp0 * (1.0 - gp0) - ((r - 1.0) / r) * s2;
-                                site_a += (s2 - (x / (n_bar - 1.0))) / a_den;
-                                site_b += nb_ratio * x;
-                            }
-                            if (has1) {
-                                const double s2 = s_ok ? ns1 / ((r - 1.0) * n_bar) : 0.0;
-                                const double x = gp1 * (1.0 - gp1) - ((r - 1.0) / r) * s2;
-                                site_a += (s2 - (x / (n_bar - 1.0))) / a_den;
-                                site_b += nb_ratio * x;
-                            }
-                        }
-                    }
-                    if (any) state = fm_fst_state(site_a, site_b);
-                    const uint32_t o = v0 + lane - P.out_base;
-                    if (P.site_state) P.site_state[o] = state;
-                    if (P.site_a) P.site_a[o] = site_a;
-                    if (P.site_b) P.site_b[o] = site_b;
-                    if (P.site_sizes)
-                        for (uint32_t g = 0; g < G; ++g) P.site_sizes[(size_t)o * G + g] = any ? sc[g].y : 0u;
-                }
-                // region sums in site order (stats.rs:2172-2184, 2222-2229)
-                const uint32_t any_mask = __ballot_sync(0xffffffffu, any);
-                for (uint32_t s = 0; s < nb; ++s) {
-                    const double a_s = __shfl_sync(0xffffffffu, site_a, s);
-                    const double b_s = __shfl_sync(0xffffffffu, site_b, s);
-                    if ((any_mask >> s) & 1u) {
-                        sum_a += a_s;
-                        sum_b += b_s;
-                        ++n_informative;
-                    }
-                }
-            } else {
-                // ---- pairwise components (r == 2), sites in order
-                for (uint32_t s = 0; s < nb; ++s) {
-                    const uint2 *sc = cnts + s * G1;
-                    const double2 *fr = freq + s * G;
-                    const uint32_t inf = info[s];
-                    const bool has0 = inf & 1u, has1 = inf & 2u, any = inf != 0;
+            // ---- pairwise components (r == 2), sites in order, SU at a time (nb <= 32, SU divides 32)
+            for (uint32_t s0 = 0; s0 < nb; s0 += SU) {
 #pragma unroll
-                    for (int k = 0; k < KP; ++k) {
-                        if (!pvalid[k]) continue;
+                for (int k = 0; k < KP; ++k) {
+                    if (!pvalid[k]) continue;
+                    double pa[SU], pb[SU];
+                    bool has[SU], poly[SU];
+                    uint32_t nsum[SU];
+                    bool any_poly = false;
+#pragma unroll
+                    for (int t = 0; t < SU; ++t) {
+                        const uint32_t s = s0 + t;  // < 32; sites past nb carry info == 0
+                        const uint2 *sc = cnts + s * G1;
                         const uint2 ci = sc[pi[k]], cj = sc[pj[k]];
-                        const uint32_t ni = ci.y, nj = cj.y;
-                        double pa = 0.0, pb = 0.0;
-                        const bool has = any && ni > 0 && nj > 0;  // stats.rs:1950-1952
-                        if (has) {
-                            const uint32_t asum = ci.x + cj.x, nsum = ni + nj;
-                            if (asum != 0 && asum != nsum) {  // polymorphic in this pair
-                                if (ni != c_ni[k] || nj != c_nj[k]) {
-                                    c_ni[k] = ni;
-                                    c_nj[k] = nj;
-                                    const double n1 = (double)ni, n2 = (double)nj;
-                                    const double n_bar = (double)nsum / 2.0;
-                                    const double d1 = n1 - n_bar, d2 = n2 - n_bar;
-                                    double ssd = 0.0;
-                                    ssd += d1 * d1;
-                                    ssd += d2 * d2;
-                                    const double c_squared = ssd / (2.0 * n_bar * n_bar);
-                                    c_nbar[k] = n_bar;
-                                    c_aden[k] = 1.0 - (c_squared / 1.0);
-                                    c_ratio[k] = n_bar / (n_bar - 1.0);
-                                }
-                                const double n_bar = c_nbar[k];
-                                if (!((n_bar - 1.0) < 1e-9)) {
-                                    const double n1 = (double)ni, n2 = (double)nj, nsd = (double)nsum;
-                                    const double2 fi = fr[pi[k]], fj = fr[pj[k]];
+                        has[t] = info[s] != 0 && s < nb && ci.y > 0 && cj.y > 0;  // stats.rs:1950-1952
+                        const uint32_t asum = ci.x + cj.x;
+                        nsum[t] = ci.y + cj.y;
+                        // polymorphic in this pair and n_bar - 1 >= 1e-9 (anything else adds exactly +0)
+                        poly[t] = has[t] && asum != 0 && asum != nsum[t] && nsum[t] > 2;
+                        any_poly = any_poly || poly[t];
+                        pa[t] = 0.0;
+                        pb[t] = 0.0;
+                    }
+                    if (SU == 1) {
+                        if (poly[0]) fm_wc_pair_site(val[s0 * G + pi[k]], val[s0 * G + pj[k]], nsum[0], T, pa[0], pb[0]);
+                    } else if (any_poly) {
+                        // evaluate all SU sites in one straight line (lanes that are not polymorphic at a site
+                        // run on clamped inputs and drop the result: under SIMT they would have waited anyway)
+                        double ea[SU], eb[SU];
 #pragma unroll
-                                    for (int u = 0; u < 2; ++u) {
-                                        if (u == 0 ? has0 : has1) {
-                                            const double gp = (double)(u == 0 ? nsum - asum : asum) / nsd;
-                                            const double q1 = (u == 0 ? fi.x : fi.y) - gp;
-                                            const double q2 = (u == 0 ? fj.x : fj.y) - gp;
-                                            double num = 0.0;
-                                            num += n1 * q1 * q1;
-                                            num += n2 * q2 * q2;
-                                            const double s2 = num / (1.0 * n_bar);
-                                            const double x = gp * (1.0 - gp) - (1.0 / 2.0) * s2;
-                                            pa += (s2 - (x / (n_bar - 1.0))) / c_aden[k];
-                                            pb += c_ratio[k] * x;
-                                        }
-                                    }
-                                }
+                        for (int t = 0; t < SU; ++t) {
+                            const double4 *sv = val + (s0 + t) * G;
+                            double4 vi = sv[pi[k]], vj = sv[pj[k]];
+                            const uint32_t ns = poly[t] ? nsum[t] : 4u;
+                            if (!poly[t]) {
+                                vi = make_double4(0.5, 0.5, 2.0, 1.0);
+                                vj = vi;
                             }
-                            acc_a[k] += pa;  // site order: stats.rs:2288-2289
-                            acc_b[k] += pb;
+                            fm_wc_pair_site(vi, vj, ns, T, ea[t], eb[t]);
+                        }
+#pragma unroll
+                        for (int t = 0; t < SU; ++t) {
+                            pa[t] = poly[t] ? ea[t] : 0.0;
+                            pb[t] = poly[t] ? eb[t] : 0.0;
+                        }
+                    }
+#pragma unroll
+                    for (int t = 0; t < SU; ++t) {
+                        if (has[t]) {  // site order: stats.rs:2288-2289
+                            acc_a[k] += pa[t];
+                            acc_b[k] += pb[t];
                             acc_n[k] += 1;
                         }
-                        if (P.pair_a) {
+                        if (P.pair_a && s0 + t < nb) {
                             const uint32_t p = warp * 32 + lane + (uint32_t)k * NW * 32;
-                            const size_t o = (size_t)(v0 + s - P.out_base) * NP + p;
-                            P.pair_a[o] = has ? pa : fm_nan();
-                            P.pair_b[o] = has ? pb : fm_nan();
+                            const size_t o = (size_t)(v0 + s0 + t - P.out_base) * NP + p;
+                            P.pair_a[o] = has[t] ? pa[t] : fm_nan();
+                            P.pair_b[o] = has[t] ? pb[t] : fm_nan();
                         }
                     }
                 }
             }
         }
-        if (overall_warp) {
-            if (lane == 0) {
-                P.part_overall[2 * (size_t)si] = sum_a;
-                P.part_overall[2 * (size_t)si + 1] = sum_b;
-                P.part_counts[si] = n_informative;
-            }
-        } else {
 #pragma unroll
-            for (int k = 0; k < KP; ++k) {
-                if (!pvalid[k]) continue;
-                const uint32_t p = warp * 32 + lane + (uint32_t)k * NW * 32;
-                P.part_pair[((size_t)si * NP + p) * 2] = acc_a[k];
-                P.part_pair[((size_t)si * NP + p) * 2 + 1] = acc_b[k];
-                P.part_pair_n[(size_t)si * NP + p] = acc_n[k];
+        for (int k = 0; k < KP; ++k) {
+            if (!pvalid[k]) continue;
+            const uint32_t p = warp * 32 + lane + (uint32_t)k * NW * 32;
+            P.part_pair[((size_t)si * NP + p) * 2] = acc_a[k];
+            P.part_pair[((size_t)si * NP + p) * 2 + 1] = acc_b[k];
+            P.part_pair_n[(size_t)si * NP + p] = acc_n[k];
+        }
+    }
+}
+
+// test hook: y[i] = fm_recip_rn(b[i]) and q[i] = fm_div_recip(a[i], b[i], RN(1 / b[i]))
+__global__ void fm_k_wc_arith_probe(const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ y,
+                                    double *__restrict__ q, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        y[i] = fm_recip_rn(b[i]);
+        q[i] = fm_div_recip(a[i], b[i], 1.0 / b[i]);
+    }
+}
+
+// ---- K4 overall: the all-population components, one WARP per segment, one site per lane (groups in order,
+// exactly as calculate_variance_components, stats.rs:2034-2127, over the groups with data: stats.rs:1907-1918),
+// then the 32 site values are added in site order (stats.rs:2172-2184, 2222-2229).  Counts come straight from
+// the per-group arrays (coalesced: lane = site).
+__global__ void __launch_bounds__(128)
+fm_k_wc_overall(const WcParams P, const WcTables T) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t GW = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t G = P.G, G1 = P.G + 1;
+    for (uint32_t si = gw; si < P.n_seg; si += GW) {
+        const uint32_t lo = P.seg_lo[si], hi = P.seg_hi[si];
+        double sum_a = 0.0, sum_b = 0.0;  // identical in every lane
+        uint32_t n_informative = 0;
+        for (uint32_t v0 = lo; v0 < hi; v0 += 32) {
+            const uint32_t nb = min(32u, hi - v0);
+            double site_a = 0.0, site_b = 0.0;
+            int state = 3;  // InsufficientDataForEstimation: no allele at all at this site
+            bool any = false;
+            if (lane < nb) {
+                const uint32_t v = v0 + lane;
+                uint32_t t_alt = 0, t_n = 0, m_alt = 0, m_n = 0, m_r = 0;
+                for (uint32_t g = 0; g < G1; ++g) {
+                    const uint32_t a = __ldg(P.alt[g] + v), n = __ldg(P.cnt[g] + v);
+                    t_alt += a;
+                    t_n += n;
+                    if (g < G && n > 0) {
+                        m_alt += a;
+                        m_n += n;
+                        m_r += 1;
+                    }
+                }
+                const bool has0 = t_n > t_alt, has1 = t_alt > 0;
+                any = has0 || has1;  // pop_sizes_populated (stats.rs:1919-1923, 1987)
+                if (any && m_r >= 2) {  // fewer than two groups with data: no allele contributes
+                    const double r = (double)m_r;
+                    const double n_bar = (double)m_n / r;
+                    if (!((n_bar - 1.0) < 1e-9)) {
+                        const double gp0 = (double)(m_n - m_alt) / (double)m_n;
+                        const double gp1 = (double)m_alt / (double)m_n;
+                        double ssd = 0.0, ns0 = 0.0, ns1 = 0.0;  // sums in group order
+                        for (uint32_t g = 0; g < G; ++g) {
+                            const uint32_t n = __ldg(P.cnt[g] + v);
+                            if (n > 0) {
+                                const uint32_t a = __ldg(P.alt[g] + v);
+                                const double nd = (double)n;
+                                const double d = nd - n_bar;
+                                ssd += d * d;
+                                const double y = __ldg(T.inv_n + n);
+                                const double f0 = fm_div_recip((double)(n - a), nd, y), f1 = fm_div_recip((double)a, nd, y);
+                                const double q0 = f0 - gp0, q1 = f1 - gp1;
+                                ns0 += nd * q0 * q0;
+                                ns1 += nd * q1 * q1;
+                            }
+                        }
+                        const double c_squared = ssd / (r * n_bar * n_bar);
+                        const double a_den = 1.0 - (c_squared / (r - 1.0));
+                        const double nb_ratio = n_bar / (n_bar - 1.0);
+                        const bool s_ok = (r - 1.0) > 1e-9 && n_bar > 1e-9;
+                        // sum over alleles in ascending order: allele 0 first (stats.rs:1859, 1939-1940)
+                        if (has0) {
+                            const double s2 = s_ok ? ns0 / ((r - 1.0) * n_bar) : 0.0;
+                            const double x = gp0 * (1.0 - gp0) - ((r - 1.0) / r) * s2;
+                            site_a += (s2 - (x / (n_bar - 1.0))) / a_den;
+                            site_b += nb_ratio * x;
+                        }
+                        if (has1) {
+                            const double s2 = s_ok ? ns1 / ((r - 1.0) * n_bar) : 0.0;
+                            const double x = gp1 * (1.0 - gp1) - ((r - 1.0) / r) * s2;
+                            site_a += (s2 - (x / (n_bar - 1.0))) / a_den;
+                            site_b += nb_ratio * x;
+                        }
+                    }
+                }
+                if (any) state = fm_fst_state(site_a, site_b);
+                const uint32_t o = v - P.out_base;
+                if (P.site_state) P.site_state[o] = state;
+                if (P.site_a) P.site_a[o] = site_a;
+                if (P.site_b) P.site_b[o] = site_b;
+                if (P.site_sizes)
+                    for (uint32_t g = 0; g < G; ++g) P.site_sizes[(size_t)o * G + g] = any ? __ldg(P.cnt[g] + v) : 0u;
             }
+            const uint32_t any_mask = __ballot_sync(0xffffffffu, any);
+            for (uint32_t s = 0; s < nb; ++s) {
+                const double a_s = __shfl_sync(0xffffffffu, site_a, s);
+                const double b_s = __shfl_sync(0xffffffffu, site_b, s);
+                if ((any_mask >> s) & 1u) {
+                    sum_a += a_s;
+                    sum_b += b_s;
+                    ++n_informative;
+                }
+            }
+        }
+        if (lane == 0) {
+            P.part_overall[2 * (size_t)si] = sum_a;
+            P.part_overall[2 * (size_t)si + 1] = sum_b;
+            P.part_counts[si] = n_informative;
         }
     }
 }
@@ -513,31 +605,51 @@ fm_k_wc_fold(const double *__restrict__ part_overall, const uint32_t *__restrict
              const uint32_t *__restrict__ wseg, uint32_t n_windows, uint32_t n_pairs,
              double *__restrict__ out_overall /*[n_w][2]*/, uint64_t *__restrict__ out_sites /*[n_w]*/,
              double *__restrict__ out_pair /*[n_w][n_pairs][2]*/, uint64_t *__restrict__ out_pair_n) {
+    // Fixed association: the window's segments are taken in chunks of kFoldChunk (counted from the window's
+    // first segment); a chunk is added in segment order, the chunk sums are added in chunk order.  All loads of
+    // a chunk are issued before the first add, so a thread keeps 3 * kFoldChunk loads in flight instead of
+    // walking ~1000 segments one L2 round trip at a time.
+    constexpr uint32_t kFoldChunk = 16;
     const uint32_t per_w = n_pairs + 1;
     const uint64_t total = (uint64_t)n_windows * per_w;
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t w = (uint32_t)(t / per_w), p = (uint32_t)(t % per_w);
         const uint32_t s0 = wseg[w], s1 = wseg[w + 1];
+        const bool ov = p == n_pairs;
+        const double *pa = ov ? part_overall : part_pair + 2 * (size_t)p;
+        const uint32_t *pn = ov ? part_counts : part_pair_n + p;
+        const size_t stride = ov ? 1 : n_pairs;  // segment stride in (a, b) pairs / counts
         double a = 0.0, b = 0.0;
         uint64_t n = 0;
-        if (p == n_pairs) {
-            for (uint32_t s = s0; s < s1; ++s) {
-                a += part_overall[2 * (size_t)s];
-                b += part_overall[2 * (size_t)s + 1];
-                n += part_counts[s];
+        for (uint32_t c0 = s0; c0 < s1; c0 += kFoldChunk) {
+            double xa[kFoldChunk], xb[kFoldChunk];
+            uint32_t xn[kFoldChunk];
+#pragma unroll
+            for (uint32_t i = 0; i < kFoldChunk; ++i) {
+                const bool in = c0 + i < s1;
+                const size_t o = (size_t)(in ? c0 + i : s0) * stride;
+                xa[i] = in ? pa[2 * o] : 0.0;
+                xb[i] = in ? pa[2 * o + 1] : 0.0;
+                xn[i] = in ? pn[o] : 0u;
             }
+            double ca = 0.0, cb = 0.0;
+#pragma unroll
+            for (uint32_t i = 0; i < kFoldChunk; ++i) {
+                if (c0 + i < s1) {
+                    ca += xa[i];
+                    cb += xb[i];
+                    n += xn[i];
+                }
+            }
+            a += ca;
+            b += cb;
+        }
+        if (ov) {
             out_overall[2 * (size_t)w] = a;
             out_overall[2 * (size_t)w + 1] = b;
             out_sites[w] = n;
         } else {
-#pragma unroll 4
-            for (uint32_t s = s0; s < s1; ++s) {
-                const size_t o = (size_t)s * n_pairs + p;
-                a += part_pair[2 * o];
-                b += part_pair[2 * o + 1];
-                n += part_pair_n[o];
-            }
             const size_t o = (size_t)w * n_pairs + p;
             out_pair[2 * o] = a;
             out_pair[2 * o + 1] = b;

@@ -173,6 +173,15 @@ fm_status fm_group_capacity(const fm_group *g, size_t *haplotype_capacity);
 fm_status fm_group_summary(fm_group *g, uint32_t *alt_out_or_null, uint32_t *called_out_or_null,
                            uint64_t *segregating_sites, double *pi_sum, uint64_t *uncallable_lt2);
 
+/* The same for MANY groups in ONE persistent launch -- normally one group per region-sized matrix, the
+ * shape of the CLI's serial loop over config entries (process.rs:2169: every entry builds its own
+ * DenseGenotypeMatrix and summary).  Groups whose summaries are not cached yet are streamed by a single
+ * pass over a segment table (any matrices of one device), so 64 regions of 100k sites run at the HBM
+ * rate of one 6.4M-site matrix instead of 64 latency-sized launches.  Outputs [n_groups], any may be
+ * NULL; afterwards every group is in the state fm_group_summary leaves it in (bit-identical scalars). */
+fm_status fm_groups_summary_batch(fm_group *const *groups, size_t n_groups, uint64_t *segregating_sites,
+                                  double *pi_sum, uint64_t *uncallable_lt2);
+
 /* count_segregating_sites_for_population (stats.rs:3831-3851) for a dense ploidy-2 context. */
 fm_status fm_group_segregating_sites(fm_group *g, uint64_t *out);
 
@@ -195,7 +204,8 @@ fm_status fm_watterson_theta(size_t seg_sites, size_t n, int64_t sequence_length
  * are 0-based half-open pairs [s,e) (mask_iv_or_null == NULL <=> None); filtered positions are
  * 0-based.  Outputs are caller-allocated with room for `capacity` sites; *n_out receives the
  * number of variants inside the region (in variant order).  raw_haplotype_count is
- * haplotypes_in_group.len() before de-duplication (the <2 guard at :4675 uses it). */
+ * haplotypes_in_group.len() before de-duplication (the <2 guard at :4675 uses it).  pos_out may be
+ * NULL when the caller already holds the positions (they are the input positions + 1). */
 fm_status fm_per_site_diversity(fm_group *g, size_t raw_haplotype_count, int64_t region_start,
                                 int64_t region_end, const int64_t *mask_iv_or_null, size_t n_mask,
                                 const int64_t *filtered_pos, size_t n_filtered, int64_t *pos_out,
@@ -286,6 +296,13 @@ fm_status fm_wc_window_sums(fm_partition *p, const int64_t *windows, size_t n_wi
  * sites = sites_attempted. */
 fm_status fm_fst_estimate_from_sums(double sum_a, double sum_b, uint64_t informative_sites,
                                     uint64_t sites_attempted, fm_fst_estimate *out);
+
+/* Test hook: the two FP64 building blocks of the W&C kernels evaluated on the device over host arrays --
+ * y[i] = the branch-free correctly rounded reciprocal of b[i] (b normal, away from the exponent limits),
+ * q[i] = a[i] / b[i] computed from RN(1 / b[i]) with two residual corrections.  Both must equal IEEE
+ * division bit for bit (tests/test_gpu_wc_arith.py); that is what lets K4 replace the per-pair divisions
+ * of stats.rs:2034-2127 by table reciprocals without changing a single rounding. */
+fm_status fm_wc_arith_probe(const double *a, const double *b, double *y, double *q, size_t n);
 
 /* ---- calculate_adjusted_sequence_length (stats.rs:3644-3736); host integer arithmetic ----
  * region is 1-based inclusive; allow/mask are 0-based half-open pairs; NULL <=> None. */
