@@ -21,7 +21,8 @@ constexpr uint32_t kCommMaxValues = 2048;  // 8-byte words per rank per exchange
 constexpr uint32_t kCommStageWords = 1024;  // staging of super-batch partial rows for the fused fold
 
 struct CommMailbox {                       // lives in device memory of its owner
-    unsigned long long flags[kCommMaxRanks * 16];  // flags[r*16]: last step rank r has fully written (own line)
+    unsigned long long flags[kCommMaxRanks * 16];  // flags[r*16]: last step rank r has fully written (own line);
+                                                   // flags[r*16 + 8]: rank r is closing (fm_k_comm_goodbye)
     unsigned long long data[2][kCommMaxRanks][kCommMaxValues];
 };
 
@@ -143,7 +144,7 @@ fm_k_comm_exchange(const CommParams P) {
     if (tid < P.world) {
         const unsigned long long t0 = fm_globaltimer();
         while (fm_ld_relaxed_sys(&mine->flags[tid * 16]) < P.step) {  // cheap polling, one fence after
-            if (fm_globaltimer() - t0 > P.timeout_ns) {
+            if (P.timeout_ns && fm_globaltimer() - t0 > P.timeout_ns) {  // 0: wait for ever, like a collective
                 timed_out = 1;
                 break;
             }
@@ -171,6 +172,30 @@ fm_k_comm_exchange(const CommParams P) {
         }
         if (P.merged) P.merged[i] = is_d ? (unsigned long long)__double_as_longlong(accd) : accu;
     }
+}
+
+// Closing handshake of fm_comm_destroy: every rank tells every peer "I will never write into your mailbox
+// again" and waits for the same word from all of them before its own mailbox is freed -- without it a slower
+// peer could still be issuing P2P stores into memory that has gone back to the driver.  status: 0 ok,
+// 1 a peer did not close within the timeout (the mailbox is then leaked on purpose, never freed under a writer).
+__global__ void __launch_bounds__(32)
+fm_k_comm_goodbye(CommMailbox *const *peers_unused, const CommParams P) {
+    (void)peers_unused;
+    const uint32_t tid = threadIdx.x;
+    if (tid < P.world) fm_st_release_sys(&P.peers[tid]->flags[P.rank * 16 + 8], 1ull);
+    CommMailbox *mine = P.peers[P.rank];
+    bool late = false;
+    if (tid < P.world) {
+        const unsigned long long t0 = fm_globaltimer();
+        while (fm_ld_relaxed_sys(&mine->flags[tid * 16 + 8]) == 0ull) {
+            if (P.timeout_ns && fm_globaltimer() - t0 > P.timeout_ns) {
+                late = true;
+                break;
+            }
+            __nanosleep(256);
+        }
+    }
+    if (__any_sync(0xffffffffu, late) && tid == 0) *P.status = 1;
 }
 
 }  // namespace fm

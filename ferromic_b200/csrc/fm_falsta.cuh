@@ -87,9 +87,13 @@ fm_k_falsta_scatter(const int64_t *__restrict__ pos1, uint32_t n, uint64_t rs, u
 // Track t of a call renders values[t * n + i]; all tracks of a call share the record positions.
 // Every token is followed by one separator byte (',' inside a line, '\n' between tracks) except the
 // very last token of the call.
+struct U32ToU64 {  // widens token lengths for the 64-bit prefix sum
+    __host__ __device__ __forceinline__ uint64_t operator()(uint32_t x) const { return (uint64_t)x; }
+};
+
 __global__ void __launch_bounds__(256)
 fm_k_falsta_lengths(const int *__restrict__ idx, const double *__restrict__ values, uint64_t n, uint64_t region_len,
-                    uint32_t n_tracks, int mode, uint32_t *__restrict__ lens) {
+                    uint32_t n_tracks, int mode, uint32_t *__restrict__ lens, uint32_t test_inflate) {
     const uint32_t dflt = mode == FM_FALSTA_FST ? 2u : 1u;
     const uint64_t total = region_len * n_tracks;
     for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total;
@@ -101,7 +105,7 @@ fm_k_falsta_lengths(const int *__restrict__ idx, const double *__restrict__ valu
             char buf[56];
             len = fm_falsta_token(values[t * n + (uint64_t)i], mode, buf);
         }
-        lens[g] = len + (g + 1 < total ? 1u : 0u);
+        lens[g] = len + (g + 1 < total ? 1u : 0u) + test_inflate;  // test_inflate: length-query tests of > 4 GiB bodies
     }
 }
 

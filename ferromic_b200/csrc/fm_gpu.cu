@@ -10,6 +10,8 @@
 #include "fm_vcf.cuh"
 
 #include <cub/device/device_scan.cuh>
+#include <thrust/iterator/transform_iterator.h>
+#include <cuda/std/functional>
 
 #include <algorithm>
 #include <atomic>
@@ -730,7 +732,7 @@ bool launch_plane_pass_tab(std::vector<fm::TabSeg> &segs, uint32_t gpu, const st
         keep.d_hud.upload(hud->data(), n_units);
         P.hud = keep.d_hud.p;
     }
-    CK(cudaStreamSynchronize(stream()));  // the descriptor vectors are host temporaries
+    // (pageable sources are staged by the driver before cudaMemcpyAsync returns: the host vectors may go away)
     P.segs = keep.d_segs.p;
     P.unit_prefix = keep.d_prefix.p;
     P.n_units = (uint32_t)n_units;
@@ -1762,9 +1764,8 @@ fm_status fm_group_summary(fm_group *g, uint32_t *alt_out, uint32_t *called_out,
 // loop over config entries (process.rs:2169 -> stats.rs:1367-1470) -- in one persistent launch: groups whose counts
 // are not cached yet become the units of one fm_k_plane_pass_tab pass (per LPS / bitmap class), their partials
 // are folded by one kernel and come back in one copy.  Each group ends up exactly as after fm_group_summary.
-fm_status fm_groups_summary_batch(fm_group *const *groups, size_t n_groups, uint64_t *seg_out, double *pi_sum_out,
-                                  uint64_t *unc_out) {
-    return guarded([&] {
+static void summarize_groups(fm_group *const *groups, size_t n_groups) {
+    {
         if (n_groups && !groups) fail(FM_ERR_INVALID_ARG, "groups is NULL");
         require_device();
         if (!n_groups) return;
@@ -1864,14 +1865,33 @@ fm_status fm_groups_summary_batch(fm_group *const *groups, size_t n_groups, uint
             }
         }
         locks.clear();
+        for (size_t i = 0; i < n_groups; ++i)
+            if (!groups[i]->have_counts) ensure_counts(groups[i]);  // multi-allelic / empty matrices / leftovers
+    }
+}
+
+fm_status fm_groups_summary_batch(fm_group *const *groups, size_t n_groups, uint64_t *seg_out, double *pi_sum_out,
+                                  uint64_t *unc_out) {
+    return guarded([&] {
+        summarize_groups(groups, n_groups);
         for (size_t i = 0; i < n_groups; ++i) {
-            fm_group *g = groups[i];
-            if (!g->have_counts) ensure_counts(g);  // multi-allelic / empty matrices / count-only leftovers
+            const fm_group *g = groups[i];
             if (seg_out) seg_out[i] = g->seg;
             if (pi_sum_out) pi_sum_out[i] = g->pi_sum;
             if (unc_out) unc_out[i] = g->unc;
         }
     });
+}
+
+// summaries of the two groups of a pair: one launch when neither is cached yet
+static void ensure_counts_pair(fm_group *g1, fm_group *g2) {
+    if (g1 != g2 && !g1->have_counts && !g2->have_counts && g1->m->device == g2->m->device) {
+        fm_group *gs[2] = {g1, g2};
+        summarize_groups(gs, 2);
+        return;
+    }
+    ensure_counts(g1);
+    ensure_counts(g2);
 }
 
 fm_status fm_group_segregating_sites(fm_group *g, uint64_t *out) {
@@ -2516,8 +2536,7 @@ fm_status fm_hudson_dxy(fm_group *g1, fm_group *g2, int64_t L1, int64_t L2, int 
         check_pair(g1, g2, path == FM_HUDSON_SUMMARIES);
         require_device();
         if (raw_n1 == 0 || raw_n2 == 0) return;
-        ensure_counts(g1);
-        ensure_counts(g2);
+        ensure_counts_pair(g1, g2);
         set_dev(g1->m);
         const int variant = path == FM_HUDSON_SUMMARIES ? -1
                             : path == FM_HUDSON_DENSE   ? dense_variant(g1->m)
@@ -2675,8 +2694,7 @@ fm_status fm_hudson_pair(fm_group *g1, fm_group *g2, int64_t L1, int64_t L2, int
             }
         }
         if (!fused) {
-            ensure_counts(g1);
-            ensure_counts(g2);
+            ensure_counts_pair(g1, g2);
             main_t = run_hudson_counts(g1, g2, lo, hi, site_variant, e);
         }
         if (!has_region || (lo == 0 && hi == V && site_variant == aux_variant)) {
@@ -2928,7 +2946,9 @@ void run_wc(fm_partition *p, const std::vector<uint32_t> &wlo, const std::vector
 
     // CTA geometry: pair warps (lane = pair, KP pairs per lane in registers); the multi-allelic kernel adds one
     // overall warp, the biallelic path evaluates the overall components in its own light kernel
-    uint32_t n_pw = std::max(1u, std::min<uint32_t>(fm::kWcMaxPairWarps, (n_pairs + 31) / 32));
+    // FM_WC_KP (tuning): pairs per lane; fewer, fatter warps per CTA leave room for more CTAs per SM
+    static const uint32_t kp_pref = env_u32("FM_WC_KP", 1);
+    uint32_t n_pw = std::max(1u, std::min<uint32_t>(fm::kWcMaxPairWarps, (n_pairs + 32 * kp_pref - 1) / (32 * kp_pref)));
     const uint32_t kp_need = std::max(1u, (n_pairs + n_pw * 32 - 1) / (n_pw * 32));
     if (kp_need > fm::kWcMaxKP) fail(FM_ERR_UNSUPPORTED, "too many populations for the W&C kernel (pairs per lane)");
     const size_t smem = multi ? fm::fm_wc_multi_cta_smem(G, A) : fm::fm_wc_cta_smem(G);
@@ -3226,8 +3246,7 @@ fm_status fm_hudson_window_sums(fm_group *g1, fm_group *g2, const int64_t *windo
         if (n_windows && !windows) fail(FM_ERR_INVALID_ARG, "NULL argument");
         require_device();
         if (!n_windows) return;
-        ensure_counts(g1);
-        ensure_counts(g2);
+        ensure_counts_pair(g1, g2);
         set_dev(g1->m);
         std::vector<uint32_t> lo, hi;
         window_ranges(g1->m, windows, n_windows, lo, hi);
@@ -3314,7 +3333,10 @@ struct fm_comm {
     unsigned long long step = 0;
     uint32_t *d_status = nullptr;
     unsigned long long *d_local = nullptr, *d_gathered = nullptr, *d_merged = nullptr;
-    unsigned long long timeout_ns = 5000000000ull;
+    // An exchange waits for the slowest rank like any collective; the timeout only exists so that a rank that
+    // died cannot hang the GPU for ever (0 = no timeout).  Ranks may legitimately be far apart (unequal shard
+    // work, host I/O between calls), hence minutes, not seconds.
+    unsigned long long timeout_ns = 120000000000ull;
 };
 
 namespace {
@@ -3335,6 +3357,7 @@ void comm_launch(fm_comm *c, const unsigned long long *d_local, uint32_t n_words
     P.n_fold = n_fold;
     for (uint32_t f = 0; f < n_fold; ++f) {
         if (folds[f].nd + folds[f].nu > 32) fail(FM_ERR_INVALID_ARG, "fold has more than 32 columns");
+        if (folds[f].nd + folds[f].nu == 0) fail(FM_ERR_INVALID_ARG, "fold has no columns");
         P.fold[f] = folds[f];
     }
     P.gathered = c->d_gathered;
@@ -3349,7 +3372,14 @@ void comm_check_status(fm_comm *c) {
     uint32_t st = 0;
     CK(cudaMemcpyAsync(&st, c->d_status, 4, cudaMemcpyDeviceToHost, stream()));
     CK(cudaStreamSynchronize(stream()));
-    if (st != 0) fail(FM_ERR_CUDA, "peer exchange timed out waiting for another rank");
+    if (st != 0) {
+        // report once: the word is cleared so that later exchanges on this communicator start clean.  The rank
+        // that timed out had already published its own contribution, so its peers completed the step; the
+        // step counters stay aligned and the next exchange is valid if the late rank has caught up.
+        CK(cudaMemsetAsync(c->d_status, 0, 4, stream()));
+        CK(cudaStreamSynchronize(stream()));
+        fail(FM_ERR_CUDA, "peer exchange timed out waiting for another rank (fm_comm_set_timeout_ms raises the limit)");
+    }
 }
 }  // namespace
 
@@ -3457,16 +3487,148 @@ fm_status fm_comm_set_timeout_ms(fm_comm *c, uint64_t ms) {
 fm_status fm_comm_destroy(fm_comm *c) {
     if (!c) return FM_OK;
     cudaSetDevice(c->device);
-    cudaDeviceSynchronize();
+    cudaDeviceSynchronize();  // every exchange this rank launched (on any stream) has finished writing to its peers
+    bool leak_mailbox = false;
+    bool cross_process = false;
+    for (int r = 0; r < c->world; ++r) cross_process = cross_process || c->ipc_opened[r];
+    if (c->connected && c->world > 1 && cross_process) {
+        // closing handshake between processes: nobody frees a mailbox a peer may still write into (ranks wired
+        // inside one process with fm_comm_connect_local are torn down by their common owner, in any order)
+        fm::CommParams P{};
+        for (int r = 0; r < c->world; ++r) P.peers[r] = c->peers[r];
+        P.rank = (uint32_t)c->rank;
+        P.world = (uint32_t)c->world;
+        P.status = c->d_status;
+        // a peer that is more than 10 s late (or dead) is not waited for: the mailbox is then kept, not freed
+        P.timeout_ns = c->timeout_ns ? std::min<unsigned long long>(c->timeout_ns, 10000000000ull) : 10000000000ull;
+        cudaMemsetAsync(c->d_status, 0, 4, stream());
+        fm::fm_k_comm_goodbye<<<1, 32, 0, stream()>>>(nullptr, P);
+        uint32_t st = 1;
+        if (cudaMemcpyAsync(&st, c->d_status, 4, cudaMemcpyDeviceToHost, stream()) != cudaSuccess ||
+            cudaStreamSynchronize(stream()) != cudaSuccess) {
+            cudaGetLastError();
+            st = 1;
+        }
+        leak_mailbox = st != 0;  // a peer never closed: keep the memory rather than free it under a writer
+    }
     for (int r = 0; r < c->world; ++r)
         if (c->ipc_opened[r]) cudaIpcCloseMemHandle(c->peers[r]);
-    cudaFree(c->mine);
+    if (!leak_mailbox) cudaFree(c->mine);
     cudaFree(c->d_status);
     cudaFree(c->d_local);
     cudaFree(c->d_merged);
     cudaFree(c->d_gathered);
     delete c;
     return FM_OK;
+}
+
+// ------------------------------------------------------------------------------------ sharded Hudson call
+namespace {
+void launch_reduce(const double *pd, int nd, const uint32_t *pu, int nu, const fm::PassGeom &G, double *sd,
+                   uint64_t *su, cudaStream_t st);
+}
+
+// One Hudson call over a cohort that is sharded by site range across the ranks of `comm`:
+// every rank sweeps its own shard once (pair units of fm_k_plane_pass_tab, nothing cached, nothing written but
+// the per-batch partials), folds the partials per super-batch, and the fold into region totals is fused with
+// the NVLink mailbox exchange; the rank-ordered merged totals come back in ONE small copy and are finished on
+// the host exactly like the single-GPU summaries path (stats.rs:3476-3566).  Three launches, one host sync.
+fm_status fm_hudson_pair_sharded(fm_group *g1, fm_group *g2, int64_t sequence_length, size_t raw_n1, size_t raw_n2,
+                                 fm_comm *comm, fm_hudson_outcome *out, fm_hudson_sums *merged_out) {
+    return guarded([&] {
+        if (!out) fail(FM_ERR_INVALID_ARG, "out is NULL");
+        std::memset(out, 0, sizeof(*out));
+        if (sequence_length <= 0)
+            fail(FM_ERR_INVALID_REGION, "Sequence length must be positive for Hudson FST calculation.");
+        check_pair(g1, g2);
+        require_device();
+        fm_matrix *m = g1->m;
+        set_dev(m);
+        if (comm && comm->device != m->device) fail(FM_ERR_INVALID_ARG, "communicator and groups live on different devices");
+        if (g1->n_bits != 1) fail(FM_ERR_UNSUPPORTED, "the summaries path does not exist for multi-allelic matrices (lib.rs:779)");
+        const uint32_t V = (uint32_t)m->V;
+        const uint32_t nb = (V + 31) / 32;
+        const uint32_t n_super = (nb + fm::kSuperBatches - 1) / fm::kSuperBatches;
+        DevBuf<double> pd((size_t)std::max(nb, 1u) * 5), sd((size_t)std::max(n_super, 1u) * 5);
+        DevBuf<uint32_t> pu((size_t)std::max(nb, 1u) * 3);
+        DevBuf<uint64_t> su((size_t)std::max(n_super, 1u) * 3);
+        fm::HudsonEpilogue he{};
+        he.variant = -1;  // aggregate_hudson_components_from_summaries (stats.rs:1554-1623)
+        he.part_d = pd.p;
+        he.part_u = pu.p;
+        Timer tm;
+        tm.start();
+        if (V) {
+            bool done = false;
+            TabLaunch keep;
+            if (g1 != g2 && !g1->count_only && !g2->count_only && !(g1->have_counts && g2->have_counts)) {
+                std::vector<fm::TabSeg> segs(2);
+                fm_group *pair[2] = {g1, g2};
+                for (int k = 0; k < 2; ++k) {
+                    segs[k] = fm::TabSeg{};
+                    segs[k].g = planes_of(pair[k]);
+                    segs[k].v_lo = 0;
+                    segs[k].v_hi = V;
+                    segs[k].n_sites_total = V;
+                }
+                std::vector<fm::HudsonEpilogue> hv{he};
+                done = launch_plane_pass_tab(segs, 2, &hv, m->device, keep);
+            }
+            if (!done) {  // cached counts, count-only groups or rows wider than the table pass: from the counts
+                ensure_counts_pair(g1, g2);
+                const uint32_t blocks = std::min<uint32_t>((nb + 7) / 8, 8u * sm_count(m->device));
+                fm::fm_k_hudson_from_counts<<<blocks, 256, 0, stream()>>>(g1->d_alt, g1->d_cnt, g2->d_alt, g2->d_cnt, he, 0,
+                                                                           V, 0, nb);
+                CK(cudaGetLastError());
+                g_launches++;
+            }
+            fm::PassGeom G{};
+            G.b_lo = 0;
+            G.n_batches = nb;
+            launch_reduce(pd.p, 5, pu.p, 3, G, sd.p, su.p, stream());
+            // `keep` (the descriptor table) goes back to the allocator here: the block carries an event on this
+            // stream, so a later owner waits for the pass -- no host synchronisation needed
+        }
+        unsigned long long w[8] = {};
+        if (comm) {
+            fm::CommFold fold{sd.p, reinterpret_cast<const unsigned long long *>(su.p), n_super, 5u, 3u};
+            comm_launch(comm, nullptr, 8, 0, &fold, 1, stream());
+            CK(cudaMemcpyAsync(w, comm->d_merged, sizeof(w), cudaMemcpyDeviceToHost, stream()));
+            comm_check_status(comm);
+        } else {
+            std::vector<double> hd((size_t)n_super * 5);
+            std::vector<uint64_t> hu((size_t)n_super * 3);
+            sd.download(hd.data(), hd.size());
+            su.download(hu.data(), hu.size());
+            CK(cudaStreamSynchronize(stream()));
+            double d[5] = {0, 0, 0, 0, 0};
+            uint64_t u[3] = {0, 0, 0};
+            for (uint32_t sb = 0; sb < n_super; ++sb) {  // fixed order
+                for (int i = 0; i < 5; ++i) d[i] += hd[(size_t)sb * 5 + i];
+                for (int i = 0; i < 3; ++i) u[i] += hu[(size_t)sb * 3 + i];
+            }
+            std::memcpy(w, d, sizeof(d));
+            for (int i = 0; i < 3; ++i) w[5 + i] = u[i];
+        }
+        tm.stop();
+        t_tim.stats_ms += tm.ms();
+        fm_hudson_sums sums;
+        std::memcpy(&sums.num, &w[0], 8);
+        std::memcpy(&sums.den, &w[1], 8);
+        std::memcpy(&sums.dxy, &w[2], 8);
+        std::memcpy(&sums.pi1, &w[3], 8);
+        std::memcpy(&sums.pi2, &w[4], 8);
+        sums.dxy_uncallable = w[5];
+        sums.unc1 = w[6];
+        sums.unc2 = w[7];
+        if (merged_out) *merged_out = sums;
+        // calculate_hudson_fst_for_pair_core, summaries path (stats.rs:3476-3488, 3505-3566)
+        fm_hudson_outcome o;
+        fm_status st = fm_hudson_outcome_from_sums(&sums, sequence_length, g1->n, g2->n, &o);
+        if (st != FM_OK) fail(st, t_err);
+        if (raw_n1 == 0 || raw_n2 == 0) o.some &= ~2u;  // dxy_from_summaries needs both haplotype lists non-empty
+        *out = o;
+    });
 }
 
 // ------------------------------------------------------------------------------------ FALSTA track bodies
@@ -3512,14 +3674,24 @@ fm_status fm_falsta_tracks(const int64_t *pos1, const double *values, size_t n, 
             g_launches++;
         }
         const uint32_t blocks = (uint32_t)std::min<uint64_t>((T + 255) / 256, 16ull * dev_sms);
+        // FM_FALSTA_TEST_INFLATE=k (length queries only) adds k bytes to every token length so that a test can push
+        // the body past 4 GiB without a multi-gigabyte input
+        const uint32_t inflate = env_u32("FM_FALSTA_TEST_INFLATE", 0);
+        if (inflate && out) fail(FM_ERR_INVALID_ARG, "FM_FALSTA_TEST_INFLATE is for length queries (out == NULL) only");
         fm::fm_k_falsta_lengths<<<blocks, 256, 0, stream()>>>(d_idx.p, d_val.p, n, L, (uint32_t)n_tracks, mode,
-                                                               d_len.p);
+                                                               d_len.p, inflate);
         CK(cudaGetLastError());
         g_launches++;
+        // The prefix sum must run in 64 bits: a body can exceed 4 GiB (a 250 Mb region with a dozen tracks).  cub
+        // derives the accumulator from the INPUT type, so the u32 lengths are widened by the input iterator and the
+        // scan is given a u64 initial value.
         size_t tmp_bytes = 0;
-        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_len.p, d_off.p, (int64_t)T, stream()));
+        thrust::transform_iterator<fm::U32ToU64, const uint32_t *> len64(d_len.p, fm::U32ToU64());
+        CK(cub::DeviceScan::ExclusiveScan(nullptr, tmp_bytes, len64, d_off.p, cuda::std::plus<>(), (uint64_t)0, (int64_t)T,
+                                          stream()));
         DevBuf<uint8_t> d_tmp(std::max<size_t>(tmp_bytes, 16));
-        CK(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, d_len.p, d_off.p, (int64_t)T, stream()));
+        CK(cub::DeviceScan::ExclusiveScan(d_tmp.p, tmp_bytes, len64, d_off.p, cuda::std::plus<>(), (uint64_t)0, (int64_t)T,
+                                          stream()));
         // line t starts at off[t*L]; the call ends at off[T-1] + len[T-1]
         std::vector<uint64_t> starts(n_tracks + 1);
         for (size_t t = 0; t < n_tracks; ++t)

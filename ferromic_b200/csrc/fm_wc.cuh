@@ -137,7 +137,7 @@ __device__ __forceinline__ void fm_wc_pair_site(const double4 vi, const double4 
 // SU sites are evaluated side by side (independent dependency chains for the FP64 pipe) and then added to the
 // pair's running sums in site order.
 template <int KP, int SU>
-__global__ void __launch_bounds__(352, (KP <= 2 && SU == 1) ? 3 : (KP <= 4 ? 2 : 1))
+__global__ void __launch_bounds__(352, KP * SU == 1 ? 3 : (KP * SU <= 4 ? 2 : 1))
 fm_k_wc_pairs(const WcParams P, const WcTables T) {
     extern __shared__ __align__(16) uint8_t wc_smem[];
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
@@ -203,64 +203,74 @@ fm_k_wc_pairs(const WcParams P, const WcTables T) {
                 info[lane] = (t_n > t_alt ? 1u : 0u) | (t_alt > 0 ? 2u : 0u);  // 0 past the segment end
             }
             __syncthreads();
-            // ---- pairwise components (r == 2), sites in order, SU at a time (nb <= 32, SU divides 32)
+            // ---- pairwise components (r == 2), sites in order, SU at a time (nb <= 32, SU divides 32).  The
+            // KP x SU (pair, site) evaluations of a lane are gathered first and run as ONE straight line of
+            // independent dependency chains; a lane whose pair is not polymorphic at a site runs on clamped inputs
+            // and drops the result (under SIMT it would have waited for its neighbours anyway).
             for (uint32_t s0 = 0; s0 < nb; s0 += SU) {
+                double pa[KP][SU], pb[KP][SU];
+                bool has[KP][SU], poly[KP][SU];
+                uint32_t nsum[KP][SU];
+                bool any_poly = false;
 #pragma unroll
                 for (int k = 0; k < KP; ++k) {
-                    if (!pvalid[k]) continue;
-                    double pa[SU], pb[SU];
-                    bool has[SU], poly[SU];
-                    uint32_t nsum[SU];
-                    bool any_poly = false;
 #pragma unroll
                     for (int t = 0; t < SU; ++t) {
                         const uint32_t s = s0 + t;  // < 32; sites past nb carry info == 0
                         const uint2 *sc = cnts + s * G1;
                         const uint2 ci = sc[pi[k]], cj = sc[pj[k]];
-                        has[t] = info[s] != 0 && s < nb && ci.y > 0 && cj.y > 0;  // stats.rs:1950-1952
+                        has[k][t] = pvalid[k] && info[s] != 0 && ci.y > 0 && cj.y > 0;  // stats.rs:1950-1952
                         const uint32_t asum = ci.x + cj.x;
-                        nsum[t] = ci.y + cj.y;
+                        nsum[k][t] = ci.y + cj.y;
                         // polymorphic in this pair and n_bar - 1 >= 1e-9 (anything else adds exactly +0)
-                        poly[t] = has[t] && asum != 0 && asum != nsum[t] && nsum[t] > 2;
-                        any_poly = any_poly || poly[t];
-                        pa[t] = 0.0;
-                        pb[t] = 0.0;
+                        poly[k][t] = has[k][t] && asum != 0 && asum != nsum[k][t] && nsum[k][t] > 2;
+                        any_poly = any_poly || poly[k][t];
+                        pa[k][t] = 0.0;
+                        pb[k][t] = 0.0;
                     }
-                    if (SU == 1) {
-                        if (poly[0]) fm_wc_pair_site(val[s0 * G + pi[k]], val[s0 * G + pj[k]], nsum[0], T, pa[0], pb[0]);
-                    } else if (any_poly) {
-                        // evaluate all SU sites in one straight line (lanes that are not polymorphic at a site
-                        // run on clamped inputs and drop the result: under SIMT they would have waited anyway)
-                        double ea[SU], eb[SU];
+                }
+                if (KP * SU == 1) {
+                    if (poly[0][0])
+                        fm_wc_pair_site(val[s0 * G + pi[0]], val[s0 * G + pj[0]], nsum[0][0], T, pa[0][0], pb[0][0]);
+                } else if (any_poly) {
+                    double ea[KP][SU], eb[KP][SU];
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) {
 #pragma unroll
                         for (int t = 0; t < SU; ++t) {
                             const double4 *sv = val + (s0 + t) * G;
                             double4 vi = sv[pi[k]], vj = sv[pj[k]];
-                            const uint32_t ns = poly[t] ? nsum[t] : 4u;
-                            if (!poly[t]) {
+                            const uint32_t ns = poly[k][t] ? nsum[k][t] : 4u;
+                            if (!poly[k][t]) {
                                 vi = make_double4(0.5, 0.5, 2.0, 1.0);
                                 vj = vi;
                             }
-                            fm_wc_pair_site(vi, vj, ns, T, ea[t], eb[t]);
-                        }
-#pragma unroll
-                        for (int t = 0; t < SU; ++t) {
-                            pa[t] = poly[t] ? ea[t] : 0.0;
-                            pb[t] = poly[t] ? eb[t] : 0.0;
+                            fm_wc_pair_site(vi, vj, ns, T, ea[k][t], eb[k][t]);
                         }
                     }
 #pragma unroll
+                    for (int k = 0; k < KP; ++k) {
+#pragma unroll
+                        for (int t = 0; t < SU; ++t) {
+                            pa[k][t] = poly[k][t] ? ea[k][t] : 0.0;
+                            pb[k][t] = poly[k][t] ? eb[k][t] : 0.0;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < KP; ++k) {
+#pragma unroll
                     for (int t = 0; t < SU; ++t) {
-                        if (has[t]) {  // site order: stats.rs:2288-2289
-                            acc_a[k] += pa[t];
-                            acc_b[k] += pb[t];
+                        if (has[k][t]) {  // site order: stats.rs:2288-2289
+                            acc_a[k] += pa[k][t];
+                            acc_b[k] += pb[k][t];
                             acc_n[k] += 1;
                         }
-                        if (P.pair_a && s0 + t < nb) {
+                        if (P.pair_a && pvalid[k] && s0 + t < nb) {
                             const uint32_t p = warp * 32 + lane + (uint32_t)k * NW * 32;
                             const size_t o = (size_t)(v0 + s0 + t - P.out_base) * NP + p;
-                            P.pair_a[o] = has[t] ? pa[t] : fm_nan();
-                            P.pair_b[o] = has[t] ? pb[t] : fm_nan();
+                            P.pair_a[o] = has[k][t] ? pa[k][t] : fm_nan();
+                            P.pair_b[o] = has[k][t] ? pb[k][t] : fm_nan();
                         }
                     }
                 }

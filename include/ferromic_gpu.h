@@ -345,8 +345,11 @@ fm_status fm_hudson_outcome_from_sums(const fm_hudson_sums *sums, int64_t sequen
  * stores this rank's words into every peer's mailbox with P2P stores, publishes a step flag,
  * waits for all peers' flags and returns the gathered words plus their rank-ordered sum (the
  * first n_double words are summed as FP64, the rest as u64) -- bit-identical on every rank.
- * Ranks must issue the same sequence of exchanges.  A peer that does not arrive within 5 s makes
- * the call fail with FM_ERR_CUDA instead of hanging the GPU. */
+ * Ranks must issue the same sequence of exchanges.  Like a collective, an exchange waits for the slowest
+ * rank; a peer that has not arrived after the timeout (default 120 s, fm_comm_set_timeout_ms; 0 = wait
+ * for ever) makes the call fail with FM_ERR_CUDA on the waiting rank instead of hanging the GPU -- the
+ * error is reported once, the communicator stays usable.  fm_comm_destroy runs a closing handshake with
+ * all peers before it frees the mailbox, so it must be called by every rank (it is collective). */
 typedef struct fm_comm fm_comm;
 #define FM_COMM_HANDLE_BYTES 64
 #define FM_COMM_MAX_WORDS 2048
@@ -358,8 +361,20 @@ fm_status fm_comm_connect_local(fm_comm *c, fm_comm *const *all);
 fm_status fm_comm_allgather(fm_comm *c, const void *local_words, size_t n_words, size_t n_double,
                             void *gathered_out_or_null /* [world][n_words] */,
                             void *merged_out_or_null /* [n_words] */);
-fm_status fm_comm_set_timeout_ms(fm_comm *c, uint64_t milliseconds); /* default 5000 */
+fm_status fm_comm_set_timeout_ms(fm_comm *c, uint64_t milliseconds); /* default 120000; 0 = none */
 fm_status fm_comm_destroy(fm_comm *c);
+
+/* One Hudson FST / Dxy call over a cohort that is sharded by site range across the ranks of a
+ * communicator (BASELINE config 3): g1 / g2 are THIS rank's shard of the two populations
+ * (built from the shard's rows), sequence_length is the whole region's.  Collective: every rank calls it
+ * (also with an empty shard) and every rank receives the same outcome, bit for bit -- summaries path of
+ * calculate_hudson_fst_for_pair_core (stats.rs:3476-3566) over the rank-ordered merged component sums.
+ * Per rank: one sweep of the shard's planes (fused two-group pass, nothing cached), one fold kernel, one
+ * fused fold + NVLink mailbox exchange kernel, one small copy.  comm == NULL computes the single shard.
+ * merged_sums_or_null receives the merged totals (for window-wise post-processing). */
+fm_status fm_hudson_pair_sharded(fm_group *g1, fm_group *g2, int64_t sequence_length, size_t raw_n1,
+                                 size_t raw_n2, fm_comm *comm_or_null, fm_hudson_outcome *out,
+                                 fm_hudson_sums *merged_sums_or_null);
 
 /* ---- FALSTA per-site track bodies (process.rs:3740-4041) ----
  * A track body is ONE comma-joined line of region_len tokens (region is 1-based inclusive, clamped

@@ -213,3 +213,29 @@ def test_track_capacity_and_argument_errors():
     assert out.raw[: total.value] == b"NA"
     assert L.fm_falsta_tracks(p(pos), p(val), 2, 1, -3, 3, 0, out, 64, None, C.byref(total)) == 0
     assert out.raw[: total.value] == b"0,0.500000,0"
+
+
+@pytest.mark.gpu
+def test_track_body_longer_than_4_gib_is_measured_in_64_bits(monkeypatch):
+    """The token offsets are a prefix sum of u32 lengths: it has to run in 64 bits, a body beyond 4 GiB (a 250 Mb
+    region with a dozen tracks) must not wrap.  FM_FALSTA_TEST_INFLATE pads every token length (length query only)
+    so the test needs no multi-gigabyte input."""
+    import ctypes as C
+    from ferromic_b200 import _lib
+    L = _lib.lib()
+    pos = np.array([2, 4], dtype=np.int64)
+    val = np.array([0.5, np.nan, 0.25, 0.125])
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    total = C.c_size_t()
+    lens = (C.c_size_t * 2)()
+    region = 3_000_000
+    assert L.fm_falsta_tracks(p(pos), p(val), 2, 2, 1, region, 1, None, 0, lens, C.byref(total)) == 0
+    plain = total.value
+    assert plain == lens[0] + lens[1] + 1
+    k = 2000
+    monkeypatch.setenv("FM_FALSTA_TEST_INFLATE", str(k))
+    assert L.fm_falsta_tracks(p(pos), p(val), 2, 2, 1, region, 1, None, 0, lens, C.byref(total)) == 0
+    assert total.value == plain + 2 * region * k and total.value > 2 ** 32
+    assert lens[0] + lens[1] + 1 == total.value
+    out = C.create_string_buffer(16)
+    assert L.fm_falsta_tracks(p(pos), p(val), 2, 2, 1, 4, 1, out, 16, None, C.byref(total)) == _lib.FM_ERR_INVALID_ARG
