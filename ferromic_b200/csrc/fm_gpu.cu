@@ -300,15 +300,43 @@ void h2d(void *dst, const void *src, size_t bytes, cudaStream_t st) {
         g_bounce.copy(dst, src, bytes, st);
 }
 
+// Event pairs are recycled per host thread and device: cudaEventCreate / Destroy cost microseconds each, and the
+// small calls (a sharded Hudson step is ~250 us) create several timers.
+struct TimerEventPool {
+    std::vector<std::pair<int, cudaEvent_t>> free_events;
+    ~TimerEventPool() {
+        for (auto &e : free_events) cudaEventDestroy(e.second);
+    }
+    cudaEvent_t take(int dev) {
+        for (size_t i = 0; i < free_events.size(); ++i)
+            if (free_events[i].first == dev) {
+                cudaEvent_t e = free_events[i].second;
+                free_events[i] = free_events.back();
+                free_events.pop_back();
+                return e;
+            }
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        return e;
+    }
+    void give(int dev, cudaEvent_t e) {
+        if (free_events.size() < 64) free_events.emplace_back(dev, e);
+        else cudaEventDestroy(e);
+    }
+};
+thread_local TimerEventPool t_timer_events;
+
 struct Timer {
     cudaEvent_t a, b;
+    int dev = 0;
     Timer() {
-        CK(cudaEventCreate(&a));
-        CK(cudaEventCreate(&b));
+        if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+        a = t_timer_events.take(dev);
+        b = t_timer_events.take(dev);
     }
     ~Timer() {
-        cudaEventDestroy(a);
-        cudaEventDestroy(b);
+        t_timer_events.give(dev, a);
+        t_timer_events.give(dev, b);
     }
     void start() { CK(cudaEventRecord(a, stream())); }
     void stop() { CK(cudaEventRecord(b, stream())); }
@@ -317,6 +345,19 @@ struct Timer {
         float t = 0.f;
         CK(cudaEventElapsedTime(&t, a, b));
         return t;
+    }
+};
+
+struct EventPairs {
+    std::vector<cudaEvent_t> ev;
+    ~EventPairs() {
+        for (auto e : ev) cudaEventDestroy(e);
+    }
+    cudaEvent_t next() {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        ev.push_back(e);
+        return e;
     }
 };
 
@@ -426,6 +467,7 @@ struct fm_partition {
     std::vector<fm_group *> groups;  // one bitplane group per subpopulation
     fm_group *rest = nullptr;        // haplotypes with no group (needed for "alleles present")
     std::mutex mu;
+    uint32_t *d_counts_slab = nullptr;  // (alt, called) arrays of all G + 1 count-only groups in one block
     double *d_wc_tab = nullptr;      // K4 reciprocal tables: RN(1/n) | RN(2/n^2), n = 0 .. wc_n_max
     uint32_t wc_n_max = 0;
 };
@@ -722,35 +764,53 @@ bool launch_plane_pass_tab(std::vector<fm::TabSeg> &segs, uint32_t gpu, const st
     if (G.n_stages < 2) return false;
     G.n_batches = (uint32_t)total;
     G.batch_counter = t_counters.take(device);
-    keep.d_segs.alloc(segs.size());
-    keep.d_segs.upload(segs.data(), segs.size());
-    keep.d_prefix.alloc(n_units + 1);
-    keep.d_prefix.upload(keep.prefix.data(), n_units + 1);
-    if (hud) {
-        if (hud->size() != n_units) fail(FM_ERR_INVALID_ARG, "internal: one Hudson epilogue per unit");
-        keep.d_hud.alloc(n_units);
-        keep.d_hud.upload(hud->data(), n_units);
-        P.hud = keep.d_hud.p;
+    if (hud && hud->size() != n_units) fail(FM_ERR_INVALID_ARG, "internal: one Hudson epilogue per unit");
+    if (n_units == 1) {  // the whole table fits the kernel parameters
+        P.use_inline = 1;
+        for (uint32_t g = 0; g < gpu; ++g) P.inline_segs[g] = segs[g];
+        P.inline_prefix[0] = keep.prefix[0];
+        P.inline_prefix[1] = keep.prefix[1];
+        if (hud) {
+            P.has_inline_hud = 1;
+            P.inline_hud = (*hud)[0];
+        }
+    } else {
+        keep.d_segs.alloc(segs.size());
+        keep.d_segs.upload(segs.data(), segs.size());
+        keep.d_prefix.alloc(n_units + 1);
+        keep.d_prefix.upload(keep.prefix.data(), n_units + 1);
+        if (hud) {
+            keep.d_hud.alloc(n_units);
+            keep.d_hud.upload(hud->data(), n_units);
+            P.hud = keep.d_hud.p;
+        }
+        // (pageable sources are staged by the driver before cudaMemcpyAsync returns: the host vectors may go away)
+        P.segs = keep.d_segs.p;
+        P.unit_prefix = keep.d_prefix.p;
     }
-    // (pageable sources are staged by the driver before cudaMemcpyAsync returns: the host vectors may go away)
-    P.segs = keep.d_segs.p;
-    P.unit_prefix = keep.d_prefix.p;
     P.n_units = (uint32_t)n_units;
     P.gpu = gpu;
     const size_t smem = (size_t)fm::kWarpsPerCta * warp_smem;
     const uint32_t grid = std::min<uint32_t>((uint32_t)sm_count(device),
                                              (uint32_t)((total * gpu + fm::kWarpsPerCta - 1) / fm::kWarpsPerCta));
-#define FM_TAB_CASE(L)                                                                                              \
-    case L:                                                                                                         \
-        if (hc) {                                                                                                   \
-            CK(cudaFuncSetAttribute(fm::fm_k_plane_pass_tab<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                    (int)smem));                                                                    \
-            fm::fm_k_plane_pass_tab<L, true><<<grid, fm::kWarpsPerCta * 32, smem, stream()>>>(P);                   \
-        } else {                                                                                                    \
-            CK(cudaFuncSetAttribute(fm::fm_k_plane_pass_tab<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                    (int)smem));                                                                    \
-            fm::fm_k_plane_pass_tab<L, false><<<grid, fm::kWarpsPerCta * 32, smem, stream()>>>(P);                  \
-        }                                                                                                           \
+    // the dynamic shared-memory limit is a per-device function attribute: set it once per (instantiation, device)
+    static std::mutex attr_mu;
+    static bool attr_done[10][64] = {};
+    auto once = [&](int slot, auto kern) {
+        std::lock_guard<std::mutex> lk(attr_mu);
+        if (device < 64 && attr_done[slot][device]) return;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (device < 64) attr_done[slot][device] = true;
+    };
+#define FM_TAB_CASE(L)                                                                                \
+    case L:                                                                                           \
+        if (hc) {                                                                                     \
+            once(2 * L, fm::fm_k_plane_pass_tab<L, true>);                                            \
+            fm::fm_k_plane_pass_tab<L, true><<<grid, fm::kWarpsPerCta * 32, smem, stream()>>>(P);     \
+        } else {                                                                                      \
+            once(2 * L + 1, fm::fm_k_plane_pass_tab<L, false>);                                       \
+            fm::fm_k_plane_pass_tab<L, false><<<grid, fm::kWarpsPerCta * 32, smem, stream()>>>(P);    \
+        }                                                                                             \
         break;
     switch (lg) {
         FM_TAB_CASE(0) FM_TAB_CASE(1) FM_TAB_CASE(2) FM_TAB_CASE(3) FM_TAB_CASE(4)
@@ -1340,7 +1400,11 @@ static size_t repack_warp_smem(const fm_matrix *m, uint32_t *row_buf_out, uint32
 static size_t repack_smem_limit(const fm_matrix *m) { return m->packed ? 100 * 1024 : 24 * 1024; }
 static bool row_fits_smem(const fm_matrix *m) { return repack_warp_smem(m, nullptr, nullptr) <= repack_smem_limit(m); }
 
-static fm_group *alloc_group(fm_matrix *m, std::vector<uint32_t> &&off, bool count_only = false) {
+// counts_slab: when non-null, a count-only group takes its alt / called arrays from the caller's slab (a W&C
+// partition allocates ONE block for all its groups: 54 separate cudaMallocs of 40 MB were 0.3 s of a cold
+// fm_partition_create over 10M sites, two orders of magnitude more than the count kernel itself)
+static fm_group *alloc_group(fm_matrix *m, std::vector<uint32_t> &&off, bool count_only = false,
+                             uint32_t *counts_slab = nullptr) {
     uint32_t n_bits = 1;
     while ((1u << n_bits) <= m->max_allele) ++n_bits;
     if (n_bits > 4)
@@ -1356,7 +1420,10 @@ static fm_group *alloc_group(fm_matrix *m, std::vector<uint32_t> &&off, bool cou
         g->n_bits = n_bits;
         g->count_only = count_only && n_bits == 1 && row_fits_smem(m);
         const size_t plane_u4 = std::max<size_t>(m->V, 1) * g->wq;
-        if (g->count_only) {
+        if (g->count_only && counts_slab) {
+            g->d_alt = counts_slab;  // interior pointers: dev_free ignores them, the partition frees the slab
+            g->d_cnt = counts_slab + std::max<size_t>(m->V, 1);
+        } else if (g->count_only) {
             g->d_alt = static_cast<uint32_t *>(dev_alloc(std::max<size_t>(m->V, 1) * sizeof(uint32_t)));
             g->d_cnt = static_cast<uint32_t *>(dev_alloc(std::max<size_t>(m->V, 1) * sizeof(uint32_t)));
         } else {
@@ -2224,7 +2291,11 @@ fm_status fm_ingest_add_partition(fm_ingest *h, const uint16_t *left, const uint
         fm_matrix_retain(h->m);
         try {
             std::vector<std::vector<uint32_t>> cols = partition_columns(h->m, left, right, n_samples, n_groups);
-            for (size_t g = 0; g <= n_groups; ++g) p->groups.push_back(alloc_group(h->m, std::move(cols[g]), true));
+            set_dev(h->m);
+            const size_t per = 2 * std::max<size_t>(h->m->V, 1);
+            p->d_counts_slab = static_cast<uint32_t *>(dev_alloc((n_groups + 1) * per * sizeof(uint32_t)));
+            for (size_t g = 0; g <= n_groups; ++g)
+                p->groups.push_back(alloc_group(h->m, std::move(cols[g]), true, p->d_counts_slab + g * per));
         } catch (...) {
             fm_partition_release(p);
             throw;
@@ -2779,7 +2850,11 @@ fm_status fm_partition_create(fm_matrix *m, const uint16_t *left, const uint16_t
                 fail(FM_ERR_UNSUPPORTED,
                      "this matrix was ingested in streaming mode: declare partitions with fm_ingest_add_partition");
             std::vector<std::vector<uint32_t>> cols = partition_columns(m, left, right, n_samples, n_groups);
-            for (size_t g = 0; g <= n_groups; ++g) p->groups.push_back(alloc_group(m, std::move(cols[g]), true));
+            set_dev(m);
+            const size_t per = 2 * std::max<size_t>(m->V, 1);
+            p->d_counts_slab = static_cast<uint32_t *>(dev_alloc((n_groups + 1) * per * sizeof(uint32_t)));
+            for (size_t g = 0; g <= n_groups; ++g)
+                p->groups.push_back(alloc_group(m, std::move(cols[g]), true, p->d_counts_slab + g * per));
             repack_resident(m, p->groups);  // the u8 matrix is read once for all G + 1 groups
         } catch (...) {
             fm_partition_release(p);
@@ -2794,6 +2869,7 @@ fm_status fm_partition_release(fm_partition *p) {
     if (p->m) cudaSetDevice(p->m->device);
     dev_free(p->d_wc_tab);
     for (fm_group *g : p->groups) fm_group_release(g);
+    dev_free(p->d_counts_slab);
     fm_matrix_release(p->m);
     delete p;
     return FM_OK;
@@ -3331,8 +3407,9 @@ struct fm_comm {
     bool ipc_opened[fm::kCommMaxRanks] = {};
     bool connected = false;
     unsigned long long step = 0;
-    uint32_t *d_status = nullptr;
+    uint32_t *d_status = nullptr;  // = d_merged + kCommMaxValues: merged words and status travel in one copy
     unsigned long long *d_local = nullptr, *d_gathered = nullptr, *d_merged = nullptr;
+    unsigned long long *h_result = nullptr;  // pinned: [kCommMaxValues + 1], small results land here asynchronously
     // An exchange waits for the slowest rank like any collective; the timeout only exists so that a rank that
     // died cannot hang the GPU for ever (0 = no timeout).  Ranks may legitimately be far apart (unequal shard
     // work, host I/O between calls), hence minutes, not seconds.
@@ -3368,6 +3445,23 @@ void comm_launch(fm_comm *c, const unsigned long long *d_local, uint32_t n_words
     CK(cudaGetLastError());
     g_launches++;
 }
+void comm_report_timeout(fm_comm *c);
+// merged words [0, n_words) + the status word in ONE asynchronous copy into pinned memory, then one synchronise
+const unsigned long long *comm_fetch_merged(fm_comm *c, uint32_t n_words) {
+    // status sits at word kCommMaxValues: copy the leading words and the status word (two small async copies into
+    // pinned memory cost ~2 us each; a pageable destination would make each a blocking driver round trip)
+    if (n_words) CK(cudaMemcpyAsync(c->h_result, c->d_merged, (size_t)n_words * 8, cudaMemcpyDeviceToHost, stream()));
+    CK(cudaMemcpyAsync(c->h_result + fm::kCommMaxValues, c->d_merged + fm::kCommMaxValues, 8, cudaMemcpyDeviceToHost,
+                       stream()));
+    CK(cudaStreamSynchronize(stream()));
+    if ((uint32_t)c->h_result[fm::kCommMaxValues] != 0) comm_report_timeout(c);
+    return c->h_result;
+}
+void comm_report_timeout(fm_comm *c) {
+    CK(cudaMemsetAsync(c->d_status, 0, 4, stream()));
+    CK(cudaStreamSynchronize(stream()));
+    fail(FM_ERR_CUDA, "peer exchange timed out waiting for another rank (fm_comm_set_timeout_ms raises the limit)");
+}
 void comm_check_status(fm_comm *c) {
     uint32_t st = 0;
     CK(cudaMemcpyAsync(&st, c->d_status, 4, cudaMemcpyDeviceToHost, stream()));
@@ -3399,10 +3493,11 @@ fm_status fm_comm_create(int rank, int world, fm_comm **out) {
             // plain cudaMalloc (not the cache): the allocation is exported through cudaIpc
             CK(cudaMalloc((void **)&c->mine, sizeof(fm::CommMailbox)));
             CK(cudaMemset(c->mine, 0, sizeof(fm::CommMailbox)));
-            CK(cudaMalloc((void **)&c->d_status, 256));
-            CK(cudaMemset(c->d_status, 0, 256));
             CK(cudaMalloc((void **)&c->d_local, fm::kCommMaxValues * 8));
-            CK(cudaMalloc((void **)&c->d_merged, fm::kCommMaxValues * 8));
+            CK(cudaMalloc((void **)&c->d_merged, (fm::kCommMaxValues + 32) * 8));
+            CK(cudaMemset(c->d_merged, 0, (fm::kCommMaxValues + 32) * 8));
+            c->d_status = reinterpret_cast<uint32_t *>(c->d_merged + fm::kCommMaxValues);
+            CK(cudaHostAlloc((void **)&c->h_result, (fm::kCommMaxValues + 32) * 8, cudaHostAllocDefault));
             CK(cudaMalloc((void **)&c->d_gathered, (size_t)world * fm::kCommMaxValues * 8));
             CK(cudaDeviceSynchronize());
             c->peers[rank] = c->mine;
@@ -3514,7 +3609,7 @@ fm_status fm_comm_destroy(fm_comm *c) {
     for (int r = 0; r < c->world; ++r)
         if (c->ipc_opened[r]) cudaIpcCloseMemHandle(c->peers[r]);
     if (!leak_mailbox) cudaFree(c->mine);
-    cudaFree(c->d_status);
+    if (c->h_result) cudaFreeHost(c->h_result);
     cudaFree(c->d_local);
     cudaFree(c->d_merged);
     cudaFree(c->d_gathered);
@@ -3557,6 +3652,14 @@ fm_status fm_hudson_pair_sharded(fm_group *g1, fm_group *g2, int64_t sequence_le
         he.part_d = pd.p;
         he.part_u = pu.p;
         Timer tm;
+        static const uint32_t trace = env_u32("FM_SHARDED_TRACE", 0);  // stage timings on stderr (tuning)
+        EventPairs tev;
+        cudaEvent_t te[4] = {nullptr, nullptr, nullptr, nullptr};
+        const auto th0 = std::chrono::steady_clock::now();
+        if (trace) {
+            for (auto &e : te) e = tev.next();
+            CK(cudaEventRecord(te[0], stream()));
+        }
         tm.start();
         if (V) {
             bool done = false;
@@ -3585,7 +3688,9 @@ fm_status fm_hudson_pair_sharded(fm_group *g1, fm_group *g2, int64_t sequence_le
             fm::PassGeom G{};
             G.b_lo = 0;
             G.n_batches = nb;
+            if (trace) CK(cudaEventRecord(te[1], stream()));
             launch_reduce(pd.p, 5, pu.p, 3, G, sd.p, su.p, stream());
+            if (trace) CK(cudaEventRecord(te[2], stream()));
             // `keep` (the descriptor table) goes back to the allocator here: the block carries an event on this
             // stream, so a later owner waits for the pass -- no host synchronisation needed
         }
@@ -3593,20 +3698,28 @@ fm_status fm_hudson_pair_sharded(fm_group *g1, fm_group *g2, int64_t sequence_le
         if (comm) {
             fm::CommFold fold{sd.p, reinterpret_cast<const unsigned long long *>(su.p), n_super, 5u, 3u};
             comm_launch(comm, nullptr, 8, 0, &fold, 1, stream());
-            CK(cudaMemcpyAsync(w, comm->d_merged, sizeof(w), cudaMemcpyDeviceToHost, stream()));
-            comm_check_status(comm);
+            if (trace) CK(cudaEventRecord(te[3], stream()));
+            std::memcpy(w, comm_fetch_merged(comm, 8), sizeof(w));
+            if (trace && V) {
+                float a = 0, b = 0, c = 0;
+                cudaEventElapsedTime(&a, te[0], te[1]);
+                cudaEventElapsedTime(&b, te[1], te[2]);
+                cudaEventElapsedTime(&c, te[2], te[3]);
+                const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - th0).count();
+                fprintf(stderr, "[sharded rank %d] pass %.1f us, fold %.1f us, exchange %.1f us, host total %.1f us\n", comm->rank,
+                        a * 1e3, b * 1e3, c * 1e3, host_ms * 1e3);
+            }
         } else {
             std::vector<double> hd((size_t)n_super * 5);
             std::vector<uint64_t> hu((size_t)n_super * 3);
             sd.download(hd.data(), hd.size());
             su.download(hu.data(), hu.size());
             CK(cudaStreamSynchronize(stream()));
-            double d[5] = {0, 0, 0, 0, 0};
+            double d[5];
             uint64_t u[3] = {0, 0, 0};
-            for (uint32_t sb = 0; sb < n_super; ++sb) {  // fixed order
-                for (int i = 0; i < 5; ++i) d[i] += hd[(size_t)sb * 5 + i];
+            for (int i = 0; i < 5; ++i) d[i] = fm::fm_comm_fold_host(hd.data(), n_super, 5, i);  // the exchange kernel's fold
+            for (uint32_t sb = 0; sb < n_super; ++sb)
                 for (int i = 0; i < 3; ++i) u[i] += hu[(size_t)sb * 3 + i];
-            }
             std::memcpy(w, d, sizeof(d));
             for (int i = 0; i < 3; ++i) w[5 + i] = u[i];
         }
@@ -4409,18 +4522,6 @@ fm_status fm_synth_fill(uint8_t *d_data, uint64_t *d_missing, size_t V, size_t S
 
 // ------------------------------------------------------------------------------------ bench hooks
 namespace {
-struct EventPairs {
-    std::vector<cudaEvent_t> ev;
-    ~EventPairs() {
-        for (auto e : ev) cudaEventDestroy(e);
-    }
-    cudaEvent_t next() {
-        cudaEvent_t e;
-        CK(cudaEventCreate(&e));
-        ev.push_back(e);
-        return e;
-    }
-};
 
 void launch_reduce(const double *pd, int nd, const uint32_t *pu, int nu, const fm::PassGeom &G, double *sd,
                    uint64_t *su, cudaStream_t st = nullptr) {
@@ -4647,8 +4748,8 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
             pg[i].sd[pl].download(hd.data(), n_super);
             pg[i].su[pl].download(hu.data(), (size_t)n_super * 2);
             CK(cudaStreamSynchronize(stream()));
+            out->last_pi_sum[i] = fm::fm_comm_fold_host(hd.data(), n_super, 1, 0);  // association of the exchange fold
             for (uint32_t sb = 0; sb < n_super; ++sb) {
-                out->last_pi_sum[i] += hd[sb];
                 out->last_seg[i] += hu[2 * (size_t)sb];
                 out->last_unc[i] += hu[2 * (size_t)sb + 1];
             }

@@ -1365,6 +1365,12 @@ struct TabParams {
     uint32_t n_units, gpu;         // gpu = segments (groups) per unit: 1 or 2
     const HudsonEpilogue *hud;     // [n_units] Hudson epilogues (gpu == 2) or nullptr
     PassGeom geom;                 // lps, n_stages, stage_bytes, warps, warp_smem_bytes, n_batches (total), counters
+    // a single unit travels in the kernel parameters themselves (no descriptor upload: three small H2D copies
+    // are ~20 us of a 250 us sharded step); use_inline selects these instead of the pointers above
+    uint32_t use_inline, has_inline_hud;
+    TabSeg inline_segs[2];
+    HudsonEpilogue inline_hud;
+    uint32_t inline_prefix[2];
 };
 
 template <int LG, bool HC>
@@ -1386,6 +1392,9 @@ fm_k_plane_pass_tab(const __grid_constant__ TabParams P) {
     const uint32_t stage_bytes = G.stage_bytes;
     const uint32_t n_batches = G.n_batches;  // whole launch
     const uint32_t gpu = P.gpu;
+    const TabSeg *const segs = P.use_inline ? P.inline_segs : P.segs;
+    const uint32_t *const unit_prefix = P.use_inline ? P.inline_prefix : P.unit_prefix;
+    const HudsonEpilogue *const hud = P.use_inline ? (P.has_inline_hud ? &P.inline_hud : nullptr) : P.hud;
 
     const uint32_t smem_base = fm_smem_u32(smem_raw) + warp * G.warp_smem_bytes;
     const uint32_t bar_base = fm_smem_u32(bars + warp * kMaxStages);
@@ -1419,7 +1428,7 @@ fm_k_plane_pass_tab(const __grid_constant__ TabParams P) {
         uint32_t lo = 0, hi = P.n_units;
         while (hi - lo > 1) {
             const uint32_t mid = (lo + hi) >> 1;
-            if (__ldg(P.unit_prefix + mid) <= gb) lo = mid; else hi = mid;
+            if (unit_prefix[mid] <= gb) lo = mid; else hi = mid;
         }
         return lo;
     };
@@ -1430,7 +1439,7 @@ fm_k_plane_pass_tab(const __grid_constant__ TabParams P) {
     const uint4 *iss_allele = nullptr, *iss_called = nullptr;
     bool iss_live = false;
     auto load_iss_seg = [&]() {
-        const TabSeg &S = P.segs[iss_unit * gpu + iss_g];
+        const TabSeg &S = segs[iss_unit * gpu + iss_g];
         iss_w16 = S.g.wq * 16u;
         iss_step_sites = SPS * S.rounds;
         iss_spb = LPS / S.rounds;
@@ -1481,7 +1490,7 @@ fm_k_plane_pass_tab(const __grid_constant__ TabParams P) {
                 iss_unit = unit_of(iss_batch);
                 iss_g = 0;
                 load_iss_seg();
-                iss_b = P.segs[iss_unit * gpu].b_lo + (iss_batch - __ldg(P.unit_prefix + iss_unit));
+                iss_b = segs[iss_unit * gpu].b_lo + (iss_batch - unit_prefix[iss_unit]);
             }
         }
         if (lane == 0) issue(iss_stage);
@@ -1502,11 +1511,11 @@ fm_k_plane_pass_tab(const __grid_constant__ TabParams P) {
         ++con_ring;
         if (gb >= n_batches) break;
         const uint32_t unit = unit_of(gb);
-        const uint32_t bl = gb - __ldg(P.unit_prefix + unit);  // batch inside the unit's range
+        const uint32_t bl = gb - unit_prefix[unit];  // batch inside the unit's range
         uint32_t alt_g0 = 0, cnt_g0 = 0, alt_g1 = 0, cnt_g1 = 0;
         uint32_t b = 0, u_vlo = 0, u_vhi = 0;
         for (uint32_t g = 0; g < gpu; ++g) {
-            const TabSeg &S = P.segs[unit * gpu + g];
+            const TabSeg &S = segs[unit * gpu + g];
             const uint32_t w = S.g.wq, w16 = w * 16u, rounds = S.rounds;
             const uint32_t step_sites = SPS * rounds, spb = LPS / rounds;
             const uint32_t nit = (w + LPS - 1) / LPS;
@@ -1594,8 +1603,8 @@ fm_k_plane_pass_tab(const __grid_constant__ TabParams P) {
                 }
             }
         }
-        if (gpu == 2 && P.hud) {  // ---- Hudson components of the batch from both groups' counts
-            const HudsonEpilogue &H = P.hud[unit];
+        if (gpu == 2 && hud) {  // ---- Hudson components of the batch from both groups' counts
+            const HudsonEpilogue &H = hud[unit];
             const uint32_t v = b * 32 + lane;
             HudsonAcc acc{0.0, 0.0, 0.0, 0.0, 0.0, 0u, 0u, 0u};
             if (v >= u_vlo && v < u_vhi) fm_hudson_contrib(H, v, u_vlo, cnt_g0, alt_g0, cnt_g1, alt_g1, acc);
