@@ -9,6 +9,8 @@
 #include "fm_falsta.cuh"
 #include "fm_vcf.cuh"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <cub/device/device_scan.cuh>
 #include <thrust/iterator/transform_iterator.h>
 #include <cuda/std/functional>
@@ -65,6 +67,16 @@ struct FmError {
                  buf_);                                                                       \
         }                                                                                     \
     } while (0)
+
+// NVTX ranges around the stages of the path (tracing): ingest / repack / plane pass / exchange / W&C /
+// VCF / FALSTA show up as named ranges in Nsight Systems and ncu --nvtx; free when no profiler is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
+#define FM_NVTX(name) NvtxRange nvtx_range_(name)
 
 template <class F>
 fm_status guarded(F &&f) {
@@ -1261,6 +1273,7 @@ fm_status fm_matrix_create(const uint8_t *data, const uint64_t *missing, size_t 
                            size_t ploidy, uint8_t max_allele, const int64_t *positions,
                            fm_matrix **out) {
     return guarded([&] {
+        FM_NVTX("fm_matrix_create (H2D u8)");
         if (!out) fail(FM_ERR_INVALID_ARG, "out is NULL");
         *out = nullptr;
         require_device();
@@ -1744,6 +1757,7 @@ static std::vector<std::vector<uint32_t>> partition_columns(const fm_matrix *m, 
 fm_status fm_group_create(fm_matrix *m, const uint64_t *sample_idx, const uint8_t *side, size_t n,
                           fm_group **out) {
     return guarded([&] {
+        FM_NVTX("fm_group_create (K1 repack)");
         if (!out || !m) fail(FM_ERR_INVALID_ARG, "NULL argument");
         *out = nullptr;
         if (n && (!sample_idx || !side)) fail(FM_ERR_INVALID_ARG, "haplotype arrays are NULL");
@@ -1756,6 +1770,7 @@ fm_status fm_group_create(fm_matrix *m, const uint64_t *sample_idx, const uint8_
 fm_status fm_groups_create(fm_matrix *m, const uint64_t *sample_idx, const uint8_t *side, const size_t *group_sizes,
                            size_t n_groups, fm_group **out) {
     return guarded([&] {
+        FM_NVTX("fm_groups_create (K1 repack)");
         if (!out || !m) fail(FM_ERR_INVALID_ARG, "NULL argument");
         for (size_t g = 0; g < n_groups; ++g) out[g] = nullptr;
         if (n_groups && !group_sizes) fail(FM_ERR_INVALID_ARG, "group_sizes is NULL");
@@ -1804,6 +1819,7 @@ fm_status fm_group_capacity(const fm_group *g, size_t *cap) {
 fm_status fm_group_summary(fm_group *g, uint32_t *alt_out, uint32_t *called_out, uint64_t *seg,
                            double *pi_sum, uint64_t *unc) {
     return guarded([&] {
+        FM_NVTX("fm_group_summary (K2 plane pass)");
         if (!g) fail(FM_ERR_INVALID_ARG, "group is NULL");
         require_device();
         if (g->n_bits > 1 && alt_out)
@@ -1940,6 +1956,7 @@ static void summarize_groups(fm_group *const *groups, size_t n_groups) {
 fm_status fm_groups_summary_batch(fm_group *const *groups, size_t n_groups, uint64_t *seg_out, double *pi_sum_out,
                                   uint64_t *unc_out) {
     return guarded([&] {
+        FM_NVTX("fm_groups_summary_batch (table plane pass)");
         summarize_groups(groups, n_groups);
         for (size_t i = 0; i < n_groups; ++i) {
             const fm_group *g = groups[i];
@@ -2035,6 +2052,7 @@ fm_status fm_per_site_diversity(fm_group *g, size_t raw_n, int64_t rs, int64_t r
                                 size_t n_mask, const int64_t *filtered, size_t n_filt, int64_t *pos_out,
                                 double *pi_out, double *theta_out, size_t capacity, size_t *n_out) {
     return guarded([&] {
+        FM_NVTX("fm_per_site_diversity (K2 plane pass + tracks)");
         if (!g || !n_out) fail(FM_ERR_INVALID_ARG, "NULL argument");
         *n_out = 0;
         require_device();
@@ -2086,6 +2104,7 @@ fm_status fm_per_site_diversity_multi(fm_group *const *groups, const size_t *raw
                                       size_t n_filt, int64_t *pos_out, double *pi_out, double *theta_out,
                                       size_t capacity, size_t *n_out) {
     return guarded([&] {
+        FM_NVTX("fm_per_site_diversity_multi (fused plane pass + tracks)");
         if (!groups || !n_groups || !n_out || !raw_n) fail(FM_ERR_INVALID_ARG, "NULL argument");
         *n_out = 0;
         require_device();
@@ -2309,6 +2328,7 @@ fm_status fm_ingest_add_partition(fm_ingest *h, const uint16_t *left, const uint
 fm_status fm_ingest_rows(fm_ingest *h, const uint8_t *rows, const uint64_t *missing_whole, size_t first_row,
                          size_t n_rows) {
     return guarded([&] {
+        FM_NVTX("fm_ingest_rows (H2D u8 + K1 repack)");
         if (!h) fail(FM_ERR_INVALID_ARG, "ingest handle is NULL");
         fm_matrix *m = h->m;
         if (first_row > m->V || n_rows > m->V - first_row) fail(FM_ERR_INVALID_ARG, "row range outside the matrix");
@@ -2403,6 +2423,7 @@ fm_status fm_pack_rows_generic(const uint8_t *rows, const uint64_t *missing_whol
 fm_status fm_ingest_rows_packed(fm_ingest *h, const uint32_t *allele_bits, const uint32_t *called_bits,
                                 size_t first_row, size_t n_rows) {
     return guarded([&] {
+        FM_NVTX("fm_ingest_rows_packed (H2D packed + K1p compress)");
         if (!h) fail(FM_ERR_INVALID_ARG, "ingest handle is NULL");
         fm_matrix *m = h->m;
         if (first_row > m->V || n_rows > m->V - first_row) fail(FM_ERR_INVALID_ARG, "row range outside the matrix");
@@ -2454,6 +2475,7 @@ fm_status fm_ingest_rows_packed(fm_ingest *h, const uint32_t *allele_bits, const
 fm_status fm_ingest_rows_pack(fm_ingest *h, const uint8_t *rows, const uint64_t *missing_whole, size_t first_row,
                               size_t n_rows, int n_threads) {
     return guarded([&] {
+        FM_NVTX("fm_ingest_rows_pack (host pack + H2D + K1p)");
         if (!h) fail(FM_ERR_INVALID_ARG, "ingest handle is NULL");
         fm_matrix *m = h->m;
         if (first_row > m->V || n_rows > m->V - first_row) fail(FM_ERR_INVALID_ARG, "row range outside the matrix");
@@ -2512,6 +2534,7 @@ fm_status fm_ingest_rows_pack(fm_ingest *h, const uint8_t *rows, const uint64_t 
 fm_status fm_matrix_create_packed(const uint32_t *allele_bits, const uint32_t *called_bits, size_t V, size_t S,
                                   size_t ploidy, const int64_t *positions, fm_matrix **out) {
     return guarded([&] {
+        FM_NVTX("fm_matrix_create_packed (H2D packed rows)");
         if (!out) fail(FM_ERR_INVALID_ARG, "out is NULL");
         *out = nullptr;
         require_device();
@@ -2639,6 +2662,7 @@ fm_status fm_hudson_pair(fm_group *g1, fm_group *g2, int64_t L1, int64_t L2, int
                          int64_t rs, int64_t re, size_t raw_n1, size_t raw_n2, fm_hudson_outcome *out,
                          fm_hudson_sites *sites, size_t *n_sites) {
     return guarded([&] {
+        FM_NVTX("fm_hudson_pair (K3 fused pass / light kernel)");
         if (!out) fail(FM_ERR_INVALID_ARG, "out is NULL");
         std::memset(out, 0, sizeof(*out));
         if (n_sites) *n_sites = 0;
@@ -2836,6 +2860,7 @@ fm_status fm_hudson_pair(fm_group *g1, fm_group *g2, int64_t L1, int64_t L2, int
 fm_status fm_partition_create(fm_matrix *m, const uint16_t *left, const uint16_t *right, size_t n_samples,
                               size_t n_groups, fm_partition **out) {
     return guarded([&] {
+        FM_NVTX("fm_partition_create (K1 count pass)");
         if (!out || !m) fail(FM_ERR_INVALID_ARG, "NULL argument");
         *out = nullptr;
         if (n_samples && (!left || !right)) fail(FM_ERR_INVALID_ARG, "membership arrays are NULL");
@@ -3139,6 +3164,7 @@ fm_status fm_wc_fst(fm_partition *p, int64_t rs, int64_t re, fm_fst_estimate *ov
                     uint8_t *pair_present, int64_t *site_pos, int32_t *site_state, double *site_a, double *site_b,
                     uint32_t *site_pop_sizes, double *pair_a, double *pair_b, size_t capacity, size_t *n_sites_out) {
     return guarded([&] {
+        FM_NVTX("fm_wc_fst (K4)");
         if (!p || !overall) fail(FM_ERR_INVALID_ARG, "NULL argument");
         if (n_sites_out) *n_sites_out = 0;
         require_device();
@@ -3192,6 +3218,7 @@ fm_status fm_wc_window_sums(fm_partition *p, const int64_t *windows, size_t n_wi
                             double *overall_a, double *overall_b, uint64_t *overall_sites, double *pair_a,
                             double *pair_b, uint64_t *pair_sites) {
     return guarded([&] {
+        FM_NVTX("fm_wc_window_sums (K4)");
         if (!p || (n_windows && !windows)) fail(FM_ERR_INVALID_ARG, "NULL argument");
         require_device();
         if (!n_windows) return;
@@ -3559,6 +3586,7 @@ fm_status fm_comm_connect_local(fm_comm *c, fm_comm *const *all) {
 fm_status fm_comm_allgather(fm_comm *c, const void *local, size_t n_words, size_t n_double, void *gathered_out,
                             void *merged_out) {
     return guarded([&] {
+        FM_NVTX("fm_comm_allgather (NVLink mailbox exchange)");
         if (!c || (n_words && !local)) fail(FM_ERR_INVALID_ARG, "NULL argument");
         if (n_words > fm::kCommMaxValues) fail(FM_ERR_INVALID_ARG, "too many values for one exchange");
         CK(cudaSetDevice(c->device));
@@ -3631,6 +3659,7 @@ void launch_reduce(const double *pd, int nd, const uint32_t *pu, int nu, const f
 fm_status fm_hudson_pair_sharded(fm_group *g1, fm_group *g2, int64_t sequence_length, size_t raw_n1, size_t raw_n2,
                                  fm_comm *comm, fm_hudson_outcome *out, fm_hudson_sums *merged_out) {
     return guarded([&] {
+        FM_NVTX("fm_hudson_pair_sharded (pass + fold + NVLink exchange)");
         if (!out) fail(FM_ERR_INVALID_ARG, "out is NULL");
         std::memset(out, 0, sizeof(*out));
         if (sequence_length <= 0)
@@ -3756,6 +3785,7 @@ fm_status fm_falsta_tracks(const int64_t *pos1, const double *values, size_t n, 
                            int64_t region_end, int mode, char *out, size_t capacity, size_t *line_len,
                            size_t *len_out) {
     return guarded([&] {
+        FM_NVTX("fm_falsta_tracks");
         if (!len_out) fail(FM_ERR_INVALID_ARG, "len_out is NULL");
         *len_out = 0;
         if (n_tracks == 0) return;
@@ -4261,6 +4291,7 @@ fm_status fm_vcf_parse(const char *text, size_t n_bytes, const char *chr, const 
                        const int64_t *allow, size_t n_allow, int mask_mode, const int64_t *mask, size_t n_mask,
                        size_t max_ploidy, fm_vcf_batch **out) {
     return guarded([&] {
+        FM_NVTX("fm_vcf_parse");
         if (!out) fail(FM_ERR_INVALID_ARG, "out is NULL");
         *out = nullptr;
         if (n_bytes && !text) fail(FM_ERR_INVALID_ARG, "text is NULL");
@@ -4475,6 +4506,59 @@ fm_status fm_vcf_batch_matrix(const fm_vcf_batch *b, int pass_only, fm_matrix **
         } catch (...) {
             if (d_data) dev_free(d_data);
             if (m) fm_matrix_release(m);
+            throw;
+        }
+        *out = m;
+    });
+}
+
+// The same matrix as PACKED rows (2 bits per genotype, resident): the batch's genotypes go straight from the parser's
+// output to full-row bit words -- the reference-layout u8 matrix is never materialised.  Biallelic
+// batches only: when an allele index above 1 turns up the call fails with FM_ERR_UNSUPPORTED and the caller uses
+// fm_vcf_batch_matrix.
+fm_status fm_vcf_batch_matrix_packed(const fm_vcf_batch *b, int pass_only, fm_matrix **out) {
+    return guarded([&] {
+        FM_NVTX("fm_vcf_batch_matrix_packed");
+        if (!b || !out) fail(FM_ERR_INVALID_ARG, "batch or out is NULL");
+        *out = nullptr;
+        CK(cudaSetDevice(b->device));
+        std::vector<uint32_t> order;
+        std::vector<int64_t> pos;
+        size_t ploidy = 0;  // from_variants: longest genotype over the selected variants (stats.rs:349-359)
+        for (size_t i = 0; i < b->var.size(); ++i) {
+            if (pass_only && b->var[i].flags != 0) continue;
+            order.push_back(b->order[i]);
+            pos.push_back(b->var[i].pos0);
+            if (b->var[i].missing_points < b->S) ploidy = std::max<size_t>(ploidy, b->var[i].stride);
+        }
+        if (order.empty() || b->S == 0 || ploidy == 0) return;  // from_variants: None
+        const size_t V = order.size(), S = b->S;
+        fm_matrix *m = matrix_common(V, S, ploidy, 1, pos.data());
+        try {
+            m->has_missing = true;  // from_variants always returns Some(missing)
+            m->streamed = true;
+            ensure_packed_storage(m, true);
+            DevBuf<uint32_t> d_ord(V), d_max(1);
+            d_ord.upload(order.data(), V);
+            CK(cudaMemsetAsync(d_max.p, 0, 4, stream()));
+            const uint64_t words = (uint64_t)V * m->rw;
+            const uint32_t blocks = (uint32_t)std::min<uint64_t>((words + 255) / 256, 32ull * sm_count(b->device));
+            fm::fm_k_vcf_to_packed<<<std::max(blocks, 1u), 256, 0, stream()>>>(b->d_gt, d_ord.p, V, (uint32_t)S, (uint32_t)b->P,
+                                                                                (uint32_t)ploidy, m->rw, m->d_abits, m->d_cbits,
+                                                                                d_max.p);
+            CK(cudaGetLastError());
+            g_launches++;
+            uint32_t mx = 0;
+            CK(cudaMemcpyAsync(&mx, d_max.p, 4, cudaMemcpyDeviceToHost, stream()));
+            m->d_pos = static_cast<int64_t *>(dev_alloc(std::max<size_t>(V, 1) * 8));
+            CK(cudaMemcpyAsync(m->d_pos, m->pos.data(), V * 8, cudaMemcpyHostToDevice, stream()));
+            CK(cudaStreamSynchronize(stream()));
+            if (mx > 1)
+                fail(FM_ERR_UNSUPPORTED, "packed rows carry one allele bit per cell: this batch has allele indices above 1 "
+                                         "(use fm_vcf_batch_matrix)");
+            m->max_allele = (uint8_t)mx;
+        } catch (...) {
+            fm_matrix_release(m);
             throw;
         }
         *out = m;

@@ -612,6 +612,50 @@ fm_k_vcf_to_matrix_p2(const uint4 *__restrict__ gt, const uint32_t *__restrict__
     if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_allele, mx);
 }
 
+// from_variants straight into PACKED rows (no u8 matrix between the parser and the bitplanes): one
+// thread per output word = 32 cells c = sample * ploidy + side of row r; allele bit = the cell is called and its
+// allele index is non-zero, called bit = every side up to this one holds an allele (a 0xFF sentinel ends the
+// genotype, process.rs:430-478; absent sides of a short genotype are missing, stats.rs:452-460).  max_allele
+// receives the largest allele index: above 1 the packed form does not apply and the caller builds the u8 matrix.
+__global__ void __launch_bounds__(256)
+fm_k_vcf_to_packed(const uint8_t *__restrict__ gt, const uint32_t *__restrict__ order, uint64_t n_rows, uint32_t S,
+                   uint32_t P, uint32_t ploidy, uint32_t rw, uint32_t *__restrict__ abits, uint32_t *__restrict__ cbits,
+                   uint32_t *__restrict__ max_allele) {
+    const uint64_t total = n_rows * rw;
+    const uint32_t stride = S * ploidy;
+    uint32_t mx = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / rw;
+        const uint32_t w = (uint32_t)(i - r * rw);
+        const uint8_t *row = gt + (size_t)order[r] * S * P;
+        uint32_t a = 0, c = 0;
+        const uint32_t c0 = w * 32u, c1 = min(stride, c0 + 32u);
+        uint32_t s = c0 / ploidy, k = c0 - s * ploidy;
+        // validity of side k needs the sides before it: start at the sample's first side
+        bool valid = true;
+        for (uint32_t kk = 0; kk < k; ++kk) valid = valid && (kk < P ? row[(size_t)s * P + kk] : (uint8_t)0xFF) != 0xFF;
+        for (uint32_t cell = c0; cell < c1; ++cell) {
+            const uint8_t v = k < P ? row[(size_t)s * P + k] : (uint8_t)0xFF;
+            valid = valid && v != 0xFF;
+            if (valid) {
+                c |= 1u << (cell - c0);
+                if (v) a |= 1u << (cell - c0);
+                mx = max(mx, (uint32_t)v);
+            }
+            if (++k == ploidy) {
+                k = 0;
+                ++s;
+                valid = true;
+            }
+        }
+        abits[i] = a;
+        cbits[i] = c;
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_allele, mx);
+}
+
 __global__ void __launch_bounds__(256)
 fm_k_vcf_gather_rows(const uint8_t *__restrict__ gt, const uint32_t *__restrict__ order, uint64_t n_rows,
                      uint32_t row_bytes, uint8_t *__restrict__ out) {

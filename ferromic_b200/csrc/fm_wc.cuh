@@ -86,7 +86,9 @@ __host__ __device__ inline size_t fm_wc_cta_smem(uint32_t G) {
 
 // RN(1 / b) for a normal b far from the exponent limits (here b = 1 - c^2 in (0, 1]): hardware seed
 // (MUFU.RCP64H, ~23 bits), two Newton steps and one residual correction of the then faithful estimate.  Branch
-// free; tests/test_gpu_wc_arith.py compares it with IEEE 1.0 / b over 2^28 divisors.
+// free; tests/test_gpu_wc_arith.py compares it with IEEE 1.0 / b over 2^24 divisors.  The one divisor shape the
+// residual correction cannot round (Markstein) is an all-ones significand, e.g. 1 - 2^-53 -> 1.0 instead of
+// 1 + 2^-52; the callers' divisors cannot take that form.
 __device__ __forceinline__ double fm_recip_rn(double b) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
@@ -117,7 +119,8 @@ __device__ __forceinline__ void fm_wc_pair_site(const double4 vi, const double4 
     const double ssd = d1 * d1 + d2 * d2;  // 0.0 + d1*d1 == d1*d1 (never -0)
     const double c_squared = fm_div_recip(ssd, 2.0 * n_bar * n_bar, __ldg(T.inv_2nb2 + nsum));
     const double aden = 1.0 - c_squared;   // c_squared / (r - 1) with r - 1 == 1
-    const double raden = 1.0 / aden;
+    // 1 - c^2 is 1 exactly or at most 1 - 1/(n_i + n_j)^2: never the all-ones significand fm_recip_rn excludes
+    const double raden = fm_recip_rn(aden);
     const double ratio = fm_div_recip(n_bar, nbm1, r_nbm1);
     const double asd = vi.w + vj.w;     // exact
     // allele 0, then allele 1 (ascending order, stats.rs:1859)

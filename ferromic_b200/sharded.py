@@ -240,7 +240,13 @@ class CohortShard:
     pre-built api._Matrix; positions: 0-based positions of the shard's sites (ascending)."""
 
     def __init__(self, genotypes, positions, rank: int = 0, world: int = 1, device: Optional[int] = None,
-                 comm: Optional[PeerComm] = None):
+                 comm: Optional[PeerComm] = None, max_allele: Optional[int] = None, reduce_max=None):
+        """max_allele: the WHOLE cohort's largest allele index.  The reference picks its estimator forms
+        (biallelic / general) from the whole matrix's max_allele (stats.rs:490, lib.rs:779); a shard that happens
+        to hold only alleles 0/1 of a multi-allelic cohort must take the same forms as the others, or the merged
+        totals would mix roundings.  When it is not given, `reduce_max` (a callable int -> int returning the maximum
+        over all ranks, e.g. an all-reduce) is applied to the shard's own maximum; with neither, the shard's own
+        maximum is used (single-shard use)."""
         from .api import _Matrix
 
         self.rank, self.world = rank, world
@@ -255,8 +261,11 @@ class CohortShard:
             miss = g < 0 if g.dtype.kind == "i" else None
             alle = np.where(miss, 0, g).astype(np.uint8) if miss is not None else g.astype(np.uint8)
             # max_allele > 1: the multi-allelic general forms (per-allele counts) serve the same window totals
-            self.matrix = _Matrix(alle, miss, np.asarray(positions, dtype=np.int64),
-                                  max_allele=int(alle.max()) if alle.size else 0)
+            if max_allele is None:
+                max_allele = int(alle.max()) if alle.size else 0
+                if reduce_max is not None:
+                    max_allele = int(reduce_max(max_allele))
+            self.matrix = _Matrix(alle, miss, np.asarray(positions, dtype=np.int64), max_allele=int(max_allele))
         self.positions = np.asarray(positions, dtype=np.int64)
         self._partitions: Dict[int, C.c_void_p] = {}
 

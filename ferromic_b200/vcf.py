@@ -108,10 +108,23 @@ class VcfBatch:
             check(lib().fm_vcf_batch_genotypes(self.handle, gt.ctypes.data_as(C.c_void_p)))
         return gt
 
-    def matrix(self, pass_only: bool = False) -> Optional[_Matrix]:
-        """DenseGenotypeMatrix::from_variants over all variants (or the flags == 0 ones), on the device."""
+    def matrix(self, pass_only: bool = False, packed: Optional[bool] = None) -> Optional[_Matrix]:
+        """DenseGenotypeMatrix::from_variants over all variants (or the flags == 0 ones), on the device.
+        packed (default: FERROMIC_GPU_INGEST != "u8"): the genotypes go straight to packed bit rows
+        (fm_vcf_batch_matrix_packed) and the u8 matrix is never built; multi-allelic batches fall back to it."""
+        import os
+        from ._lib import FM_ERR_UNSUPPORTED
+        if packed is None:
+            packed = os.environ.get("FERROMIC_GPU_INGEST", "packed") != "u8"
         h = C.c_void_p()
-        check(lib().fm_vcf_batch_matrix(self.handle, int(bool(pass_only)), C.byref(h)))
+        st = FM_ERR_UNSUPPORTED
+        if packed:
+            st = lib().fm_vcf_batch_matrix_packed(self.handle, int(bool(pass_only)), C.byref(h))
+            if st != FM_ERR_UNSUPPORTED:
+                check(st)
+        if st == FM_ERR_UNSUPPORTED:
+            h = C.c_void_p()
+            check(lib().fm_vcf_batch_matrix(self.handle, int(bool(pass_only)), C.byref(h)))
         if not h:
             return None
         m = _Matrix.__new__(_Matrix)

@@ -466,6 +466,10 @@ fm_status fm_vcf_batch_errors(const fm_vcf_batch *b, uint64_t *line_index, int32
  * only those with flags == 0, the CLI's "filtered" set) without leaving the device.  *out is NULL
  * when from_variants would return None (no variants / no genotype data). */
 fm_status fm_vcf_batch_matrix(const fm_vcf_batch *b, int pass_only, fm_matrix **out);
+/* The same matrix as resident PACKED rows (2 bits per genotype): genotypes go from the parser's output
+ * straight to full-row bit words, the u8 matrix is never materialised.  Biallelic batches
+ * only -- FM_ERR_UNSUPPORTED when an allele index above 1 occurs (then use fm_vcf_batch_matrix). */
+fm_status fm_vcf_batch_matrix_packed(const fm_vcf_batch *b, int pass_only, fm_matrix **out);
 fm_status fm_vcf_batch_release(fm_vcf_batch *b);
 
 /* ---- synthetic cohorts for benchmarks and full-size parity tests ----

@@ -156,3 +156,4 @@ def test_groups_created_together_equal_groups_created_alone(S, missing):
         assert np.array_equal(a["alt"], b["alt"]) and np.array_equal(a["called"], b["called"])
         assert np.array_equal(a["alt"], so.alt) and np.array_equal(a["called"], so.called)
         assert a["segregating_sites"] == b["segregating_sites"] == so.seg
+

@@ -34,10 +34,15 @@ def test_branch_free_reciprocal_is_ieee_reciprocal():
     n = 1 << 24
     # the a-denominator 1 - c^2 lies in (0, 1]; cover [2^-20, 2) densely plus exact powers of two and 1 - ulp
     b = np.concatenate([rng.random(n) * 0.999 + 0.001, np.ldexp(rng.random(n // 4) + 1.0, rng.integers(-20, 1, n // 4)),
-                        np.array([1.0, 0.5, 0.25, np.nextafter(1.0, 0.0), np.nextafter(0.5, 1.0), 0.75, 1.0 - 2.0 ** -30])])
+                        np.array([1.0, 0.5, 0.25, np.nextafter(0.5, 1.0), 0.75, 1.0 - 2.0 ** -30, 1.0 - 1.0 / 452.0 ** 2])])
     y, q = probe(b, b)
     assert np.array_equal(y.view(np.uint64), (1.0 / b).view(np.uint64))
     assert np.all(q == 1.0)
+    # the documented exception (Markstein): a divisor whose significand is all ones; K4's divisor 1 - c^2 is either 1
+    # or at most 1 - 1/(n_i + n_j)^2 and never has that form
+    ones = np.array([np.nextafter(1.0, 0.0)])
+    y1, _ = probe(ones, ones)
+    assert y1[0] == 1.0 and 1.0 / ones[0] == np.nextafter(1.0, 2.0)
 
 
 def test_wc_per_site_values_are_bit_identical_to_the_oracle():

@@ -280,8 +280,9 @@ def test_device_parser_alignment_sweep():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("packed", [True, False])  # packed: bit rows straight from the parser's output, no u8 matrix
 @pytest.mark.parametrize("excluded", [(3, 7), ()])  # 22 samples: general to_matrix kernel; 24: whole 16-byte rows
-def test_vcf_text_to_estimators_without_host_round_trip(excluded):
+def test_vcf_text_to_estimators_without_host_round_trip(excluded, packed):
     """Raw VCF text -> device parser -> from_variants on the device -> groups -> pi / S / Hudson, against the
     oracle estimators over the oracle-parsed variants."""
     from ferromic_b200 import _lib, vcf
@@ -304,7 +305,7 @@ def test_vcf_text_to_estimators_without_host_round_trip(excluded):
     S = len(kept)
     for pass_only in (False, True):
         sel = [v for v in out if (v[2] == 0 or not pass_only)]
-        m = batch.matrix(pass_only=pass_only)
+        m = batch.matrix(pass_only=pass_only, packed=packed)
         if not sel:
             assert m is None
             continue
