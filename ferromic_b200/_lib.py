@@ -61,7 +61,7 @@ class VcfInfo(C.Structure):
 
 
 EXPORTS = [
-    "fm_last_error", "fm_version", "fm_device_count", "fm_set_device", "fm_synchronize", "fm_trim_pool",
+    "fm_last_error", "fm_version", "fm_device_count", "fm_set_device", "fm_set_devices", "fm_get_devices", "fm_synchronize", "fm_trim_pool",
     "fm_matrix_create", "fm_matrix_create_inband", "fm_matrix_create_device", "fm_matrix_retain", "fm_matrix_release",
     "fm_matrix_info", "fm_ingest_begin", "fm_ingest_add_group", "fm_ingest_add_partition",
     "fm_ingest_rows", "fm_ingest_finish", "fm_ingest_abort", "fm_packed_row_words", "fm_ingest_rows_packed",
@@ -99,6 +99,8 @@ def lib() -> C.CDLL:
     L.fm_version.restype = C.c_char_p
     L.fm_device_count.argtypes = [C.POINTER(C.c_int)]
     L.fm_set_device.argtypes = [C.c_int]
+    L.fm_set_devices.argtypes = [vp, sz]
+    L.fm_get_devices.argtypes = [vp, sz, C.POINTER(sz)]
     L.fm_matrix_create.argtypes = [vp, vp, sz, sz, sz, C.c_uint8, vp, C.POINTER(vp)]
     L.fm_matrix_create_inband.argtypes = [vp, sz, sz, sz, C.c_uint8, vp, C.POINTER(vp)]
     L.fm_matrix_create_device.argtypes = [vp, vp, sz, sz, sz, C.c_uint8, vp, C.POINTER(vp)]

@@ -42,7 +42,53 @@ const char *fm_host_pack_rows_generic(const uint8_t *rows, const uint64_t *missi
 namespace {
 
 thread_local std::string t_err;
-thread_local int t_device = 0;
+// Device selection: fm_set_devices -- or the environment variable FERROMIC_GPU_DEVICES, a comma
+// separated list of CUDA ordinals, read once -- restricts the library to a subset of the visible GPUs; a host thread
+// that never called fm_set_device works on the first allowed device, fm_set_device accepts only allowed ordinals.
+thread_local int t_device_sel = -1;  // -1: not chosen yet on this thread
+std::mutex g_dev_mu;
+std::vector<int> g_devices;          // empty: every visible device is allowed
+bool g_devices_init = false;
+void devices_init_locked() {
+    if (g_devices_init) return;
+    g_devices_init = true;
+    const char *e = getenv("FERROMIC_GPU_DEVICES");
+    if (!e || !*e) return;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    std::string tok;
+    for (const char *p = e;; ++p) {
+        if (*p == ',' || *p == 0) {
+            if (!tok.empty()) {
+                char *end = nullptr;
+                const long d = strtol(tok.c_str(), &end, 10);
+                if (end && *end == 0 && d >= 0 && d < n &&
+                    std::find(g_devices.begin(), g_devices.end(), (int)d) == g_devices.end())
+                    g_devices.push_back((int)d);
+                tok.clear();
+            }
+            if (*p == 0) break;
+        } else if (*p != ' ')
+            tok.push_back(*p);
+    }
+}
+bool device_allowed(int d) {
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    devices_init_locked();
+    return g_devices.empty() || std::find(g_devices.begin(), g_devices.end(), d) != g_devices.end();
+}
+int cur_dev() {
+    if (t_device_sel < 0) {
+        std::lock_guard<std::mutex> lk(g_dev_mu);
+        devices_init_locked();
+        t_device_sel = g_devices.empty() ? 0 : g_devices[0];
+    }
+    return t_device_sel;
+}
+#define t_device (cur_dev())
 thread_local fm_timings t_tim = {};
 std::atomic<uint64_t> g_launches{0};
 
@@ -1212,8 +1258,45 @@ fm_status fm_device_count(int *count) {
 fm_status fm_set_device(int device) {
     return guarded([&] {
         require_device();
+        if (!device_allowed(device))
+            fail(FM_ERR_INVALID_ARG, "device is not in the allowed list (fm_set_devices / FERROMIC_GPU_DEVICES)");
         CK(cudaSetDevice(device));
-        t_device = device;
+        t_device_sel = device;
+    });
+}
+
+fm_status fm_set_devices(const int *devices, size_t n) {
+    return guarded([&] {
+        if (n && !devices) fail(FM_ERR_INVALID_ARG, "devices is NULL");
+        require_device();
+        int count = 0;
+        CK(cudaGetDeviceCount(&count));
+        std::vector<int> v;
+        for (size_t i = 0; i < n; ++i) {
+            if (devices[i] < 0 || devices[i] >= count) fail(FM_ERR_INVALID_ARG, "device ordinal out of range");
+            if (std::find(v.begin(), v.end(), devices[i]) == v.end()) v.push_back(devices[i]);
+        }
+        std::lock_guard<std::mutex> lk(g_dev_mu);
+        g_devices_init = true;  // an explicit list overrides FERROMIC_GPU_DEVICES
+        g_devices = v;          // n == 0: every visible device again
+    });
+}
+
+fm_status fm_get_devices(int *devices_out, size_t capacity, size_t *n_out) {
+    return guarded([&] {
+        if (!n_out) fail(FM_ERR_INVALID_ARG, "n_out is NULL");
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess) {
+            cudaGetLastError();
+            count = 0;
+        }
+        std::lock_guard<std::mutex> lk(g_dev_mu);
+        devices_init_locked();
+        std::vector<int> v = g_devices;
+        if (v.empty())
+            for (int d = 0; d < count; ++d) v.push_back(d);
+        *n_out = v.size();
+        for (size_t i = 0; i < v.size() && i < capacity && devices_out; ++i) devices_out[i] = v[i];
     });
 }
 

@@ -46,6 +46,13 @@ const char *fm_last_error(void);
 const char *fm_version(void);
 fm_status fm_device_count(int *count);
 fm_status fm_set_device(int device); /* device used by handles created afterwards on this thread */
+/* Restrict the library to a subset of the visible GPUs (process-wide).  Without a call the environment
+ * variable FERROMIC_GPU_DEVICES (comma separated CUDA ordinals, e.g. "0,2,3") is read once; neither:
+ * every visible device.  A thread that never called fm_set_device works on the first allowed device;
+ * fm_set_device rejects ordinals outside the list.  n == 0 lifts the restriction.  fm_get_devices
+ * returns the allowed ordinals (one shard / rank per entry). */
+fm_status fm_set_devices(const int *devices, size_t n);
+fm_status fm_get_devices(int *devices_out, size_t capacity, size_t *n_out);
 fm_status fm_synchronize(void);
 /* Device buffers come from a caching allocator inside the library and are kept for reuse when a
  * handle is released; this returns the cached memory of the current device to the driver. */
