@@ -519,6 +519,20 @@ def run_ours(args):
             _lib.check(L.fm_pack_rows(h_data.data_ptr(), h_bitmap.data_ptr(), 1, 0, V, V, stride, h_ab.data_ptr(),
                                       h_cb.data_ptr(), 0))
             pack_ms.append((time.perf_counter() - t0) * 1e3)
+        # the same rows with a sparse missing list instead of the called plane (1.17 instead of 2 bits per genotype
+        # at 1 % missing): what a parser emits when it notes the "./." calls as it reads them
+        h_start = torch.empty(V + 1, dtype=torch.int64, pin_memory=True)
+        need = C.c_size_t()
+        cap = int(V * stride * MISSING_RATE * 1.5) + 1024
+        h_cols = torch.empty(cap, dtype=torch.int16, pin_memory=True)
+        h_ab2 = torch.empty(V * rw, dtype=torch.int32, pin_memory=True)
+        pack_sparse_ms = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            _lib.check(L.fm_pack_rows_sparse(h_data.data_ptr(), h_bitmap.data_ptr(), 1, 0, V, V, stride, h_ab2.data_ptr(),
+                                             h_start.data_ptr(), h_cols.data_ptr(), cap, 2, 0, C.byref(need)))
+            pack_sparse_ms.append((time.perf_counter() - t0) * 1e3)
+        n_missing = int(need.value)
         out_pos = torch.empty(V, dtype=torch.int64, pin_memory=True).numpy()  # caller-owned result buffers are pinned
         out_pi = torch.empty((2, V), dtype=torch.float64, pin_memory=True).numpy()
         out_th = torch.empty((2, V), dtype=torch.float64, pin_memory=True).numpy()
@@ -536,7 +550,9 @@ def run_ours(args):
             for idx, side in garrs:
                 _lib.check(L.fm_ingest_add_group(ih, idx.ctypes.data, side.ctypes.data, len(idx), None))
             lap("begin+declare_groups")
-            if mode == "packed":      # 2-bit rows over PCIe, compressed into both groups' planes chunk by chunk
+            if mode == "packed_sparse":  # allele bits + sparse missing list; called words rebuilt on the device
+                _lib.check(L.fm_ingest_rows_packed_sparse(ih, h_ab2.data_ptr(), h_start.data_ptr(), h_cols.data_ptr(), 2, 0, V))
+            elif mode == "packed":    # 2-bit rows over PCIe, compressed into both groups' planes chunk by chunk
                 _lib.check(L.fm_ingest_rows_packed(ih, h_ab.data_ptr(), h_cb.data_ptr(), 0, V))
             elif mode == "u8_pack":   # u8 + bitmap in, the library packs on the host while the previous chunk uploads
                 d, b = src or (h_data.data_ptr(), h_bitmap.data_ptr())
@@ -584,11 +600,14 @@ def run_ours(args):
                     "host_phase_ms_per_step": {k_: v_ / k for k_, v_ in phases.items()}}
 
         k = max(1, min(args.steps, args.e2e_steps))
-        r_packed = timed("packed", k)
+        r_sparse = timed("packed_sparse", k)
         check_pi = out_pi.copy()
+        r_packed = timed("packed", k)
+        same0 = bool(np.array_equal(np.isnan(check_pi), np.isnan(out_pi)) and
+                     np.array_equal(check_pi[~np.isnan(check_pi)], out_pi[~np.isnan(out_pi)]))
         r_u8pack = timed("u8_pack", k)
-        same = bool(np.array_equal(np.isnan(check_pi), np.isnan(out_pi)) and
-                    np.array_equal(check_pi[~np.isnan(check_pi)], out_pi[~np.isnan(out_pi)]))
+        same = same0 and bool(np.array_equal(np.isnan(check_pi), np.isnan(out_pi)) and
+                              np.array_equal(check_pi[~np.isnan(check_pi)], out_pi[~np.isnan(out_pi)]))
         r_u8 = timed("u8", k) if not args.skip_u8 else None
         if r_u8 is not None:
             same = same and bool(np.array_equal(check_pi[~np.isnan(check_pi)], out_pi[~np.isnan(out_pi)]))
@@ -603,17 +622,25 @@ def run_ours(args):
                         "u8_ms_per_step": None if args.skip_u8 else timed("u8", 1, src)["ms_per_step"]}
             del p_data, p_bitmap
         h2d_packed = int(2 * V * rw * 4 + V * 8 + mask.size * 8)
-        e2e = {"value": r_packed["value"], "unit": UNIT, "h2d_bytes_per_step": h2d_packed,
-               "d2h_bytes_per_step": int(2 * 2 * V * 8), "steps": k, "ms_per_step": r_packed["ms_per_step"],
-               "breakdown_ms_per_step": r_packed["breakdown_ms_per_step"],
-               "host_phase_ms_per_step": r_packed["host_phase_ms_per_step"],
-               "api": "fm_ingest_begin / add_group x2 / fm_ingest_rows_packed (2-bit rows from pinned host memory; chunked "
-                      "H2D overlapped with the compress pass K1p) / finish + fm_per_site_diversity_multi (one fused launch, "
-                      "tracks D2H into pinned host memory); per rank",
-               "input": "packed rows: allele bit + called bit per genotype, as a parser emits them (include/ferromic_gpu.h)",
-               "packer": {"ms": min(pack_ms), "cores": threads, "u8_GBps": V * stride / (min(pack_ms) * 1e-3) / 1e9,
-                          "what": "fm_pack_rows over the pinned u8 matrix + bitmap (AVX2, all host threads), outside the "
-                                  "timed region of `value` above; inside it for from_u8_pack_on_host"},
+        h2d_sparse = int(V * rw * 4 + (V + 1) * 8 + n_missing * 2 + V * 8 + mask.size * 8)
+        e2e = {"value": r_sparse["value"], "unit": UNIT, "h2d_bytes_per_step": h2d_sparse,
+               "d2h_bytes_per_step": int(2 * 2 * V * 8), "steps": k, "ms_per_step": r_sparse["ms_per_step"],
+               "breakdown_ms_per_step": r_sparse["breakdown_ms_per_step"],
+               "host_phase_ms_per_step": r_sparse["host_phase_ms_per_step"],
+               "api": "fm_ingest_begin / add_group x2 / fm_ingest_rows_packed_sparse (allele bit words + sparse missing list "
+                      "from pinned host memory; chunked H2D overlapped with fm_k_expand_called + the compress pass K1p) / "
+                      "finish + fm_per_site_diversity_multi (one fused launch, tracks D2H into pinned host memory); per rank",
+               "input": "packed rows: one allele bit per genotype + the columns of the missing cells of every row (CSR, u16), "
+                        "as a parser emits them (include/ferromic_gpu.h); %d missing cells = %.2f %% of the matrix"
+                        % (n_missing, 100.0 * n_missing / (V * stride)),
+               "bits_per_genotype_over_pcie": 8.0 * h2d_sparse / (V * stride),
+               "packed_called_plane": {**r_packed, "h2d_bytes_per_step": h2d_packed,
+                                       "what": "fm_ingest_rows_packed: allele bit + called bit per genotype (2 bits)"},
+               "packer": {"ms": min(pack_ms), "sparse_ms": min(pack_sparse_ms), "cores": threads,
+                          "u8_GBps": V * stride / (min(pack_ms) * 1e-3) / 1e9,
+                          "what": "fm_pack_rows / fm_pack_rows_sparse over the pinned u8 matrix + bitmap (AVX-512 or AVX2, all "
+                                  "host threads), outside the timed region of `value` above; inside it for "
+                                  "from_u8_pack_on_host"},
                "from_u8_pack_on_host": {**r_u8pack, "h2d_bytes_per_step": h2d_packed,
                                         "what": "fm_ingest_rows_pack: the caller holds the reference's u8 matrix + bitmap "
                                                 "(pinned); the library packs chunk i+1 on the host while chunk i uploads"},

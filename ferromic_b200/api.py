@@ -171,6 +171,37 @@ def pack_rows(alleles2d: np.ndarray, missing_mode: int, bitmap: Optional[np.ndar
     return ab, cb
 
 
+def pack_rows_sparse(alleles2d: np.ndarray, missing_mode: int, bitmap: Optional[np.ndarray] = None, first_row: int = 0,
+                     n_total_rows: Optional[int] = None, threads: int = 0):
+    """fm_pack_rows_sparse: (allele_bits [rows, rw] u32, row_start [rows + 1] u64, missing_cols u16 / u32) -- the
+    packed rows with a sparse missing list instead of a called plane."""
+    a = np.ascontiguousarray(alleles2d).view(np.uint8)
+    assert a.ndim == 2
+    rows, stride = a.shape
+    rw = (stride + 31) // 32
+    ab = np.zeros((rows, rw), dtype=np.uint32)
+    start = np.zeros(rows + 1, dtype=np.uint64)
+    col_t = np.uint16 if stride <= 65536 else np.uint32
+    total = rows + first_row if n_total_rows is None else n_total_rows
+    L = lib()
+    need = C.c_size_t()
+    cols = np.zeros(max(16, rows * stride // 32), dtype=col_t)
+    for _ in range(2):
+        st = L.fm_pack_rows_sparse(_ptr(a), _ptr(bitmap), missing_mode, first_row, rows, total, stride, _ptr(ab),
+                                   _ptr(start), _ptr(cols), cols.size, cols.itemsize, threads, C.byref(need))
+        if st == _lib.FM_ERR_INVALID_ARG and need.value > cols.size:
+            cols = np.zeros(need.value, dtype=col_t)  # the first call reported the size: retry
+            continue
+        check(st)
+        break
+    return ab, start, cols[:need.value]
+
+
+def _sparse_missing_pays(missing_mask: Optional[np.ndarray]) -> bool:
+    """The sparse list (2-4 bytes per missing cell) beats the called plane (1 bit per cell) below ~3 % missing."""
+    return missing_mask is not None and missing_mask.size > 0 and float(missing_mask.mean()) < 1.0 / 40.0
+
+
 # --------------------------------------------------------------------------- device handles
 class _Matrix:
     def __init__(self, alleles: np.ndarray, missing_mask: Optional[np.ndarray], positions: np.ndarray,
@@ -186,11 +217,19 @@ class _Matrix:
         pos = np.ascontiguousarray(positions, dtype=np.int64)
         h = C.c_void_p()
         self.ingest_mode = ingest or _ingest_mode(self.max_allele)
-        if self.ingest_mode == "packed":
+        if self.ingest_mode in ("packed", "packed-dense"):
             # convert_numeric_array / from_variants seam (lib.rs:1135-1227, stats.rs:339-500): the host packs
-            # bit words (several threads) and only 0.25 B per genotype cross PCIe
-            ab, cb = pack_rows(a.reshape(self.V, self.S * self.P), 1 if bits is not None else 0, bits)
-            check(lib().fm_matrix_create_packed(_ptr(ab), _ptr(cb), self.V, self.S, self.P, _ptr(pos), C.byref(h)))
+            # bit words (several threads) and only 0.25 B per genotype cross PCIe ("packed-dense" keeps the called
+            # plane even when the sparse missing list would be smaller)
+            flat = a.reshape(self.V, self.S * self.P)
+            if self.ingest_mode == "packed" and bits is not None and _sparse_missing_pays(missing_mask):
+                ab, start, cols = pack_rows_sparse(flat, 1, bits)
+                check(lib().fm_matrix_create_packed_sparse(_ptr(ab), _ptr(start), _ptr(cols), cols.itemsize, self.V, self.S,
+                                                           self.P, _ptr(pos), C.byref(h)))
+                self.ingest_mode = "packed-sparse"
+            else:
+                ab, cb = pack_rows(flat, 1 if bits is not None else 0, bits)
+                check(lib().fm_matrix_create_packed(_ptr(ab), _ptr(cb), self.V, self.S, self.P, _ptr(pos), C.byref(h)))
         else:
             check(lib().fm_matrix_create(_ptr(a), _ptr(bits), self.V, self.S, self.P, self.max_allele, _ptr(pos),
                                          C.byref(h)))
@@ -225,7 +264,7 @@ class _Matrix:
     @classmethod
     def ingest(cls, alleles: np.ndarray, missing_mask: Optional[np.ndarray], positions: np.ndarray,
                group_haplotypes: Sequence[Sequence[Tuple[int, int]]], partitions=(), chunk_rows: int = 0,
-               calls: int = 1, always_bitmap: bool = False, packed: bool = False) -> "_Matrix":
+               calls: int = 1, always_bitmap: bool = False, packed: bool = False, sparse: bool = False) -> "_Matrix":
         """Streaming ingestion (fm_ingest_*): the u8 rows are uploaded in chunks and repacked into
         the declared groups' bitplanes while the next chunk is in flight; the u8 matrix is never
         resident.  partitions: (left, right, n_groups) triples; their handles land in
@@ -261,7 +300,11 @@ class _Matrix:
             for r0, r1 in zip(cuts[:-1], cuts[1:]):
                 if r1 <= r0:
                     continue
-                if packed:  # fm_pack_rows on the host, 2 bits per genotype over PCIe (fm_ingest_rows_packed)
+                if packed and sparse and bits is not None:  # allele bits + sparse missing list
+                    ab, start, cols = pack_rows_sparse(flat[r0:r1], 1, bits, first_row=int(r0), n_total_rows=self.V)
+                    check(L.fm_ingest_rows_packed_sparse(ih, _ptr(ab), _ptr(start), _ptr(cols), cols.itemsize, int(r0),
+                                                         int(r1 - r0)))
+                elif packed:  # fm_pack_rows on the host, 2 bits per genotype over PCIe (fm_ingest_rows_packed)
                     ab, cb = pack_rows(flat[r0:r1], 1 if bits is not None else 0, bits, first_row=int(r0),
                                        n_total_rows=self.V)
                     check(L.fm_ingest_rows_packed(ih, _ptr(ab), _ptr(cb), int(r0), int(r1 - r0)))

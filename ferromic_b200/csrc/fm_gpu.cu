@@ -35,6 +35,10 @@
 const char *fm_host_pack_rows(const uint8_t *rows, const uint64_t *missing_whole_or_null, int missing_mode,
                               size_t first_row, size_t n_rows, size_t n_total_rows, size_t stride,
                               uint32_t *allele_bits, uint32_t *called_bits_or_null, int n_threads);
+const char *fm_host_pack_rows_sparse(const uint8_t *rows, const uint64_t *missing_whole_or_null, int missing_mode,
+                                     size_t first_row, size_t n_rows, size_t n_total_rows, size_t stride,
+                                     uint32_t *allele_bits, uint64_t *row_start, void *missing_cols, size_t capacity,
+                                     int col_bytes, int n_threads, size_t *needed);
 const char *fm_host_pack_rows_generic(const uint8_t *rows, const uint64_t *missing, int mode, size_t first_row,
                                       size_t n_rows, size_t n_total_rows, size_t stride, uint32_t *abits,
                                       uint32_t *cbits);
@@ -2549,6 +2553,153 @@ fm_status fm_ingest_rows_packed(fm_ingest *h, const uint32_t *allele_bits, const
         CK(cudaEventRecord(h->t_comp1, h->comp_s));
         ingest_late_setup(h);
         CK(cudaStreamSynchronize(h->copy_s));  // the caller's buffers are free again on return
+    });
+}
+
+// ---- packed rows with a sparse missing list
+// Shared by the streaming and the one-shot entry points: rows [first_row, first_row + n_rows) arrive as allele bit
+// words + a CSR list of missing cells (row_start relative to this call).  Chunks of rows are copied on copy_s; on
+// comp_s every chunk's called words are rebuilt on the device (fm_k_expand_called) and -- when groups are declared --
+// compressed into their planes (K1p), while the next chunk is on the bus.
+static void expand_called_launch(fm_matrix *m, const uint64_t *d_start, const void *d_cols, int col_bytes, uint64_t cols_base,
+                                 uint32_t r_base, uint32_t v_lo, uint32_t v_hi, cudaStream_t st) {
+    if (v_hi <= v_lo || !m->rw) return;
+    const size_t warp_bytes = (size_t)m->rw * 4;
+    if (warp_bytes > 200 * 1024) fail(FM_ERR_UNSUPPORTED, "packed rows wider than the expand kernel's shared memory");
+    const uint32_t warps = (uint32_t)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / warp_bytes));
+    const size_t smem = warps * warp_bytes;
+    const uint32_t rows = v_hi - v_lo;
+    const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / std::max<size_t>(smem, 1)));
+    const uint32_t blocks = std::max(1u, std::min<uint32_t>((rows + warps - 1) / warps, per_sm * (uint32_t)sm_count(m->device)));
+    static std::once_flag once2, once4;
+    if (col_bytes == 2) {
+        std::call_once(once2, [] {
+            cudaFuncSetAttribute(fm::fm_k_expand_called<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        });
+        fm::fm_k_expand_called<uint16_t><<<blocks, warps * 32, smem, st>>>(d_start, static_cast<const uint16_t *>(d_cols),
+                                                                            cols_base, r_base, v_lo, v_hi, m->rw,
+                                                                            (uint32_t)m->stride, m->d_cbits);
+    } else {
+        std::call_once(once4, [] {
+            cudaFuncSetAttribute(fm::fm_k_expand_called<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        });
+        fm::fm_k_expand_called<uint32_t><<<blocks, warps * 32, smem, st>>>(d_start, static_cast<const uint32_t *>(d_cols),
+                                                                            cols_base, r_base, v_lo, v_hi, m->rw,
+                                                                            (uint32_t)m->stride, m->d_cbits);
+    }
+    CK(cudaGetLastError());
+    g_launches++;
+}
+
+static void packed_sparse_rows(fm_matrix *m, const RepackSet *set, const uint32_t *allele_bits, const uint64_t *row_start,
+                               const void *missing_cols, int col_bytes, size_t first_row, size_t n_rows, cudaStream_t copy_s,
+                               cudaStream_t comp_s, cudaEvent_t ev[2]) {
+    if (col_bytes != 2 && col_bytes != 4) fail(FM_ERR_INVALID_ARG, "col_bytes must be 2 or 4");
+    if (col_bytes == 2 && m->stride > 65536) fail(FM_ERR_INVALID_ARG, "16-bit columns need a row stride <= 65536");
+    if (n_rows && !row_start) fail(FM_ERR_INVALID_ARG, "row_start is NULL");
+    const size_t rw = m->rw;
+    if (!n_rows || !rw) return;
+    if (row_start[0] != 0) fail(FM_ERR_INVALID_ARG, "row_start[0] must be 0 (offsets are relative to the call)");
+    const uint64_t total = row_start[n_rows];
+    if (total && !missing_cols) fail(FM_ERR_INVALID_ARG, "missing_cols is NULL");
+    DevBuf<uint64_t> d_start(n_rows + 1);
+    DevBuf<uint8_t> d_cols(std::max<uint64_t>(total * col_bytes, 16));
+    CK(cudaStreamSynchronize(stream()));  // fresh (or recycled) scratch is settled before other streams touch it
+    const size_t chunk = std::max<size_t>(32, ((size_t)32 << 20) / (rw * 4));
+    int b = 0;
+    for (size_t r0 = 0; r0 < n_rows; r0 += chunk, b ^= 1) {
+        const size_t r1 = std::min(n_rows, r0 + chunk);
+        if (row_start[r1] < row_start[r0] || row_start[r1] > total) fail(FM_ERR_INVALID_ARG, "row_start is not ascending");
+        h2d(m->d_abits + (first_row + r0) * rw, allele_bits + r0 * rw, (r1 - r0) * rw * 4, copy_s);
+        h2d(d_start.p + r0, row_start + r0, (r1 - r0 + 1) * 8, copy_s);
+        const uint64_t c0 = row_start[r0], c1 = row_start[r1];
+        if (c1 > c0)
+            h2d(d_cols.p + c0 * col_bytes, static_cast<const uint8_t *>(missing_cols) + c0 * col_bytes, (c1 - c0) * col_bytes,
+                copy_s);
+        CK(cudaEventRecord(ev[b], copy_s));
+        CK(cudaStreamWaitEvent(comp_s, ev[b], 0));
+        expand_called_launch(m, d_start.p, d_cols.p, col_bytes, 0, (uint32_t)first_row, (uint32_t)(first_row + r0),
+                             (uint32_t)(first_row + r1), comp_s);
+        if (set) launch_repack(*set, nullptr, 0, nullptr, 0, 0, (uint32_t)(first_row + r0), (uint32_t)(first_row + r1), comp_s);
+    }
+    // the scratch lists go back to the allocator ordered after the last kernel that reads them
+    CK(cudaEventRecord(ev[b], comp_s));
+    CK(cudaStreamWaitEvent(stream(), ev[b], 0));
+}
+
+fm_status fm_pack_rows_sparse(const uint8_t *rows, const uint64_t *missing_whole, int missing_mode, size_t first_row,
+                              size_t n_rows, size_t n_total_rows, size_t stride, uint32_t *allele_bits,
+                              uint64_t *row_missing_start, void *missing_cols, size_t capacity, int col_bytes,
+                              int n_threads, size_t *needed) {
+    return guarded([&] {  // host only
+        const char *err = fm_host_pack_rows_sparse(rows, missing_whole, missing_mode, first_row, n_rows, n_total_rows, stride,
+                                                   allele_bits, row_missing_start, missing_cols, capacity, col_bytes,
+                                                   n_threads, needed);
+        if (err) fail(FM_ERR_INVALID_ARG, err);
+    });
+}
+
+fm_status fm_ingest_rows_packed_sparse(fm_ingest *h, const uint32_t *allele_bits, const uint64_t *row_missing_start,
+                                       const void *missing_cols, int col_bytes, size_t first_row, size_t n_rows) {
+    return guarded([&] {
+        FM_NVTX("fm_ingest_rows_packed_sparse (H2D packed + expand + K1p compress)");
+        if (!h) fail(FM_ERR_INVALID_ARG, "ingest handle is NULL");
+        fm_matrix *m = h->m;
+        if (first_row > m->V || n_rows > m->V - first_row) fail(FM_ERR_INVALID_ARG, "row range outside the matrix");
+        if (h->stage[0]) fail(FM_ERR_INVALID_ARG, "this ingest already received u8 rows (fm_ingest_rows)");
+        if (m->in_band) fail(FM_ERR_INVALID_ARG, "packed rows carry their own missingness: begin with FM_MISSING_BITMAP");
+        if (!m->has_missing) fail(FM_ERR_INVALID_ARG, "matrix was declared without missing data: use fm_ingest_rows_packed");
+        if (n_rows && m->stride && !allele_bits) fail(FM_ERR_INVALID_ARG, "allele_bits is NULL");
+        set_dev(m);
+        const bool first_call = !m->d_abits;
+        ensure_packed_storage(m, true);
+        if (first_call) CK(cudaStreamSynchronize(stream()));
+        if (!h->set.d_desc && !h->all.empty()) h->set.build(h->all);
+        if (!h->timing_started && n_rows) {
+            CK(cudaEventRecord(h->t_copy0, h->copy_s));
+            CK(cudaEventRecord(h->t_comp0, h->comp_s));
+            h->timing_started = true;
+        }
+        packed_sparse_rows(m, h->all.empty() ? nullptr : &h->set, allele_bits, row_missing_start, missing_cols, col_bytes,
+                           first_row, n_rows, h->copy_s, h->comp_s, h->copied);
+        h->rows_done += n_rows;
+        CK(cudaEventRecord(h->t_copy1, h->copy_s));
+        CK(cudaEventRecord(h->t_comp1, h->comp_s));
+        ingest_late_setup(h);
+        CK(cudaStreamSynchronize(h->copy_s));  // the caller's buffers are free again on return
+    });
+}
+
+fm_status fm_matrix_create_packed_sparse(const uint32_t *allele_bits, const uint64_t *row_missing_start,
+                                         const void *missing_cols, int col_bytes, size_t V, size_t S, size_t ploidy,
+                                         const int64_t *positions, fm_matrix **out) {
+    return guarded([&] {
+        FM_NVTX("fm_matrix_create_packed_sparse (H2D packed + expand)");
+        if (!out) fail(FM_ERR_INVALID_ARG, "out is NULL");
+        *out = nullptr;
+        require_device();
+        CK(cudaSetDevice(t_device));
+        fm_matrix *m = matrix_common(V, S, ploidy, 1, positions);
+        try {
+            m->has_missing = true;
+            m->streamed = true;
+            ensure_packed_storage(m, true);
+            if ((V * (size_t)m->rw) != 0 && !allele_bits) fail(FM_ERR_INVALID_ARG, "allele_bits is NULL");
+            Timer tm;
+            tm.start();
+            EventPairs evs;
+            cudaEvent_t ev[2] = {evs.next(), evs.next()};
+            packed_sparse_rows(m, nullptr, allele_bits, row_missing_start, missing_cols, col_bytes, 0, V, stream(), stream(), ev);
+            m->d_pos = static_cast<int64_t *>(dev_alloc(std::max<size_t>(V, 1) * 8));
+            if (V) CK(cudaMemcpyAsync(m->d_pos, m->pos.data(), V * 8, cudaMemcpyHostToDevice, stream()));
+            tm.stop();
+            CK(cudaStreamSynchronize(stream()));
+            t_tim.h2d_ms += tm.ms();
+        } catch (...) {
+            fm_matrix_release(m);
+            throw;
+        }
+        *out = m;
     });
 }
 

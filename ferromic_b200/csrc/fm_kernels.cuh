@@ -468,6 +468,36 @@ fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint
     }
 }
 
+// ------------------------------------------------------------------------------ sparse missing list -> called plane
+// Packed rows may arrive with a sparse list of missing cells instead of a called plane (0.15 instead of 1 bit per
+// genotype over PCIe at 1 % missing).  One warp per row rebuilds the row's called words in shared memory -- all
+// ones, the listed cells cleared -- and writes them to the resident packed matrix with coalesced stores.
+//   start[r - r_base] .. start[r - r_base + 1]: the row's slice of `cols` (indices relative to cols_base)
+template <typename ColT>
+__global__ void __launch_bounds__(256)
+fm_k_expand_called(const uint64_t *__restrict__ start, const ColT *__restrict__ cols, uint64_t cols_base, uint32_t r_base,
+                   uint32_t v_lo, uint32_t v_hi, uint32_t rw, uint32_t stride, uint32_t *__restrict__ cbits) {
+    extern __shared__ uint32_t ex_smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *crow = ex_smem + (size_t)warp * rw;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t GW = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t tail = stride & 31u;
+    for (uint32_t v = v_lo + gw; v < v_hi; v += GW) {
+        for (uint32_t w = lane; w < rw; w += 32) crow[w] = (tail && w == rw - 1) ? ((1u << tail) - 1u) : 0xffffffffu;
+        __syncwarp();
+        const uint64_t s0 = start[v - r_base], s1 = start[v - r_base + 1];
+        for (uint64_t i = s0 + lane; i < s1; i += 32) {
+            const uint32_t c = (uint32_t)cols[i - cols_base];
+            if (c < stride) atomicAnd(crow + (c >> 5), ~(1u << (c & 31u)));
+        }
+        __syncwarp();
+        uint32_t *dst = cbits + (size_t)v * rw;
+        for (uint32_t w = lane; w < rw; w += 32) dst[w] = crow[w];
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------------------ synthetic cohorts
 // Counter-based generator for benchmarks and full-size parity tests: every matrix entry is a pure
 // integer function of (seed, site, column), so any slice can be re-evaluated on the CPU

@@ -130,6 +130,25 @@ fm_status fm_ingest_rows(fm_ingest *h, const uint8_t *rows, const uint64_t *miss
 fm_status fm_packed_row_words(size_t n_samples, size_t ploidy, size_t *row_words);
 fm_status fm_ingest_rows_packed(fm_ingest *h, const uint32_t *allele_bits, const uint32_t *called_bits_or_null,
                                 size_t first_row, size_t n_rows);
+/* Packed rows with a SPARSE MISSING LIST: the allele bit words as above and, instead of a called plane,
+ * the columns c = sample * ploidy + side of the missing cells of every row in ascending order, as a CSR
+ * list -- row_missing_start[r] .. row_missing_start[r + 1] (n_rows + 1 entries, relative to the call,
+ * [0] == 0) index missing_cols, whose elements are col_bytes = 2 (row stride <= 65536) or 4 bytes wide.
+ * With 1 % missing cells that is 1.17 bits per genotype over PCIe instead of 2 (and 9 for u8 + bitmap);
+ * the called words are rebuilt on the device.  A parser sees the missing calls as it reads them ("./."),
+ * so this is the natural output of process.rs:2602-2660; fm_pack_rows_sparse derives it from an existing
+ * u8 / int8 matrix (*needed = number of list entries; FM_ERR_INVALID_ARG when capacity is too small, with
+ * *needed and row_missing_start filled in so the caller can retry). */
+fm_status fm_pack_rows_sparse(const uint8_t *rows, const uint64_t *missing_whole_or_null, int missing_mode,
+                              size_t first_row, size_t n_rows, size_t n_total_rows, size_t stride,
+                              uint32_t *allele_bits, uint64_t *row_missing_start, void *missing_cols,
+                              size_t capacity, int col_bytes, int n_threads, size_t *needed);
+fm_status fm_ingest_rows_packed_sparse(fm_ingest *h, const uint32_t *allele_bits, const uint64_t *row_missing_start,
+                                       const void *missing_cols, int col_bytes, size_t first_row, size_t n_rows);
+fm_status fm_matrix_create_packed_sparse(const uint32_t *allele_bits, const uint64_t *row_missing_start,
+                                         const void *missing_cols, int col_bytes, size_t n_variants,
+                                         size_t n_samples, size_t ploidy, const int64_t *positions_or_null,
+                                         fm_matrix **out);
 /* fm_ingest_rows with the packer inside: same arguments (u8 rows + whole-matrix bitmap, or in-band
  * cells), but the library packs chunk i+1 on the host with n_threads threads (<= 0: all) while chunk i
  * crosses PCIe as bit words -- the drop-in for callers that hold the reference's u8 / int8 matrix

@@ -17,9 +17,9 @@ def _mats(g, pos, always_bitmap=False):
     from ferromic_b200.api import _Matrix
     miss = g < 0
     alle = np.where(miss, 0, g).astype(np.uint8)
-    packed = _Matrix(alle, miss, pos, max_allele=1, always_bitmap=always_bitmap, ingest="packed")
+    packed = _Matrix(alle, miss, pos, max_allele=1, always_bitmap=always_bitmap, ingest="packed-dense")
     u8 = _Matrix(alle, miss, pos, max_allele=1, always_bitmap=always_bitmap, ingest="u8")
-    assert packed.ingest_mode == "packed" and u8.ingest_mode == "u8"
+    assert packed.ingest_mode == "packed-dense" and u8.ingest_mode == "u8"
     return packed, u8
 
 
@@ -160,3 +160,41 @@ def test_packed_error_behaviour():
     m = C.c_void_p()
     _lib.check(L.fm_matrix_create_packed(None, None, 0, 3, 2, None, C.byref(m)))
     L.fm_matrix_release(m)
+
+
+@pytest.mark.parametrize("n_samples,missing", [(3, 0.02), (65, 0.01), (700, 0.02), (2504, 0.01), (40000, 0.005)])
+def test_sparse_missing_list_equals_called_plane(n_samples, missing):
+    """Packed rows whose missingness arrives as a sparse CSR list (fm_pack_rows_sparse -> fm_matrix_create_packed_sparse
+    -> fm_k_expand_called) give the counts of the called-plane form, of the u8 path and of the oracle."""
+    from ferromic_b200.api import _Matrix
+    V = 2500 if n_samples < 1000 else (500 if n_samples < 10000 else 40)
+    g, pos, _ = make_cohort(V, n_samples, missing_rate=missing, seed=900 + n_samples)
+    g[7] = -1  # a row without any call
+    miss = g < 0
+    alle = np.where(miss, 0, g).astype(np.uint8)
+    sparse = _Matrix(alle, miss, pos, max_allele=1, always_bitmap=True, ingest="packed")
+    assert sparse.ingest_mode == "packed-sparse"
+    u8 = _Matrix(alle, miss, pos, max_allele=1, always_bitmap=True, ingest="u8")
+    vs, d = orc.from_numpy(g, pos)
+    for haps in (both_sides(range(n_samples)), both_sides(range(0, n_samples, 3)) + [(1, 1)]):
+        ref = orc.build_summary(d, haps)
+        got = sparse.group(haps).summary(want_arrays=True)
+        assert np.array_equal(got["alt"], ref.alt) and np.array_equal(got["called"], ref.called)
+        _same_summary(got, u8.group(haps).summary(want_arrays=True))
+
+
+@pytest.mark.parametrize("calls", [1, 4])
+def test_sparse_missing_streaming_ingest(calls):
+    from ferromic_b200.api import _Matrix
+    g, pos, pops = make_cohort(1800, 45, n_pops=3, missing_rate=0.02, seed=55 + calls)
+    miss = g < 0
+    alle = np.where(miss, 0, g).astype(np.uint8)
+    hap_lists = [both_sides(pops[0]), both_sides(pops[1]) + [(pops[2][0], 1)], [(s, 0) for s in pops[2]]]
+    left = np.full(45, 0xFFFF, dtype=np.uint16)
+    for p, members in enumerate(pops):
+        left[members] = p
+    resident = _Matrix(alle, miss, pos, max_allele=1, ingest="u8")
+    streamed = _Matrix.ingest(alle, miss, pos, hap_lists, partitions=[(left, left, 3)], calls=calls, packed=True,
+                              sparse=True, always_bitmap=True)
+    for haps in hap_lists + [[(0, 0), (1, 1), (44, 0)]]:
+        _same_summary(resident.group(haps).summary(True), streamed.group(haps).summary(True))

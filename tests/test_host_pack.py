@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from ferromic_b200 import _lib
-from ferromic_b200.api import _pack_bits, pack_rows
+from ferromic_b200.api import _pack_bits, pack_rows, pack_rows_sparse
 
 
 def numpy_pack(cells_u8, missing_bool):
@@ -89,3 +89,53 @@ def test_pack_rows_argument_errors():
     assert L.fm_pack_rows(cells.ctypes.data, None, 7, 0, 2, 2, 40, out.ctypes.data, None, 1) == _lib.FM_ERR_INVALID_ARG
     assert L.fm_pack_rows(cells.ctypes.data, None, 0, 1, 2, 2, 40, out.ctypes.data, None, 1) == _lib.FM_ERR_INVALID_ARG
     assert L.fm_pack_rows(None, None, 0, 0, 0, 0, 40, None, None, 1) == 0  # nothing to do
+
+
+@pytest.mark.parametrize("stride", [1, 33, 100, 5008, 70000])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_pack_rows_sparse_matches_the_dense_packer(stride, mode):
+    """Allele bits identical to fm_pack_rows; the CSR list holds exactly the zero bits of its called plane, ascending."""
+    rng = np.random.default_rng(31 * stride + mode)
+    rows = 41 if stride < 10000 else 5
+    cells = (rng.random((rows, stride)) < 0.4).astype(np.uint8)
+    miss = rng.random(cells.shape) < 0.03 if mode else np.zeros(cells.shape, dtype=bool)
+    miss[rows // 2] = mode != 0          # a row that is missing altogether
+    miss[0] = False                      # and one without any missing cell
+    bitmap, src = None, cells
+    if mode == 1:
+        bitmap = _pack_bits(miss.reshape(-1).astype(np.uint8))
+    elif mode == 2:
+        src = cells.copy()
+        src[miss] = 0xFF
+    dense_a, dense_c = pack_rows(src, mode, bitmap)
+    for threads in (1, 4):
+        ab, start, cols = pack_rows_sparse(src, mode, bitmap, threads=threads)
+        assert np.array_equal(ab, dense_a)
+        assert cols.dtype == (np.uint16 if stride <= 65536 else np.uint32)
+        assert start[0] == 0 and np.all(np.diff(start.astype(np.int64)) >= 0) and int(start[-1]) == len(cols) == int(miss.sum())
+        for r in range(rows):
+            want = np.nonzero(miss[r])[0]
+            assert np.array_equal(cols[int(start[r]):int(start[r + 1])].astype(np.int64), want)
+
+
+def test_pack_rows_sparse_chunk_and_capacity():
+    from ferromic_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(3)
+    V, stride = 30, 77
+    cells = rng.integers(0, 2, size=(V, stride), dtype=np.uint8)
+    miss = rng.random(cells.shape) < 0.2
+    bitmap = _pack_bits(miss.reshape(-1).astype(np.uint8))
+    ab, start, cols = pack_rows_sparse(cells[7:19], 1, bitmap, first_row=7, n_total_rows=V)
+    for r in range(12):
+        assert np.array_equal(cols[int(start[r]):int(start[r + 1])].astype(np.int64), np.nonzero(miss[7 + r])[0])
+    # capacity too small: the needed size and the row starts are still reported
+    need = C.c_size_t()
+    st2 = np.zeros(V + 1, dtype=np.uint64)
+    a2 = np.zeros((V, 3), dtype=np.uint32)
+    tiny = np.zeros(4, dtype=np.uint16)
+    rc = L.fm_pack_rows_sparse(cells.ctypes.data, bitmap.ctypes.data, 1, 0, V, V, stride, a2.ctypes.data, st2.ctypes.data,
+                               tiny.ctypes.data, 4, 2, 2, C.byref(need))
+    assert rc == _lib.FM_ERR_INVALID_ARG and need.value == int(miss.sum()) == int(st2[-1])
+    assert L.fm_pack_rows_sparse(cells.ctypes.data, bitmap.ctypes.data, 1, 0, V, V, stride, a2.ctypes.data, st2.ctypes.data,
+                                 tiny.ctypes.data, 4, 3, 2, C.byref(need)) == _lib.FM_ERR_INVALID_ARG  # bad col_bytes
