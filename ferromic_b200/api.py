@@ -217,12 +217,13 @@ class _Matrix:
         pos = np.ascontiguousarray(positions, dtype=np.int64)
         h = C.c_void_p()
         self.ingest_mode = ingest or _ingest_mode(self.max_allele)
-        if self.ingest_mode in ("packed", "packed-dense"):
+        if self.ingest_mode in ("packed", "packed-dense", "packed-sparse"):
             # convert_numeric_array / from_variants seam (lib.rs:1135-1227, stats.rs:339-500): the host packs
             # bit words (several threads) and only 0.25 B per genotype cross PCIe ("packed-dense" keeps the called
             # plane even when the sparse missing list would be smaller)
             flat = a.reshape(self.V, self.S * self.P)
-            if self.ingest_mode == "packed" and bits is not None and _sparse_missing_pays(missing_mask):
+            if bits is not None and (self.ingest_mode == "packed-sparse" or
+                                     (self.ingest_mode == "packed" and _sparse_missing_pays(missing_mask))):
                 ab, start, cols = pack_rows_sparse(flat, 1, bits)
                 check(lib().fm_matrix_create_packed_sparse(_ptr(ab), _ptr(start), _ptr(cols), cols.itemsize, self.V, self.S,
                                                            self.P, _ptr(pos), C.byref(h)))

@@ -1624,12 +1624,17 @@ struct RepackSet {  // device-resident descriptor tables of the groups one launc
                 plan_len.push_back(ne);
             }
         }
-        if (m->packed && plan.empty() && !h.empty()) plan.resize(8, 0u);  // empty groups still take the plan path
+        // every biallelic plane group takes the plan path when plans are in use -- also an empty group (no entries):
+        // the direct and packed kernels compile without the ballot gathers
+        const bool plans_on = (staged && !no_plan) || m->packed;
+        bool any_bial = false;
+        for (const fm::RepackGroup &rg : h) any_bial = any_bial || rg.n_bits == 1;
+        if (plans_on && any_bial && plan.empty()) plan.resize(8, 0u);
         if (!plan.empty()) {
             d_plan = static_cast<uint4 *>(dev_alloc(plan.size() * 4));
             CK(cudaMemcpyAsync(d_plan, plan.data(), plan.size() * 4, cudaMemcpyHostToDevice, stream()));
             for (size_t i = 0; i < h.size(); ++i)
-                if (plan_len[i] || (m->packed && h[i].n_bits == 1)) {
+                if (plan_len[i] || (plans_on && h[i].n_bits == 1)) {
                     h[i].plan = d_plan + 2 * plan_at[i];
                     h[i].n_ent = (uint32_t)plan_len[i];
                 }
@@ -1699,14 +1704,14 @@ static void launch_repack(const RepackSet &set, const uint8_t *data, size_t data
         const size_t smem = (size_t)warps * warp_smem;
         static std::once_flag attr_once_p;
         std::call_once(attr_once_p, [] {
-            cudaFuncSetAttribute(fm::fm_k_repack_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(fm::fm_k_repack_rows<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         });
         const uint32_t rows = v_hi - v_lo;
         const uint32_t per_sm = std::max(1u, std::min(8u, (uint32_t)((220u * 1024u) / smem)));
         const uint32_t blocks = std::max(1u, std::min<uint32_t>((rows + warps - 1) / warps,
                                                                 per_sm * (uint32_t)sm_count(m->device)));
         const fm::PackedRows pk{m->d_abits, m->d_cbits, m->rw};
-        fm::fm_k_repack_rows<<<blocks, warps * 32, smem, st>>>(nullptr, 0, nullptr, m->stride, 0, 0, v_lo, v_hi,
+        fm::fm_k_repack_rows<2, true><<<blocks, warps * 32, smem, st>>>(nullptr, 0, nullptr, m->stride, 0, 0, v_lo, v_hi,
                                                                set.d_desc, (uint32_t)set.plane_gs.size(), warp_smem, 0, 0,
                                                                set.ct, 0u, 1u, 0u, pk);
         CK(cudaGetLastError());
@@ -1728,17 +1733,29 @@ static void launch_repack(const RepackSet &set, const uint8_t *data, size_t data
         const size_t smem = (size_t)warps * warp_smem;
         static std::once_flag attr_once;
         std::call_once(attr_once, [] {
-            cudaFuncSetAttribute(fm::fm_k_repack_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(fm::fm_k_repack_rows<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(fm::fm_k_repack_rows<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(fm::fm_k_repack_rows<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(fm::fm_k_repack_rows<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         });
         const uint32_t rows = v_hi - v_lo;
         const uint32_t per_sm = std::max(1u, std::min(8u, (uint32_t)((220u * 1024u) / smem)));
         const uint32_t blocks = std::max(1u, std::min<uint32_t>((rows + warps - 1) / warps,
                                                                 per_sm * (uint32_t)sm_count(m->device)));
-        fm::fm_k_repack_rows<<<blocks, warps * 32, smem, st>>>(data, data_bytes, missing, m->stride, v_base, word_base,
-                                                               v_lo, v_hi, set.d_desc, (uint32_t)set.plane_gs.size(),
-                                                               warp_smem, row_buf, bit_buf, set.ct, m->in_band ? 1u : 0u,
-                                                               set.need_row_bits ? 1u : 0u, direct ? 1u : 0u,
-                                                               fm::PackedRows{nullptr, nullptr, 0});
+        const bool bial = m->max_allele <= 1;
+        auto go = [&](auto kern) {
+            kern<<<blocks, warps * 32, smem, st>>>(data, data_bytes, missing, m->stride, v_base, word_base, v_lo, v_hi,
+                                                   set.d_desc, (uint32_t)set.plane_gs.size(), warp_smem, row_buf, bit_buf,
+                                                   set.ct, m->in_band ? 1u : 0u, set.need_row_bits ? 1u : 0u,
+                                                   direct ? 1u : 0u, fm::PackedRows{nullptr, nullptr, 0});
+        };
+        if (direct) {
+            if (bial) go(fm::fm_k_repack_rows<1, true>);
+            else go(fm::fm_k_repack_rows<1, false>);
+        } else {
+            if (bial) go(fm::fm_k_repack_rows<0, true>);
+            else go(fm::fm_k_repack_rows<0, false>);
+        }
         CK(cudaGetLastError());
         g_launches++;
         return;

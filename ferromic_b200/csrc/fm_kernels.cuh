@@ -155,12 +155,21 @@ struct PackedRows {
     uint32_t rw;
 };
 
-__global__ void __launch_bounds__(256)
+// MODE: 0 = general (staged row, every group kind), 1 = direct rows (whole 16-byte rows read straight from global
+// memory; groups are served from the full-row bit words only), 2 = packed rows.  Modes 1 and 2 compile without
+// the ballot-gather paths (fewer registers, more resident warps).  BIAL: every cell is 0, 1 or (in band) missing,
+// so the allele bit of a byte is its bit 0 -- three operations per four cells instead of seven.
+template <int MODE, bool BIAL>
+__global__ void __launch_bounds__(256, MODE == 0 ? 4 : 6)
 fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint64_t *__restrict__ missing,
                  size_t stride, uint32_t v_base, uint64_t word_base, uint32_t v_lo, uint32_t v_hi,
                  const RepackGroup *__restrict__ groups, uint32_t n_groups, uint32_t warp_smem_bytes,
                  uint32_t row_buf_bytes, uint32_t bit_buf_bytes, CountTable ct, uint32_t in_band,
-                 uint32_t need_row_bits, uint32_t direct_rows, PackedRows pk) {
+                 uint32_t need_row_bits, uint32_t direct_rows_arg, PackedRows pk_arg) {
+    constexpr uint32_t direct_rows = MODE == 1 ? 1u : 0u;
+    PackedRows pk = pk_arg;
+    if (MODE != 2) pk.a = nullptr;  // lets the compiler drop the packed path
+    (void)direct_rows_arg;
     // direct_rows: every group is served from the full-row bit words (compress plans / count tables) and rows are
     // whole 16-byte words, so the u8 row is packed straight from global memory (coalesced 16-byte loads) and is
     // never staged: row_buf_bytes == 0, three times the resident warps per SM
@@ -250,6 +259,7 @@ fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint
                 const uint32_t nq16 = ((uint32_t)stride + 15u) >> 4;
                 // bit 7 of every non-zero byte (the add only sees 7-bit fields: no carry crosses bytes), gathered by one multiply
                 auto nib = [](uint32_t w) {
+                    if (BIAL) return ((w & 0x01010101u) * 0x01020408u) >> 24;  // cells are 0 / 1 (missing ones are masked later)
                     return (((((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w) >> 7 & 0x01010101u) * 0x01020408u) >> 24;
                 };
                 auto cnib = [](uint32_t w) { return (((~w >> 7) & 0x01010101u) * 0x01020408u >> 24) & 0xFu; };
@@ -373,6 +383,7 @@ fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint
                 __syncwarp();
                 continue;
             }
+            if (MODE != 0) continue;  // direct / packed launches only carry plan groups (checked on the host)
             if (G.n_bits == 1) {
                 // biallelic fast path: words whose 32 haplotypes all exist run a branch-free loop
                 // (one offset load, one bit test, one byte test, two ballots per word)

@@ -172,7 +172,7 @@ def test_sparse_missing_list_equals_called_plane(n_samples, missing):
     g[7] = -1  # a row without any call
     miss = g < 0
     alle = np.where(miss, 0, g).astype(np.uint8)
-    sparse = _Matrix(alle, miss, pos, max_allele=1, always_bitmap=True, ingest="packed")
+    sparse = _Matrix(alle, miss, pos, max_allele=1, always_bitmap=True, ingest="packed-sparse")
     assert sparse.ingest_mode == "packed-sparse"
     u8 = _Matrix(alle, miss, pos, max_allele=1, always_bitmap=True, ingest="u8")
     vs, d = orc.from_numpy(g, pos)
