@@ -145,7 +145,7 @@ def lib() -> C.CDLL:
                             C.POINTER(sz)]
     L.fm_wc_window_sums.argtypes = [vp, vp, sz, vp, vp, vp, vp, vp, vp, vp]
     L.fm_fst_estimate_from_sums.argtypes = [dbl, dbl, u64, u64, C.POINTER(FstEstimateC)]
-    L.fm_wc_arith_probe.argtypes = [vp, vp, vp, vp, sz]
+    L.fm_wc_arith_probe.argtypes = [vp, vp, vp, vp, vp, sz]
     L.fm_adjusted_sequence_length.argtypes = [i64, i64, vp, sz, vp, sz, C.POINTER(i64)]
     L.fm_group_window_sums.argtypes = [vp, vp, sz, vp, vp, vp, vp]
     L.fm_hudson_window_sums.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, vp, vp]

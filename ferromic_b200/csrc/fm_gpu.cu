@@ -388,6 +388,21 @@ struct TimerEventPool {
 };
 thread_local TimerEventPool t_timer_events;
 
+// One non-blocking side stream per (host thread, device) for small kernels that run underneath a large one.
+struct SideStreams {
+    cudaStream_t s[64] = {};
+    ~SideStreams() {
+        for (cudaStream_t x : s)
+            if (x) cudaStreamDestroy(x);
+    }
+    cudaStream_t get(int dev) {
+        const int d = (dev >= 0 && dev < 64) ? dev : 0;
+        if (!s[d]) CK(cudaStreamCreateWithFlags(&s[d], cudaStreamNonBlocking));
+        return s[d];
+    }
+};
+thread_local SideStreams t_side_streams;
+
 struct Timer {
     cudaEvent_t a, b;
     int dev = 0;
@@ -3309,6 +3324,8 @@ void run_wc(fm_partition *p, const std::vector<uint32_t> &wlo, const std::vector
     const uint32_t blocks = std::max<uint32_t>(1, std::min<uint32_t>(n_seg, 8u * sm_count(m->device)));
     Timer tm;
     tm.start();
+    EventPairs wc_events;
+    cudaEvent_t wc_ready = wc_events.next();
     if (multi) {
         const uint32_t threads = (n_pw + 1) * 32;
         auto launch = [&](auto kern) {
@@ -3323,6 +3340,7 @@ void run_wc(fm_partition *p, const std::vector<uint32_t> &wlo, const std::vector
         g_launches++;
     } else {
         const fm::WcTables T = wc_tables(p);
+        CK(cudaEventRecord(wc_ready, stream()));
         if (n_pairs) {
             auto launch = [&](auto kern) {
                 CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -3337,10 +3355,17 @@ void run_wc(fm_partition *p, const std::vector<uint32_t> &wlo, const std::vector
             CK(cudaGetLastError());
             g_launches++;
         }
+        // the overall components are one latency-bound warp per segment: they run on a side stream underneath the
+        // pair kernel (both only read the cached counts; the fold below joins them)
         const uint32_t ob = std::max<uint32_t>(1, std::min<uint32_t>((n_seg + 3) / 4, 16u * sm_count(m->device)));
-        fm::fm_k_wc_overall<<<ob, 128, 0, stream()>>>(W, T);
+        cudaStream_t side = t_side_streams.get(m->device);
+        CK(cudaStreamWaitEvent(side, wc_ready, 0));  // inputs and output buffers were set up before the pair launch
+        fm::fm_k_wc_overall<<<ob, 128, 0, side>>>(W, T);
         CK(cudaGetLastError());
         g_launches++;
+        cudaEvent_t join = wc_events.next();
+        CK(cudaEventRecord(join, side));
+        CK(cudaStreamWaitEvent(stream(), join, 0));
     }
     DevBuf<double> d_oo(nw * 2), d_op(nw * std::max(n_pairs, 1u) * 2);
     DevBuf<uint64_t> d_os(nw), d_on(nw * std::max(n_pairs, 1u));
@@ -3385,19 +3410,20 @@ fm_fst_estimate insufficient_estimate(uint64_t sites) {
 
 // test hook for the FP64 building blocks of the W&C kernels (fm_wc.cuh): y[i] = fm_recip_rn(b[i]),
 // q[i] = fm_div_recip(a[i], b[i], RN(1 / b[i])); host arrays
-fm_status fm_wc_arith_probe(const double *a, const double *b, double *y, double *q, size_t n) {
+fm_status fm_wc_arith_probe(const double *a, const double *b, double *y, double *q, double *q_int, size_t n) {
     return guarded([&] {
         if (n && (!a || !b || !y || !q)) fail(FM_ERR_INVALID_ARG, "NULL argument");
         require_device();
         CK(cudaSetDevice(t_device));
         if (!n) return;
-        DevBuf<double> da(n), db(n), dy(n), dq(n);
+        DevBuf<double> da(n), db(n), dy(n), dq(n), dq3(n);
         da.upload(a, n);
         db.upload(b, n);
-        fm::fm_k_wc_arith_probe<<<1024, 256, 0, stream()>>>(da.p, db.p, dy.p, dq.p, n);
+        fm::fm_k_wc_arith_probe<<<1024, 256, 0, stream()>>>(da.p, db.p, dy.p, dq.p, q_int ? dq3.p : nullptr, n);
         CK(cudaGetLastError());
         dy.download(y, n);
         dq.download(q, n);
+        if (q_int) dq3.download(q_int, n);
         CK(cudaStreamSynchronize(stream()));
     });
 }
@@ -3924,9 +3950,31 @@ fm_status fm_hudson_pair_sharded(fm_group *g1, fm_group *g2, int64_t sequence_le
         const uint32_t V = (uint32_t)m->V;
         const uint32_t nb = (V + 31) / 32;
         const uint32_t n_super = (nb + fm::kSuperBatches - 1) / fm::kSuperBatches;
-        DevBuf<double> pd((size_t)std::max(nb, 1u) * 5), sd((size_t)std::max(n_super, 1u) * 5);
-        DevBuf<uint32_t> pu((size_t)std::max(nb, 1u) * 3);
-        DevBuf<uint64_t> su((size_t)std::max(n_super, 1u) * 3);
+        // one allocation for all four scratch arrays: every trip through the caching allocator costs a few driver
+        // calls (event wait / create / record), and this call is only ~250 us long on an eighth of config 3
+        const size_t nb1 = std::max(nb, 1u), ns1 = std::max(n_super, 1u);
+        const size_t off_pd = 0, off_sd = off_pd + nb1 * 5 * 8, off_su = off_sd + ns1 * 5 * 8,
+                     off_pu = off_su + ns1 * 3 * 8, total_scratch = off_pu + nb1 * 3 * 4;
+        DevBuf<uint8_t> scratch(total_scratch);
+        struct View {
+            double *pd_, *sd_;
+            uint64_t *su_;
+            uint32_t *pu_;
+        } vw{reinterpret_cast<double *>(scratch.p + off_pd), reinterpret_cast<double *>(scratch.p + off_sd),
+             reinterpret_cast<uint64_t *>(scratch.p + off_su), reinterpret_cast<uint32_t *>(scratch.p + off_pu)};
+        struct { double *p; } pd{vw.pd_}, sd{vw.sd_};
+        struct { uint32_t *p; } pu{vw.pu_};
+        struct SuView {
+            uint64_t *p;
+            void download(uint64_t *h, size_t n) const {
+                if (n) CK(cudaMemcpyAsync(h, p, n * 8, cudaMemcpyDeviceToHost, stream()));
+            }
+        } su{vw.su_};
+        struct SdDl {
+            static void dl(const double *p, double *h, size_t n) {
+                if (n) CK(cudaMemcpyAsync(h, p, n * 8, cudaMemcpyDeviceToHost, stream()));
+            }
+        };
         fm::HudsonEpilogue he{};
         he.variant = -1;  // aggregate_hudson_components_from_summaries (stats.rs:1554-1623)
         he.part_d = pd.p;
@@ -3992,7 +4040,7 @@ fm_status fm_hudson_pair_sharded(fm_group *g1, fm_group *g2, int64_t sequence_le
         } else {
             std::vector<double> hd((size_t)n_super * 5);
             std::vector<uint64_t> hu((size_t)n_super * 3);
-            sd.download(hd.data(), hd.size());
+            SdDl::dl(sd.p, hd.data(), hd.size());
             su.download(hu.data(), hu.size());
             CK(cudaStreamSynchronize(stream()));
             double d[5];

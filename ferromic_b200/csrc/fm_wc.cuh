@@ -73,6 +73,20 @@ __device__ __forceinline__ double fm_div_recip(double a, double b, double y) {
     return __fma_rn(r, y, q);
 }
 
+// a / b from y = RN(1 / b) with ONE residual correction, for divisors that are "small integers up to a power of
+// two": b = n * 2^k with an integer 1 <= n < 2^40 (here n_i + n_j, half of it, half of it minus one, and
+// (n_i + n_j)^2 / 2).  Proof of exactness: q0 = RN(a * y) is within 1.5 ulp of a / b, and the corrected value
+// q0 + (a - b*q0) * y differs from a / b by at most 2^-53 * 1.5 ulp, so RN of it is RN(a / b) unless a / b lies
+// within 3 * 2^-54 ulp of a rounding midpoint m.  But a - n * 2^k * m is a non-zero multiple of ulp(a / b) * 2^k / 2
+// (a has 53 bits, m 54, and the exponents differ by at least log2 n), so |a / b - m| >= ulp / (2n) > 2^-41 ulp: no
+// quotient by such a divisor comes that close to a midpoint.  (An arbitrary 53-bit divisor can come within 2^-54
+// ulp -- the a-denominator 1 - c^2 therefore keeps the two-step fm_div_recip.)
+__device__ __forceinline__ double fm_div_recip_int(double a, double b, double y) {
+    const double q = a * y;
+    const double r = __fma_rn(-b, q, a);
+    return __fma_rn(r, y, q);
+}
+
 struct WcTables {            // indexed by an integer n = 0 .. n_max (n_max >= largest n_i + n_j of any pair)
     const double *inv_n;     // RN(1 / n)
     const double *inv_2nb2;  // RN(1 / (2 * (n/2) * (n/2))) = RN(2 / n^2): the c^2 divisor of a pair with n_i + n_j = n
@@ -117,21 +131,21 @@ __device__ __forceinline__ void fm_wc_pair_site(const double4 vi, const double4 
     // size-only terms
     const double d1 = n1 - n_bar, d2 = n2 - n_bar;
     const double ssd = d1 * d1 + d2 * d2;  // 0.0 + d1*d1 == d1*d1 (never -0)
-    const double c_squared = fm_div_recip(ssd, 2.0 * n_bar * n_bar, __ldg(T.inv_2nb2 + nsum));
+    const double c_squared = fm_div_recip_int(ssd, 2.0 * n_bar * n_bar, __ldg(T.inv_2nb2 + nsum));
     const double aden = 1.0 - c_squared;   // c_squared / (r - 1) with r - 1 == 1
     // 1 - c^2 is 1 exactly or at most 1 - 1/(n_i + n_j)^2: never the all-ones significand fm_recip_rn excludes
     const double raden = fm_recip_rn(aden);
-    const double ratio = fm_div_recip(n_bar, nbm1, r_nbm1);
+    const double ratio = fm_div_recip_int(n_bar, nbm1, r_nbm1);
     const double asd = vi.w + vj.w;     // exact
     // allele 0, then allele 1 (ascending order, stats.rs:1859)
-    const double gp0 = fm_div_recip(nsd - asd, nsd, r_nsd), gp1 = fm_div_recip(asd, nsd, r_nsd);
+    const double gp0 = fm_div_recip_int(nsd - asd, nsd, r_nsd), gp1 = fm_div_recip_int(asd, nsd, r_nsd);
     const double q10 = vi.x - gp0, q20 = vj.x - gp0, q11 = vi.y - gp1, q21 = vj.y - gp1;
     const double num0 = n1 * q10 * q10 + n2 * q20 * q20;  // 0.0 + (n1*q1)*q1, then + (n2*q2)*q2
     const double num1 = n1 * q11 * q11 + n2 * q21 * q21;
-    const double s20 = fm_div_recip(num0, n_bar, r_nbar), s21 = fm_div_recip(num1, n_bar, r_nbar);
+    const double s20 = fm_div_recip_int(num0, n_bar, r_nbar), s21 = fm_div_recip_int(num1, n_bar, r_nbar);
     const double x0 = gp0 * (1.0 - gp0) - (1.0 / 2.0) * s20, x1 = gp1 * (1.0 - gp1) - (1.0 / 2.0) * s21;
-    const double ta0 = fm_div_recip(s20 - fm_div_recip(x0, nbm1, r_nbm1), aden, raden);
-    const double ta1 = fm_div_recip(s21 - fm_div_recip(x1, nbm1, r_nbm1), aden, raden);
+    const double ta0 = fm_div_recip(s20 - fm_div_recip_int(x0, nbm1, r_nbm1), aden, raden);
+    const double ta1 = fm_div_recip(s21 - fm_div_recip_int(x1, nbm1, r_nbm1), aden, raden);
     pa = ta0 + ta1;  // 0.0 + ta0 == ta0 up to the sign of a zero
     pb = ratio * x0 + ratio * x1;
 }
@@ -189,7 +203,7 @@ fm_k_wc_pairs(const WcParams P, const WcTables T) {
                     if (c.y > 0) {
                         const double nd = (double)c.y, ad = (double)c.x;
                         const double y = __ldg(T.inv_n + c.y);
-                        o = make_double4(fm_div_recip((double)(c.y - c.x), nd, y), fm_div_recip(ad, nd, y), nd, ad);
+                        o = make_double4(fm_div_recip_int((double)(c.y - c.x), nd, y), fm_div_recip_int(ad, nd, y), nd, ad);
                     }
                 }
                 val[s * G + g] = o;
@@ -292,10 +306,11 @@ fm_k_wc_pairs(const WcParams P, const WcTables T) {
 
 // test hook: y[i] = fm_recip_rn(b[i]) and q[i] = fm_div_recip(a[i], b[i], RN(1 / b[i]))
 __global__ void fm_k_wc_arith_probe(const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ y,
-                                    double *__restrict__ q, uint64_t n) {
+                                    double *__restrict__ q, double *__restrict__ q3, uint64_t n) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         y[i] = fm_recip_rn(b[i]);
         q[i] = fm_div_recip(a[i], b[i], 1.0 / b[i]);
+        if (q3) q3[i] = fm_div_recip_int(a[i], b[i], 1.0 / b[i]);
     }
 }
 
@@ -348,7 +363,7 @@ fm_k_wc_overall(const WcParams P, const WcTables T) {
                                 const double d = nd - n_bar;
                                 ssd += d * d;
                                 const double y = __ldg(T.inv_n + n);
-                                const double f0 = fm_div_recip((double)(n - a), nd, y), f1 = fm_div_recip((double)a, nd, y);
+                                const double f0 = fm_div_recip_int((double)(n - a), nd, y), f1 = fm_div_recip_int((double)a, nd, y);
                                 const double q0 = f0 - gp0, q1 = f1 - gp1;
                                 ns0 += nd * q0 * q0;
                                 ns1 += nd * q1 * q1;

@@ -328,7 +328,8 @@ fm_status fm_fst_estimate_from_sums(double sum_a, double sum_b, uint64_t informa
  * q[i] = a[i] / b[i] computed from RN(1 / b[i]) with two residual corrections.  Both must equal IEEE
  * division bit for bit (tests/test_gpu_wc_arith.py); that is what lets K4 replace the per-pair divisions
  * of stats.rs:2034-2127 by table reciprocals without changing a single rounding. */
-fm_status fm_wc_arith_probe(const double *a, const double *b, double *y, double *q, size_t n);
+fm_status fm_wc_arith_probe(const double *a, const double *b, double *y, double *q, double *q_int_or_null,
+                            size_t n); /* q_int: the one-correction form used for integer-like divisors */
 
 /* ---- calculate_adjusted_sequence_length (stats.rs:3644-3736); host integer arithmetic ----
  * region is 1-based inclusive; allow/mask are 0-based half-open pairs; NULL <=> None. */

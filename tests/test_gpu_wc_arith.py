@@ -14,8 +14,9 @@ def probe(a, b):
     L = _lib.lib()
     a = np.ascontiguousarray(a, dtype=np.float64)
     b = np.ascontiguousarray(b, dtype=np.float64)
-    y, q = np.empty_like(a), np.empty_like(a)
-    _lib.check(L.fm_wc_arith_probe(a.ctypes.data, b.ctypes.data, y.ctypes.data, q.ctypes.data, a.size))
+    y, q, q3 = np.empty_like(a), np.empty_like(a), np.empty_like(a)
+    _lib.check(L.fm_wc_arith_probe(a.ctypes.data, b.ctypes.data, y.ctypes.data, q.ctypes.data, q3.ctypes.data, a.size))
+    probe.q_int = q3
     return y, q
 
 
@@ -27,6 +28,8 @@ def test_division_by_table_reciprocal_is_ieee_division():
     a = np.concatenate([rng.integers(0, 400_000, size=n // 2).astype(np.float64), rng.random(n - n // 2) * 3.0 - 1.0])
     _, q = probe(a, b)
     assert np.array_equal(q.view(np.uint64), (a / b).view(np.uint64))
+    # the one-correction form K4 uses for integer-like divisors (n, n/2, n^2/2 with n < 2^19): provably exact there
+    assert np.array_equal(probe.q_int.view(np.uint64), (a / b).view(np.uint64))
 
 
 def test_branch_free_reciprocal_is_ieee_reciprocal():
