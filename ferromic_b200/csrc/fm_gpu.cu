@@ -3956,25 +3956,15 @@ fm_status fm_hudson_pair_sharded(fm_group *g1, fm_group *g2, int64_t sequence_le
         const size_t off_pd = 0, off_sd = off_pd + nb1 * 5 * 8, off_su = off_sd + ns1 * 5 * 8,
                      off_pu = off_su + ns1 * 3 * 8, total_scratch = off_pu + nb1 * 3 * 4;
         DevBuf<uint8_t> scratch(total_scratch);
-        struct View {
-            double *pd_, *sd_;
-            uint64_t *su_;
-            uint32_t *pu_;
-        } vw{reinterpret_cast<double *>(scratch.p + off_pd), reinterpret_cast<double *>(scratch.p + off_sd),
-             reinterpret_cast<uint64_t *>(scratch.p + off_su), reinterpret_cast<uint32_t *>(scratch.p + off_pu)};
-        struct { double *p; } pd{vw.pd_}, sd{vw.sd_};
-        struct { uint32_t *p; } pu{vw.pu_};
-        struct SuView {
+        struct {
+            double *p;
+        } pd{reinterpret_cast<double *>(scratch.p + off_pd)}, sd{reinterpret_cast<double *>(scratch.p + off_sd)};
+        struct {
             uint64_t *p;
-            void download(uint64_t *h, size_t n) const {
-                if (n) CK(cudaMemcpyAsync(h, p, n * 8, cudaMemcpyDeviceToHost, stream()));
-            }
-        } su{vw.su_};
-        struct SdDl {
-            static void dl(const double *p, double *h, size_t n) {
-                if (n) CK(cudaMemcpyAsync(h, p, n * 8, cudaMemcpyDeviceToHost, stream()));
-            }
-        };
+        } su{reinterpret_cast<uint64_t *>(scratch.p + off_su)};
+        struct {
+            uint32_t *p;
+        } pu{reinterpret_cast<uint32_t *>(scratch.p + off_pu)};
         fm::HudsonEpilogue he{};
         he.variant = -1;  // aggregate_hudson_components_from_summaries (stats.rs:1554-1623)
         he.part_d = pd.p;
@@ -4040,8 +4030,8 @@ fm_status fm_hudson_pair_sharded(fm_group *g1, fm_group *g2, int64_t sequence_le
         } else {
             std::vector<double> hd((size_t)n_super * 5);
             std::vector<uint64_t> hu((size_t)n_super * 3);
-            SdDl::dl(sd.p, hd.data(), hd.size());
-            su.download(hu.data(), hu.size());
+            if (!hd.empty()) CK(cudaMemcpyAsync(hd.data(), sd.p, hd.size() * 8, cudaMemcpyDeviceToHost, stream()));
+            if (!hu.empty()) CK(cudaMemcpyAsync(hu.data(), su.p, hu.size() * 8, cudaMemcpyDeviceToHost, stream()));
             CK(cudaStreamSynchronize(stream()));
             double d[5];
             uint64_t u[3] = {0, 0, 0};
