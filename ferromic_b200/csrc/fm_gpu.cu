@@ -526,6 +526,10 @@ struct fm_group {
     uint32_t wq = 0;  // uint4 per plane row
     uint4 *d_allele = nullptr;
     uint4 *d_called = nullptr;
+    // tail layout (biallelic plane groups written by the compress plans): wq counts the FULL 16-byte words of a row,
+    // the last n % 128 haplotypes live in tw u32 words per row in d_tail_a / d_tail_c (fm_kernels.cuh GroupPlanes)
+    uint32_t tw = 0;
+    uint32_t *d_tail_a = nullptr, *d_tail_c = nullptr;
     double *d_tab = nullptr;   // 3 x (n+1) doubles: 1/k, k/(k-1), 1/H_{k-1}
     uint32_t *d_off = nullptr; // device copy of `off` (K1)
     std::mutex mu;
@@ -694,7 +698,7 @@ void launch_plane_pass(fm::PassParams<NG> P, int device) {
     t_tim.stats_launches++;
     uint64_t bytes = 0;
     for (int g = 0; g < NG; ++g)
-        bytes += (uint64_t)(P.geom.v_hi - P.geom.v_lo) * P.g[g].wq * 16u * (P.g[g].called ? 2u : 1u);
+        bytes += (uint64_t)(P.geom.v_hi - P.geom.v_lo) * (P.g[g].wq * 16u + P.g[g].tw * 4u) * (P.g[g].called ? 2u : 1u);
     t_tim.stats_bytes = bytes;
 }
 
@@ -776,7 +780,7 @@ void launch_plane_pass_seq(fm::SeqParams P, int device) {
     t_tim.stats_launches++;
     uint64_t bytes = 0;
     for (uint32_t i = 0; i < P.n_seg; ++i)
-        bytes += (uint64_t)(P.geom.v_hi - P.geom.v_lo) * P.seg[i].g.wq * 16u * (P.seg[i].g.called ? 2u : 1u);
+        bytes += (uint64_t)(P.geom.v_hi - P.geom.v_lo) * (P.seg[i].g.wq * 16u + P.seg[i].g.tw * 4u) * (P.seg[i].g.called ? 2u : 1u);
     t_tim.stats_bytes = bytes;
 }
 
@@ -822,7 +826,7 @@ bool launch_plane_pass_tab(std::vector<fm::TabSeg> &segs, uint32_t gpu, const st
             sg.rounds = rounds;
             sg.b_lo = sg.v_lo / 32;
             max_step = std::max(max_step, round_bytes * rounds);
-            bytes += (uint64_t)(sg.v_hi - sg.v_lo) * sg.g.wq * 16u * planes;
+            bytes += (uint64_t)(sg.v_hi - sg.v_lo) * (sg.g.wq * 16u + sg.g.tw * 4u) * planes;
         }
         keep.prefix[u] = (uint32_t)total;
         total += nb;
@@ -934,7 +938,7 @@ void set_tables(fm::DivEpilogue &e, const fm_group *g) {
 }
 
 fm::GroupPlanes planes_of(const fm_group *g) {
-    return fm::GroupPlanes{g->d_allele, g->d_called, g->wq, g->n};
+    return fm::GroupPlanes{g->d_allele, g->d_called, g->wq, g->n, g->d_tail_a, g->d_tail_c, g->tw};
 }
 
 // K5a: mask / filtered-position bit per site, one word per batch
@@ -1534,6 +1538,21 @@ static fm_group *alloc_group(fm_matrix *m, std::vector<uint32_t> &&off, bool cou
         g->wq = std::max<uint32_t>(1, (g->n + 127) / 128);
         g->n_bits = n_bits;
         g->count_only = count_only && n_bits == 1 && row_fits_smem(m);
+        {
+            // tail layout when the padded last word would waste more than a quarter of itself and the group is
+            // certain to be written by the compress plans (the only writer that knows the layout)
+            static const uint32_t no_tail = env_u32("FM_NO_TAIL", 0), no_plan = env_u32("FM_REPACK_BALLOT", 0),
+                                  v1 = env_u32("FM_REPACK_V1", 0);
+            const uint32_t tail_bits = g->n % 128;
+            const uint32_t tw = (tail_bits + 31) / 32;
+            // worth it when the row shrinks by at least 2 % (the tail words cost two extra loads per site in the
+            // epilogue: 2504 haplotypes = 19 words + 72 bits would save 4 of 320 bytes and run 3 % slower)
+            if (!no_tail && !no_plan && !v1 && n_bits == 1 && !g->count_only && row_fits_smem(m) && g->n >= 128 &&
+                tail_bits != 0 && tail_bits <= 96 && (16u - 4u * tw) * 50u >= 16u * g->wq) {
+                g->wq = g->n / 128;
+                g->tw = tw;
+            }
+        }
         const size_t plane_u4 = std::max<size_t>(m->V, 1) * g->wq;
         if (g->count_only && counts_slab) {
             g->d_alt = counts_slab;  // interior pointers: dev_free ignores them, the partition frees the slab
@@ -1544,6 +1563,11 @@ static fm_group *alloc_group(fm_matrix *m, std::vector<uint32_t> &&off, bool cou
         } else {
             g->d_allele = static_cast<uint4 *>(dev_alloc(plane_u4 * 16 * n_bits));
             if (m->has_missing) g->d_called = static_cast<uint4 *>(dev_alloc(plane_u4 * 16));
+            if (g->tw) {
+                const size_t tail_words = std::max<size_t>(m->V, 1) * g->tw;
+                g->d_tail_a = static_cast<uint32_t *>(dev_alloc(tail_words * 4));
+                if (m->has_missing) g->d_tail_c = static_cast<uint32_t *>(dev_alloc(tail_words * 4));
+            }
         }
         // per-n tables: 1/n, n/(n-1) (stats.rs:2728-2732) and 1/H_{n-1} with the harmonic number
         // by forward summation exactly like stats.rs:4234-4240 / 4718-4719
@@ -1611,7 +1635,8 @@ struct RepackSet {  // device-resident descriptor tables of the groups one launc
                 plane_gs.push_back(g);
                 h.push_back(fm::RepackGroup{g->d_off, g->n, g->wq, g->n_bits, reinterpret_cast<uint32_t *>(g->d_allele),
                                             reinterpret_cast<uint32_t *>(g->d_called),
-                                            std::max<size_t>(m->V, 1) * g->wq * 4, nullptr, nullptr, nullptr, 0});
+                                            std::max<size_t>(m->V, 1) * g->wq * 4, nullptr, nullptr, nullptr, 0,
+                                            g->d_tail_a, g->d_tail_c, g->tw});
                 plan_at.push_back(plan.size() / 8);
                 size_t ne = 0;
                 if (g->n_bits == 1 && ((staged && !no_plan) || m->packed)) {
@@ -1776,6 +1801,8 @@ static void launch_repack(const RepackSet &set, const uint8_t *data, size_t data
         return;
     }
     if (set.ct.n_groups) fail(FM_ERR_INVALID_ARG, "internal: count-only groups need the row-staged repack");
+    for (const fm_group *g : set.plane_gs)
+        if (g->tw) fail(FM_ERR_INVALID_ARG, "internal: a tail-layout group needs the plan path of the row-staged repack");
     for (const fm_group *g : set.plane_gs) {
         const uint32_t blocks = (uint32_t)std::min<uint64_t>(
             (uint64_t)sm_count(m->device) * 8,
@@ -1919,6 +1946,8 @@ fm_status fm_group_release(fm_group *g) {
     if (g->m) cudaSetDevice(g->m->device);
     dev_free(g->d_allele);
     dev_free(g->d_called);
+    dev_free(g->d_tail_a);
+    dev_free(g->d_tail_c);
     dev_free(g->d_tab);
     dev_free(g->d_off);
     dev_free(g->d_alt);
@@ -4953,8 +4982,8 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
             e.pi_form = FM_PIFORM_COUNTS;
             e.part_pi = pg[i].part_pi[0].p;
             e.part_u = pg[i].part_u[0].p;
-            bytes += (uint64_t)V * g->wq * 16u * (g->d_called ? 2u : 1u);
-            if (i < 8) out->group_bytes[i] = (uint64_t)V * g->wq * 16u * (g->d_called ? 2u : 1u) + (mode == 1 ? (uint64_t)V * 16u : 0);
+            bytes += (uint64_t)V * (g->wq * 16u + g->tw * 4u) * (g->d_called ? 2u : 1u);
+            if (i < 8) out->group_bytes[i] = (uint64_t)V * (g->wq * 16u + g->tw * 4u) * (g->d_called ? 2u : 1u) + (mode == 1 ? (uint64_t)V * 16u : 0);
             if (mode == 1) {
                 pg[i].pi.alloc(std::max<uint32_t>(V, 1));
                 pg[i].theta.alloc(std::max<uint32_t>(V, 1));
