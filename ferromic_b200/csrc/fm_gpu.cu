@@ -514,6 +514,11 @@ struct fm_matrix {
     uint32_t rw = 0;           // u32 words per packed row = ceil(stride / 32)
     size_t V = 0, S = 0, ploidy = 0, stride = 0;
     uint8_t max_allele = 0;
+    // max_allele > 15: the distinct allele values of the matrix (at most 16, value 0 always among them) are mapped to
+    // dense ranks in ascending order before they are bit-sliced; every estimator only depends on which alleles are
+    // equal and on their ascending order (stats.rs:1859), so the ranks give the reference's results
+    uint8_t plane_max_allele = 0;   // largest value the bitplanes have to hold (== max_allele without a remap)
+    uint8_t *d_lut = nullptr;       // [256] value -> rank, or nullptr
     std::vector<int64_t> pos;
     int64_t *d_pos = nullptr;
     bool sorted = true;
@@ -1365,14 +1370,54 @@ static fm_matrix *matrix_common(size_t V, size_t S, size_t ploidy, uint8_t max_a
     m->ploidy = ploidy;
     m->stride = S * ploidy;
     m->max_allele = max_allele;
-    if (positions)
+    m->plane_max_allele = max_allele;
+    // copy the caller's positions (one memcpy) and check that they ascend (branch-free, vectorisable pass)
+    bool sorted = true;
+    if (positions) {
         m->pos.assign(positions, positions + V);
-    else {
+        const int64_t *p = m->pos.data();
+        unsigned bad = 0;
+        for (size_t i = 1; i < V; ++i) bad |= (unsigned)(p[i] < p[i - 1]);
+        sorted = bad == 0;
+    } else {
         m->pos.resize(V);
         for (size_t i = 0; i < V; ++i) m->pos[i] = (int64_t)i;
     }
-    m->sorted = std::is_sorted(m->pos.begin(), m->pos.end());
+    m->sorted = sorted;
     return m;
+}
+
+// max_allele > 15 on a resident u8 matrix: find the allele values that occur (called cells), rank them in ascending
+// order (0 always first) and keep the value -> rank table on the device; K1 applies it while it bit-slices.  Real VCF
+// cohorts have at most 8 distinct values (the parser's 7-ALT limit); more than 16 stay unsupported.
+static void build_allele_remap(fm_matrix *m) {
+    if (m->max_allele <= 15 || !m->d_data) return;
+    const uint64_t total = (uint64_t)m->V * m->stride;
+    DevBuf<uint32_t> d_present(8);
+    CK(cudaMemsetAsync(d_present.p, 0, 32, stream()));
+    if (total) {
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>((total + 255) / 256, 32ull * sm_count(m->device));
+        fm::fm_k_allele_presence<<<blocks, 256, 0, stream()>>>(m->d_data, m->d_missing, total, m->in_band ? 1u : 0u,
+                                                               d_present.p);
+        CK(cudaGetLastError());
+        g_launches++;
+    }
+    uint32_t present[8] = {};
+    d_present.download(present, 8);
+    CK(cudaStreamSynchronize(stream()));
+    present[0] |= 1u;  // the reference allele keeps rank 0 whether it occurs or not
+    uint8_t lut[256] = {};
+    uint32_t rank = 0;
+    for (uint32_t v = 0; v < 256; ++v)
+        if ((present[v >> 5] >> (v & 31u)) & 1u) {
+            lut[v] = (uint8_t)std::min<uint32_t>(rank, 255u);
+            ++rank;
+        }
+    if (rank > 16) return;  // alloc_group reports the limit when a group is asked for
+    m->plane_max_allele = (uint8_t)std::max<uint32_t>(rank - 1, 2u);  // max_allele > 1 keeps the general (multi-allelic) forms
+    m->d_lut = static_cast<uint8_t *>(dev_alloc(256));
+    CK(cudaMemcpyAsync(m->d_lut, lut, 256, cudaMemcpyHostToDevice, stream()));
+    CK(cudaStreamSynchronize(stream()));
 }
 
 fm_status fm_matrix_create(const uint8_t *data, const uint64_t *missing, size_t V, size_t S,
@@ -1404,6 +1449,7 @@ fm_status fm_matrix_create(const uint8_t *data, const uint64_t *missing, size_t 
             if (V) CK(cudaMemcpyAsync(m->d_pos, m->pos.data(), V * 8, cudaMemcpyHostToDevice, stream()));
             tm.stop();
             t_tim.h2d_ms += tm.ms();
+            build_allele_remap(m);
         } catch (...) {
             fm_matrix_release(m);
             throw;
@@ -1435,6 +1481,7 @@ fm_status fm_matrix_create_inband(const uint8_t *data, size_t V, size_t S, size_
             if (V) CK(cudaMemcpyAsync(m->d_pos, m->pos.data(), V * 8, cudaMemcpyHostToDevice, stream()));
             tm.stop();
             t_tim.h2d_ms += tm.ms();
+            build_allele_remap(m);
         } catch (...) {
             fm_matrix_release(m);
             throw;
@@ -1462,6 +1509,7 @@ fm_status fm_matrix_create_device(const uint8_t *d_data, const uint64_t *d_missi
             m->d_pos = static_cast<int64_t *>(dev_alloc(std::max<size_t>(V, 1) * 8));
             if (V) CK(cudaMemcpyAsync(m->d_pos, m->pos.data(), V * 8, cudaMemcpyHostToDevice, stream()));
             CK(cudaStreamSynchronize(stream()));
+            build_allele_remap(m);
         } catch (...) {
             fm_matrix_release(m);
             throw;
@@ -1486,6 +1534,7 @@ fm_status fm_matrix_release(fm_matrix *m) {
         }
         dev_free(m->d_abits);
         dev_free(m->d_cbits);
+        dev_free(m->d_lut);
         dev_free(m->d_pos);
         delete m;
     }
@@ -1525,9 +1574,11 @@ static bool row_fits_smem(const fm_matrix *m) { return repack_warp_smem(m, nullp
 static fm_group *alloc_group(fm_matrix *m, std::vector<uint32_t> &&off, bool count_only = false,
                              uint32_t *counts_slab = nullptr) {
     uint32_t n_bits = 1;
-    while ((1u << n_bits) <= m->max_allele) ++n_bits;
+    while ((1u << n_bits) <= m->plane_max_allele) ++n_bits;
     if (n_bits > 4)
-        fail(FM_ERR_UNSUPPORTED, "allele indices above 15 are not supported on the GPU path (max_allele <= 15)");
+        fail(FM_ERR_UNSUPPORTED,
+             "more than 16 distinct allele values (or allele indices above 15 on a streamed / device-owned matrix) are "
+             "not supported on the GPU path");
     set_dev(m);
     fm_group *g = new fm_group();
     g->m = m;
@@ -1753,7 +1804,7 @@ static void launch_repack(const RepackSet &set, const uint8_t *data, size_t data
         const fm::PackedRows pk{m->d_abits, m->d_cbits, m->rw};
         fm::fm_k_repack_rows<2, true><<<blocks, warps * 32, smem, st>>>(nullptr, 0, nullptr, m->stride, 0, 0, v_lo, v_hi,
                                                                set.d_desc, (uint32_t)set.plane_gs.size(), warp_smem, 0, 0,
-                                                               set.ct, 0u, 1u, 0u, pk);
+                                                               set.ct, 0u, 1u, 0u, pk, nullptr);
         CK(cudaGetLastError());
         g_launches++;
         return;
@@ -1782,12 +1833,12 @@ static void launch_repack(const RepackSet &set, const uint8_t *data, size_t data
         const uint32_t per_sm = std::max(1u, std::min(8u, (uint32_t)((220u * 1024u) / smem)));
         const uint32_t blocks = std::max(1u, std::min<uint32_t>((rows + warps - 1) / warps,
                                                                 per_sm * (uint32_t)sm_count(m->device)));
-        const bool bial = m->max_allele <= 1;
+        const bool bial = m->plane_max_allele <= 1;
         auto go = [&](auto kern) {
             kern<<<blocks, warps * 32, smem, st>>>(data, data_bytes, missing, m->stride, v_base, word_base, v_lo, v_hi,
                                                    set.d_desc, (uint32_t)set.plane_gs.size(), warp_smem, row_buf, bit_buf,
                                                    set.ct, m->in_band ? 1u : 0u, set.need_row_bits ? 1u : 0u,
-                                                   direct ? 1u : 0u, fm::PackedRows{nullptr, nullptr, 0});
+                                                   direct ? 1u : 0u, fm::PackedRows{nullptr, nullptr, 0}, m->d_lut);
         };
         if (direct) {
             if (bial) go(fm::fm_k_repack_rows<1, true>);
@@ -1810,7 +1861,7 @@ static void launch_repack(const RepackSet &set, const uint8_t *data, size_t data
         fm::fm_k_repack<<<blocks, 256, 0, st>>>(data, missing, m->stride, g->d_off, g->n, g->wq, v_base, word_base, v_lo,
                                                 v_hi, reinterpret_cast<uint32_t *>(g->d_allele),
                                                 reinterpret_cast<uint32_t *>(g->d_called), g->n_bits,
-                                                std::max<size_t>(m->V, 1) * g->wq * 4, m->in_band ? 1u : 0u);
+                                                std::max<size_t>(m->V, 1) * g->wq * 4, m->in_band ? 1u : 0u, m->d_lut);
         CK(cudaGetLastError());
         g_launches++;
     }
@@ -4821,6 +4872,7 @@ fm_status fm_vcf_batch_matrix(const fm_vcf_batch *b, int pass_only, fm_matrix **
             m->d_pos = static_cast<int64_t *>(dev_alloc(std::max<size_t>(V, 1) * 8));
             CK(cudaMemcpyAsync(m->d_pos, m->pos.data(), V * 8, cudaMemcpyHostToDevice, stream()));
             CK(cudaStreamSynchronize(stream()));
+            build_allele_remap(m);
         } catch (...) {
             if (d_data) dev_free(d_data);
             if (m) fm_matrix_release(m);

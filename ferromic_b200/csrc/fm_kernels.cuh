@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256)
 fm_k_repack(const uint8_t *__restrict__ data, const uint64_t *__restrict__ missing, size_t stride,
             const uint32_t *__restrict__ off, uint32_t n, uint32_t wq, uint32_t v_base, uint64_t word_base,
             uint32_t v_lo, uint32_t v_hi, uint32_t *__restrict__ allele, uint32_t *__restrict__ called,
-            uint32_t n_bits, size_t plane_stride_words, uint32_t in_band) {
+            uint32_t n_bits, size_t plane_stride_words, uint32_t in_band, const uint8_t *__restrict__ lut) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -70,6 +70,7 @@ fm_k_repack(const uint8_t *__restrict__ data, const uint64_t *__restrict__ missi
                 byte = data[base + o];
                 if (in_band) c = byte < 0x80u;  // in-band missingness: a negative int8 cell
                 if (!c) byte = 0u;
+                else if (lut) byte = __ldg(lut + byte);  // allele values above 15: order-preserving dense ranks
             }
             const uint32_t wc = __ballot_sync(0xffffffffu, c);
             if (n_bits == 1) {  // biallelic: any non-zero allele index is the alternate allele
@@ -169,7 +170,7 @@ fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint
                  size_t stride, uint32_t v_base, uint64_t word_base, uint32_t v_lo, uint32_t v_hi,
                  const RepackGroup *__restrict__ groups, uint32_t n_groups, uint32_t warp_smem_bytes,
                  uint32_t row_buf_bytes, uint32_t bit_buf_bytes, CountTable ct, uint32_t in_band,
-                 uint32_t need_row_bits, uint32_t direct_rows_arg, PackedRows pk_arg) {
+                 uint32_t need_row_bits, uint32_t direct_rows_arg, PackedRows pk_arg, const uint8_t *__restrict__ lut) {
     constexpr uint32_t direct_rows = MODE == 1 ? 1u : 0u;
     PackedRows pk = pk_arg;
     if (MODE != 2) pk.a = nullptr;  // lets the compiler drop the packed path
@@ -466,6 +467,7 @@ fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint
                             c = byte < 0x80u;
                         }
                         if (!c) byte = 0u;
+                        else if (lut) byte = __ldg(lut + byte);  // allele values above 15: dense ranks
                     }
                     const uint32_t wc = __ballot_sync(FULL, c);
 #pragma unroll
@@ -517,6 +519,33 @@ fm_k_expand_called(const uint64_t *__restrict__ start, const ColT *__restrict__ 
         for (uint32_t w = lane; w < rw; w += 32) dst[w] = crow[w];
         __syncwarp();
     }
+}
+
+// Which allele values occur in a u8 matrix (called cells only)?  256-bit presence set, for the order-preserving
+// remap of matrices whose max_allele exceeds 15 (the bitplanes hold at most 4 bits per cell).
+__global__ void __launch_bounds__(256)
+fm_k_allele_presence(const uint8_t *__restrict__ data, const uint64_t *__restrict__ missing, uint64_t total,
+                     uint32_t in_band, uint32_t *__restrict__ present /*[8]*/) {
+    __shared__ uint32_t sp[8];
+    if (threadIdx.x < 8) sp[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t mine[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t b = data[i];
+        bool called = true;
+        if (missing) called = !((missing[i >> 6] >> (i & 63)) & 1ull);
+        else if (in_band) called = b < 0x80u;
+        if (called) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if ((b >> 5) == (uint32_t)k) mine[k] |= 1u << (b & 31u);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (mine[k]) atomicOr(&sp[k], mine[k]);
+    __syncthreads();
+    if (threadIdx.x < 8 && sp[threadIdx.x]) atomicOr(&present[threadIdx.x], sp[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------ synthetic cohorts

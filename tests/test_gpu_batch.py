@@ -123,3 +123,50 @@ def test_fused_hudson_first_call_equals_cached_path_and_oracle(ingest, missing):
         r = orc.build_summary(d, haps)
         assert np.array_equal(s["alt"], r.alt) and np.array_equal(s["called"], r.called)
         assert s["segregating_sites"] == r.seg
+
+
+@pytest.mark.parametrize("ingest", ["packed-dense", "packed-sparse", "u8"])
+def test_tail_word_plane_layout_group_sizes(ingest):
+    """Groups whose size is a few haplotypes past a multiple of 128 keep only their full 16-byte words in the streamed
+    plane; the rest of the row lives in per-site tail words (fm_kernels.cuh GroupPlanes).  Every size class -- no tail,
+    1 / 2 / 3 tail words, a tail too long to pay, below one word -- must count exactly like the oracle, through the
+    single-group pass, the multi-group launch, the fused Hudson sweep and the per-site tracks."""
+    import ferromic_b200 as F
+    from ferromic_b200 import _lib
+    from ferromic_b200.api import _Matrix
+    L = _lib.lib()
+    S = 1800
+    g, pos, _ = make_cohort(1300, S, missing_rate=0.02, seed=4242)
+    miss = g < 0
+    alle = np.where(miss, 0, g).astype(np.uint8)
+    vs, d = orc.from_numpy(g, pos)
+    rng = np.random.default_rng(9)
+    all_haps = both_sides(range(S))
+    sizes = [100, 128, 129, 160, 200, 224, 225, 256 + 33, 1545, 3463]
+    lists = []
+    for n in sizes:
+        pick = np.sort(rng.choice(len(all_haps), n, replace=False))
+        lists.append([all_haps[i] for i in pick])
+    m = _Matrix(alle, miss, pos, max_allele=1, always_bitmap=True, ingest=ingest)
+    groups = m.groups(lists)
+    refs = [orc.build_summary(d, h) for h in lists]
+    for grp, ref in zip(groups, refs):
+        got = grp.summary(want_arrays=True)
+        assert np.array_equal(got["alt"], ref.alt) and np.array_equal(got["called"], ref.called)
+        assert got["segregating_sites"] == ref.seg
+    # fused Hudson sweep on fresh groups of tail sizes (1545 vs 3463: the bench's orientation-group sizes)
+    m2 = _Matrix(alle, miss, pos, max_allele=1, always_bitmap=True, ingest=ingest)
+    a, b = m2.group(lists[-2]), m2.group(lists[-1])
+    Lseq = int(pos[-1] - pos[0] + 1)
+    out = _lib.HudsonOutcome()
+    n = C.c_size_t()
+    _lib.check(L.fm_hudson_pair(a.handle, b.handle, Lseq, Lseq, _lib.FM_HUDSON_SUMMARIES, 0, 0, 0, len(lists[-2]),
+                                len(lists[-1]), C.byref(out), None, C.byref(n)))
+    o1 = orc.Pop(lists[-2], vs, S, Lseq, dense=d, summary=refs[-2])
+    o2 = orc.Pop(lists[-1], vs, S, Lseq, dense=d, summary=refs[-1])
+    rc, ref, _ = orc.hudson_pair(o1, o2)
+    for k in ("fst", "d_xy", "pi_pop1", "pi_pop2"):
+        assert abs(getattr(out, k) - ref[k]) <= 1e-9 * abs(ref[k])
+    for grp, r in ((a, refs[-2]), (b, refs[-1])):
+        s = grp.summary(want_arrays=True)
+        assert np.array_equal(s["alt"], r.alt) and np.array_equal(s["called"], r.called)

@@ -505,6 +505,58 @@ def test_multi_allelic_dense_population_paths(max_allele, missing):
             assert close(getattr(s, a), r[a], 1e-12), (s.position, a)
 
 
+@pytest.mark.parametrize("values,missing", [([0, 3, 17, 40, 200, 254], 0.1), ([0, 16], 0.0), ([0, 1, 2, 250], 0.05),
+                                            (list(range(0, 160, 10)), 0.02)])
+def test_allele_values_above_15_are_remapped(values, missing):
+    """Allele indices up to 254 (stats.rs:4573-4589 counts in 256 bins): the GPU path bit-slices at most 4 bits per cell,
+    so a matrix whose max_allele exceeds 15 has its DISTINCT values (up to 16, 0 always among them) mapped to ranks in
+    ascending order before K1 -- the estimators only depend on allele identity and ascending order.  Dense population
+    paths against the oracle on the original values."""
+    F = fm()
+    S = 22
+    k = len(values) - 1
+    g0, pos = make_multi_cohort(600, S, k, missing, seed=700 + k)
+    lut = np.asarray(values, dtype=np.int16)
+    g = np.where(g0 < 0, np.int16(-1), lut[np.clip(g0, 0, k)]).astype(np.int16)
+    L = int(pos[-1] - pos[0] + 1)
+    names = [f"s{i}" for i in range(S)]
+    h1 = both_sides(range(0, S // 2)) + [(S - 1, 0)]
+    h2 = both_sides(range(S // 2, S - 1)) + [(S - 1, 1)]
+    base = F.Population.from_numpy("all", g, pos, h1 + h2, L, sample_names=names)
+    p1, p2 = base.with_haplotypes("p1", h1), base.with_haplotypes("p2", h2)
+    vs, d = orc.from_numpy(g, pos)
+    assert d.max_allele == max(values)
+    o1 = orc.Pop(h1, vs, S, L, dense=d)
+    o2 = orc.Pop(h2, vs, S, L, dense=d)
+    assert p1.segregating_sites() == orc.count_segregating_sites_for_population(o1)
+    assert p2.segregating_sites() == orc.count_segregating_sites_for_population(o2)
+    assert close(p1.nucleotide_diversity(), orc.pi_for_population(o1))
+    rc, ref, _ = orc.hudson_pair(o1, o2)
+    got = F.hudson_fst(p1, p2)
+    assert rc == 0
+    for key in ("fst", "d_xy", "pi_pop1", "pi_pop2", "pi_xy_avg"):
+        assert close(getattr(got, key), ref[key]), key
+    region = (int(pos[5]), int(pos[-7]))
+    rc, ref, rsites = orc.hudson_pair(o1, o2, region=region)
+    out, sites = F.hudson_fst_with_sites(p1, p2, region)
+    assert rc == 0 and len(sites) == len(rsites)
+    for s_, r in zip(sites, rsites):
+        for a in ("fst", "d_xy", "pi_pop1", "pi_pop2"):
+            assert close(getattr(s_, a), r[a], 1e-12), (s_.position, a)
+
+
+def test_more_than_16_distinct_allele_values_fail_loudly():
+    F = fm()
+    S = 12
+    rng = np.random.default_rng(1)
+    g = rng.integers(0, 40, size=(50, S, 2)).astype(np.int16)  # 40 distinct values
+    pos = np.arange(50, dtype=np.int64) * 7
+    haps = both_sides(range(S))
+    base = F.Population.from_numpy("all", g, pos, haps, 400, sample_names=[f"s{i}" for i in range(S)])
+    with pytest.raises(NotImplementedError):
+        base.segregating_sites()
+
+
 @pytest.mark.parametrize("max_allele", [2, 5])
 def test_multi_allelic_sparse_paths(max_allele):
     """Variant-list inputs (no dense matrix): calculate_pi, per-site diversity, cohort segregating sites and
