@@ -352,6 +352,39 @@ bool host_is_pinned(const void *p) {
     return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
 }
 
+// Device alias of a caller's host buffer when the WHOLE range [p, p + bytes) lies inside one page-locked allocation
+// (cudaHostAlloc / cudaHostRegister): kernels can then store results straight into it over PCIe instead of writing
+// HBM and copying afterwards.  nullptr for pageable memory or when the range cannot be proved.
+void *mapped_host_range(const void *p, size_t bytes) {
+    if (!p || !bytes) return nullptr;
+    static const uint32_t off = env_u32_early("FM_NO_DIRECT_TRACKS", 0);
+    if (off) return nullptr;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    typedef int (*range_fn)(unsigned long long *, size_t *, unsigned long long);  // cuMemGetAddressRange
+    static range_fn get_range = [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            fn = nullptr;
+        }
+        return reinterpret_cast<range_fn>(fn);
+    }();
+    if (!get_range) return nullptr;
+    unsigned long long base = 0;
+    size_t size = 0;
+    const unsigned long long dp = (unsigned long long)(uintptr_t)at.devicePointer;
+    if (get_range(&base, &size, dp) != 0) return nullptr;
+    if (dp < base || dp - base > size || bytes > size - (dp - base)) return nullptr;
+    return at.devicePointer;
+}
+
 // copy caller memory to the device on `st`; the source may be reused as soon as this returns
 // only if the caller synchronises `st` (pinned) -- pageable sources are already released.
 void h2d(void *dst, const void *src, size_t bytes, cudaStream_t st) {
@@ -1110,24 +1143,28 @@ DivResult run_diversity(fm_group *g, uint32_t v_lo, uint32_t v_hi, int pi_form, 
 // Diversity statistics of several groups of one matrix over [v_lo, v_hi).  Groups whose counts
 // are not cached yet and whose rows fit the non-chunked geometry share ONE plane-pass launch
 // (fm_k_plane_pass_seq); everything else goes group by group through run_diversity.
-void run_diversity_multi(fm_group *const *gs, size_t n, uint32_t v_lo, uint32_t v_hi, int pi_form,
+bool run_diversity_multi(fm_group *const *gs, size_t n, uint32_t v_lo, uint32_t v_hi, int pi_form,
                          double *const *d_pi, double *const *d_theta, const int64_t *d_mask, uint32_t n_mask,
-                         const int64_t *d_filt, uint32_t n_filt, DivResult *out, bool store_counts = false) {
+                         const int64_t *d_filt, uint32_t n_filt, DivResult *out, bool store_counts = false,
+                         Timer *ext_tm = nullptr) {
     fm::SeqParams P{};
     bool fuse = v_hi > v_lo;
     for (size_t i = 0; i < n && fuse; ++i) fuse = !gs[i]->have_counts;
     if (fuse) fuse = make_seq_params(gs, n, v_lo, v_hi, P);
     if (!fuse) {
-        for (size_t i = 0; i < n; ++i)
-            out[i] = run_diversity(gs[i], v_lo, v_hi, pi_form, d_pi ? d_pi[i] : nullptr, d_theta ? d_theta[i] : nullptr,
-                                   d_mask, n_mask, d_filt, n_filt, store_counts);
-        return;
+        for (size_t i = 0; i < n; ++i) {
+            DivResult r = run_diversity(gs[i], v_lo, v_hi, pi_form, d_pi ? d_pi[i] : nullptr, d_theta ? d_theta[i] : nullptr,
+                                        d_mask, n_mask, d_filt, n_filt, store_counts);
+            if (out) out[i] = r;
+        }
+        return false;
     }
     const fm::PassGeom &G = P.geom;
     std::vector<DevBuf<double>> part_pi(n);
     std::vector<DevBuf<uint32_t>> part_u(n);
     DevBuf<uint32_t> flags;
-    Timer tm;
+    Timer own_tm;
+    Timer &tm = ext_tm ? *ext_tm : own_tm;
     tm.start();
     const bool tracks = d_pi != nullptr;
     if (tracks && (d_mask || d_filt)) {
@@ -1153,13 +1190,14 @@ void run_diversity_multi(fm_group *const *gs, size_t n, uint32_t v_lo, uint32_t 
     }
     launch_plane_pass_seq(P, gs[0]->m->device);
     tm.stop();
-    for (size_t i = 0; i < n; ++i) {
+    for (size_t i = 0; i < n && out; ++i) {  // out == nullptr: the caller only wants the tracks
         double od[1];
         uint64_t ou[2];
         finish_partials(part_pi[i].p, 1, part_u[i].p, 2, G, od, ou);
         out[i] = DivResult{od[0], ou[0], ou[1]};
     }
-    t_tim.stats_ms += tm.ms();
+    if (out) t_tim.stats_ms += tm.ms();  // out == nullptr: the caller reads `ext_tm` after its own synchronise
+    return true;  // one fused launch, timed by `tm`
 }
 
 void ensure_counts(fm_group *g) {
@@ -1357,6 +1395,30 @@ fm_status fm_timings_get(fm_timings *out) {
 }
 
 // ------------------------------------------------------------------------------------ matrix
+// Host position vectors of released matrices, kept for the next matrix (see matrix_common).
+struct PosPool {
+    std::mutex mu;
+    std::vector<std::vector<int64_t>> free_list;
+    std::vector<int64_t> take(size_t n) {
+        std::lock_guard<std::mutex> lk(mu);
+        size_t best = free_list.size();
+        for (size_t i = 0; i < free_list.size(); ++i)
+            if (free_list[i].capacity() >= n && (best == free_list.size() || free_list[i].capacity() < free_list[best].capacity()))
+                best = i;
+        if (best == free_list.size()) return {};
+        std::vector<int64_t> v = std::move(free_list[best]);
+        free_list.erase(free_list.begin() + best);
+        if (v.capacity() > 2 * n + 1024) return {};  // far too large for this matrix: let it go
+        return v;
+    }
+    void give(std::vector<int64_t> &&v) {
+        if (v.capacity() < ((size_t)1 << 15) || v.capacity() > ((size_t)1 << 28)) return;
+        std::lock_guard<std::mutex> lk(mu);
+        if (free_list.size() < 4) free_list.emplace_back(std::move(v));
+    }
+};
+static PosPool g_pos_pool;
+
 static fm_matrix *matrix_common(size_t V, size_t S, size_t ploidy, uint8_t max_allele,
                                 const int64_t *positions) {
     if (ploidy != 0 && S != 0 && V > std::numeric_limits<size_t>::max() / S / ploidy)
@@ -1371,14 +1433,33 @@ static fm_matrix *matrix_common(size_t V, size_t S, size_t ploidy, uint8_t max_a
     m->stride = S * ploidy;
     m->max_allele = max_allele;
     m->plane_max_allele = max_allele;
-    // copy the caller's positions (one memcpy) and check that they ascend (branch-free, vectorisable pass)
+    // copy the caller's positions and check that they ascend.  The vector comes from a small pool of buffers
+    // handed back by released matrices (a fresh 8 MB vector costs ~1.5 ms of page faults per 1M sites, more than
+    // every kernel of a per-site call); large copies are split over a few host threads.
     bool sorted = true;
+    m->pos = g_pos_pool.take(V);
     if (positions) {
-        m->pos.assign(positions, positions + V);
-        const int64_t *p = m->pos.data();
-        unsigned bad = 0;
-        for (size_t i = 1; i < V; ++i) bad |= (unsigned)(p[i] < p[i - 1]);
-        sorted = bad == 0;
+        m->pos.resize(V);
+        int64_t *dst = m->pos.data();
+        auto copy_check = [dst, positions](size_t lo, size_t hi) -> unsigned {
+            std::memcpy(dst + lo, positions + lo, (hi - lo) * sizeof(int64_t));
+            unsigned bad = 0;
+            for (size_t i = std::max<size_t>(lo, 1); i < hi; ++i) bad |= (unsigned)(dst[i] < positions[i - 1]);
+            return bad;
+        };
+        const size_t T = V >= ((size_t)1 << 18) ? 4 : 1;
+        if (T == 1) {
+            sorted = copy_check(0, V) == 0;
+        } else {
+            unsigned bad[4] = {0, 0, 0, 0};
+            std::vector<std::thread> pool;
+            const size_t slice = (V + T - 1) / T;
+            for (size_t t = 1; t < T; ++t)
+                pool.emplace_back([&, t] { bad[t] = copy_check(std::min(V, slice * t), std::min(V, slice * (t + 1))); });
+            bad[0] = copy_check(0, std::min(V, slice));
+            for (auto &th : pool) th.join();
+            sorted = (bad[0] | bad[1] | bad[2] | bad[3]) == 0;
+        }
     } else {
         m->pos.resize(V);
         for (size_t i = 0; i < V; ++i) m->pos[i] = (int64_t)i;
@@ -1536,6 +1617,7 @@ fm_status fm_matrix_release(fm_matrix *m) {
         dev_free(m->d_cbits);
         dev_free(m->d_lut);
         dev_free(m->d_pos);
+        g_pos_pool.give(std::move(m->pos));
         delete m;
     }
     return FM_OK;
@@ -2247,55 +2329,23 @@ fm_status fm_watterson_theta(size_t seg, size_t n, int64_t L, double *out) {
     return FM_OK;
 }
 
+fm_status fm_per_site_diversity_multi(fm_group *const *groups, const size_t *raw_n, size_t n_groups, int64_t rs,
+                                      int64_t re, const int64_t *mask_iv, size_t n_mask, const int64_t *filtered,
+                                      size_t n_filt, int64_t *pos_out, double *pi_out, double *theta_out,
+                                      size_t capacity, size_t *n_out);
+
 fm_status fm_per_site_diversity(fm_group *g, size_t raw_n, int64_t rs, int64_t re, const int64_t *mask_iv,
                                 size_t n_mask, const int64_t *filtered, size_t n_filt, int64_t *pos_out,
                                 double *pi_out, double *theta_out, size_t capacity, size_t *n_out) {
-    return guarded([&] {
-        FM_NVTX("fm_per_site_diversity (K2 plane pass + tracks)");
+    fm_status st = guarded([&] {
         if (!g || !n_out) fail(FM_ERR_INVALID_ARG, "NULL argument");
         *n_out = 0;
         require_device();
-        if (region_len(rs, re) <= 0) return;  // stats.rs:4656-4666
-        if (raw_n < 2) return;                // stats.rs:4675-4681
-        set_dev(g->m);
-        uint32_t lo, hi;
-        site_range(g->m, rs, re, lo, hi);
-        const size_t n = hi - lo;
-        if (n == 0) return;
-        if (n > capacity) fail(FM_ERR_INVALID_ARG, "output capacity too small");
-        if (!pi_out || !theta_out) fail(FM_ERR_INVALID_ARG, "output arrays are NULL");
-        std::vector<int64_t> merged;
-        DevBuf<int64_t> d_mask, d_filt;
-        if (mask_iv) {
-            merge_intervals(mask_iv, n_mask, merged);
-            d_mask.alloc(std::max<size_t>(merged.size(), 2));
-            d_mask.upload(merged.data(), merged.size());
-        }
-        std::vector<int64_t> fs;
-        if (filtered && n_filt) {
-            fs.assign(filtered, filtered + n_filt);
-            std::sort(fs.begin(), fs.end());
-            d_filt.alloc(fs.size());
-            d_filt.upload(fs.data(), fs.size());
-        }
-        DevBuf<double> d_pi(n), d_theta(n);
-        {
-            std::lock_guard<std::mutex> lk(g->mu);  // serialise with lazy count caching
-            run_diversity(g, lo, hi, FM_PIFORM_COMPONENTS, d_pi.p, d_theta.p, mask_iv ? d_mask.p : nullptr,
-                          (uint32_t)(merged.size() / 2), fs.empty() ? nullptr : d_filt.p,
-                          (uint32_t)fs.size(), false);
-        }
-        Timer tm;
-        tm.start();
-        d_pi.download(pi_out, n);
-        d_theta.download(theta_out, n);
-        DevBuf<int64_t> d_p1;
-        download_positions_plus1(g->m, lo, n, pos_out, d_p1);  // stats.rs:4746
-        tm.stop();
-        CK(cudaStreamSynchronize(stream()));
-        t_tim.d2h_ms += tm.ms();
-        *n_out = n;
     });
+    if (st != FM_OK) return st;
+    if (raw_n < 2) return FM_OK;  // stats.rs:4675-4681: no sites at all (the multi-group call reports NaN rows)
+    return fm_per_site_diversity_multi(&g, &raw_n, 1, rs, re, mask_iv, n_mask, filtered, n_filt, pos_out, pi_out, theta_out,
+                                       capacity, n_out);
 }
 
 fm_status fm_per_site_diversity_multi(fm_group *const *groups, const size_t *raw_n, size_t n_groups, int64_t rs,
@@ -2340,15 +2390,47 @@ fm_status fm_per_site_diversity_multi(fm_group *const *groups, const size_t *raw
                 act.push_back(groups[i]);
                 act_idx.push_back(i);
             }
+        // Page-locked output arrays take the tracks straight from the kernel's epilogue (coalesced 256-byte stores
+        // over PCIe, no HBM round trip and no copy after the pass); pageable ones get device buffers + D2H copies.
         std::vector<DevBuf<double>> d_pi(act.size()), d_th(act.size());
         std::vector<double *> ppi(act.size()), pth(act.size());
+        std::vector<char> direct(act.size(), 0);
         for (size_t i = 0; i < act.size(); ++i) {
-            d_pi[i].alloc(n);
-            d_th[i].alloc(n);
-            ppi[i] = d_pi[i].p;
-            pth[i] = d_th[i].p;
+            double *mp = static_cast<double *>(mapped_host_range(pi_out + act_idx[i] * capacity, n * 8));
+            double *mt = static_cast<double *>(mapped_host_range(theta_out + act_idx[i] * capacity, n * 8));
+            if (mp && mt) {
+                direct[i] = 1;
+                ppi[i] = mp;
+                pth[i] = mt;
+            } else {
+                d_pi[i].alloc(n);
+                d_th[i].alloc(n);
+                ppi[i] = d_pi[i].p;
+                pth[i] = d_th[i].p;
+            }
         }
-        std::vector<DivResult> res(act.size());
+        // positions + 1 (stats.rs:4746): a small kernel on a side stream underneath the pass
+        DevBuf<int64_t> d_p1;
+        int64_t *pos_direct = (pos_out && n >= 65536) ? static_cast<int64_t *>(mapped_host_range(pos_out, n * 8)) : nullptr;
+        cudaStream_t side = nullptr;
+        struct SideJoin {  // an early exit must not leave the side kernel writing into the caller's buffer
+            cudaStream_t *s;
+            ~SideJoin() {
+                if (*s) cudaStreamSynchronize(*s);
+            }
+        } side_join{&side};
+        EventPairs evs;
+        if (pos_direct) {
+            side = t_side_streams.get(m->device);
+            cudaEvent_t e0 = evs.next();
+            CK(cudaEventRecord(e0, stream()));
+            CK(cudaStreamWaitEvent(side, e0, 0));
+            fm_k_pos_plus1<<<(uint32_t)std::min<size_t>((n + 255) / 256, 2048), 256, 0, side>>>(m->d_pos, lo, (uint32_t)n, pos_direct);
+            CK(cudaGetLastError());
+            g_launches++;
+        }
+        Timer pass_tm;
+        bool fused = false;
         {
             std::vector<std::unique_lock<std::mutex>> locks;
             std::vector<fm_group *> order(act);
@@ -2356,21 +2438,29 @@ fm_status fm_per_site_diversity_multi(fm_group *const *groups, const size_t *raw
             order.erase(std::unique(order.begin(), order.end()), order.end());
             for (fm_group *g : order) locks.emplace_back(g->mu);  // address order: no lock inversion
             if (!act.empty())
-                run_diversity_multi(act.data(), act.size(), lo, hi, FM_PIFORM_COMPONENTS, ppi.data(), pth.data(),
-                                    mask_iv ? d_mask.p : nullptr, (uint32_t)(merged.size() / 2),
-                                    fs.empty() ? nullptr : d_filt.p, (uint32_t)fs.size(), res.data());
+                fused = run_diversity_multi(act.data(), act.size(), lo, hi, FM_PIFORM_COMPONENTS, ppi.data(), pth.data(),
+                                            mask_iv ? d_mask.p : nullptr, (uint32_t)(merged.size() / 2),
+                                            fs.empty() ? nullptr : d_filt.p, (uint32_t)fs.size(), /*out=*/nullptr, false,
+                                            &pass_tm);
         }
         Timer tm;
         tm.start();
-        for (size_t i = 0; i < act.size(); ++i) {
-            d_pi[i].download(pi_out + act_idx[i] * capacity, n);
-            d_th[i].download(theta_out + act_idx[i] * capacity, n);
+        for (size_t i = 0; i < act.size(); ++i)
+            if (!direct[i]) {
+                d_pi[i].download(pi_out + act_idx[i] * capacity, n);
+                d_th[i].download(theta_out + act_idx[i] * capacity, n);
+            }
+        if (pos_direct) {
+            cudaEvent_t e1 = evs.next();
+            CK(cudaEventRecord(e1, side));
+            CK(cudaStreamWaitEvent(stream(), e1, 0));
+        } else {
+            download_positions_plus1(m, lo, n, pos_out, d_p1);
         }
-        DevBuf<int64_t> d_p1;
-        download_positions_plus1(m, lo, n, pos_out, d_p1);  // stats.rs:4746
         tm.stop();
         CK(cudaStreamSynchronize(stream()));
         t_tim.d2h_ms += tm.ms();
+        if (fused) t_tim.stats_ms += pass_tm.ms();
         const double NaN = std::numeric_limits<double>::quiet_NaN();
         for (size_t i = 0; i < n_groups; ++i)
             if (raw_n[i] < 2)
@@ -3316,10 +3406,11 @@ void run_wc(fm_partition *p, const std::vector<uint32_t> &wlo, const std::vector
     tot.pair.assign(nw * std::max(n_pairs, 1u) * 2, 0.0);
     tot.pair_n.assign(nw * std::max(n_pairs, 1u), 0);
     std::vector<uint32_t> seg_lo, seg_hi, wseg(nw + 1, 0);
+    static const uint32_t seg_sites = env_u32("FM_WC_SEG", fm::kWcSegSites);  // tuning only: changes the association
     for (size_t w = 0; w < nw; ++w) {
         wseg[w] = (uint32_t)seg_lo.size();
         for (uint32_t v = wlo[w]; v < whi[w];) {
-            const uint32_t e = std::min<uint64_t>(whi[w], ((uint64_t)v / fm::kWcSegSites + 1) * fm::kWcSegSites);
+            const uint32_t e = std::min<uint64_t>(whi[w], ((uint64_t)v / seg_sites + 1) * seg_sites);
             seg_lo.push_back(v);
             seg_hi.push_back(e);
             v = e;
@@ -3391,15 +3482,16 @@ void run_wc(fm_partition *p, const std::vector<uint32_t> &wlo, const std::vector
     W.part_pair = d_pp.p;
     W.part_pair_n = d_pn.p;
 
-    // CTA geometry: pair warps (lane = pair, KP pairs per lane in registers); the multi-allelic kernel adds one
-    // overall warp, the biallelic path evaluates the overall components in its own light kernel
-    // FM_WC_KP (tuning): pairs per lane; fewer, fatter warps per CTA leave room for more CTAs per SM
+    // multi-allelic kernel geometry: pair warps (lane = pair, KP pairs per lane in registers) + one overall warp per
+    // CTA, one CTA per segment; the biallelic path has its own pairs / overall kernels (below)
     static const uint32_t kp_pref = env_u32("FM_WC_KP", 1);
     uint32_t n_pw = std::max(1u, std::min<uint32_t>(fm::kWcMaxPairWarps, (n_pairs + 32 * kp_pref - 1) / (32 * kp_pref)));
     const uint32_t kp_need = std::max(1u, (n_pairs + n_pw * 32 - 1) / (n_pw * 32));
-    if (kp_need > fm::kWcMaxKP) fail(FM_ERR_UNSUPPORTED, "too many populations for the W&C kernel (pairs per lane)");
-    const size_t smem = multi ? fm::fm_wc_multi_cta_smem(G, A) : fm::fm_wc_cta_smem(G);
-    if (smem > 200 * 1024) fail(FM_ERR_UNSUPPORTED, "too many populations for the W&C kernel's staging");
+    const size_t smem = multi ? fm::fm_wc_multi_cta_smem(G, A) : 0;
+    if (multi) {
+        if (kp_need > fm::kWcMaxKP) fail(FM_ERR_UNSUPPORTED, "too many populations for the W&C kernel (pairs per lane)");
+        if (smem > 200 * 1024) fail(FM_ERR_UNSUPPORTED, "too many populations for the W&C kernel's staging");
+    }
     W.n_pair_warps = n_pw;
     const uint32_t blocks = std::max<uint32_t>(1, std::min<uint32_t>(n_seg, 8u * sm_count(m->device)));
     Timer tm;
@@ -3422,16 +3514,23 @@ void run_wc(fm_partition *p, const std::vector<uint32_t> &wlo, const std::vector
         const fm::WcTables T = wc_tables(p);
         CK(cudaEventRecord(wc_ready, stream()));
         if (n_pairs) {
+            // producer / consumer pairs kernel: task = (segment, chunk of 352 pair slots), grid-strided over a
+            // persistent grid of two CTAs per SM
+            const size_t psm = fm::fm_wc_pc_smem(G);
+            if (psm > 200 * 1024) fail(FM_ERR_UNSUPPORTED, "too many populations for the W&C kernel's staging");
+            const uint32_t n_chunks = (n_pairs + fm::kWcPcPairWarps * 32 - 1) / (fm::kWcPcPairWarps * 32);
+            static const uint32_t su = env_u32("FM_WC_SITES_PER_STEP", 1);
             auto launch = [&](auto kern) {
-                CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                kern<<<blocks, n_pw * 32, smem, stream()>>>(W, T);
+                CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+                int per_sm = 1;
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (int)((fm::kWcPcPairWarps + 1) * 32), psm));
+                const uint64_t tasks = (uint64_t)n_seg * n_chunks;
+                const uint32_t grid = (uint32_t)std::max<uint64_t>(
+                    1, std::min<uint64_t>(tasks, (uint64_t)std::max(per_sm, 1) * sm_count(m->device)));
+                kern<<<grid, (fm::kWcPcPairWarps + 1) * 32, psm, stream()>>>(W, T, n_chunks);
             };
-            static const uint32_t su = env_u32("FM_WC_SITES_PER_STEP", 2);
-            if (kp_need <= 1 && su >= 2) launch(fm::fm_k_wc_pairs<1, 2>);
-            else if (kp_need <= 1) launch(fm::fm_k_wc_pairs<1, 1>);
-            else if (kp_need <= 2) launch(fm::fm_k_wc_pairs<2, 1>);
-            else if (kp_need <= 4) launch(fm::fm_k_wc_pairs<4, 1>);
-            else launch(fm::fm_k_wc_pairs<8, 1>);
+            if (su >= 2) launch(fm::fm_k_wc_pairs_pc<2>);
+            else launch(fm::fm_k_wc_pairs_pc<1>);
             CK(cudaGetLastError());
             g_launches++;
         }
@@ -3450,11 +3549,15 @@ void run_wc(fm_partition *p, const std::vector<uint32_t> &wlo, const std::vector
     DevBuf<double> d_oo(nw * 2), d_op(nw * std::max(n_pairs, 1u) * 2);
     DevBuf<uint64_t> d_os(nw), d_on(nw * std::max(n_pairs, 1u));
     {
-        const uint64_t threads = (uint64_t)nw * (n_pairs + 1);
-        const uint32_t fb = (uint32_t)std::min<uint64_t>((threads + 127) / 128, 8ull * sm_count(m->device));
-        fm::fm_k_wc_fold<<<std::max(fb, 1u), 128, 0, stream()>>>(d_po.p, d_pc.p, d_pp.p, d_pn.p, d_wseg.p,
-                                                                  (uint32_t)nw, n_pairs, d_oo.p, d_os.p, d_op.p,
-                                                                  d_on.p);
+        // one CTA per (window, block of 32 slots); as many warps as the longest window has chunks (up to 16)
+        uint32_t max_seg = 1;
+        for (size_t w = 0; w < nw; ++w) max_seg = std::max(max_seg, wseg[w + 1] - wseg[w]);
+        const uint32_t fw = std::max(1u, std::min<uint32_t>(fm::kWcFoldMaxWarps, (max_seg + fm::kWcFoldChunk - 1) / fm::kWcFoldChunk));
+        const uint32_t n_pb = (n_pairs + 1 + 31) / 32;
+        const uint32_t fb = (uint32_t)std::min<uint64_t>((uint64_t)nw * n_pb, 64ull * sm_count(m->device));
+        fm::fm_k_wc_fold<<<std::max(fb, 1u), fw * 32, 0, stream()>>>(d_po.p, d_pc.p, d_pp.p, d_pn.p, d_wseg.p,
+                                                                   (uint32_t)nw, n_pairs, n_pb, d_oo.p, d_os.p, d_op.p,
+                                                                   d_on.p);
         CK(cudaGetLastError());
         g_launches++;
     }
