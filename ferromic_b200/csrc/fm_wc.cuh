@@ -120,10 +120,11 @@ __device__ __forceinline__ void fm_wc_pair_site(const double4 vi, const double4 
     const double r_nsd = __ldg(T.inv_n + nsum);
     const double r_nbar = 2.0 * r_nsd;                        // RN(1 / n_bar), exact scaling
     const double r_nbm1 = 2.0 * __ldg(T.inv_n + (nsum - 2));  // RN(1 / (n_bar - 1))
-    // size-only terms
-    const double d1 = n1 - n_bar, d2 = n2 - n_bar;
-    const double ssd = d1 * d1 + d2 * d2;  // 0.0 + d1*d1 == d1*d1 (never -0)
-    const double c_squared = fm_div_recip_int(ssd, 2.0 * n_bar * n_bar, __ldg(T.inv_2nb2 + nsum));
+    // size-only terms.  Exact shortcuts (every intermediate is a small dyadic rational, nothing rounds):
+    // n2 - n_bar == -(n1 - n_bar), so (n1 - n_bar)^2 + (n2 - n_bar)^2 == 2 d1^2; and 2 * n_bar * n_bar == nsd * n_bar.
+    const double d1 = n1 - n_bar;
+    const double ssd = 2.0 * (d1 * d1);
+    const double c_squared = fm_div_recip_int(ssd, nsd * n_bar, __ldg(T.inv_2nb2 + nsum));
     const double aden = 1.0 - c_squared;   // c_squared / (r - 1) with r - 1 == 1
     // 1 - c^2 is 1 exactly or at most 1 - 1/(n_i + n_j)^2: never the all-ones significand fm_recip_rn excludes
     const double raden = fm_recip_rn(aden);
@@ -135,7 +136,9 @@ __device__ __forceinline__ void fm_wc_pair_site(const double4 vi, const double4 
     const double num0 = n1 * q10 * q10 + n2 * q20 * q20;  // 0.0 + (n1*q1)*q1, then + (n2*q2)*q2
     const double num1 = n1 * q11 * q11 + n2 * q21 * q21;
     const double s20 = fm_div_recip_int(num0, n_bar, r_nbar), s21 = fm_div_recip_int(num1, n_bar, r_nbar);
-    const double x0 = gp0 * (1.0 - gp0) - (1.0 / 2.0) * s20, x1 = gp1 * (1.0 - gp1) - (1.0 / 2.0) * s21;
+    // x = p(1 - p) - ((r - 1) / r) s^2 with (r - 1) / r == 0.5: halving is exact, so the fused form rounds once,
+    // exactly where the reference's subtraction does
+    const double x0 = __fma_rn(-0.5, s20, gp0 * (1.0 - gp0)), x1 = __fma_rn(-0.5, s21, gp1 * (1.0 - gp1));
     const double ta0 = fm_div_recip(s20 - fm_div_recip_int(x0, nbm1, r_nbm1), aden, raden);
     const double ta1 = fm_div_recip(s21 - fm_div_recip_int(x1, nbm1, r_nbm1), aden, raden);
     pa = ta0 + ta1;  // 0.0 + ta0 == ta0 up to the sign of a zero

@@ -1,4 +1,4 @@
-"""Parity at BASELINE.json's full sizes (configs 2-5) through size-independent properties:
+"""Parity at BASELINE.json's full sizes: configs[0] site by site, configs 2-5 through size-independent properties:
   * the cohort is generated on the device by the library's counter-based generator
     (fm_synth_fill) -- the host never holds the 50 GB matrix;
   * random site slices are re-evaluated on the CPU (tests/synth.py::synth_rows, integer-exact),
@@ -117,6 +117,47 @@ def check_count_slices(co, groups_haps, n_slices, width, rng):
             sums.append(s)
         slices.append((lo, hi, g, vs, d, sums))
     return dev, slices
+
+
+def test_config1_100k_sites_one_group_every_site_bit_exact():
+    """BASELINE configs[0] at its full size: 100k sites x 2504 diploid samples, ONE group of all 5008 haplotypes, no
+    missing data.  Every site's counts are compared with the oracle (the whole matrix is regenerated on the CPU in
+    chunks), then S, sum pi, pi and Watterson's theta of the region."""
+    L = _lib()
+    V, S = int(100_000 * SCALE), 2504
+    co = DeviceCohort(V, S, 102_504, np.zeros(S, dtype=np.uint16), 0.0, 0.0)
+    try:
+        haps = [(s, k) for s in range(S) for k in (0, 1)]
+        g = co.group(haps)
+        alt, called, seg, pi_sum, unc = co.counts(g)
+        ref_seg, ref_pi = 0, 0.0
+        step = 10_000
+        for lo in range(0, V, step):
+            hi = min(V, lo + step)
+            rows = co.slice_rows(lo, hi)
+            _, d = orc.from_numpy(rows, co.pos[lo:hi])
+            s = orc.build_summary(d, haps)
+            assert np.array_equal(alt[lo:hi], s.alt), f"alt counts differ in sites [{lo}, {hi})"
+            assert np.array_equal(called[lo:hi], s.called), f"called counts differ in sites [{lo}, {hi})"
+            ref_seg += s.seg
+            ref_pi += s.pi_sum
+        assert seg == ref_seg and unc == 0
+        assert _close(pi_sum, ref_pi, 1e-9)
+        Lr = int(co.pos[-1] - co.pos[0] + 1)
+        whole = orc.Summary(alt, called, len(haps), ref_seg, ref_pi)
+        ref = orc.pi_for_population(orc.Pop(haps, None, S, Lr, summary=whole))
+        for path in (L.FM_PI_SUMMARY, L.FM_PI_DENSE):
+            out = C.c_double()
+            L.check(L.lib().fm_group_pi(g, Lr, path, len(haps), C.byref(out)))
+            assert _close(out.value, ref, 1e-9)
+        n_seg = C.c_uint64()
+        L.check(L.lib().fm_group_segregating_sites(g, C.byref(n_seg)))
+        assert n_seg.value == ref_seg
+        th = C.c_double()
+        L.check(L.lib().fm_watterson_theta(ref_seg, len(haps), Lr, C.byref(th)))
+        assert _close(th.value, orc.watterson_theta(ref_seg, len(haps), Lr), 1e-12)
+    finally:
+        co.close()
 
 
 def test_config3_hudson_10M_sites_two_populations():
