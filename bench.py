@@ -624,12 +624,14 @@ def run_ours(args):
         h2d_packed = int(2 * V * rw * 4 + V * 8 + mask.size * 8)
         h2d_sparse = int(V * rw * 4 + (V + 1) * 8 + n_missing * 2 + V * 8 + mask.size * 8)
         e2e = {"value": r_sparse["value"], "unit": UNIT, "h2d_bytes_per_step": h2d_sparse,
-               "d2h_bytes_per_step": int(2 * 2 * V * 8), "steps": k, "ms_per_step": r_sparse["ms_per_step"],
+               "d2h_bytes_per_step": int(2 * 2 * V * 8 + V * 8), "steps": k, "ms_per_step": r_sparse["ms_per_step"],
                "breakdown_ms_per_step": r_sparse["breakdown_ms_per_step"],
                "host_phase_ms_per_step": r_sparse["host_phase_ms_per_step"],
                "api": "fm_ingest_begin / add_group x2 / fm_ingest_rows_packed_sparse (allele bit words + sparse missing list "
                       "from pinned host memory; chunked H2D overlapped with fm_k_expand_called + the compress pass K1p) / "
-                      "finish + fm_per_site_diversity_multi (one fused launch, tracks D2H into pinned host memory); per rank",
+                      "finish + fm_per_site_diversity_multi (one fused launch; the pi / theta tracks and the positions are stored by the "
+                      "kernels straight into the caller's page-locked arrays over PCIe, so `stats` in the breakdown includes the "
+                      "device-to-host traffic and `d2h` is ~0); per rank",
                "input": "packed rows: one allele bit per genotype + the columns of the missing cells of every row (CSR, u16), "
                         "as a parser emits them (include/ferromic_gpu.h); %d missing cells = %.2f %% of the matrix"
                         % (n_missing, 100.0 * n_missing / (V * stride)),

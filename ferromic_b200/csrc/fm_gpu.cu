@@ -530,6 +530,63 @@ inline int64_t region_len(int64_t rs, int64_t re) {  // QueryRegion::len (proces
 
 }  // namespace
 
+// Host copy of a matrix's variant positions: a page-locked buffer (pooled, see PosPool) so that the upload to the
+// device is a true asynchronous DMA, with a plain heap fallback.  The vector subset the library uses.
+struct HostPos {
+    int64_t *p = nullptr;
+    size_t n = 0, cap = 0;
+    bool pinned = false;
+    HostPos() = default;
+    HostPos(const HostPos &) = delete;
+    HostPos &operator=(const HostPos &) = delete;
+    HostPos(HostPos &&o) noexcept : p(o.p), n(o.n), cap(o.cap), pinned(o.pinned) { o.p = nullptr; o.n = o.cap = 0; }
+    HostPos &operator=(HostPos &&o) noexcept {
+        if (this != &o) {
+            reset();
+            p = o.p; n = o.n; cap = o.cap; pinned = o.pinned;
+            o.p = nullptr; o.n = o.cap = 0;
+        }
+        return *this;
+    }
+    ~HostPos() { reset(); }
+    void reset() {
+        if (p) {
+            if (pinned) cudaFreeHost(p);
+            else delete[] p;
+        }
+        p = nullptr;
+        n = cap = 0;
+    }
+    void reserve_fresh(size_t count) {  // contents are not kept
+        if (count <= cap) return;
+        reset();
+        const size_t want = (std::max<size_t>(count, 1) + 131071) & ~(size_t)131071;  // 1 MB steps
+        void *q = nullptr;
+        // small matrices stay on the heap: page-locking costs more than their whole upload
+        if (count >= ((size_t)1 << 18) && cudaHostAlloc(&q, want * sizeof(int64_t), cudaHostAllocDefault) == cudaSuccess) {
+            p = static_cast<int64_t *>(q);
+            pinned = true;
+        } else {
+            cudaGetLastError();
+            p = new int64_t[want];
+            pinned = false;
+        }
+        cap = want;
+    }
+    void resize(size_t count) {
+        reserve_fresh(count);
+        n = count;
+    }
+    int64_t *data() { return p; }
+    const int64_t *data() const { return p; }
+    size_t size() const { return n; }
+    const int64_t *begin() const { return p; }
+    const int64_t *end() const { return p + n; }
+    int64_t &operator[](size_t i) { return p[i]; }
+    const int64_t &operator[](size_t i) const { return p[i]; }
+    bool operator!=(const HostPos &o) const { return n != o.n || (n && std::memcmp(p, o.p, n * sizeof(int64_t)) != 0); }
+};
+
 // ------------------------------------------------------------------------------------ handles
 struct fm_matrix {
     std::atomic<int> refs{1};
@@ -552,7 +609,7 @@ struct fm_matrix {
     // equal and on their ascending order (stats.rs:1859), so the ranks give the reference's results
     uint8_t plane_max_allele = 0;   // largest value the bitplanes have to hold (== max_allele without a remap)
     uint8_t *d_lut = nullptr;       // [256] value -> rank, or nullptr
-    std::vector<int64_t> pos;
+    HostPos pos;               // host copy of the positions, page-locked when possible (uploads straight from it)
     int64_t *d_pos = nullptr;
     bool sorted = true;
 };
@@ -1395,24 +1452,25 @@ fm_status fm_timings_get(fm_timings *out) {
 }
 
 // ------------------------------------------------------------------------------------ matrix
-// Host position vectors of released matrices, kept for the next matrix (see matrix_common).
+// Host position buffers of released matrices, kept for the next matrix: a fresh page-locked 8 MB buffer costs
+// milliseconds (cudaHostAlloc), a fresh pageable one ~1.5 ms of page faults per 1M sites -- more than every kernel
+// of a per-site call.
 struct PosPool {
     std::mutex mu;
-    std::vector<std::vector<int64_t>> free_list;
-    std::vector<int64_t> take(size_t n) {
+    std::vector<HostPos> free_list;
+    HostPos take(size_t n) {
         std::lock_guard<std::mutex> lk(mu);
         size_t best = free_list.size();
         for (size_t i = 0; i < free_list.size(); ++i)
-            if (free_list[i].capacity() >= n && (best == free_list.size() || free_list[i].capacity() < free_list[best].capacity()))
-                best = i;
+            if (free_list[i].cap >= n && (best == free_list.size() || free_list[i].cap < free_list[best].cap)) best = i;
         if (best == free_list.size()) return {};
-        std::vector<int64_t> v = std::move(free_list[best]);
+        HostPos v = std::move(free_list[best]);
         free_list.erase(free_list.begin() + best);
-        if (v.capacity() > 2 * n + 1024) return {};  // far too large for this matrix: let it go
+        if (v.cap > 2 * n + ((size_t)1 << 18)) return {};  // far too large for this matrix: let it go
         return v;
     }
-    void give(std::vector<int64_t> &&v) {
-        if (v.capacity() < ((size_t)1 << 15) || v.capacity() > ((size_t)1 << 28)) return;
+    void give(HostPos &&v) {
+        if (!v.p || v.cap > ((size_t)1 << 28)) return;
         std::lock_guard<std::mutex> lk(mu);
         if (free_list.size() < 4) free_list.emplace_back(std::move(v));
     }
@@ -2499,6 +2557,15 @@ struct fm_ingest {
 
 // Host work that does not depend on the rows -- the upload of the (pageable) position vector -- is done once,
 // after a rows call has queued its asynchronous copies, so it hides under the DMA instead of preceding it.
+// Page-locked positions (large matrices) are a true asynchronous copy: they go first on the copy stream of the first
+// rows call, 0.15 ms per 1M sites ahead of the row chunks.
+static void ingest_early_setup(fm_ingest *h) {
+    if (h->pos_uploaded || !h->m->pos.pinned) return;
+    fm_matrix *m = h->m;
+    if (m->V) CK(cudaMemcpyAsync(m->d_pos, m->pos.data(), m->V * 8, cudaMemcpyHostToDevice, h->copy_s));
+    h->pos_uploaded = true;
+}
+
 static void ingest_late_setup(fm_ingest *h) {
     if (h->pos_uploaded) return;
     fm_matrix *m = h->m;
@@ -2637,6 +2704,7 @@ fm_status fm_ingest_rows(fm_ingest *h, const uint8_t *rows, const uint64_t *miss
         if (!h->set.d_desc && !h->all.empty()) h->set.build(h->all);  // groups are final from here on
         if (!h->timing_started && n_rows) {
             CK(cudaEventRecord(h->t_copy0, h->copy_s));
+            ingest_early_setup(h);
             CK(cudaEventRecord(h->t_comp0, h->comp_s));
             h->timing_started = true;
         }
@@ -2730,6 +2798,7 @@ fm_status fm_ingest_rows_packed(fm_ingest *h, const uint32_t *allele_bits, const
         if (!h->set.d_desc && !h->all.empty()) h->set.build(h->all);  // groups are final from here on
         if (!h->timing_started && n_rows) {
             CK(cudaEventRecord(h->t_copy0, h->copy_s));
+            ingest_early_setup(h);
             CK(cudaEventRecord(h->t_comp0, h->comp_s));
             h->timing_started = true;
         }
@@ -2853,22 +2922,39 @@ fm_status fm_ingest_rows_packed_sparse(fm_ingest *h, const uint32_t *allele_bits
         if (!m->has_missing) fail(FM_ERR_INVALID_ARG, "matrix was declared without missing data: use fm_ingest_rows_packed");
         if (n_rows && m->stride && !allele_bits) fail(FM_ERR_INVALID_ARG, "allele_bits is NULL");
         set_dev(m);
+        static const uint32_t trace = env_u32("FM_INGEST_TRACE", 0);
+        std::vector<std::pair<const char *, std::chrono::steady_clock::time_point>> tr;
+        auto mark = [&](const char *what) {
+            if (trace) tr.emplace_back(what, std::chrono::steady_clock::now());
+        };
+        mark("start");
         const bool first_call = !m->d_abits;
         ensure_packed_storage(m, true);
         if (first_call) CK(cudaStreamSynchronize(stream()));
+        mark("storage");
         if (!h->set.d_desc && !h->all.empty()) h->set.build(h->all);
+        mark("plans");
         if (!h->timing_started && n_rows) {
             CK(cudaEventRecord(h->t_copy0, h->copy_s));
+            ingest_early_setup(h);
             CK(cudaEventRecord(h->t_comp0, h->comp_s));
             h->timing_started = true;
         }
         packed_sparse_rows(m, h->all.empty() ? nullptr : &h->set, allele_bits, row_missing_start, missing_cols, col_bytes,
                            first_row, n_rows, h->copy_s, h->comp_s, h->copied);
+        mark("queued");
         h->rows_done += n_rows;
         CK(cudaEventRecord(h->t_copy1, h->copy_s));
         CK(cudaEventRecord(h->t_comp1, h->comp_s));
         ingest_late_setup(h);
+        mark("positions");
         CK(cudaStreamSynchronize(h->copy_s));  // the caller's buffers are free again on return
+        mark("copies done");
+        if (trace) {
+            for (size_t i = 1; i < tr.size(); ++i)
+                fprintf(stderr, "[ingest] %-12s +%.3f ms\n", tr[i].first,
+                        std::chrono::duration<double, std::milli>(tr[i].second - tr[i - 1].second).count());
+        }
     });
 }
 
@@ -2926,6 +3012,7 @@ fm_status fm_ingest_rows_pack(fm_ingest *h, const uint8_t *rows, const uint64_t 
         if (!h->set.d_desc && !h->all.empty()) h->set.build(h->all);
         if (!h->timing_started && n_rows) {
             CK(cudaEventRecord(h->t_copy0, h->copy_s));
+            ingest_early_setup(h);
             CK(cudaEventRecord(h->t_comp0, h->comp_s));
             h->timing_started = true;
         }
@@ -5188,6 +5275,10 @@ fm_status fm_bench_diversity(fm_group *const *groups, size_t n_groups, int mode,
             out->other_launches++;
         };
         CK(cudaStreamSynchronize(stream()));
+        // start line on the device: an exchange without payload is a barrier over the mailboxes, so every rank's t0
+        // fires within microseconds of the others (the host-side barrier before this call leaves the ranks hundreds
+        // of microseconds apart after their own setup above, which the first timed exchange would then absorb)
+        if (comm) comm_launch(comm, nullptr, 0, 0, nullptr, 0, stream());
         CK(cudaEventRecord(t0, stream()));
         if (use_flags) {
             CK(cudaStreamWaitEvent(side.s, t0, 0));

@@ -24,12 +24,17 @@ def main():
     rw = (S * 2 + 31) // 32
     h_ab = torch.randint(0, 2 ** 31 - 1, (V * rw,), dtype=torch.int32).pin_memory()
     h_cb = torch.full((V * rw,), -1, dtype=torch.int32).pin_memory()
+    # sparse missing list: 50 missing cells per row (1 %), ascending columns
+    rng = np.random.default_rng(7)
+    cols = np.sort(rng.integers(0, S * 2, size=(V, 50), dtype=np.int64).astype(np.uint16), axis=1)
+    h_cols = torch.from_numpy(cols.reshape(-1).view(np.int16).copy()).pin_memory()
+    h_start = torch.arange(0, 50 * (V + 1), 50, dtype=torch.int64).pin_memory()
     out_pos = torch.empty(V, dtype=torch.int64, pin_memory=True).numpy()
     out_pi = torch.empty((2, V), dtype=torch.float64, pin_memory=True).numpy()
     out_th = torch.empty((2, V), dtype=torch.float64, pin_memory=True).numpy()
     raw_n = (C.c_size_t * 2)(len(g0), len(g1))
     rows = []
-    for it in range(4):
+    for it in range(5):
         T = {}
 
         def call(name, fn, *a):
@@ -41,7 +46,11 @@ def main():
         call("begin", L.fm_ingest_begin, V, S, 2, 1, 1, pos.ctypes.data, 0, C.byref(ih))
         for idx, side in garrs:
             call("add_group", L.fm_ingest_add_group, ih, idx.ctypes.data, side.ctypes.data, len(idx), None)
-        call("rows_packed", L.fm_ingest_rows_packed, ih, h_ab.data_ptr(), h_cb.data_ptr(), 0, V)
+        if it % 2 == 0:
+            call("rows_packed", L.fm_ingest_rows_packed, ih, h_ab.data_ptr(), h_cb.data_ptr(), 0, V)
+        else:
+            call("rows_packed_sparse", L.fm_ingest_rows_packed_sparse, ih, h_ab.data_ptr(), h_start.data_ptr(),
+                 h_cols.data_ptr(), 2, 0, V)
         mh = C.c_void_p()
         gh = (C.c_void_p * 2)()
         call("finish", L.fm_ingest_finish, ih, C.byref(mh), gh, None)
