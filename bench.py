@@ -533,6 +533,12 @@ def run_ours(args):
                                              h_start.data_ptr(), h_cols.data_ptr(), cap, 2, 0, C.byref(need)))
             pack_sparse_ms.append((time.perf_counter() - t0) * 1e3)
         n_missing = int(need.value)
+        # ... and the same list as one-byte gap codes (col_bytes = 1, include/ferromic_gpu.h): the headline input
+        h_startg = torch.empty(V + 1, dtype=torch.int64, pin_memory=True)
+        h_gaps = torch.empty(cap * 2, dtype=torch.uint8, pin_memory=True)
+        _lib.check(L.fm_pack_rows_sparse(h_data.data_ptr(), h_bitmap.data_ptr(), 1, 0, V, V, stride, h_ab2.data_ptr(),
+                                         h_startg.data_ptr(), h_gaps.data_ptr(), cap * 2, 1, 0, C.byref(need)))
+        n_gap_bytes = int(need.value)
         out_pos = torch.empty(V, dtype=torch.int64, pin_memory=True).numpy()  # caller-owned result buffers are pinned
         out_pi = torch.empty((2, V), dtype=torch.float64, pin_memory=True).numpy()
         out_th = torch.empty((2, V), dtype=torch.float64, pin_memory=True).numpy()
@@ -550,7 +556,9 @@ def run_ours(args):
             for idx, side in garrs:
                 _lib.check(L.fm_ingest_add_group(ih, idx.ctypes.data, side.ctypes.data, len(idx), None))
             lap("begin+declare_groups")
-            if mode == "packed_sparse":  # allele bits + sparse missing list; called words rebuilt on the device
+            if mode == "packed_gaps":  # allele bits + gap-coded missing list; called words rebuilt on the device
+                _lib.check(L.fm_ingest_rows_packed_sparse(ih, h_ab2.data_ptr(), h_startg.data_ptr(), h_gaps.data_ptr(), 1, 0, V))
+            elif mode == "packed_sparse":  # the same with u16 column indices
                 _lib.check(L.fm_ingest_rows_packed_sparse(ih, h_ab2.data_ptr(), h_start.data_ptr(), h_cols.data_ptr(), 2, 0, V))
             elif mode == "packed":    # 2-bit rows over PCIe, compressed into both groups' planes chunk by chunk
                 _lib.check(L.fm_ingest_rows_packed(ih, h_ab.data_ptr(), h_cb.data_ptr(), 0, V))
@@ -600,11 +608,14 @@ def run_ours(args):
                     "host_phase_ms_per_step": {k_: v_ / k for k_, v_ in phases.items()}}
 
         k = max(1, min(args.steps, args.e2e_steps))
-        r_sparse = timed("packed_sparse", k)
+        r_sparse = timed("packed_gaps", k)
         check_pi = out_pi.copy()
+        r_cols = timed("packed_sparse", k)
+        same_cols = bool(np.array_equal(np.isnan(check_pi), np.isnan(out_pi)) and
+                         np.array_equal(check_pi[~np.isnan(check_pi)], out_pi[~np.isnan(out_pi)]))
         r_packed = timed("packed", k)
-        same0 = bool(np.array_equal(np.isnan(check_pi), np.isnan(out_pi)) and
-                     np.array_equal(check_pi[~np.isnan(check_pi)], out_pi[~np.isnan(out_pi)]))
+        same0 = same_cols and bool(np.array_equal(np.isnan(check_pi), np.isnan(out_pi)) and
+                                   np.array_equal(check_pi[~np.isnan(check_pi)], out_pi[~np.isnan(out_pi)]))
         r_u8pack = timed("u8_pack", k)
         same = same0 and bool(np.array_equal(np.isnan(check_pi), np.isnan(out_pi)) and
                               np.array_equal(check_pi[~np.isnan(check_pi)], out_pi[~np.isnan(out_pi)]))
@@ -622,20 +633,23 @@ def run_ours(args):
                         "u8_ms_per_step": None if args.skip_u8 else timed("u8", 1, src)["ms_per_step"]}
             del p_data, p_bitmap
         h2d_packed = int(2 * V * rw * 4 + V * 8 + mask.size * 8)
-        h2d_sparse = int(V * rw * 4 + (V + 1) * 8 + n_missing * 2 + V * 8 + mask.size * 8)
+        h2d_cols = int(V * rw * 4 + (V + 1) * 8 + n_missing * 2 + V * 8 + mask.size * 8)
+        h2d_sparse = int(V * rw * 4 + (V + 1) * 8 + n_gap_bytes + V * 8 + mask.size * 8)
         e2e = {"value": r_sparse["value"], "unit": UNIT, "h2d_bytes_per_step": h2d_sparse,
                "d2h_bytes_per_step": int(2 * 2 * V * 8 + V * 8), "steps": k, "ms_per_step": r_sparse["ms_per_step"],
                "breakdown_ms_per_step": r_sparse["breakdown_ms_per_step"],
                "host_phase_ms_per_step": r_sparse["host_phase_ms_per_step"],
-               "api": "fm_ingest_begin / add_group x2 / fm_ingest_rows_packed_sparse (allele bit words + sparse missing list "
+               "api": "fm_ingest_begin / add_group x2 / fm_ingest_rows_packed_sparse (allele bit words + gap-coded missing list "
                       "from pinned host memory; chunked H2D overlapped with fm_k_expand_called + the compress pass K1p) / "
                       "finish + fm_per_site_diversity_multi (one fused launch; the pi / theta tracks and the positions are stored by the "
                       "kernels straight into the caller's page-locked arrays over PCIe, so `stats` in the breakdown includes the "
                       "device-to-host traffic and `d2h` is ~0); per rank",
-               "input": "packed rows: one allele bit per genotype + the columns of the missing cells of every row (CSR, u16), "
-                        "as a parser emits them (include/ferromic_gpu.h); %d missing cells = %.2f %% of the matrix"
-                        % (n_missing, 100.0 * n_missing / (V * stride)),
+               "input": "packed rows: one allele bit per genotype + the missing cells of every row as one-byte gap codes "
+                        "(CSR, col_bytes = 1), as a parser emits them (include/ferromic_gpu.h); %d missing cells = %.2f %% of "
+                        "the matrix in %d bytes" % (n_missing, 100.0 * n_missing / (V * stride), n_gap_bytes),
                "bits_per_genotype_over_pcie": 8.0 * h2d_sparse / (V * stride),
+               "packed_u16_columns": {**r_cols, "h2d_bytes_per_step": h2d_cols,
+                                      "what": "the same ingest with the missing list as u16 column indices (col_bytes = 2)"},
                "packed_called_plane": {**r_packed, "h2d_bytes_per_step": h2d_packed,
                                        "what": "fm_ingest_rows_packed: allele bit + called bit per genotype (2 bits)"},
                "packer": {"ms": min(pack_ms), "sparse_ms": min(pack_sparse_ms), "cores": threads,

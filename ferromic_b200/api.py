@@ -171,17 +171,23 @@ def pack_rows(alleles2d: np.ndarray, missing_mode: int, bitmap: Optional[np.ndar
     return ab, cb
 
 
+# The sparse missing list of packed rows goes over PCIe as one-byte gap codes (include/ferromic_gpu.h) unless this is
+# switched off (tests cover both forms).
+SPARSE_GAP_CODE = True
+
+
 def pack_rows_sparse(alleles2d: np.ndarray, missing_mode: int, bitmap: Optional[np.ndarray] = None, first_row: int = 0,
-                     n_total_rows: Optional[int] = None, threads: int = 0):
-    """fm_pack_rows_sparse: (allele_bits [rows, rw] u32, row_start [rows + 1] u64, missing_cols u16 / u32) -- the
-    packed rows with a sparse missing list instead of a called plane."""
+                     n_total_rows: Optional[int] = None, threads: int = 0, gap_code: bool = False):
+    """fm_pack_rows_sparse: (allele_bits [rows, rw] u32, row_start [rows + 1] u64, missing_cols) -- the packed rows
+    with a sparse missing list instead of a called plane.  missing_cols holds u16 / u32 column indices, or with
+    gap_code=True the one-byte gap code (col_bytes == 1)."""
     a = np.ascontiguousarray(alleles2d).view(np.uint8)
     assert a.ndim == 2
     rows, stride = a.shape
     rw = (stride + 31) // 32
     ab = np.zeros((rows, rw), dtype=np.uint32)
     start = np.zeros(rows + 1, dtype=np.uint64)
-    col_t = np.uint16 if stride <= 65536 else np.uint32
+    col_t = np.uint8 if gap_code else (np.uint16 if stride <= 65536 else np.uint32)
     total = rows + first_row if n_total_rows is None else n_total_rows
     L = lib()
     need = C.c_size_t()
@@ -224,7 +230,7 @@ class _Matrix:
             flat = a.reshape(self.V, self.S * self.P)
             if bits is not None and (self.ingest_mode == "packed-sparse" or
                                      (self.ingest_mode == "packed" and _sparse_missing_pays(missing_mask))):
-                ab, start, cols = pack_rows_sparse(flat, 1, bits)
+                ab, start, cols = pack_rows_sparse(flat, 1, bits, gap_code=SPARSE_GAP_CODE)
                 check(lib().fm_matrix_create_packed_sparse(_ptr(ab), _ptr(start), _ptr(cols), cols.itemsize, self.V, self.S,
                                                            self.P, _ptr(pos), C.byref(h)))
                 self.ingest_mode = "packed-sparse"
@@ -302,7 +308,8 @@ class _Matrix:
                 if r1 <= r0:
                     continue
                 if packed and sparse and bits is not None:  # allele bits + sparse missing list
-                    ab, start, cols = pack_rows_sparse(flat[r0:r1], 1, bits, first_row=int(r0), n_total_rows=self.V)
+                    ab, start, cols = pack_rows_sparse(flat[r0:r1], 1, bits, first_row=int(r0), n_total_rows=self.V,
+                                                       gap_code=SPARSE_GAP_CODE)
                     check(L.fm_ingest_rows_packed_sparse(ih, _ptr(ab), _ptr(start), _ptr(cols), cols.itemsize, int(r0),
                                                          int(r1 - r0)))
                 elif packed:  # fm_pack_rows on the host, 2 bits per genotype over PCIe (fm_ingest_rows_packed)

@@ -2843,7 +2843,15 @@ static void expand_called_launch(fm_matrix *m, const uint64_t *d_start, const vo
     const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / std::max<size_t>(smem, 1)));
     const uint32_t blocks = std::max(1u, std::min<uint32_t>((rows + warps - 1) / warps, per_sm * (uint32_t)sm_count(m->device)));
     static std::once_flag once2, once4;
-    if (col_bytes == 2) {
+    if (col_bytes == 1) {
+        static std::once_flag once1;
+        std::call_once(once1, [] {
+            cudaFuncSetAttribute(fm::fm_k_expand_called<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        });
+        fm::fm_k_expand_called<uint8_t><<<blocks, warps * 32, smem, st>>>(d_start, static_cast<const uint8_t *>(d_cols),
+                                                                           cols_base, r_base, v_lo, v_hi, m->rw,
+                                                                           (uint32_t)m->stride, m->d_cbits);
+    } else if (col_bytes == 2) {
         std::call_once(once2, [] {
             cudaFuncSetAttribute(fm::fm_k_expand_called<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         });
@@ -2865,7 +2873,7 @@ static void expand_called_launch(fm_matrix *m, const uint64_t *d_start, const vo
 static void packed_sparse_rows(fm_matrix *m, const RepackSet *set, const uint32_t *allele_bits, const uint64_t *row_start,
                                const void *missing_cols, int col_bytes, size_t first_row, size_t n_rows, cudaStream_t copy_s,
                                cudaStream_t comp_s, cudaEvent_t ev[2]) {
-    if (col_bytes != 2 && col_bytes != 4) fail(FM_ERR_INVALID_ARG, "col_bytes must be 2 or 4");
+    if (col_bytes != 1 && col_bytes != 2 && col_bytes != 4) fail(FM_ERR_INVALID_ARG, "col_bytes must be 1 (gap code), 2 or 4");
     if (col_bytes == 2 && m->stride > 65536) fail(FM_ERR_INVALID_ARG, "16-bit columns need a row stride <= 65536");
     if (n_rows && !row_start) fail(FM_ERR_INVALID_ARG, "row_start is NULL");
     const size_t rw = m->rw;

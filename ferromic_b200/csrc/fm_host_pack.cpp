@@ -266,7 +266,7 @@ const char *fm_host_pack_rows_sparse(const uint8_t *rows, const uint64_t *missin
                                      uint32_t *allele_bits, uint64_t *row_start, void *missing_cols, size_t capacity,
                                      int col_bytes, int n_threads, size_t *needed) {
     if (needed) *needed = 0;
-    if (col_bytes != 2 && col_bytes != 4) return "fm_pack_rows_sparse: col_bytes must be 2 or 4";
+    if (col_bytes != 1 && col_bytes != 2 && col_bytes != 4) return "fm_pack_rows_sparse: col_bytes must be 1 (gap code), 2 or 4";
     if (col_bytes == 2 && stride > 65536) return "fm_pack_rows_sparse: 16-bit columns need a row stride <= 65536";
     if (!row_start) return "fm_pack_rows_sparse: row_start is NULL";
     row_start[0] = 0;
@@ -289,10 +289,12 @@ const char *fm_host_pack_rows_sparse(const uint8_t *rows, const uint64_t *missin
     T = (unsigned)std::min<size_t>(std::min<unsigned>(T, 64), std::max<size_t>(1, n_rows * stride / (1u << 20)));
     const size_t per = (n_rows + T - 1) / T;
     std::vector<std::vector<uint32_t>> lists(T);
+    std::vector<std::vector<uint8_t>> gaps(T);  // col_bytes == 1: the rows' gap codes (FM gap code, ferromic_gpu.h)
     std::vector<std::vector<uint32_t>> counts(T);
     auto work = [&](unsigned t) {
         const size_t lo = std::min(n_rows, per * t), hi = std::min(n_rows, per * (t + 1));
         std::vector<uint32_t> &L = lists[t];
+        std::vector<uint8_t> &Gp = gaps[t];
         std::vector<uint32_t> &Cn = counts[t];
         Cn.resize(hi - lo);
         const size_t block = std::max<size_t>(1, (64u << 10) / (rw * 4));  // scratch called plane: ~64 KB, stays in L2
@@ -305,14 +307,28 @@ const char *fm_host_pack_rows_sparse(const uint8_t *rows, const uint64_t *missin
             for (size_t r = b0; r < b1; ++r) {
                 const uint32_t *c = cb.data() + (r - b0) * rw;
                 uint32_t n = 0;
+                int64_t prev = -1;  // gap code: last emitted (or skipped-to) column
                 for (size_t w = 0; w < rw; ++w) {
                     const size_t cells = std::min<size_t>(32, stride - w * 32);
                     uint32_t miss = ~c[w] & (cells == 32 ? 0xffffffffu : ((1u << cells) - 1u));
                     while (miss) {
                         const uint32_t bit = (uint32_t)__builtin_ctz(miss);
                         miss &= miss - 1;
-                        L.push_back((uint32_t)(w * 32 + bit));
-                        ++n;
+                        const uint32_t col = (uint32_t)(w * 32 + bit);
+                        if (col_bytes == 1) {
+                            int64_t gap = (int64_t)col - prev;  // >= 1
+                            while (gap > 255) {                 // 255: skip 255 columns, no cell
+                                Gp.push_back(255);
+                                gap -= 255;
+                                ++n;
+                            }
+                            Gp.push_back((uint8_t)(gap - 1));   // b < 255: the cell b + 1 columns further on
+                            prev = col;
+                            ++n;
+                        } else {
+                            L.push_back(col);
+                            ++n;
+                        }
                     }
                 }
                 Cn[r - lo] = n;
@@ -346,7 +362,9 @@ const char *fm_host_pack_rows_sparse(const uint8_t *rows, const uint64_t *missin
     if (acc > capacity || (acc && !missing_cols)) return "fm_pack_rows_sparse: missing_cols capacity too small (see needed)";
     auto copy = [&](unsigned t) {
         const std::vector<uint32_t> &L = lists[t];
-        if (col_bytes == 4) {
+        if (col_bytes == 1) {
+            if (!gaps[t].empty()) std::memcpy(static_cast<uint8_t *>(missing_cols) + base[t], gaps[t].data(), gaps[t].size());
+        } else if (col_bytes == 4) {
             std::memcpy(static_cast<uint32_t *>(missing_cols) + base[t], L.data(), L.size() * 4);
         } else {
             uint16_t *dst = static_cast<uint16_t *>(missing_cols) + base[t];

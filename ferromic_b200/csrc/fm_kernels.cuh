@@ -493,7 +493,7 @@ fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint
 
 // ------------------------------------------------------------------------------ sparse missing list -> called plane
 // Packed rows may arrive with a sparse list of missing cells instead of a called plane (0.15 instead of 1 bit per
-// genotype over PCIe at 1 % missing).  One warp per row rebuilds the row's called words in shared memory -- all
+// genotype over PCIe at 1 % missing; 0.09 with the one-byte gap code, ColT = uint8_t).  One warp per row rebuilds the row's called words in shared memory -- all
 // ones, the listed cells cleared -- and writes them to the resident packed matrix with coalesced stores.
 //   start[r - r_base] .. start[r - r_base + 1]: the row's slice of `cols` (indices relative to cols_base)
 template <typename ColT>
@@ -510,9 +510,28 @@ fm_k_expand_called(const uint64_t *__restrict__ start, const ColT *__restrict__ 
         for (uint32_t w = lane; w < rw; w += 32) crow[w] = (tail && w == rw - 1) ? ((1u << tail) - 1u) : 0xffffffffu;
         __syncwarp();
         const uint64_t s0 = start[v - r_base], s1 = start[v - r_base + 1];
-        for (uint64_t i = s0 + lane; i < s1; i += 32) {
-            const uint32_t c = (uint32_t)cols[i - cols_base];
-            if (c < stride) atomicAnd(crow + (c >> 5), ~(1u << (c & 31u)));
+        if (sizeof(ColT) == 1) {
+            // gap code: byte b < 255 = the missing cell b + 1 columns after the previous position, 255 = move on 255
+            // columns without a cell; positions start at -1.  Warp-wide inclusive scan of the steps, 32 bytes at a time.
+            uint32_t at = 0;  // position + 1 reached so far
+            for (uint64_t i0 = s0; i0 < s1; i0 += 32) {
+                const uint64_t i = i0 + lane;
+                const uint32_t b = i < s1 ? (uint32_t)cols[i - cols_base] : 255u;
+                uint32_t step = i < s1 ? (b == 255u ? 255u : b + 1u) : 0u;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, step, o);
+                    if ((int)lane >= o) step += up;
+                }
+                const uint32_t c = at + step - 1u;  // at + step >= 1 whenever this lane holds a cell
+                if (i < s1 && b != 255u && c < stride) atomicAnd(crow + (c >> 5), ~(1u << (c & 31u)));
+                at += __shfl_sync(0xffffffffu, step, 31);
+            }
+        } else {
+            for (uint64_t i = s0 + lane; i < s1; i += 32) {
+                const uint32_t c = (uint32_t)cols[i - cols_base];
+                if (c < stride) atomicAnd(crow + (c >> 5), ~(1u << (c & 31u)));
+            }
         }
         __syncwarp();
         uint32_t *dst = cbits + (size_t)v * rw;

@@ -134,8 +134,11 @@ fm_status fm_ingest_rows_packed(fm_ingest *h, const uint32_t *allele_bits, const
  * the columns c = sample * ploidy + side of the missing cells of every row in ascending order, as a CSR
  * list -- row_missing_start[r] .. row_missing_start[r + 1] (n_rows + 1 entries, relative to the call,
  * [0] == 0) index missing_cols, whose elements are col_bytes = 2 (row stride <= 65536) or 4 bytes wide.
- * With 1 % missing cells that is 1.17 bits per genotype over PCIe instead of 2 (and 9 for u8 + bitmap);
- * the called words are rebuilt on the device.  A parser sees the missing calls as it reads them ("./."),
+ * col_bytes = 1 is the GAP CODE of the same list: the position starts at -1 in every row; a byte b < 255
+ * moves it b + 1 columns on and names the cell it lands on, the byte 255 moves it 255 columns on without
+ * naming a cell (row_missing_start then counts bytes).  With 1 % missing cells the list costs 0.16 bits
+ * per genotype as u16 columns and 0.09 as gap codes -- 1.1 bits per genotype over PCIe in all instead of 2
+ * (and 9 for u8 + bitmap); the called words are rebuilt on the device.  A parser sees the missing calls as it reads them ("./."),
  * so this is the natural output of process.rs:2602-2660; fm_pack_rows_sparse derives it from an existing
  * u8 / int8 matrix (*needed = number of list entries; FM_ERR_INVALID_ARG when capacity is too small, with
  * *needed and row_missing_start filled in so the caller can retry). */

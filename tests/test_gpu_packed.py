@@ -162,11 +162,15 @@ def test_packed_error_behaviour():
     L.fm_matrix_release(m)
 
 
+@pytest.mark.parametrize("gap_code", [True, False])
 @pytest.mark.parametrize("n_samples,missing", [(3, 0.02), (65, 0.01), (700, 0.02), (2504, 0.01), (40000, 0.005)])
-def test_sparse_missing_list_equals_called_plane(n_samples, missing):
+def test_sparse_missing_list_equals_called_plane(n_samples, missing, gap_code, monkeypatch):
     """Packed rows whose missingness arrives as a sparse CSR list (fm_pack_rows_sparse -> fm_matrix_create_packed_sparse
-    -> fm_k_expand_called) give the counts of the called-plane form, of the u8 path and of the oracle."""
+    -> fm_k_expand_called), as column indices or as the one-byte gap code, give the counts of the called-plane form,
+    of the u8 path and of the oracle."""
+    from ferromic_b200 import api
     from ferromic_b200.api import _Matrix
+    monkeypatch.setattr(api, "SPARSE_GAP_CODE", gap_code)
     V = 2500 if n_samples < 1000 else (500 if n_samples < 10000 else 40)
     g, pos, _ = make_cohort(V, n_samples, missing_rate=missing, seed=900 + n_samples)
     g[7] = -1  # a row without any call
@@ -183,9 +187,12 @@ def test_sparse_missing_list_equals_called_plane(n_samples, missing):
         _same_summary(got, u8.group(haps).summary(want_arrays=True))
 
 
+@pytest.mark.parametrize("gap_code", [True, False])
 @pytest.mark.parametrize("calls", [1, 4])
-def test_sparse_missing_streaming_ingest(calls):
+def test_sparse_missing_streaming_ingest(calls, gap_code, monkeypatch):
+    from ferromic_b200 import api
     from ferromic_b200.api import _Matrix
+    monkeypatch.setattr(api, "SPARSE_GAP_CODE", gap_code)
     g, pos, pops = make_cohort(1800, 45, n_pops=3, missing_rate=0.02, seed=55 + calls)
     miss = g < 0
     alle = np.where(miss, 0, g).astype(np.uint8)

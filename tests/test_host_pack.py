@@ -118,6 +118,48 @@ def test_pack_rows_sparse_matches_the_dense_packer(stride, mode):
             assert np.array_equal(cols[int(start[r]):int(start[r + 1])].astype(np.int64), want)
 
 
+def _decode_gap_code(b):
+    """One row of the one-byte gap code (include/ferromic_gpu.h): the ascending columns it lists."""
+    out, at = [], -1
+    for x in b.tolist():
+        if x == 255:
+            at += 255
+        else:
+            at += x + 1
+            out.append(at)
+    return np.asarray(out, dtype=np.int64)
+
+
+@pytest.mark.parametrize("stride", [1, 33, 700, 5008, 70000])
+@pytest.mark.parametrize("mode", [1, 2])
+def test_pack_rows_sparse_gap_code(stride, mode):
+    """col_bytes == 1: every row's bytes decode to exactly the missing columns (gaps above 255 take escape bytes)."""
+    rng = np.random.default_rng(77 * stride + mode)
+    rows = 37 if stride < 10000 else 5
+    cells = (rng.random((rows, stride)) < 0.4).astype(np.uint8)
+    miss = rng.random(cells.shape) < (0.002 if stride > 600 else 0.05)   # wide rows: mostly gaps > 255
+    miss[rows // 2] = True               # a row that is missing altogether (all gaps are 1)
+    miss[0] = False                      # one without any missing cell
+    miss[1] = False
+    miss[1, stride - 1] = True           # a single cell at the far end: only escapes before it
+    bitmap, src = None, cells
+    if mode == 1:
+        bitmap = _pack_bits(miss.reshape(-1).astype(np.uint8))
+    else:
+        src = cells.copy()
+        src[miss] = 0xFF
+    dense_a, _ = pack_rows(src, mode, bitmap)
+    for threads in (1, 4):
+        ab, start, code = pack_rows_sparse(src, mode, bitmap, threads=threads, gap_code=True)
+        assert code.dtype == np.uint8 and np.array_equal(ab, dense_a)
+        assert start[0] == 0 and int(start[-1]) == len(code)
+        for r in range(rows):
+            got = _decode_gap_code(code[int(start[r]):int(start[r + 1])])
+            assert np.array_equal(got, np.nonzero(miss[r])[0])
+        n_escape = int((code == 255).sum())
+        assert len(code) == int(miss.sum()) + n_escape
+
+
 def test_pack_rows_sparse_chunk_and_capacity():
     from ferromic_b200 import _lib
     L = _lib.lib()
