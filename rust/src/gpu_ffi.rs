@@ -212,6 +212,14 @@ impl PackedIngest {
         check(unsafe { fm_ingest_rows_packed_sparse(self.h, allele_bits.as_ptr(), row_start.as_ptr(),
                                                     missing_cols.as_ptr() as *const _, 2, first_row, n_rows) })
     }
+    /// The same list as one-byte gap codes (col_bytes = 1, include/ferromic_gpu.h): per row the position starts at
+    /// -1; a byte b < 255 moves it b + 1 columns on and names that cell, 255 moves it 255 columns on without a cell.
+    /// `row_start` counts bytes.
+    pub fn push_gaps(&mut self, first_row: usize, n_rows: usize, allele_bits: &[u32], row_start: &[u64],
+                     gap_codes: &[u8]) -> Result<(), VcfError> {
+        check(unsafe { fm_ingest_rows_packed_sparse(self.h, allele_bits.as_ptr(), row_start.as_ptr(),
+                                                    gap_codes.as_ptr() as *const _, 1, first_row, n_rows) })
+    }
     pub fn finish(self) -> Result<(Arc<GpuMatrix>, Vec<GpuGroup>), VcfError> {
         let mut m = ptr::null_mut();
         let mut gs = vec![ptr::null_mut(); self.n_groups.max(1)];
