@@ -337,10 +337,11 @@ def _to_python_variants(g, pos):
             for p, site in zip(pos, g)]
 
 
-@pytest.mark.parametrize("n_pops,missing", [(2, 0.0), (2, 0.3), (5, 0.15), (26, 0.02)])
+@pytest.mark.parametrize("n_pops,missing", [(2, 0.0), (2, 0.3), (5, 0.15), (26, 0.02), (40, 0.05)])
 def test_wc_fst_matches_oracle(n_pops, missing):
+    # 40 populations = 780 pairs: three chunks of the pairs kernel's 352 pair slots per segment
     F = fm()
-    S = 60 if n_pops < 26 else 130
+    S = 60 if n_pops < 26 else (130 if n_pops == 26 else 170)
     V = 900 if n_pops < 26 else 300
     g, pos, pops = make_cohort(V, S, n_pops=n_pops, sigma=0.08, missing_rate=missing, seed=100 + n_pops)
     g[:, :, 1][g[:, :, 0] < 0] = -1
