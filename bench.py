@@ -596,6 +596,7 @@ def run_ours(args):
         out_pi = torch.empty((2, V), dtype=torch.float64, pin_memory=True).numpy()
         out_th = torch.empty((2, V), dtype=torch.float64, pin_memory=True).numpy()
         raw_n = (C.c_size_t * 2)(len(g0), len(g1))
+        gidx2 = np.array([0, 1], dtype=np.uint64)
 
         def e2e_step(mode, phases, src=None):
             t = [time.perf_counter()]
@@ -608,8 +609,14 @@ def run_ours(args):
             _lib.check(L.fm_ingest_begin(V, S, 2, 1, 1, pos.ctypes.data, 0, C.byref(ih)))
             for idx, side in garrs:
                 _lib.check(L.fm_ingest_add_group(ih, idx.ctypes.data, side.ctypes.data, len(idx), None))
+            streamed = mode == "packed_gaps_streamed"
+            n = C.c_size_t()
+            if streamed:  # the tracks are requested up front and stream out while the rows stream in
+                _lib.check(L.fm_ingest_request_tracks(ih, gidx2.ctypes.data, raw_n, 2, int(pos[0]), int(pos[-1]),
+                                                      mask.ctypes.data, mask.size // 2, None, 0, out_pos.ctypes.data,
+                                                      out_pi.ctypes.data, out_th.ctypes.data, V, C.byref(n)))
             lap("begin+declare_groups")
-            if mode == "packed_gaps":  # allele bits + gap-coded missing list; called words rebuilt on the device
+            if mode in ("packed_gaps", "packed_gaps_streamed"):  # allele bits + gap-coded missing list
                 _lib.check(L.fm_ingest_rows_packed_sparse(ih, h_ab2.data_ptr(), h_startg.data_ptr(), h_gaps.data_ptr(), 1, 0, V))
             elif mode == "packed_sparse":  # the same with u16 column indices
                 _lib.check(L.fm_ingest_rows_packed_sparse(ih, h_ab2.data_ptr(), h_start.data_ptr(), h_cols.data_ptr(), 2, 0, V))
@@ -626,10 +633,10 @@ def run_ours(args):
             gh = (C.c_void_p * 2)()
             _lib.check(L.fm_ingest_finish(ih, C.byref(mh), gh, None))
             lap("finish")
-            n = C.c_size_t()
-            _lib.check(L.fm_per_site_diversity_multi(gh, raw_n, 2, int(pos[0]), int(pos[-1]), mask.ctypes.data,
-                                                     mask.size // 2, None, 0, out_pos.ctypes.data, out_pi.ctypes.data,
-                                                     out_th.ctypes.data, V, C.byref(n)))
+            if not streamed:
+                _lib.check(L.fm_per_site_diversity_multi(gh, raw_n, 2, int(pos[0]), int(pos[-1]), mask.ctypes.data,
+                                                         mask.size // 2, None, 0, out_pos.ctypes.data, out_pi.ctypes.data,
+                                                         out_th.ctypes.data, V, C.byref(n)))
             lap("per_site_diversity_multi")
             for g in gh:
                 L.fm_group_release(C.c_void_p(g))
@@ -661,8 +668,20 @@ def run_ours(args):
                     "host_phase_ms_per_step": {k_: v_ / k for k_, v_ in phases.items()}}
 
         k = max(1, min(args.steps, args.e2e_steps))
-        r_sparse = timed("packed_gaps", k)
+        r_two = timed("packed_gaps", k)
         check_pi = out_pi.copy()
+        check_th, check_pos = out_th.copy(), out_pos.copy()
+        out_pi[:] = -1.0
+        out_th[:] = -1.0
+        out_pos[:] = -1
+        r_sparse = timed("packed_gaps_streamed", k)
+        same_streamed = bool(np.array_equal(out_pos, check_pos) and
+                             np.array_equal(np.isnan(check_pi), np.isnan(out_pi)) and
+                             np.array_equal(check_pi[~np.isnan(check_pi)], out_pi[~np.isnan(out_pi)]) and
+                             np.array_equal(np.isnan(check_th), np.isnan(out_th)) and
+                             np.array_equal(check_th[~np.isnan(check_th)], out_th[~np.isnan(out_th)]))
+        if not same_streamed:
+            raise RuntimeError("parity: the streamed tracks differ from fm_per_site_diversity_multi after finish")
         r_cols = timed("packed_sparse", k)
         same_cols = bool(np.array_equal(np.isnan(check_pi), np.isnan(out_pi)) and
                          np.array_equal(check_pi[~np.isnan(check_pi)], out_pi[~np.isnan(out_pi)]))
@@ -692,15 +711,18 @@ def run_ours(args):
                "d2h_bytes_per_step": int(2 * 2 * V * 8 + V * 8), "steps": k, "ms_per_step": r_sparse["ms_per_step"],
                "breakdown_ms_per_step": r_sparse["breakdown_ms_per_step"],
                "host_phase_ms_per_step": r_sparse["host_phase_ms_per_step"],
-               "api": "fm_ingest_begin / add_group x2 / fm_ingest_rows_packed_sparse (allele bit words + gap-coded missing list "
-                      "from pinned host memory; chunked H2D overlapped with fm_k_expand_called + the compress pass K1p) / "
-                      "finish + fm_per_site_diversity_multi (one fused launch; the pi / theta tracks and the positions are stored by the "
-                      "kernels straight into the caller's page-locked arrays over PCIe, so `stats` in the breakdown includes the "
-                      "device-to-host traffic and `d2h` is ~0); per rank",
+               "api": "fm_ingest_begin / add_group x2 / fm_ingest_request_tracks / fm_ingest_rows_packed_sparse (allele bit words "
+                      "+ gap-coded missing list from pinned host memory; chunked H2D overlapped with fm_k_expand_called, the "
+                      "compress pass K1p and the per-site pass of every chunk, whose pi / theta tracks and positions the kernels "
+                      "store straight into the caller's page-locked arrays over PCIe while the next chunks upload) / finish; per "
+                      "rank.  `two_calls` is the same ingest followed by fm_per_site_diversity_multi after finish",
                "input": "packed rows: one allele bit per genotype + the missing cells of every row as one-byte gap codes "
                         "(CSR, col_bytes = 1), as a parser emits them (include/ferromic_gpu.h); %d missing cells = %.2f %% of "
                         "the matrix in %d bytes" % (n_missing, 100.0 * n_missing / (V * stride), n_gap_bytes),
                "bits_per_genotype_over_pcie": 8.0 * h2d_sparse / (V * stride),
+               "two_calls": {**r_two, "h2d_bytes_per_step": h2d_sparse,
+                             "what": "ingest (gap-coded list), finish, then ONE fm_per_site_diversity_multi call for both groups "
+                                     "(tracks stored by the kernel into the page-locked arrays)"},
                "packed_u16_columns": {**r_cols, "h2d_bytes_per_step": h2d_cols,
                                       "what": "the same ingest with the missing list as u16 column indices (col_bytes = 2)"},
                "packed_called_plane": {**r_packed, "h2d_bytes_per_step": h2d_packed,

@@ -65,7 +65,7 @@ EXPORTS = [
     "fm_matrix_create", "fm_matrix_create_inband", "fm_matrix_create_device", "fm_matrix_retain", "fm_matrix_release",
     "fm_matrix_info", "fm_ingest_begin", "fm_ingest_add_group", "fm_ingest_add_partition",
     "fm_ingest_rows", "fm_ingest_finish", "fm_ingest_abort", "fm_packed_row_words", "fm_ingest_rows_packed",
-    "fm_matrix_create_packed", "fm_pack_rows", "fm_pack_rows_generic", "fm_ingest_rows_pack", "fm_pack_rows_sparse", "fm_ingest_rows_packed_sparse",
+    "fm_matrix_create_packed", "fm_pack_rows", "fm_pack_rows_generic", "fm_ingest_rows_pack", "fm_pack_rows_sparse", "fm_ingest_rows_packed_sparse", "fm_ingest_request_tracks",
     "fm_matrix_create_packed_sparse", "fm_group_create", "fm_groups_create", "fm_group_release", "fm_group_capacity", "fm_group_summary", "fm_groups_summary_batch",
     "fm_group_segregating_sites", "fm_group_pi", "fm_harmonic", "fm_watterson_theta",
     "fm_per_site_diversity", "fm_per_site_diversity_multi", "fm_hudson_pair", "fm_hudson_dxy", "fm_partition_create",
@@ -115,6 +115,7 @@ def lib() -> C.CDLL:
     L.fm_ingest_rows.argtypes = [vp, vp, vp, sz, sz]
     L.fm_packed_row_words.argtypes = [sz, sz, C.POINTER(sz)]
     L.fm_ingest_rows_packed.argtypes = [vp, vp, vp, sz, sz]
+    L.fm_ingest_request_tracks.argtypes = [vp, vp, vp, sz, i64, i64, vp, sz, vp, sz, vp, vp, vp, sz, C.POINTER(sz)]
     L.fm_pack_rows_sparse.argtypes = [vp, vp, C.c_int, sz, sz, sz, sz, vp, vp, vp, sz, C.c_int, C.c_int, C.POINTER(sz)]
     L.fm_ingest_rows_packed_sparse.argtypes = [vp, vp, vp, vp, C.c_int, sz, sz]
     L.fm_matrix_create_packed_sparse.argtypes = [vp, vp, vp, C.c_int, sz, sz, sz, vp, C.POINTER(vp)]

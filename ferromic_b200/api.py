@@ -271,11 +271,16 @@ class _Matrix:
     @classmethod
     def ingest(cls, alleles: np.ndarray, missing_mask: Optional[np.ndarray], positions: np.ndarray,
                group_haplotypes: Sequence[Sequence[Tuple[int, int]]], partitions=(), chunk_rows: int = 0,
-               calls: int = 1, always_bitmap: bool = False, packed: bool = False, sparse: bool = False) -> "_Matrix":
+               calls: int = 1, always_bitmap: bool = False, packed: bool = False, sparse: bool = False,
+               tracks: Optional[dict] = None) -> "_Matrix":
         """Streaming ingestion (fm_ingest_*): the u8 rows are uploaded in chunks and repacked into
         the declared groups' bitplanes while the next chunk is in flight; the u8 matrix is never
         resident.  partitions: (left, right, n_groups) triples; their handles land in
-        `self.partitions`.  calls > 1 pushes the rows in several fm_ingest_rows calls."""
+        `self.partitions`.  calls > 1 pushes the rows in several fm_ingest_rows calls.
+        tracks: per-site pi / theta of declared groups computed while the rows arrive (fm_ingest_request_tracks):
+        {"groups": [indices], "raw_n": [...], "region": (start, end), "mask": int64 [k, 2] or None,
+        "filtered": int64 [m] or None, "pos": int64 [cap], "pi": f64 [n_groups, cap], "theta": f64 [n_groups, cap]}
+        (arrays or raw addresses); the number of sites lands in `self.track_sites`."""
         a = np.ascontiguousarray(alleles, dtype=np.uint8)
         assert a.ndim == 3
         self = cls.__new__(cls)
@@ -302,6 +307,23 @@ class _Matrix:
                 lft = np.ascontiguousarray(left, dtype=np.uint16)
                 rgt = np.ascontiguousarray(right, dtype=np.uint16)
                 check(L.fm_ingest_add_partition(ih, _ptr(lft), _ptr(rgt), len(lft), ng, None))
+            self.track_sites = None
+            if tracks is not None:
+                def addr(x):
+                    return x if (x is None or isinstance(x, int)) else x.ctypes.data
+                gi = np.ascontiguousarray(tracks["groups"], dtype=np.uint64)
+                rn = np.ascontiguousarray(tracks["raw_n"], dtype=np.uint64)
+                mk = tracks.get("mask")
+                mk = None if mk is None else np.ascontiguousarray(mk, dtype=np.int64).reshape(-1)
+                fl = tracks.get("filtered")
+                fl = None if fl is None else np.ascontiguousarray(fl, dtype=np.int64)
+                n = C.c_size_t()
+                check(L.fm_ingest_request_tracks(ih, _ptr(gi), _ptr(rn), len(gi), int(tracks["region"][0]),
+                                                 int(tracks["region"][1]), _ptr(mk), 0 if mk is None else mk.size // 2,
+                                                 _ptr(fl), 0 if fl is None else fl.size, addr(tracks.get("pos")),
+                                                 addr(tracks["pi"]), addr(tracks["theta"]), int(tracks["capacity"]),
+                                                 C.byref(n)))
+                self.track_sites = n.value
             flat = a.reshape(self.V, -1)
             cuts = np.linspace(0, self.V, max(1, calls) + 1).astype(int)
             for r0, r1 in zip(cuts[:-1], cuts[1:]):

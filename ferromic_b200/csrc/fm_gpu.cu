@@ -158,7 +158,15 @@ void require_device() {
     }
 }
 
-cudaStream_t stream() { return cudaStreamPerThread; }
+// The calling thread's stream.  A scope may redirect it (StreamScope): the streaming ingest runs the per-site pass
+// of a chunk on its own compute stream with the very code of the public call.
+thread_local cudaStream_t t_stream_override = nullptr;
+cudaStream_t stream() { return t_stream_override ? t_stream_override : cudaStreamPerThread; }
+struct StreamScope {
+    cudaStream_t saved;
+    explicit StreamScope(cudaStream_t s) : saved(t_stream_override) { t_stream_override = s; }
+    ~StreamScope() { t_stream_override = saved; }
+};
 
 uint32_t env_u32_early(const char *name, uint32_t dflt) {
     const char *v = getenv(name);
@@ -2532,8 +2540,29 @@ fm_status fm_per_site_diversity_multi(fm_group *const *groups, const size_t *raw
 // repacked straight into the bitplanes of every declared group while the next chunk is still
 // on the PCIe bus.  The u8 rows are never resident (1.125 B/genotype of HBM and the separate
 // repack pass are saved).
+// Per-site pi / theta tracks requested for the matrix being ingested (fm_ingest_request_tracks): every chunk's
+// tracks are computed right after its repack and stored while the next chunks are still on the bus.
+struct IngestTracks {
+    std::vector<fm_group *> act;        // groups with >= 2 listed haplotypes
+    std::vector<size_t> act_idx;        // their row in the caller's arrays
+    std::vector<size_t> nan_rows;       // rows of groups with < 2 listed haplotypes: NaN (stats.rs:4675-4681)
+    uint32_t lo = 0, hi = 0;            // site range of the region
+    size_t capacity = 0;
+    DevBuf<int64_t> d_mask, d_filt;
+    uint32_t n_mask = 0, n_filt = 0;
+    bool has_mask = false;
+    std::vector<double *> ppi, pth;     // device-visible destinations (the caller's page-locked rows or own buffers)
+    std::vector<DevBuf<double>> own_pi, own_th;
+    std::vector<char> direct;
+    int64_t *pos_out = nullptr, *pos_direct = nullptr;
+    double *pi_out = nullptr, *theta_out = nullptr;
+    bool pos_done = false;
+};
+
 struct fm_ingest {
     fm_matrix *m = nullptr;
+    std::unique_ptr<IngestTracks> tracks;
+    cudaEvent_t pos_up = nullptr;         // the positions are on the device (recorded on copy_s)
     std::vector<fm_group *> groups;       // declared with fm_ingest_add_group (owned until finish)
     std::vector<fm_partition *> parts;    // declared with fm_ingest_add_partition
     std::vector<fm_group *> all;          // every group that receives rows
@@ -2564,6 +2593,41 @@ static void ingest_early_setup(fm_ingest *h) {
     fm_matrix *m = h->m;
     if (m->V) CK(cudaMemcpyAsync(m->d_pos, m->pos.data(), m->V * 8, cudaMemcpyHostToDevice, h->copy_s));
     h->pos_uploaded = true;
+    if (h->tracks) {  // the track kernels read the positions (mask lookup, positions + 1)
+        if (!h->pos_up) CK(cudaEventCreateWithFlags(&h->pos_up, cudaEventDisableTiming));
+        CK(cudaEventRecord(h->pos_up, h->copy_s));
+        CK(cudaStreamWaitEvent(h->comp_s, h->pos_up, 0));
+    }
+}
+
+// Tracks of the freshly repacked rows [r0, r1) on the ingest's compute stream (after launch_repack).
+static void ingest_tracks_chunk(fm_ingest *h, size_t r0, size_t r1) {
+    IngestTracks *T = h->tracks.get();
+    if (!T || T->act.empty()) return;
+    const uint32_t lo = (uint32_t)std::max<size_t>(r0, T->lo), hi = (uint32_t)std::min<size_t>(r1, T->hi);
+    if (lo >= hi) return;
+    fm_matrix *m = h->m;
+    if (!h->pos_uploaded) {  // pageable positions (small matrices): put them on the device now, ordered before the pass
+        if (m->V) CK(cudaMemcpyAsync(m->d_pos, m->pos.data(), m->V * 8, cudaMemcpyHostToDevice, h->comp_s));
+        h->pos_uploaded = true;
+    }
+    StreamScope on_comp(h->comp_s);
+    if (!T->pos_done && T->pos_direct) {
+        const size_t n = T->hi - T->lo;
+        fm_k_pos_plus1<<<(uint32_t)std::min<size_t>((n + 255) / 256, 2048), 256, 0, h->comp_s>>>(m->d_pos, T->lo, (uint32_t)n,
+                                                                                                    T->pos_direct);
+        CK(cudaGetLastError());
+        g_launches++;
+        T->pos_done = true;
+    }
+    std::vector<double *> ppi(T->act.size()), pth(T->act.size());
+    for (size_t i = 0; i < T->act.size(); ++i) {
+        ppi[i] = T->ppi[i] + (lo - T->lo);
+        pth[i] = T->pth[i] + (lo - T->lo);
+    }
+    run_diversity_multi(T->act.data(), T->act.size(), lo, hi, FM_PIFORM_COMPONENTS, ppi.data(), pth.data(),
+                        T->has_mask ? T->d_mask.p : nullptr, T->n_mask, T->n_filt ? T->d_filt.p : nullptr, T->n_filt,
+                        /*out=*/nullptr);
 }
 
 static void ingest_late_setup(fm_ingest *h) {
@@ -2586,7 +2650,7 @@ static void ingest_destroy(fm_ingest *h, bool release_handles) {
         if (h->copied[i]) cudaEventDestroy(h->copied[i]);
         if (h->consumed[i]) cudaEventDestroy(h->consumed[i]);
     }
-    for (cudaEvent_t e : {h->t_copy0, h->t_copy1, h->t_comp0, h->t_comp1, h->pin_free[0], h->pin_free[1]})
+    for (cudaEvent_t e : {h->t_copy0, h->t_copy1, h->t_comp0, h->t_comp1, h->pin_free[0], h->pin_free[1], h->pos_up})
         if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) g_pinned.give(h->pin[i]);  // the copy stream was synchronised above
     if (h->copy_s) cudaStreamDestroy(h->copy_s);
@@ -2681,6 +2745,94 @@ fm_status fm_ingest_add_partition(fm_ingest *h, const uint16_t *left, const uint
     });
 }
 
+fm_status fm_ingest_request_tracks(fm_ingest *h, const size_t *group_index, const size_t *raw_n, size_t n_groups,
+                                   int64_t rs, int64_t re, const int64_t *mask_iv, size_t n_mask, const int64_t *filtered,
+                                   size_t n_filt, int64_t *pos_out, double *pi_out, double *theta_out, size_t capacity,
+                                   size_t *n_out) {
+    return guarded([&] {
+        if (!h || !group_index || !raw_n || !n_groups || !n_out) fail(FM_ERR_INVALID_ARG, "NULL argument");
+        *n_out = 0;
+        if (h->rows_done) fail(FM_ERR_INVALID_ARG, "tracks must be requested before the first rows call");
+        if (h->tracks) fail(FM_ERR_INVALID_ARG, "tracks were already requested for this ingest");
+        fm_matrix *m = h->m;
+        set_dev(m);
+        auto T = std::make_unique<IngestTracks>();
+        for (size_t i = 0; i < n_groups; ++i) {
+            if (group_index[i] >= h->groups.size()) fail(FM_ERR_INVALID_ARG, "group index out of range");
+            fm_group *g = h->groups[group_index[i]];
+            if (g->n_bits != 1 || g->count_only)
+                fail(FM_ERR_UNSUPPORTED, "streamed tracks need biallelic bitplane groups (use fm_per_site_diversity after finish)");
+            if (raw_n[i] >= 2) {
+                T->act.push_back(g);
+                T->act_idx.push_back(i);
+            } else {
+                T->nan_rows.push_back(i);
+            }
+        }
+        if (region_len(rs, re) <= 0) {  // stats.rs:4656-4666: no sites; nothing to compute while the rows arrive
+            h->tracks = std::move(T);
+            h->tracks->act.clear();
+            h->tracks->nan_rows.clear();
+            return;
+        }
+        uint32_t lo, hi;
+        site_range(m, rs, re, lo, hi);
+        const size_t n = hi - lo;
+        T->lo = lo;
+        T->hi = hi;
+        T->capacity = capacity;
+        T->pos_out = pos_out;
+        T->pi_out = pi_out;
+        T->theta_out = theta_out;
+        if (n) {
+            if (n > capacity) fail(FM_ERR_INVALID_ARG, "output capacity too small");
+            if (!pi_out || !theta_out) fail(FM_ERR_INVALID_ARG, "output arrays are NULL");
+            std::vector<int64_t> merged, fs;
+            if (mask_iv) {
+                merge_intervals(mask_iv, n_mask, merged);
+                T->d_mask.alloc(std::max<size_t>(merged.size(), 2));
+                T->d_mask.upload(merged.data(), merged.size());
+                T->n_mask = (uint32_t)(merged.size() / 2);
+                T->has_mask = true;
+            }
+            if (filtered && n_filt) {
+                fs.assign(filtered, filtered + n_filt);
+                std::sort(fs.begin(), fs.end());
+                T->d_filt.alloc(fs.size());
+                T->d_filt.upload(fs.data(), fs.size());
+                T->n_filt = (uint32_t)fs.size();
+            }
+            const size_t na = T->act.size();
+            T->ppi.resize(na);
+            T->pth.resize(na);
+            T->own_pi = std::vector<DevBuf<double>>(na);
+            T->own_th = std::vector<DevBuf<double>>(na);
+            T->direct.assign(na, 0);
+            for (size_t i = 0; i < na; ++i) {
+                double *mp = static_cast<double *>(mapped_host_range(pi_out + T->act_idx[i] * capacity, n * 8));
+                double *mt = static_cast<double *>(mapped_host_range(theta_out + T->act_idx[i] * capacity, n * 8));
+                if (mp && mt) {
+                    T->direct[i] = 1;
+                    T->ppi[i] = mp;
+                    T->pth[i] = mt;
+                } else {
+                    T->own_pi[i].alloc(n);
+                    T->own_th[i].alloc(n);
+                    T->ppi[i] = T->own_pi[i].p;
+                    T->pth[i] = T->own_th[i].p;
+                }
+            }
+            if (pos_out) T->pos_direct = static_cast<int64_t *>(mapped_host_range(pos_out, n * 8));
+            CK(cudaStreamSynchronize(stream()));  // the interval lists are host temporaries; buffers usable on comp_s
+        } else {
+            T->act.clear();
+            T->nan_rows.clear();
+        }
+        *n_out = n;
+        h->tracks = std::move(T);
+    });
+}
+
 fm_status fm_ingest_rows(fm_ingest *h, const uint8_t *rows, const uint64_t *missing_whole, size_t first_row,
                          size_t n_rows) {
     return guarded([&] {
@@ -2725,6 +2877,7 @@ fm_status fm_ingest_rows(fm_ingest *h, const uint8_t *rows, const uint64_t *miss
             CK(cudaStreamWaitEvent(h->comp_s, h->copied[b], 0));
             launch_repack(h->set, h->stage[b], (r1 - r0) * stride, bitmap ? h->stage_m[b] : nullptr,
                           (uint32_t)r0, w0, (uint32_t)r0, (uint32_t)r1, h->comp_s);
+            ingest_tracks_chunk(h, r0, r1);
             CK(cudaEventRecord(h->consumed[b], h->comp_s));
             h->used[b] = true;
         }
@@ -2818,6 +2971,7 @@ fm_status fm_ingest_rows_packed(fm_ingest *h, const uint32_t *allele_bits, const
             CK(cudaEventRecord(h->copied[b], h->copy_s));
             CK(cudaStreamWaitEvent(h->comp_s, h->copied[b], 0));
             launch_repack(h->set, nullptr, 0, nullptr, 0, 0, (uint32_t)r0, (uint32_t)r1, h->comp_s);
+            ingest_tracks_chunk(h, r0, r1);
         }
         h->rows_done += n_rows;
         CK(cudaEventRecord(h->t_copy1, h->copy_s));
@@ -2872,7 +3026,7 @@ static void expand_called_launch(fm_matrix *m, const uint64_t *d_start, const vo
 
 static void packed_sparse_rows(fm_matrix *m, const RepackSet *set, const uint32_t *allele_bits, const uint64_t *row_start,
                                const void *missing_cols, int col_bytes, size_t first_row, size_t n_rows, cudaStream_t copy_s,
-                               cudaStream_t comp_s, cudaEvent_t ev[2]) {
+                               cudaStream_t comp_s, cudaEvent_t ev[2], fm_ingest *tracks_of = nullptr) {
     if (col_bytes != 1 && col_bytes != 2 && col_bytes != 4) fail(FM_ERR_INVALID_ARG, "col_bytes must be 1 (gap code), 2 or 4");
     if (col_bytes == 2 && m->stride > 65536) fail(FM_ERR_INVALID_ARG, "16-bit columns need a row stride <= 65536");
     if (n_rows && !row_start) fail(FM_ERR_INVALID_ARG, "row_start is NULL");
@@ -2900,6 +3054,7 @@ static void packed_sparse_rows(fm_matrix *m, const RepackSet *set, const uint32_
         expand_called_launch(m, d_start.p, d_cols.p, col_bytes, 0, (uint32_t)first_row, (uint32_t)(first_row + r0),
                              (uint32_t)(first_row + r1), comp_s);
         if (set) launch_repack(*set, nullptr, 0, nullptr, 0, 0, (uint32_t)(first_row + r0), (uint32_t)(first_row + r1), comp_s);
+        if (tracks_of) ingest_tracks_chunk(tracks_of, first_row + r0, first_row + r1);
     }
     // the scratch lists go back to the allocator ordered after the last kernel that reads them
     CK(cudaEventRecord(ev[b], comp_s));
@@ -2949,7 +3104,7 @@ fm_status fm_ingest_rows_packed_sparse(fm_ingest *h, const uint32_t *allele_bits
             h->timing_started = true;
         }
         packed_sparse_rows(m, h->all.empty() ? nullptr : &h->set, allele_bits, row_missing_start, missing_cols, col_bytes,
-                           first_row, n_rows, h->copy_s, h->comp_s, h->copied);
+                           first_row, n_rows, h->copy_s, h->comp_s, h->copied, h);
         mark("queued");
         h->rows_done += n_rows;
         CK(cudaEventRecord(h->t_copy1, h->copy_s));
@@ -3053,6 +3208,7 @@ fm_status fm_ingest_rows_pack(fm_ingest *h, const uint8_t *rows, const uint64_t 
             h->pin_used[b] = true;
             CK(cudaStreamWaitEvent(h->comp_s, h->pin_free[b], 0));
             launch_repack(h->set, nullptr, 0, nullptr, 0, 0, (uint32_t)r0, (uint32_t)r1, h->comp_s);
+            ingest_tracks_chunk(h, r0, r1);
         }
         h->rows_done += n_rows;
         CK(cudaEventRecord(h->t_copy1, h->copy_s));
@@ -3103,6 +3259,22 @@ fm_status fm_ingest_finish(fm_ingest *h, fm_matrix **matrix_out, fm_group **grou
         set_dev(h->m);
         ingest_late_setup(h);
         CK(cudaStreamSynchronize(h->comp_s));
+        if (IngestTracks *T = h->tracks.get()) {  // requested tracks: everything was computed as the rows arrived
+            const size_t n = T->hi - T->lo;
+            DevBuf<int64_t> d_p1;
+            if (n) {
+                for (size_t i = 0; i < T->act.size(); ++i)
+                    if (!T->direct[i]) {  // pageable output rows: copy them out now
+                        T->own_pi[i].download(T->pi_out + T->act_idx[i] * T->capacity, n);
+                        T->own_th[i].download(T->theta_out + T->act_idx[i] * T->capacity, n);
+                    }
+                if (!T->pos_done) download_positions_plus1(h->m, T->lo, n, T->pos_out, d_p1);  // stats.rs:4746
+                CK(cudaStreamSynchronize(stream()));
+                const double NaN = std::numeric_limits<double>::quiet_NaN();
+                for (size_t row : T->nan_rows)
+                    for (size_t k = 0; k < n; ++k) T->pi_out[row * T->capacity + k] = T->theta_out[row * T->capacity + k] = NaN;
+            }
+        }
         if (h->timing_started) {
             float a = 0.f, b = 0.f;
             CK(cudaEventElapsedTime(&a, h->t_copy0, h->t_copy1));

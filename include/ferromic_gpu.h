@@ -111,6 +111,20 @@ fm_status fm_ingest_add_partition(fm_ingest *h, const uint16_t *left, const uint
                                   size_t n_samples, size_t n_groups, size_t *partition_index);
 fm_status fm_ingest_rows(fm_ingest *h, const uint8_t *rows, const uint64_t *missing_whole_or_null,
                          size_t first_row, size_t n_rows);
+/* Per-site tracks WHILE the rows arrive (calculate_per_site_diversity, stats.rs:4628-4806, for groups declared
+ * with fm_ingest_add_group): same arguments, output layout and NaN rules as fm_per_site_diversity_multi, with
+ * group_index[] naming declared groups.  Must be called after the groups are declared and before the first
+ * rows call; *n_out (the number of sites in the region) is known at once, the arrays are complete when
+ * fm_ingest_finish returns.  Every chunk's tracks are computed right after its repack on the ingest's compute
+ * stream; page-locked output arrays receive them over PCIe while the following chunks are still being uploaded
+ * (the two directions of the link do not compete), pageable ones are copied out in fm_ingest_finish.  The
+ * caller's arrays must stay valid until then.  Biallelic bitplane groups only. */
+fm_status fm_ingest_request_tracks(fm_ingest *h, const size_t *group_index, const size_t *raw_haplotype_counts,
+                                   size_t n_groups, int64_t region_start, int64_t region_end,
+                                   const int64_t *mask_intervals_or_null, size_t n_mask,
+                                   const int64_t *filtered_positions_or_null, size_t n_filtered,
+                                   int64_t *pos_out_or_null, double *pi_out, double *theta_out, size_t capacity,
+                                   size_t *n_out);
 /* ---- packed rows: 2 bits per genotype instead of 9 over PCIe ("skip the u8 matrix") ----
  * Row v of the cohort as row_words = ceil(n_samples * ploidy / 32) u32 words of ALLELE bits followed
  * (in a second array) by row_words words of CALLED bits: bit (c & 31) of word (c >> 5) describes cell

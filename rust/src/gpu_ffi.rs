@@ -171,6 +171,11 @@ extern "C" {
                                n_rows: usize, n_threads: c_int) -> c_int;
     pub fn fm_ingest_rows_packed(h: *mut fm_ingest, allele_bits: *const u32, called_bits: *const u32, first_row: usize,
                                  n_rows: usize) -> c_int;
+    pub fn fm_ingest_request_tracks(h: *mut fm_ingest, group_index: *const usize, raw_haplotype_counts: *const usize,
+                                    n_groups: usize, region_start: i64, region_end: i64, mask_intervals: *const i64,
+                                    n_mask: usize, filtered_positions: *const i64, n_filtered: usize,
+                                    pos_out: *mut i64, pi_out: *mut f64, theta_out: *mut f64, capacity: usize,
+                                    n_out: *mut usize) -> c_int;
     pub fn fm_ingest_rows_packed_sparse(h: *mut fm_ingest, allele_bits: *const u32, row_missing_start: *const u64,
                                         missing_cols: *const core::ffi::c_void, col_bytes: c_int, first_row: usize,
                                         n_rows: usize) -> c_int;
