@@ -2630,6 +2630,8 @@ static void ingest_tracks_chunk(fm_ingest *h, size_t r0, size_t r1) {
                         /*out=*/nullptr);
 }
 
+static size_t tapered_chunk(size_t rows_left, size_t chunk);
+
 static void ingest_late_setup(fm_ingest *h) {
     if (h->pos_uploaded) return;
     fm_matrix *m = h->m;
@@ -2959,8 +2961,9 @@ fm_status fm_ingest_rows_packed(fm_ingest *h, const uint32_t *allele_bits, const
         // chunk = ~32 MB of bit words: small enough that the last chunk's compress pass is short
         const size_t per_row = std::max<size_t>(rw * 4 * (m->has_missing ? 2 : 1), 1);
         const size_t chunk = std::max<size_t>(32, ((size_t)32 << 20) / per_row);
-        for (size_t r0 = first_row; r0 < first_row + n_rows; r0 += chunk) {
-            const size_t r1 = std::min(first_row + n_rows, r0 + chunk);
+        for (size_t r0 = first_row, step = 0; r0 < first_row + n_rows; r0 += step) {
+            step = tapered_chunk(first_row + n_rows - r0, chunk);
+            const size_t r1 = r0 + step;
             if (rw) {
                 h2d(m->d_abits + r0 * rw, allele_bits + (r0 - first_row) * rw, (r1 - r0) * rw * 4, h->copy_s);
                 if (m->has_missing)
@@ -3024,6 +3027,14 @@ static void expand_called_launch(fm_matrix *m, const uint64_t *d_start, const vo
     g_launches++;
 }
 
+// Chunk sizes of a chunked upload: full chunks, then halves of what is left down to a quarter chunk -- the kernels of the LAST chunk are the only work
+// that is not hidden under the DMA of a following one, so the last chunk is a quarter of the others.
+static size_t tapered_chunk(size_t rows_left, size_t chunk) {
+    if (chunk < 128 || rows_left > 2 * chunk) return std::min(rows_left, chunk);
+    if (rows_left <= chunk / 4) return rows_left;
+    return std::min(rows_left, std::min(chunk, std::max(chunk / 4, (rows_left + 1) / 2)));
+}
+
 static void packed_sparse_rows(fm_matrix *m, const RepackSet *set, const uint32_t *allele_bits, const uint64_t *row_start,
                                const void *missing_cols, int col_bytes, size_t first_row, size_t n_rows, cudaStream_t copy_s,
                                cudaStream_t comp_s, cudaEvent_t ev[2], fm_ingest *tracks_of = nullptr) {
@@ -3040,8 +3051,9 @@ static void packed_sparse_rows(fm_matrix *m, const RepackSet *set, const uint32_
     CK(cudaStreamSynchronize(stream()));  // fresh (or recycled) scratch is settled before other streams touch it
     const size_t chunk = std::max<size_t>(32, ((size_t)32 << 20) / (rw * 4));
     int b = 0;
-    for (size_t r0 = 0; r0 < n_rows; r0 += chunk, b ^= 1) {
-        const size_t r1 = std::min(n_rows, r0 + chunk);
+    for (size_t r0 = 0, step = 0; r0 < n_rows; r0 += step, b ^= 1) {
+        step = tapered_chunk(n_rows - r0, chunk);
+        const size_t r1 = r0 + step;
         if (row_start[r1] < row_start[r0] || row_start[r1] > total) fail(FM_ERR_INVALID_ARG, "row_start is not ascending");
         h2d(m->d_abits + (first_row + r0) * rw, allele_bits + r0 * rw, (r1 - r0) * rw * 4, copy_s);
         h2d(d_start.p + r0, row_start + r0, (r1 - r0 + 1) * 8, copy_s);
