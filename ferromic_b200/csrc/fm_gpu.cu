@@ -3049,7 +3049,8 @@ static void packed_sparse_rows(fm_matrix *m, const RepackSet *set, const uint32_
     DevBuf<uint64_t> d_start(n_rows + 1);
     DevBuf<uint8_t> d_cols(std::max<uint64_t>(total * col_bytes, 16));
     CK(cudaStreamSynchronize(stream()));  // fresh (or recycled) scratch is settled before other streams touch it
-    const size_t chunk = std::max<size_t>(32, ((size_t)32 << 20) / (rw * 4));
+    static const uint32_t chunk_mb = std::max(1u, env_u32("FM_PACKED_CHUNK_MB", 32));
+    const size_t chunk = std::max<size_t>(32, ((size_t)chunk_mb << 20) / (rw * 4));
     int b = 0;
     for (size_t r0 = 0, step = 0; r0 < n_rows; r0 += step, b ^= 1) {
         step = tapered_chunk(n_rows - r0, chunk);

@@ -212,6 +212,20 @@ impl PackedIngest {
         self.n_groups += 1;
         Ok(gi)
     }
+    /// Per-site pi / theta of declared groups, produced chunk by chunk while the rows upload (call between
+    /// `add_group` and the first `push_*`).  The output slices must stay alive and unmoved until `finish()`; page-locked
+    /// ones (cudaHostAlloc / cudaHostRegister) receive the values straight from the kernels.  Returns the number of sites.
+    pub fn request_tracks(&mut self, groups: &[usize], raw_counts: &[usize], region: (i64, i64), mask: &[(i64, i64)],
+                          pos_out: &mut [i64], pi_out: &mut [f64], theta_out: &mut [f64], capacity: usize)
+                          -> Result<usize, VcfError> {
+        assert!(pi_out.len() >= groups.len() * capacity && theta_out.len() >= groups.len() * capacity);
+        let mut n = 0usize;
+        check(unsafe { fm_ingest_request_tracks(self.h, groups.as_ptr(), raw_counts.as_ptr(), groups.len(), region.0,
+                                                region.1, mask.as_ptr() as *const i64, mask.len(), ptr::null(), 0,
+                                                pos_out.as_mut_ptr(), pi_out.as_mut_ptr(), theta_out.as_mut_ptr(),
+                                                capacity, &mut n) })?;
+        Ok(n)
+    }
     pub fn push_sparse(&mut self, first_row: usize, n_rows: usize, allele_bits: &[u32], row_start: &[u64],
                        missing_cols: &[u16]) -> Result<(), VcfError> {
         check(unsafe { fm_ingest_rows_packed_sparse(self.h, allele_bits.as_ptr(), row_start.as_ptr(),
