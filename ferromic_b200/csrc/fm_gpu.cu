@@ -444,6 +444,39 @@ struct SideStreams {
 };
 thread_local SideStreams t_side_streams;
 
+// Streams of the streaming ingests are recycled per device: creating and destroying a stream is a trip into the
+// kernel driver, which serialises across the processes of a multi-GPU job (fm_ingest_begin took 1.4-12 ms with four
+// ranks on one host against 0.6 ms alone).  A stream goes back to the pool idle (synchronised).
+struct StreamPool {
+    std::mutex mu;
+    std::vector<std::pair<int, cudaStream_t>> free_list;
+    cudaStream_t take(int dev) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            for (size_t i = 0; i < free_list.size(); ++i)
+                if (free_list[i].first == dev) {
+                    cudaStream_t st = free_list[i].second;
+                    free_list[i] = free_list.back();
+                    free_list.pop_back();
+                    return st;
+                }
+        }
+        cudaStream_t st = nullptr;
+        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        return st;
+    }
+    void give(int dev, cudaStream_t st) {
+        if (!st) return;
+        std::lock_guard<std::mutex> lk(mu);
+        if (free_list.size() < 16) {
+            free_list.emplace_back(dev, st);
+            return;
+        }
+        cudaStreamDestroy(st);
+    }
+};
+StreamPool g_stream_pool;
+
 struct Timer {
     cudaEvent_t a, b;
     int dev = 0;
@@ -2655,8 +2688,9 @@ static void ingest_destroy(fm_ingest *h, bool release_handles) {
     for (cudaEvent_t e : {h->t_copy0, h->t_copy1, h->t_comp0, h->t_comp1, h->pin_free[0], h->pin_free[1], h->pos_up})
         if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) g_pinned.give(h->pin[i]);  // the copy stream was synchronised above
-    if (h->copy_s) cudaStreamDestroy(h->copy_s);
-    if (h->comp_s) cudaStreamDestroy(h->comp_s);
+    const int pool_dev = h->m ? h->m->device : t_device;  // both streams were synchronised above
+    g_stream_pool.give(pool_dev, h->copy_s);
+    g_stream_pool.give(pool_dev, h->comp_s);
     if (release_handles) {
         for (fm_group *g : h->groups) fm_group_release(g);
         for (fm_partition *p : h->parts) fm_partition_release(p);
@@ -2673,8 +2707,13 @@ fm_status fm_ingest_begin(size_t V, size_t S, size_t ploidy, int has_missing, ui
         require_device();
         CK(cudaSetDevice(t_device));
         fm_ingest *h = new fm_ingest();
+        static const uint32_t trace = env_u32("FM_INGEST_TRACE", 0);
+        const auto tb0 = std::chrono::steady_clock::now();
+        auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb0).count(); };
+        double tb_pos = 0, tb_ev = 0, tb_st = 0;
         try {
             h->m = matrix_common(V, S, ploidy, max_allele, positions);
+            tb_pos = since();
             h->m->has_missing = has_missing != 0;
             h->m->in_band = has_missing == FM_MISSING_IN_BAND;
             if (h->m->in_band && max_allele > 127)
@@ -2695,9 +2734,14 @@ fm_status fm_ingest_begin(size_t V, size_t S, size_t ploidy, int has_missing, ui
             CK(cudaEventCreate(&h->t_copy1));
             CK(cudaEventCreate(&h->t_comp0));
             CK(cudaEventCreate(&h->t_comp1));
-            CK(cudaStreamCreateWithFlags(&h->copy_s, cudaStreamNonBlocking));
-            CK(cudaStreamCreateWithFlags(&h->comp_s, cudaStreamNonBlocking));
+            tb_ev = since();
+            h->copy_s = g_stream_pool.take(h->m->device);
+            h->comp_s = g_stream_pool.take(h->m->device);
+            tb_st = since();
             CK(cudaStreamSynchronize(stream()));  // staging buffers are now usable from any stream
+            if (trace)
+                fprintf(stderr, "[ingest begin] positions %.3f ms, alloc + events %.3f ms, streams %.3f ms, sync %.3f ms\n", tb_pos,
+                        tb_ev - tb_pos, tb_st - tb_ev, since() - tb_st);
         } catch (...) {
             ingest_destroy(h, true);
             throw;
