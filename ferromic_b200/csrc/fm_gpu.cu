@@ -1741,7 +1741,8 @@ static size_t repack_warp_smem(const fm_matrix *m, uint32_t *row_buf_out, uint32
     const size_t row_buf = m->packed ? 0 : ((m->stride + 15) & ~(size_t)15) + 32;
     const size_t bit_buf = (!m->packed && m->has_missing && !m->in_band) ? ((m->stride + 63) / 64 + 2) * 8 : 0;
     // full-row allele / called bit words + one group's two plane rows while they are assembled
-    const size_t cnt_buf = 2 * ((m->stride + 31) / 32 + 1) * 4 + 2 * ((m->stride + 127) / 128) * 4 * 4;
+    // (+ 4 padding words per assembled row: the compress fragments or a zero into the word after the last one)
+    const size_t cnt_buf = 2 * ((m->stride + 31) / 32 + 1) * 4 + 2 * (((m->stride + 127) / 128) * 4 + 4) * 4;
     if (row_buf_out) *row_buf_out = (uint32_t)row_buf;
     if (bit_buf_out) *bit_buf_out = (uint32_t)bit_buf;
     return (row_buf + bit_buf + cnt_buf + 15) & ~(size_t)15;

@@ -229,7 +229,7 @@ fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint
         uint32_t *arow = reinterpret_cast<uint32_t *>(rowb + row_buf_bytes + bit_buf_bytes);
         uint32_t *crow = arow + rw + 1;
         uint32_t *outb = crow + rw + 1;  // 2 x out_cap words: one group's plane rows while they are assembled
-        const uint32_t out_cap = (uint32_t)((stride + 127) >> 7) * 4u;
+        const uint32_t out_cap = (uint32_t)((stride + 127) >> 7) * 4u + 4u;  // + one padding word (16-byte granule) per row
         if (pk.a) {  // packed rows: the full-row bit words arrive ready-made
             const size_t r0 = (size_t)(v - v_base) * pk.rw;
             const uint32_t tail = (uint32_t)stride & 31u;
@@ -365,18 +365,17 @@ fm_k_repack_rows(const uint8_t *__restrict__ data, size_t data_bytes, const uint
                     const uint32_t cw = crow[p0.x];
                     const uint32_t xa = fm_compress32(arow[p0.x] & cw, p0, p1);
                     const uint32_t sh = p0.z & 31u, wi = p0.z >> 5;
-                    if (xa) {
-                        atomicOr(oa + wi, xa << sh);
-                        const uint32_t hi = sh ? xa >> (32u - sh) : 0u;
-                        if (hi) atomicOr(oa + wi + 1, hi);
-                    }
+                    // straight-line: the fragment's low part and the part that spills into the next word (zero when
+                    // sh == 0: the funnel shift yields the high word of (0 : x) << sh).  Nearly every fragment is
+                    // non-empty and spills, so the four tests this replaces only cost issue slots and reconvergence
+                    // barriers (ncu: 9 % BRA + 7 % BSSY / BSYNC of the kernel's instructions); or-ing a zero is free.
+                    // The word after the row's last one is padding (repack_warp_smem).
+                    atomicOr(oa + wi, xa << sh);
+                    atomicOr(oa + wi + 1, __funnelshift_l(xa, 0u, sh));
                     if (G.called) {
                         const uint32_t xc = fm_compress32(cw, p0, p1);
-                        if (xc) {
-                            atomicOr(oc + wi, xc << sh);
-                            const uint32_t hi = sh ? xc >> (32u - sh) : 0u;
-                            if (hi) atomicOr(oc + wi + 1, hi);
-                        }
+                        atomicOr(oc + wi, xc << sh);
+                        atomicOr(oc + wi + 1, __funnelshift_l(xc, 0u, sh));
                     }
                 }
                 __syncwarp();
