@@ -276,7 +276,8 @@ class _Matrix:
         """Streaming ingestion (fm_ingest_*): the u8 rows are uploaded in chunks and repacked into
         the declared groups' bitplanes while the next chunk is in flight; the u8 matrix is never
         resident.  partitions: (left, right, n_groups) triples; their handles land in
-        `self.partitions`.  calls > 1 pushes the rows in several fm_ingest_rows calls.
+        `self.partitions`.  calls > 1 pushes the rows in several fm_ingest_rows calls.  packed: False (u8 rows over
+        PCIe), True (bit rows packed by the caller with fm_pack_rows / _sparse) or "library" (fm_ingest_rows_pack).
         tracks: per-site pi / theta of declared groups computed while the rows arrive (fm_ingest_request_tracks):
         {"groups": [indices], "raw_n": [...], "region": (start, end), "mask": int64 [k, 2] or None,
         "filtered": int64 [m] or None, "pos": int64 [cap], "pi": f64 [n_groups, cap], "theta": f64 [n_groups, cap]}
@@ -334,6 +335,8 @@ class _Matrix:
                                                        gap_code=SPARSE_GAP_CODE)
                     check(L.fm_ingest_rows_packed_sparse(ih, _ptr(ab), _ptr(start), _ptr(cols), cols.itemsize, int(r0),
                                                          int(r1 - r0)))
+                elif packed == "library":  # u8 rows in, packed inside the call while the previous chunk uploads
+                    check(L.fm_ingest_rows_pack(ih, flat[r0:r1].ctypes.data, _ptr(bits), int(r0), int(r1 - r0), 0))
                 elif packed:  # fm_pack_rows on the host, 2 bits per genotype over PCIe (fm_ingest_rows_packed)
                     ab, cb = pack_rows(flat[r0:r1], 1 if bits is not None else 0, bits, first_row=int(r0),
                                        n_total_rows=self.V)

@@ -73,10 +73,12 @@ def test_packed_in_band_int8():
         assert np.array_equal(got["alt"], ref.alt) and np.array_equal(got["called"], ref.called)
 
 
+@pytest.mark.parametrize("packed", [True, "library"])
 @pytest.mark.parametrize("calls,missing", [(1, 0.1), (3, 0.1), (7, 0.0), (2, 0.3)])
-def test_packed_streaming_ingest(calls, missing):
-    """fm_ingest_rows_packed in several calls, groups and a W&C partition declared up front; afterwards the packed
-    rows are resident, so groups and partitions can still be created (Population.with_haplotypes, lib.rs:622)."""
+def test_packed_streaming_ingest(calls, missing, packed):
+    """fm_ingest_rows_packed (rows packed by the caller) / fm_ingest_rows_pack (u8 rows packed inside the call) in
+    several calls, groups and a W&C partition declared up front; afterwards the packed rows are resident, so groups
+    and partitions can still be created (Population.with_haplotypes, lib.rs:622)."""
     from ferromic_b200 import _lib
     from ferromic_b200.api import _Matrix
     g, pos, pops = make_cohort(1500, 45, n_pops=3, missing_rate=missing, seed=17 + calls)
@@ -87,7 +89,8 @@ def test_packed_streaming_ingest(calls, missing):
     for p, members in enumerate(pops):
         left[members] = p
     resident = _Matrix(alle, miss, pos, max_allele=1, ingest="u8")
-    streamed = _Matrix.ingest(alle, miss, pos, hap_lists, partitions=[(left, left, 3)], calls=calls, packed=True)
+    streamed = _Matrix.ingest(alle, miss, pos, hap_lists, partitions=[(left, left, 3)], calls=calls, packed=packed,
+                              always_bitmap=packed == "library")
     for haps in hap_lists:
         _same_summary(resident.group(haps).summary(True), streamed.group(haps).summary(True))
     late = [(0, 0), (1, 1), (44, 0)]

@@ -30,7 +30,7 @@ def _same(a, b):
 
 
 @pytest.mark.parametrize("pinned", [True, False])
-@pytest.mark.parametrize("mode", ["u8", "packed", "sparse"])
+@pytest.mark.parametrize("mode", ["u8", "packed", "sparse", "library"])
 @pytest.mark.parametrize("V,calls", [(5000, 1), (5000, 3), (70001, 4)])
 def test_streamed_tracks_equal_the_call_after_finish(V, calls, mode, pinned):
     import torch
@@ -58,8 +58,8 @@ def test_streamed_tracks_equal_the_call_after_finish(V, calls, mode, pinned):
         a_pos, a_pi, a_th = o_pos, o_pi, o_th
     req = {"groups": [0, 1, 2], "raw_n": raw_n, "region": region, "mask": mask, "filtered": filt, "pos": a_pos,
            "pi": a_pi, "theta": a_th, "capacity": cap}
-    m = _Matrix.ingest(alle, miss, pos, lists, calls=calls, always_bitmap=True, packed=mode != "u8",
-                       sparse=mode == "sparse", tracks=req)
+    m = _Matrix.ingest(alle, miss, pos, lists, calls=calls, always_bitmap=True,
+                       packed="library" if mode == "library" else mode != "u8", sparse=mode == "sparse", tracks=req)
     n_ref, r_pos, r_pi, r_th = _reference(L, _lib, m, lists, raw_n, region, mask, filt, cap)
     assert m.track_sites == n_ref == V - 11 - 37 + 1
     n = n_ref
