@@ -248,7 +248,10 @@ fm_status fm_watterson_theta(size_t seg_sites, size_t n, int64_t sequence_length
  * 0-based.  Outputs are caller-allocated with room for `capacity` sites; *n_out receives the
  * number of variants inside the region (in variant order).  raw_haplotype_count is
  * haplotypes_in_group.len() before de-duplication (the <2 guard at :4675 uses it).  pos_out may be
- * NULL when the caller already holds the positions (they are the input positions + 1). */
+ * NULL when the caller already holds the positions (they are the input positions + 1).
+ * Output arrays in page-locked host memory (cudaHostAlloc / cudaHostRegister, the whole row inside one
+ * allocation) are written by the kernels themselves over PCIe; pageable arrays are filled by copies
+ * from device buffers.  Same values either way. */
 fm_status fm_per_site_diversity(fm_group *g, size_t raw_haplotype_count, int64_t region_start,
                                 int64_t region_end, const int64_t *mask_iv_or_null, size_t n_mask,
                                 const int64_t *filtered_pos, size_t n_filtered, int64_t *pos_out,
