@@ -163,11 +163,18 @@ fm_k_comm_exchange(const CommParams P) {
         (void)fm_ld_acquire_sys(&mine->flags[tid * 16]);  // acquire: slot loads below are ordered after the flag
     }
     __syncthreads();
+    // the status also travels right behind the merged words, so that one copy fetches both
     if (timed_out) {
-        if (tid == 0) *P.status = 1;
+        if (tid == 0) {
+            *P.status = 1;
+            if (P.merged) P.merged[P.n_words] = 1ull;
+        }
         return;
     }
-    if (tid == 0) *P.status = 0;
+    if (tid == 0) {
+        *P.status = 0;
+        if (P.merged) P.merged[P.n_words] = 0ull;
+    }
     // ---- 4. gather / rank-ordered sum
     for (uint32_t i = tid; i < P.n_words; i += nt) {
         const bool is_d = fm_comm_is_double(P, i);

@@ -4260,13 +4260,12 @@ void comm_launch(fm_comm *c, const unsigned long long *d_local, uint32_t n_words
 void comm_report_timeout(fm_comm *c);
 // merged words [0, n_words) + the status word in ONE asynchronous copy into pinned memory, then one synchronise
 const unsigned long long *comm_fetch_merged(fm_comm *c, uint32_t n_words) {
-    // status sits at word kCommMaxValues: copy the leading words and the status word (two small async copies into
-    // pinned memory cost ~2 us each; a pageable destination would make each a blocking driver round trip)
-    if (n_words) CK(cudaMemcpyAsync(c->h_result, c->d_merged, (size_t)n_words * 8, cudaMemcpyDeviceToHost, stream()));
-    CK(cudaMemcpyAsync(c->h_result + fm::kCommMaxValues, c->d_merged + fm::kCommMaxValues, 8, cudaMemcpyDeviceToHost,
-                       stream()));
+    // the kernel leaves a copy of the status word right behind the merged words: ONE asynchronous copy into pinned
+    // memory and one synchronise (a pageable destination would make the copy a blocking driver round trip)
+    if (n_words >= fm::kCommMaxValues) fail(FM_ERR_INVALID_ARG, "too many values for one fetch");
+    CK(cudaMemcpyAsync(c->h_result, c->d_merged, ((size_t)n_words + 1) * 8, cudaMemcpyDeviceToHost, stream()));
     CK(cudaStreamSynchronize(stream()));
-    if ((uint32_t)c->h_result[fm::kCommMaxValues] != 0) comm_report_timeout(c);
+    if ((uint32_t)c->h_result[n_words] != 0) comm_report_timeout(c);
     return c->h_result;
 }
 void comm_report_timeout(fm_comm *c) {
